@@ -1,0 +1,736 @@
+/* md_oracle.c — plain-C CPU restatement of the reference hot path. TEST INFRASTRUCTURE ONLY (see md_oracle.h).
+ *
+ * Written from the reference's behaviour, scalar and in program order, so that every float operation that
+ * decides a bin / voxel index is performed with the same operands, in the same order and with the same
+ * rounding as the reference's strict (non -ffast-math) build:
+ *   - a*b+c written in the reference as separate mul and add stays separate (compile with -ffp-contract=off);
+ *   - explicit fmadd intrinsics in the reference are fmaf() here;
+ *   - double accumulators / double setup stay double.
+ * Paths cited below are relative to /root/reference/ext/mdlib/src.
+ */
+#include "md_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdbool.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define MAXV(a, b) ((a) > (b) ? (a) : (b))
+#define MINV(a, b) ((a) < (b) ? (a) : (b))
+#define CLAMPV(v, lo, hi) MINV(MAXV(v, lo), hi)
+
+/* ------------------------------------------------------------------------------------------------
+ * Unit cell matrices: md_unitcell_A_extract_double / md_unitcell_I_extract_double (md_unitcell.inl:129-175)
+ * A[col][row]; columns are the basis vectors.
+ */
+static void cell_A(double A[3][3], const mdo_unitcell_t* c) {
+    A[0][0] = c->x;  A[0][1] = 0;     A[0][2] = 0;
+    A[1][0] = c->xy; A[1][1] = c->y;  A[1][2] = 0;
+    A[2][0] = c->xz; A[2][1] = c->yz; A[2][2] = c->z;
+}
+static void cell_I(double I[3][3], const mdo_unitcell_t* c) {
+    if (!c->flags) { memset(I, 0, sizeof(double) * 9); return; }
+    const double i11 = c->x > 0.0 ? 1.0 / c->x : 0.0;
+    const double i22 = c->y > 0.0 ? 1.0 / c->y : 0.0;
+    const double i33 = c->z > 0.0 ? 1.0 / c->z : 0.0;
+    const double i12 = (c->x * c->y) > 0.0 ? -c->xy / (c->x * c->y) : 0.0;
+    const double i13 = (c->x * c->y * c->z) > 0.0 ? (c->xy * c->yz - c->xz * c->y) / (c->x * c->y * c->z) : 0.0;
+    const double i23 = (c->y * c->z) > 0.0 ? -c->yz / (c->y * c->z) : 0.0;
+    I[0][0] = i11; I[0][1] = 0.0; I[0][2] = 0.0;
+    I[1][0] = i12; I[1][1] = i22; I[1][2] = 0.0;
+    I[2][0] = i13; I[2][1] = i23; I[2][2] = i33;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Spatial acceleration structure: md_spatial_acc_init (core/md_spatial_acc.c:155-438)
+ */
+typedef struct acc_t {
+    size_t num_elems, num_cells;
+    float *ex, *ey, *ez; uint32_t* eidx; uint32_t* cell_off;
+    uint32_t cell_dim[3]; float inv_cell_ext[3];
+    float G00, G11, G22, H01, H02, H12;
+    float A[3][3], I[3][3], origin[3];
+    uint32_t flags;
+} acc_t;
+
+static void acc_free(acc_t* a) { free(a->ex); free(a->ey); free(a->ez); free(a->eidx); free(a->cell_off); memset(a, 0, sizeof(*a)); }
+
+/* coordinate stream: SoA x/y/z + optional index, or AoS xyz (md_coord_stream_t, core/md_spatial_acc.h:15-37) */
+typedef struct stream_t { const float *x, *y, *z; const int32_t* idx; const float* aos; size_t count; } stream_t;
+static inline void stream_load(const stream_t* s, size_t i, float r[3]) {
+    if (s->aos) { r[0] = s->aos[3 * i]; r[1] = s->aos[3 * i + 1]; r[2] = s->aos[3 * i + 2]; return; }
+    const size_t src = s->idx ? (size_t)s->idx[i] : i;
+    r[0] = s->x[src]; r[1] = s->y[src]; r[2] = s->z[src];
+}
+
+/* vec4_linear_combine_3(r - origin, I) (core/md_vec_math.h:1323): ((I0*a.x) + (I1*a.y)) + (I2*a.z), component-wise */
+static inline void cart_to_fract_f(float s[3], const float r[3], const float origin[3], const float I[3][3]) {
+    const float ax = r[0] - origin[0], ay = r[1] - origin[1], az = r[2] - origin[2];
+    for (int k = 0; k < 3; ++k) {
+        float v = I[0][k] * ax;
+        v = v + I[1][k] * ay;
+        v = v + I[2][k] * az;
+        s[k] = v;
+    }
+}
+
+static void acc_init(acc_t* acc, const stream_t* st, double in_cell_ext, const mdo_unitcell_t* cell, bool use_supplied_idx) {
+    memset(acc, 0, sizeof(*acc));
+    if (st->count == 0) return;                                   /* :174 */
+    if (in_cell_ext <= 0.0) in_cell_ext = 6.0;                    /* :179 */
+    const double CELL_EXT = MAXV(in_cell_ext, 3.0);               /* :187 */
+    double A[3][3] = { { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 } }, I[3][3] = { { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 } };
+    uint32_t flags = 0;
+    if (cell) { cell_A(A, cell); cell_I(I, cell); flags = cell->flags; }
+    float origin[3] = { 0, 0, 0 };
+
+    if ((flags & MDO_CELL_PBC_ALL) != MDO_CELL_PBC_ALL) {         /* :201-243 : AABB fit on non-periodic axes */
+        float mn[3] = { 0, 0, 0 }, mx[3] = { 0, 0, 0 };           /* NB: the box starts at the origin (vec4 {0}) */
+        for (size_t i = 0; i < st->count; ++i) {
+            float r[3]; stream_load(st, i, r);
+            for (int k = 0; k < 3; ++k) { mn[k] = MINV(mn[k], r[k]); mx[k] = MAXV(mx[k], r[k]); }
+        }
+        for (int k = 0; k < 3; ++k) {
+            float ext = mx[k] - mn[k];
+            ext = ceilf(ext / (float)CELL_EXT) * (float)CELL_EXT;
+            const float cen = (mn[k] + mx[k]) * 0.5f;
+            const float lo = cen - ext * 0.5f;
+            if ((flags & (MDO_CELL_PBC_X << k)) == 0) {
+                origin[k] = lo;
+                if (ext > 0.0f) { A[k][k] = ext; I[k][k] = 1.0 / ext; }
+            }
+        }
+    }
+    const double a[3] = { A[0][0], A[0][1], A[0][2] }, b[3] = { A[1][0], A[1][1], A[1][2] }, c[3] = { A[2][0], A[2][1], A[2][2] };
+    const double G00 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    const double G11 = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+    const double G22 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    const double G01 = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    const double G02 = a[0] * c[0] + a[1] * c[1] + a[2] * c[2];
+    const double G12 = b[0] * c[0] + b[1] * c[1] + b[2] * c[2];
+    double H01 = 0, H02 = 0, H12 = 0;
+    const double na = sqrt(G00), nb = sqrt(G11), nc = sqrt(G22);
+    float inv_cell_ext[3] = { (float)(na > 0.0 ? 1.0 / na : 0.0), (float)(nb > 0.0 ? 1.0 / nb : 0.0), (float)(nc > 0.0 ? 1.0 / nc : 0.0) };
+    if (flags & MDO_CELL_TRICLINIC) {                             /* :270-290 */
+        H01 = 2.0 * G01; H02 = 2.0 * G02; H12 = 2.0 * G12;
+        const double det = G00 * (G11 * G22 - G12 * G12) - G01 * (G01 * G22 - G12 * G02) + G02 * (G01 * G12 - G11 * G02);
+        if (det < DBL_EPSILON) return;
+        inv_cell_ext[0] = (float)sqrt((G11 * G22 - G12 * G12) / det);
+        inv_cell_ext[1] = (float)sqrt((G00 * G22 - G02 * G02) / det);
+        inv_cell_ext[2] = (float)sqrt((G00 * G11 - G01 * G01) / det);
+    }
+    uint32_t cd[3] = { (uint32_t)(na / CELL_EXT), (uint32_t)(nb / CELL_EXT), (uint32_t)(nc / CELL_EXT) };   /* :294-298 */
+    for (int k = 0; k < 3; ++k) cd[k] = CLAMPV(cd[k], 1u, 1024u);
+    const uint32_t c0 = cd[0], c01 = cd[0] * cd[1];
+    const size_t num_cells = (size_t)cd[0] * cd[1] * cd[2];
+
+    const size_t n = st->count;
+    uint32_t* local_idx = malloc(n * 4); uint32_t* cell_idx = malloc(n * 4);
+    float* sx = malloc(n * 4); float* sy = malloc(n * 4); float* sz = malloc(n * 4); uint32_t* sidx = malloc(n * 4);
+    acc->ex = calloc(n + 16, 4); acc->ey = calloc(n + 16, 4); acc->ez = calloc(n + 16, 4); acc->eidx = calloc(n + 16, 4);
+    acc->cell_off = calloc(num_cells + 1, 4);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { acc->A[i][j] = (float)A[i][j]; acc->I[i][j] = (float)I[i][j]; }
+    for (int k = 0; k < 3; ++k) acc->origin[k] = origin[k];
+
+    for (size_t i = 0; i < n; ++i) {                              /* :341-371 */
+        float r[3], s[3]; stream_load(st, i, r);
+        cart_to_fract_f(s, r, origin, acc->I);
+        uint32_t cc[3];
+        for (int k = 0; k < 3; ++k) {
+            if (flags & (MDO_CELL_PBC_X << k)) s[k] = s[k] - floorf(s[k]);     /* vec4_fract, blended by pbc mask */
+            int ic = (int)floorf(s[k] * (float)cd[k]);                          /* cvtps of an integral float */
+            ic = CLAMPV(ic, 0, (int)cd[k] - 1);
+            cc[k] = (uint32_t)ic;
+        }
+        const size_t ci = (size_t)cc[2] * c01 + (size_t)cc[1] * c0 + cc[0];
+        local_idx[i] = acc->cell_off[ci]++;
+        cell_idx[i] = (uint32_t)ci;
+        sx[i] = s[0]; sy[i] = s[1]; sz[i] = s[2];
+        sidx[i] = (use_supplied_idx && st->idx) ? (uint32_t)st->idx[i] : (uint32_t)i;
+    }
+    uint32_t sum = 0;                                             /* :373-379 */
+    for (size_t ci = 0; ci <= num_cells; ++ci) { uint32_t len = acc->cell_off[ci]; acc->cell_off[ci] = sum; sum += len; }
+    for (size_t i = 0; i < n; ++i) {                              /* :383-390 : input order preserved inside a cell */
+        const uint32_t dst = acc->cell_off[cell_idx[i]] + local_idx[i];
+        acc->ex[dst] = sx[i]; acc->ey[dst] = sy[i]; acc->ez[dst] = sz[i]; acc->eidx[dst] = sidx[i];
+    }
+    free(local_idx); free(cell_idx); free(sx); free(sy); free(sz); free(sidx);
+    acc->num_elems = n; acc->num_cells = num_cells;
+    memcpy(acc->cell_dim, cd, sizeof(cd)); memcpy(acc->inv_cell_ext, inv_cell_ext, sizeof(inv_cell_ext));
+    acc->G00 = (float)G00; acc->G11 = (float)G11; acc->G22 = (float)G22;
+    acc->H01 = (float)H01; acc->H02 = (float)H02; acc->H12 = (float)H12;
+    acc->flags = flags;
+}
+
+/* calc_r2 core/md_spatial_acc.c:541-544 */
+static float calc_r2(double cutoff) { float r2 = (float)(cutoff * cutoff); return nextafterf(r2, r2 + 1.0f); }
+
+typedef void (*pair_cb_t)(uint32_t i, uint32_t j, float d2, void* user);
+
+/* for_each_external_pair_within_cutoff_ortho / _triclinic (core/md_spatial_acc.c:1649-1803, 1498-1647) */
+static void acc_ext_pairs(const acc_t* acc, const stream_t* ext, double cutoff, bool use_supplied_idx, pair_cb_t cb, void* user) {
+    if (acc->num_elems == 0) return;
+    int ncell[3];
+    for (int k = 0; k < 3; ++k) ncell[k] = (int)ceil(cutoff * (double)acc->inv_cell_ext[k] * acc->cell_dim[k]);
+    for (int k = 0; k < 3; ++k) if (2 * ncell[k] + 1 > 5) return;  /* "cutoff too large for cell size": logs an error, yields no pairs */
+    const float r2 = calc_r2(cutoff);
+    const bool tri = (acc->flags & MDO_CELL_TRICLINIC) != 0;
+    const int cd[3] = { (int)acc->cell_dim[0], (int)acc->cell_dim[1], (int)acc->cell_dim[2] };
+    const uint32_t c0 = acc->cell_dim[0], c01 = acc->cell_dim[0] * acc->cell_dim[1];
+
+    for (size_t ei = 0; ei < ext->count; ++ei) {
+        float r[3], f[3]; stream_load(ext, ei, r);
+        cart_to_fract_f(f, r, acc->origin, acc->I);
+        int cv[3];
+        for (int k = 0; k < 3; ++k) {
+            if (!tri && (acc->flags & (MDO_CELL_PBC_X << k))) f[k] = f[k] - floorf(f[k]);   /* ortho only (:1718); the triclinic path does not wrap (:1565) */
+            cv[k] = (int)floorf(f[k] * (float)cd[k]);                                       /* NOT clamped */
+        }
+        const uint32_t idx_i = (use_supplied_idx && ext->idx) ? (uint32_t)ext->idx[ei] : (uint32_t)ei;
+        for (int dz = -ncell[2]; dz <= ncell[2]; ++dz)
+        for (int dy = -ncell[1]; dy <= ncell[1]; ++dy)
+        for (int dx = -ncell[0]; dx <= ncell[0]; ++dx) {
+            const int off[3] = { dx, dy, dz };
+            int nv[3]; float fs[3]; bool skip = false;
+            for (int k = 0; k < 3; ++k) {
+                nv[k] = cv[k] + off[k];
+                const bool up = nv[k] > cd[k] - 1, lo = nv[k] < 0;
+                if ((up || lo) && !tri && !(acc->flags & (MDO_CELL_PBC_X << k))) skip = true;   /* :1733 */
+                if (lo) nv[k] += cd[k];
+                if (up) nv[k] -= cd[k];
+                fs[k] = f[k] + (float)((lo ? 1 : 0) - (up ? 1 : 0));                              /* :1750-1755 */
+            }
+            if (skip) continue;
+            /* the reference wraps once only; an index still out of range would be an out-of-bounds read there */
+            if (nv[0] < 0 || nv[0] >= cd[0] || nv[1] < 0 || nv[1] >= cd[1] || nv[2] < 0 || nv[2] >= cd[2]) continue;
+            const size_t cj = (size_t)nv[2] * c01 + (size_t)nv[1] * c0 + (size_t)nv[0];
+            const uint32_t o = acc->cell_off[cj], len = acc->cell_off[cj + 1] - o;
+            for (uint32_t j = 0; j < len; ++j) {
+                const float ddx = fs[0] - acc->ex[o + j], ddy = fs[1] - acc->ey[o + j], ddz = fs[2] - acc->ez[o + j];
+                const float dx2 = ddx * ddx, dy2 = ddy * ddy, dz2 = ddz * ddz;
+                float d2 = fmaf(acc->G00, dx2, fmaf(acc->G11, dy2, acc->G22 * dz2));              /* :517-528 */
+                if (tri) {
+                    const float dxy = ddx * ddy, dxz = ddx * ddz, dyz = ddy * ddz;
+                    const float cross = fmaf(acc->H01, dxy, fmaf(acc->H02, dxz, acc->H12 * dyz));  /* :503-515 */
+                    d2 = d2 + cross;
+                }
+                if (d2 <= r2) cb(idx_i, acc->eidx[o + j], d2, user);
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * RDF: compute_rdf / rdf_cb / rdf_cb_excl_mask / rdf_increment_bin (md_script_functions.inl:5221-5338)
+ */
+typedef struct rdf_payload_t {
+    float min_cutoff, inv_cutoff_range; float* bins; int32_t num_bins; uint64_t total;
+    const uint32_t* excl_off; const int32_t* excl_idx;
+} rdf_payload_t;
+
+static void rdf_pair(uint32_t i, uint32_t j, float d2, void* user) {
+    rdf_payload_t* p = user;
+    const float min_r2 = p->min_cutoff * p->min_cutoff;
+    if (d2 < min_r2) return;
+    if (p->excl_off) {  /* md_bitfield_test_bit(&exclusion_masks[i], j) */
+        for (uint32_t k = p->excl_off[i]; k < p->excl_off[i + 1]; ++k) if ((uint32_t)p->excl_idx[k] == j) return;
+    }
+    const float d = sqrtf(d2);
+    int32_t b = (int32_t)(((d - p->min_cutoff) * p->inv_cutoff_range) * p->num_bins);
+    b = CLAMPV(b, 0, p->num_bins - 1);
+    p->bins[b] += 1.0f;
+    p->total += 1;
+}
+
+static double sphere_volume(double r) { return (4.0 / 3.0) * 3.1415926535897932 * (r * r * r); }
+
+uint64_t mdo_rdf_frame(const float* x, const float* y, const float* z,
+                       const int32_t* ref_idx, const float* ref_pos_aos, size_t n_ref,
+                       const int32_t* trg_idx, size_t n_trg,
+                       const mdo_unitcell_t* cell, float min_cutoff, float max_cutoff,
+                       const uint32_t* excl_off, const int32_t* excl_idx,
+                       float* bins, float* weights) {
+    const int num_bins = MDO_DIST_BINS;
+    const float inv_cutoff_range = 1.0f / (max_cutoff - min_cutoff);   /* before the clamp (:5264) */
+    min_cutoff = MAXV(min_cutoff, 1e-3f);                               /* :5269 */
+    memset(bins, 0, sizeof(float) * num_bins);
+    stream_t ref = { x, y, z, ref_idx, ref_pos_aos, n_ref };
+    stream_t trg = { x, y, z, trg_idx, NULL, n_trg };
+    acc_t acc; acc_init(&acc, &trg, max_cutoff, cell, true);
+    rdf_payload_t p = { min_cutoff, inv_cutoff_range, bins, num_bins, 0, excl_off, excl_idx };
+    /* with exclusion masks i must be the structure index: COM references carry no idx, so i = ei (:1721) */
+    acc_ext_pairs(&acc, &ref, max_cutoff, ref_pos_aos == NULL, rdf_pair, &p);
+    acc_free(&acc);
+    const double total_vol = sphere_volume(max_cutoff) - sphere_volume(min_cutoff);
+    const double ref_rho = (double)p.total / total_vol;
+    const double dr = (max_cutoff - min_cutoff) / (float)num_bins;     /* float expression widened (:5330) */
+    double prev = 0;
+    for (int64_t i = 0; i < num_bins; ++i) {
+        const double sv = sphere_volume(min_cutoff + (i + 0.5) * dr);
+        const double bv = sv - prev; prev = sv;
+        weights[i] = (float)(ref_rho * bv);
+    }
+    return p.total;
+}
+
+static void count_pair(uint32_t i, uint32_t j, float d2, void* user) { (void)i; (void)j; (void)d2; *(uint64_t*)user += 1; }
+uint64_t mdo_count_pairs(const float* x, const float* y, const float* z, const int32_t* ref_idx, size_t n_ref,
+                         const int32_t* trg_idx, size_t n_trg, const mdo_unitcell_t* cell, double cell_ext, double cutoff) {
+    stream_t ref = { x, y, z, ref_idx, NULL, n_ref }, trg = { x, y, z, trg_idx, NULL, n_trg };
+    acc_t acc; acc_init(&acc, &trg, cell_ext, cell, true);
+    uint64_t n = 0; acc_ext_pairs(&acc, &ref, cutoff, true, count_pair, &n);
+    acc_free(&acc); return n;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * 3x3 SVD: ext/svd3/svd3.c (McAdams et al. TR1690; CPU version by E. Jang), restated line for line in float.
+ */
+static inline float inv_sqrt(float v) { return 1.0f / sqrtf(v); }
+static inline void cond_swap(bool c, float* X, float* Y) { float Z = *X; *X = c ? *Y : *X; *Y = c ? Z : *Y; }
+static inline void cond_neg_swap(bool c, float* X, float* Y) { float Z = -*X; *X = c ? *Y : *X; *Y = c ? Z : *Y; }
+
+static void approx_givens(float a11, float a12, float a22, float* ch, float* sh) {
+    *ch = 2 * (a11 - a22);
+    *sh = a12;
+    /* gamma is a double literal in the reference: the comparison is carried out in double */
+    bool b = 5.828427124746190097 * *sh * *sh < *ch * *ch;
+    float w = inv_sqrt(*ch * *ch + *sh * *sh);
+    *ch = b ? w * *ch : (float)0.923879532511286756;
+    *sh = b ? w * *sh : (float)0.382683432365089771;
+}
+
+static void jacobi_conj(const int x, const int y, const int z, float S[3][3], float q[4]) {
+    float ch, sh; approx_givens(S[0][0], S[1][0], S[1][1], &ch, &sh);
+    float scale = ch * ch + sh * sh;
+    float a = (ch * ch - sh * sh) / scale;
+    float b = (2 * sh * ch) / scale;
+    float _S[3][3];
+    _S[0][0] = S[0][0]; _S[1][0] = S[1][0]; _S[1][1] = S[1][1]; _S[2][0] = S[2][0]; _S[2][1] = S[2][1]; _S[2][2] = S[2][2];
+    S[0][0] = a * (a * _S[0][0] + b * _S[1][0]) + b * (a * _S[1][0] + b * _S[1][1]);
+    S[1][0] = a * (-b * _S[0][0] + a * _S[1][0]) + b * (-b * _S[1][0] + a * _S[1][1]);
+    S[1][1] = -b * (-b * _S[0][0] + a * _S[1][0]) + a * (-b * _S[1][0] + a * _S[1][1]);
+    S[2][0] = a * _S[2][0] + b * _S[2][1];
+    S[2][1] = -b * _S[2][0] + a * _S[2][1];
+    S[2][2] = _S[2][2];
+    float tmp[3] = { q[0] * sh, q[1] * sh, q[2] * sh };
+    sh *= q[3];
+    q[0] *= ch; q[1] *= ch; q[2] *= ch; q[3] *= ch;
+    q[z] += sh; q[3] -= tmp[z]; q[x] += tmp[y]; q[y] -= tmp[x];
+    _S[0][0] = S[1][1]; _S[1][0] = S[2][1]; _S[1][1] = S[2][2]; _S[2][0] = S[1][0]; _S[2][1] = S[2][0]; _S[2][2] = S[0][0];
+    S[0][0] = _S[0][0]; S[1][0] = _S[1][0]; S[1][1] = _S[1][1]; S[2][0] = _S[2][0]; S[2][1] = _S[2][1]; S[2][2] = _S[2][2];
+}
+
+static inline float dist2(float a, float b, float c) { return a * a + b * b + c * c; }
+
+static void qr_givens(float a1, float a2, float* ch, float* sh) {
+    float epsilon = (float)1e-6;
+    float rho = sqrtf(a1 * a1 + a2 * a2);
+    *sh = rho > epsilon ? a2 : 0;
+    *ch = fabsf(a1) + fmaxf(rho, epsilon);
+    bool b = a1 < 0;
+    cond_swap(b, sh, ch);
+    float w = inv_sqrt(*ch * *ch + *sh * *sh);
+    *ch *= w; *sh *= w;
+}
+
+void mdo_svd3(const float A[3][3], float U[3][3], float S[3][3], float V[3][3]) {
+    float ATA[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) ATA[i][j] = A[0][i] * A[0][j] + A[1][i] * A[1][j] + A[2][i] * A[2][j];  /* multAtB */
+    float q[4] = { 0, 0, 0, 1 };
+    for (int i = 0; i < 4; ++i) { jacobi_conj(0, 1, 2, ATA, q); jacobi_conj(1, 2, 0, ATA, q); jacobi_conj(2, 0, 1, ATA, q); }
+    {   /* quatToMat3 */
+        float x = q[0], y = q[1], z = q[2], w = q[3];
+        float qxx = x * x, qyy = y * y, qzz = z * z, qxz = x * z, qxy = x * y, qyz = y * z, qwx = w * x, qwy = w * y, qwz = w * z;
+        V[0][0] = 1 - 2 * (qyy + qzz); V[0][1] = 2 * (qxy - qwz);     V[0][2] = 2 * (qxz + qwy);
+        V[1][0] = 2 * (qxy + qwz);     V[1][1] = 1 - 2 * (qxx + qzz); V[1][2] = 2 * (qyz - qwx);
+        V[2][0] = 2 * (qxz - qwy);     V[2][1] = 2 * (qyz + qwx);     V[2][2] = 1 - 2 * (qxx + qyy);
+    }
+    float B[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) B[i][j] = A[i][0] * V[0][j] + A[i][1] * V[1][j] + A[i][2] * V[2][j];   /* multAB */
+    {   /* sortSingularValues */
+        float rho1 = dist2(B[0][0], B[1][0], B[2][0]), rho2 = dist2(B[0][1], B[1][1], B[2][1]), rho3 = dist2(B[0][2], B[1][2], B[2][2]);
+        bool c = rho1 < rho2;
+        for (int r = 0; r < 3; ++r) { cond_neg_swap(c, &B[r][0], &B[r][1]); cond_neg_swap(c, &V[r][0], &V[r][1]); }
+        cond_swap(c, &rho1, &rho2);
+        c = rho1 < rho3;
+        for (int r = 0; r < 3; ++r) { cond_neg_swap(c, &B[r][0], &B[r][2]); cond_neg_swap(c, &V[r][0], &V[r][2]); }
+        cond_swap(c, &rho1, &rho3);
+        c = rho2 < rho3;
+        for (int r = 0; r < 3; ++r) { cond_neg_swap(c, &B[r][1], &B[r][2]); cond_neg_swap(c, &V[r][1], &V[r][2]); }
+    }
+    {   /* QRDecomposition(B, Q=U, R=S) */
+        float (*Q)[3] = U, (*R)[3] = S;
+        float ch1, sh1, ch2, sh2, ch3, sh3, a, b;
+        qr_givens(B[0][0], B[1][0], &ch1, &sh1);
+        a = 1 - 2 * sh1 * sh1; b = 2 * ch1 * sh1;
+        R[0][0] = a * B[0][0] + b * B[1][0];  R[0][1] = a * B[0][1] + b * B[1][1];  R[0][2] = a * B[0][2] + b * B[1][2];
+        R[1][0] = -b * B[0][0] + a * B[1][0]; R[1][1] = -b * B[0][1] + a * B[1][1]; R[1][2] = -b * B[0][2] + a * B[1][2];
+        R[2][0] = B[2][0]; R[2][1] = B[2][1]; R[2][2] = B[2][2];
+        qr_givens(R[0][0], R[2][0], &ch2, &sh2);
+        a = 1 - 2 * sh2 * sh2; b = 2 * ch2 * sh2;
+        B[0][0] = a * R[0][0] + b * R[2][0];  B[0][1] = a * R[0][1] + b * R[2][1];  B[0][2] = a * R[0][2] + b * R[2][2];
+        B[1][0] = R[1][0]; B[1][1] = R[1][1]; B[1][2] = R[1][2];
+        B[2][0] = -b * R[0][0] + a * R[2][0]; B[2][1] = -b * R[0][1] + a * R[2][1]; B[2][2] = -b * R[0][2] + a * R[2][2];
+        qr_givens(B[1][1], B[2][1], &ch3, &sh3);
+        a = 1 - 2 * sh3 * sh3; b = 2 * ch3 * sh3;
+        R[0][0] = B[0][0]; R[0][1] = B[0][1]; R[0][2] = B[0][2];
+        R[1][0] = a * B[1][0] + b * B[2][0];  R[1][1] = a * B[1][1] + b * B[2][1];  R[1][2] = a * B[1][2] + b * B[2][2];
+        R[2][0] = -b * B[1][0] + a * B[2][0]; R[2][1] = -b * B[1][1] + a * B[2][1]; R[2][2] = -b * B[1][2] + a * B[2][2];
+        float sh12 = sh1 * sh1, sh22 = sh2 * sh2, sh32 = sh3 * sh3;
+        Q[0][0] = (-1 + 2 * sh12) * (-1 + 2 * sh22);
+        Q[0][1] = 4 * ch2 * ch3 * (-1 + 2 * sh12) * sh2 * sh3 + 2 * ch1 * sh1 * (-1 + 2 * sh32);
+        Q[0][2] = 4 * ch1 * ch3 * sh1 * sh3 - 2 * ch2 * (-1 + 2 * sh12) * sh2 * (-1 + 2 * sh32);
+        Q[1][0] = 2 * ch1 * sh1 * (1 - 2 * sh22);
+        Q[1][1] = -8 * ch1 * ch2 * ch3 * sh1 * sh2 * sh3 + (-1 + 2 * sh12) * (-1 + 2 * sh32);
+        Q[1][2] = -2 * ch3 * sh3 + 4 * sh1 * (ch3 * sh1 * sh3 + ch1 * ch2 * sh2 * (-1 + 2 * sh32));
+        Q[2][0] = 2 * ch2 * sh2;
+        Q[2][1] = 2 * ch3 * (1 - 2 * sh22) * sh3;
+        Q[2][2] = (-1 + 2 * sh22) * (-1 + 2 * sh32);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Small matrix helpers with the reference's storage convention elem[col][row] (core/md_vec_math.h:107-121)
+ */
+typedef struct { float e[3][3]; } m3;
+typedef struct { float e[4][4]; } m4;
+
+static m3 m3_transpose(m3 M) { m3 T; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) T.e[i][j] = M.e[j][i]; return T; }
+static m3 m3_mul(m3 A, m3 B) {   /* core/md_vec_math.h:1631 */
+    m3 C;
+    for (int col = 0; col < 3; ++col) for (int row = 0; row < 3; ++row)
+        C.e[col][row] = A.e[0][row] * B.e[col][0] + A.e[1][row] * B.e[col][1] + A.e[2][row] * B.e[col][2];
+    return C;
+}
+static float m3_det(m3 M) {      /* :1687 */
+    return M.e[0][0] * (M.e[1][1] * M.e[2][2] - M.e[2][1] * M.e[1][2])
+         - M.e[1][0] * (M.e[0][1] * M.e[2][2] - M.e[2][1] * M.e[0][2])
+         + M.e[2][0] * (M.e[0][1] * M.e[1][2] - M.e[1][1] * M.e[0][2]);
+}
+static m4 m4_from_m3(m3 M) { m4 R; memset(&R, 0, sizeof(R)); for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R.e[i][j] = M.e[i][j]; R.e[3][3] = 1; return R; }
+static m4 m4_mul(m4 A, m4 B) {   /* linear_combine_4 (:1512): C.col[j] = ((B[j][0]*A0 + B[j][1]*A1) + B[j][2]*A2) + B[j][3]*A3 */
+    m4 C;
+    for (int j = 0; j < 4; ++j) for (int r = 0; r < 4; ++r) {
+        float v = B.e[j][0] * A.e[0][r];
+        v = v + B.e[j][1] * A.e[1][r];
+        v = v + B.e[j][2] * A.e[2][r];
+        v = v + B.e[j][3] * A.e[3][r];
+        C.e[j][r] = v;
+    }
+    return C;
+}
+static void m4_mul_v(float out[4], const m4* M, const float v[4]) {
+    for (int r = 0; r < 4; ++r) {
+        float t = v[0] * M->e[0][r];
+        t = t + v[1] * M->e[1][r];
+        t = t + v[2] * M->e[2][r];
+        t = t + v[3] * M->e[3][r];
+        out[r] = t;
+    }
+}
+
+typedef struct { m3 U, V; float s[3]; } svd_t;
+static svd_t m3_svd(m3 M) {      /* core/md_vec_math.c:7-20 */
+    m3 Mt = m3_transpose(M), U, S, V;
+    mdo_svd3((const float(*)[3])Mt.e, U.e, S.e, V.e);
+    svd_t r; r.U = m3_transpose(U); r.V = m3_transpose(V); r.s[0] = S.e[0][0]; r.s[1] = S.e[1][1]; r.s[2] = S.e[2][2];
+    return r;
+}
+static m3 m3_eigen_vectors(m3 M) {   /* mat3_eigen core/md_vec_math.c:22-42 */
+    svd_t s = m3_svd(M);
+    const float mx = MAXV(s.s[0], MAXV(s.s[1], s.s[2]));
+    const float ev[3] = { s.s[0] / mx, s.s[1] / mx, s.s[2] / mx };
+    int l[3] = { 0, 1, 2 }, t;
+    if (ev[l[0]] < ev[l[1]]) { t = l[0]; l[0] = l[1]; l[1] = t; }
+    if (ev[l[1]] < ev[l[2]]) { t = l[1]; l[1] = l[2]; l[2] = t; }
+    if (ev[l[0]] < ev[l[1]]) { t = l[0]; l[0] = l[1]; l[1] = t; }
+    m3 R; for (int k = 0; k < 3; ++k) for (int r = 0; r < 3; ++r) R.e[k][r] = s.U.e[l[k]][r];
+    return R;
+}
+static m3 m3_extract_rotation(m3 M) {   /* core/md_vec_math.c:292-300 */
+    svd_t s = m3_svd(M);
+    m3 Ut = m3_transpose(s.U);
+    float d = m3_det(m3_mul(s.V, Ut));
+    m3 D; memset(&D, 0, sizeof(D)); D.e[0][0] = 1; D.e[1][1] = 1; D.e[2][2] = (float)((d > 0.0f) - (d < 0.0f));
+    return m3_mul(m3_mul(s.V, D), Ut);
+}
+
+/* vec4_deperiodize_ortho core/md_vec_math.h:1242-1253 (round = nearest-even, SSE4.1 roundps) */
+static inline float deperiodize1(float x, float r, float ext) {
+    if (ext == 0.0f) return x;
+    const float inv = 1.0f / ext;
+    float dx = (x - r) * inv;
+    const float dxp = dx - rintf(dx);
+    return r + dxp * ext;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * SDF: _sdf (md_script_functions.inl:5699-5856)
+ */
+typedef float v4[4];
+
+/* unwrap_topology_vec4 with indices == NULL (md_util.c:8738-8819): NB the BFS runs over the bonds of GLOBAL atoms
+ * 0..count-1 (seed = local index used as a global atom index) — replicated as is. Ortho only. */
+static void unwrap_vec4(v4* xyzw, size_t count, const uint32_t* conn_off, const int32_t* conn_idx, size_t conn_off_count, const mdo_unitcell_t* cell) {
+    if (count == 0 || !conn_off || conn_off_count == 0) return;
+    if (!(cell->flags & MDO_CELL_ORTHO)) return;   /* triclinic: deperiodize_triclinic, not restated yet */
+    const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
+    const size_t atom_count = conn_off_count - 1;
+    unsigned char* visited = calloc(atom_count + 1, 1);
+    int* queue = malloc(sizeof(int) * (count + 1));
+    for (size_t i = 0; i < count; ++i) {
+        const int seed = (int)i;
+        if ((size_t)seed >= atom_count || visited[seed]) continue;
+        visited[seed] = 1;
+        size_t qh = 0, qt = 0; queue[qt++] = seed;
+        while (qh < qt) {
+            const int cur = queue[qh++];
+            for (uint32_t k = conn_off[cur]; k < conn_off[cur + 1]; ++k) {
+                const int next = conn_idx[k];
+                if ((size_t)next >= count) continue;
+                if (visited[next]) continue;
+                for (int a = 0; a < 3; ++a) xyzw[next][a] = deperiodize1(xyzw[next][a], xyzw[cur][a], ext[a]);
+                visited[next] = 1; queue[qt++] = next;
+            }
+        }
+    }
+    free(visited); free(queue);
+}
+
+/* com_vec4 md_util.c:8048-8061 (the unit_cell argument is 0 at both call sites in _sdf) */
+static void com_v4(float com[3], const v4* p, size_t n) {
+    float acc[4] = { 0, 0, 0, 0 };
+    for (size_t i = 0; i < n; ++i) {
+        const float w = p[i][3];
+        acc[0] = acc[0] + p[i][0] * w; acc[1] = acc[1] + p[i][1] * w; acc[2] = acc[2] + p[i][2] * w; acc[3] = acc[3] + p[i][3] * 1.0f;
+    }
+    com[0] = acc[0] / acc[3]; com[1] = acc[1] / acc[3]; com[2] = acc[2] / acc[3];
+}
+
+/* mat3_covariance_matrix_vec4 core/md_vec_math.c:101-156 */
+static m3 covariance_v4(const v4* p, size_t n, const float com[3]) {
+    double A[3][3] = { { 0 } }; double ws = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        const float x = p[i][0] - com[0], y = p[i][1] - com[1], z = p[i][2] - com[2], w = p[i][3];
+        A[0][0] += w * x * x; A[0][1] += w * x * y; A[0][2] += w * x * z;
+        A[1][0] += w * y * x; A[1][1] += w * y * y; A[1][2] += w * y * z;
+        A[2][0] += w * z * x; A[2][1] += w * z * y; A[2][2] += w * z * z;
+        ws += w;
+    }
+    m3 R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] /= ws; R.e[i][j] = (float)A[i][j]; }
+    return R;
+}
+/* mat3_cross_covariance_matrix_vec4 core/md_vec_math.c:227-290 (in_idx == NULL) */
+static m3 cross_covariance_v4(const v4* p0, const v4* p1, size_t n, const float com0[3], const float com1[3]) {
+    double A[3][3] = { { 0 } }; double ws = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        const float px = p0[i][0] - com0[0], py = p0[i][1] - com0[1], pz = p0[i][2] - com0[2], pw = p0[i][3] - 0.0f;
+        const float qx = p1[i][0] - com1[0], qy = p1[i][1] - com1[1], qz = p1[i][2] - com1[2], qw = p1[i][3] - 0.0f;
+        const float w = (pw + qw) * 0.5f;
+        A[0][0] += w * px * qx; A[0][1] += w * px * qy; A[0][2] += w * px * qz;
+        A[1][0] += w * py * qx; A[1][1] += w * py * qy; A[1][2] += w * py * qz;
+        A[2][0] += w * pz * qx; A[2][1] += w * pz * qy; A[2][2] += w * pz * qz;
+        ws += w;
+    }
+    m3 R; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] /= ws; R.e[i][j] = (float)A[i][j]; }
+    return R;
+}
+
+static inline int wrap_coord(int v, int N) { v += (v < 0) ? N : 0; v -= (v >= N) ? N : 0; return v; }
+static inline int isign(int a) { return (a > 0) - (a < 0); }
+
+typedef void (*point_cb_t)(uint32_t idx, float px, float py, float pz, void* user);
+
+/* for_each_point_in_aabb_ortho + cell_range_from_aabb_center_radius (core/md_spatial_acc.c:1805-2007) */
+static void acc_points_in_aabb_ortho(const acc_t* acc, const double cen[3], const double rad[3], point_cb_t cb, void* user) {
+    if (acc->num_elems == 0) return;
+    const int pbc[3] = { (acc->flags & MDO_CELL_PBC_X) != 0, (acc->flags & MDO_CELL_PBC_Y) != 0, (acc->flags & MDO_CELL_PBC_Z) != 0 };
+    const int cd[3] = { (int)acc->cell_dim[0], (int)acc->cell_dim[1], (int)acc->cell_dim[2] };
+    double sc[3], cc[3];
+    {   /* cart_to_fract (double, float matrix entries widened) :556-565 */
+        const double px = cen[0] - acc->origin[0], py = cen[1] - acc->origin[1], pz = cen[2] - acc->origin[2];
+        sc[0] = acc->I[0][0] * px + acc->I[1][0] * py + acc->I[2][0] * pz;
+        sc[1] = acc->I[0][1] * px + acc->I[1][1] * py + acc->I[2][1] * pz;
+        sc[2] = acc->I[0][2] * px + acc->I[1][2] * py + acc->I[2][2] * pz;
+    }
+    for (int a = 0; a < 3; ++a) if (pbc[a]) sc[a] = sc[a] - floor(sc[a]);
+    cc[0] = acc->A[0][0] * sc[0] + acc->A[1][0] * sc[1] + acc->A[2][0] * sc[2] + acc->origin[0];
+    cc[1] = acc->A[0][1] * sc[0] + acc->A[1][1] * sc[1] + acc->A[2][1] * sc[2] + acc->origin[1];
+    cc[2] = acc->A[0][2] * sc[0] + acc->A[1][2] * sc[1] + acc->A[2][2] * sc[2] + acc->origin[2];
+    double fmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, fmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+    for (int iz = 0; iz < 2; ++iz) { const double pz = cc[2] + (iz ? +rad[2] : -rad[2]);
+    for (int iy = 0; iy < 2; ++iy) { const double py = cc[1] + (iy ? +rad[1] : -rad[1]);
+    for (int ix = 0; ix < 2; ++ix) { const double px = cc[0] + (ix ? +rad[0] : -rad[0]);
+        const double qx = px - acc->origin[0], qy = py - acc->origin[1], qz = pz - acc->origin[2];
+        double s[3];
+        s[0] = acc->I[0][0] * qx + acc->I[1][0] * qy + acc->I[2][0] * qz;
+        s[1] = acc->I[0][1] * qx + acc->I[1][1] * qy + acc->I[2][1] * qz;
+        s[2] = acc->I[0][2] * qx + acc->I[1][2] * qy + acc->I[2][2] * qz;
+        for (int a = 0; a < 3; ++a) { fmin[a] = MINV(fmin[a], s[a]); fmax[a] = MAXV(fmax[a], s[a]); }
+    } } }
+    double frad[3]; int cmin[3], cmax[3];
+    for (int a = 0; a < 3; ++a) {
+        frad[a] = 0.5 * (fmax[a] - fmin[a]);
+        int lo = (int)floor(fmin[a] * (double)cd[a]), hi = (int)ceil(fmax[a] * (double)cd[a]);
+        if (hi <= lo) hi = lo + 1;
+        if (!pbc[a]) { lo = CLAMPV(lo, 0, cd[a]); hi = CLAMPV(hi, 0, cd[a]); if (hi <= lo) hi = MINV(lo + 1, cd[a]); }
+        cmin[a] = lo; cmax[a] = hi;
+        frad[a] = MINV(frad[a], 0.5);                                      /* :1913-1915 */
+    }
+    const float lo3[3] = { (float)(sc[0] - frad[0]), (float)(sc[1] - frad[1]), (float)(sc[2] - frad[2]) };
+    const float hi3[3] = { (float)(sc[0] + frad[0]), (float)(sc[1] + frad[1]), (float)(sc[2] + frad[2]) };
+    const uint32_t c0 = acc->cell_dim[0], c01 = acc->cell_dim[0] * acc->cell_dim[1];
+    for (int icz = cmin[2]; icz < cmax[2]; ++icz) { const int cz = pbc[2] ? wrap_coord(icz, cd[2]) : icz; const float shz = (float)isign(icz - cz);
+    for (int icy = cmin[1]; icy < cmax[1]; ++icy) { const int cy = pbc[1] ? wrap_coord(icy, cd[1]) : icy; const float shy = (float)isign(icy - cy);
+    for (int icx = cmin[0]; icx < cmax[0]; ++icx) { const int cx = pbc[0] ? wrap_coord(icx, cd[0]) : icx; const float shx = (float)isign(icx - cx);
+        if (cx < 0 || cx >= cd[0] || cy < 0 || cy >= cd[1] || cz < 0 || cz >= cd[2]) continue;   /* single wrap only in the reference */
+        const size_t ci = (size_t)cz * c01 + (size_t)cy * c0 + (size_t)cx;
+        const uint32_t o = acc->cell_off[ci], len = acc->cell_off[ci + 1] - o;
+        for (uint32_t j = 0; j < len; ++j) {
+            const float vx = acc->ex[o + j] + shx, vy = acc->ey[o + j] + shy, vz = acc->ez[o + j] + shz;
+            if (vx >= lo3[0] && vy >= lo3[1] && vz >= lo3[2] && vx <= hi3[0] && vy <= hi3[1] && vz <= hi3[2]) {
+                /* fract_to_cart_ort_256: single fused multiply-add per axis (:583-592) */
+                cb(acc->eidx[o + j], fmaf(vx, acc->A[0][0], acc->origin[0]), fmaf(vy, acc->A[1][1], acc->origin[1]), fmaf(vz, acc->A[2][2], acc->origin[2]), user);
+            }
+        }
+    } } }
+}
+
+typedef struct sdf_payload_t { m4 M; float* vol; const int32_t* excl; size_t n_excl; uint64_t count; } sdf_payload_t;
+static void sdf_point(uint32_t idx, float px, float py, float pz, void* user) {   /* sdf_cb :5664-5697 */
+    sdf_payload_t* p = user;
+    for (size_t k = 0; k < p->n_excl; ++k) if ((uint32_t)p->excl[k] == idx) return;
+    const float v[4] = { px, py, pz, 1.0f }; float c[4];
+    m4_mul_v(c, &p->M, v);
+    const uint32_t ix = (uint32_t)CLAMPV((int32_t)c[0], 0, MDO_VOL_DIM - 1);
+    const uint32_t iy = (uint32_t)CLAMPV((int32_t)c[1], 0, MDO_VOL_DIM - 1);
+    const uint32_t iz = (uint32_t)CLAMPV((int32_t)c[2], 0, MDO_VOL_DIM - 1);
+    p->vol[(size_t)iz * (MDO_VOL_DIM * MDO_VOL_DIM) + iy * MDO_VOL_DIM + ix] += 1.0f;
+    p->count += 1;
+}
+
+uint64_t mdo_sdf_frame(const float* x, const float* y, const float* z,
+                       const float* init_x, const float* init_y, const float* init_z, const float* mass,
+                       const int32_t* struct_idx, size_t n_struct, size_t struct_size,
+                       const int32_t* trg_idx, size_t n_trg,
+                       const uint32_t* conn_off, const int32_t* conn_idx, size_t conn_off_count,
+                       const mdo_unitcell_t* cell, float cutoff, float* vol, float* out_matrices) {
+    if (n_struct == 0 || struct_size == 0 || n_trg == 0) return 0;
+    v4* r0 = malloc(sizeof(v4) * struct_size); v4* r1 = malloc(sizeof(v4) * struct_size);
+    float com0[3], com1[3];
+    for (size_t k = 0; k < struct_size; ++k) {   /* extract_xyzw_vec4 from the INITIAL frame, structure 0 (:5762) */
+        const int32_t a = struct_idx[k];
+        r0[k][0] = init_x[a]; r0[k][1] = init_y[a]; r0[k][2] = init_z[a]; r0[k][3] = mass ? mass[a] : 1.0f;
+    }
+    unwrap_vec4(r0, struct_size, conn_off, conn_idx, conn_off_count, cell);   /* with the CURRENT frame's cell (:5768) */
+    com_v4(com0, r0, struct_size);
+    stream_t trg = { x, y, z, trg_idx, NULL, n_trg };
+    acc_t acc; acc_init(&acc, &trg, (double)cutoff, cell, true);
+    m3 eig = m3_eigen_vectors(covariance_v4(r0, struct_size, com0));
+    m4 A = m4_from_m3(m3_transpose(eig));
+    m4 V;   /* compute_volume_matrix :5643-5655 */
+    {
+        const float voxel_ext = (2 * cutoff) / MDO_VOL_DIM;
+        const float s = 1.0f / voxel_ext;
+        m4 S; memset(&S, 0, sizeof(S)); S.e[0][0] = s; S.e[1][1] = s; S.e[2][2] = s; S.e[3][3] = 1;
+        const float t = (MDO_VOL_DIM / 2);
+        m4 T; memset(&T, 0, sizeof(T)); T.e[0][0] = T.e[1][1] = T.e[2][2] = T.e[3][3] = 1; T.e[3][0] = t; T.e[3][1] = t; T.e[3][2] = t;
+        V = m4_mul(T, S);
+    }
+    m4 VA = m4_mul(V, A);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n_struct; ++i) {
+        const int32_t* sidx = struct_idx + i * struct_size;
+        for (size_t k = 0; k < struct_size; ++k) { const int32_t a = sidx[k]; r1[k][0] = x[a]; r1[k][1] = y[a]; r1[k][2] = z[a]; r1[k][3] = mass ? mass[a] : 1.0f; }
+        unwrap_vec4(r1, struct_size, conn_off, conn_idx, conn_off_count, cell);
+        com_v4(com1, r1, struct_size);
+        m3 R = m3_extract_rotation(cross_covariance_v4(r0, r1, struct_size, com0, com1));
+        m4 Tm; memset(&Tm, 0, sizeof(Tm)); Tm.e[0][0] = Tm.e[1][1] = Tm.e[2][2] = Tm.e[3][3] = 1; Tm.e[3][0] = -com1[0]; Tm.e[3][1] = -com1[1]; Tm.e[3][2] = -com1[2];
+        m4 RT = m4_mul(m4_from_m3(R), Tm);
+        sdf_payload_t p; p.M = m4_mul(VA, RT); p.vol = vol; p.excl = sidx; p.n_excl = struct_size; p.count = 0;
+        if (out_matrices) memcpy(out_matrices + 16 * i, p.M.e, sizeof(float) * 16);
+        const double cen[3] = { com1[0], com1[1], com1[2] }, rad[3] = { cutoff, cutoff, cutoff };
+        if (vol) {
+            if (acc.flags & MDO_CELL_TRICLINIC) { /* for_each_point_in_aabb_triclinic: not restated yet */ }
+            else acc_points_in_aabb_ortho(&acc, cen, rad, sdf_point, &p);
+        }
+        total += p.count;
+    }
+    acc_free(&acc); free(r0); free(r1);
+    return total;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * density_x/_y/_z: _internal_density (md_script_functions.inl:4825-4947), axis in 0..2
+ */
+void mdo_density_frame(const float* x, const float* y, const float* z, const float* mass,
+                       const int32_t* idx, size_t n, const mdo_unitcell_t* init_cell, int axis, float* bins, float* weights) {
+    for (int i = 0; i < MDO_DIST_BINS; ++i) { weights[i] = 1.0f; bins[i] = 0.0f; }
+    float Af[3][3]; { double A[3][3]; cell_A(A, init_cell); for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Af[i][j] = (float)A[i][j]; }
+    /* rc = A * (0.5,0.5,0.5) (mat3_mul_vec3 :1623), re = diag(A) */
+    float rc[3], re[3];
+    for (int r = 0; r < 3; ++r) rc[r] = Af[0][r] * 0.5f + Af[1][r] * 0.5f + Af[2][r] * 0.5f;
+    for (int r = 0; r < 3; ++r) re[r] = Af[r][r];
+    float inv_ext[3], min_point[3];
+    for (int r = 0; r < 3; ++r) { inv_ext[r] = re[r] > 0.0f ? 1.0f / re[r] : 0.0f; min_point[r] = rc[r] - re[r] * 0.5f; }
+    const float* src[3] = { x, y, z };
+    for (size_t i = 0; i < n; ++i) {
+        const int32_t a = idx[i];
+        const float v = deperiodize1(src[axis][a], rc[axis], re[axis]);
+        const float fc = (v - min_point[axis]) * inv_ext[axis];
+        const int b = CLAMPV((int)(fc * MDO_DIST_BINS), 0, MDO_DIST_BINS - 1);
+        bins[b] += mass[a];
+    }
+    const double slice_vol = (re[0] * re[1] * re[2]) / MDO_DIST_BINS;   /* float product widened (:4930) */
+    const double factor = 1660.5390666 / slice_vol;
+    for (int i = 0; i < MDO_DIST_BINS; ++i) bins[i] = (float)(bins[i] * factor);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * distance / angle / dihedral for single-atom arguments
+ */
+float mdo_distance(const float* x, const float* y, const float* z, int32_t a, int32_t b, const mdo_unitcell_t* cell) {
+    const float pa[3] = { x[a], y[a], z[a] }; float pb[3] = { x[b], y[b], z[b] };
+    if (cell->flags & MDO_CELL_ORTHO) {   /* md_util_deperiodize_vec4 md_util.c:8971-8990 */
+        const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
+        for (int k = 0; k < 3; ++k) pb[k] = deperiodize1(pb[k], pa[k], ext[k]);
+    }
+    const float d[3] = { pa[0] - pb[0], pa[1] - pb[1], pa[2] - pb[2] };
+    return sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+}
+
+static void normalize3(float v[3]) {
+    const float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (len > 1.0e-5) { v[0] = v[0] / len; v[1] = v[1] / len; v[2] = v[2] / len; } else { v[0] = v[1] = v[2] = 0; }
+}
+
+float mdo_angle(const float* x, const float* y, const float* z, int32_t a, int32_t b, int32_t c) {
+    float v0[3] = { x[a] - x[b], y[a] - y[b], z[a] - z[b] }, v1[3] = { x[c] - x[b], y[c] - y[b], z[c] - z[b] };
+    normalize3(v0); normalize3(v1);
+    return acosf(v0[0] * v1[0] + v0[1] * v1[1] + v0[2] * v1[2]);
+}
+
+float mdo_dihedral(const float* x, const float* y, const float* z, int32_t a, int32_t b, int32_t c, int32_t d, const mdo_unitcell_t* cell) {
+    const int32_t id[4] = { a, b, c, d };
+    float dx[3][3];
+    for (int k = 0; k < 3; ++k) { dx[k][0] = x[id[k + 1]] - x[id[k]]; dx[k][1] = y[id[k + 1]] - y[id[k]]; dx[k][2] = z[id[k + 1]] - z[id[k]]; }
+    if (cell->flags & MDO_CELL_ORTHO) {   /* md_util_min_image_vec3 -> min_image_ortho md_util.c:8424-8436 */
+        const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
+        for (int k = 0; k < 3; ++k) for (int i = 0; i < 3; ++i) {
+            const float half = ext[i] * 0.5f;
+            if (ext[i] > 0.0f) { while (dx[k][i] > half) dx[k][i] -= ext[i]; while (dx[k][i] <= -half) dx[k][i] += ext[i]; }
+        }
+    }
+    /* vec3_dihedral_angle core/md_vec_math.h:558-567 */
+    const float* d1 = dx[0]; const float* d2 = dx[1]; const float* d3 = dx[2];
+    const float v1[3] = { d1[1] * d2[2] - d1[2] * d2[1], d1[2] * d2[0] - d1[0] * d2[2], d1[0] * d2[1] - d1[1] * d2[0] };
+    const float v2[3] = { d2[1] * d3[2] - d2[2] * d3[1], d2[2] * d3[0] - d2[0] * d3[2], d2[0] * d3[1] - d2[1] * d3[0] };
+    const float w[3] = { v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0] };
+    const float wl = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    const float s = v1[0] * v2[0] + v1[1] * v2[1] + v1[2] * v2[2];
+    float angle = atan2f(wl, s);
+    const float dot = d1[0] * v2[0] + d1[1] * v2[1] + d1[2] * v2[2];
+    if (dot < 0) angle = -angle;
+    return angle;
+}

@@ -1,0 +1,295 @@
+/* ref_harness.c — drives the UNMODIFIED reference (scanberg/mdlib) through its public API.
+ *
+ * TEST INFRASTRUCTURE ONLY. Nothing under viamd_b200/ may link, import or execute this.
+ * It exists so that (a) the plain-C oracle restatement (oracle/md_oracle.c) can be pinned
+ * against the real reference, (b) golden vectors under tests/golden/ can be generated, and
+ * (c) bench.py can time the reference's own CPU md_script_eval_frame_range on the host cores.
+ *
+ * It is linked against objects compiled by oracle/Makefile straight from the sources under
+ * /root/reference/ext/mdlib (never copied into this repository); outputs go to oracle/_ref/.
+ *
+ * Calls used (all public, mdlib/src/md_script.h:171-253, md_trajectory.h:49-67):
+ *   md_gro_system_init_from_file / md_pdb_system_init_from_file, md_util_system_postprocess,
+ *   md_script_ir_create / _compile_from_source, md_script_eval_create / _frame_range /
+ *   _property_data / _clear_data.
+ * The trajectory is an in-memory md_trajectory_i (no file I/O in the timed region), exactly
+ * the shape SURVEY.md §8(d) "CPU timing" prescribes; threads take contiguous frame slices the
+ * way VIAMD's enkiTS range task does (reference src/main.cpp:993-997, src/task_system.cpp:73-87).
+ *
+ * usage:
+ *   ref_harness sysinfo --sys F --out O
+ *   ref_harness eval    --sys F --traj SPEC --script S --out O [--perframe B:E] [--full B:E] [--threads T]
+ *   ref_harness time    --sys F --traj SPEC --script S --frames B:E --threads T [--repeat R]
+ * traj SPEC:  raw:<file> | synthwater:<n>:<seed>:<nframes> | sys (trajectory attached by the loader, e.g. multi-model PDB)
+ */
+#include <md_script.h>
+#include <md_system.h>
+#include <md_trajectory.h>
+#include <md_gro.h>
+#include <md_pdb.h>
+#include <md_util.h>
+#include <core/md_allocator.h>
+#include <core/md_arena_allocator.h>
+#include <core/md_str.h>
+#include <core/md_os.h>
+#include <core/md_log.h>
+#include <core/md_bitfield.h>
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <time.h>
+
+#include "../viamd_b200/csrc/synth.h"
+
+/* ---------------------------------------------------------------- in-memory trajectories */
+
+typedef enum { TRAJ_RAW, TRAJ_SYNTHWATER } traj_kind_t;
+
+typedef struct mem_traj_t {
+    traj_kind_t kind;
+    size_t num_frames, num_atoms;
+    double* frame_times;
+    /* raw */
+    const unsigned char* raw; size_t raw_frame_bytes;
+    /* synthwater */
+    mdsynth_water_t water; float *bx, *by, *bz;
+} mem_traj_t;
+
+typedef struct raw_frame_hdr_t { double cell[6]; uint32_t flags; uint32_t pad; } raw_frame_hdr_t;
+
+static bool mt_get_header(struct md_trajectory_o* inst, md_trajectory_header_t* h) {
+    mem_traj_t* t = (mem_traj_t*)inst;
+    memset(h, 0, sizeof(*h));
+    h->num_frames = t->num_frames; h->num_atoms = t->num_atoms; h->frame_times = t->frame_times;
+    return true;
+}
+
+static bool mt_load_frame(struct md_trajectory_reader_o* inst, int64_t idx, md_trajectory_frame_header_t* hdr, float* x, float* y, float* z) {
+    mem_traj_t* t = (mem_traj_t*)inst;
+    if (idx < 0 || (size_t)idx >= t->num_frames) return false;
+    md_unitcell_t cell = {0};
+    if (t->kind == TRAJ_RAW) {
+        const unsigned char* p = t->raw + (size_t)idx * t->raw_frame_bytes;
+        raw_frame_hdr_t fh; memcpy(&fh, p, sizeof(fh)); p += sizeof(fh);
+        cell.x = fh.cell[0]; cell.xy = fh.cell[1]; cell.xz = fh.cell[2];
+        cell.y = fh.cell[3]; cell.yz = fh.cell[4]; cell.z = fh.cell[5];
+        cell.flags = (md_unitcell_flags_t)fh.flags;
+        if (x) { memcpy(x, p, t->num_atoms * 4); memcpy(y, p + t->num_atoms * 4, t->num_atoms * 4); memcpy(z, p + t->num_atoms * 8, t->num_atoms * 4); }
+    } else {
+        cell = md_unitcell_from_extent((double)t->water.L, (double)t->water.L, (double)t->water.L);
+        if (x) mdsynth_water_frame(&t->water, (uint32_t)idx, t->bx, t->by, t->bz, x, y, z);
+    }
+    if (hdr) {
+        hdr->num_atoms = t->num_atoms; hdr->index = idx; hdr->timestamp = (double)idx; hdr->unitcell = cell;
+    }
+    return true;
+}
+
+static void mt_reader_free(struct md_trajectory_reader_i* r) { (void)r; }
+static bool mt_init_reader(md_trajectory_reader_i* r, struct md_trajectory_o* inst) {
+    r->inst = (struct md_trajectory_reader_o*)inst; r->free = mt_reader_free; r->load_frame = mt_load_frame;
+    return true;
+}
+static void mt_free(struct md_trajectory_i* t) { (void)t; }
+
+static void* read_file(const char* path, size_t* out_size) {
+    FILE* f = fopen(path, "rb"); if (!f) return NULL;
+    fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+    void* p = malloc((size_t)n); if (fread(p, 1, (size_t)n, f) != (size_t)n) { fclose(f); free(p); return NULL; }
+    fclose(f); *out_size = (size_t)n; return p;
+}
+
+static bool make_traj(md_trajectory_i* out, mem_traj_t* mt, const char* spec, md_system_t* sys) {
+    memset(mt, 0, sizeof(*mt));
+    if (strncmp(spec, "raw:", 4) == 0) {
+        size_t sz = 0; unsigned char* buf = read_file(spec + 4, &sz);
+        if (!buf || sz < 24 || memcmp(buf, "MDRAWTRJ", 8) != 0) { fprintf(stderr, "bad raw traj %s\n", spec); return false; }
+        uint64_t nf, na; memcpy(&nf, buf + 8, 8); memcpy(&na, buf + 16, 8);
+        mt->kind = TRAJ_RAW; mt->num_frames = nf; mt->num_atoms = na; mt->raw = buf + 24;
+        mt->raw_frame_bytes = sizeof(raw_frame_hdr_t) + na * 12;
+        if (sz < 24 + nf * mt->raw_frame_bytes) { fprintf(stderr, "raw traj truncated\n"); return false; }
+    } else if (strncmp(spec, "synthwater:", 11) == 0) {
+        unsigned n, seed, nf;
+        if (sscanf(spec + 11, "%u:%u:%u", &n, &seed, &nf) != 3) return false;
+        mt->kind = TRAJ_SYNTHWATER; mt->water = mdsynth_water_desc(n, seed);
+        mt->num_frames = nf; mt->num_atoms = mt->water.num_atoms;
+        mt->bx = malloc(mt->num_atoms * 4); mt->by = malloc(mt->num_atoms * 4); mt->bz = malloc(mt->num_atoms * 4);
+        mdsynth_water_base(&mt->water, mt->bx, mt->by, mt->bz, NULL, NULL, NULL);
+    } else if (strcmp(spec, "sys") == 0) {
+        if (!sys->trajectory) { fprintf(stderr, "system has no attached trajectory\n"); return false; }
+        *out = *sys->trajectory; return true;
+    } else { fprintf(stderr, "unknown traj spec %s\n", spec); return false; }
+    mt->frame_times = malloc(mt->num_frames * sizeof(double));
+    for (size_t i = 0; i < mt->num_frames; ++i) mt->frame_times[i] = (double)i;
+    out->inst = (struct md_trajectory_o*)mt; out->free = mt_free; out->get_header = mt_get_header; out->init_reader = mt_init_reader;
+    return true;
+}
+
+/* ---------------------------------------------------------------- helpers */
+
+static bool ends_with(const char* s, const char* suf) { size_t a = strlen(s), b = strlen(suf); return a >= b && strcmp(s + a - b, suf) == 0; }
+
+static bool load_system(md_system_t* sys, const char* path, md_allocator_i* alloc) {
+    memset(sys, 0, sizeof(*sys)); sys->alloc = alloc;
+    str_t p = { path, strlen(path) };
+    bool ok = false;
+    if (ends_with(path, ".gro")) ok = md_gro_system_init_from_file(sys, p);
+    else if (ends_with(path, ".pdb")) ok = md_pdb_system_init_from_file(sys, p, MD_PDB_OPTION_DISABLE_CACHE_FILE_WRITE);
+    if (!ok) { fprintf(stderr, "failed to load system %s\n", path); return false; }
+    md_util_system_postprocess(sys, MD_UTIL_POSTPROCESS_ALL);
+    return true;
+}
+
+static const char* arg_val(int argc, char** argv, const char* key, const char* def) {
+    for (int i = 2; i + 1 < argc; ++i) if (strcmp(argv[i], key) == 0) return argv[i + 1];
+    return def;
+}
+static bool parse_range(const char* s, long* b, long* e) { return s && sscanf(s, "%ld:%ld", b, e) == 2; }
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+static void wr(FILE* f, const void* p, size_t n) { if (fwrite(p, 1, n, f) != n) { perror("fwrite"); exit(3); } }
+static void wr_u32(FILE* f, uint32_t v) { wr(f, &v, 4); }
+static void wr_i64(FILE* f, int64_t v) { wr(f, &v, 8); }
+static void wr_u64(FILE* f, uint64_t v) { wr(f, &v, 8); }
+
+/* record: kind(0 perframe,1 full) prop beg end  min_value max_value min_range[2] max_range[2]  storage(0 dense,1 sparse) count payload */
+static void write_record(FILE* f, uint32_t kind, uint32_t prop, int64_t beg, int64_t end, const md_script_property_data_t* d, const float* vals, size_t n) {
+    wr_u32(f, kind); wr_u32(f, prop); wr_i64(f, beg); wr_i64(f, end);
+    wr(f, &d->min_value, 4); wr(f, &d->max_value, 4); wr(f, d->min_range, 8); wr(f, d->max_range, 8);
+    size_t nnz = 0; for (size_t i = 0; i < n; ++i) nnz += (vals[i] != 0.0f);
+    if (n > 65536 && nnz * 2 < n) {
+        wr_u32(f, 1); wr_u64(f, nnz);
+        for (size_t i = 0; i < n; ++i) if (vals[i] != 0.0f) { uint32_t ii = (uint32_t)i; wr(f, &ii, 4); wr(f, &vals[i], 4); }
+    } else { wr_u32(f, 0); wr_u64(f, n); wr(f, vals, n * 4); }
+}
+
+typedef struct { md_script_eval_t* eval; const md_script_ir_t* ir; const md_system_t* sys; const md_trajectory_i* traj; uint32_t beg, end; bool ok; } job_t;
+static void* job_main(void* p) { job_t* j = p; j->ok = md_script_eval_frame_range(j->eval, j->ir, j->sys, j->traj, j->beg, j->end); return NULL; }
+
+static bool run_threads(md_script_eval_t* eval, const md_script_ir_t* ir, const md_system_t* sys, const md_trajectory_i* traj, long beg, long end, int T) {
+    if (T <= 1) return md_script_eval_frame_range(eval, ir, sys, traj, (uint32_t)beg, (uint32_t)end);
+    pthread_t* th = calloc(T, sizeof(pthread_t)); job_t* jobs = calloc(T, sizeof(job_t));
+    long n = end - beg; bool ok = true;
+    for (int t = 0; t < T; ++t) {
+        jobs[t] = (job_t){ eval, ir, sys, traj, (uint32_t)(beg + n * t / T), (uint32_t)(beg + n * (t + 1) / T), false };
+        pthread_create(&th[t], NULL, job_main, &jobs[t]);
+    }
+    for (int t = 0; t < T; ++t) { pthread_join(th[t], NULL); ok = ok && jobs[t].ok; }
+    free(th); free(jobs); return ok;
+}
+
+/* ---------------------------------------------------------------- modes */
+
+static int mode_sysinfo(int argc, char** argv) {
+    md_allocator_i* alloc = md_vm_arena_create(GIGABYTES(8));
+    md_system_t sys; if (!load_system(&sys, arg_val(argc, argv, "--sys", ""), alloc)) return 2;
+    FILE* f = fopen(arg_val(argc, argv, "--out", "sysinfo.bin"), "wb"); if (!f) return 2;
+    const size_t n = sys.atom.count;
+    wr(f, "MDSYSINF", 8); wr_u64(f, n);
+    float* mass = malloc(n * 4); md_atom_extract_masses(mass, 0, n, &sys.atom); wr(f, mass, n * 4);
+    for (size_t i = 0; i < n; ++i) { uint32_t z = md_atom_atomic_number(&sys.atom, i); wr_u32(f, z); }
+    for (size_t i = 0; i < n; ++i) { str_t s = md_atom_name(&sys.atom, i); char b[8] = {0}; memcpy(b, s.ptr, s.len < 8 ? s.len : 7); wr(f, b, 8); }
+    /* component (residue) atom offsets */
+    wr_u64(f, sys.component.count);
+    wr(f, sys.component.atom_offset, (sys.component.count + 1) * 4);
+    /* bond connectivity CSR */
+    wr_u64(f, sys.bond.conn.offset_count); wr_u64(f, sys.bond.conn.count);
+    wr(f, sys.bond.conn.offset, sys.bond.conn.offset_count * 4);
+    wr(f, sys.bond.conn.atom_idx, sys.bond.conn.count * 4);
+    wr(f, &sys.unitcell, sizeof(md_unitcell_t));
+    wr(f, sys.atom.x, n * 4); wr(f, sys.atom.y, n * 4); wr(f, sys.atom.z, n * 4);
+    fclose(f);
+    printf("{\"atoms\": %zu, \"components\": %zu, \"bonds\": %zu}\n", n, sys.component.count, sys.bond.count);
+    return 0;
+}
+
+static int mode_eval(int argc, char** argv, bool timing) {
+    md_allocator_i* alloc = md_vm_arena_create(GIGABYTES(16));
+    md_system_t sys; if (!load_system(&sys, arg_val(argc, argv, "--sys", ""), alloc)) return 2;
+    md_trajectory_i traj = {0}; mem_traj_t mt;
+    if (!make_traj(&traj, &mt, arg_val(argc, argv, "--traj", "sys"), &sys)) return 2;
+    const size_t num_frames = md_trajectory_num_frames(&traj);
+    if (md_trajectory_num_atoms(&traj) != sys.atom.count) { fprintf(stderr, "atom count mismatch traj %zu sys %zu\n", md_trajectory_num_atoms(&traj), sys.atom.count); return 2; }
+
+    const char* src = arg_val(argc, argv, "--script", "");
+    md_script_ir_t* ir = md_script_ir_create(alloc);
+    if (!md_script_ir_compile_from_source(ir, (str_t){ src, strlen(src) }, &sys, &traj, NULL) || !md_script_ir_valid(ir)) {
+        fprintf(stderr, "script failed to compile: %s\n", src);
+        const md_log_token_t* e = md_script_ir_errors(ir);
+        for (size_t i = 0; i < md_script_ir_num_errors(ir); ++i) fprintf(stderr, "  error: %.*s\n", (int)e[i].text.len, e[i].text.ptr);
+        return 2;
+    }
+    const int T = atoi(arg_val(argc, argv, "--threads", "1"));
+    md_script_eval_t* eval = md_script_eval_create(num_frames, ir, alloc);
+    if (!eval) { fprintf(stderr, "no properties in script\n"); return 2; }
+    const size_t np = md_script_ir_property_count(ir);
+    const str_t* names = md_script_ir_property_names(ir);
+
+    if (timing) {
+        long b = 0, e = (long)num_frames; parse_range(arg_val(argc, argv, "--frames", NULL), &b, &e);
+        const int R = atoi(arg_val(argc, argv, "--repeat", "1"));
+        /* warm-up: one short pass so page faults / arena commits are out of the timed region */
+        long wb = b, we = b + (e - b < 2L * T ? e - b : 2L * T);
+        md_script_eval_clear_data(eval); run_threads(eval, ir, &sys, &traj, wb, we, T);
+        double best = 1e300, sum = 0;
+        for (int r = 0; r < R; ++r) {
+            md_script_eval_clear_data(eval);
+            double t0 = now_s(); bool ok = run_threads(eval, ir, &sys, &traj, b, e, T); double dt = now_s() - t0;
+            if (!ok) { fprintf(stderr, "evaluation failed\n"); return 2; }
+            if (dt < best) best = dt; sum += dt;
+        }
+        double chk = 0; for (size_t p = 0; p < np; ++p) { const md_script_property_data_t* d = md_script_eval_property_data(eval, names[p]); for (size_t i = 0; i < d->num_values; ++i) chk += d->values[i]; }
+        printf("{\"frames\": %ld, \"threads\": %d, \"repeat\": %d, \"best_s\": %.6f, \"mean_s\": %.6f, \"frames_per_s\": %.3f, \"checksum\": %.6f}\n",
+               e - b, T, R, best, sum / R, (double)(e - b) / best, chk);
+        return 0;
+    }
+
+    FILE* f = fopen(arg_val(argc, argv, "--out", "refout.bin"), "wb"); if (!f) return 2;
+    long pb = 0, pe = 0, fb = 0, fe = 0;
+    const bool perframe = parse_range(arg_val(argc, argv, "--perframe", NULL), &pb, &pe);
+    const bool full = parse_range(arg_val(argc, argv, "--full", NULL), &fb, &fe);
+    wr(f, "MDREFOUT", 8); wr_u32(f, 1); wr_u32(f, (uint32_t)np);
+    for (size_t p = 0; p < np; ++p) {
+        const md_script_property_data_t* d = md_script_eval_property_data(eval, names[p]);
+        char nm[64] = {0}; memcpy(nm, names[p].ptr, names[p].len < 63 ? names[p].len : 63); wr(f, nm, 64);
+        wr_u32(f, (uint32_t)md_script_ir_property_flags(ir, names[p])); wr(f, d->dim, 16); wr_u64(f, d->num_values);
+    }
+    if (perframe) {
+        /* raw per-frame outputs: a cleared eval + a single-frame range makes the cumulative
+         * moving average return the frame's own values (n = 0), md_script.c:5912-5921 */
+        for (long fr = pb; fr < pe; ++fr) {
+            md_script_eval_clear_data(eval);
+            if (!md_script_eval_frame_range(eval, ir, &sys, &traj, (uint32_t)fr, (uint32_t)fr + 1)) { fprintf(stderr, "frame %ld failed\n", fr); return 2; }
+            for (size_t p = 0; p < np; ++p) {
+                const md_script_property_data_t* d = md_script_eval_property_data(eval, names[p]);
+                const uint32_t fl = (uint32_t)md_script_ir_property_flags(ir, names[p]);
+                if (fl & MD_SCRIPT_PROPERTY_FLAG_TEMPORAL) {
+                    const size_t w = d->num_values / num_frames;
+                    write_record(f, 0, (uint32_t)p, fr, fr + 1, d, d->values + (size_t)fr * w, w);
+                } else write_record(f, 0, (uint32_t)p, fr, fr + 1, d, d->values, d->num_values);
+            }
+        }
+    }
+    if (full) {
+        md_script_eval_clear_data(eval);
+        if (!run_threads(eval, ir, &sys, &traj, fb, fe, T)) { fprintf(stderr, "full evaluation failed\n"); return 2; }
+        for (size_t p = 0; p < np; ++p) {
+            const md_script_property_data_t* d = md_script_eval_property_data(eval, names[p]);
+            write_record(f, 1, (uint32_t)p, fb, fe, d, d->values, d->num_values);
+        }
+    }
+    fclose(f);
+    printf("{\"properties\": %zu, \"frames\": %zu}\n", np, num_frames);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) { fprintf(stderr, "usage: ref_harness sysinfo|eval|time ...\n"); return 1; }
+    if (strcmp(argv[1], "sysinfo") == 0) return mode_sysinfo(argc, argv);
+    if (strcmp(argv[1], "eval") == 0) return mode_eval(argc, argv, false);
+    if (strcmp(argv[1], "time") == 0) return mode_eval(argc, argv, true);
+    fprintf(stderr, "unknown mode %s\n", argv[1]);
+    return 1;
+}

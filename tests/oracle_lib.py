@@ -1,0 +1,126 @@
+"""ctypes binding of the plain-C oracle (oracle/md_oracle.c). TEST INFRASTRUCTURE ONLY.
+
+Builds oracle/build/liboracle.so on first use (gcc, strict IEEE flags).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+ORTHO, TRICLINIC, PBC_X, PBC_Y, PBC_Z, PBC_ALL = 1, 2, 4, 8, 16, 28
+
+
+class UnitCell(C.Structure):
+    _fields_ = [("x", C.c_double), ("xy", C.c_double), ("xz", C.c_double), ("y", C.c_double), ("yz", C.c_double),
+                ("z", C.c_double), ("flags", C.c_uint32)]
+
+    @staticmethod
+    def ortho(x, y, z, flags=ORTHO | PBC_ALL):
+        return UnitCell(float(x), 0.0, 0.0, float(y), 0.0, float(z), flags)
+
+    @staticmethod
+    def from_params(x, xy, xz, y, yz, z, flags):
+        return UnitCell(float(x), float(xy), float(xz), float(y), float(yz), float(z), int(flags))
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ORACLE_DIR, "build", "liboracle.so")
+        src = [os.path.join(ORACLE_DIR, f) for f in ("md_oracle.c", "md_oracle.h")]
+        if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in src):
+            build()
+        _lib = C.CDLL(path)
+        _lib.mdo_rdf_frame.restype = C.c_uint64
+        _lib.mdo_sdf_frame.restype = C.c_uint64
+        _lib.mdo_count_pairs.restype = C.c_uint64
+        _lib.mdo_distance.restype = C.c_float
+        _lib.mdo_angle.restype = C.c_float
+        _lib.mdo_dihedral.restype = C.c_float
+    return _lib
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, np.float32)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, np.int32)
+
+
+def rdf_frame(x, y, z, ref_idx, trg_idx, cell: UnitCell, min_cutoff, max_cutoff, ref_pos=None, excl_off=None, excl_idx=None):
+    x, y, z = _f32(x), _f32(y), _f32(z)
+    ref_idx, trg_idx, ref_pos = _i32(ref_idx), _i32(trg_idx), _f32(ref_pos)
+    n_ref = len(ref_pos) // 3 if ref_pos is not None and ref_pos.ndim == 1 else (len(ref_pos) if ref_pos is not None else len(ref_idx))
+    eo = None if excl_off is None else np.ascontiguousarray(excl_off, np.uint32)
+    ei = _i32(excl_idx)
+    bins = np.zeros(1024, np.float32); w = np.zeros(1024, np.float32)
+    total = lib().mdo_rdf_frame(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float),
+                                _p(ref_idx, C.c_int32), _p(ref_pos, C.c_float), C.c_size_t(n_ref),
+                                _p(trg_idx, C.c_int32), C.c_size_t(len(trg_idx)), C.byref(cell),
+                                C.c_float(min_cutoff), C.c_float(max_cutoff), _p(eo, C.c_uint32), _p(ei, C.c_int32),
+                                _p(bins, C.c_float), _p(w, C.c_float))
+    return bins, w, int(total)
+
+
+def sdf_frame(x, y, z, init_xyz, mass, struct_idx, trg_idx, conn_off, conn_idx, cell: UnitCell, cutoff, vol=None, want_matrices=False):
+    x, y, z = _f32(x), _f32(y), _f32(z)
+    ix, iy, iz = (_f32(a) for a in init_xyz)
+    mass = _f32(mass)
+    struct_idx = _i32(struct_idx); n_struct, ssize = struct_idx.shape
+    trg_idx = _i32(trg_idx)
+    conn_off = np.ascontiguousarray(conn_off, np.uint32); conn_idx = _i32(conn_idx)
+    if vol is None:
+        vol = np.zeros(128 ** 3, np.float32)
+    mats = np.zeros((n_struct, 16), np.float32) if want_matrices else None
+    n = lib().mdo_sdf_frame(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(ix, C.c_float), _p(iy, C.c_float), _p(iz, C.c_float),
+                            _p(mass, C.c_float), _p(struct_idx, C.c_int32), C.c_size_t(n_struct), C.c_size_t(ssize),
+                            _p(trg_idx, C.c_int32), C.c_size_t(len(trg_idx)), _p(conn_off, C.c_uint32), _p(conn_idx, C.c_int32),
+                            C.c_size_t(len(conn_off)), C.byref(cell), C.c_float(cutoff), _p(vol, C.c_float), _p(mats, C.c_float))
+    return (vol, int(n), mats) if want_matrices else (vol, int(n))
+
+
+def density_frame(x, y, z, mass, idx, init_cell: UnitCell, axis):
+    x, y, z, mass, idx = _f32(x), _f32(y), _f32(z), _f32(mass), _i32(idx)
+    bins = np.zeros(1024, np.float32); w = np.zeros(1024, np.float32)
+    lib().mdo_density_frame(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(mass, C.c_float), _p(idx, C.c_int32),
+                            C.c_size_t(len(idx)), C.byref(init_cell), C.c_int(axis), _p(bins, C.c_float), _p(w, C.c_float))
+    return bins, w
+
+
+def distance(x, y, z, a, b, cell):
+    x, y, z = _f32(x), _f32(y), _f32(z)
+    return float(lib().mdo_distance(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), C.c_int32(a), C.c_int32(b), C.byref(cell)))
+
+
+def angle(x, y, z, a, b, c):
+    x, y, z = _f32(x), _f32(y), _f32(z)
+    return float(lib().mdo_angle(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), C.c_int32(a), C.c_int32(b), C.c_int32(c)))
+
+
+def dihedral(x, y, z, a, b, c, d, cell):
+    x, y, z = _f32(x), _f32(y), _f32(z)
+    return float(lib().mdo_dihedral(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), C.c_int32(a), C.c_int32(b), C.c_int32(c), C.c_int32(d), C.byref(cell)))
+
+
+def count_pairs(x, y, z, ref_idx, trg_idx, cell, cell_ext, cutoff):
+    x, y, z = _f32(x), _f32(y), _f32(z); ref_idx, trg_idx = _i32(ref_idx), _i32(trg_idx)
+    return int(lib().mdo_count_pairs(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(ref_idx, C.c_int32), C.c_size_t(len(ref_idx)),
+                                     _p(trg_idx, C.c_int32), C.c_size_t(len(trg_idx)), C.byref(cell), C.c_double(cell_ext), C.c_double(cutoff)))
