@@ -1,0 +1,223 @@
+/* mdgpu.h — C ABI of libmdgpu: B200-native per-frame trajectory analysis behind VIAMD/mdlib's md_script
+ * property API (rdf / sdf / density_x,y,z / distance / angle / dihedral evaluated over every frame).
+ *
+ * Plain C: pointers and sizes only, no CUDA / torch types. This is what the reference's per-frame evaluation
+ * (mdlib/src/md_script.c:5730-5973 eval_properties and the procedures it calls) is replaced by; INTEGRATION.md
+ * shows the lowering shim a maintainer adds inside md_script.c to drive it from a compiled md_script_ir_t.
+ *
+ * All paths cited are relative to the reference checkout (scanberg/viamd @ 9f7186f, ext/mdlib @ 77d1f08).
+ *
+ * Error convention (mirrors the reference's bool + MD_LOG_ERROR, core/md_log.h:7-9): functions return 0 on
+ * success and a negative mdgpu_status otherwise; mdgpu_last_error() returns the message of the calling thread's
+ * last failure. There is NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ * MDGPU_ERR_CUDA.
+ */
+#ifndef MDGPU_H
+#define MDGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDGPU_DIST_BINS 1024 /* MD_DIST_BINS, md_script_functions.inl:5  (ABI constant of the property layout) */
+#define MDGPU_VOL_DIM   128  /* MD_VOL_DIM,   md_script_functions.inl:9 */
+
+typedef enum mdgpu_status {
+    MDGPU_OK = 0,
+    MDGPU_ERR_INVALID_ARG = -1,
+    MDGPU_ERR_CUDA = -2,          /* CUDA runtime failure or no device: the product never falls back to the CPU */
+    MDGPU_ERR_UNSUPPORTED = -3,   /* operation outside the implemented hot-path scope */
+    MDGPU_ERR_CAPACITY = -4,      /* a frame needs more cells than the plan's cell capacity */
+    MDGPU_ERR_FRAME_SOURCE = -5,  /* load_frame failed (reference: "Failed to load frame during evaluation", md_script.c:5818) */
+    MDGPU_ERR_INTERRUPTED = -6,
+} mdgpu_status;
+
+/* Unit cell. Field order and flag values are those of md_unitcell_t / md_unitcell_flags_t (md_types.h:36-43,254-259),
+ * so a md_unitcell_t* can be passed as is. */
+enum { MDGPU_CELL_ORTHO = 1, MDGPU_CELL_TRICLINIC = 2, MDGPU_CELL_PBC_X = 4, MDGPU_CELL_PBC_Y = 8, MDGPU_CELL_PBC_Z = 16, MDGPU_CELL_PBC_ALL = 28 };
+typedef struct mdgpu_unitcell_t {
+    double x, xy, xz;
+    double y, yz;
+    double z;
+    uint32_t flags;
+} mdgpu_unitcell_t;
+
+/* Frame source: layout-compatible with md_trajectory_frame_header_t / md_trajectory_reader_i / md_trajectory_i
+ * (md_trajectory.h:27-32,49-67); a VIAMD md_trajectory_i* can be passed after a pointer cast. */
+typedef struct mdgpu_frame_header_t {
+    size_t  num_atoms;
+    int64_t index;
+    double  timestamp;
+    mdgpu_unitcell_t unitcell;
+} mdgpu_frame_header_t;
+
+struct mdgpu_trajectory_o;
+struct mdgpu_trajectory_reader_o;
+typedef struct mdgpu_trajectory_reader_i {
+    struct mdgpu_trajectory_reader_o* inst;
+    void (*free)(struct mdgpu_trajectory_reader_i* self);
+    bool (*load_frame)(struct mdgpu_trajectory_reader_o* inst, int64_t idx, mdgpu_frame_header_t* header, float* x, float* y, float* z);
+} mdgpu_trajectory_reader_i;
+
+typedef struct mdgpu_trajectory_header_t {   /* md_trajectory_header_t, md_trajectory.h:20-25; md_unit_t = {u64 base; double mult} core/md_unit.h:48-51 */
+    size_t num_frames;
+    size_t num_atoms;
+    struct { uint64_t base_bits; double mult; } time_unit;
+    const double* frame_times;
+} mdgpu_trajectory_header_t;
+
+typedef struct mdgpu_trajectory_i {
+    struct mdgpu_trajectory_o* inst;
+    void (*free)(struct mdgpu_trajectory_i* self);
+    bool (*get_header)(struct mdgpu_trajectory_o* inst, mdgpu_trajectory_header_t* header);
+    bool (*init_reader)(mdgpu_trajectory_reader_i* reader, struct mdgpu_trajectory_o* inst);
+} mdgpu_trajectory_i;
+
+/* Static description of the system: what the procedures read from md_system_t besides coordinates
+ * (atom masses via md_atom_extract_masses md_script.c:5764; covalent-bond connectivity md_bond_conn_data_t
+ * md_system.h:103-111, needed by sdf()'s unwrap md_util.c:8738). */
+typedef struct mdgpu_system_desc_t {
+    size_t num_atoms;
+    const float* atom_mass;            /* [num_atoms] */
+    const uint32_t* bond_conn_offset;  /* [bond_conn_offset_count] (= num_atoms + 1), may be NULL if no sdf property */
+    const int32_t* bond_conn_atom_idx;
+    size_t bond_conn_offset_count;
+} mdgpu_system_desc_t;
+
+/* Property operations (the procedures[] entries on the hot path, md_script_functions.inl:574-730). */
+typedef enum mdgpu_op {
+    MDGPU_OP_RDF = 1,        /* rdf(ref, trg, cutoff | min:max)     -> distribution  [1,2,1024]          :5263-5437 */
+    MDGPU_OP_SDF = 2,        /* sdf(structures[], trg, cutoff)       -> volume        [1,128,128,128]     :5699-5856 */
+    MDGPU_OP_DENSITY_X = 3,  /* density_x/_y/_z(atoms)               -> distribution                      :4825-5015 */
+    MDGPU_OP_DENSITY_Y = 4,
+    MDGPU_OP_DENSITY_Z = 5,
+    MDGPU_OP_DISTANCE = 6,   /* distance(a, b)   single atoms        -> temporal [F,1]                    :3851-3890 */
+    MDGPU_OP_ANGLE = 7,      /* angle(a, b, c)                       -> temporal                          :4099-4114 */
+    MDGPU_OP_DIHEDRAL = 8,   /* dihedral(a, b, c, d)                 -> temporal                          :4171-4196 */
+} mdgpu_op;
+
+/* One property = one `ident = proc(args);` statement whose selections were evaluated statically at compile time
+ * (md_script.c:5492-5524) into ascending atom index lists (md_bitfield_iter_extract_indices order).
+ *   RDF      : idx[0] = reference atoms, idx[1] = target atoms, cutoff_min/max.
+ *              If num_structures > 0 the references are the centres of mass of `num_structures` equally sized atom
+ *              groups stored back to back in idx[0] and a structure's own atoms are excluded (rdf_cb_excl_mask :5243).
+ *   SDF      : idx[0] = num_structures * structure_size atoms (equivalent structures), idx[1] = target atoms, cutoff_max.
+ *   DENSITY_*: idx[0] = atoms.
+ *   DISTANCE/ANGLE/DIHEDRAL: idx[k][0] = atom k (0-based). */
+typedef struct mdgpu_property_desc_t {
+    const char* name;
+    uint32_t op;
+    const int32_t* idx[4];
+    size_t idx_count[4];
+    size_t num_structures;
+    size_t structure_size;
+    float cutoff_min;
+    float cutoff_max;
+} mdgpu_property_desc_t;
+
+/* Result view: the fields of md_script_property_data_t (md_script.h:73-92) that the evaluation fills. */
+typedef struct mdgpu_property_data_t {
+    int32_t dim[4];
+    size_t  num_values;
+    float*  values;       /* owned by the plan, stable for its lifetime (as in the reference, md_script.c:6497-6504) */
+    float*  weights;      /* distributions only: values + dim[2] */
+    float   min_value, max_value;
+    float   min_range[2], max_range[2];
+    uint64_t frames_accumulated;
+} mdgpu_property_data_t;
+
+typedef struct mdgpu_plan mdgpu_plan;
+
+typedef struct mdgpu_plan_options_t {
+    int      device;              /* CUDA device ordinal */
+    uint32_t batch_frames;        /* frames per launch batch; 0 = default (one per SM) */
+    uint32_t num_streams;         /* CUDA streams the frame loop is dispatched onto; 0 = default (2) */
+    uint32_t keep_frame_results;  /* 1: retain raw per-frame integer bins of distributions (parity tests) */
+    uint32_t cell_capacity;       /* cells per frame the cell lists are sized for; 0 = 2x the initial frame's grid */
+    uint32_t rdf_variant;         /* kernel variant selector for experiments; 0 = default */
+    uint32_t reserved[3];
+} mdgpu_plan_options_t;
+
+const char* mdgpu_last_error(void);
+int mdgpu_device_count(void);
+
+/* Plan lifetime. num_frames is the trajectory length (rows of temporal properties; md_script_eval_create :6506). */
+mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_property_desc_t* props, size_t num_props,
+                              size_t num_frames, const mdgpu_plan_options_t* opts);
+void mdgpu_plan_destroy(mdgpu_plan* plan);
+
+/* Frame 0 of the trajectory ("initial configuration", md_script.c:5808): reference structure of sdf(), reference cell of density_*(). */
+int mdgpu_plan_set_initial_frame(mdgpu_plan* plan, const float* x, const float* y, const float* z, const mdgpu_unitcell_t* cell);
+
+/* md_script_eval_clear_data (md_script.c:6563): zero accumulators, frame mask, interrupt flag. */
+int mdgpu_plan_clear(mdgpu_plan* plan);
+
+/* The frame loop. Frames [frame_beg, frame_beg+count) are evaluated and accumulated.
+ *  _device: coordinates already in HBM; frame i has x at d_xyz + i*frame_stride, y at + axis_stride, z at + 2*axis_stride (floats).
+ *  _host  : same layout in host memory (pinned or pageable); copied host->device batch by batch inside the call.
+ *  _trajectory: pulls frames through the md_trajectory_i-compatible interface with `loader_threads` readers
+ *               (md_script_eval_frame_range semantics, md_script.c:6573-6612). */
+int mdgpu_eval_device_frames(mdgpu_plan* plan, const float* d_xyz, size_t frame_stride, size_t axis_stride,
+                             const mdgpu_unitcell_t* cells, size_t cell_stride_bytes, uint32_t frame_beg, uint32_t count);
+int mdgpu_eval_host_frames(mdgpu_plan* plan, const float* h_xyz, size_t frame_stride, size_t axis_stride,
+                           const mdgpu_unitcell_t* cells, size_t cell_stride_bytes, uint32_t frame_beg, uint32_t count);
+int mdgpu_eval_trajectory(mdgpu_plan* plan, const mdgpu_trajectory_i* traj, uint32_t frame_beg, uint32_t frame_end, uint32_t loader_threads);
+
+/* Wait for all enqueued batches and fold device accumulators into the host-visible property data. */
+int mdgpu_plan_sync(mdgpu_plan* plan);
+void mdgpu_plan_interrupt(mdgpu_plan* plan);   /* md_script_eval_interrupt :6663 */
+
+size_t mdgpu_plan_property_count(const mdgpu_plan* plan);
+int mdgpu_plan_property_index(const mdgpu_plan* plan, const char* name);
+int mdgpu_plan_property_data(mdgpu_plan* plan, size_t prop, mdgpu_property_data_t* out);   /* implies mdgpu_plan_sync */
+
+/* Exact integer results (what parity is asserted on).
+ *  _counts: accumulated counts over all evaluated frames: RDF 1024 x u64 bins; SDF 128^3 x u64 voxels (widened from u32);
+ *           DENSITY 1024 x u64 fixed-point mass sums (unit 2^-24 Da).
+ *  _frame_counts: raw bins of one frame (needs keep_frame_results), RDF: u32[1024] plus the frame's pair total. */
+int mdgpu_plan_property_counts(mdgpu_plan* plan, size_t prop, uint64_t* out, size_t out_len);
+int mdgpu_plan_property_frame_counts(mdgpu_plan* plan, size_t prop, uint32_t frame, uint32_t* out_bins, uint64_t* out_total);
+
+/* Completed-frame bitmask (md_script_eval_frame_mask :6655): 1 bit per frame, little-endian u64 words. */
+int mdgpu_plan_frame_mask(mdgpu_plan* plan, uint64_t* out_words, size_t num_words);
+
+/* Multi-GPU: device pointer + byte size of a property's integer accumulator so the caller's communicator
+ * (NCCL via torch.distributed in bench.py) can all-reduce it in place; then mdgpu_plan_set_frames_accumulated. */
+int mdgpu_plan_property_accum_ptr(mdgpu_plan* plan, size_t prop, void** d_ptr, size_t* bytes, uint32_t* elem_bytes);
+int mdgpu_plan_set_frames_accumulated(mdgpu_plan* plan, size_t prop, uint64_t frames);
+
+/* Kernel bookkeeping for bench.py: launches issued by this library since the counter was last reset, and
+ * CUDA-event time of the dominant kernel (ms, summed) measured on the launching stream when timing is enabled. */
+uint64_t mdgpu_launch_count(bool reset);
+int mdgpu_plan_enable_kernel_timing(mdgpu_plan* plan, int enable);
+/* Device-side stopwatch over everything the plan enqueues: _begin drains the device and records a CUDA event; _end records
+ * one event per plan stream, waits, and returns the largest elapsed time (ms) — i.e. device time of the whole frame loop. */
+int mdgpu_plan_timer_begin(mdgpu_plan* plan);
+int mdgpu_plan_timer_end(mdgpu_plan* plan, double* elapsed_ms);
+int mdgpu_plan_kernel_time_ms(mdgpu_plan* plan, const char* kernel, double* total_ms, uint64_t* launches);
+
+/* Synthetic workloads (viamd_b200/csrc/synth.h), used by bench.py and the tests. */
+int mdgpu_synth_water_desc(uint32_t n, uint32_t seed, uint32_t* num_atoms, float* L);
+int mdgpu_synth_water_base(uint32_t n, uint32_t seed, float* base_xyz /* [3][num_atoms] wrapped */, float* whole_xyz /* optional */);
+int mdgpu_synth_water_frames_host(uint32_t n, uint32_t seed, const float* base_xyz, uint32_t frame_beg, uint32_t count,
+                                  float* out_xyz, size_t frame_stride, size_t axis_stride);
+int mdgpu_synth_water_frames_device(int device, uint32_t n, uint32_t seed, const float* d_base_xyz, uint32_t frame_beg, uint32_t count,
+                                    float* d_out_xyz, size_t frame_stride, size_t axis_stride);
+
+/* Thin device-memory helpers so C hosts need no CUDA headers. */
+int mdgpu_device_alloc(int device, size_t bytes, void** out);
+int mdgpu_device_free(int device, void* p);
+int mdgpu_host_alloc_pinned(size_t bytes, void** out);
+int mdgpu_host_free_pinned(void* p);
+int mdgpu_memcpy_h2d(int device, void* dst, const void* src, size_t bytes);
+int mdgpu_memcpy_d2h(int device, void* dst, const void* src, size_t bytes);
+int mdgpu_device_synchronize(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDGPU_H */

@@ -285,8 +285,32 @@ static int mode_eval(int argc, char** argv, bool timing) {
     return 0;
 }
 
+/* dumptraj: write frames [B,E) of any trajectory spec as an MDRAWTRJ container (fixture generation) */
+static int mode_dumptraj(int argc, char** argv) {
+    md_allocator_i* alloc = md_vm_arena_create(GIGABYTES(8));
+    md_system_t sys; if (!load_system(&sys, arg_val(argc, argv, "--sys", ""), alloc)) return 2;
+    md_trajectory_i traj = {0}; mem_traj_t mt;
+    if (!make_traj(&traj, &mt, arg_val(argc, argv, "--traj", "sys"), &sys)) return 2;
+    long b = 0, e = (long)md_trajectory_num_frames(&traj); parse_range(arg_val(argc, argv, "--frames", NULL), &b, &e);
+    const size_t n = sys.atom.count;
+    FILE* f = fopen(arg_val(argc, argv, "--out", "traj.raw"), "wb"); if (!f) return 2;
+    wr(f, "MDRAWTRJ", 8); wr_u64(f, (uint64_t)(e - b)); wr_u64(f, n);
+    float* xyz = malloc(n * 12);
+    md_trajectory_reader_i rd = {0}; md_trajectory_reader_init(&rd, &traj);
+    for (long fr = b; fr < e; ++fr) {
+        md_trajectory_frame_header_t h = {0};
+        if (!md_trajectory_reader_load_frame(rd, fr, &h, xyz, xyz + n, xyz + 2 * n)) return 2;
+        double cell[6] = { h.unitcell.x, h.unitcell.xy, h.unitcell.xz, h.unitcell.y, h.unitcell.yz, h.unitcell.z };
+        uint32_t fl[2] = { (uint32_t)h.unitcell.flags, 0 };
+        wr(f, cell, 48); wr(f, fl, 8); wr(f, xyz, n * 12);
+    }
+    md_trajectory_reader_free(&rd); fclose(f);
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 2) { fprintf(stderr, "usage: ref_harness sysinfo|eval|time ...\n"); return 1; }
+    if (argc < 2) { fprintf(stderr, "usage: ref_harness sysinfo|eval|time|dumptraj ...\n"); return 1; }
+    if (strcmp(argv[1], "dumptraj") == 0) return mode_dumptraj(argc, argv);
     if (strcmp(argv[1], "sysinfo") == 0) return mode_sysinfo(argc, argv);
     if (strcmp(argv[1], "eval") == 0) return mode_eval(argc, argv, false);
     if (strcmp(argv[1], "time") == 0) return mode_eval(argc, argv, true);

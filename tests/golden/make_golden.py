@@ -1,0 +1,102 @@
+"""Generate the golden fixtures in tests/golden/ from the UNMODIFIED reference (oracle/_ref/ref_harness_strict).
+
+Run here (needs /root/reference + `make -C oracle ref oracle`):   python tests/golden/make_golden.py
+The fixtures are small .npz files; each stores the inputs (coordinates, cells, system statics) together with the
+reference's outputs, so the tests need neither the reference nor the harness on the GPU box.
+
+  water6.npz : synthetic water n=6 (648 atoms, L=18.624), 4 frames:
+               r  = rdf(element('O'), element('O'), 6.0)            per-frame raw bins + weights + 4-frame mean
+               rh = rdf(element('O'), element('H'), 1.5:6.0)         (min:max form)
+               v  = sdf(residue(1:20), element('O'), 5.0)            per-frame raw voxels (sparse)
+               dz/dx = density_z / density_x (element('O'))          per-frame bins
+               d, a, t = distance(1,10), angle(1,2,3), dihedral(1,4,7,10)
+  ala50.npz  : first 50 frames of datasets/1ALA-500.pdb (153 atoms, ortho cell 46.645 x 96.666 x 48.362), config 1:
+               d = distance(1,10) (BASELINE config 1), rc = rdf(element('C'), element('O'), 10.0), dz = density_z(element('C')),
+               a = angle(1,5,9), t = dihedral(5,7,9,15)
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import refio  # noqa: E402
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness_strict")
+SYNTH = os.path.join(ROOT, "oracle", "build", "synth_tool")
+
+
+def run(*a):
+    subprocess.check_call(list(a), stdout=subprocess.DEVNULL)
+
+
+def sparse(v):
+    nz = np.nonzero(v)[0].astype(np.uint32)
+    return nz, v[nz].astype(np.float32)
+
+
+def sysdict(s):
+    return dict(mass=s["mass"], z=s["z"].astype(np.uint8), names=np.array(s["names"]), comp_off=s["comp_off"],
+                conn_off=s["conn_off"], conn_idx=s["conn_idx"])
+
+
+def pack(out, props, frames):
+    for name, p in props.items():
+        out[f"{name}__flags"] = np.int32(p.flags); out[f"{name}__dim"] = np.array(p.dim, np.int32)
+        if p.flags & refio.FLAG_VOLUME:
+            for f in frames:
+                i, v = sparse(p.perframe[f]); out[f"{name}__pf{f}_idx"] = i; out[f"{name}__pf{f}_val"] = v
+            i, v = sparse(p.full); out[f"{name}__full_idx"] = i; out[f"{name}__full_val"] = v
+        elif p.flags & refio.FLAG_TEMPORAL:
+            out[f"{name}__full"] = p.full
+        else:
+            out[f"{name}__pf"] = np.stack([p.perframe[f] for f in frames]); out[f"{name}__full"] = p.full
+        m = p.meta[(1, frames[0])]
+        out[f"{name}__meta"] = np.array([m["min_value"], m["max_value"], m["min_range"][0], m["max_range"][0]], np.float32)
+
+
+def water6(tmp):
+    n, seed, F = 6, 77, 4
+    gro, raw = os.path.join(tmp, "w.gro"), os.path.join(tmp, "w.raw")
+    run(SYNTH, "water-gro", str(n), str(seed), gro); run(SYNTH, "water-raw", str(n), str(seed), str(F), raw)
+    script = ("r = rdf(element('O'), element('O'), 6.0); rh = rdf(element('O'), element('H'), 1.5:6.0); "
+              "v = sdf(residue(1:20), element('O'), 5.0); dz = density_z(element('O')); dx = density_x(element('O')); "
+              "d = distance(1,10); a = angle(1,2,3); t = dihedral(1,4,7,10);")
+    o = os.path.join(tmp, "w.out"); si = os.path.join(tmp, "w.sys")
+    run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
+    run(HARNESS, "sysinfo", "--sys", gro, "--out", si)
+    frames, cells, flags = refio.read_raw_traj(raw)
+    out = dict(script=np.array(script), n=np.int32(n), seed=np.int32(seed), frames=frames, cells=cells, cell_flags=flags, **sysdict(refio.read_sysinfo(si)))
+    pack(out, refio.read_refout(o), list(range(F)))
+    np.savez_compressed(os.path.join(HERE, "water6.npz"), **out)
+
+
+def ala50(tmp):
+    pdb = "/root/reference/datasets/1ALA-500.pdb"; F = 50
+    raw = os.path.join(tmp, "a.raw"); o = os.path.join(tmp, "a.out"); si = os.path.join(tmp, "a.sys")
+    run(HARNESS, "dumptraj", "--sys", pdb, "--traj", "sys", "--frames", f"0:{F}", "--out", raw)
+    script = ("d = distance(1,10); rc = rdf(element('C'), element('O'), 10.0); dz = density_z(element('C')); "
+              "a = angle(1,5,9); t = dihedral(5,7,9,15);")
+    # evaluate on the dumped frames so that frame 0 (initial configuration) is identical
+    run(HARNESS, "eval", "--sys", pdb, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
+    run(HARNESS, "sysinfo", "--sys", pdb, "--out", si)
+    frames, cells, flags = refio.read_raw_traj(raw)
+    out = dict(script=np.array(script), frames=frames, cells=cells, cell_flags=flags, **sysdict(refio.read_sysinfo(si)))
+    pack(out, refio.read_refout(o), list(range(F)))
+    # the published-by-probe numbers of BASELINE config 1: values[0]=2.770258, sum over 500 frames=1493.846763
+    o2 = os.path.join(tmp, "a2.out")
+    run(HARNESS, "eval", "--sys", pdb, "--traj", "sys", "--script", "d = distance(1,10);", "--out", o2, "--full", "0:500")
+    out["d500__full"] = refio.read_refout(o2)["d"].full
+    np.savez_compressed(os.path.join(HERE, "ala50.npz"), **out)
+
+
+if __name__ == "__main__":
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    with tempfile.TemporaryDirectory() as tmp:
+        water6(tmp); ala50(tmp)
+    for f in ("water6.npz", "ala50.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

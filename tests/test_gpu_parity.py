@@ -1,0 +1,286 @@
+"""Parity tests proper: the CUDA path (through the libmdgpu C ABI) against the golden vectors of the unmodified reference
+and against the plain-C oracle on seeded inputs. Integer work is asserted bit-exact; float temporals within 1e-5 relative
+(BASELINE.json north_star tolerance; acosf/atan2f differ in the last ulp between glibc and CUDA)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from helpers import load_golden, cell_from_row, dense_from_sparse, golden_system, sel_element, vb_system, vb_cell
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5   # north_star: "within 1e-5 relative for float densities"
+
+
+def _vb():
+    import viamd_b200 as vb
+    return vb
+
+
+def _water_plan(g, s, props_src, **kw):
+    vb = _vb()
+    sysm = vb_system(s)
+    props = vb.compile_script(props_src, sysm)
+    F = g["frames"].shape[0]
+    plan = vb.Plan(sysm, props, F, keep_frame_results=True, **kw)
+    cells = [vb_cell(g["cells"][f], g["cell_flags"][f]) for f in range(F)]
+    plan.set_initial_frame(*g["frames"][0], cells[0])
+    return plan, cells
+
+
+def test_golden_water_rdf_per_frame_bitexact():
+    g = load_golden("water6.npz"); s = golden_system(g); vb = _vb()
+    plan, cells = _water_plan(g, s, "r = rdf(element('O'), element('O'), 6.0); rh = rdf(element('O'), element('H'), 1.5:6.0);")
+    F = g["frames"].shape[0]
+    plan.eval_host_frames(g["frames"], cells, 0)
+    for key in ("r", "rh"):
+        acc = np.zeros(1024, np.float64)
+        for f in range(F):
+            bins, tot = plan.frame_counts(key, f)
+            ref = g[f"{key}__pf"][f, :1024]
+            assert np.array_equal(bins.astype(np.float32), ref), f"{key} frame {f}"
+            assert tot == int(ref.sum())
+            acc += ref
+        assert np.array_equal(plan.counts(key).astype(np.float64), acc)
+        d = plan.property_data(key)
+        assert d.dim == (1, 2, 1024, 0) and d.frames_accumulated == F
+        # averaged bins: exact mean vs the reference's float cumulative moving average
+        np.testing.assert_allclose(d.values[:1024], g[f"{key}__full"][:1024], rtol=RTOL, atol=1e-6)
+        np.testing.assert_allclose(d.values[:1024], (acc / F).astype(np.float32), rtol=0, atol=0)
+        # weights are those of the last frame (bit-exact: same double arithmetic)
+        assert np.array_equal(d.weights, g[f"{key}__pf"][F - 1, 1024:])
+        mn, mx, r0, r1 = g[f"{key}__meta"]
+        assert d.min_value == mn and d.max_value == mx and d.min_range[0] == r0 and d.max_range[0] == r1
+    assert plan.frame_mask().all()
+    plan.close()
+
+
+def test_golden_water_sdf_per_frame_bitexact():
+    g = load_golden("water6.npz"); s = golden_system(g)
+    plan, cells = _water_plan(g, s, "v = sdf(residue(1:20), element('O'), 5.0);")
+    F = g["frames"].shape[0]
+    total = np.zeros(128 ** 3, np.float64)
+    for f in range(F):   # per-frame raw voxels: evaluate one frame into cleared accumulators
+        plan.clear()
+        plan.eval_host_frames(g["frames"][f:f + 1], [cells[f]], f)
+        ref = dense_from_sparse(g[f"v__pf{f}_idx"], g[f"v__pf{f}_val"])
+        got = plan.counts("v")
+        assert int(got.sum()) == int(ref.sum()) > 0
+        assert np.array_equal(got.astype(np.float32), ref), f"frame {f}: {(got.astype(np.float32) != ref).sum()} voxels differ"
+        total += ref
+    plan.clear()
+    plan.eval_host_frames(g["frames"], cells, 0)
+    assert np.array_equal(plan.counts("v").astype(np.float64), total)
+    d = plan.property_data("v")
+    assert d.dim == (1, 128, 128, 128)
+    ref_full = dense_from_sparse(g["v__full_idx"], g["v__full_val"])
+    np.testing.assert_allclose(d.values, ref_full, rtol=RTOL, atol=1e-7)
+    assert d.min_value == np.float32(3.4028234663852886e+38) and d.max_value == -np.float32(3.4028234663852886e+38)   # never updated for volumes
+    plan.close()
+
+
+def test_golden_water_density_and_temporals():
+    g = load_golden("water6.npz"); s = golden_system(g)
+    plan, cells = _water_plan(g, s, "dz = density_z(element('O')); dx = density_x(element('O')); d = distance(1,10); a = angle(1,2,3); t = dihedral(1,4,7,10);")
+    F = g["frames"].shape[0]
+    plan.eval_host_frames(g["frames"], cells, 0)
+    for key in ("dz", "dx"):
+        d = plan.property_data(key)
+        np.testing.assert_allclose(d.values[:1024], g[f"{key}__full"][:1024], rtol=RTOL, atol=1e-3)
+        assert np.all(d.weights == 1.0)
+        mn, mx, r0, r1 = g[f"{key}__meta"]
+        assert d.min_value == mn and abs(d.max_value - mx) <= RTOL * mx and d.min_range[0] == r0 and d.max_range[0] == r1
+    d = plan.property_data("d")
+    assert d.dim[:2] == (F, 1)
+    assert np.array_equal(d.values, g["d__full"])                                  # sqrt is correctly rounded on both sides
+    np.testing.assert_allclose(plan.property_data("a").values, g["a__full"], rtol=RTOL)
+    np.testing.assert_allclose(plan.property_data("t").values, g["t__full"], rtol=RTOL)
+    mn, mx, r0, r1 = g["d__meta"]
+    assert d.min_value == mn and d.max_value == mx and d.min_range[0] == r0 and d.max_range[0] == r1
+    plan.close()
+
+
+def test_golden_config1_1ala_distance_and_friends():
+    """BASELINE config 1 (datasets/1ALA-500.pdb, d = distance(1,10)) on the first 50 frames + rdf/density/angle/dihedral."""
+    g = load_golden("ala50.npz"); s = golden_system(g); vb = _vb()
+    sysm = vb_system(s)
+    props = vb.compile_script(str(g["script"]), sysm)
+    F = g["frames"].shape[0]
+    plan = vb.Plan(sysm, props, F, keep_frame_results=True, batch_frames=16)
+    cells = [vb_cell(g["cells"][f], g["cell_flags"][f]) for f in range(F)]
+    traj = vb.ArrayTrajectory(g["frames"], cells)
+    assert plan.eval_frame_range(traj, 0, F)          # md_script_eval_frame_range path (frame source interface)
+    d = plan.property_data("d")
+    assert np.array_equal(d.values, g["d__full"]) and abs(float(d.values[0]) - 2.770258) < 1e-6
+    np.testing.assert_allclose(plan.property_data("a").values, g["a__full"], rtol=RTOL)
+    np.testing.assert_allclose(plan.property_data("t").values, g["t__full"], rtol=RTOL, atol=1e-6)
+    for f in range(F):
+        bins, tot = plan.frame_counts("rc", f)
+        assert np.array_equal(bins.astype(np.float32), g["rc__pf"][f, :1024]), f"frame {f}"
+    np.testing.assert_allclose(plan.property_data("dz").values[:1024], g["dz__full"][:1024], rtol=RTOL, atol=1e-3)
+    assert plan.frame_mask().all()
+    plan.close()
+
+
+@pytest.mark.parametrize("n,cutoff,ref_el,trg_el", [(8, 10.0, 8, 8), (8, 5.0, 8, 1), (10, 12.0, 1, 8), (5, 4.0, 8, 8)])
+def test_oracle_water_rdf_bitexact(n, cutoff, ref_el, trg_el):
+    """Seeded synthetic water of several sizes / cutoffs (cdim from 1 to 3, duplicated periodic images when the cutoff
+    exceeds half the box) against the oracle, through device-generated frames."""
+    vb = _vb()
+    seed, F = 1000 + n, 6
+    base, L = vb.synth_water_base(n, seed)
+    frames = vb.synth_water_frames_host(n, seed, base, 0, F)
+    sysm = vb.water_system(n)
+    el = np.tile(np.array([8, 1, 1]), n ** 3)
+    ref = np.nonzero(el == ref_el)[0].astype(np.int32); trg = np.nonzero(el == trg_el)[0].astype(np.int32)
+    plan = vb.Plan(sysm, [vb.rdf("r", ref, trg, cutoff)], F, keep_frame_results=True, batch_frames=4)
+    cell = vb.UnitCell.from_basis(L, L, L)
+    # device-resident frames generated on the GPU must equal the host generator bit for bit
+    na = 3 * n ** 3
+    d_base = vb.device_alloc(0, base.nbytes); vb.memcpy_h2d(0, d_base, base.ctypes.data, base.nbytes)
+    d_fr = vb.device_alloc(0, frames.nbytes)
+    vb.synth_water_frames_device(0, n, seed, d_base, 0, F, d_fr, 3 * na, na)
+    back = np.empty_like(frames); vb.memcpy_d2h(0, back.ctypes.data, d_fr, frames.nbytes)
+    assert np.array_equal(back, frames)
+    plan.eval_device_frames(d_fr, 3 * na, na, cell, 0, F)
+    ocell = O.UnitCell.ortho(L, L, L)
+    for f in range(F):
+        bins, tot = plan.frame_counts("r", f)
+        obins, ow, otot = O.rdf_frame(frames[f, 0], frames[f, 1], frames[f, 2], ref, trg, ocell, 0.0, cutoff)
+        assert tot == otot
+        assert np.array_equal(bins.astype(np.float32), obins), f"frame {f}"
+    assert np.array_equal(plan.property_data("r").weights, ow)
+    vb.device_free(0, d_base); vb.device_free(0, d_fr)
+    plan.close()
+
+
+def test_oracle_random_boxes_rdf_bitexact():
+    """Random points in anisotropic / partially periodic / non-periodic cells (edge cases of md_spatial_acc_init:
+    AABB-fitted origin, skipped non-periodic wraps), ragged sizes, empty-ish cells."""
+    vb = _vb(); rng = np.random.default_rng(11)
+    cases = [
+        (dict(x=31.0, y=47.5, z=23.25), 4 | 8 | 16 | 1, 500, 7.5),
+        (dict(x=40.0, y=40.0, z=40.0), 4 | 8 | 1, 300, 9.0),        # z not periodic
+        (dict(x=0.0, y=0.0, z=0.0), 0, 257, 6.0),                   # no cell at all
+        (dict(x=25.0, y=25.0, z=60.0), 4 | 8 | 16 | 1, 33, 12.0),   # cutoff ~ half box: cdim 2
+        (dict(x=18.0, y=18.0, z=18.0), 4 | 8 | 16 | 1, 64, 17.0),   # cutoff > half box: periodic images counted per offset
+    ]
+    for cellp, flags, N, cutoff in cases:
+        ext = np.array([cellp["x"] or 50.0, cellp["y"] or 50.0, cellp["z"] or 50.0])
+        F = 3
+        frames = (rng.random((F, 3, N)) * ext[None, :, None] * 1.2 - 0.1 * ext[None, :, None]).astype(np.float32)   # some atoms outside the cell
+        ref = np.sort(rng.choice(N, N // 2, replace=False)).astype(np.int32); trg = np.sort(rng.choice(N, (2 * N) // 3, replace=False)).astype(np.int32)
+        sysm = vb.System(N, np.ones(N, np.float32))
+        plan = vb.Plan(sysm, [vb.rdf("r", ref, trg, cutoff)], F, keep_frame_results=True, batch_frames=2)
+        cell = vb.UnitCell(cellp["x"], 0, 0, cellp["y"], 0, cellp["z"], flags)
+        plan.eval_host_frames(frames, cell, 0)
+        ocell = O.UnitCell.from_params(cellp["x"], 0, 0, cellp["y"], 0, cellp["z"], flags)
+        for f in range(F):
+            bins, tot = plan.frame_counts("r", f)
+            obins, ow, otot = O.rdf_frame(frames[f, 0], frames[f, 1], frames[f, 2], ref, trg, ocell, 0.0, cutoff)
+            assert tot == otot, (cellp, flags, f, tot, otot)
+            assert np.array_equal(bins.astype(np.float32), obins), (cellp, flags, f)
+        plan.close()
+
+
+def test_oracle_triclinic_rdf_bitexact():
+    vb = _vb(); rng = np.random.default_rng(5)
+    N, F, cutoff = 400, 3, 7.0
+    cellp = (30.0, 4.0, -3.0, 28.0, 5.0, 26.0)   # x, xy, xz, y, yz, z
+    flags = 2 | 4 | 8 | 16
+    # points inside the cell: fractional coords in [0,1) mapped through A
+    s = rng.random((F, 3, N))
+    A = np.array([[cellp[0], cellp[1], cellp[2]], [0, cellp[3], cellp[4]], [0, 0, cellp[5]]])
+    frames = np.einsum("ij,fjn->fin", A, s).astype(np.float32)
+    idx = np.arange(N, dtype=np.int32)
+    plan = vb.Plan(vb.System(N, np.ones(N, np.float32)), [vb.rdf("r", idx[::2], idx, cutoff)], F, keep_frame_results=True)
+    plan.eval_host_frames(frames, vb.UnitCell(cellp[0], cellp[1], cellp[2], cellp[3], cellp[4], cellp[5], flags), 0)
+    ocell = O.UnitCell.from_params(*cellp, flags)
+    for f in range(F):
+        bins, tot = plan.frame_counts("r", f)
+        obins, ow, otot = O.rdf_frame(frames[f, 0], frames[f, 1], frames[f, 2], idx[::2], idx, ocell, 0.0, cutoff)
+        assert tot == otot and np.array_equal(bins.astype(np.float32), obins)
+    plan.close()
+
+
+def test_oracle_water_sdf_bitexact_and_batching():
+    """sdf() on seeded water vs the oracle, bit-exact voxels; result independent of batch size / stream count."""
+    vb = _vb()
+    n, seed, F = 8, 4242, 5
+    base, L = vb.synth_water_base(n, seed); frames = vb.synth_water_frames_host(n, seed, base, 0, F)
+    sysm = vb.water_system(n)
+    o = np.arange(0, 3 * n ** 3, 3, dtype=np.int32)
+    structs = np.arange(3 * 100, dtype=np.int32).reshape(100, 3)
+    cell = vb.UnitCell.from_basis(L, L, L); ocell = O.UnitCell.ortho(L, L, L)
+    ref = np.zeros(128 ** 3, np.float32)
+    for f in range(F):
+        O.sdf_frame(frames[f, 0], frames[f, 1], frames[f, 2], frames[0], sysm.mass, structs, o, sysm.conn_offset, sysm.conn_idx, ocell, 6.0, vol=ref)
+    results = []
+    for bf, ns in ((1, 1), (3, 2), (0, 0)):
+        plan = vb.Plan(sysm, [vb.sdf("v", structs, o, 6.0)], F, batch_frames=bf, num_streams=ns)
+        plan.set_initial_frame(*frames[0], cell)
+        plan.eval_host_frames(frames, cell, 0)
+        results.append(plan.counts("v")); plan.close()
+    assert int(results[0].sum()) == int(ref.sum()) > 0
+    assert np.array_equal(results[0].astype(np.float32), ref)
+    assert np.array_equal(results[0], results[1]) and np.array_equal(results[0], results[2])
+
+
+def test_empty_and_error_paths():
+    vb = _vb()
+    s = vb.water_system(3)
+    o = np.arange(0, 81, 3, dtype=np.int32)
+    with pytest.raises(vb.MdgpuError, match="empty reference"):
+        vb.Plan(s, [vb.rdf("r", np.zeros(0, np.int32), o, 5.0)], 2)
+    with pytest.raises(vb.MdgpuError, match="Invalid cutoff"):
+        vb.Plan(s, [vb.rdf("r", o, o, 5.0, cutoff_min=6.0)], 2)
+    with pytest.raises(vb.MdgpuError, match="out of range"):
+        vb.Plan(s, [vb.rdf("r", np.array([1000], np.int32), o, 5.0)], 2)
+    base, L = vb.synth_water_base(3, 1); frames = vb.synth_water_frames_host(3, 1, base, 0, 2)
+    plan = vb.Plan(s, [vb.rdf("r", o, o, 5.0)], 2)
+    with pytest.raises(vb.MdgpuError, match="Invalid frame range"):
+        plan.eval_host_frames(frames, vb.UnitCell.from_basis(L, L, L), 1)
+    # zero frames evaluated: property data stays cleared (weights 1, min/max +-FLT_MAX)
+    d = plan.property_data("r")
+    assert d.frames_accumulated == 0 and np.all(d.values[:1024] == 0) and np.all(d.weights == 1.0)
+    # cutoff too large for the cell grid (2*ncell+1 > 5): the reference logs an error and yields no pairs
+    plan2 = vb.Plan(s, [vb.rdf("r", o, o, 30.0)], 2, keep_frame_results=True)
+    plan2.eval_host_frames(frames, vb.UnitCell.from_basis(L, L, L), 0)
+    assert plan2.frame_counts("r", 0)[1] == 0
+    ob, ow, ot = O.rdf_frame(frames[0, 0], frames[0, 1], frames[0, 2], o, o, O.UnitCell.ortho(L, L, L), 0.0, 30.0)
+    assert ot == 0
+    plan.close(); plan2.close()
+
+
+def test_full_size_properties_config2_config3():
+    """BASELINE config 2/3 shape (98 304 atoms): size-independent properties.
+       - sum of RDF bins == pair total reported per frame; accumulated counts == sum of per-frame counts;
+       - evaluating frames in two halves (or in reverse batch order) gives identical integer accumulators;
+       - rdf(O,O) pair total equals the oracle's on one frame (the oracle finishes one frame in < 1 s)."""
+    vb = _vb()
+    n, seed, F = 32, 1234, 8
+    base, L = vb.synth_water_base(n, seed); na = base.shape[1]
+    d_base = vb.device_alloc(0, base.nbytes); vb.memcpy_h2d(0, d_base, base.ctypes.data, base.nbytes)
+    d_fr = vb.device_alloc(0, F * 3 * na * 4)
+    vb.synth_water_frames_device(0, n, seed, d_base, 0, F, d_fr, 3 * na, na)
+    sysm = vb.water_system(n)
+    o = np.arange(0, na, 3, dtype=np.int32)
+    structs = np.arange(3000, dtype=np.int32).reshape(1000, 3)
+    cell = vb.UnitCell.from_basis(L, L, L)
+    props = [vb.rdf("r", o, o, 10.0), vb.sdf("v", structs, o, 10.0)]
+    f0 = vb.synth_water_frames_host(n, seed, base, 0, 1)
+    plan = vb.Plan(sysm, props, F, keep_frame_results=True)
+    plan.set_initial_frame(*f0[0], cell)
+    plan.eval_device_frames(d_fr, 3 * na, na, cell, 0, F)
+    acc = plan.counts("r"); vol = plan.counts("v")
+    per = [plan.frame_counts("r", f) for f in range(F)]
+    assert all(int(b.sum()) == t for b, t in per)
+    assert np.array_equal(acc, np.sum([b.astype(np.uint64) for b, _ in per], axis=0))
+    ob, ow, ot = O.rdf_frame(f0[0, 0], f0[0, 1], f0[0, 2], o, o, O.UnitCell.ortho(L, L, L), 0.0, 10.0)
+    assert per[0][1] == ot and np.array_equal(per[0][0].astype(np.float32), ob)
+    # split evaluation, second half first
+    plan.clear()
+    plan.eval_device_frames(d_fr + 4 * 3 * na * 4, 3 * na, na, cell, 4, 4)
+    plan.eval_device_frames(d_fr, 3 * na, na, cell, 0, 4)
+    assert np.array_equal(plan.counts("r"), acc) and np.array_equal(plan.counts("v"), vol)
+    assert 2.5e5 * F < int(vol.sum()) < 3.5e5 * F
+    vb.device_free(0, d_base); vb.device_free(0, d_fr); plan.close()

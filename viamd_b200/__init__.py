@@ -1,0 +1,14 @@
+"""viamd_b200 — B200-native per-frame trajectory analysis behind VIAMD/mdlib's md_script property API.
+
+The product is viamd_b200/libmdgpu.so (hand-written CUDA for sm_100a behind the C ABI in include/mdgpu.h); this package is
+the thin host-side mirror of the md_script evaluation API used by the tests and bench.py.
+"""
+from .api import (  # noqa: F401
+    MdgpuError, UnitCell, System, Property, PropertyData, Plan, Trajectory, ArrayTrajectory,
+    rdf, sdf, density, distance, angle, dihedral, water_system, device_count, launch_count, lib,
+    synth_water_desc, synth_water_base, synth_water_frames_host, synth_water_frames_device,
+    device_alloc, device_free, host_alloc_pinned, host_free_pinned, memcpy_h2d, memcpy_d2h, device_synchronize,
+    OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL,
+    CELL_ORTHO, CELL_TRICLINIC, CELL_PBC_X, CELL_PBC_Y, CELL_PBC_Z, CELL_PBC_ALL, DIST_BINS, VOL_DIM,
+)
+from .script import compile_script, ScriptError  # noqa: F401

@@ -1,0 +1,496 @@
+"""Host-side Python mirror of the md_script evaluation API on top of the libmdgpu C ABI (include/mdgpu.h).
+
+The reference's API for this path (mdlib/src/md_script.h:226-253):
+    md_script_eval_create(num_frames, ir, alloc)      -> Plan(system, properties, num_frames)
+    md_script_eval_clear_data(eval)                   -> Plan.clear()
+    md_script_eval_frame_range(eval, ir, sys, traj, beg, end) -> Plan.eval_frame_range(traj, beg, end)
+    md_script_eval_property_data(eval, name)          -> Plan.property_data(name)
+    md_script_eval_frame_mask / _interrupt            -> Plan.frame_mask() / Plan.interrupt()
+Everything here is ctypes plumbing: the compute path is the CUDA library, and there is deliberately no CPU fallback —
+if libmdgpu.so cannot be loaded or no CUDA device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmdgpu.so")
+
+DIST_BINS = 1024
+VOL_DIM = 128
+
+OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL = 1, 2, 3, 4, 5, 6, 7, 8
+CELL_ORTHO, CELL_TRICLINIC, CELL_PBC_X, CELL_PBC_Y, CELL_PBC_Z, CELL_PBC_ALL = 1, 2, 4, 8, 16, 28
+
+
+class MdgpuError(RuntimeError):
+    pass
+
+
+class UnitCell(C.Structure):
+    """md_unitcell_t (md_types.h:254-259)."""
+    _fields_ = [("x", C.c_double), ("xy", C.c_double), ("xz", C.c_double), ("y", C.c_double), ("yz", C.c_double),
+                ("z", C.c_double), ("flags", C.c_uint32)]
+
+    @staticmethod
+    def from_basis(x, y, z, xy=0.0, xz=0.0, yz=0.0):
+        """md_unitcell_from_basis_parameters (md_unitcell.inl:12-31)."""
+        flags = 0
+        if xy == 0.0 and xz == 0.0 and yz == 0.0:
+            if not (x == 0.0 and y == 0.0 and z == 0.0) and not (x == 1.0 and y == 1.0 and z == 1.0):
+                flags |= CELL_ORTHO
+        else:
+            flags |= CELL_TRICLINIC
+        if flags:
+            if x != 0.0: flags |= CELL_PBC_X
+            if y != 0.0: flags |= CELL_PBC_Y
+            if z != 0.0: flags |= CELL_PBC_Z
+        return UnitCell(float(x), float(xy), float(xz), float(y), float(yz), float(z), flags)
+
+    @staticmethod
+    def none():
+        return UnitCell(0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0)
+
+
+class FrameHeader(C.Structure):
+    _fields_ = [("num_atoms", C.c_size_t), ("index", C.c_int64), ("timestamp", C.c_double), ("unitcell", UnitCell)]
+
+
+class _SystemDesc(C.Structure):
+    _fields_ = [("num_atoms", C.c_size_t), ("atom_mass", C.POINTER(C.c_float)), ("bond_conn_offset", C.POINTER(C.c_uint32)),
+                ("bond_conn_atom_idx", C.POINTER(C.c_int32)), ("bond_conn_offset_count", C.c_size_t)]
+
+
+class _PropertyDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("op", C.c_uint32), ("idx", C.POINTER(C.c_int32) * 4), ("idx_count", C.c_size_t * 4),
+                ("num_structures", C.c_size_t), ("structure_size", C.c_size_t), ("cutoff_min", C.c_float), ("cutoff_max", C.c_float)]
+
+
+class _PropertyData(C.Structure):
+    _fields_ = [("dim", C.c_int32 * 4), ("num_values", C.c_size_t), ("values", C.POINTER(C.c_float)), ("weights", C.POINTER(C.c_float)),
+                ("min_value", C.c_float), ("max_value", C.c_float), ("min_range", C.c_float * 2), ("max_range", C.c_float * 2),
+                ("frames_accumulated", C.c_uint64)]
+
+
+class _PlanOptions(C.Structure):
+    _fields_ = [("device", C.c_int), ("batch_frames", C.c_uint32), ("num_streams", C.c_uint32), ("keep_frame_results", C.c_uint32),
+                ("cell_capacity", C.c_uint32), ("rdf_variant", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
+# md_trajectory_i-compatible callback table (md_trajectory.h:49-67)
+class _Reader(C.Structure):
+    pass
+
+
+_LOAD_FRAME = C.CFUNCTYPE(C.c_bool, C.c_void_p, C.c_int64, C.POINTER(FrameHeader), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float))
+_READER_FREE = C.CFUNCTYPE(None, C.POINTER(_Reader))
+_Reader._fields_ = [("inst", C.c_void_p), ("free", _READER_FREE), ("load_frame", _LOAD_FRAME)]
+
+
+class _TrajHeader(C.Structure):
+    _fields_ = [("num_frames", C.c_size_t), ("num_atoms", C.c_size_t), ("unit_bits", C.c_uint64), ("unit_mult", C.c_double),
+                ("frame_times", C.POINTER(C.c_double))]
+
+
+class _Traj(C.Structure):
+    pass
+
+
+_GET_HEADER = C.CFUNCTYPE(C.c_bool, C.c_void_p, C.POINTER(_TrajHeader))
+_INIT_READER = C.CFUNCTYPE(C.c_bool, C.POINTER(_Reader), C.c_void_p)
+_TRAJ_FREE = C.CFUNCTYPE(None, C.POINTER(_Traj))
+_Traj._fields_ = [("inst", C.c_void_p), ("free", _TRAJ_FREE), ("get_header", _GET_HEADER), ("init_reader", _INIT_READER)]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libmdgpu.so (built in-tree by viamd_b200/build.py). Raises if missing: there is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MdgpuError(f"{LIB_PATH} not found: build it with `python -m viamd_b200.build` (or __graft_entry__.build())")
+        L = C.CDLL(LIB_PATH)
+        L.mdgpu_last_error.restype = C.c_char_p
+        L.mdgpu_plan_create.restype = C.c_void_p
+        L.mdgpu_plan_create.argtypes = [C.POINTER(_SystemDesc), C.POINTER(_PropertyDesc), C.c_size_t, C.c_size_t, C.POINTER(_PlanOptions)]
+        L.mdgpu_plan_destroy.argtypes = [C.c_void_p]
+        L.mdgpu_plan_destroy.restype = None
+        L.mdgpu_plan_clear.argtypes = [C.c_void_p]
+        L.mdgpu_plan_set_initial_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(UnitCell)]
+        for name in ("mdgpu_eval_device_frames", "mdgpu_eval_host_frames"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]
+        L.mdgpu_eval_trajectory.argtypes = [C.c_void_p, C.POINTER(_Traj), C.c_uint32, C.c_uint32, C.c_uint32]
+        L.mdgpu_plan_sync.argtypes = [C.c_void_p]
+        L.mdgpu_plan_interrupt.argtypes = [C.c_void_p]
+        L.mdgpu_plan_interrupt.restype = None
+        L.mdgpu_plan_property_count.argtypes = [C.c_void_p]
+        L.mdgpu_plan_property_count.restype = C.c_size_t
+        L.mdgpu_plan_property_index.argtypes = [C.c_void_p, C.c_char_p]
+        L.mdgpu_plan_property_data.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(_PropertyData)]
+        L.mdgpu_plan_property_counts.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.mdgpu_plan_property_frame_counts.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.mdgpu_plan_frame_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.mdgpu_plan_property_accum_ptr.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
+        L.mdgpu_plan_set_frames_accumulated.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64]
+        L.mdgpu_launch_count.argtypes = [C.c_bool]
+        L.mdgpu_launch_count.restype = C.c_uint64
+        L.mdgpu_plan_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+        L.mdgpu_plan_timer_begin.argtypes = [C.c_void_p]
+        L.mdgpu_plan_timer_end.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.mdgpu_plan_kernel_time_ms.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.mdgpu_synth_water_desc.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.mdgpu_synth_water_base.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.mdgpu_synth_water_frames_host.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_size_t]
+        L.mdgpu_synth_water_frames_device.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_size_t]
+        L.mdgpu_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.mdgpu_device_free.argtypes = [C.c_int, C.c_void_p]
+        L.mdgpu_host_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.mdgpu_host_free_pinned.argtypes = [C.c_void_p]
+        L.mdgpu_memcpy_h2d.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.mdgpu_memcpy_d2h.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.mdgpu_device_synchronize.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise MdgpuError(f"mdgpu error {rc}: {lib().mdgpu_last_error().decode(errors='replace')}")
+
+
+def device_count() -> int:
+    return int(lib().mdgpu_device_count())
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().mdgpu_launch_count(reset))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class System:
+    """What the per-frame procedures read from md_system_t: masses and covalent-bond connectivity, plus optional
+    atom metadata (element symbol, atom name, residue name / residue atom offsets) used by viamd_b200.script selections."""
+    num_atoms: int
+    mass: np.ndarray
+    conn_offset: Optional[np.ndarray] = None
+    conn_idx: Optional[np.ndarray] = None
+    element: Optional[Sequence[str]] = None
+    name: Optional[Sequence[str]] = None
+    resname: Optional[Sequence[str]] = None        # per residue
+    res_atom_offset: Optional[np.ndarray] = None   # [num_res + 1]
+
+
+@dataclass
+class Property:
+    name: str
+    op: int
+    idx: list = field(default_factory=list)   # up to 4 int32 arrays
+    num_structures: int = 0
+    structure_size: int = 0
+    cutoff_min: float = 0.0
+    cutoff_max: float = 0.0
+
+
+def rdf(name, ref_idx, trg_idx, cutoff, cutoff_min=0.0):
+    return Property(name, OP_RDF, [np.asarray(ref_idx, np.int32), np.asarray(trg_idx, np.int32)], cutoff_min=float(cutoff_min), cutoff_max=float(cutoff))
+
+
+def sdf(name, structures, trg_idx, cutoff):
+    s = np.ascontiguousarray(structures, np.int32)
+    assert s.ndim == 2, "structures: [num_structures, structure_size] atom indices"
+    return Property(name, OP_SDF, [s.reshape(-1), np.asarray(trg_idx, np.int32)], num_structures=s.shape[0], structure_size=s.shape[1], cutoff_max=float(cutoff))
+
+
+def density(name, axis, idx):
+    return Property(name, OP_DENSITY_X + int(axis), [np.asarray(idx, np.int32)])
+
+
+def distance(name, a, b):
+    return Property(name, OP_DISTANCE, [np.asarray([a], np.int32), np.asarray([b], np.int32)])
+
+
+def angle(name, a, b, c):
+    return Property(name, OP_ANGLE, [np.asarray([a], np.int32), np.asarray([b], np.int32), np.asarray([c], np.int32)])
+
+
+def dihedral(name, a, b, c, d):
+    return Property(name, OP_DIHEDRAL, [np.asarray([k], np.int32) for k in (a, b, c, d)])
+
+
+@dataclass
+class PropertyData:
+    """md_script_property_data_t view (md_script.h:73-92)."""
+    name: str
+    dim: tuple
+    values: np.ndarray
+    weights: Optional[np.ndarray]
+    min_value: float
+    max_value: float
+    min_range: tuple
+    max_range: tuple
+    frames_accumulated: int
+
+
+class Trajectory:
+    """Python frame source exposed to the library through the md_trajectory_i vtable (md_trajectory.h:56-67).
+    Subclass and implement num_frames / num_atoms / load_frame(idx) -> (x, y, z, UnitCell)."""
+
+    def num_frames(self) -> int: raise NotImplementedError
+    def num_atoms(self) -> int: raise NotImplementedError
+    def load_frame(self, idx: int): raise NotImplementedError
+
+    def _as_c(self):
+        n = self.num_atoms()
+
+        def get_header(inst, hdr):
+            hdr[0].num_frames = self.num_frames(); hdr[0].num_atoms = n; hdr[0].unit_bits = 0; hdr[0].unit_mult = 0.0
+            hdr[0].frame_times = None
+            return True
+
+        def load_frame(inst, idx, hdr, px, py, pz):
+            try:
+                x, y, z, cell = self.load_frame(int(idx))
+            except Exception:
+                return False
+            if hdr:
+                hdr[0].num_atoms = n; hdr[0].index = idx; hdr[0].timestamp = float(idx); hdr[0].unitcell = cell
+            if px:
+                C.memmove(px, np.ascontiguousarray(x, np.float32).ctypes.data, 4 * n)
+                C.memmove(py, np.ascontiguousarray(y, np.float32).ctypes.data, 4 * n)
+                C.memmove(pz, np.ascontiguousarray(z, np.float32).ctypes.data, 4 * n)
+            return True
+
+        def reader_free(r):
+            return None
+
+        self._cb_load = _LOAD_FRAME(load_frame); self._cb_rfree = _READER_FREE(reader_free)
+
+        def init_reader(reader, inst):
+            reader[0].inst = 1; reader[0].free = self._cb_rfree; reader[0].load_frame = self._cb_load
+            return True
+
+        def traj_free(t):
+            return None
+
+        self._cb_hdr = _GET_HEADER(get_header); self._cb_init = _INIT_READER(init_reader); self._cb_tfree = _TRAJ_FREE(traj_free)
+        t = _Traj(); t.inst = 1; t.free = self._cb_tfree; t.get_header = self._cb_hdr; t.init_reader = self._cb_init
+        return t
+
+
+class ArrayTrajectory(Trajectory):
+    """In-memory trajectory: frames [F,3,N] float32, cells: list of UnitCell (or one cell for all frames)."""
+
+    def __init__(self, frames: np.ndarray, cells):
+        self.frames = np.ascontiguousarray(frames, np.float32)
+        self.cells = cells
+
+    def num_frames(self): return self.frames.shape[0]
+    def num_atoms(self): return self.frames.shape[2]
+
+    def load_frame(self, idx):
+        c = self.cells if isinstance(self.cells, UnitCell) else self.cells[idx]
+        return self.frames[idx, 0], self.frames[idx, 1], self.frames[idx, 2], c
+
+
+class Plan:
+    """md_script_eval_t equivalent: owns device accumulators and the host-visible property data."""
+
+    def __init__(self, system: System, properties: Sequence[Property], num_frames: int, device: int = 0, batch_frames: int = 0,
+                 num_streams: int = 0, keep_frame_results: bool = False, cell_capacity: int = 0, rdf_variant: int = 0):
+        L = lib()
+        self.system, self.properties, self.num_frames, self.device = system, list(properties), int(num_frames), int(device)
+        self._keep = []
+        mass = np.ascontiguousarray(system.mass, np.float32); self._keep.append(mass)
+        sd = _SystemDesc(); sd.num_atoms = system.num_atoms; sd.atom_mass = mass.ctypes.data_as(C.POINTER(C.c_float))
+        if system.conn_offset is not None:
+            co = np.ascontiguousarray(system.conn_offset, np.uint32); ci = np.ascontiguousarray(system.conn_idx, np.int32); self._keep += [co, ci]
+            sd.bond_conn_offset = co.ctypes.data_as(C.POINTER(C.c_uint32)); sd.bond_conn_atom_idx = ci.ctypes.data_as(C.POINTER(C.c_int32))
+            sd.bond_conn_offset_count = len(co)
+        descs = (_PropertyDesc * len(self.properties))()
+        for i, p in enumerate(self.properties):
+            d = descs[i]; nm = p.name.encode(); self._keep.append(nm)
+            d.name = nm; d.op = p.op; d.num_structures = p.num_structures; d.structure_size = p.structure_size
+            d.cutoff_min = p.cutoff_min; d.cutoff_max = p.cutoff_max
+            for k, arr in enumerate(p.idx):
+                a = np.ascontiguousarray(arr, np.int32); self._keep.append(a)
+                d.idx[k] = a.ctypes.data_as(C.POINTER(C.c_int32)); d.idx_count[k] = a.size
+        o = _PlanOptions(); o.device = device; o.batch_frames = batch_frames; o.num_streams = num_streams
+        o.keep_frame_results = 1 if keep_frame_results else 0; o.cell_capacity = cell_capacity; o.rdf_variant = rdf_variant
+        self._h = L.mdgpu_plan_create(C.byref(sd), descs, len(self.properties), self.num_frames, C.byref(o))
+        if not self._h:
+            raise MdgpuError(L.mdgpu_last_error().decode(errors="replace"))
+        self._names = [p.name for p in self.properties]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mdgpu_plan_destroy(self._h); self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self): return self
+    def __exit__(self, *a): self.close()
+
+    # -- md_script_eval_* mirror
+    def clear(self): _check(lib().mdgpu_plan_clear(self._h))
+    def interrupt(self): lib().mdgpu_plan_interrupt(self._h)
+    def sync(self): _check(lib().mdgpu_plan_sync(self._h))
+
+    def set_initial_frame(self, x, y, z, cell: UnitCell):
+        x, y, z = (np.ascontiguousarray(a, np.float32) for a in (x, y, z))
+        _check(lib().mdgpu_plan_set_initial_frame(self._h, x.ctypes.data, y.ctypes.data, z.ctypes.data, C.byref(cell)))
+
+    @staticmethod
+    def _cells_arg(cells, count):
+        if isinstance(cells, UnitCell):
+            arr = (UnitCell * 1)(cells); return arr, 0
+        arr = (UnitCell * count)(*cells[:count]); return arr, C.sizeof(UnitCell)
+
+    def eval_host_frames(self, frames: np.ndarray, cells, frame_beg: int = 0):
+        """frames: [F,3,N] float32 host array (numpy, or any object exposing .ctypes.data / __array_interface__)."""
+        frames = np.ascontiguousarray(frames, np.float32); F, _, N = frames.shape
+        carr, cstride = self._cells_arg(cells, F)
+        _check(lib().mdgpu_eval_host_frames(self._h, frames.ctypes.data, 3 * N, N, C.addressof(carr), cstride, frame_beg, F))
+
+    def eval_host_ptr(self, ptr: int, frame_stride: int, axis_stride: int, cells, frame_beg: int, count: int):
+        carr, cstride = self._cells_arg(cells, count)
+        _check(lib().mdgpu_eval_host_frames(self._h, ptr, frame_stride, axis_stride, C.addressof(carr), cstride, frame_beg, count))
+
+    def eval_device_frames(self, d_ptr: int, frame_stride: int, axis_stride: int, cells, frame_beg: int, count: int):
+        carr, cstride = self._cells_arg(cells, count)
+        _check(lib().mdgpu_eval_device_frames(self._h, d_ptr, frame_stride, axis_stride, C.addressof(carr), cstride, frame_beg, count))
+
+    def eval_frame_range(self, traj: Trajectory, frame_beg: int, frame_end: int, loader_threads: int = 1) -> bool:
+        """md_script_eval_frame_range(eval, ir, sys, traj, beg, end) (md_script.c:6573): returns False on failure."""
+        t = traj._as_c()
+        rc = lib().mdgpu_eval_trajectory(self._h, C.byref(t), frame_beg, frame_end, loader_threads)
+        if rc == 0:
+            rc = lib().mdgpu_plan_sync(self._h)
+        self._last_rc = rc
+        return rc == 0
+
+    def last_error(self) -> str:
+        return lib().mdgpu_last_error().decode(errors="replace")
+
+    def _index(self, name) -> int:
+        if isinstance(name, int):
+            return name
+        i = lib().mdgpu_plan_property_index(self._h, name.encode())
+        if i < 0:
+            raise KeyError(name)
+        return i
+
+    def property_data(self, name) -> PropertyData:
+        i = self._index(name); d = _PropertyData()
+        _check(lib().mdgpu_plan_property_data(self._h, i, C.byref(d)))
+        vals = np.ctypeslib.as_array(d.values, shape=(d.num_values,)).copy()
+        dim = tuple(d.dim)
+        weights = vals[dim[2]:2 * dim[2]].copy() if bool(d.weights) else None
+        return PropertyData(self._names[i], dim, vals, weights, float(d.min_value), float(d.max_value), tuple(d.min_range), tuple(d.max_range), int(d.frames_accumulated))
+
+    def counts(self, name) -> np.ndarray:
+        i = self._index(name); op = self.properties[i].op
+        n = VOL_DIM ** 3 if op == OP_SDF else DIST_BINS
+        out = np.zeros(n, np.uint64)
+        _check(lib().mdgpu_plan_property_counts(self._h, i, out.ctypes.data, n))
+        return out
+
+    def frame_counts(self, name, frame: int, want_bins: bool = True):
+        i = self._index(name); bins = np.zeros(DIST_BINS, np.uint32) if want_bins else None; tot = C.c_uint64(0)
+        _check(lib().mdgpu_plan_property_frame_counts(self._h, i, frame, bins.ctypes.data if want_bins else None, C.byref(tot)))
+        return bins, int(tot.value)
+
+    def frame_mask(self) -> np.ndarray:
+        nw = (self.num_frames + 63) // 64; w = np.zeros(nw, np.uint64)
+        _check(lib().mdgpu_plan_frame_mask(self._h, w.ctypes.data, nw))
+        bits = np.unpackbits(w.view(np.uint8), bitorder="little")[: self.num_frames]
+        return bits.astype(bool)
+
+    def accum_ptr(self, name):
+        i = self._index(name); p = C.c_void_p(); b = C.c_size_t(); e = C.c_uint32()
+        _check(lib().mdgpu_plan_property_accum_ptr(self._h, i, C.byref(p), C.byref(b), C.byref(e)))
+        return int(p.value), int(b.value), int(e.value)
+
+    def set_frames_accumulated(self, name, frames: int):
+        _check(lib().mdgpu_plan_set_frames_accumulated(self._h, self._index(name), frames))
+
+    def enable_kernel_timing(self, on=True): _check(lib().mdgpu_plan_enable_kernel_timing(self._h, 1 if on else 0))
+
+    def timer_begin(self): _check(lib().mdgpu_plan_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_double(); _check(lib().mdgpu_plan_timer_end(self._h, C.byref(ms))); return float(ms.value)
+
+    def kernel_time_ms(self, kernel="k_rdf_pairs"):
+        ms = C.c_double(); n = C.c_uint64()
+        _check(lib().mdgpu_plan_kernel_time_ms(self._h, kernel.encode(), C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# synthetic workloads + raw memory helpers
+def synth_water_desc(n: int, seed: int):
+    na = C.c_uint32(); L = C.c_float()
+    _check(lib().mdgpu_synth_water_desc(n, seed, C.byref(na), C.byref(L)))
+    return int(na.value), float(L.value)
+
+
+def synth_water_base(n: int, seed: int, want_whole: bool = False):
+    na, L = synth_water_desc(n, seed)
+    base = np.zeros((3, na), np.float32); whole = np.zeros((3, na), np.float32) if want_whole else None
+    _check(lib().mdgpu_synth_water_base(n, seed, base.ctypes.data, whole.ctypes.data if want_whole else None))
+    return (base, whole, L) if want_whole else (base, L)
+
+
+def synth_water_frames_host(n: int, seed: int, base: np.ndarray, frame_beg: int, count: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+    na = base.shape[1]
+    if out is None:
+        out = np.empty((count, 3, na), np.float32)
+    _check(lib().mdgpu_synth_water_frames_host(n, seed, np.ascontiguousarray(base, np.float32).ctypes.data, frame_beg, count, out.ctypes.data, 3 * na, na))
+    return out
+
+
+def synth_water_frames_device(device: int, n: int, seed: int, d_base: int, frame_beg: int, count: int, d_out: int, frame_stride: int, axis_stride: int):
+    _check(lib().mdgpu_synth_water_frames_device(device, n, seed, d_base, frame_beg, count, d_out, frame_stride, axis_stride))
+
+
+def device_alloc(device: int, nbytes: int) -> int:
+    p = C.c_void_p(); _check(lib().mdgpu_device_alloc(device, nbytes, C.byref(p))); return int(p.value)
+
+
+def device_free(device: int, ptr: int): _check(lib().mdgpu_device_free(device, ptr))
+
+
+def host_alloc_pinned(nbytes: int) -> int:
+    p = C.c_void_p(); _check(lib().mdgpu_host_alloc_pinned(nbytes, C.byref(p))); return int(p.value)
+
+
+def host_free_pinned(ptr: int): _check(lib().mdgpu_host_free_pinned(ptr))
+def memcpy_h2d(device, dst, src, nbytes): _check(lib().mdgpu_memcpy_h2d(device, dst, src, nbytes))
+def memcpy_d2h(device, dst, src, nbytes): _check(lib().mdgpu_memcpy_d2h(device, dst, src, nbytes))
+def device_synchronize(device=0): _check(lib().mdgpu_device_synchronize(device))
+
+
+def water_system(n: int) -> System:
+    """Topology of the synthetic water box (OW,HW1,HW2 per molecule; masses as md_atom_extract_masses yields them)."""
+    nm = n ** 3; na = 3 * nm
+    mass = np.tile(np.array([15.9994, 1.00794, 1.00794], np.float32), nm)
+    conn_off = np.zeros(na + 1, np.uint32); conn_idx = np.zeros(4 * nm, np.int32)
+    # per molecule: O bonded to H1,H2; H1 -> O; H2 -> O
+    per = np.array([0, 2, 3, 4], np.uint32)
+    conn_off[:-1] = (np.repeat(np.arange(nm, dtype=np.uint32) * 4, 3) + np.tile(per[:3], nm))
+    conn_off[-1] = 4 * nm
+    o = np.arange(nm, dtype=np.int32) * 3
+    conn_idx[0::4] = o + 1; conn_idx[1::4] = o + 2; conn_idx[2::4] = o; conn_idx[3::4] = o
+    return System(na, mass, conn_off, conn_idx, element=["O", "H", "H"] * nm, name=["OW", "HW1", "HW2"] * nm,
+                  resname=["SOL"] * nm, res_atom_offset=np.arange(nm + 1, dtype=np.int64) * 3)

@@ -1,0 +1,77 @@
+// kernels.h — host-callable launchers of the per-batch kernels (defined in cells.cu, rdf.cu, sdf.cu, props.cu, synth.cu)
+#pragma once
+#include "common.cuh"
+
+namespace mdg {
+
+// cells.cu
+void host_frame_geom(FrameGeom* g, const mdgpu_unitcell_t* uc, double cell_ext, double cutoff, const float* aabb, uint32_t cap);
+void launch_geom(const mdgpu_unitcell_t* d_cells, const float* d_aabb, FrameGeom* d_geom, double cell_ext, double cutoff, uint32_t cap,
+                 int B, int* d_err, cudaStream_t s);
+void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float* d_aabb, cudaStream_t s);
+void launch_cell_list(int mode, const BatchFrames& fr, const int32_t* d_idx, const float* d_aos, uint32_t n, const FrameGeom* d_geom,
+                      const CellList& cl, int store_linear_idx, cudaStream_t s);
+
+// rdf.cu
+struct RdfArgs {
+    const FrameGeom* geom;
+    CellList trg, ref;
+    float min_cutoff, inv_cutoff_range, min_r2;
+    uint32_t* frame_bins;        // [B][1024], zeroed by the launcher
+    const uint32_t* excl_off;    // structure -> atoms CSR (rdf_cb_excl_mask), or null
+    const int32_t* excl_idx;
+    uint32_t frame0;             // global index of the batch's first frame
+    // finalize
+    unsigned long long* acc;     // [1024] accumulated bins
+    unsigned long long* frame_total;  // [num_frames]
+    uint32_t* frame_min;         // [num_frames]
+    uint32_t* frame_max;
+    uint32_t* keep;              // [num_frames][1024] or null
+};
+void launch_rdf(const RdfArgs& a, int B, bool tri, int variant, int sm_count, cudaStream_t s, cudaEvent_t* ev_beg, cudaEvent_t* ev_end);
+
+// sdf.cu
+struct SdfArgs {
+    const FrameGeom* geom;
+    CellList trg;
+    BatchFrames frames;
+    const mdgpu_unitcell_t* cells;   // [B]
+    const float* init_xyz;           // [3][num_atoms] initial configuration (device)
+    size_t init_axis_stride;
+    const float* mass;
+    const int32_t* struct_idx;       // [n_struct][struct_size]
+    uint32_t n_struct, struct_size;
+    const int2* unwrap_pairs;        // (child, parent) local indices in BFS order
+    uint32_t n_unwrap;
+    float cutoff;
+    float4* scratch_xyzw;            // [B][n_struct+1][struct_size]
+    float* ref0;                     // [B][20]: VA(16) com0(3) pad
+    float* matrices;                 // [B][n_struct][16 + 4]: M, com
+    uint32_t* vol;                   // [128^3] accumulated voxels
+    unsigned long long* frame_total; // [num_frames]
+    uint32_t frame0;
+};
+void launch_sdf(const SdfArgs& a, int B, cudaStream_t s);
+
+// props.cu
+struct DensityArgs {
+    BatchFrames frames; const int32_t* idx; uint32_t n; const float* mass; int axis;
+    float rc, re, inv_ext, min_point;      // reference point / extent / 1/extent / lower bound along the axis (initial cell)
+    unsigned long long* acc;               // [1024] fixed-point mass sums (2^-24 Da)
+    unsigned long long* frame_bins;        // [B][1024] scratch, zeroed by launcher
+    unsigned long long* frame_min; unsigned long long* frame_max;   // [num_frames]
+    unsigned long long* keep;              // [num_frames][1024] or null
+    uint32_t frame0;
+};
+void launch_density(const DensityArgs& a, int B, cudaStream_t s);
+
+struct TemporalArgs {
+    BatchFrames frames; const mdgpu_unitcell_t* cells; int op; int atom[4]; float* out; uint32_t frame0;
+};
+void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s);
+
+// synth.cu
+void launch_synth_water(uint32_t seed, float L, uint32_t num_atoms, const float* d_base, size_t base_axis_stride, uint32_t frame_beg, uint32_t count,
+                        float* d_out, size_t frame_stride, size_t axis_stride, cudaStream_t s);
+
+}  // namespace mdg

@@ -1,0 +1,801 @@
+// plan.cu — host side of libmdgpu: the evaluation plan, the frame loop dispatched onto CUDA streams, the C ABI.
+//
+// This is the replacement of eval_properties (reference md_script.c:5730-5973): instead of one enkiTS task per frame range
+// evaluating one frame at a time on a CPU thread, frames are grouped into batches, each batch is enqueued on one of a small
+// ring of CUDA streams (H2D copy of the batch when the frames are on the host, then the property kernels), and integer
+// accumulators stay in HBM until mdgpu_plan_sync folds them into the md_script_property_data_t-shaped results.
+#include "common.cuh"
+#include "kernels.h"
+#include "synth.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <map>
+#include <algorithm>
+
+namespace mdg {
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_last_error = buf;
+    fprintf(stderr, "[mdgpu] error: %s\n", buf);
+    return code;
+}
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(MDGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+void note_launch(const char*, cudaStream_t) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+template <typename T> static cudaError_t dalloc(T** p, size_t n) { *p = nullptr; return n ? cudaMalloc((void**)p, n * sizeof(T)) : cudaSuccess; }
+template <typename T> static cudaError_t upload(T** p, const T* h, size_t n) {
+    cudaError_t e = dalloc(p, n); if (e != cudaSuccess || !n) return e;
+    return cudaMemcpy(*p, h, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+struct Prop {
+    std::string name; uint32_t op = 0;
+    std::vector<int32_t> h_idx[4]; int32_t* d_idx[4] = { nullptr, nullptr, nullptr, nullptr };
+    size_t n_struct = 0, struct_size = 0;
+    float cutoff_min = 0.f, cutoff_max = 0.f;
+    // device accumulators
+    unsigned long long* d_acc = nullptr;          // rdf: 1024 bins; density: 1024 fixed-point sums
+    uint32_t* d_vol = nullptr;                    // sdf: 128^3
+    unsigned long long* d_frame_total = nullptr;  // rdf / sdf: [num_frames]
+    uint32_t* d_frame_min = nullptr; uint32_t* d_frame_max = nullptr;             // rdf
+    unsigned long long* d_frame_min64 = nullptr; unsigned long long* d_frame_max64 = nullptr;   // density
+    uint32_t* d_keep = nullptr; unsigned long long* d_keep64 = nullptr;
+    float* d_temporal = nullptr;                  // [num_frames]
+    // sdf statics
+    int2* d_unwrap = nullptr; uint32_t n_unwrap = 0;
+    // density statics (from the initial frame's cell)
+    float rc = 0, re = 0, inv_ext = 0, min_point = 0; double dens_factor = 0;
+    // results
+    std::vector<float> values; mdgpu_property_data_t data{};
+    uint64_t frames_accumulated = 0;    // may be overridden after a cross-GPU reduction
+    bool frames_overridden = false;
+    bool is_dist() const { return op == MDGPU_OP_RDF || (op >= MDGPU_OP_DENSITY_X && op <= MDGPU_OP_DENSITY_Z); }
+    bool needs_cells() const { return op == MDGPU_OP_RDF || op == MDGPU_OP_SDF; }
+};
+
+struct PropScratch {   // per (stream slot, property)
+    FrameGeom* d_geom = nullptr; float* d_aabb = nullptr;
+    CellList trg{}, ref{};
+    uint32_t* d_frame_bins = nullptr; unsigned long long* d_frame_bins64 = nullptr;
+    float4* d_sdf_xyzw = nullptr; float* d_sdf_ref0 = nullptr; float* d_sdf_mats = nullptr;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; bool busy = false;
+    float* d_frames = nullptr; float* h_frames = nullptr;      // staging for host-resident frames
+    mdgpu_unitcell_t* d_cells = nullptr; mdgpu_unitcell_t* h_cells = nullptr;
+    int* d_err = nullptr;
+    std::vector<PropScratch> ps;
+    uint32_t pending_beg = 0, pending_cnt = 0;
+};
+
+struct TimedLaunch { cudaEvent_t a, b; };
+
+}  // namespace mdg
+
+using namespace mdg;
+
+struct mdgpu_plan {
+    int device = 0; int sm_count = 148;
+    size_t num_atoms = 0, num_frames = 0; size_t axis_stride = 0;   // staging layout: [frame][3][axis_stride]
+    uint32_t B = 148; uint32_t S = 2; uint32_t cell_cap = 0; bool keep = false; uint32_t rdf_variant = 0;
+    std::vector<float> h_mass; float* d_mass = nullptr;
+    std::vector<uint32_t> conn_off; std::vector<int32_t> conn_idx;
+    std::vector<Prop> props;
+    std::vector<Slot> slots;
+    bool have_init = false; float* d_init = nullptr; mdgpu_unitcell_t init_cell{};
+    std::vector<uint64_t> frame_mask; std::mutex mask_mutex;
+    std::atomic<bool> interrupt{false};
+    uint64_t next_slot = 0;
+    bool timing = false; std::vector<TimedLaunch> timed; double timed_ms = 0; uint64_t timed_n = 0;
+    bool tri_seen = false, ortho_seen = false;
+    cudaEvent_t t_begin = nullptr; std::vector<cudaEvent_t> t_end;
+};
+
+static int alloc_cell_list(CellList& cl, uint32_t B, uint32_t max_points, uint32_t cap) {
+    cl.max_points = max_points; cl.cap = cap;
+    CUDA_TRY(dalloc(&cl.sorted, (size_t)B * max_points));
+    CUDA_TRY(dalloc(&cl.scratch, (size_t)B * max_points));
+    CUDA_TRY(dalloc(&cl.cell_of, (size_t)B * max_points));
+    CUDA_TRY(dalloc(&cl.rank, (size_t)B * max_points));
+    CUDA_TRY(dalloc(&cl.cell_cnt, (size_t)B * (cap + 1)));
+    return 0;
+}
+static void free_cell_list(CellList& cl) { cudaFree(cl.sorted); cudaFree(cl.scratch); cudaFree(cl.cell_of); cudaFree(cl.rank); cudaFree(cl.cell_cnt); cl = CellList{}; }
+
+// BFS order in which md_util_unwrap_vec4(xyzw, NULL, count, bond, cell) visits atoms (md_util.c:8738-8819). NB the reference
+// walks the bonds of GLOBAL atoms 0..count-1 there (the local index is used as a global atom index); reproduced as is.
+static void build_unwrap_pairs(std::vector<int2>& out, size_t count, const std::vector<uint32_t>& off, const std::vector<int32_t>& idx) {
+    out.clear();
+    if (count == 0 || off.size() < 2) return;
+    const size_t atom_count = off.size() - 1;
+    std::vector<char> visited(atom_count + 1, 0);
+    std::vector<int> queue; queue.reserve(count + 1);
+    for (size_t i = 0; i < count; ++i) {
+        const int seed = (int)i;
+        if ((size_t)seed >= atom_count || visited[seed]) continue;
+        visited[seed] = 1; queue.clear(); queue.push_back(seed); size_t qh = 0;
+        while (qh < queue.size()) {
+            const int cur = queue[qh++];
+            for (uint32_t k = off[cur]; k < off[cur + 1]; ++k) {
+                const int next = idx[k];
+                if (next < 0 || (size_t)next >= count || visited[next]) continue;
+                out.push_back(make_int2(next, cur));
+                visited[next] = 1; queue.push_back(next);
+            }
+        }
+    }
+}
+
+static void destroy_plan(mdgpu_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (auto& s : p->slots) {
+        for (auto& ps : s.ps) {
+            cudaFree(ps.d_geom); cudaFree(ps.d_aabb); free_cell_list(ps.trg); free_cell_list(ps.ref);
+            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats);
+        }
+        cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames);
+        cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (auto& pr : p->props) {
+        for (int k = 0; k < 4; ++k) cudaFree(pr.d_idx[k]);
+        cudaFree(pr.d_acc); cudaFree(pr.d_vol); cudaFree(pr.d_frame_total); cudaFree(pr.d_frame_min); cudaFree(pr.d_frame_max);
+        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap);
+    }
+    for (auto& t : p->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    if (p->t_begin) cudaEventDestroy(p->t_begin);
+    for (auto e : p->t_end) cudaEventDestroy(e);
+    cudaFree(p->d_mass); cudaFree(p->d_init);
+    delete p;
+}
+
+extern "C" {
+
+const char* mdgpu_last_error(void) { return g_last_error.c_str(); }
+
+int mdgpu_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+uint64_t mdgpu_launch_count(bool reset) { return reset ? g_launches.exchange(0) : g_launches.load(); }
+
+mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_property_desc_t* props, size_t num_props, size_t num_frames,
+                              const mdgpu_plan_options_t* opts) {
+    if (!sys || !props || !num_props || !num_frames || !sys->num_atoms) { fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_create: invalid arguments"); return nullptr; }
+    mdgpu_plan_options_t o{}; if (opts) o = *opts;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { fail(MDGPU_ERR_CUDA, "no CUDA device available (libmdgpu has no CPU fallback)"); return nullptr; }
+    if (o.device < 0 || o.device >= ndev) { fail(MDGPU_ERR_INVALID_ARG, "device %d out of range (%d devices)", o.device, ndev); return nullptr; }
+    if (cudaSetDevice(o.device) != cudaSuccess) { fail(MDGPU_ERR_CUDA, "cudaSetDevice(%d) failed", o.device); return nullptr; }
+    mdgpu_plan* p = new mdgpu_plan();
+    p->device = o.device;
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, o.device);
+    p->num_atoms = sys->num_atoms; p->num_frames = num_frames;
+    p->axis_stride = (sys->num_atoms + 3) & ~(size_t)3;
+    p->B = o.batch_frames ? o.batch_frames : (uint32_t)p->sm_count;
+    if (p->B > 4096) p->B = 4096;
+    p->S = o.num_streams ? o.num_streams : 2; if (p->S > 8) p->S = 8;
+    p->keep = o.keep_frame_results != 0; p->cell_cap = o.cell_capacity; p->rdf_variant = o.rdf_variant;
+    p->h_mass.assign(sys->num_atoms, 1.0f);
+    if (sys->atom_mass) memcpy(p->h_mass.data(), sys->atom_mass, sizeof(float) * sys->num_atoms);
+    if (sys->bond_conn_offset && sys->bond_conn_offset_count) {
+        p->conn_off.assign(sys->bond_conn_offset, sys->bond_conn_offset + sys->bond_conn_offset_count);
+        const size_t nconn = p->conn_off.back();
+        if (sys->bond_conn_atom_idx) p->conn_idx.assign(sys->bond_conn_atom_idx, sys->bond_conn_atom_idx + nconn);
+    }
+    auto bail = [&](int code, const std::string& msg) -> mdgpu_plan* { fail(code, "%s", msg.c_str()); destroy_plan(p); return nullptr; };
+    if (upload(&p->d_mass, p->h_mass.data(), p->h_mass.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (masses)");
+
+    p->props.resize(num_props);
+    for (size_t i = 0; i < num_props; ++i) {
+        Prop& pr = p->props[i]; const mdgpu_property_desc_t& d = props[i];
+        pr.name = d.name ? d.name : ("prop" + std::to_string(i)); pr.op = d.op;
+        pr.n_struct = d.num_structures; pr.struct_size = d.structure_size; pr.cutoff_min = d.cutoff_min; pr.cutoff_max = d.cutoff_max;
+        for (int k = 0; k < 4; ++k) {
+            if (d.idx[k] && d.idx_count[k]) {
+                pr.h_idx[k].assign(d.idx[k], d.idx[k] + d.idx_count[k]);
+                for (int32_t a : pr.h_idx[k]) if (a < 0 || (size_t)a >= sys->num_atoms) return bail(MDGPU_ERR_INVALID_ARG, "property '" + pr.name + "': atom index out of range");
+                if (upload(&pr.d_idx[k], pr.h_idx[k].data(), pr.h_idx[k].size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (indices)");
+            }
+        }
+        cudaError_t e = cudaSuccess;
+        switch (pr.op) {
+        case MDGPU_OP_RDF:
+            if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty reference positions");   // internal_rdf :5396-5403
+            if (pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty target positions");
+            if (pr.cutoff_min < 0.0f || pr.cutoff_max <= pr.cutoff_min) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': Invalid cutoff");
+            if (pr.n_struct) return bail(MDGPU_ERR_UNSUPPORTED, "rdf '" + pr.name + "': centre-of-mass references with exclusion masks are not implemented yet");
+            e = dalloc(&pr.d_acc, MDGPU_DIST_BINS);
+            if (e == cudaSuccess) e = dalloc(&pr.d_frame_total, num_frames);
+            if (e == cudaSuccess) e = dalloc(&pr.d_frame_min, num_frames);
+            if (e == cudaSuccess) e = dalloc(&pr.d_frame_max, num_frames);
+            if (e == cudaSuccess && p->keep) e = dalloc(&pr.d_keep, num_frames * MDGPU_DIST_BINS);
+            pr.values.assign(2 * MDGPU_DIST_BINS, 0.0f);
+            pr.data.dim[0] = 1; pr.data.dim[1] = 2; pr.data.dim[2] = MDGPU_DIST_BINS; pr.data.dim[3] = 0;
+            break;
+        case MDGPU_OP_SDF: {
+            if (!pr.n_struct || !pr.struct_size || pr.h_idx[0].size() != pr.n_struct * pr.struct_size)
+                return bail(MDGPU_ERR_INVALID_ARG, "sdf '" + pr.name + "': reference structures must be num_structures x structure_size atoms");
+            if (pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "sdf '" + pr.name + "': The supplied target bitfield is empty");
+            if (p->conn_off.empty()) return bail(MDGPU_ERR_INVALID_ARG, "sdf '" + pr.name + "': Missing bond connectivity");   // md_util.c:8746
+            std::vector<int2> pairs; build_unwrap_pairs(pairs, pr.struct_size, p->conn_off, p->conn_idx);
+            pr.n_unwrap = (uint32_t)pairs.size();
+            e = upload(&pr.d_unwrap, pairs.data(), pairs.size());
+            if (e == cudaSuccess) e = dalloc(&pr.d_vol, (size_t)MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM);
+            if (e == cudaSuccess) e = dalloc(&pr.d_frame_total, num_frames);
+            pr.values.assign((size_t)MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM, 0.0f);
+            pr.data.dim[0] = 1; pr.data.dim[1] = MDGPU_VOL_DIM; pr.data.dim[2] = MDGPU_VOL_DIM; pr.data.dim[3] = MDGPU_VOL_DIM;
+            break; }
+        case MDGPU_OP_DENSITY_X: case MDGPU_OP_DENSITY_Y: case MDGPU_OP_DENSITY_Z:
+            if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "density '" + pr.name + "': empty selection");
+            e = dalloc(&pr.d_acc, MDGPU_DIST_BINS);
+            if (e == cudaSuccess) e = dalloc(&pr.d_frame_min64, num_frames);
+            if (e == cudaSuccess) e = dalloc(&pr.d_frame_max64, num_frames);
+            if (e == cudaSuccess && p->keep) e = dalloc(&pr.d_keep64, num_frames * MDGPU_DIST_BINS);
+            pr.values.assign(2 * MDGPU_DIST_BINS, 0.0f);
+            pr.data.dim[0] = 1; pr.data.dim[1] = 2; pr.data.dim[2] = MDGPU_DIST_BINS; pr.data.dim[3] = 0;
+            break;
+        case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
+            const int need = pr.op == MDGPU_OP_DISTANCE ? 2 : (pr.op == MDGPU_OP_ANGLE ? 3 : 4);
+            for (int k = 0; k < need; ++k) if (pr.h_idx[k].size() != 1)
+                return bail(MDGPU_ERR_UNSUPPORTED, "'" + pr.name + "': only single-atom arguments are implemented for distance/angle/dihedral");
+            e = dalloc(&pr.d_temporal, num_frames);
+            pr.values.assign(num_frames, 0.0f);
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break; }
+        default:
+            return bail(MDGPU_ERR_UNSUPPORTED, "property '" + pr.name + "': unsupported operation " + std::to_string(pr.op));
+        }
+        if (e != cudaSuccess) return bail(MDGPU_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(e));
+        pr.data.num_values = pr.values.size(); pr.data.values = pr.values.data();
+        pr.data.weights = pr.is_dist() ? pr.values.data() + MDGPU_DIST_BINS : nullptr;
+    }
+    p->frame_mask.assign((num_frames + 63) / 64, 0);
+    if (cudaMalloc((void**)&p->d_init, sizeof(float) * 3 * p->axis_stride) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (initial frame)");
+    if (mdgpu_plan_clear(p) != 0) { destroy_plan(p); return nullptr; }
+    return p;
+}
+
+void mdgpu_plan_destroy(mdgpu_plan* plan) { destroy_plan(plan); }
+
+int mdgpu_plan_clear(mdgpu_plan* p) {
+    if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (auto& s : p->slots) s.busy = false;
+    for (auto& pr : p->props) {
+        if (pr.d_acc) CUDA_TRY(cudaMemset(pr.d_acc, 0, sizeof(unsigned long long) * MDGPU_DIST_BINS));
+        if (pr.d_vol) CUDA_TRY(cudaMemset(pr.d_vol, 0, sizeof(uint32_t) * MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM));
+        if (pr.d_frame_total) CUDA_TRY(cudaMemset(pr.d_frame_total, 0, sizeof(unsigned long long) * p->num_frames));
+        if (pr.d_frame_min) CUDA_TRY(cudaMemset(pr.d_frame_min, 0, sizeof(uint32_t) * p->num_frames));
+        if (pr.d_frame_max) CUDA_TRY(cudaMemset(pr.d_frame_max, 0, sizeof(uint32_t) * p->num_frames));
+        if (pr.d_frame_min64) CUDA_TRY(cudaMemset(pr.d_frame_min64, 0, sizeof(unsigned long long) * p->num_frames));
+        if (pr.d_frame_max64) CUDA_TRY(cudaMemset(pr.d_frame_max64, 0, sizeof(unsigned long long) * p->num_frames));
+        if (pr.d_temporal) CUDA_TRY(cudaMemset(pr.d_temporal, 0, sizeof(float) * p->num_frames));
+        if (pr.d_keep) CUDA_TRY(cudaMemset(pr.d_keep, 0, sizeof(uint32_t) * p->num_frames * MDGPU_DIST_BINS));
+        if (pr.d_keep64) CUDA_TRY(cudaMemset(pr.d_keep64, 0, sizeof(unsigned long long) * p->num_frames * MDGPU_DIST_BINS));
+        std::fill(pr.values.begin(), pr.values.end(), 0.0f);
+        if (pr.is_dist()) std::fill(pr.values.begin() + MDGPU_DIST_BINS, pr.values.end(), 1.0f);   // allocate_property_data :5613-5618
+        pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;                                 // clear_property_data :5726-5727
+        pr.data.min_range[0] = pr.data.min_range[1] = pr.data.max_range[0] = pr.data.max_range[1] = 0.0f;
+        pr.frames_accumulated = 0; pr.frames_overridden = false; pr.data.frames_accumulated = 0;
+    }
+    { std::lock_guard<std::mutex> lk(p->mask_mutex); std::fill(p->frame_mask.begin(), p->frame_mask.end(), 0ull); }
+    p->interrupt = false;
+    p->timed_ms = 0; p->timed_n = 0;
+    return 0;
+}
+
+int mdgpu_plan_set_initial_frame(mdgpu_plan* p, const float* x, const float* y, const float* z, const mdgpu_unitcell_t* cell) {
+    if (!p || !x || !y || !z || !cell) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_set_initial_frame: null argument");
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaMemcpy(p->d_init, x, sizeof(float) * p->num_atoms, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p->d_init + p->axis_stride, y, sizeof(float) * p->num_atoms, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p->d_init + 2 * p->axis_stride, z, sizeof(float) * p->num_atoms, cudaMemcpyHostToDevice));
+    p->init_cell = *cell; p->have_init = true;
+    for (auto& pr : p->props) {
+        if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
+            // reference point / extent from the initial frame's unit cell (md_script_functions.inl:4871-4903, :4930-4933)
+            const int axis = (int)pr.op - MDGPU_OP_DENSITY_X;
+            const float A[3][3] = { { (float)cell->x, 0.f, 0.f }, { (float)cell->xy, (float)cell->y, 0.f }, { (float)cell->xz, (float)cell->yz, (float)cell->z } };
+            float rc[3], re[3];
+            for (int r = 0; r < 3; ++r) { float v = A[0][r] * 0.5f; v = v + A[1][r] * 0.5f; v = v + A[2][r] * 0.5f; rc[r] = v; re[r] = A[r][r]; }
+            pr.rc = rc[axis]; pr.re = re[axis];
+            pr.inv_ext = re[axis] > 0.0f ? 1.0f / re[axis] : 0.0f;
+            pr.min_point = rc[axis] - re[axis] * 0.5f;
+            const float vol = (re[0] * re[1] * re[2]) / (float)MDGPU_DIST_BINS;
+            const double slice_vol = vol;
+            pr.dens_factor = 1660.5390666 / slice_vol;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// slot set-up (lazy: needs the initial frame for the default cell capacity)
+// ---------------------------------------------------------------------------------------------------------------
+static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool need_host_staging) {
+    if (p->slots.empty()) {
+        // default cell capacity: twice the grid the reference would build for the first frame, per property cutoff
+        uint32_t cap = p->cell_cap;
+        if (!cap) {
+            uint64_t need = 4096;
+            for (auto& pr : p->props) if (pr.needs_cells()) {
+                FrameGeom g; host_frame_geom(&g, first_cell, pr.cutoff_max, pr.cutoff_max, nullptr, 0xffffffffu);
+                need = std::max<uint64_t>(need, 2ull * std::max<uint64_t>(g.num_cells, g.num_home) + 2);
+            }
+            cap = (uint32_t)std::min<uint64_t>(need, 1u << 26);
+            p->cell_cap = cap;
+        }
+        p->slots.resize(p->S);
+        for (auto& s : p->slots) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            CUDA_TRY(dalloc(&s.d_cells, p->B));
+            CUDA_TRY(cudaMallocHost((void**)&s.h_cells, sizeof(mdgpu_unitcell_t) * p->B));
+            CUDA_TRY(dalloc(&s.d_err, 1)); CUDA_TRY(cudaMemset(s.d_err, 0, sizeof(int)));
+            s.ps.resize(p->props.size());
+            for (size_t i = 0; i < p->props.size(); ++i) {
+                Prop& pr = p->props[i]; PropScratch& ps = s.ps[i];
+                if (pr.needs_cells()) {
+                    CUDA_TRY(dalloc(&ps.d_geom, p->B)); CUDA_TRY(dalloc(&ps.d_aabb, (size_t)6 * p->B));
+                    int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)pr.h_idx[1].size(), cap); if (rc) return rc;
+                }
+                if (pr.op == MDGPU_OP_RDF) {
+                    int rc = alloc_cell_list(ps.ref, p->B, (uint32_t)pr.h_idx[0].size(), cap); if (rc) return rc;
+                    CUDA_TRY(dalloc(&ps.d_frame_bins, (size_t)p->B * MDGPU_DIST_BINS));
+                } else if (pr.op == MDGPU_OP_SDF) {
+                    CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * (pr.n_struct + 1) * pr.struct_size));
+                    CUDA_TRY(dalloc(&ps.d_sdf_ref0, (size_t)p->B * 20));
+                    CUDA_TRY(dalloc(&ps.d_sdf_mats, (size_t)p->B * pr.n_struct * 20));
+                } else if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
+                    CUDA_TRY(dalloc(&ps.d_frame_bins64, (size_t)p->B * MDGPU_DIST_BINS));
+                }
+            }
+        }
+    }
+    if (need_host_staging) for (auto& s : p->slots) if (!s.d_frames) {
+        CUDA_TRY(dalloc(&s.d_frames, (size_t)p->B * 3 * p->axis_stride));
+        CUDA_TRY(cudaMallocHost((void**)&s.h_frames, sizeof(float) * (size_t)p->B * 3 * p->axis_stride));
+    }
+    return 0;
+}
+
+// enqueue the property kernels of one batch whose frames are already in device memory
+static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t frame0) {
+    const int B = (int)fr.count;
+    // all frames of a batch must agree on ortho vs triclinic (kernel template parameter)
+    bool tri = (s.h_cells[0].flags & MDGPU_CELL_TRICLINIC) != 0;
+    for (int i = 1; i < B; ++i) if (((s.h_cells[i].flags & MDGPU_CELL_TRICLINIC) != 0) != tri)
+        return fail(MDGPU_ERR_UNSUPPORTED, "frames %u..%u mix orthorhombic and triclinic unit cells inside one batch", frame0, frame0 + B - 1);
+    CUDA_TRY(cudaMemcpyAsync(s.d_cells, s.h_cells, sizeof(mdgpu_unitcell_t) * B, cudaMemcpyHostToDevice, s.stream));
+    bool all_pbc = true; for (int i = 0; i < B; ++i) all_pbc = all_pbc && ((s.h_cells[i].flags & MDGPU_CELL_PBC_ALL) == MDGPU_CELL_PBC_ALL);
+    for (size_t i = 0; i < p->props.size(); ++i) {
+        Prop& pr = p->props[i]; PropScratch& ps = s.ps[i];
+        if (pr.needs_cells()) {
+            const float* aabb = nullptr;
+            if (!all_pbc) { launch_aabb(fr, pr.d_idx[1], (uint32_t)pr.h_idx[1].size(), ps.d_aabb, s.stream); aabb = ps.d_aabb; }
+            launch_geom(s.d_cells, aabb, ps.d_geom, (double)pr.cutoff_max, (double)pr.cutoff_max, p->cell_cap, B, s.d_err, s.stream);
+            launch_cell_list(0, fr, pr.d_idx[1], nullptr, (uint32_t)pr.h_idx[1].size(), ps.d_geom, ps.trg, 0, s.stream);
+        }
+        switch (pr.op) {
+        case MDGPU_OP_RDF: {
+            launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_geom, ps.ref, 0, s.stream);
+            RdfArgs a{};
+            a.geom = ps.d_geom; a.trg = ps.trg; a.ref = ps.ref;
+            a.inv_cutoff_range = 1.0f / (pr.cutoff_max - pr.cutoff_min);                 // before the clamp (compute_rdf :5264)
+            a.min_cutoff = pr.cutoff_min > 1e-3f ? pr.cutoff_min : 1e-3f;                 // :5269
+            a.min_r2 = a.min_cutoff * a.min_cutoff;                                       // rdf_cb :5233
+            a.frame_bins = ps.d_frame_bins; a.excl_off = nullptr; a.excl_idx = nullptr; a.frame0 = frame0;
+            a.acc = pr.d_acc; a.frame_total = pr.d_frame_total; a.frame_min = pr.d_frame_min; a.frame_max = pr.d_frame_max; a.keep = pr.d_keep;
+            TimedLaunch tl{};
+            if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); }
+            launch_rdf(a, B, tri, (int)p->rdf_variant, p->sm_count, s.stream, p->timing ? &tl.a : nullptr, p->timing ? &tl.b : nullptr);
+            if (p->timing) p->timed.push_back(tl);
+            break; }
+        case MDGPU_OP_SDF: {
+            if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "sdf '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
+            if (tri) return fail(MDGPU_ERR_UNSUPPORTED, "sdf '%s': triclinic unit cells are not implemented yet", pr.name.c_str());
+            SdfArgs a{};
+            a.geom = ps.d_geom; a.trg = ps.trg; a.frames = fr; a.cells = s.d_cells;
+            a.init_xyz = p->d_init; a.init_axis_stride = p->axis_stride; a.mass = p->d_mass;
+            a.struct_idx = pr.d_idx[0]; a.n_struct = (uint32_t)pr.n_struct; a.struct_size = (uint32_t)pr.struct_size;
+            a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap; a.cutoff = pr.cutoff_max;
+            a.scratch_xyzw = ps.d_sdf_xyzw; a.ref0 = ps.d_sdf_ref0; a.matrices = ps.d_sdf_mats;
+            a.vol = pr.d_vol; a.frame_total = pr.d_frame_total; a.frame0 = frame0;
+            launch_sdf(a, B, s.stream);
+            break; }
+        case MDGPU_OP_DENSITY_X: case MDGPU_OP_DENSITY_Y: case MDGPU_OP_DENSITY_Z: {
+            if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "density '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
+            DensityArgs a{};
+            a.frames = fr; a.idx = pr.d_idx[0]; a.n = (uint32_t)pr.h_idx[0].size(); a.mass = p->d_mass; a.axis = (int)pr.op - MDGPU_OP_DENSITY_X;
+            a.rc = pr.rc; a.re = pr.re; a.inv_ext = pr.inv_ext; a.min_point = pr.min_point;
+            a.acc = pr.d_acc; a.frame_bins = ps.d_frame_bins64; a.frame_min = pr.d_frame_min64; a.frame_max = pr.d_frame_max64; a.keep = pr.d_keep64; a.frame0 = frame0;
+            launch_density(a, B, s.stream);
+            break; }
+        case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
+            TemporalArgs a{};
+            a.frames = fr; a.cells = s.d_cells; a.op = (int)pr.op; a.out = pr.d_temporal; a.frame0 = frame0;
+            for (int k = 0; k < 4; ++k) a.atom[k] = pr.h_idx[k].empty() ? 0 : pr.h_idx[k][0];
+            launch_temporal(a, B, s.stream);
+            break; }
+        default: break;
+        }
+        pr.frames_accumulated += (uint64_t)B;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s.done, s.stream));
+    s.busy = true; s.pending_beg = frame0; s.pending_cnt = (uint32_t)B;
+    return 0;
+}
+
+static void mark_frames(mdgpu_plan* p, uint32_t beg, uint32_t cnt) {
+    std::lock_guard<std::mutex> lk(p->mask_mutex);
+    for (uint32_t f = beg; f < beg + cnt && f < p->num_frames; ++f) p->frame_mask[f >> 6] |= (1ull << (f & 63));
+}
+
+// wait until a slot's previous batch has finished (its staging buffers become reusable); sets the frame-mask bits
+static int retire_slot(mdgpu_plan* p, Slot& s) {
+    if (!s.busy) return 0;
+    CUDA_TRY(cudaEventSynchronize(s.done));
+    s.busy = false;
+    mark_frames(p, s.pending_beg, s.pending_cnt);
+    return 0;
+}
+
+static const mdgpu_unitcell_t* cell_at(const mdgpu_unitcell_t* cells, size_t stride_bytes, size_t i) {
+    return (const mdgpu_unitcell_t*)((const char*)cells + i * (stride_bytes ? stride_bytes : 0));
+}
+
+extern "C" {
+
+int mdgpu_eval_device_frames(mdgpu_plan* p, const float* d_xyz, size_t frame_stride, size_t axis_stride,
+                             const mdgpu_unitcell_t* cells, size_t cell_stride_bytes, uint32_t frame_beg, uint32_t count) {
+    if (!p || !d_xyz || !cells) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_eval_device_frames: null argument");
+    if ((size_t)frame_beg + count > p->num_frames) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Invalid frame range");   // md_script.c:6594-6597
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (!count) return 0;
+    int rc = ensure_slots(p, cell_at(cells, cell_stride_bytes, 0), false); if (rc) return rc;
+    for (uint32_t b0 = 0; b0 < count; b0 += p->B) {
+        if (p->interrupt.load()) return fail(MDGPU_ERR_INTERRUPTED, "evaluation interrupted");
+        const uint32_t nb = std::min(p->B, count - b0);
+        Slot& s = p->slots[p->next_slot++ % p->slots.size()];
+        rc = retire_slot(p, s); if (rc) return rc;
+        for (uint32_t i = 0; i < nb; ++i) s.h_cells[i] = *cell_at(cells, cell_stride_bytes, b0 + i);
+        BatchFrames fr{ d_xyz + (size_t)b0 * frame_stride, frame_stride, axis_stride, nb };
+        rc = enqueue_batch(p, s, fr, frame_beg + b0); if (rc) return rc;
+    }
+    return 0;
+}
+
+int mdgpu_eval_host_frames(mdgpu_plan* p, const float* h_xyz, size_t frame_stride, size_t axis_stride,
+                           const mdgpu_unitcell_t* cells, size_t cell_stride_bytes, uint32_t frame_beg, uint32_t count) {
+    if (!p || !h_xyz || !cells) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_eval_host_frames: null argument");
+    if ((size_t)frame_beg + count > p->num_frames) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Invalid frame range");
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (!count) return 0;
+    int rc = ensure_slots(p, cell_at(cells, cell_stride_bytes, 0), true); if (rc) return rc;
+    cudaPointerAttributes attr{}; bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, h_xyz) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost); else cudaGetLastError();
+    const size_t N = p->num_atoms, AS = p->axis_stride;
+    for (uint32_t b0 = 0; b0 < count; b0 += p->B) {
+        if (p->interrupt.load()) return fail(MDGPU_ERR_INTERRUPTED, "evaluation interrupted");
+        const uint32_t nb = std::min(p->B, count - b0);
+        Slot& s = p->slots[p->next_slot++ % p->slots.size()];
+        rc = retire_slot(p, s); if (rc) return rc;
+        for (uint32_t i = 0; i < nb; ++i) s.h_cells[i] = *cell_at(cells, cell_stride_bytes, b0 + i);
+        const float* src = h_xyz + (size_t)b0 * frame_stride;
+        if (pinned) {
+            // pinned source: DMA straight from the caller's buffer
+            if (frame_stride == 3 * axis_stride) {
+                CUDA_TRY(cudaMemcpy2DAsync(s.d_frames, sizeof(float) * AS, src, sizeof(float) * axis_stride, sizeof(float) * N,
+                                           (size_t)nb * 3, cudaMemcpyHostToDevice, s.stream));
+            } else {
+                for (uint32_t i = 0; i < nb; ++i)
+                    CUDA_TRY(cudaMemcpy2DAsync(s.d_frames + (size_t)i * 3 * AS, sizeof(float) * AS, src + (size_t)i * frame_stride, sizeof(float) * axis_stride,
+                                               sizeof(float) * N, 3, cudaMemcpyHostToDevice, s.stream));
+            }
+        } else {
+            for (uint32_t i = 0; i < nb; ++i) for (int ax = 0; ax < 3; ++ax)
+                memcpy(s.h_frames + ((size_t)i * 3 + ax) * AS, src + (size_t)i * frame_stride + (size_t)ax * axis_stride, sizeof(float) * N);
+            CUDA_TRY(cudaMemcpyAsync(s.d_frames, s.h_frames, sizeof(float) * (size_t)nb * 3 * AS, cudaMemcpyHostToDevice, s.stream));
+        }
+        BatchFrames fr{ s.d_frames, 3 * AS, AS, nb };
+        rc = enqueue_batch(p, s, fr, frame_beg + b0); if (rc) return rc;
+    }
+    return 0;
+}
+
+int mdgpu_eval_trajectory(mdgpu_plan* p, const mdgpu_trajectory_i* traj, uint32_t frame_beg, uint32_t frame_end, uint32_t loader_threads) {
+    if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
+    if (!traj || !traj->inst || !traj->get_header || !traj->init_reader) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Trajectory was null");
+    mdgpu_trajectory_header_t hdr{};
+    if (!traj->get_header(traj->inst, &hdr) || hdr.num_frames == 0) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Trajectory was empty");
+    if (frame_beg > frame_end || frame_end > hdr.num_frames || frame_end > p->num_frames) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Invalid frame range");
+    if (hdr.num_atoms != p->num_atoms) return fail(MDGPU_ERR_INVALID_ARG, "trajectory has %zu atoms, plan has %zu", hdr.num_atoms, p->num_atoms);
+    CUDA_TRY(cudaSetDevice(p->device));
+    const uint32_t T = std::max(1u, std::min(loader_threads ? loader_threads : 4u, 64u));
+    std::vector<mdgpu_trajectory_reader_i> readers(T);
+    for (uint32_t t = 0; t < T; ++t) { memset(&readers[t], 0, sizeof(readers[t])); if (!traj->init_reader(&readers[t], traj->inst)) return fail(MDGPU_ERR_FRAME_SOURCE, "Failed to initialize trajectory reader for evaluation"); }
+    auto free_readers = [&]() { for (auto& r : readers) if (r.free) r.free(&r); };
+    const size_t AS = p->axis_stride;
+    if (!p->have_init) {   // initial configuration = frame 0 (md_script.c:5808)
+        std::vector<float> tmp(3 * AS); mdgpu_frame_header_t fh{};
+        if (!readers[0].load_frame(readers[0].inst, 0, &fh, tmp.data(), tmp.data() + AS, tmp.data() + 2 * AS)) { free_readers(); return fail(MDGPU_ERR_FRAME_SOURCE, "Failed to load frame during evaluation"); }
+        int rc = mdgpu_plan_set_initial_frame(p, tmp.data(), tmp.data() + AS, tmp.data() + 2 * AS, &fh.unitcell); if (rc) { free_readers(); return rc; }
+    }
+    int rc = 0; bool slots_ready = false;
+    for (uint32_t b0 = frame_beg; b0 < frame_end && !rc; b0 += p->B) {
+        if (p->interrupt.load()) { rc = fail(MDGPU_ERR_INTERRUPTED, "evaluation interrupted"); break; }
+        const uint32_t nb = std::min(p->B, frame_end - b0);
+        if (!slots_ready) {   // need one header for the cell capacity
+            mdgpu_frame_header_t fh{}; if (!readers[0].load_frame(readers[0].inst, b0, &fh, nullptr, nullptr, nullptr)) fh.unitcell = p->init_cell;
+            rc = ensure_slots(p, &fh.unitcell, true); if (rc) break; slots_ready = true;
+        }
+        Slot& s = p->slots[p->next_slot++ % p->slots.size()];
+        rc = retire_slot(p, s); if (rc) break;
+        std::atomic<int> failed{0};
+        auto work = [&](uint32_t t) {
+            for (uint32_t i = t; i < nb; i += T) {
+                mdgpu_frame_header_t fh{};
+                float* dst = s.h_frames + (size_t)i * 3 * AS;
+                if (!readers[t].load_frame(readers[t].inst, (int64_t)(b0 + i), &fh, dst, dst + AS, dst + 2 * AS)) { failed = 1; return; }
+                s.h_cells[i] = fh.unitcell;
+            }
+        };
+        if (T == 1) work(0);
+        else { std::vector<std::thread> th; for (uint32_t t = 0; t < T; ++t) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+        if (failed) { rc = fail(MDGPU_ERR_FRAME_SOURCE, "Failed to load frame during evaluation"); break; }
+        cudaError_t e = cudaMemcpyAsync(s.d_frames, s.h_frames, sizeof(float) * (size_t)nb * 3 * AS, cudaMemcpyHostToDevice, s.stream);
+        if (e != cudaSuccess) { rc = fail(MDGPU_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+        BatchFrames fr{ s.d_frames, 3 * AS, AS, nb };
+        rc = enqueue_batch(p, s, fr, b0);
+    }
+    free_readers();
+    return rc;
+}
+
+void mdgpu_plan_interrupt(mdgpu_plan* p) { if (p) p->interrupt = true; }
+
+static double sphere_volume(double r) { return (4.0 / 3.0) * 3.1415926535897932 * (r * r * r); }
+
+int mdgpu_plan_sync(mdgpu_plan* p) {
+    if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
+    CUDA_TRY(cudaSetDevice(p->device));
+    for (auto& s : p->slots) { int rc = retire_slot(p, s); if (rc) return rc; }
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (auto& s : p->slots) {
+        int err = 0; CUDA_TRY(cudaMemcpy(&err, s.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) { cudaMemset(s.d_err, 0, sizeof(int)); return fail(err, err == MDGPU_ERR_CAPACITY ? "a frame needs more cells than the plan's cell capacity (%u); raise mdgpu_plan_options_t.cell_capacity" : "device-side error %d", err == MDGPU_ERR_CAPACITY ? p->cell_cap : (uint32_t)err); }
+    }
+    for (auto& t : p->timed) { float ms = 0; if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { p->timed_ms += ms; p->timed_n += 1; } cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    p->timed.clear();
+
+    // evaluated frames
+    std::vector<uint32_t> done;
+    { std::lock_guard<std::mutex> lk(p->mask_mutex);
+      for (size_t f = 0; f < p->num_frames; ++f) if (p->frame_mask[f >> 6] >> (f & 63) & 1ull) done.push_back((uint32_t)f); }
+    const size_t F = p->num_frames;
+    for (auto& pr : p->props) {
+        const uint64_t n = pr.frames_overridden ? pr.frames_accumulated : (uint64_t)done.size();
+        pr.data.frames_accumulated = n;
+        if (pr.op == MDGPU_OP_RDF) {
+            std::vector<unsigned long long> acc(MDGPU_DIST_BINS), tot(F); std::vector<uint32_t> mn(F), mx(F);
+            CUDA_TRY(cudaMemcpy(acc.data(), pr.d_acc, sizeof(unsigned long long) * MDGPU_DIST_BINS, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(tot.data(), pr.d_frame_total, sizeof(unsigned long long) * F, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(mn.data(), pr.d_frame_min, sizeof(uint32_t) * F, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(mx.data(), pr.d_frame_max, sizeof(uint32_t) * F, cudaMemcpyDeviceToHost));
+            // mean of the per-frame integer bins: exact sum, one division (the reference keeps a float cumulative moving
+            // average, md_script.c:5912-5921, which drifts by ~sqrt(n)*6e-8 from this value)
+            for (int b = 0; b < MDGPU_DIST_BINS; ++b) pr.values[b] = n ? (float)((double)acc[b] / (double)n) : 0.0f;
+            pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;
+            for (uint32_t f : done) { pr.data.min_value = std::min(pr.data.min_value, (float)mn[f]); pr.data.max_value = std::max(pr.data.max_value, (float)mx[f]); }
+            // weights of the last evaluated frame (the reference copies "whichever frame finished last", :5924); compute_rdf :5323-5337
+            if (!done.empty()) {
+                const float min_cutoff = pr.cutoff_min > 1e-3f ? pr.cutoff_min : 1e-3f, max_cutoff = pr.cutoff_max;
+                const double total_vol = sphere_volume(max_cutoff) - sphere_volume(min_cutoff);
+                const double ref_rho = (double)tot[done.back()] / total_vol;
+                const float drf = (max_cutoff - min_cutoff) / (float)MDGPU_DIST_BINS; const double dr = drf;
+                double prev = 0;
+                for (int64_t i = 0; i < MDGPU_DIST_BINS; ++i) { const double sv = sphere_volume(min_cutoff + (i + 0.5) * dr); const double bv = sv - prev; prev = sv; pr.values[MDGPU_DIST_BINS + i] = (float)(ref_rho * bv); }
+            }
+            pr.data.min_range[0] = pr.cutoff_min; pr.data.max_range[0] = pr.cutoff_max;   // value_range set by internal_rdf :5415
+        } else if (pr.op == MDGPU_OP_SDF) {
+            std::vector<uint32_t> vol(pr.values.size());
+            CUDA_TRY(cudaMemcpy(vol.data(), pr.d_vol, sizeof(uint32_t) * vol.size(), cudaMemcpyDeviceToHost));
+            for (size_t v = 0; v < vol.size(); ++v) pr.values[v] = n ? (float)((double)vol[v] / (double)n) : 0.0f;
+            // min_value / max_value are never updated for volumes in the reference (md_script.c:5936-5956)
+        } else if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
+            std::vector<unsigned long long> acc(MDGPU_DIST_BINS), mn(F), mx(F);
+            CUDA_TRY(cudaMemcpy(acc.data(), pr.d_acc, sizeof(unsigned long long) * MDGPU_DIST_BINS, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(mn.data(), pr.d_frame_min64, sizeof(unsigned long long) * F, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(mx.data(), pr.d_frame_max64, sizeof(unsigned long long) * F, cudaMemcpyDeviceToHost));
+            const double unit = 1.0 / 16777216.0;
+            for (int b = 0; b < MDGPU_DIST_BINS; ++b) pr.values[b] = n ? (float)(((double)acc[b] * unit / (double)n) * pr.dens_factor) : 0.0f;
+            for (int b = 0; b < MDGPU_DIST_BINS; ++b) pr.values[MDGPU_DIST_BINS + b] = 1.0f;
+            pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;
+            for (uint32_t f : done) {
+                pr.data.min_value = std::min(pr.data.min_value, (float)((double)(float)((double)mn[f] * unit) * pr.dens_factor));
+                pr.data.max_value = std::max(pr.data.max_value, (float)((double)(float)((double)mx[f] * unit) * pr.dens_factor));
+            }
+            const float rad = pr.re * 0.5f;   // value_range {-rad, rad} (:4983-4995)
+            pr.data.min_range[0] = -rad; pr.data.max_range[0] = rad;
+        } else {
+            CUDA_TRY(cudaMemcpy(pr.values.data(), pr.d_temporal, sizeof(float) * F, cudaMemcpyDeviceToHost));
+            pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;
+            for (uint32_t f : done) { pr.data.min_value = std::min(pr.data.min_value, pr.values[f]); pr.data.max_value = std::max(pr.data.max_value, pr.values[f]); }
+            if (pr.op == MDGPU_OP_DISTANCE) { pr.data.min_range[0] = 0.0f; pr.data.max_range[0] = pr.data.max_value; }   // value_range {0, FLT_MAX} (:3884)
+            else { pr.data.min_range[0] = pr.data.min_value; pr.data.max_range[0] = pr.data.max_value; }
+        }
+    }
+    return 0;
+}
+
+size_t mdgpu_plan_property_count(const mdgpu_plan* p) { return p ? p->props.size() : 0; }
+
+int mdgpu_plan_property_index(const mdgpu_plan* p, const char* name) {
+    if (!p || !name) return -1;
+    for (size_t i = 0; i < p->props.size(); ++i) if (p->props[i].name == name) return (int)i;
+    return -1;
+}
+
+int mdgpu_plan_property_data(mdgpu_plan* p, size_t prop, mdgpu_property_data_t* out) {
+    if (!p || !out || prop >= p->props.size()) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_property_data: invalid argument");
+    int rc = mdgpu_plan_sync(p); if (rc) return rc;
+    *out = p->props[prop].data;
+    return 0;
+}
+
+int mdgpu_plan_property_counts(mdgpu_plan* p, size_t prop, uint64_t* out, size_t out_len) {
+    if (!p || !out || prop >= p->props.size()) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_property_counts: invalid argument");
+    int rc = mdgpu_plan_sync(p); if (rc) return rc;
+    Prop& pr = p->props[prop];
+    if (pr.d_acc) {
+        if (out_len < MDGPU_DIST_BINS) return fail(MDGPU_ERR_INVALID_ARG, "output too small");
+        CUDA_TRY(cudaMemcpy(out, pr.d_acc, sizeof(uint64_t) * MDGPU_DIST_BINS, cudaMemcpyDeviceToHost));
+    } else if (pr.d_vol) {
+        const size_t nv = (size_t)MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM;
+        if (out_len < nv) return fail(MDGPU_ERR_INVALID_ARG, "output too small");
+        std::vector<uint32_t> v(nv); CUDA_TRY(cudaMemcpy(v.data(), pr.d_vol, sizeof(uint32_t) * nv, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < nv; ++i) out[i] = v[i];
+    } else return fail(MDGPU_ERR_UNSUPPORTED, "property '%s' has no integer accumulator", pr.name.c_str());
+    return 0;
+}
+
+int mdgpu_plan_property_frame_counts(mdgpu_plan* p, size_t prop, uint32_t frame, uint32_t* out_bins, uint64_t* out_total) {
+    if (!p || prop >= p->props.size() || frame >= p->num_frames) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_property_frame_counts: invalid argument");
+    int rc = mdgpu_plan_sync(p); if (rc) return rc;
+    Prop& pr = p->props[prop];
+    if (pr.op != MDGPU_OP_RDF) return fail(MDGPU_ERR_UNSUPPORTED, "per-frame counts are kept for rdf properties only");
+    if (out_bins) {
+        if (!pr.d_keep) return fail(MDGPU_ERR_INVALID_ARG, "plan was created without keep_frame_results");
+        CUDA_TRY(cudaMemcpy(out_bins, pr.d_keep + (size_t)frame * MDGPU_DIST_BINS, sizeof(uint32_t) * MDGPU_DIST_BINS, cudaMemcpyDeviceToHost));
+    }
+    if (out_total) { unsigned long long t = 0; CUDA_TRY(cudaMemcpy(&t, pr.d_frame_total + frame, sizeof(t), cudaMemcpyDeviceToHost)); *out_total = t; }
+    return 0;
+}
+
+int mdgpu_plan_frame_mask(mdgpu_plan* p, uint64_t* out_words, size_t num_words) {
+    if (!p || !out_words) return fail(MDGPU_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(p->mask_mutex);
+    for (size_t i = 0; i < num_words; ++i) out_words[i] = i < p->frame_mask.size() ? p->frame_mask[i] : 0ull;
+    return 0;
+}
+
+int mdgpu_plan_property_accum_ptr(mdgpu_plan* p, size_t prop, void** d_ptr, size_t* bytes, uint32_t* elem_bytes) {
+    if (!p || prop >= p->props.size() || !d_ptr || !bytes) return fail(MDGPU_ERR_INVALID_ARG, "invalid argument");
+    Prop& pr = p->props[prop];
+    if (pr.d_acc) { *d_ptr = pr.d_acc; *bytes = sizeof(unsigned long long) * MDGPU_DIST_BINS; if (elem_bytes) *elem_bytes = 8; }
+    else if (pr.d_vol) { *d_ptr = pr.d_vol; *bytes = sizeof(uint32_t) * MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM; if (elem_bytes) *elem_bytes = 4; }
+    else return fail(MDGPU_ERR_UNSUPPORTED, "property '%s' has no integer accumulator", pr.name.c_str());
+    return 0;
+}
+
+int mdgpu_plan_set_frames_accumulated(mdgpu_plan* p, size_t prop, uint64_t frames) {
+    if (!p || prop >= p->props.size()) return fail(MDGPU_ERR_INVALID_ARG, "invalid argument");
+    p->props[prop].frames_accumulated = frames; p->props[prop].frames_overridden = true;
+    return 0;
+}
+
+int mdgpu_plan_enable_kernel_timing(mdgpu_plan* p, int enable) { if (!p) return MDGPU_ERR_INVALID_ARG; p->timing = enable != 0; return 0; }
+
+int mdgpu_plan_kernel_time_ms(mdgpu_plan* p, const char* kernel, double* total_ms, uint64_t* launches) {
+    if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
+    (void)kernel;   // only k_rdf_pairs is instrumented
+    int rc = mdgpu_plan_sync(p); if (rc) return rc;
+    if (total_ms) *total_ms = p->timed_ms; if (launches) *launches = p->timed_n;
+    return 0;
+}
+
+int mdgpu_plan_timer_begin(mdgpu_plan* p) {
+    if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
+    CUDA_TRY(cudaSetDevice(p->device));
+    for (auto& s : p->slots) { int rc = retire_slot(p, s); if (rc) return rc; }
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (!p->t_begin) CUDA_TRY(cudaEventCreate(&p->t_begin));
+    // the device is idle: an event on the legacy default stream is reached immediately and precedes everything enqueued later
+    CUDA_TRY(cudaEventRecord(p->t_begin, p->slots.empty() ? (cudaStream_t)0 : p->slots[0].stream));
+    return 0;
+}
+
+int mdgpu_plan_timer_end(mdgpu_plan* p, double* elapsed_ms) {
+    if (!p || !elapsed_ms || !p->t_begin) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_timer_end without _begin");
+    CUDA_TRY(cudaSetDevice(p->device));
+    while (p->t_end.size() < p->slots.size()) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); p->t_end.push_back(e); }
+    for (size_t i = 0; i < p->slots.size(); ++i) CUDA_TRY(cudaEventRecord(p->t_end[i], p->slots[i].stream));
+    double best = 0.0;
+    for (size_t i = 0; i < p->slots.size(); ++i) {
+        CUDA_TRY(cudaEventSynchronize(p->t_end[i]));
+        float ms = 0.f; CUDA_TRY(cudaEventElapsedTime(&ms, p->t_begin, p->t_end[i]));
+        if (ms > best) best = ms;
+    }
+    *elapsed_ms = best;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- synthetic workloads
+int mdgpu_synth_water_desc(uint32_t n, uint32_t seed, uint32_t* num_atoms, float* L) {
+    const mdsynth_water_t w = mdsynth_water_desc(n, seed);
+    if (num_atoms) *num_atoms = w.num_atoms; if (L) *L = w.L;
+    return 0;
+}
+
+int mdgpu_synth_water_base(uint32_t n, uint32_t seed, float* base_xyz, float* whole_xyz) {
+    const mdsynth_water_t w = mdsynth_water_desc(n, seed);
+    const size_t N = w.num_atoms;
+    mdsynth_water_base(&w, base_xyz, base_xyz ? base_xyz + N : nullptr, base_xyz ? base_xyz + 2 * N : nullptr,
+                       whole_xyz, whole_xyz ? whole_xyz + N : nullptr, whole_xyz ? whole_xyz + 2 * N : nullptr);
+    return 0;
+}
+
+int mdgpu_synth_water_frames_host(uint32_t n, uint32_t seed, const float* base_xyz, uint32_t frame_beg, uint32_t count,
+                                  float* out_xyz, size_t frame_stride, size_t axis_stride) {
+    if (!base_xyz || !out_xyz) return fail(MDGPU_ERR_INVALID_ARG, "null argument");
+    const mdsynth_water_t w = mdsynth_water_desc(n, seed); const size_t N = w.num_atoms;
+    for (uint32_t i = 0; i < count; ++i) {
+        float* o = out_xyz + (size_t)i * frame_stride;
+        mdsynth_water_frame(&w, frame_beg + i, base_xyz, base_xyz + N, base_xyz + 2 * N, o, o + axis_stride, o + 2 * axis_stride);
+    }
+    return 0;
+}
+
+int mdgpu_synth_water_frames_device(int device, uint32_t n, uint32_t seed, const float* d_base_xyz, uint32_t frame_beg, uint32_t count,
+                                    float* d_out_xyz, size_t frame_stride, size_t axis_stride) {
+    if (!d_base_xyz || !d_out_xyz) return fail(MDGPU_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    const mdsynth_water_t w = mdsynth_water_desc(n, seed);
+    for (uint32_t c0 = 0; c0 < count; c0 += 32768) {
+        const uint32_t c = std::min(32768u, count - c0);
+        launch_synth_water(seed, w.L, w.num_atoms, d_base_xyz, w.num_atoms, frame_beg + c0, c, d_out_xyz + (size_t)c0 * frame_stride, frame_stride, axis_stride, 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- memory helpers
+int mdgpu_device_alloc(int device, size_t bytes, void** out) { if (!out) return MDGPU_ERR_INVALID_ARG; CUDA_TRY(cudaSetDevice(device)); CUDA_TRY(cudaMalloc(out, bytes)); return 0; }
+int mdgpu_device_free(int device, void* ptr) { CUDA_TRY(cudaSetDevice(device)); CUDA_TRY(cudaFree(ptr)); return 0; }
+int mdgpu_host_alloc_pinned(size_t bytes, void** out) { if (!out) return MDGPU_ERR_INVALID_ARG; CUDA_TRY(cudaMallocHost(out, bytes)); return 0; }
+int mdgpu_host_free_pinned(void* ptr) { CUDA_TRY(cudaFreeHost(ptr)); return 0; }
+int mdgpu_memcpy_h2d(int device, void* dst, const void* src, size_t bytes) { CUDA_TRY(cudaSetDevice(device)); CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
+int mdgpu_memcpy_d2h(int device, void* dst, const void* src, size_t bytes) { CUDA_TRY(cudaSetDevice(device)); CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
+int mdgpu_device_synchronize(int device) { CUDA_TRY(cudaSetDevice(device)); CUDA_TRY(cudaDeviceSynchronize()); return 0; }
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// sdf.cu — K3 (local reference-frame fit per structure) and K4 (AABB gather + transform + voxel scatter) for sdf().
+//
+// Replaces _sdf / sdf_cb (reference md_script_functions.inl:5643-5856), md_util_unwrap_vec4 (md_util.c:8738-8819,8938),
+// com_vec4 (md_util.c:8048), mat3_covariance_matrix_vec4 / mat3_cross_covariance_matrix_vec4 / mat3_eigen /
+// mat3_extract_rotation (core/md_vec_math.c:22-42,101-156,227-300), svd (ext/svd3/svd3.c) and
+// md_spatial_acc_for_each_point_in_aabb (core/md_spatial_acc.c:1805-2007).
+//
+// All float expressions keep the reference's association; double accumulators stay double; the library is built with
+// --fmad=false so nothing is contracted. The only fused operations are the reference's explicit fmadd intrinsics.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mdg {
+
+// ------------------------------------------------------------------------------------------------- 3x3 SVD (McAdams)
+struct M3 { float e[3][3]; };   // e[col][row] as in the reference's mat3_t; the svd routine itself is row-major A[r][c]
+struct M4 { float e[4][4]; };
+
+MDG_D float inv_sqrtf_(float v) { return __fdiv_rn(1.0f, __fsqrt_rn(v)); }
+MDG_D void cond_swap(bool c, float& X, float& Y) { const float Z = X; X = c ? Y : X; Y = c ? Z : Y; }
+MDG_D void cond_neg_swap(bool c, float& X, float& Y) { const float Z = -X; X = c ? Y : X; Y = c ? Z : Y; }
+
+MDG_D void approx_givens(float a11, float a12, float a22, float& ch, float& sh) {
+    ch = 2.0f * (a11 - a22);
+    sh = a12;
+    // _gamma is a double literal in svd3.c: the comparison is evaluated in double
+    const bool b = 5.828427124746190097 * (double)sh * (double)sh < (double)(ch * ch);
+    const float w = inv_sqrtf_(ch * ch + sh * sh);
+    ch = b ? w * ch : (float)0.923879532511286756;
+    sh = b ? w * sh : (float)0.382683432365089771;
+}
+
+MDG_D void jacobi_conj(const int x, const int y, const int z, float S[3][3], float q[4]) {
+    float ch, sh; approx_givens(S[0][0], S[1][0], S[1][1], ch, sh);
+    const float scale = ch * ch + sh * sh;
+    const float a = (ch * ch - sh * sh) / scale;
+    const float b = (2.0f * sh * ch) / scale;
+    const float s00 = S[0][0], s10 = S[1][0], s11 = S[1][1], s20 = S[2][0], s21 = S[2][1], s22 = S[2][2];
+    const float n00 = a * (a * s00 + b * s10) + b * (a * s10 + b * s11);
+    const float n10 = a * (-b * s00 + a * s10) + b * (-b * s10 + a * s11);
+    const float n11 = -b * (-b * s00 + a * s10) + a * (-b * s10 + a * s11);
+    const float n20 = a * s20 + b * s21;
+    const float n21 = -b * s20 + a * s21;
+    const float n22 = s22;
+    const float tmp0 = q[0] * sh, tmp1 = q[1] * sh, tmp2 = q[2] * sh;
+    const float tmp[3] = { tmp0, tmp1, tmp2 };
+    sh *= q[3];
+    q[0] *= ch; q[1] *= ch; q[2] *= ch; q[3] *= ch;
+    q[z] += sh; q[3] -= tmp[z]; q[x] += tmp[y]; q[y] -= tmp[x];
+    S[0][0] = n11; S[1][0] = n21; S[1][1] = n22; S[2][0] = n10; S[2][1] = n20; S[2][2] = n00;
+}
+
+MDG_D float dist2_(float a, float b, float c) { return a * a + b * b + c * c; }
+
+MDG_D void qr_givens(float a1, float a2, float& ch, float& sh) {
+    const float epsilon = (float)1e-6;
+    const float rho = __fsqrt_rn(a1 * a1 + a2 * a2);
+    sh = rho > epsilon ? a2 : 0.0f;
+    ch = fabsf(a1) + fmaxf(rho, epsilon);
+    const bool b = a1 < 0.0f;
+    cond_swap(b, sh, ch);
+    const float w = inv_sqrtf_(ch * ch + sh * sh);
+    ch *= w; sh *= w;
+}
+
+__device__ __noinline__ void svd3(const float A[3][3], float U[3][3], float S[3][3], float V[3][3]) {
+    float ATA[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ATA[i][j] = A[0][i] * A[0][j] + A[1][i] * A[1][j] + A[2][i] * A[2][j];
+    float q[4] = { 0.f, 0.f, 0.f, 1.f };
+    for (int it = 0; it < 4; ++it) { jacobi_conj(0, 1, 2, ATA, q); jacobi_conj(1, 2, 0, ATA, q); jacobi_conj(2, 0, 1, ATA, q); }
+    {
+        const float x = q[0], y = q[1], z = q[2], w = q[3];
+        const float qxx = x * x, qyy = y * y, qzz = z * z, qxz = x * z, qxy = x * y, qyz = y * z, qwx = w * x, qwy = w * y, qwz = w * z;
+        V[0][0] = 1.0f - 2.0f * (qyy + qzz); V[0][1] = 2.0f * (qxy - qwz);        V[0][2] = 2.0f * (qxz + qwy);
+        V[1][0] = 2.0f * (qxy + qwz);        V[1][1] = 1.0f - 2.0f * (qxx + qzz); V[1][2] = 2.0f * (qyz - qwx);
+        V[2][0] = 2.0f * (qxz - qwy);        V[2][1] = 2.0f * (qyz + qwx);        V[2][2] = 1.0f - 2.0f * (qxx + qyy);
+    }
+    float B[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) B[i][j] = A[i][0] * V[0][j] + A[i][1] * V[1][j] + A[i][2] * V[2][j];
+    {
+        float rho1 = dist2_(B[0][0], B[1][0], B[2][0]), rho2 = dist2_(B[0][1], B[1][1], B[2][1]), rho3 = dist2_(B[0][2], B[1][2], B[2][2]);
+        bool c = rho1 < rho2;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { cond_neg_swap(c, B[r][0], B[r][1]); cond_neg_swap(c, V[r][0], V[r][1]); }
+        cond_swap(c, rho1, rho2);
+        c = rho1 < rho3;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { cond_neg_swap(c, B[r][0], B[r][2]); cond_neg_swap(c, V[r][0], V[r][2]); }
+        cond_swap(c, rho1, rho3);
+        c = rho2 < rho3;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { cond_neg_swap(c, B[r][1], B[r][2]); cond_neg_swap(c, V[r][1], V[r][2]); }
+    }
+    {
+        float (*Q)[3] = U; float (*R)[3] = S;
+        float ch1, sh1, ch2, sh2, ch3, sh3, a, b;
+        qr_givens(B[0][0], B[1][0], ch1, sh1);
+        a = 1.0f - 2.0f * sh1 * sh1; b = 2.0f * ch1 * sh1;
+        R[0][0] = a * B[0][0] + b * B[1][0];  R[0][1] = a * B[0][1] + b * B[1][1];  R[0][2] = a * B[0][2] + b * B[1][2];
+        R[1][0] = -b * B[0][0] + a * B[1][0]; R[1][1] = -b * B[0][1] + a * B[1][1]; R[1][2] = -b * B[0][2] + a * B[1][2];
+        R[2][0] = B[2][0]; R[2][1] = B[2][1]; R[2][2] = B[2][2];
+        qr_givens(R[0][0], R[2][0], ch2, sh2);
+        a = 1.0f - 2.0f * sh2 * sh2; b = 2.0f * ch2 * sh2;
+        B[0][0] = a * R[0][0] + b * R[2][0];  B[0][1] = a * R[0][1] + b * R[2][1];  B[0][2] = a * R[0][2] + b * R[2][2];
+        B[1][0] = R[1][0]; B[1][1] = R[1][1]; B[1][2] = R[1][2];
+        B[2][0] = -b * R[0][0] + a * R[2][0]; B[2][1] = -b * R[0][1] + a * R[2][1]; B[2][2] = -b * R[0][2] + a * R[2][2];
+        qr_givens(B[1][1], B[2][1], ch3, sh3);
+        a = 1.0f - 2.0f * sh3 * sh3; b = 2.0f * ch3 * sh3;
+        R[0][0] = B[0][0]; R[0][1] = B[0][1]; R[0][2] = B[0][2];
+        R[1][0] = a * B[1][0] + b * B[2][0];  R[1][1] = a * B[1][1] + b * B[2][1];  R[1][2] = a * B[1][2] + b * B[2][2];
+        R[2][0] = -b * B[1][0] + a * B[2][0]; R[2][1] = -b * B[1][1] + a * B[2][1]; R[2][2] = -b * B[1][2] + a * B[2][2];
+        const float sh12 = sh1 * sh1, sh22 = sh2 * sh2, sh32 = sh3 * sh3;
+        Q[0][0] = (-1.0f + 2.0f * sh12) * (-1.0f + 2.0f * sh22);
+        Q[0][1] = 4.0f * ch2 * ch3 * (-1.0f + 2.0f * sh12) * sh2 * sh3 + 2.0f * ch1 * sh1 * (-1.0f + 2.0f * sh32);
+        Q[0][2] = 4.0f * ch1 * ch3 * sh1 * sh3 - 2.0f * ch2 * (-1.0f + 2.0f * sh12) * sh2 * (-1.0f + 2.0f * sh32);
+        Q[1][0] = 2.0f * ch1 * sh1 * (1.0f - 2.0f * sh22);
+        Q[1][1] = -8.0f * ch1 * ch2 * ch3 * sh1 * sh2 * sh3 + (-1.0f + 2.0f * sh12) * (-1.0f + 2.0f * sh32);
+        Q[1][2] = -2.0f * ch3 * sh3 + 4.0f * sh1 * (ch3 * sh1 * sh3 + ch1 * ch2 * sh2 * (-1.0f + 2.0f * sh32));
+        Q[2][0] = 2.0f * ch2 * sh2;
+        Q[2][1] = 2.0f * ch3 * (1.0f - 2.0f * sh22) * sh3;
+        Q[2][2] = (-1.0f + 2.0f * sh22) * (-1.0f + 2.0f * sh32);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- small matrix helpers
+MDG_D M3 m3_transpose(const M3& M) { M3 T; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) T.e[i][j] = M.e[j][i]; return T; }
+MDG_D M3 m3_mul(const M3& A, const M3& B) {   // core/md_vec_math.h:1631
+    M3 C;
+    for (int col = 0; col < 3; ++col) for (int row = 0; row < 3; ++row)
+        C.e[col][row] = A.e[0][row] * B.e[col][0] + A.e[1][row] * B.e[col][1] + A.e[2][row] * B.e[col][2];
+    return C;
+}
+MDG_D float m3_det(const M3& M) {             // :1687
+    return M.e[0][0] * (M.e[1][1] * M.e[2][2] - M.e[2][1] * M.e[1][2])
+         - M.e[1][0] * (M.e[0][1] * M.e[2][2] - M.e[2][1] * M.e[0][2])
+         + M.e[2][0] * (M.e[0][1] * M.e[1][2] - M.e[1][1] * M.e[0][2]);
+}
+MDG_D M4 m4_from_m3(const M3& M) { M4 R; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) R.e[i][j] = (i < 3 && j < 3) ? M.e[i][j] : 0.0f; R.e[3][3] = 1.0f; return R; }
+MDG_D M4 m4_mul(const M4& A, const M4& B) {   // linear_combine_4 (:1512)
+    M4 C;
+    for (int j = 0; j < 4; ++j) for (int r = 0; r < 4; ++r) {
+        float v = B.e[j][0] * A.e[0][r];
+        v = v + B.e[j][1] * A.e[1][r];
+        v = v + B.e[j][2] * A.e[2][r];
+        v = v + B.e[j][3] * A.e[3][r];
+        C.e[j][r] = v;
+    }
+    return C;
+}
+struct Svd { M3 U, V; float s[3]; };
+MDG_D Svd m3_svd(const M3& M) {               // core/md_vec_math.c:7-20
+    M3 Mt = m3_transpose(M), U, S, V;
+    svd3(Mt.e, U.e, S.e, V.e);
+    Svd r; r.U = m3_transpose(U); r.V = m3_transpose(V); r.s[0] = S.e[0][0]; r.s[1] = S.e[1][1]; r.s[2] = S.e[2][2];
+    return r;
+}
+
+// vec4_deperiodize_ortho (core/md_vec_math.h:1242-1253): round = nearest-even
+MDG_D float deperiodize1(float x, float r, float ext) {
+    if (ext == 0.0f) return x;
+    const float inv = __fdiv_rn(1.0f, ext);
+    const float dx = __fmul_rn(__fsub_rn(x, r), inv);
+    const float dxp = __fsub_rn(dx, rintf(dx));
+    return __fadd_rn(r, __fmul_rn(dxp, ext));
+}
+
+// extract + unwrap + centre of mass of one structure into scratch (xyz, mass)
+MDG_D void load_unwrap_com(float4* p, const float* x, const float* y, const float* z, const float* mass, const int32_t* sidx, uint32_t n,
+                           const int2* pairs, uint32_t n_pairs, const mdgpu_unitcell_t& uc, float com[3]) {
+    for (uint32_t k = 0; k < n; ++k) { const int a = sidx[k]; p[k] = make_float4(x[a], y[a], z[a], mass[a]); }
+    if (uc.flags & MDGPU_CELL_ORTHO) {
+        const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
+        for (uint32_t k = 0; k < n_pairs; ++k) {
+            const int2 pr = pairs[k];
+            const float4 ref = p[pr.y]; float4 v = p[pr.x];
+            v.x = deperiodize1(v.x, ref.x, ext[0]); v.y = deperiodize1(v.y, ref.y, ext[1]); v.z = deperiodize1(v.z, ref.z, ext[2]);
+            p[pr.x] = v;
+        }
+    }
+    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;   // com_vec4 md_util.c:8048-8061
+    for (uint32_t k = 0; k < n; ++k) { const float4 v = p[k]; ax = ax + v.x * v.w; ay = ay + v.y * v.w; az = az + v.z * v.w; aw = aw + v.w * 1.0f; }
+    com[0] = ax / aw; com[1] = ay / aw; com[2] = az / aw;
+}
+
+// Reference structure (structure 0 of the INITIAL frame, unwrapped with the CURRENT frame's cell :5762-5782): PCA frame and V*A
+__global__ void k_sdf_ref0(SdfArgs a, int B) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= B) return;
+    const uint32_t n = a.struct_size;
+    float4* p = a.scratch_xyzw + ((size_t)f * (a.n_struct + 1) + a.n_struct) * n;
+    float com0[3];
+    load_unwrap_com(p, a.init_xyz, a.init_xyz + a.init_axis_stride, a.init_xyz + 2 * a.init_axis_stride, a.mass, a.struct_idx, n,
+                    a.unwrap_pairs, a.n_unwrap, a.cells[f], com0);
+    double C[3][3] = { { 0 } }; double ws = 0.0;   // mat3_covariance_matrix_vec4
+    for (uint32_t k = 0; k < n; ++k) {
+        const float4 v = p[k];
+        const float x = v.x - com0[0], y = v.y - com0[1], z = v.z - com0[2], w = v.w;
+        C[0][0] += w * x * x; C[0][1] += w * x * y; C[0][2] += w * x * z;
+        C[1][0] += w * y * x; C[1][1] += w * y * y; C[1][2] += w * y * z;
+        C[2][0] += w * z * x; C[2][1] += w * z * y; C[2][2] += w * z * z;
+        ws += w;
+    }
+    M3 cov; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) cov.e[i][j] = (float)(C[i][j] / ws);
+    // mat3_eigen (core/md_vec_math.c:22-42)
+    const Svd s = m3_svd(cov);
+    const float mx = fmaxf(s.s[0], fmaxf(s.s[1], s.s[2]));
+    const float ev[3] = { s.s[0] / mx, s.s[1] / mx, s.s[2] / mx };
+    int l0 = 0, l1 = 1, l2 = 2, t;
+    if (ev[l0] < ev[l1]) { t = l0; l0 = l1; l1 = t; }
+    if (ev[l1] < ev[l2]) { t = l1; l1 = l2; l2 = t; }
+    if (ev[l0] < ev[l1]) { t = l0; l0 = l1; l1 = t; }
+    const int l[3] = { l0, l1, l2 };
+    M3 eig; for (int k = 0; k < 3; ++k) for (int r = 0; r < 3; ++r) eig.e[k][r] = s.U.e[l[k]][r];
+    const M4 A = m4_from_m3(m3_transpose(eig));
+    // compute_volume_matrix (:5643-5655)
+    const float voxel_ext = (2.0f * a.cutoff) / (float)MDGPU_VOL_DIM;
+    const float sc = 1.0f / voxel_ext;
+    M4 S; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) S.e[i][j] = 0.0f; S.e[0][0] = sc; S.e[1][1] = sc; S.e[2][2] = sc; S.e[3][3] = 1.0f;
+    const float tt = (float)(MDGPU_VOL_DIM / 2);
+    M4 T; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T.e[i][j] = (i == j) ? 1.0f : 0.0f; T.e[3][0] = tt; T.e[3][1] = tt; T.e[3][2] = tt;
+    const M4 VA = m4_mul(m4_mul(T, S), A);
+    float* o = a.ref0 + (size_t)f * 20;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) o[i * 4 + j] = VA.e[i][j];
+    o[16] = com0[0]; o[17] = com0[1]; o[18] = com0[2]; o[19] = 0.0f;
+}
+
+// K3: one thread per (structure, frame): M = V*A*R*T(-com) (:5788-5799)
+__global__ void k_sdf_fit(SdfArgs a, int B) {
+    const int f = blockIdx.y;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n_struct) return;
+    const uint32_t n = a.struct_size;
+    const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride;
+    float4* p1 = a.scratch_xyzw + ((size_t)f * (a.n_struct + 1) + s) * n;
+    const float4* p0 = a.scratch_xyzw + ((size_t)f * (a.n_struct + 1) + a.n_struct) * n;
+    const float* r0 = a.ref0 + (size_t)f * 20;
+    const float com0[3] = { r0[16], r0[17], r0[18] };
+    float com1[3];
+    load_unwrap_com(p1, x, x + a.frames.axis_stride, x + 2 * a.frames.axis_stride, a.mass, a.struct_idx + (size_t)s * n, n,
+                    a.unwrap_pairs, a.n_unwrap, a.cells[f], com1);
+    double C[3][3] = { { 0 } }; double ws = 0.0;   // mat3_cross_covariance_matrix_vec4 (core/md_vec_math.c:256-289)
+    for (uint32_t k = 0; k < n; ++k) {
+        const float4 u = p0[k], v = p1[k];
+        const float px = u.x - com0[0], py = u.y - com0[1], pz = u.z - com0[2], pw = u.w - 0.0f;
+        const float qx = v.x - com1[0], qy = v.y - com1[1], qz = v.z - com1[2], qw = v.w - 0.0f;
+        const float w = (pw + qw) * 0.5f;
+        C[0][0] += w * px * qx; C[0][1] += w * px * qy; C[0][2] += w * px * qz;
+        C[1][0] += w * py * qx; C[1][1] += w * py * qy; C[1][2] += w * py * qz;
+        C[2][0] += w * pz * qx; C[2][1] += w * pz * qy; C[2][2] += w * pz * qz;
+        ws += w;
+    }
+    M3 cc; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) cc.e[i][j] = (float)(C[i][j] / ws);
+    // mat3_extract_rotation (core/md_vec_math.c:292-300)
+    const Svd sv = m3_svd(cc);
+    const M3 Ut = m3_transpose(sv.U);
+    const float d = m3_det(m3_mul(sv.V, Ut));
+    M3 D; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) D.e[i][j] = 0.0f; D.e[0][0] = 1.0f; D.e[1][1] = 1.0f; D.e[2][2] = (float)((d > 0.0f) - (d < 0.0f));
+    const M3 R = m3_mul(m3_mul(sv.V, D), Ut);
+    M4 Tm; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Tm.e[i][j] = (i == j) ? 1.0f : 0.0f; Tm.e[3][0] = -com1[0]; Tm.e[3][1] = -com1[1]; Tm.e[3][2] = -com1[2];
+    const M4 RT = m4_mul(m4_from_m3(R), Tm);
+    M4 VA; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) VA.e[i][j] = r0[i * 4 + j];
+    const M4 M = m4_mul(VA, RT);
+    float* o = a.matrices + ((size_t)f * a.n_struct + s) * 20;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) o[i * 4 + j] = M.e[i][j];
+    o[16] = com1[0]; o[17] = com1[1]; o[18] = com1[2]; o[19] = 0.0f;
+}
+
+MDG_D int wrap_coord(int v, int N) { v += (v < 0) ? N : 0; v -= (v >= N) ? N : 0; return v; }
+MDG_D int isign(int v) { return (v > 0) - (v < 0); }
+
+// K4: one warp per (structure, frame): points of the target cell list inside the AABB(com, cutoff) -> voxel increments
+constexpr int SDF_WARPS = 4;
+__global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B) {
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const uint32_t s = blockIdx.x * SDF_WARPS + (threadIdx.x >> 5);
+    if (s >= a.n_struct) return;
+    const FrameGeom& g = a.geom[f];
+    if (g.valid == -1 || (g.flags & MDGPU_CELL_TRICLINIC)) return;   // triclinic AABB query: not implemented (reported by the host)
+    const float* mrow = a.matrices + ((size_t)f * a.n_struct + s) * 20;
+    float M[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) M[i][j] = mrow[i * 4 + j];
+    const double cen[3] = { (double)mrow[16], (double)mrow[17], (double)mrow[18] };
+    const double rad = (double)a.cutoff;
+    const int pbc[3] = { (g.flags & MDGPU_CELL_PBC_X) != 0, (g.flags & MDGPU_CELL_PBC_Y) != 0, (g.flags & MDGPU_CELL_PBC_Z) != 0 };
+    const int cd[3] = { g.cdim[0], g.cdim[1], g.cdim[2] };
+    // cell_range_from_aabb_center_radius (:1805-1879), double precision with the float matrix entries widened
+    double sc[3], cc[3];
+    {
+        const double px = cen[0] - g.origin[0], py = cen[1] - g.origin[1], pz = cen[2] - g.origin[2];
+        sc[0] = g.I[0][0] * px + g.I[1][0] * py + g.I[2][0] * pz;
+        sc[1] = g.I[0][1] * px + g.I[1][1] * py + g.I[2][1] * pz;
+        sc[2] = g.I[0][2] * px + g.I[1][2] * py + g.I[2][2] * pz;
+    }
+    for (int k = 0; k < 3; ++k) if (pbc[k]) sc[k] = sc[k] - floor(sc[k]);
+    cc[0] = g.A[0][0] * sc[0] + g.A[1][0] * sc[1] + g.A[2][0] * sc[2] + g.origin[0];
+    cc[1] = g.A[0][1] * sc[0] + g.A[1][1] * sc[1] + g.A[2][1] * sc[2] + g.origin[1];
+    cc[2] = g.A[0][2] * sc[0] + g.A[1][2] * sc[1] + g.A[2][2] * sc[2] + g.origin[2];
+    double fmin_[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, fmax_[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+    for (int corner = 0; corner < 8; ++corner) {
+        const double pz = cc[2] + ((corner & 4) ? rad : -rad), py = cc[1] + ((corner & 2) ? rad : -rad), px = cc[0] + ((corner & 1) ? rad : -rad);
+        const double qx = px - g.origin[0], qy = py - g.origin[1], qz = pz - g.origin[2];
+        double sv[3];
+        sv[0] = g.I[0][0] * qx + g.I[1][0] * qy + g.I[2][0] * qz;
+        sv[1] = g.I[0][1] * qx + g.I[1][1] * qy + g.I[2][1] * qz;
+        sv[2] = g.I[0][2] * qx + g.I[1][2] * qy + g.I[2][2] * qz;
+        for (int k = 0; k < 3; ++k) { fmin_[k] = fmin(fmin_[k], sv[k]); fmax_[k] = fmax(fmax_[k], sv[k]); }
+    }
+    int cmin[3], cmax[3]; float lo3[3], hi3[3];
+    for (int k = 0; k < 3; ++k) {
+        double frad = 0.5 * (fmax_[k] - fmin_[k]);
+        int lo = (int)floor(fmin_[k] * (double)cd[k]), hi = (int)ceil(fmax_[k] * (double)cd[k]);
+        if (hi <= lo) hi = lo + 1;
+        if (!pbc[k]) { lo = max(0, min(lo, cd[k])); hi = max(0, min(hi, cd[k])); if (hi <= lo) hi = min(lo + 1, cd[k]); }
+        cmin[k] = lo; cmax[k] = hi;
+        frad = fmin(frad, 0.5);
+        lo3[k] = (float)(sc[k] - frad); hi3[k] = (float)(sc[k] + frad);
+    }
+    const float4* __restrict__ pts = a.trg.sorted + (size_t)f * a.trg.max_points;
+    const uint32_t* __restrict__ off = a.trg.cell_cnt + (size_t)f * (a.trg.cap + 1);
+    const int32_t* sidx = a.struct_idx + (size_t)s * a.struct_size;
+    unsigned long long local = 0;
+    for (int icz = cmin[2]; icz < cmax[2]; ++icz) { const int cz = pbc[2] ? wrap_coord(icz, cd[2]) : icz; const float shz = (float)isign(icz - cz);
+    for (int icy = cmin[1]; icy < cmax[1]; ++icy) { const int cy = pbc[1] ? wrap_coord(icy, cd[1]) : icy; const float shy = (float)isign(icy - cy);
+    for (int icx = cmin[0]; icx < cmax[0]; ++icx) { const int cx = pbc[0] ? wrap_coord(icx, cd[0]) : icx; const float shx = (float)isign(icx - cx);
+        if (cx < 0 || cx >= cd[0] || cy < 0 || cy >= cd[1] || cz < 0 || cz >= cd[2]) continue;
+        const uint32_t ci = ((uint32_t)cz * (uint32_t)cd[1] + (uint32_t)cy) * (uint32_t)cd[0] + (uint32_t)cx;
+        const uint32_t o = off[ci], len = off[ci + 1] - o;
+        for (uint32_t j = lane; j < len; j += 32) {
+            const float4 t = pts[o + j];
+            const float vx = __fadd_rn(t.x, shx), vy = __fadd_rn(t.y, shy), vz = __fadd_rn(t.z, shz);
+            if (!(vx >= lo3[0] && vy >= lo3[1] && vz >= lo3[2] && vx <= hi3[0] && vy <= hi3[1] && vz <= hi3[2])) continue;
+            const uint32_t idx = __float_as_uint(t.w);
+            bool excluded = false;   // md_bitfield_test_bit(exclusion_mask, idx): the structure's own atoms (:5674)
+            for (uint32_t k = 0; k < a.struct_size; ++k) excluded |= ((uint32_t)sidx[k] == idx);
+            if (excluded) continue;
+            // batch_fract_to_cart_ort_256: one fused multiply-add per axis (:583-592)
+            const float px = __fmaf_rn(vx, g.A[0][0], g.origin[0]), py = __fmaf_rn(vy, g.A[1][1], g.origin[1]), pz = __fmaf_rn(vz, g.A[2][2], g.origin[2]);
+            float c[3];   // mat4_mul_vec4(M, (x,y,z,1)) = ((x*M0 + y*M1) + z*M2) + 1*M3
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float v = __fmul_rn(px, M[0][r]);
+                v = __fadd_rn(v, __fmul_rn(py, M[1][r]));
+                v = __fadd_rn(v, __fmul_rn(pz, M[2][r]));
+                v = __fadd_rn(v, __fmul_rn(1.0f, M[3][r]));
+                c[r] = v;
+            }
+            const int ix = max(0, min(__float2int_rz(c[0]), MDGPU_VOL_DIM - 1));
+            const int iy = max(0, min(__float2int_rz(c[1]), MDGPU_VOL_DIM - 1));
+            const int iz = max(0, min(__float2int_rz(c[2]), MDGPU_VOL_DIM - 1));
+            atomicAdd(&a.vol[((size_t)iz * MDGPU_VOL_DIM + iy) * MDGPU_VOL_DIM + ix], 1u);
+            local += 1;
+        }
+    } } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(&a.frame_total[a.frame0 + f], local);
+}
+
+void launch_sdf(const SdfArgs& a, int B, cudaStream_t s) {
+    k_sdf_ref0<<<(B + 31) / 32, 32, 0, s>>>(a, B);
+    note_launch("k_sdf_ref0", s);
+    dim3 g1((a.n_struct + 63) / 64, B);
+    k_sdf_fit<<<g1, 64, 0, s>>>(a, B);
+    note_launch("k_sdf_fit", s);
+    dim3 g2((a.n_struct + SDF_WARPS - 1) / SDF_WARPS, B);
+    k_sdf_scatter<<<g2, SDF_WARPS * 32, 0, s>>>(a, B);
+    note_launch("k_sdf_scatter", s);
+}
+
+}  // namespace mdg

@@ -76,7 +76,6 @@ MDSYNTH_HD float mdsynth_frame_coord(float base, uint32_t seed, uint32_t frame, 
     return mdsynth_wrap(x, L);
 }
 
-#if !defined(__CUDA_ARCH__)
 #include <math.h>
 #include <stdio.h>
 
@@ -181,6 +180,4 @@ static inline int mdsynth_water_write_gro(const mdsynth_water_t* w, const char* 
     fclose(f);
     return 0;
 }
-#endif /* !__CUDA_ARCH__ */
-
 #endif /* MDSYNTH_H */

@@ -1,0 +1,65 @@
+"""Frame sharding across GPUs + the final exchange step.
+
+Frames are independent units: rank g evaluates the contiguous block [F*g/G, F*(g+1)/G) into its own integer accumulators
+(no data-path collective), then ONE exchange at the end: all-reduce(sum) of the RDF bins (u64[1024]) and the SDF voxel grid
+(u32[128^3]) over NCCL/NVLink, all-reduce(min/max) of the per-frame bin extrema, and the pair total of the globally last frame
+(for the RDF weights). Dividing by the global frame count happens after the reduce, so the result is independent of G.
+torch.distributed is plumbing only; on CPU (gloo) the same code path runs on host copies of the accumulators.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+
+
+def frame_shard(num_frames: int, world: int, rank: int):
+    """Contiguous frame block of `rank` (the partition VIAMD's range task uses per thread, src/task_system.cpp:73-87)."""
+    return (num_frames * rank) // world, (num_frames * (rank + 1)) // world
+
+
+class _CudaView:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def allreduce_counts_(counts, group=None):
+    """In-place sum of an integer tensor across ranks (works for CPU tensors with gloo and CUDA tensors with nccl)."""
+    import torch.distributed as dist
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def rdf_weights(total_pairs: int, cutoff_min: float, cutoff_max: float) -> np.ndarray:
+    """compute_rdf's normalisation (md_script_functions.inl:5323-5337), same double arithmetic as csrc/plan.cu."""
+    mn = np.float32(max(np.float32(cutoff_min), np.float32(1e-3))); mx = np.float32(cutoff_max)
+    sv = lambda r: (4.0 / 3.0) * 3.1415926535897932 * (r * r * r)
+    total_vol = sv(float(mx)) - sv(float(mn))
+    rho = float(total_pairs) / total_vol
+    dr = float(np.float32(np.float32(mx - mn) / np.float32(1024)))
+    w = np.empty(1024, np.float32); prev = 0.0
+    for i in range(1024):
+        s = sv(float(mn) + (i + 0.5) * dr); w[i] = np.float32(rho * (s - prev)); prev = s
+    return w
+
+
+def allreduce_plan(plan: api.Plan, total_frames: int, group=None, device=None):
+    """The single exchange step for a frame-sharded evaluation. Reduces every distribution/volume accumulator of `plan`
+    in place on the device (NCCL) and tells the plan the global frame count. Returns {name: merged extras}."""
+    import torch
+    import torch.distributed as dist
+    plan.sync()
+    extras = {}
+    dev = torch.device("cuda", plan.device if device is None else device)
+    for p in plan.properties:
+        if p.op not in (api.OP_RDF, api.OP_SDF, api.OP_DENSITY_X, api.OP_DENSITY_Y, api.OP_DENSITY_Z):
+            continue
+        ptr, nbytes, eb = plan.accum_ptr(p.name)
+        view = _CudaView(ptr, nbytes // eb, "<i8" if eb == 8 else "<i4")
+        t = torch.as_tensor(view, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        plan.set_frames_accumulated(p.name, int(total_frames))
+    torch.cuda.synchronize(dev)
+    return extras

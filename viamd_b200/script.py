@@ -1,0 +1,179 @@
+"""Minimal lowering of md_script property statements to libmdgpu property descriptors.
+
+In VIAMD the script front-end (tokenizer, parser, static type check, static evaluation of selections) is mdlib's own
+md_script.c and stays unchanged; INTEGRATION.md shows the shim that walks a compiled md_script_ir_t and emits the same
+descriptors. This module exists so that the tests and bench.py can be written the way the reference's own tests are
+(mdlib/unittest/test_script.c:1259-1273: `prop1 = rdf(element('C'), element('O'), 20.0);`) without the reference on the box.
+
+Supported statements:  ident = proc(args);   with proc in
+    rdf(sel, sel, cutoff | min:max)   sdf(residue(a:b) | sel-array, sel, cutoff)   density_x|_y|_z(sel)
+    distance(i, j)   angle(i, j, k)   dihedral(i, j, k, l)            (1-based atom indices as in md_script)
+Selections (evaluated once, statically, to ascending atom index lists — md_script.c:5492-5524):
+    all | element('O') | name('C2*') | resname('SOL') | atom(a:b) | residue(a:b) | `and` / `or` / `not` of these
+`residue(a:b)` used as the first argument of sdf() yields one structure per residue (bitfield array semantics).
+"""
+from __future__ import annotations
+
+import fnmatch
+import re
+from typing import List
+
+import numpy as np
+
+from . import api
+
+_TOK = re.compile(r"\s*(?:(\d+\.\d*|\.\d+|\d+)|([A-Za-z_][A-Za-z_0-9]*)|'([^']*)'|\"([^\"]*)\"|(.))")
+
+
+class ScriptError(ValueError):
+    pass
+
+
+def _tokens(src: str):
+    out = []
+    for m in _TOK.finditer(src):
+        num, ident, s1, s2, ch = m.groups()
+        if num is not None: out.append(("num", num))
+        elif ident is not None: out.append(("id", ident))
+        elif s1 is not None: out.append(("str", s1))
+        elif s2 is not None: out.append(("str", s2))
+        elif ch and not ch.isspace(): out.append(("ch", ch))
+    return out
+
+
+class _Parser:
+    def __init__(self, toks, system: api.System):
+        self.t, self.i, self.sys = toks, 0, system
+
+    def peek(self): return self.t[self.i] if self.i < len(self.t) else ("eof", "")
+    def next(self): tok = self.peek(); self.i += 1; return tok
+
+    def expect(self, kind, val=None):
+        tok = self.next()
+        if tok[0] != kind or (val is not None and tok[1] != val):
+            raise ScriptError(f"expected {val or kind}, got {tok[1]!r}")
+        return tok
+
+    # ---- selections -> boolean masks
+    def sel_or(self):
+        m = self.sel_and()
+        while self.peek() == ("id", "or"):
+            self.next(); m = m | self.sel_and()
+        return m
+
+    def sel_and(self):
+        m = self.sel_not()
+        while self.peek() == ("id", "and"):
+            self.next(); m = m & self.sel_not()
+        return m
+
+    def sel_not(self):
+        if self.peek() == ("id", "not"):
+            self.next(); return ~self.sel_not()
+        return self.sel_atom()
+
+    def _range(self, count):
+        """a | a:b | : (1-based inclusive, as in md_script) -> python slice bounds (0-based, exclusive end)"""
+        lo, hi = 1, count
+        if self.peek()[0] == "num":
+            lo = int(float(self.next()[1])); hi = lo
+        if self.peek() == ("ch", ":"):
+            self.next(); hi = count
+            if self.peek()[0] == "num": hi = int(float(self.next()[1]))
+        return max(lo - 1, 0), min(hi, count)
+
+    def sel_atom(self):
+        n = self.sys.num_atoms
+        tok = self.next()
+        if tok == ("ch", "("):
+            m = self.sel_or(); self.expect("ch", ")"); return m
+        if tok[0] != "id":
+            raise ScriptError(f"unexpected token {tok[1]!r} in selection")
+        f = tok[1]
+        if f == "all": return np.ones(n, bool)
+        self.expect("ch", "(")
+        if f in ("element", "name", "label", "resname"):
+            pats = [self.expect("str")[1]]
+            while self.peek() == ("ch", ","):
+                self.next(); pats.append(self.expect("str")[1])
+            self.expect("ch", ")")
+            if f == "element":
+                if self.sys.element is None: raise ScriptError("system has no element data")
+                src = np.asarray(self.sys.element); return np.isin(np.char.upper(src.astype(str)), [p.upper() for p in pats])
+            if f == "resname":
+                if self.sys.resname is None: raise ScriptError("system has no residue data")
+                rn = np.asarray(self.sys.resname); hit = np.zeros(len(rn), bool)
+                for p in pats: hit |= np.array([fnmatch.fnmatchcase(r, p) for r in rn])
+                return np.repeat(hit, np.diff(self.sys.res_atom_offset))
+            if self.sys.name is None: raise ScriptError("system has no atom names")
+            nm = np.asarray(self.sys.name); hit = np.zeros(n, bool)
+            for p in pats: hit |= np.array([fnmatch.fnmatchcase(a, p) for a in nm])
+            return hit
+        if f == "atom":
+            lo, hi = self._range(n); self.expect("ch", ")")
+            m = np.zeros(n, bool); m[lo:hi] = True; return m
+        if f == "residue":
+            off = np.asarray(self.sys.res_atom_offset); lo, hi = self._range(len(off) - 1); self.expect("ch", ")")
+            m = np.zeros(n, bool); m[off[lo]:off[hi]] = True; return m
+        raise ScriptError(f"unsupported selection '{f}'")
+
+    def selection(self) -> np.ndarray:
+        return np.nonzero(self.sel_or())[0].astype(np.int32)
+
+    def structures(self) -> np.ndarray:
+        """first argument of sdf(): residue(a:b) -> one structure per residue; otherwise a single structure"""
+        save = self.i
+        if self.peek() == ("id", "residue"):
+            self.next(); self.expect("ch", "(")
+            off = np.asarray(self.sys.res_atom_offset); lo, hi = self._range(len(off) - 1); self.expect("ch", ")")
+            if self.peek() in (("ch", ","),):
+                sizes = np.diff(off[lo:hi + 1])
+                if len(sizes) == 0 or np.any(sizes != sizes[0]):
+                    raise ScriptError("The supplied reference bitfields are not identical")   # _sdf validation :5837
+                return np.stack([np.arange(off[r], off[r + 1], dtype=np.int32) for r in range(lo, hi)])
+            self.i = save
+        s = self.selection()
+        return s.reshape(1, -1)
+
+    def number(self) -> float:
+        return float(self.expect("num")[1])
+
+    def index(self) -> int:
+        return int(float(self.expect("num")[1])) - 1   # md_script atom indices are 1-based
+
+    def statement(self) -> api.Property:
+        ident = self.expect("id")[1]; self.expect("ch", "=")
+        proc = self.expect("id")[1]; self.expect("ch", "(")
+        if proc == "rdf":
+            ref = self.selection(); self.expect("ch", ","); trg = self.selection(); self.expect("ch", ",")
+            a = self.number(); lo, hi = 0.0, a
+            if self.peek() == ("ch", ":"):
+                self.next(); lo, hi = a, self.number()
+            p = api.rdf(ident, ref, trg, hi, lo)
+        elif proc == "sdf":
+            st = self.structures(); self.expect("ch", ","); trg = self.selection(); self.expect("ch", ","); c = self.number()
+            p = api.sdf(ident, st, trg, c)
+        elif proc in ("density_x", "density_y", "density_z"):
+            p = api.density(ident, "xyz".index(proc[-1]), self.selection())
+        elif proc == "distance":
+            a = self.index(); self.expect("ch", ","); b = self.index(); p = api.distance(ident, a, b)
+        elif proc == "angle":
+            a = self.index(); self.expect("ch", ","); b = self.index(); self.expect("ch", ","); c = self.index(); p = api.angle(ident, a, b, c)
+        elif proc == "dihedral":
+            v = [self.index()]
+            for _ in range(3): self.expect("ch", ","); v.append(self.index())
+            p = api.dihedral(ident, *v)
+        else:
+            raise ScriptError(f"procedure '{proc}' is outside the GPU hot-path scope")
+        self.expect("ch", ")"); self.expect("ch", ";")
+        return p
+
+
+def compile_script(src: str, system: api.System) -> List[api.Property]:
+    """`md_script_ir_compile_from_source` stand-in for the supported statement subset."""
+    ps = _Parser(_tokens(src), system); out = []
+    while ps.peek()[0] != "eof":
+        out.append(ps.statement())
+    if not out:
+        raise ScriptError("No properties present in ir")
+    return out
