@@ -200,6 +200,11 @@ int mdgpu_plan_timer_begin(mdgpu_plan* plan);
 int mdgpu_plan_timer_end(mdgpu_plan* plan, double* elapsed_ms);
 int mdgpu_plan_kernel_time_ms(mdgpu_plan* plan, const char* kernel, double* total_ms, uint64_t* launches);
 
+/* Host evaluation of the per-frame cell-grid geometry (the same code the device runs, one thread per frame); used by the
+ * CPU-side tests and for sizing. out_i[13] = cdim[3], ncell[3], hlo[3], hdim[3], valid; out_f[7] = G00,G11,G22,H01,H02,H12,r2. */
+int mdgpu_debug_frame_geom(const mdgpu_unitcell_t* cell, double cell_ext, double cutoff, const float* aabb_min_max /* 6 floats or NULL */,
+                           int32_t* out_i, float* out_f);
+
 /* Synthetic workloads (viamd_b200/csrc/synth.h), used by bench.py and the tests. */
 int mdgpu_synth_water_desc(uint32_t n, uint32_t seed, uint32_t* num_atoms, float* L);
 int mdgpu_synth_water_base(uint32_t n, uint32_t seed, float* base_xyz /* [3][num_atoms] wrapped */, float* whole_xyz /* optional */);

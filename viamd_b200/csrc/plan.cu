@@ -335,7 +335,7 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
         // default cell capacity: twice the grid the reference would build for the first frame, per property cutoff
         uint32_t cap = p->cell_cap;
         if (!cap) {
-            uint64_t need = 4096;
+            uint64_t need = 1u << 16;   // floor: non-periodic axes get their extent from the data (AABB fit), unknown here
             for (auto& pr : p->props) if (pr.needs_cells()) {
                 FrameGeom g; host_frame_geom(&g, first_cell, pr.cutoff_max, pr.cutoff_max, nullptr, 0xffffffffu);
                 need = std::max<uint64_t>(need, 2ull * std::max<uint64_t>(g.num_cells, g.num_home) + 2);
@@ -746,6 +746,15 @@ int mdgpu_plan_timer_end(mdgpu_plan* p, double* elapsed_ms) {
         if (ms > best) best = ms;
     }
     *elapsed_ms = best;
+    return 0;
+}
+
+int mdgpu_debug_frame_geom(const mdgpu_unitcell_t* cell, double cell_ext, double cutoff, const float* aabb, int32_t* out_i, float* out_f) {
+    if (!cell || !out_i || !out_f) return fail(MDGPU_ERR_INVALID_ARG, "null argument");
+    FrameGeom g; host_frame_geom(&g, cell, cell_ext, cutoff, aabb, 0xffffffffu);
+    for (int k = 0; k < 3; ++k) { out_i[k] = g.cdim[k]; out_i[3 + k] = g.ncell[k]; out_i[6 + k] = g.hlo[k]; out_i[9 + k] = g.hdim[k]; }
+    out_i[12] = g.valid;
+    out_f[0] = g.G00; out_f[1] = g.G11; out_f[2] = g.G22; out_f[3] = g.H01; out_f[4] = g.H02; out_f[5] = g.H12; out_f[6] = g.r2;
     return 0;
 }
 
