@@ -205,6 +205,10 @@ int mdgpu_plan_kernel_time_ms(mdgpu_plan* plan, const char* kernel, double* tota
 int mdgpu_debug_frame_geom(const mdgpu_unitcell_t* cell, double cell_ext, double cutoff, const float* aabb_min_max /* 6 floats or NULL */,
                            int32_t* out_i, float* out_f);
 
+/* Self-check of the branch-free correctly-rounded sqrt used when binning RDF hits: compares it with the IEEE sqrt for every
+ * float whose bit pattern lies in [lo_bits, hi_bits) and returns the number of mismatches (must be 0 in the normal range). */
+int mdgpu_debug_sqrt_sweep(int device, uint32_t lo_bits, uint32_t hi_bits, uint64_t* mismatches);
+
 /* Synthetic workloads (viamd_b200/csrc/synth.h), used by bench.py and the tests. */
 int mdgpu_synth_water_desc(uint32_t n, uint32_t seed, uint32_t* num_atoms, float* L);
 int mdgpu_synth_water_base(uint32_t n, uint32_t seed, float* base_xyz /* [3][num_atoms] wrapped */, float* whole_xyz /* optional */);

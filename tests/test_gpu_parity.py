@@ -284,3 +284,12 @@ def test_full_size_properties_config2_config3():
     assert np.array_equal(plan.counts("r"), acc) and np.array_equal(plan.counts("v"), vol)
     assert 2.5e5 * F < int(vol.sum()) < 3.5e5 * F
     vb.device_free(0, d_base); vb.device_free(0, d_fr); plan.close()
+
+
+def test_fast_sqrt_matches_ieee():
+    """The branch-free sqrt used when binning RDF hits equals the correctly rounded sqrt for every float in [2^-100, 2^100]
+    (d2 values that reach it lie in [1e-6, cutoff^2])."""
+    from viamd_b200.api import debug_sqrt_sweep
+    import struct
+    bits = lambda x: struct.unpack("<I", struct.pack("<f", x))[0]
+    assert debug_sqrt_sweep(bits(2.0 ** -100), bits(2.0 ** 100)) == 0

@@ -481,6 +481,13 @@ def memcpy_d2h(device, dst, src, nbytes): _check(lib().mdgpu_memcpy_d2h(device, 
 def device_synchronize(device=0): _check(lib().mdgpu_device_synchronize(device))
 
 
+def debug_sqrt_sweep(lo_bits: int, hi_bits: int, device: int = 0) -> int:
+    n = C.c_uint64()
+    lib().mdgpu_debug_sqrt_sweep.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    _check(lib().mdgpu_debug_sqrt_sweep(device, lo_bits, hi_bits, C.byref(n)))
+    return int(n.value)
+
+
 def water_system(n: int) -> System:
     """Topology of the synthetic water box (OW,HW1,HW2 per molecule; masses as md_atom_extract_masses yields them)."""
     nm = n ** 3; na = 3 * nm

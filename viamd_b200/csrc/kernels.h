@@ -30,6 +30,8 @@ struct RdfArgs {
 };
 void launch_rdf(const RdfArgs& a, int B, bool tri, int variant, int sm_count, cudaStream_t s, cudaEvent_t* ev_beg, cudaEvent_t* ev_end);
 
+unsigned long long run_sqrt_sweep(uint32_t lo_bits, uint32_t hi_bits);
+
 // sdf.cu
 struct SdfArgs {
     const FrameGeom* geom;

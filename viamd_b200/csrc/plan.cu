@@ -758,6 +758,14 @@ int mdgpu_debug_frame_geom(const mdgpu_unitcell_t* cell, double cell_ext, double
     return 0;
 }
 
+int mdgpu_debug_sqrt_sweep(int device, uint32_t lo_bits, uint32_t hi_bits, uint64_t* mismatches) {
+    if (!mismatches) return fail(MDGPU_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    *mismatches = run_sqrt_sweep(lo_bits, hi_bits);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------- synthetic workloads
 int mdgpu_synth_water_desc(uint32_t n, uint32_t seed, uint32_t* num_atoms, float* L) {
     const mdsynth_water_t w = mdsynth_water_desc(n, seed);
