@@ -241,7 +241,7 @@ def main():
         step_device(i)
     if world > 1:
         plan.sync()
-        vdist.allreduce_plan(plan, total_frames=world * K * FPS)   # the one exchange step: bins + voxels over NCCL
+        vdist.allreduce_plan(plan, total_frames=world * (W + K) * FPS)   # the one exchange step: bins + voxels over NCCL
     ms_dev = plan.timer_end()
     barrier()
     t_wall = time.perf_counter() - t_wall0

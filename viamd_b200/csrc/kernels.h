@@ -48,7 +48,7 @@ struct SdfArgs {
     float cutoff;
     float4* scratch_xyzw;            // [B][n_struct+1][struct_size]
     float* ref0;                     // [B][20]: VA(16) com0(3) pad
-    float* matrices;                 // [B][n_struct][16 + 4]: M, com
+    float* matrices;                 // [B][n_struct][32]: M[16] com[3] pad lo[3] hi[3] cmin[3] cmax[3] (ints)
     uint32_t* vol;                   // [128^3] accumulated voxels
     unsigned long long* frame_total; // [num_frames]
     uint32_t frame0;

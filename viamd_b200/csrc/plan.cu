@@ -63,6 +63,7 @@ struct Prop {
     bool frames_overridden = false;
     bool is_dist() const { return op == MDGPU_OP_RDF || (op >= MDGPU_OP_DENSITY_X && op <= MDGPU_OP_DENSITY_Z); }
     bool needs_cells() const { return op == MDGPU_OP_RDF || op == MDGPU_OP_SDF; }
+    int share_trg = -1;   // index of an earlier property with the same target selection and cutoff: its target cell list is reused
 };
 
 struct PropScratch {   // per (stream slot, property)
@@ -102,6 +103,7 @@ struct mdgpu_plan {
     bool timing = false; std::vector<TimedLaunch> timed; double timed_ms = 0; uint64_t timed_n = 0;
     bool tri_seen = false, ortho_seen = false;
     cudaEvent_t t_begin = nullptr; std::vector<cudaEvent_t> t_end;
+    bool dirty = true;   // device accumulators changed since the last fold into the host-visible property data
 };
 
 static int alloc_cell_list(CellList& cl, uint32_t B, uint32_t max_points, uint32_t cap) {
@@ -264,6 +266,10 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
         pr.data.num_values = pr.values.size(); pr.data.values = pr.values.data();
         pr.data.weights = pr.is_dist() ? pr.values.data() + MDGPU_DIST_BINS : nullptr;
     }
+    for (size_t i = 0; i < num_props; ++i) for (size_t j = 0; j < i; ++j) {
+        Prop& a = p->props[i]; Prop& b = p->props[j];
+        if (a.needs_cells() && b.needs_cells() && b.share_trg < 0 && a.cutoff_max == b.cutoff_max && a.h_idx[1] == b.h_idx[1]) { a.share_trg = (int)j; break; }
+    }
     p->frame_mask.assign((num_frames + 63) / 64, 0);
     if (cudaMalloc((void**)&p->d_init, sizeof(float) * 3 * p->axis_stride) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (initial frame)");
     if (mdgpu_plan_clear(p) != 0) { destroy_plan(p); return nullptr; }
@@ -297,6 +303,7 @@ int mdgpu_plan_clear(mdgpu_plan* p) {
     { std::lock_guard<std::mutex> lk(p->mask_mutex); std::fill(p->frame_mask.begin(), p->frame_mask.end(), 0ull); }
     p->interrupt = false;
     p->timed_ms = 0; p->timed_n = 0;
+    p->dirty = true;
     return 0;
 }
 
@@ -353,7 +360,7 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
             s.ps.resize(p->props.size());
             for (size_t i = 0; i < p->props.size(); ++i) {
                 Prop& pr = p->props[i]; PropScratch& ps = s.ps[i];
-                if (pr.needs_cells()) {
+                if (pr.needs_cells() && pr.share_trg < 0) {
                     CUDA_TRY(dalloc(&ps.d_geom, p->B)); CUDA_TRY(dalloc(&ps.d_aabb, (size_t)6 * p->B));
                     int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)pr.h_idx[1].size(), cap); if (rc) return rc;
                 }
@@ -363,7 +370,7 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                 } else if (pr.op == MDGPU_OP_SDF) {
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * (pr.n_struct + 1) * pr.struct_size));
                     CUDA_TRY(dalloc(&ps.d_sdf_ref0, (size_t)p->B * 20));
-                    CUDA_TRY(dalloc(&ps.d_sdf_mats, (size_t)p->B * pr.n_struct * 20));
+                    CUDA_TRY(dalloc(&ps.d_sdf_mats, (size_t)p->B * pr.n_struct * 32));
                 } else if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
                     CUDA_TRY(dalloc(&ps.d_frame_bins64, (size_t)p->B * MDGPU_DIST_BINS));
                 }
@@ -388,7 +395,8 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
     bool all_pbc = true; for (int i = 0; i < B; ++i) all_pbc = all_pbc && ((s.h_cells[i].flags & MDGPU_CELL_PBC_ALL) == MDGPU_CELL_PBC_ALL);
     for (size_t i = 0; i < p->props.size(); ++i) {
         Prop& pr = p->props[i]; PropScratch& ps = s.ps[i];
-        if (pr.needs_cells()) {
+        const PropScratch& cs = (pr.share_trg >= 0) ? s.ps[pr.share_trg] : ps;   // owner of the target cell list + geometry
+        if (pr.needs_cells() && pr.share_trg < 0) {
             const float* aabb = nullptr;
             if (!all_pbc) { launch_aabb(fr, pr.d_idx[1], (uint32_t)pr.h_idx[1].size(), ps.d_aabb, s.stream); aabb = ps.d_aabb; }
             launch_geom(s.d_cells, aabb, ps.d_geom, (double)pr.cutoff_max, (double)pr.cutoff_max, p->cell_cap, B, s.d_err, s.stream);
@@ -396,9 +404,9 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
         }
         switch (pr.op) {
         case MDGPU_OP_RDF: {
-            launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_geom, ps.ref, 0, s.stream);
+            launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), cs.d_geom, ps.ref, 0, s.stream);
             RdfArgs a{};
-            a.geom = ps.d_geom; a.trg = ps.trg; a.ref = ps.ref;
+            a.geom = cs.d_geom; a.trg = cs.trg; a.ref = ps.ref;
             a.inv_cutoff_range = 1.0f / (pr.cutoff_max - pr.cutoff_min);                 // before the clamp (compute_rdf :5264)
             a.min_cutoff = pr.cutoff_min > 1e-3f ? pr.cutoff_min : 1e-3f;                 // :5269
             a.min_r2 = a.min_cutoff * a.min_cutoff;                                       // rdf_cb :5233
@@ -413,7 +421,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "sdf '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
             if (tri) return fail(MDGPU_ERR_UNSUPPORTED, "sdf '%s': triclinic unit cells are not implemented yet", pr.name.c_str());
             SdfArgs a{};
-            a.geom = ps.d_geom; a.trg = ps.trg; a.frames = fr; a.cells = s.d_cells;
+            a.geom = cs.d_geom; a.trg = cs.trg; a.frames = fr; a.cells = s.d_cells;
             a.init_xyz = p->d_init; a.init_axis_stride = p->axis_stride; a.mass = p->d_mass;
             a.struct_idx = pr.d_idx[0]; a.n_struct = (uint32_t)pr.n_struct; a.struct_size = (uint32_t)pr.struct_size;
             a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap; a.cutoff = pr.cutoff_max;
@@ -442,6 +450,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s.done, s.stream));
     s.busy = true; s.pending_beg = frame0; s.pending_cnt = (uint32_t)B;
+    p->dirty = true;
     return 0;
 }
 
@@ -579,6 +588,7 @@ int mdgpu_plan_sync(mdgpu_plan* p) {
     if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
     CUDA_TRY(cudaSetDevice(p->device));
     for (auto& s : p->slots) { int rc = retire_slot(p, s); if (rc) return rc; }
+    if (!p->dirty) return 0;
     CUDA_TRY(cudaDeviceSynchronize());
     for (auto& s : p->slots) {
         int err = 0; CUDA_TRY(cudaMemcpy(&err, s.d_err, sizeof(int), cudaMemcpyDeviceToHost));
@@ -644,6 +654,7 @@ int mdgpu_plan_sync(mdgpu_plan* p) {
             else { pr.data.min_range[0] = pr.data.min_value; pr.data.max_range[0] = pr.data.max_value; }
         }
     }
+    p->dirty = false;
     return 0;
 }
 
@@ -709,7 +720,7 @@ int mdgpu_plan_property_accum_ptr(mdgpu_plan* p, size_t prop, void** d_ptr, size
 
 int mdgpu_plan_set_frames_accumulated(mdgpu_plan* p, size_t prop, uint64_t frames) {
     if (!p || prop >= p->props.size()) return fail(MDGPU_ERR_INVALID_ARG, "invalid argument");
-    p->props[prop].frames_accumulated = frames; p->props[prop].frames_overridden = true;
+    p->props[prop].frames_accumulated = frames; p->props[prop].frames_overridden = true; p->dirty = true;
     return 0;
 }
 

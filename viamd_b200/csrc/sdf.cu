@@ -12,6 +12,8 @@
 
 namespace mdg {
 
+constexpr int SDF_REC = 32;   // floats per structure record: M[16] com[3] pad lo[3] hi[3] cmin[3] cmax[3]
+
 // ------------------------------------------------------------------------------------------------- 3x3 SVD (McAdams)
 struct M3 { float e[3][3]; };   // e[col][row] as in the reference's mat3_t; the svd routine itself is row-major A[r][c]
 struct M4 { float e[4][4]; };
@@ -266,35 +268,17 @@ __global__ void k_sdf_fit(SdfArgs a, int B) {
     const M4 RT = m4_mul(m4_from_m3(R), Tm);
     M4 VA; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) VA.e[i][j] = r0[i * 4 + j];
     const M4 M = m4_mul(VA, RT);
-    float* o = a.matrices + ((size_t)f * a.n_struct + s) * 20;
+    float* o = a.matrices + ((size_t)f * a.n_struct + s) * SDF_REC;
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) o[i * 4 + j] = M.e[i][j];
     o[16] = com1[0]; o[17] = com1[1]; o[18] = com1[2]; o[19] = 0.0f;
-}
 
-MDG_D int wrap_coord(int v, int N) { v += (v < 0) ? N : 0; v -= (v >= N) ? N : 0; return v; }
-MDG_D int isign(int v) { return (v > 0) - (v < 0); }
-
-// K4: one warp per (structure, frame): points of the target cell list inside the AABB(com, cutoff) -> voxel increments
-constexpr int SDF_WARPS = 4;
-__global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B) {
-    const int f = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const uint32_t s = blockIdx.x * SDF_WARPS + (threadIdx.x >> 5);
-    if (s >= a.n_struct) return;
+    // cell_range_from_aabb_center_radius + the fractional bounds of for_each_point_in_aabb_ortho (core/md_spatial_acc.c:1805-1923),
+    // double precision with the float matrix entries widened, evaluated once per structure
     const FrameGeom& g = a.geom[f];
-    if (g.valid == -1 || (g.flags & MDGPU_CELL_TRICLINIC)) return;   // triclinic AABB query: not implemented (reported by the host)
-    const float* mrow = a.matrices + ((size_t)f * a.n_struct + s) * 20;
-    float M[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) M[i][j] = mrow[i * 4 + j];
-    const double cen[3] = { (double)mrow[16], (double)mrow[17], (double)mrow[18] };
+    const double cen[3] = { (double)com1[0], (double)com1[1], (double)com1[2] };
     const double rad = (double)a.cutoff;
     const int pbc[3] = { (g.flags & MDGPU_CELL_PBC_X) != 0, (g.flags & MDGPU_CELL_PBC_Y) != 0, (g.flags & MDGPU_CELL_PBC_Z) != 0 };
-    const int cd[3] = { g.cdim[0], g.cdim[1], g.cdim[2] };
-    // cell_range_from_aabb_center_radius (:1805-1879), double precision with the float matrix entries widened
-    double sc[3], cc[3];
+    double sc[3], ccen[3];
     {
         const double px = cen[0] - g.origin[0], py = cen[1] - g.origin[1], pz = cen[2] - g.origin[2];
         sc[0] = g.I[0][0] * px + g.I[1][0] * py + g.I[2][0] * pz;
@@ -302,12 +286,12 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
         sc[2] = g.I[0][2] * px + g.I[1][2] * py + g.I[2][2] * pz;
     }
     for (int k = 0; k < 3; ++k) if (pbc[k]) sc[k] = sc[k] - floor(sc[k]);
-    cc[0] = g.A[0][0] * sc[0] + g.A[1][0] * sc[1] + g.A[2][0] * sc[2] + g.origin[0];
-    cc[1] = g.A[0][1] * sc[0] + g.A[1][1] * sc[1] + g.A[2][1] * sc[2] + g.origin[1];
-    cc[2] = g.A[0][2] * sc[0] + g.A[1][2] * sc[1] + g.A[2][2] * sc[2] + g.origin[2];
+    ccen[0] = g.A[0][0] * sc[0] + g.A[1][0] * sc[1] + g.A[2][0] * sc[2] + g.origin[0];
+    ccen[1] = g.A[0][1] * sc[0] + g.A[1][1] * sc[1] + g.A[2][1] * sc[2] + g.origin[1];
+    ccen[2] = g.A[0][2] * sc[0] + g.A[1][2] * sc[1] + g.A[2][2] * sc[2] + g.origin[2];
     double fmin_[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, fmax_[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
     for (int corner = 0; corner < 8; ++corner) {
-        const double pz = cc[2] + ((corner & 4) ? rad : -rad), py = cc[1] + ((corner & 2) ? rad : -rad), px = cc[0] + ((corner & 1) ? rad : -rad);
+        const double pz = ccen[2] + ((corner & 4) ? rad : -rad), py = ccen[1] + ((corner & 2) ? rad : -rad), px = ccen[0] + ((corner & 1) ? rad : -rad);
         const double qx = px - g.origin[0], qy = py - g.origin[1], qz = pz - g.origin[2];
         double sv[3];
         sv[0] = g.I[0][0] * qx + g.I[1][0] * qy + g.I[2][0] * qz;
@@ -315,36 +299,94 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
         sv[2] = g.I[0][2] * qx + g.I[1][2] * qy + g.I[2][2] * qz;
         for (int k = 0; k < 3; ++k) { fmin_[k] = fmin(fmin_[k], sv[k]); fmax_[k] = fmax(fmax_[k], sv[k]); }
     }
-    int cmin[3], cmax[3]; float lo3[3], hi3[3];
+    int* oi = (int*)(o + 26);
     for (int k = 0; k < 3; ++k) {
+        const int cdk = g.cdim[k];
         double frad = 0.5 * (fmax_[k] - fmin_[k]);
-        int lo = (int)floor(fmin_[k] * (double)cd[k]), hi = (int)ceil(fmax_[k] * (double)cd[k]);
+        int lo = (int)floor(fmin_[k] * (double)cdk), hi = (int)ceil(fmax_[k] * (double)cdk);
         if (hi <= lo) hi = lo + 1;
-        if (!pbc[k]) { lo = max(0, min(lo, cd[k])); hi = max(0, min(hi, cd[k])); if (hi <= lo) hi = min(lo + 1, cd[k]); }
-        cmin[k] = lo; cmax[k] = hi;
+        if (!pbc[k]) { lo = max(0, min(lo, cdk)); hi = max(0, min(hi, cdk)); if (hi <= lo) hi = min(lo + 1, cdk); }
         frad = fmin(frad, 0.5);
-        lo3[k] = (float)(sc[k] - frad); hi3[k] = (float)(sc[k] + frad);
+        o[20 + k] = (float)(sc[k] - frad); o[23 + k] = (float)(sc[k] + frad);
+        oi[k] = lo; oi[3 + k] = hi;
     }
+}
+
+MDG_D int wrap_coord(int v, int N) { v += (v < 0) ? N : 0; v -= (v >= N) ? N : 0; return v; }
+MDG_D int isign(int v) { return (v > 0) - (v < 0); }
+
+// K4: one warp per (structure, frame): target points of the cells overlapping AABB(com, cutoff) -> voxel increments.
+// The cells of the range are flattened into one index range (prefix table in shared memory) so that all 32 lanes stay busy.
+constexpr int SDF_WARPS = 8;
+constexpr int SDF_MAXSEG = 128;
+__global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B) {
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t s = blockIdx.x * SDF_WARPS + warp;
+    __shared__ uint32_t s_pre[SDF_WARPS][SDF_MAXSEG + 1];
+    __shared__ uint32_t s_start[SDF_WARPS][SDF_MAXSEG];
+    __shared__ uint32_t s_code[SDF_WARPS][SDF_MAXSEG];
+    if (s >= a.n_struct) return;
+    const FrameGeom& g = a.geom[f];
+    if (g.valid == -1 || (g.flags & MDGPU_CELL_TRICLINIC)) return;   // triclinic AABB query: rejected by the host
+    const float* rec = a.matrices + ((size_t)f * a.n_struct + s) * SDF_REC;
+    float M[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) M[i][j] = rec[i * 4 + j];
+    const float lo3[3] = { rec[20], rec[21], rec[22] }, hi3[3] = { rec[23], rec[24], rec[25] };
+    const int* ri = (const int*)(rec + 26);
+    const int cmin[3] = { ri[0], ri[1], ri[2] }, cmax[3] = { ri[3], ri[4], ri[5] };
+    const int pbc[3] = { (g.flags & MDGPU_CELL_PBC_X) != 0, (g.flags & MDGPU_CELL_PBC_Y) != 0, (g.flags & MDGPU_CELL_PBC_Z) != 0 };
+    const int cd[3] = { g.cdim[0], g.cdim[1], g.cdim[2] };
+    const float A00 = g.A[0][0], A11 = g.A[1][1], A22 = g.A[2][2], O0 = g.origin[0], O1 = g.origin[1], O2 = g.origin[2];
     const float4* __restrict__ pts = a.trg.sorted + (size_t)f * a.trg.max_points;
     const uint32_t* __restrict__ off = a.trg.cell_cnt + (size_t)f * (a.trg.cap + 1);
     const int32_t* sidx = a.struct_idx + (size_t)s * a.struct_size;
+    const int ex = cmax[0] - cmin[0], ey = cmax[1] - cmin[1], ez = cmax[2] - cmin[2];
+    const int ncells = ex * ey * ez;
     unsigned long long local = 0;
-    for (int icz = cmin[2]; icz < cmax[2]; ++icz) { const int cz = pbc[2] ? wrap_coord(icz, cd[2]) : icz; const float shz = (float)isign(icz - cz);
-    for (int icy = cmin[1]; icy < cmax[1]; ++icy) { const int cy = pbc[1] ? wrap_coord(icy, cd[1]) : icy; const float shy = (float)isign(icy - cy);
-    for (int icx = cmin[0]; icx < cmax[0]; ++icx) { const int cx = pbc[0] ? wrap_coord(icx, cd[0]) : icx; const float shx = (float)isign(icx - cx);
-        if (cx < 0 || cx >= cd[0] || cy < 0 || cy >= cd[1] || cz < 0 || cz >= cd[2]) continue;
-        const uint32_t ci = ((uint32_t)cz * (uint32_t)cd[1] + (uint32_t)cy) * (uint32_t)cd[0] + (uint32_t)cx;
-        const uint32_t o = off[ci], len = off[ci + 1] - o;
-        for (uint32_t j = lane; j < len; j += 32) {
-            const float4 t = pts[o + j];
-            const float vx = __fadd_rn(t.x, shx), vy = __fadd_rn(t.y, shy), vz = __fadd_rn(t.z, shz);
+    for (int c0 = 0; c0 < ncells; c0 += SDF_MAXSEG) {   // (:1925-1943) cells of the range, SDF_MAXSEG at a time
+        const int nc = min(SDF_MAXSEG, ncells - c0);
+        uint32_t base = 0;
+        __syncwarp();
+        for (int n0 = 0; n0 < nc; n0 += 32) {
+            const int n = n0 + lane;
+            uint32_t len = 0, start = 0, code = 0x15;
+            if (n < nc) {
+                const int q = c0 + n;
+                const int icx = cmin[0] + q % ex, icy = cmin[1] + (q / ex) % ey, icz = cmin[2] + q / (ex * ey);
+                const int cx = pbc[0] ? wrap_coord(icx, cd[0]) : icx, cy = pbc[1] ? wrap_coord(icy, cd[1]) : icy, cz = pbc[2] ? wrap_coord(icz, cd[2]) : icz;
+                if (!(cx < 0 || cx >= cd[0] || cy < 0 || cy >= cd[1] || cz < 0 || cz >= cd[2])) {
+                    const uint32_t ci = ((uint32_t)cz * (uint32_t)cd[1] + (uint32_t)cy) * (uint32_t)cd[0] + (uint32_t)cx;
+                    start = off[ci]; len = off[ci + 1] - start;
+                    code = (uint32_t)(isign(icx - cx) + 1) | ((uint32_t)(isign(icy - cy) + 1) << 2) | ((uint32_t)(isign(icz - cz) + 1) << 4);
+                }
+            }
+            uint32_t incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (n < nc) { s_pre[warp][n] = base + incl - len; s_start[warp][n] = start; s_code[warp][n] = code; }
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        const uint32_t total = base;
+        if (lane == 0) s_pre[warp][nc] = total;
+        __syncwarp();
+        for (uint32_t j = lane; j < total; j += 32) {
+            int lo = 0, hi = nc;   // last k with pre[k] <= j (empty segments allowed)
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[warp][mid] <= j) lo = mid; else hi = mid; }
+            const float4 t = pts[s_start[warp][lo] + (j - s_pre[warp][lo])];
+            const uint32_t code = s_code[warp][lo];
+            const float shx = (float)((int)(code & 3u) - 1), shy = (float)((int)((code >> 2) & 3u) - 1), shz = (float)((int)((code >> 4) & 3u) - 1);
+            const float vx = __fadd_rn(t.x, shx), vy = __fadd_rn(t.y, shy), vz = __fadd_rn(t.z, shz);   // (:1962-1964)
             if (!(vx >= lo3[0] && vy >= lo3[1] && vz >= lo3[2] && vx <= hi3[0] && vy <= hi3[1] && vz <= hi3[2])) continue;
             const uint32_t idx = __float_as_uint(t.w);
             bool excluded = false;   // md_bitfield_test_bit(exclusion_mask, idx): the structure's own atoms (:5674)
             for (uint32_t k = 0; k < a.struct_size; ++k) excluded |= ((uint32_t)sidx[k] == idx);
             if (excluded) continue;
             // batch_fract_to_cart_ort_256: one fused multiply-add per axis (:583-592)
-            const float px = __fmaf_rn(vx, g.A[0][0], g.origin[0]), py = __fmaf_rn(vy, g.A[1][1], g.origin[1]), pz = __fmaf_rn(vz, g.A[2][2], g.origin[2]);
+            const float px = __fmaf_rn(vx, A00, O0), py = __fmaf_rn(vy, A11, O1), pz = __fmaf_rn(vz, A22, O2);
             float c[3];   // mat4_mul_vec4(M, (x,y,z,1)) = ((x*M0 + y*M1) + z*M2) + 1*M3
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -360,7 +402,7 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
             atomicAdd(&a.vol[((size_t)iz * MDGPU_VOL_DIM + iy) * MDGPU_VOL_DIM + ix], 1u);
             local += 1;
         }
-    } } }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if (lane == 0 && local) atomicAdd(&a.frame_total[a.frame0 + f], local);
