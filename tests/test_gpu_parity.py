@@ -223,6 +223,15 @@ def test_oracle_water_sdf_bitexact_and_batching():
     assert int(results[0].sum()) == int(ref.sum()) > 0
     assert np.array_equal(results[0].astype(np.float32), ref)
     assert np.array_equal(results[0], results[1]) and np.array_equal(results[0], results[2])
+    # non-contiguous structures (O + second H of each molecule): exercises the general exclusion-mask path
+    st2 = np.stack([np.arange(60) * 3, np.arange(60) * 3 + 2], axis=1).astype(np.int32)
+    ref2 = np.zeros(128 ** 3, np.float32)
+    for f in range(F):
+        O.sdf_frame(frames[f, 0], frames[f, 1], frames[f, 2], frames[0], sysm.mass, st2, o, sysm.conn_offset, sysm.conn_idx, ocell, 7.5, vol=ref2)
+    plan = vb.Plan(sysm, [vb.sdf("v", st2, o, 7.5)], F)
+    plan.set_initial_frame(*frames[0], cell); plan.eval_host_frames(frames, cell, 0)
+    assert np.array_equal(plan.counts("v").astype(np.float32), ref2) and ref2.sum() > 0
+    plan.close()
 
 
 def test_empty_and_error_paths():

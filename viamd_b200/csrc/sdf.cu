@@ -319,6 +319,7 @@ MDG_D int isign(int v) { return (v > 0) - (v < 0); }
 // The cells of the range are flattened into one index range (prefix table in shared memory) so that all 32 lanes stay busy.
 constexpr int SDF_WARPS = 8;
 constexpr int SDF_MAXSEG = 128;
+constexpr int SDF_EXCL_CACHE = 64;
 __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B) {
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -344,12 +345,18 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
     const float4* __restrict__ pts = a.trg.sorted + (size_t)f * a.trg.max_points;
     const uint32_t* __restrict__ off = a.trg.cell_cnt + (size_t)f * (a.trg.cap + 1);
     const int32_t* sidx = a.struct_idx + (size_t)s * a.struct_size;
+    // exclusion mask = the structure's own atoms (:5674). Ascending index lists: a contiguous run (the usual case: a residue)
+    // is tested with one compare; otherwise the list (cached in shared memory when it fits) is scanned.
+    const uint32_t ex_lo = (uint32_t)sidx[0], ex_n = a.struct_size;
+    const bool ex_contig = ((uint32_t)sidx[a.struct_size - 1] - ex_lo + 1u) == ex_n;
+    __shared__ int32_t s_excl[SDF_WARPS][SDF_EXCL_CACHE];
+    if (!ex_contig) { for (uint32_t k = lane; k < min(ex_n, (uint32_t)SDF_EXCL_CACHE); k += 32) s_excl[warp][k] = sidx[k]; }
     const int ex = cmax[0] - cmin[0], ey = cmax[1] - cmin[1], ez = cmax[2] - cmin[2];
     const int ncells = ex * ey * ez;
     unsigned long long local = 0;
     for (int c0 = 0; c0 < ncells; c0 += SDF_MAXSEG) {   // (:1925-1943) cells of the range, SDF_MAXSEG at a time
         const int nc = min(SDF_MAXSEG, ncells - c0);
-        uint32_t base = 0;
+        uint32_t base = 0; int nseg = 0;
         __syncwarp();
         for (int n0 = 0; n0 < nc; n0 += 32) {
             const int n = n0 + lane;
@@ -364,26 +371,38 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
                     code = (uint32_t)(isign(icx - cx) + 1) | ((uint32_t)(isign(icy - cy) + 1) << 2) | ((uint32_t)(isign(icz - cz) + 1) << 4);
                 }
             }
+            const uint32_t have = __ballot_sync(0xffffffffu, len != 0u);   // keep non-empty cells only
             uint32_t incl = len;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (n < nc) { s_pre[warp][n] = base + incl - len; s_start[warp][n] = start; s_code[warp][n] = code; }
+            if (len) { const int slot = nseg + __popc(have & ((1u << lane) - 1u)); s_pre[warp][slot] = base + incl - len; s_start[warp][slot] = start; s_code[warp][slot] = code; }
             base += __shfl_sync(0xffffffffu, incl, 31);
+            nseg += __popc(have);
         }
         const uint32_t total = base;
-        if (lane == 0) s_pre[warp][nc] = total;
+        if (lane == 0) s_pre[warp][nseg] = total;
         __syncwarp();
-        for (uint32_t j = lane; j < total; j += 32) {
-            int lo = 0, hi = nc;   // last k with pre[k] <= j (empty segments allowed)
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[warp][mid] <= j) lo = mid; else hi = mid; }
-            const float4 t = pts[s_start[warp][lo] + (j - s_pre[warp][lo])];
-            const uint32_t code = s_code[warp][lo];
+        int kbase = 0;
+        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+            while (kbase + 1 < nseg && s_pre[warp][kbase + 1] <= j0) ++kbase;   // warp-uniform
+            const uint32_t j = j0 + lane;
+            if (j >= total) continue;
+            int k = kbase;
+            while (s_pre[warp][k + 1] <= j) ++k;
+            const float4 t = pts[s_start[warp][k] + (j - s_pre[warp][k])];
+            const uint32_t code = s_code[warp][k];
             const float shx = (float)((int)(code & 3u) - 1), shy = (float)((int)((code >> 2) & 3u) - 1), shz = (float)((int)((code >> 4) & 3u) - 1);
             const float vx = __fadd_rn(t.x, shx), vy = __fadd_rn(t.y, shy), vz = __fadd_rn(t.z, shz);   // (:1962-1964)
             if (!(vx >= lo3[0] && vy >= lo3[1] && vz >= lo3[2] && vx <= hi3[0] && vy <= hi3[1] && vz <= hi3[2])) continue;
             const uint32_t idx = __float_as_uint(t.w);
-            bool excluded = false;   // md_bitfield_test_bit(exclusion_mask, idx): the structure's own atoms (:5674)
-            for (uint32_t k = 0; k < a.struct_size; ++k) excluded |= ((uint32_t)sidx[k] == idx);
+            bool excluded;
+            if (ex_contig) excluded = (idx - ex_lo) < ex_n;
+            else {
+                excluded = false;
+                const uint32_t nc_ = min(ex_n, (uint32_t)SDF_EXCL_CACHE);
+                for (uint32_t q = 0; q < nc_; ++q) excluded |= ((uint32_t)s_excl[warp][q] == idx);
+                for (uint32_t q = nc_; q < ex_n; ++q) excluded |= ((uint32_t)sidx[q] == idx);
+            }
             if (excluded) continue;
             // batch_fract_to_cart_ort_256: one fused multiply-add per axis (:583-592)
             const float px = __fmaf_rn(vx, A00, O0), py = __fmaf_rn(vy, A11, O1), pz = __fmaf_rn(vz, A22, O2);
