@@ -1,0 +1,169 @@
+/* md_script_mdgpu.inl — the reference-side binding of libmdgpu (include/mdgpu.h).
+ *
+ * HOW A MAINTAINER USES IT: add `#include "md_script_mdgpu.inl"` at the end of mdlib/src/md_script.c (it needs
+ * the translation unit's private types: md_script_ir_t, ast_node_t, data_t — the same trick the reference's own white-box tests use,
+ * mdlib/unittest/test_script.c:20) and call md_script_gpu_eval_frame_range where VIAMD calls md_script_eval_frame_range
+ * (src/main.cpp:993-997, 1029-1033). Nothing else in mdlib changes: the tokenizer, parser, static type check and static evaluation
+ * of selections stay as they are; this file only LOWERS the compiled IR's property statements to flat descriptors.
+ *
+ * Lowering rule: a property statement `ident = proc(args);` is accepted when proc is on the GPU hot path (rdf, sdf, density_x/_y/_z,
+ * distance, angle, dihedral) and every argument was evaluated statically at compile time (FLAG_CONSTANT, md_script.c:5492-5524), i.e.
+ * selections are fixed atom sets. Bitfields become ascending atom index lists (md_bitfield_iter_extract_indices), 1-based script atom
+ * indices become 0-based. Anything else is reported through MD_LOG_ERROR and the call returns false — there is no silent CPU fallback.
+ *
+ * This file is written against the reference's private API on purpose and contains no reference code.
+ */
+#include <mdgpu.h>
+
+typedef struct md_script_gpu_lowered_t {
+    size_t num_props;
+    mdgpu_property_desc_t* props;   /* arena-allocated, as are the index lists they point to */
+    char (*names)[64];
+} md_script_gpu_lowered_t;
+
+static const ast_node_t* mdgpu__rhs(const ast_node_t* node) {
+    /* property nodes are the assignment `ident = expr` (extract_properties, md_script.c:6173-6193) */
+    if (node->type == AST_ASSIGNMENT && node->children && md_array_size(node->children) == 2) return node->children[1];
+    return node;
+}
+
+/* static argument -> ascending 0-based atom index list (concatenated over all bitfields of an array); returns count, -1 on error */
+static int64_t mdgpu__arg_indices(int32_t** out, size_t* out_num_sets, size_t* out_set_size, const ast_node_t* arg, md_allocator_i* alloc) {
+    if (!(arg->flags & FLAG_CONSTANT) || !arg->data.ptr) return -1;
+    const data_t d = arg->data;
+    if (d.type.base_type == TYPE_BITFIELD) {
+        const md_bitfield_t* bf = (const md_bitfield_t*)d.ptr;
+        const size_t n = element_count(d);
+        size_t total = 0; size_t set_size = 0; bool uniform = true;
+        for (size_t i = 0; i < n; ++i) { const size_t c = md_bitfield_popcount(&bf[i]); if (i == 0) set_size = c; else if (c != set_size) uniform = false; total += c; }
+        int32_t* idx = (int32_t*)md_alloc(alloc, sizeof(int32_t) * (total ? total : 1));
+        size_t off = 0;
+        for (size_t i = 0; i < n; ++i) { const size_t c = md_bitfield_popcount(&bf[i]); md_bitfield_iter_extract_indices(idx + off, c, md_bitfield_iter_create(&bf[i])); off += c; }
+        *out = idx; if (out_num_sets) *out_num_sets = n; if (out_set_size) *out_set_size = uniform ? set_size : 0;
+        return (int64_t)total;
+    }
+    if (d.type.base_type == TYPE_INT) {
+        const int32_t* v = (const int32_t*)d.ptr;
+        const size_t n = element_count(d);
+        int32_t* idx = (int32_t*)md_alloc(alloc, sizeof(int32_t) * (n ? n : 1));
+        for (size_t i = 0; i < n; ++i) idx[i] = v[i] - 1;   /* remap_index_to_context with the whole system as context (md_script_functions.inl:1023) */
+        *out = idx; if (out_num_sets) *out_num_sets = 1; if (out_set_size) *out_set_size = n;
+        return (int64_t)n;
+    }
+    return -1;
+}
+
+static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const ast_node_t* node, md_allocator_i* alloc) {
+    const ast_node_t* rhs = mdgpu__rhs(node);
+    if (rhs->type != AST_PROC_CALL || !rhs->proc) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "' is not a direct procedure call", STR_ARG(ident)); return false; }
+    const str_t pname = rhs->proc->name;
+    const size_t nargs = md_array_size(rhs->children);
+    ast_node_t** args = rhs->children;
+    memset(out, 0, sizeof(*out));
+    size_t nsets = 0, set_size = 0; int64_t n;
+    if (str_eq(pname, STR_LIT("rdf")) && nargs == 3) {
+        out->op = MDGPU_OP_RDF;
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &nsets, &set_size, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
+        if (args[0]->data.type.base_type == TYPE_BITFIELD && nsets > 1) { out->num_structures = nsets; out->structure_size = set_size; }   /* COM references + exclusion (:5275) */
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[1], NULL, NULL, args[1], alloc)) < 0) goto dynamic; out->idx_count[1] = (size_t)n;
+        if (!(args[2]->flags & FLAG_CONSTANT)) goto dynamic;
+        if (args[2]->data.type.base_type == TYPE_FRANGE) { const frange_t r = *(const frange_t*)args[2]->data.ptr; out->cutoff_min = r.beg; out->cutoff_max = r.end; }
+        else { out->cutoff_min = 0.0f; out->cutoff_max = *(const float*)args[2]->data.ptr; }
+        return true;
+    }
+    if (str_eq(pname, STR_LIT("sdf")) && nargs == 3) {
+        out->op = MDGPU_OP_SDF;
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &nsets, &set_size, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
+        out->num_structures = nsets; out->structure_size = set_size;
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[1], NULL, NULL, args[1], alloc)) < 0) goto dynamic; out->idx_count[1] = (size_t)n;
+        if (!(args[2]->flags & FLAG_CONSTANT)) goto dynamic;
+        out->cutoff_max = *(const float*)args[2]->data.ptr;
+        return true;
+    }
+    if ((str_eq(pname, STR_LIT("density_x")) || str_eq(pname, STR_LIT("density_y")) || str_eq(pname, STR_LIT("density_z"))) && nargs == 1) {
+        out->op = MDGPU_OP_DENSITY_X + (uint32_t)(pname.ptr[8] - 'x');
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], NULL, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
+        /* _internal_flatten_bf: union of the bitfields; concatenated lists of disjoint sets are already that union. Sort + unique for safety. */
+        int32_t* v = (int32_t*)out->idx[0];
+        for (size_t i = 1; i < out->idx_count[0]; ++i) { int32_t t = v[i]; size_t j = i; while (j > 0 && v[j - 1] > t) { v[j] = v[j - 1]; --j; } v[j] = t; }
+        size_t w = 0; for (size_t i = 0; i < out->idx_count[0]; ++i) if (w == 0 || v[i] != v[w - 1]) v[w++] = v[i];
+        out->idx_count[0] = w;
+        return true;
+    }
+    {
+        const bool dist = str_eq(pname, STR_LIT("distance")), ang = str_eq(pname, STR_LIT("angle")), dih = str_eq(pname, STR_LIT("dihedral"));
+        const size_t need = dist ? 2 : (ang ? 3 : (dih ? 4 : 0));
+        if (need && nargs == need) {
+            out->op = dist ? MDGPU_OP_DISTANCE : (ang ? MDGPU_OP_ANGLE : MDGPU_OP_DIHEDRAL);
+            for (size_t k = 0; k < need; ++k) { if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], NULL, NULL, args[k], alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n; }
+            return true;
+        }
+    }
+    MD_LOG_ERROR("mdgpu: procedure '" STR_FMT "' of property '" STR_FMT "' is outside the GPU hot-path scope", STR_ARG(pname), STR_ARG(ident));
+    return false;
+dynamic:
+    MD_LOG_ERROR("mdgpu: property '" STR_FMT "' has a dynamic (per-frame) argument; only static selections are lowered", STR_ARG(ident));
+    return false;
+}
+
+/* Lower every property of a compiled script. */
+static bool md_script_gpu_lower(md_script_gpu_lowered_t* out, const md_script_ir_t* ir, md_allocator_i* alloc) {
+    const size_t np = md_array_size(ir->property_names);
+    out->num_props = np;
+    out->props = (mdgpu_property_desc_t*)md_alloc(alloc, sizeof(mdgpu_property_desc_t) * (np ? np : 1));
+    out->names = (char(*)[64])md_alloc(alloc, 64 * (np ? np : 1));
+    for (size_t i = 0; i < np; ++i) {
+        if (!mdgpu__lower_property(&out->props[i], ir->property_names[i], ir->property_nodes[i], alloc)) return false;
+        const str_t nm = ir->property_names[i];
+        memset(out->names[i], 0, 64); memcpy(out->names[i], nm.ptr, nm.len < 63 ? nm.len : 63);
+        out->props[i].name = out->names[i];
+    }
+    return true;
+}
+
+/* md_script_eval_create counterpart for the device side: the plan holds what md_script_eval_t holds on the host. */
+static mdgpu_plan* md_script_gpu_plan_create(const md_script_ir_t* ir, const md_system_t* mol, size_t num_frames, int device, md_allocator_i* alloc) {
+    md_script_gpu_lowered_t low = {0};
+    if (!md_script_gpu_lower(&low, ir, alloc)) return NULL;
+    float* mass = (float*)md_alloc(alloc, sizeof(float) * mol->atom.count);
+    md_atom_extract_masses(mass, 0, mol->atom.count, &mol->atom);                       /* as eval_properties does, md_script.c:5764 */
+    mdgpu_system_desc_t sys = {0};
+    sys.num_atoms = mol->atom.count; sys.atom_mass = mass;
+    sys.bond_conn_offset = mol->bond.conn.offset; sys.bond_conn_atom_idx = mol->bond.conn.atom_idx; sys.bond_conn_offset_count = mol->bond.conn.offset_count;
+    mdgpu_plan_options_t opt = {0}; opt.device = device;
+    mdgpu_plan* plan = mdgpu_plan_create(&sys, low.props, low.num_props, num_frames, &opt);
+    if (!plan) MD_LOG_ERROR("mdgpu: %s", mdgpu_last_error());
+    return plan;
+}
+
+/* md_script_eval_frame_range with the frame loop on the GPU: same arguments plus the plan; fills eval->property_data exactly where the
+ * CPU path does (values, weights, min/max, ranges), sets the completed-frame bits, stamps a fresh fingerprint (md_script.c:6604-6609). */
+static bool md_script_gpu_eval_frame_range(mdgpu_plan* plan, md_script_eval_t* eval, const md_script_ir_t* ir, const md_trajectory_i* traj,
+                                           uint32_t frame_beg, uint32_t frame_end, uint32_t loader_threads) {
+    (void)ir;
+    if (mdgpu_eval_trajectory(plan, (const mdgpu_trajectory_i*)traj, frame_beg, frame_end, loader_threads) != 0 || mdgpu_plan_sync(plan) != 0) {
+        MD_LOG_ERROR("mdgpu: %s", mdgpu_last_error());
+        return false;
+    }
+    const size_t np = md_array_size(eval->property_data);
+    for (size_t i = 0; i < np; ++i) {
+        mdgpu_property_data_t d;
+        if (mdgpu_plan_property_data(plan, i, &d) != 0) { MD_LOG_ERROR("mdgpu: %s", mdgpu_last_error()); return false; }
+        md_script_property_data_t* p = &eval->property_data[i];
+        if (d.num_values != p->num_values) { MD_LOG_ERROR("mdgpu: property %zu layout mismatch", i); return false; }
+        MEMCPY(p->values, d.values, sizeof(float) * d.num_values);
+        p->min_value = d.min_value; p->max_value = d.max_value;
+        p->min_range[0] = d.min_range[0]; p->max_range[0] = d.max_range[0];
+    }
+    const size_t nwords = (eval->frame_count + 63) / 64;
+    uint64_t* words = (uint64_t*)md_alloc(md_get_heap_allocator(), sizeof(uint64_t) * (nwords ? nwords : 1));
+    if (mdgpu_plan_frame_mask(plan, words, nwords) == 0) {
+        md_mutex_lock(&eval->frame_lock);
+        for (size_t f = 0; f < eval->frame_count; ++f) if (words[f >> 6] >> (f & 63) & 1ull) md_bitfield_set_bit(&eval->frame_mask, f);
+        md_mutex_unlock(&eval->frame_lock);
+    }
+    md_free(md_get_heap_allocator(), words, sizeof(uint64_t) * (nwords ? nwords : 1));
+    const uint64_t fingerprint = generate_fingerprint();
+    for (size_t i = 0; i < np; ++i) eval->property_data[i].fingerprint = fingerprint;
+    return true;
+}

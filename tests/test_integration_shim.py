@@ -1,0 +1,70 @@
+"""The drop-in boundary, end to end: the reference's own md_script.c + integration/md_script_mdgpu.inl compiled as one translation
+unit (oracle/_ref/shim_harness, built where /root/reference exists; the prebuilt binary travels to the GPU box).
+ - CPU: the shim's lowering of a compiled md_script IR equals viamd_b200.script's lowering (same ops, index lists, cutoffs).
+ - GPU: md_script_eval_frame_range (reference CPU path) vs md_script_gpu_eval_frame_range (libmdgpu) on the same script."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "oracle", "_ref", "shim_harness")
+TOOL = os.path.join(ROOT, "oracle", "build", "synth_tool")
+
+SCRIPT = ("r = rdf(element('O'), element('O'), 6.0); v = sdf(residue(1:20), element('O'), 5.0); dz = density_z(element('O')); "
+          "d = distance(1,10); rr = rdf(element('O'), element('H'), 1.5:6.0); a = angle(1,2,3); t = dihedral(1,4,7,10);")
+
+
+def _need():
+    if not os.path.exists(SHIM):
+        pytest.skip("oracle/_ref/shim_harness not built (needs /root/reference: make -C oracle ref)")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+
+
+def _read_lowered(path):
+    b = open(path, "rb").read(); assert b[:8] == b"MDLOWER1"
+    n, = struct.unpack_from("<Q", b, 8); off = 16; out = []
+    for _ in range(n):
+        name = b[off:off + 64].split(b"\0")[0].decode(); off += 64
+        op, ns, ss = struct.unpack_from("<3Q", b, off); off += 24
+        cmin, cmax = struct.unpack_from("<2f", b, off); off += 8
+        lists = []
+        for _k in range(4):
+            c, = struct.unpack_from("<Q", b, off); off += 8
+            lists.append(np.frombuffer(b, np.int32, c, off).copy()); off += 4 * c
+        out.append(dict(name=name, op=op, ns=ns, ss=ss, cmin=cmin, cmax=cmax, idx=lists))
+    return out
+
+
+def test_shim_lowering_matches_python_lowering(tmp_path):
+    _need()
+    import viamd_b200 as vb
+    gro = str(tmp_path / "w6.gro"); out = str(tmp_path / "low.bin")
+    subprocess.check_call([TOOL, "water-gro", "6", "77", gro])
+    subprocess.check_call([SHIM, "lower", "--sys", gro, "--script", SCRIPT, "--out", out], stdout=subprocess.DEVNULL)
+    low = _read_lowered(out)
+    props = vb.compile_script(SCRIPT, vb.water_system(6))
+    assert [p["name"] for p in low] == [p.name for p in props]
+    for a, b in zip(low, props):
+        assert a["op"] == b.op and a["cmin"] == np.float32(b.cutoff_min) and a["cmax"] == np.float32(b.cutoff_max), a["name"]
+        if b.op == vb.OP_SDF:
+            assert a["ns"] == b.num_structures and a["ss"] == b.structure_size
+        for k, arr in enumerate(b.idx):
+            assert np.array_equal(a["idx"][k], arr), (a["name"], k)
+
+
+@pytest.mark.gpu
+def test_md_script_api_cpu_vs_gpu_through_the_shim(tmp_path):
+    _need()
+    gro = str(tmp_path / "w8.gro")
+    subprocess.check_call([TOOL, "water-gro", "8", "1008", gro])
+    script = "r = rdf(element('O'), element('O'), 10.0); v = sdf(residue(1:50), element('O'), 6.0); dz = density_z(element('O')); d = distance(1,10);"
+    p = subprocess.run([SHIM, "eval", "--sys", gro, "--traj", "synthwater:8:1008:12", "--script", script], capture_output=True, text=True)
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert line, p.stdout + p.stderr
+    res = json.loads(line[-1])
+    assert p.returncode == 0 and res["parity"] is True, res
+    assert all(q["out_of_tol"] == 0 and q["frame_mask_equal"] for q in res["properties"])
