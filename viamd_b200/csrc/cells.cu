@@ -98,6 +98,8 @@ MDG_HD void compute_frame_geom(FrameGeom& g, const mdgpu_unitcell_t& uc, double 
         g.hdim[k] = (int)cd[k] + 2 * extra + 2 * reach + 2;
     }
     g.num_home = (uint32_t)((uint64_t)g.hdim[0] * g.hdim[1] * g.hdim[2]);
+    g.sym_ok = 1;
+    for (int k = 0; k < 3; ++k) if ((flags & (MDGPU_CELL_PBC_X << k)) && (int)cd[k] < 2 * g.ncell[k] + 1) g.sym_ok = 0;
     {   // calc_r2: (float)(cutoff^2) rounded up by one ulp
         const float r2 = (float)(cutoff * cutoff);
         g.r2 = nextafterf(r2, r2 + 1.0f);
@@ -204,6 +206,7 @@ __global__ void k_bin_points(BatchFrames fr, const int32_t* __restrict__ idx, co
             const float cl_ = fminf(fmaxf(cf, lo), hi);
             hc[k] = (int)cl_ - g.hlo[k];
             if (!(cf == cf)) hc[k] = 0;   // NaN coordinate: park on the sentinel plane
+            if (!(cf >= 0.0f && cf < (float)g.cdim[k])) cl.oob[f] = 1u;   // e.g. fract() rounded up to 1.0: home cell != target cell of the same atom
         }
         cell = ((uint32_t)hc[2] * (uint32_t)g.hdim[1] + (uint32_t)hc[1]) * (uint32_t)g.hdim[0] + (uint32_t)hc[0];
     }
@@ -278,6 +281,7 @@ void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float*
 void launch_cell_list(int mode, const BatchFrames& fr, const int32_t* d_idx, const float* d_aos, uint32_t n, const FrameGeom* d_geom,
                       const CellList& cl, int store_linear_idx, cudaStream_t s) {
     cudaMemsetAsync(cl.cell_cnt, 0, sizeof(uint32_t) * (size_t)fr.count * (cl.cap + 1), s);
+    cudaMemsetAsync(cl.oob, 0, sizeof(uint32_t) * fr.count, s);
     if (n) {
         dim3 grid((n + 255u) / 256u, fr.count);
         if (mode == 0) k_bin_points<0><<<grid, 256, 0, s>>>(fr, d_idx, d_aos, n, d_geom, cl, store_linear_idx);

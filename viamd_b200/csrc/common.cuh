@@ -35,6 +35,7 @@ struct FrameGeom {
     uint32_t num_cells;
     uint32_t num_home;
     int   valid;        // 0: the reference yields no pairs (degenerate cell / "cutoff too large for cell size")
+    int   sym_ok;       // every periodic axis has cdim >= 2*ncell+1: each target cell is reached by exactly one neighbour offset
 };
 
 // One cell list (sorted fractional points + offsets) for a batch of frames.
@@ -43,7 +44,8 @@ struct CellList {
     float4*   scratch;    // [B][max_points] unsorted
     uint32_t* cell_of;    // [B][max_points]
     uint32_t* rank;       // [B][max_points]
-    uint32_t* cell_cnt;   // [B][cap+1]  counts, then exclusive offsets
+    uint32_t* cell_cnt;   // [B][cap+1]  counts, then exclusive offsets; followed by [B] out-of-grid flags (oob)
+    uint32_t* oob;        // [B] set when a reference point's unclamped cell coordinate lies outside [0,cdim) (home-grid lists only)
     uint32_t  max_points;
     uint32_t  cap;        // cell capacity per frame
 };

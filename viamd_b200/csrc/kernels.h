@@ -21,6 +21,7 @@ struct RdfArgs {
     const uint32_t* excl_off;    // structure -> atoms CSR (rdf_cb_excl_mask), or null
     const int32_t* excl_idx;
     uint32_t frame0;             // global index of the batch's first frame
+    int symmetric;               // reference selection == target selection
     // finalize
     unsigned long long* acc;     // [1024] accumulated bins
     unsigned long long* frame_total;  // [num_frames]
@@ -71,6 +72,7 @@ struct TemporalArgs {
     BatchFrames frames; const mdgpu_unitcell_t* cells; int op; int atom[4]; float* out; uint32_t frame0;
 };
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s);
+void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned long long n, cudaStream_t s);
 
 // synth.cu
 void launch_synth_water(uint32_t seed, float L, uint32_t num_atoms, const float* d_base, size_t base_axis_stride, uint32_t frame_beg, uint32_t count,

@@ -48,6 +48,7 @@ struct Prop {
     // device accumulators
     unsigned long long* d_acc = nullptr;          // rdf: 1024 bins; density: 1024 fixed-point sums
     uint32_t* d_vol = nullptr;                    // sdf: 128^3
+    float* d_vol_mean = nullptr; bool values_registered = false;   // sdf: device-side fold target; host values pinned for the D2H
     unsigned long long* d_frame_total = nullptr;  // rdf / sdf: [num_frames]
     uint32_t* d_frame_min = nullptr; uint32_t* d_frame_max = nullptr;             // rdf
     unsigned long long* d_frame_min64 = nullptr; unsigned long long* d_frame_max64 = nullptr;   // density
@@ -112,7 +113,8 @@ static int alloc_cell_list(CellList& cl, uint32_t B, uint32_t max_points, uint32
     CUDA_TRY(dalloc(&cl.scratch, (size_t)B * max_points));
     CUDA_TRY(dalloc(&cl.cell_of, (size_t)B * max_points));
     CUDA_TRY(dalloc(&cl.rank, (size_t)B * max_points));
-    CUDA_TRY(dalloc(&cl.cell_cnt, (size_t)B * (cap + 1)));
+    CUDA_TRY(dalloc(&cl.cell_cnt, (size_t)B * (cap + 1) + B));
+    cl.oob = cl.cell_cnt + (size_t)B * (cap + 1);
     return 0;
 }
 static void free_cell_list(CellList& cl) { cudaFree(cl.sorted); cudaFree(cl.scratch); cudaFree(cl.cell_of); cudaFree(cl.rank); cudaFree(cl.cell_cnt); cl = CellList{}; }
@@ -157,6 +159,8 @@ static void destroy_plan(mdgpu_plan* p) {
     }
     for (auto& pr : p->props) {
         for (int k = 0; k < 4; ++k) cudaFree(pr.d_idx[k]);
+        if (pr.values_registered) cudaHostUnregister(pr.values.data());
+        cudaFree(pr.d_vol_mean);
         cudaFree(pr.d_acc); cudaFree(pr.d_vol); cudaFree(pr.d_frame_total); cudaFree(pr.d_frame_min); cudaFree(pr.d_frame_max);
         cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap);
     }
@@ -238,8 +242,10 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.n_unwrap = (uint32_t)pairs.size();
             e = upload(&pr.d_unwrap, pairs.data(), pairs.size());
             if (e == cudaSuccess) e = dalloc(&pr.d_vol, (size_t)MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM);
+            if (e == cudaSuccess) e = dalloc(&pr.d_vol_mean, (size_t)MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM);
             if (e == cudaSuccess) e = dalloc(&pr.d_frame_total, num_frames);
             pr.values.assign((size_t)MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM, 0.0f);
+            if (cudaHostRegister(pr.values.data(), pr.values.size() * sizeof(float), cudaHostRegisterDefault) == cudaSuccess) pr.values_registered = true; else cudaGetLastError();
             pr.data.dim[0] = 1; pr.data.dim[1] = MDGPU_VOL_DIM; pr.data.dim[2] = MDGPU_VOL_DIM; pr.data.dim[3] = MDGPU_VOL_DIM;
             break; }
         case MDGPU_OP_DENSITY_X: case MDGPU_OP_DENSITY_Y: case MDGPU_OP_DENSITY_Z:
@@ -411,6 +417,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.min_cutoff = pr.cutoff_min > 1e-3f ? pr.cutoff_min : 1e-3f;                 // :5269
             a.min_r2 = a.min_cutoff * a.min_cutoff;                                       // rdf_cb :5233
             a.frame_bins = ps.d_frame_bins; a.excl_off = nullptr; a.excl_idx = nullptr; a.frame0 = frame0;
+            a.symmetric = (pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
             a.acc = pr.d_acc; a.frame_total = pr.d_frame_total; a.frame_min = pr.d_frame_min; a.frame_max = pr.d_frame_max; a.keep = pr.d_keep;
             TimedLaunch tl{};
             if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); }
@@ -627,9 +634,8 @@ int mdgpu_plan_sync(mdgpu_plan* p) {
             }
             pr.data.min_range[0] = pr.cutoff_min; pr.data.max_range[0] = pr.cutoff_max;   // value_range set by internal_rdf :5415
         } else if (pr.op == MDGPU_OP_SDF) {
-            std::vector<uint32_t> vol(pr.values.size());
-            CUDA_TRY(cudaMemcpy(vol.data(), pr.d_vol, sizeof(uint32_t) * vol.size(), cudaMemcpyDeviceToHost));
-            for (size_t v = 0; v < vol.size(); ++v) pr.values[v] = n ? (float)((double)vol[v] / (double)n) : 0.0f;
+            launch_mean_u32(pr.d_vol, pr.d_vol_mean, pr.values.size(), n, 0);   // exact mean, one division per voxel, on the device
+            CUDA_TRY(cudaMemcpy(pr.values.data(), pr.d_vol_mean, sizeof(float) * pr.values.size(), cudaMemcpyDeviceToHost));
             // min_value / max_value are never updated for volumes in the reference (md_script.c:5936-5956)
         } else if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
             std::vector<unsigned long long> acc(MDGPU_DIST_BINS), mn(F), mx(F);

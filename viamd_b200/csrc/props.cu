@@ -126,6 +126,17 @@ __global__ void k_temporal(TemporalArgs a, int B) {
     a.out[a.frame0 + f] = out;
 }
 
+// fold of an integer accumulator into the float mean the property data exposes: (float)((double)count / (double)n), IEEE on the device
+__global__ void k_mean_u32(const uint32_t* __restrict__ in, float* __restrict__ out, size_t count, unsigned long long n) {
+    const double dn = (double)n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = n ? (float)((double)in[i] / dn) : 0.0f;
+}
+void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned long long n, cudaStream_t s) {
+    k_mean_u32<<<148 * 4, 256, 0, s>>>(d_in, d_out, count, n);
+    note_launch("k_mean_u32", s);
+}
+
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s) {
     k_temporal<<<(B + 63) / 64, 64, 0, s>>>(a, B);
     note_launch("k_temporal", s);
