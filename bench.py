@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=1184)   # 8 x 148 frames
+    ap.add_argument("--frames-per-step", type=int, default=2368)   # 16 x 148 frames
     ap.add_argument("--batch-frames", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--rdf-variant", type=int, default=0)
