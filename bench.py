@@ -88,6 +88,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(frames_per_launch: float):
+    """dram__bytes_read+write of the dominant kernel per launch, from the committed ncu --set full capture (scaled to this run's
+    frames per launch); None when no capture is recorded."""
+    p = os.path.join(ROOT, "profiles", "rdf_traffic.json")
+    try:
+        t = json.load(open(p))
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (frames_per_launch / t["frames_per_launch"])
+    except Exception:
+        return None
+
+
 def harness_path(kind="fast"):
     return os.path.join(ROOT, "oracle", "_ref", f"ref_harness_{kind}")
 
@@ -309,7 +320,8 @@ def main():
             "wall_s": t_wall,
             "checks": checks,
             "roofline": {"bound": "hbm", "kernel": "k_rdf_pairs", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic(frames_per_launch), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes_per_frame * frames_per_launch,
                          "note": "k_rdf_pairs is FP32-ALU/shared-atomic bound, not DRAM bound (SURVEY.md §7): see alu",
                          "kernel_share_of_step": (k_ms / max(ms_dev, 1e-9)),
                          "alu": {"pair_tests_per_s": pair_tests_per_frame * frames_per_launch / max(avg_launch_s, 1e-12),
