@@ -217,6 +217,14 @@ int mdgpu_synth_water_frames_host(uint32_t n, uint32_t seed, const float* base_x
 int mdgpu_synth_water_frames_device(int device, uint32_t n, uint32_t seed, const float* d_base_xyz, uint32_t frame_beg, uint32_t count,
                                     float* d_out_xyz, size_t frame_stride, size_t axis_stride);
 
+/* membrane workload of BASELINE config 4 (coarse-grained bilayer + solvent beads, viamd_b200/csrc/synth.h) */
+int mdgpu_synth_membrane_desc(uint32_t nl, uint32_t nw_xy, uint32_t nwz, uint32_t seed, uint32_t* num_atoms, uint32_t* num_lipids, float* L3);
+int mdgpu_synth_membrane_base(uint32_t nl, uint32_t nw_xy, uint32_t nwz, uint32_t seed, float* base_xyz, float* whole_xyz, uint32_t* mol_id);
+int mdgpu_synth_membrane_frames_host(uint32_t nl, uint32_t nw_xy, uint32_t nwz, uint32_t seed, const float* base_xyz, const uint32_t* mol_id,
+                                     uint32_t frame_beg, uint32_t count, float* out_xyz, size_t frame_stride, size_t axis_stride);
+int mdgpu_synth_membrane_frames_device(int device, uint32_t nl, uint32_t nw_xy, uint32_t nwz, uint32_t seed, const float* d_base_xyz, const uint32_t* d_mol_id,
+                                       uint32_t frame_beg, uint32_t count, float* d_out_xyz, size_t frame_stride, size_t axis_stride);
+
 /* Thin device-memory helpers so C hosts need no CUDA headers. */
 int mdgpu_device_alloc(int device, size_t bytes, void** out);
 int mdgpu_device_free(int device, void* p);

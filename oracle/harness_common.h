@@ -10,7 +10,7 @@
 
 /* ---------------------------------------------------------------- in-memory trajectories */
 
-typedef enum { TRAJ_RAW, TRAJ_SYNTHWATER } traj_kind_t;
+typedef enum { TRAJ_RAW, TRAJ_SYNTHWATER, TRAJ_SYNTHMEMBRANE } traj_kind_t;
 
 typedef struct mem_traj_t {
     traj_kind_t kind;
@@ -20,6 +20,8 @@ typedef struct mem_traj_t {
     const unsigned char* raw; size_t raw_frame_bytes;
     /* synthwater */
     mdsynth_water_t water; float *bx, *by, *bz;
+    /* synthmembrane */
+    mdsynth_membrane_t memb; float* mbase; uint32_t* mmol;
 } mem_traj_t;
 
 typedef struct raw_frame_hdr_t { double cell[6]; uint32_t flags; uint32_t pad; } raw_frame_hdr_t;
@@ -42,6 +44,9 @@ static bool mt_load_frame(struct md_trajectory_reader_o* inst, int64_t idx, md_t
         cell.y = fh.cell[3]; cell.yz = fh.cell[4]; cell.z = fh.cell[5];
         cell.flags = (md_unitcell_flags_t)fh.flags;
         if (x) { memcpy(x, p, t->num_atoms * 4); memcpy(y, p + t->num_atoms * 4, t->num_atoms * 4); memcpy(z, p + t->num_atoms * 8, t->num_atoms * 4); }
+    } else if (t->kind == TRAJ_SYNTHMEMBRANE) {
+        cell = md_unitcell_from_extent((double)t->memb.Lx, (double)t->memb.Ly, (double)t->memb.Lz);
+        if (x) mdsynth_membrane_frame(&t->memb, (uint32_t)idx, t->mbase, t->mmol, x, y, z);
     } else {
         cell = md_unitcell_from_extent((double)t->water.L, (double)t->water.L, (double)t->water.L);
         if (x) mdsynth_water_frame(&t->water, (uint32_t)idx, t->bx, t->by, t->bz, x, y, z);
@@ -82,6 +87,13 @@ static bool make_traj(md_trajectory_i* out, mem_traj_t* mt, const char* spec, md
         mt->num_frames = nf; mt->num_atoms = mt->water.num_atoms;
         mt->bx = malloc(mt->num_atoms * 4); mt->by = malloc(mt->num_atoms * 4); mt->bz = malloc(mt->num_atoms * 4);
         mdsynth_water_base(&mt->water, mt->bx, mt->by, mt->bz, NULL, NULL, NULL);
+    } else if (strncmp(spec, "synthmembrane:", 14) == 0) {
+        unsigned nl, nwxy, nwz, seed, nf;
+        if (sscanf(spec + 14, "%u:%u:%u:%u:%u", &nl, &nwxy, &nwz, &seed, &nf) != 5) return false;
+        mt->kind = TRAJ_SYNTHMEMBRANE; mt->memb = mdsynth_membrane_desc(nl, nwxy, nwz, seed);
+        mt->num_frames = nf; mt->num_atoms = mt->memb.num_atoms;
+        mt->mbase = malloc(mt->num_atoms * 12); mt->mmol = malloc(mt->num_atoms * 4);
+        mdsynth_membrane_base(&mt->memb, mt->mbase, NULL, mt->mmol);
     } else if (strcmp(spec, "sys") == 0) {
         if (!sys->trajectory) { fprintf(stderr, "system has no attached trajectory\n"); return false; }
         *out = *sys->trajectory; return true;

@@ -28,6 +28,26 @@ int main(int argc, char** argv) {
         }
         fclose(f); return 0;
     }
-    fprintf(stderr, "usage: synth_tool water-gro n seed out.gro | water-raw n seed nframes out.raw\n");
+    if (argc >= 7 && strcmp(argv[1], "membrane-gro") == 0) {
+        mdsynth_membrane_t m = mdsynth_membrane_desc((uint32_t)atoi(argv[2]), (uint32_t)atoi(argv[3]), (uint32_t)atoi(argv[4]), (uint32_t)atoi(argv[5]));
+        float* p = malloc((size_t)m.num_atoms * 12);
+        mdsynth_membrane_base(&m, NULL, p, NULL);
+        return mdsynth_membrane_write_gro(&m, argv[6], p) ? 2 : 0;
+    }
+    if (argc >= 8 && strcmp(argv[1], "membrane-raw") == 0) {
+        mdsynth_membrane_t m = mdsynth_membrane_desc((uint32_t)atoi(argv[2]), (uint32_t)atoi(argv[3]), (uint32_t)atoi(argv[4]), (uint32_t)atoi(argv[5]));
+        const uint64_t nf = (uint64_t)atoll(argv[6]), na = m.num_atoms;
+        float* b = malloc(na * 12), *x = malloc(na * 12); uint32_t* mol = malloc(na * 4);
+        mdsynth_membrane_base(&m, b, NULL, mol);
+        FILE* f = fopen(argv[7], "wb"); if (!f) return 2;
+        fwrite("MDRAWTRJ", 1, 8, f); fwrite(&nf, 8, 1, f); fwrite(&na, 8, 1, f);
+        for (uint64_t fr = 0; fr < nf; ++fr) {
+            double cell[6] = { m.Lx, 0, 0, m.Ly, 0, m.Lz }; uint32_t fl[2] = { 1 | 4 | 8 | 16, 0 };
+            mdsynth_membrane_frame(&m, (uint32_t)fr, b, mol, x, x + na, x + 2 * na);
+            fwrite(cell, 8, 6, f); fwrite(fl, 4, 2, f); fwrite(x, 4, na * 3, f);
+        }
+        fclose(f); return 0;
+    }
+    fprintf(stderr, "usage: synth_tool water-gro n seed out.gro | water-raw n seed nframes out.raw | membrane-gro nl nwxy nwz seed out.gro | membrane-raw nl nwxy nwz seed nframes out.raw\n");
     return 1;
 }

@@ -10,6 +10,8 @@ reference's outputs, so the tests need neither the reference nor the harness on 
                v  = sdf(residue(1:20), element('O'), 5.0)            per-frame raw voxels (sparse)
                dz/dx = density_z / density_x (element('O'))          per-frame bins
                d, a, t = distance(1,10), angle(1,2,3), dihedral(1,4,7,10)
+  membrane6.npz : synthetic coarse-grained membrane (BASELINE config 4 shape at 1728 atoms: 72 lipids x 12 beads + 864 solvent beads,
+               cell 48 x 48 x 75), 4 frames: rt = rdf(name('C2*'), name('C2*'), 12.0), dz = density_z(name('C2*')), dall/dxall = density over all atoms
   ala50.npz  : first 50 frames of datasets/1ALA-500.pdb (153 atoms, ortho cell 46.645 x 96.666 x 48.362), config 1:
                d = distance(1,10) (BASELINE config 1), rc = rdf(element('C'), element('O'), 10.0), dz = density_z(element('C')),
                a = angle(1,5,9), t = dihedral(5,7,9,15)
@@ -94,9 +96,25 @@ def ala50(tmp):
     np.savez_compressed(os.path.join(HERE, "ala50.npz"), **out)
 
 
+def membrane6(tmp):
+    nl, nwxy, nwz, seed, F = 6, 12, 3, 4321, 4
+    gro, raw = os.path.join(tmp, "m.gro"), os.path.join(tmp, "m.raw")
+    run(SYNTH, "membrane-gro", str(nl), str(nwxy), str(nwz), str(seed), gro)
+    run(SYNTH, "membrane-raw", str(nl), str(nwxy), str(nwz), str(seed), str(F), raw)
+    script = "rt = rdf(name('C2*'), name('C2*'), 12.0); dz = density_z(name('C2*')); dall = density_z(all); dxall = density_x(all);"
+    o = os.path.join(tmp, "m.out"); si = os.path.join(tmp, "m.sys")
+    run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
+    run(HARNESS, "sysinfo", "--sys", gro, "--out", si)
+    frames, cells, flags = refio.read_raw_traj(raw)
+    out = dict(script=np.array(script), params=np.array([nl, nwxy, nwz, seed], np.int32), frames=frames, cells=cells, cell_flags=flags,
+               **sysdict(refio.read_sysinfo(si)))
+    pack(out, refio.read_refout(o), list(range(F)))
+    np.savez_compressed(os.path.join(HERE, "membrane6.npz"), **out)
+
+
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     with tempfile.TemporaryDirectory() as tmp:
-        water6(tmp); ala50(tmp)
-    for f in ("water6.npz", "ala50.npz"):
+        water6(tmp); ala50(tmp); membrane6(tmp)
+    for f in ("water6.npz", "ala50.npz", "membrane6.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -302,3 +302,66 @@ def test_fast_sqrt_matches_ieee():
     import struct
     bits = lambda x: struct.unpack("<I", struct.pack("<f", x))[0]
     assert debug_sqrt_sweep(bits(2.0 ** -100), bits(2.0 ** 100)) == 0
+
+
+def test_golden_membrane_config4_shape():
+    """BASELINE config 4 at reduced size against the reference's goldens: lipid-tail rdf (symmetric same-selection path, non-cubic cell),
+    density profiles of a subset and of all atoms."""
+    g = load_golden("membrane6.npz"); s = golden_system(g); vb = _vb()
+    names = np.array(s["names"]); c2 = np.nonzero(np.char.startswith(names, "C2"))[0].astype(np.int32); allat = np.arange(len(names), dtype=np.int32)
+    sysm = vb.System(len(names), s["mass"])
+    props = [vb.rdf("rt", c2, c2, 12.0), vb.density("dz", 2, c2), vb.density("dall", 2, allat), vb.density("dxall", 0, allat)]
+    F = g["frames"].shape[0]
+    plan = vb.Plan(sysm, props, F, keep_frame_results=True)
+    cells = [vb_cell(g["cells"][f], g["cell_flags"][f]) for f in range(F)]
+    plan.set_initial_frame(*g["frames"][0], cells[0])
+    plan.eval_host_frames(g["frames"], cells, 0)
+    for f in range(F):
+        bins, tot = plan.frame_counts("rt", f)
+        assert np.array_equal(bins.astype(np.float32), g["rt__pf"][f, :1024]) and tot == int(g["rt__pf"][f, :1024].sum())
+    assert np.array_equal(plan.property_data("rt").weights, g["rt__pf"][F - 1, 1024:])
+    for key in ("dz", "dall", "dxall"):
+        d = plan.property_data(key)
+        np.testing.assert_allclose(d.values[:1024], g[f"{key}__full"][:1024], rtol=RTOL, atol=1e-3)
+    plan.close()
+
+
+def test_full_size_config4_membrane_1M_atoms():
+    """BASELINE config 4 at full size (994 656 atoms): frames generated on the device, lipid-tail rdf + density_z over all atoms.
+    Size-independent properties: bins sum to the pair total, accumulators independent of evaluation order, total mass conserved in
+    every frame's density profile, frame 0 equal to the oracle."""
+    vb = _vb()
+    nl, nwxy, nwz, seed, F = 38, 100, 48, 4321, 6
+    base, whole, mol, L3 = vb.synth_membrane_base(nl, nwxy, nwz, seed); na = base.shape[1]
+    assert na == 994656
+    sysm = vb.membrane_system(nl, nwxy, nwz)
+    props = vb.compile_script("rt = rdf(name('C2*'), name('C2*'), 12.0); dz = density_z(all);", sysm)
+    d_base = vb.device_alloc(0, base.nbytes); vb.memcpy_h2d(0, d_base, base.ctypes.data, base.nbytes)
+    d_mol = vb.device_alloc(0, mol.nbytes); vb.memcpy_h2d(0, d_mol, mol.ctypes.data, mol.nbytes)
+    d_fr = vb.device_alloc(0, F * 3 * na * 4)
+    vb.synth_membrane_frames_device(0, nl, nwxy, nwz, seed, d_base, d_mol, 0, F, d_fr, 3 * na, na)
+    f0 = vb.synth_membrane_frames_host(nl, nwxy, nwz, seed, base, mol, 0, 1)
+    back = np.empty((3, na), np.float32); vb.memcpy_d2h(0, back.ctypes.data, d_fr, back.nbytes)
+    assert np.array_equal(back, f0[0])                       # device generator == host generator
+    cell = vb.UnitCell.from_basis(*L3)
+    plan = vb.Plan(sysm, props, F, keep_frame_results=True, batch_frames=4)
+    plan.set_initial_frame(*f0[0], cell)
+    plan.eval_device_frames(d_fr, 3 * na, na, cell, 0, F)
+    acc = plan.counts("rt"); dacc = plan.counts("dz")
+    per = [plan.frame_counts("rt", f) for f in range(F)]
+    assert all(int(b.sum()) == t > 0 for b, t in per)
+    assert np.array_equal(acc, np.sum([b.astype(np.uint64) for b, _ in per], axis=0))
+    # every atom lands in exactly one bin: fixed-point mass sum is exact
+    assert int(dacc.sum()) == F * int(np.round(sysm.mass.astype(np.float64) * 2 ** 24).sum())
+    c2 = props[0].idx[0]; oc = O.UnitCell.ortho(*L3)
+    ob, ow, ot = O.rdf_frame(*f0[0], c2, c2, oc, 0.0, 12.0)
+    assert per[0][1] == ot and np.array_equal(per[0][0].astype(np.float32), ob)
+    db, _ = O.density_frame(*f0[0], sysm.mass, np.arange(na, dtype=np.int32), oc, 2)
+    plan.clear()
+    plan.eval_device_frames(d_fr + 3 * 3 * na * 4, 3 * na, na, cell, 3, 3)
+    plan.eval_device_frames(d_fr, 3 * na, na, cell, 0, 3)
+    assert np.array_equal(plan.counts("rt"), acc) and np.array_equal(plan.counts("dz"), dacc)
+    plan.clear(); plan.eval_device_frames(d_fr, 3 * na, na, cell, 0, 1)
+    np.testing.assert_allclose(plan.property_data("dz").values[:1024], db, rtol=3e-5, atol=1e-3)   # float sequential sum of ~1000 masses per bin in the reference
+    for p in (d_base, d_mol, d_fr): vb.device_free(0, p)
+    plan.close()

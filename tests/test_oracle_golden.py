@@ -81,6 +81,20 @@ def test_rdf_and_density_1ala(ala):
         assert np.array_equal(b, g["dz__pf"][f, :1024])
 
 
+def test_membrane_config4_shape():
+    """BASELINE config 4 at reduced size: lipid-tail rdf() and density_z/x profiles, bit-exact vs the reference."""
+    g = load_golden("membrane6.npz"); s = golden_system(g)
+    names = np.array(s["names"]); c2 = np.nonzero(np.char.startswith(names, "C2"))[0].astype(np.int32); allat = np.arange(len(names), dtype=np.int32)
+    c0 = cell_from_row(g["cells"][0], g["cell_flags"][0])
+    for f in range(g["frames"].shape[0]):
+        x, y, z = g["frames"][f]; cell = cell_from_row(g["cells"][f], g["cell_flags"][f])
+        bins, w, tot = O.rdf_frame(x, y, z, c2, c2, cell, 0.0, 12.0)
+        assert np.array_equal(bins, g["rt__pf"][f, :1024]) and np.array_equal(w, g["rt__pf"][f, 1024:]) and tot > 0
+        for key, sel, axis in (("dz", c2, 2), ("dall", allat, 2), ("dxall", allat, 0)):
+            b, _ = O.density_frame(x, y, z, s["mass"], sel, c0, axis)
+            assert np.array_equal(b, g[f"{key}__pf"][f, :1024]), key
+
+
 def test_svd3_reconstructs():
     rng = np.random.default_rng(3)
     import ctypes as C

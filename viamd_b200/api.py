@@ -481,6 +481,47 @@ def memcpy_d2h(device, dst, src, nbytes): _check(lib().mdgpu_memcpy_d2h(device, 
 def device_synchronize(device=0): _check(lib().mdgpu_device_synchronize(device))
 
 
+LIPID_BEADS = 12
+LIPID_NAMES = ["NC3", "PO4", "GL1", "GL2", "C1A", "C2A", "C3A", "C4A", "C1B", "C2B", "C3B", "C4B"]
+
+
+def synth_membrane_desc(nl: int, nw_xy: int, nwz: int, seed: int):
+    na = C.c_uint32(); nlip = C.c_uint32(); L3 = (C.c_float * 3)()
+    f = lib().mdgpu_synth_membrane_desc; f.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    _check(f(nl, nw_xy, nwz, seed, C.byref(na), C.byref(nlip), L3))
+    return int(na.value), int(nlip.value), tuple(float(v) for v in L3)
+
+
+def synth_membrane_base(nl: int, nw_xy: int, nwz: int, seed: int):
+    na, nlip, L3 = synth_membrane_desc(nl, nw_xy, nwz, seed)
+    base = np.zeros((3, na), np.float32); whole = np.zeros((3, na), np.float32); mol = np.zeros(na, np.uint32)
+    f = lib().mdgpu_synth_membrane_base; f.argtypes = [C.c_uint32] * 4 + [C.c_void_p] * 3
+    _check(f(nl, nw_xy, nwz, seed, base.ctypes.data, whole.ctypes.data, mol.ctypes.data))
+    return base, whole, mol, L3
+
+
+def synth_membrane_frames_host(nl, nw_xy, nwz, seed, base, mol, frame_beg, count):
+    na = base.shape[1]; out = np.empty((count, 3, na), np.float32)
+    f = lib().mdgpu_synth_membrane_frames_host; f.argtypes = [C.c_uint32] * 4 + [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_size_t]
+    _check(f(nl, nw_xy, nwz, seed, np.ascontiguousarray(base, np.float32).ctypes.data, np.ascontiguousarray(mol, np.uint32).ctypes.data, frame_beg, count, out.ctypes.data, 3 * na, na))
+    return out
+
+
+def synth_membrane_frames_device(device, nl, nw_xy, nwz, seed, d_base, d_mol, frame_beg, count, d_out, frame_stride, axis_stride):
+    f = lib().mdgpu_synth_membrane_frames_device
+    f.argtypes = [C.c_int] + [C.c_uint32] * 4 + [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_size_t]
+    _check(f(device, nl, nw_xy, nwz, seed, d_base, d_mol, frame_beg, count, d_out, frame_stride, axis_stride))
+
+
+def membrane_system(nl: int, nw_xy: int, nwz: int, mass_lipid: float = 72.0, mass_water: float = 72.0) -> System:
+    """Topology of the synthetic membrane: 12-bead lipids (residue LIP) then one-bead solvent residues (SOLW)."""
+    nlip = 2 * nl * nl; nw = 2 * nwz * nw_xy * nw_xy; na = nlip * LIPID_BEADS + nw
+    names = LIPID_NAMES * nlip + ["W"] * nw
+    res_off = np.concatenate([np.arange(nlip, dtype=np.int64) * LIPID_BEADS, nlip * LIPID_BEADS + np.arange(nw + 1, dtype=np.int64)])
+    mass = np.concatenate([np.full(nlip * LIPID_BEADS, mass_lipid, np.float32), np.full(nw, mass_water, np.float32)])
+    return System(na, mass, None, None, element=["X"] * na, name=names, resname=["LIP"] * nlip + ["SOLW"] * nw, res_atom_offset=res_off)
+
+
 def debug_sqrt_sweep(lo_bits: int, hi_bits: int, device: int = 0) -> int:
     n = C.c_uint64()
     lib().mdgpu_debug_sqrt_sweep.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]

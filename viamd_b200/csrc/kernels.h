@@ -75,7 +75,7 @@ void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned long long n, cudaStream_t s);
 
 // synth.cu
-void launch_synth_water(uint32_t seed, float L, uint32_t num_atoms, const float* d_base, size_t base_axis_stride, uint32_t frame_beg, uint32_t count,
-                        float* d_out, size_t frame_stride, size_t axis_stride, cudaStream_t s);
+void launch_synth_frames(uint32_t seed, float Lx, float Ly, float Lz, uint32_t num_atoms, const float* d_base, size_t base_axis_stride,
+                         const uint32_t* d_mol_id, uint32_t frame_beg, uint32_t count, float* d_out, size_t frame_stride, size_t axis_stride, cudaStream_t s);
 
 }  // namespace mdg

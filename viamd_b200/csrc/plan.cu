@@ -816,7 +816,45 @@ int mdgpu_synth_water_frames_device(int device, uint32_t n, uint32_t seed, const
     const mdsynth_water_t w = mdsynth_water_desc(n, seed);
     for (uint32_t c0 = 0; c0 < count; c0 += 32768) {
         const uint32_t c = std::min(32768u, count - c0);
-        launch_synth_water(seed, w.L, w.num_atoms, d_base_xyz, w.num_atoms, frame_beg + c0, c, d_out_xyz + (size_t)c0 * frame_stride, frame_stride, axis_stride, 0);
+        launch_synth_frames(seed, w.L, w.L, w.L, w.num_atoms, d_base_xyz, w.num_atoms, nullptr, frame_beg + c0, c, d_out_xyz + (size_t)c0 * frame_stride, frame_stride, axis_stride, 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+int mdgpu_synth_membrane_desc(uint32_t nl, uint32_t nw_xy, uint32_t nwz, uint32_t seed, uint32_t* num_atoms, uint32_t* num_lipids, float* L3) {
+    const mdsynth_membrane_t m = mdsynth_membrane_desc(nl, nw_xy, nwz, seed);
+    if (num_atoms) *num_atoms = m.num_atoms; if (num_lipids) *num_lipids = m.num_lipids;
+    if (L3) { L3[0] = m.Lx; L3[1] = m.Ly; L3[2] = m.Lz; }
+    return 0;
+}
+
+int mdgpu_synth_membrane_base(uint32_t nl, uint32_t nw_xy, uint32_t nwz, uint32_t seed, float* base_xyz, float* whole_xyz, uint32_t* mol_id) {
+    const mdsynth_membrane_t m = mdsynth_membrane_desc(nl, nw_xy, nwz, seed);
+    mdsynth_membrane_base(&m, base_xyz, whole_xyz, mol_id);
+    return 0;
+}
+
+int mdgpu_synth_membrane_frames_host(uint32_t nl, uint32_t nw_xy, uint32_t nwz, uint32_t seed, const float* base_xyz, const uint32_t* mol_id,
+                                     uint32_t frame_beg, uint32_t count, float* out_xyz, size_t frame_stride, size_t axis_stride) {
+    if (!base_xyz || !mol_id || !out_xyz) return fail(MDGPU_ERR_INVALID_ARG, "null argument");
+    const mdsynth_membrane_t m = mdsynth_membrane_desc(nl, nw_xy, nwz, seed);
+    for (uint32_t i = 0; i < count; ++i) {
+        float* o = out_xyz + (size_t)i * frame_stride;
+        mdsynth_membrane_frame(&m, frame_beg + i, base_xyz, mol_id, o, o + axis_stride, o + 2 * axis_stride);
+    }
+    return 0;
+}
+
+int mdgpu_synth_membrane_frames_device(int device, uint32_t nl, uint32_t nw_xy, uint32_t nwz, uint32_t seed, const float* d_base_xyz, const uint32_t* d_mol_id,
+                                       uint32_t frame_beg, uint32_t count, float* d_out_xyz, size_t frame_stride, size_t axis_stride) {
+    if (!d_base_xyz || !d_mol_id || !d_out_xyz) return fail(MDGPU_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    const mdsynth_membrane_t m = mdsynth_membrane_desc(nl, nw_xy, nwz, seed);
+    for (uint32_t c0 = 0; c0 < count; c0 += 32768) {
+        const uint32_t c = std::min(32768u, count - c0);
+        launch_synth_frames(seed, m.Lx, m.Ly, m.Lz, m.num_atoms, d_base_xyz, m.num_atoms, d_mol_id, frame_beg + c0, c, d_out_xyz + (size_t)c0 * frame_stride, frame_stride, axis_stride, 0);
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());

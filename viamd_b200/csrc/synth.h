@@ -180,4 +180,105 @@ static inline int mdsynth_water_write_gro(const mdsynth_water_t* w, const char* 
     fclose(f);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * membrane (BASELINE config 4): coarse-grained bilayer slab + solvent beads in an orthorhombic cell.
+ *   nl x nl lipids per leaflet on an 8 A grid (Lx = Ly = 8*nl), two leaflets, 12 beads per lipid
+ *   (NC3 PO4 GL1 GL2 | C1A C2A C3A C4A | C1B C2B C3B C4B; tails 4.7 A bead spacing along -/+z), one residue "LIP" per lipid;
+ *   nwz layers of nw_xy x nw_xy solvent beads "W" (one residue "SOLW" each) above and below the slab; Lz from the content.
+ *   Frame f = base + per-molecule rigid displacement (same law as the water box), each atom wrapped per axis.
+ * name('C2*') selects the two C2 tail beads of every lipid (the "lipid-tail" selection of config 4). */
+#define MDSYNTH_LIPID_BEADS 12
+typedef struct mdsynth_membrane_t {
+    uint32_t seed, nl, nw_xy, nwz;
+    uint32_t num_lipids, num_water, num_atoms, num_mol;
+    float Lx, Ly, Lz;
+} mdsynth_membrane_t;
+
+static inline mdsynth_membrane_t mdsynth_membrane_desc(uint32_t nl, uint32_t nw_xy, uint32_t nwz, uint32_t seed) {
+    mdsynth_membrane_t m;
+    m.seed = seed; m.nl = nl; m.nw_xy = nw_xy; m.nwz = nwz;
+    m.num_lipids = 2 * nl * nl; m.num_water = 2 * nwz * nw_xy * nw_xy;
+    m.num_atoms = m.num_lipids * MDSYNTH_LIPID_BEADS + m.num_water; m.num_mol = m.num_lipids + m.num_water;
+    m.Lx = m.Ly = 8.0f * (float)nl;
+    m.Lz = 48.0f + 2.0f * (float)nwz * 4.5f;   /* 2 x 24 A leaflets + solvent layers of 4.5 A */
+    return m;
+}
+
+static const char* const mdsynth_lipid_names[MDSYNTH_LIPID_BEADS] = { "NC3", "PO4", "GL1", "GL2", "C1A", "C2A", "C3A", "C4A", "C1B", "C2B", "C3B", "C4B" };
+
+/* base_xyz: [3][num_atoms] wrapped; whole_xyz: unbroken molecules (for the .gro); mol_id: [num_atoms] molecule of each atom. */
+static inline void mdsynth_membrane_base(const mdsynth_membrane_t* m, float* base_xyz, float* whole_xyz, uint32_t* mol_id) {
+    const size_t N = m->num_atoms;
+    const float L[3] = { m->Lx, m->Ly, m->Lz };
+    const double zc = 0.5 * (double)m->Lz;
+    /* bead offsets along the leaflet normal (towards the bilayer centre) and a small in-plane fan for the two tails */
+    static const double dn[MDSYNTH_LIPID_BEADS] = { 0.0, 3.5, 7.0, 7.0, 10.5, 15.2, 19.9, 24.0 - 0.4, 10.5, 15.2, 19.9, 24.0 - 0.4 };
+    static const double dxp[MDSYNTH_LIPID_BEADS] = { 0.0, 0.0, -1.8, 1.8, -2.2, -2.2, -2.2, -2.2, 2.2, 2.2, 2.2, 2.2 };
+    size_t a = 0; uint32_t mol = 0;
+    for (uint32_t leaf = 0; leaf < 2; ++leaf)
+    for (uint32_t iy = 0; iy < m->nl; ++iy)
+    for (uint32_t ix = 0; ix < m->nl; ++ix, ++mol) {
+        const double jx = mdsynth_u01(mdsynth_hash4(m->seed, 0x11D00001u, mol, 3)) * 3.0 - 1.5;
+        const double jy = mdsynth_u01(mdsynth_hash4(m->seed, 0x11D00002u, mol, 3)) * 3.0 - 1.5;
+        const double ang = mdsynth_u01(mdsynth_hash4(m->seed, 0x11D00003u, mol, 3)) * 6.283185307179586;
+        const double ca = cos(ang), sa = sin(ang);
+        const double hx = ((double)ix + 0.5) * 8.0 + jx, hy = ((double)iy + 0.5) * 8.0 + jy;
+        const double hz = leaf ? zc + 24.0 : zc - 24.0;   /* head plane; normal points to the centre */
+        const double sgn = leaf ? -1.0 : 1.0;
+        for (uint32_t b = 0; b < MDSYNTH_LIPID_BEADS; ++b, ++a) {
+            const double p[3] = { hx + ca * dxp[b], hy + sa * dxp[b], hz + sgn * dn[b] };
+            for (uint32_t k = 0; k < 3; ++k) {
+                const float v = (float)p[k];
+                if (whole_xyz) whole_xyz[k * N + a] = v;
+                if (base_xyz) base_xyz[k * N + a] = mdsynth_wrap(v, L[k]);
+            }
+            if (mol_id) mol_id[a] = mol;
+        }
+    }
+    const double wsp = (double)m->Lx / (double)m->nw_xy;
+    for (uint32_t side = 0; side < 2; ++side)
+    for (uint32_t iz = 0; iz < m->nwz; ++iz)
+    for (uint32_t iy = 0; iy < m->nw_xy; ++iy)
+    for (uint32_t ix = 0; ix < m->nw_xy; ++ix, ++mol, ++a) {
+        const double jx = mdsynth_u01(mdsynth_hash4(m->seed, 0x3A7E0001u, mol, 4)) * 1.6 - 0.8;
+        const double jy = mdsynth_u01(mdsynth_hash4(m->seed, 0x3A7E0002u, mol, 4)) * 1.6 - 0.8;
+        const double jz = mdsynth_u01(mdsynth_hash4(m->seed, 0x3A7E0003u, mol, 4)) * 1.6 - 0.8;
+        const double zoff = 26.5 + ((double)iz + 0.5) * 4.5;
+        const double p[3] = { ((double)ix + 0.5) * wsp + jx, ((double)iy + 0.5) * wsp + jy, (side ? zc + zoff : zc - zoff) + jz };
+        for (uint32_t k = 0; k < 3; ++k) {
+            const float v = mdsynth_wrap((float)p[k], L[k]);
+            if (whole_xyz) whole_xyz[k * N + a] = v;
+            if (base_xyz) base_xyz[k * N + a] = v;
+        }
+        if (mol_id) mol_id[a] = mol;
+    }
+}
+
+static inline void mdsynth_membrane_frame(const mdsynth_membrane_t* m, uint32_t frame, const float* base_xyz, const uint32_t* mol_id,
+                                          float* x, float* y, float* z) {
+    const size_t N = m->num_atoms;
+    for (size_t i = 0; i < N; ++i) {
+        x[i] = mdsynth_frame_coord(base_xyz[i], m->seed, frame, mol_id[i], 0, m->Lx);
+        y[i] = mdsynth_frame_coord(base_xyz[N + i], m->seed, frame, mol_id[i], 1, m->Ly);
+        z[i] = mdsynth_frame_coord(base_xyz[2 * N + i], m->seed, frame, mol_id[i], 2, m->Lz);
+    }
+}
+
+static inline int mdsynth_membrane_write_gro(const mdsynth_membrane_t* m, const char* path, const float* whole_xyz) {
+    FILE* f = fopen(path, "w");
+    if (!f) return -1;
+    const size_t N = m->num_atoms;
+    fprintf(f, "synthetic membrane nl=%u nw=%u x %u seed=%u\n%zu\n", m->nl, m->nw_xy, m->nwz, m->seed, N);
+    for (size_t i = 0; i < N; ++i) {
+        const size_t nlip = (size_t)m->num_lipids * MDSYNTH_LIPID_BEADS;
+        const int is_lip = i < nlip;
+        const size_t res = is_lip ? i / MDSYNTH_LIPID_BEADS : m->num_lipids + (i - nlip);
+        fprintf(f, "%5zu%-5s%5s%5zu%8.3f%8.3f%8.3f\n", (res + 1) % 100000, is_lip ? "LIP" : "SOLW", is_lip ? mdsynth_lipid_names[i % MDSYNTH_LIPID_BEADS] : "W",
+                (i + 1) % 100000, whole_xyz[i] * 0.1, whole_xyz[N + i] * 0.1, whole_xyz[2 * N + i] * 0.1);
+    }
+    fprintf(f, "%10.5f%10.5f%10.5f\n", m->Lx * 0.1, m->Ly * 0.1, m->Lz * 0.1);
+    fclose(f);
+    return 0;
+}
 #endif /* MDSYNTH_H */
