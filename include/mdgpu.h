@@ -135,7 +135,7 @@ typedef struct mdgpu_plan mdgpu_plan;
 typedef struct mdgpu_plan_options_t {
     int      device;              /* CUDA device ordinal */
     uint32_t batch_frames;        /* frames per launch batch; 0 = default (one per SM) */
-    uint32_t num_streams;         /* CUDA streams the frame loop is dispatched onto; 0 = default (2) */
+    uint32_t num_streams;         /* CUDA streams the frame loop is dispatched onto; 0 = default (3) */
     uint32_t keep_frame_results;  /* 1: retain raw per-frame integer bins of distributions (parity tests) */
     uint32_t cell_capacity;       /* cells per frame the cell lists are sized for; 0 = 2x the initial frame's grid */
     uint32_t rdf_variant;         /* kernel variant selector for experiments; 0 = default */
@@ -191,7 +191,8 @@ int mdgpu_plan_property_accum_ptr(mdgpu_plan* plan, size_t prop, void** d_ptr, s
 int mdgpu_plan_set_frames_accumulated(mdgpu_plan* plan, size_t prop, uint64_t frames);
 
 /* Kernel bookkeeping for bench.py: launches issued by this library since the counter was last reset, and
- * CUDA-event time of the dominant kernel (ms, summed) measured on the launching stream when timing is enabled. */
+ * CUDA-event time (ms, summed over launches) measured on the launching stream when timing is enabled; `kernel` selects
+ * "k_rdf_pairs" (the pair kernel alone), "k_sdf" (fit + scatter kernels of an sdf) or "k_density" (binning + finalize). */
 uint64_t mdgpu_launch_count(bool reset);
 int mdgpu_plan_enable_kernel_timing(mdgpu_plan* plan, int enable);
 /* Device-side stopwatch over everything the plan enqueues: _begin drains the device and records a CUDA event; _end records

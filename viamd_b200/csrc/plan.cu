@@ -83,7 +83,7 @@ struct Slot {
     uint32_t pending_beg = 0, pending_cnt = 0;
 };
 
-struct TimedLaunch { cudaEvent_t a, b; };
+struct TimedLaunch { cudaEvent_t a, b; int kind; };   // kind: 0 rdf pair kernel, 1 sdf (all three kernels), 2 density (+finalize)
 
 }  // namespace mdg
 
@@ -101,7 +101,7 @@ struct mdgpu_plan {
     std::vector<uint64_t> frame_mask; std::mutex mask_mutex;
     std::atomic<bool> interrupt{false};
     uint64_t next_slot = 0;
-    bool timing = false; std::vector<TimedLaunch> timed; double timed_ms = 0; uint64_t timed_n = 0;
+    bool timing = false; std::vector<TimedLaunch> timed; double timed_ms[3] = {0, 0, 0}; uint64_t timed_n[3] = {0, 0, 0};
     bool tri_seen = false, ortho_seen = false;
     cudaEvent_t t_begin = nullptr; std::vector<cudaEvent_t> t_end;
     bool dirty = true;   // device accumulators changed since the last fold into the host-visible property data
@@ -194,7 +194,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
     p->axis_stride = (sys->num_atoms + 3) & ~(size_t)3;
     p->B = o.batch_frames ? o.batch_frames : (uint32_t)p->sm_count;
     if (p->B > 4096) p->B = 4096;
-    p->S = o.num_streams ? o.num_streams : 2; if (p->S > 8) p->S = 8;
+    p->S = o.num_streams ? o.num_streams : 3; if (p->S > 8) p->S = 8;   // 3: copy of batch k+2 overlaps compute of k and k+1 (2 streams left the copy engine idle 25 % of the time)
     p->keep = o.keep_frame_results != 0; p->cell_cap = o.cell_capacity; p->rdf_variant = o.rdf_variant;
     p->h_mass.assign(sys->num_atoms, 1.0f);
     if (sys->atom_mass) memcpy(p->h_mass.data(), sys->atom_mass, sizeof(float) * sys->num_atoms);
@@ -308,7 +308,7 @@ int mdgpu_plan_clear(mdgpu_plan* p) {
     }
     { std::lock_guard<std::mutex> lk(p->mask_mutex); std::fill(p->frame_mask.begin(), p->frame_mask.end(), 0ull); }
     p->interrupt = false;
-    p->timed_ms = 0; p->timed_n = 0;
+    for (int k = 0; k < 3; ++k) { p->timed_ms[k] = 0; p->timed_n[k] = 0; }
     p->dirty = true;
     return 0;
 }
@@ -422,7 +422,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             TimedLaunch tl{};
             if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); }
             launch_rdf(a, B, tri, (int)p->rdf_variant, p->sm_count, s.stream, p->timing ? &tl.a : nullptr, p->timing ? &tl.b : nullptr);
-            if (p->timing) p->timed.push_back(tl);
+            if (p->timing) { tl.kind = 0; p->timed.push_back(tl); }
             break; }
         case MDGPU_OP_SDF: {
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "sdf '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
@@ -434,7 +434,10 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap; a.cutoff = pr.cutoff_max;
             a.scratch_xyzw = ps.d_sdf_xyzw; a.ref0 = ps.d_sdf_ref0; a.matrices = ps.d_sdf_mats;
             a.vol = pr.d_vol; a.frame_total = pr.d_frame_total; a.frame0 = frame0;
+            TimedLaunch tl{};
+            if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); cudaEventRecord(tl.a, s.stream); }
             launch_sdf(a, B, s.stream);
+            if (p->timing) { cudaEventRecord(tl.b, s.stream); tl.kind = 1; p->timed.push_back(tl); }
             break; }
         case MDGPU_OP_DENSITY_X: case MDGPU_OP_DENSITY_Y: case MDGPU_OP_DENSITY_Z: {
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "density '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
@@ -442,7 +445,10 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.frames = fr; a.idx = pr.d_idx[0]; a.n = (uint32_t)pr.h_idx[0].size(); a.mass = p->d_mass; a.axis = (int)pr.op - MDGPU_OP_DENSITY_X;
             a.rc = pr.rc; a.re = pr.re; a.inv_ext = pr.inv_ext; a.min_point = pr.min_point;
             a.acc = pr.d_acc; a.frame_bins = ps.d_frame_bins64; a.frame_min = pr.d_frame_min64; a.frame_max = pr.d_frame_max64; a.keep = pr.d_keep64; a.frame0 = frame0;
+            TimedLaunch tl{};
+            if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); cudaEventRecord(tl.a, s.stream); }
             launch_density(a, B, s.stream);
+            if (p->timing) { cudaEventRecord(tl.b, s.stream); tl.kind = 2; p->timed.push_back(tl); }
             break; }
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
             TemporalArgs a{};
@@ -519,7 +525,9 @@ int mdgpu_eval_host_frames(mdgpu_plan* p, const float* h_xyz, size_t frame_strid
         const float* src = h_xyz + (size_t)b0 * frame_stride;
         if (pinned) {
             // pinned source: DMA straight from the caller's buffer
-            if (frame_stride == 3 * axis_stride) {
+            if (frame_stride == 3 * axis_stride && axis_stride == AS && AS == N) {   // fully contiguous: one linear DMA
+                CUDA_TRY(cudaMemcpyAsync(s.d_frames, src, sizeof(float) * (size_t)nb * 3 * AS, cudaMemcpyHostToDevice, s.stream));
+            } else if (frame_stride == 3 * axis_stride) {
                 CUDA_TRY(cudaMemcpy2DAsync(s.d_frames, sizeof(float) * AS, src, sizeof(float) * axis_stride, sizeof(float) * N,
                                            (size_t)nb * 3, cudaMemcpyHostToDevice, s.stream));
             } else {
@@ -601,7 +609,7 @@ int mdgpu_plan_sync(mdgpu_plan* p) {
         int err = 0; CUDA_TRY(cudaMemcpy(&err, s.d_err, sizeof(int), cudaMemcpyDeviceToHost));
         if (err) { cudaMemset(s.d_err, 0, sizeof(int)); return fail(err, err == MDGPU_ERR_CAPACITY ? "a frame needs more cells than the plan's cell capacity (%u); raise mdgpu_plan_options_t.cell_capacity" : "device-side error %d", err == MDGPU_ERR_CAPACITY ? p->cell_cap : (uint32_t)err); }
     }
-    for (auto& t : p->timed) { float ms = 0; if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { p->timed_ms += ms; p->timed_n += 1; } cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto& t : p->timed) { float ms = 0; if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { p->timed_ms[t.kind] += ms; p->timed_n[t.kind] += 1; } cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     p->timed.clear();
 
     // evaluated frames
@@ -734,9 +742,9 @@ int mdgpu_plan_enable_kernel_timing(mdgpu_plan* p, int enable) { if (!p) return 
 
 int mdgpu_plan_kernel_time_ms(mdgpu_plan* p, const char* kernel, double* total_ms, uint64_t* launches) {
     if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
-    (void)kernel;   // only k_rdf_pairs is instrumented
+    const int kind = (kernel && strncmp(kernel, "k_sdf", 5) == 0) ? 1 : (kernel && strncmp(kernel, "k_density", 9) == 0) ? 2 : 0;
     int rc = mdgpu_plan_sync(p); if (rc) return rc;
-    if (total_ms) *total_ms = p->timed_ms; if (launches) *launches = p->timed_n;
+    if (total_ms) *total_ms = p->timed_ms[kind]; if (launches) *launches = p->timed_n[kind];
     return 0;
 }
 

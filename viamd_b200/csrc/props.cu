@@ -18,10 +18,13 @@ MDG_D float deperiodize1p(float x, float r, float ext) {   // vec4_deperiodize_o
     return __fadd_rn(r, __fmul_rn(dxp, ext));
 }
 
+// Per-CTA histogram in two 32-bit limbs: a 64-bit shared atomicAdd is a CAS loop (64 cyc/warp, more under contention), a 32-bit one is native.
+// The low limb takes the low word of the 2^-24 fixed-point mass; the carry out of each individual add (old + lo wraps) goes to the
+// high limb together with the high word, which for masses < 256 u happens for mass/256 of the atoms only.
 __global__ void __launch_bounds__(256) k_density(DensityArgs a) {
     const int f = blockIdx.y;
-    __shared__ unsigned long long hist[MDGPU_DIST_BINS];
-    for (int b = threadIdx.x; b < MDGPU_DIST_BINS; b += blockDim.x) hist[b] = 0ull;
+    __shared__ uint32_t hist_lo[MDGPU_DIST_BINS], hist_hi[MDGPU_DIST_BINS];
+    for (int b = threadIdx.x; b < MDGPU_DIST_BINS; b += blockDim.x) { hist_lo[b] = 0u; hist_hi[b] = 0u; }
     __syncthreads();
     const float* src = a.frames.xyz + (size_t)f * a.frames.frame_stride + (size_t)a.axis * a.frames.axis_stride;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
@@ -30,11 +33,17 @@ __global__ void __launch_bounds__(256) k_density(DensityArgs a) {
         const float fc = __fmul_rn(__fsub_rn(v, a.min_point), a.inv_ext);
         const int b = max(0, min(__float2int_rz(__fmul_rn(fc, (float)MDGPU_DIST_BINS)), MDGPU_DIST_BINS - 1));
         const unsigned long long m = __float2ull_rn(__fmul_rn(a.mass[at], 16777216.0f));
-        atomicAdd(&hist[b], m);
+        const uint32_t lo = (uint32_t)m;
+        const uint32_t old = atomicAdd(&hist_lo[b], lo);
+        const uint32_t hi = (uint32_t)(m >> 32) + ((old + lo) < old ? 1u : 0u);
+        if (hi) atomicAdd(&hist_hi[b], hi);
     }
     __syncthreads();
     unsigned long long* out = a.frame_bins + (size_t)f * MDGPU_DIST_BINS;
-    for (int b = threadIdx.x; b < MDGPU_DIST_BINS; b += blockDim.x) { const unsigned long long v = hist[b]; if (v) atomicAdd(&out[b], v); }
+    for (int b = threadIdx.x; b < MDGPU_DIST_BINS; b += blockDim.x) {
+        const unsigned long long v = ((unsigned long long)hist_hi[b] << 32) + hist_lo[b];
+        if (v) atomicAdd(&out[b], v);
+    }
 }
 
 __global__ void k_density_finalize(DensityArgs a) {
