@@ -103,8 +103,10 @@ typedef enum mdgpu_op {
 /* One property = one `ident = proc(args);` statement whose selections were evaluated statically at compile time
  * (md_script.c:5492-5524) into ascending atom index lists (md_bitfield_iter_extract_indices order).
  *   RDF      : idx[0] = reference atoms, idx[1] = target atoms, cutoff_min/max.
- *              If num_structures > 0 the references are the centres of mass of `num_structures` equally sized atom
- *              groups stored back to back in idx[0] and a structure's own atoms are excluded (rdf_cb_excl_mask :5243).
+ *              If num_structures > 0 the reference argument was an ARRAY of bitfields (e.g. residue(1:100)): the references are
+ *              the centres of mass of `num_structures` atom groups stored back to back in idx[0] (extract_com :857, no periodic
+ *              treatment) and a group's own atoms are excluded from its pairs (rdf_cb_excl_mask :5243). Groups are delimited
+ *              by structure_offsets[num_structures+1], or are `structure_size` atoms each when that pointer is NULL.
  *   SDF      : idx[0] = num_structures * structure_size atoms (equivalent structures), idx[1] = target atoms, cutoff_max.
  *   DENSITY_*: idx[0] = atoms.
  *   DISTANCE/ANGLE/DIHEDRAL: idx[k][0] = atom k (0-based). */
@@ -117,6 +119,7 @@ typedef struct mdgpu_property_desc_t {
     size_t structure_size;
     float cutoff_min;
     float cutoff_max;
+    const uint32_t* structure_offsets;   /* optional CSR offsets into idx[0] for groups of different sizes (rdf) */
 } mdgpu_property_desc_t;
 
 /* Result view: the fields of md_script_property_data_t (md_script.h:73-92) that the evaluation fills. */

@@ -64,7 +64,12 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
     if (str_eq(pname, STR_LIT("rdf")) && nargs == 3) {
         out->op = MDGPU_OP_RDF;
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &nsets, &set_size, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
-        if (args[0]->data.type.base_type == TYPE_BITFIELD && nsets > 1) { out->num_structures = nsets; out->structure_size = set_size; }   /* COM references + exclusion (:5275) */
+        if (args[0]->data.type.base_type == TYPE_BITFIELD && nsets > 1) {   /* array of bitfields: COM references + exclusion masks (:5275) */
+            const md_bitfield_t* bf = (const md_bitfield_t*)args[0]->data.ptr;
+            uint32_t* off = (uint32_t*)md_alloc(alloc, sizeof(uint32_t) * (nsets + 1));
+            off[0] = 0; for (size_t i = 0; i < nsets; ++i) off[i + 1] = off[i] + (uint32_t)md_bitfield_popcount(&bf[i]);
+            out->num_structures = nsets; out->structure_size = set_size; out->structure_offsets = off;
+        }
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[1], NULL, NULL, args[1], alloc)) < 0) goto dynamic; out->idx_count[1] = (size_t)n;
         if (!(args[2]->flags & FLAG_CONSTANT)) goto dynamic;
         if (args[2]->data.type.base_type == TYPE_FRANGE) { const frange_t r = *(const frange_t*)args[2]->data.ptr; out->cutoff_min = r.beg; out->cutoff_max = r.end; }

@@ -734,3 +734,18 @@ float mdo_dihedral(const float* x, const float* y, const float* z, int32_t a, in
     if (dot < 0) angle = -angle;
     return angle;
 }
+
+/* extract_com md_script_functions.inl:857-874: vec4 sum += (x,y,z,1) * w in atom order; w == 0 -> 1; xyz / w (vec3_div1 md_vec_math.h:471) */
+void mdo_group_com(const float* x, const float* y, const float* z, const float* mass,
+                   const int32_t* idx, const uint32_t* off, size_t n_groups, float* out) {
+    for (size_t g = 0; g < n_groups; ++g) {
+        volatile float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;   /* volatile: keep every intermediate rounded to float */
+        for (uint32_t k = off[g]; k < off[g + 1]; ++k) {
+            const int32_t a = idx[k]; const float w = mass ? mass[a] : 1.0f;
+            volatile float px = x[a] * w, py = y[a] * w, pz = z[a] * w, pw = 1.0f * w;
+            sx = sx + px; sy = sy + py; sz = sz + pz; sw = sw + pw;
+        }
+        if (sw == 0.0f) sw = 1.0f;
+        out[3 * g + 0] = sx / sw; out[3 * g + 1] = sy / sw; out[3 * g + 2] = sz / sw;
+    }
+}

@@ -35,6 +35,11 @@ uint64_t mdo_rdf_frame(const float* x, const float* y, const float* z,
                        const uint32_t* excl_off, const int32_t* excl_idx,
                        float* bins, float* weights);
 
+/* coordinate_extract() for an ARRAY of bitfields (md_script_functions.inl:1496-1507): one centre of mass per group through
+ * extract_com :857-874 — sequential float sums in ascending atom order, no periodic treatment. out: AoS xyz [n_groups][3]. */
+void mdo_group_com(const float* x, const float* y, const float* z, const float* mass,
+                   const int32_t* idx, const uint32_t* off, size_t n_groups, float* out_aos);
+
 /* sdf(ref_structures[], target, cutoff): _sdf md_script_functions.inl:5699-5856.
  * struct_idx: n_struct * struct_size ascending atom indices; conn_*: bond connectivity CSR (md_bond_conn_data_t);
  * init_*: frame-0 coordinates; mass: per atom. vol: 128^3 floats, incremented. Returns number of voxel increments. */

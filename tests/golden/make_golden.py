@@ -10,11 +10,13 @@ reference's outputs, so the tests need neither the reference nor the harness on 
                v  = sdf(residue(1:20), element('O'), 5.0)            per-frame raw voxels (sparse)
                dz/dx = density_z / density_x (element('O'))          per-frame bins
                d, a, t = distance(1,10), angle(1,2,3), dihedral(1,4,7,10)
+               rc = rdf(residue(1:20), element('O'), 5.0)            centre-of-mass references + exclusion masks (array-of-bitfields form)
   membrane6.npz : synthetic coarse-grained membrane (BASELINE config 4 shape at 1728 atoms: 72 lipids x 12 beads + 864 solvent beads,
                cell 48 x 48 x 75), 4 frames: rt = rdf(name('C2*'), name('C2*'), 12.0), dz = density_z(name('C2*')), dall/dxall = density over all atoms
+  tric6.npz  : water n=6 sheared into a TRICLINIC cell that changes every frame, 4 frames: rt, rth (min:max), rtc (centre-of-mass references)
   ala50.npz  : first 50 frames of datasets/1ALA-500.pdb (153 atoms, ortho cell 46.645 x 96.666 x 48.362), config 1:
                d = distance(1,10) (BASELINE config 1), rc = rdf(element('C'), element('O'), 10.0), dz = density_z(element('C')),
-               a = angle(1,5,9), t = dihedral(5,7,9,15)
+               a = angle(1,5,9), t = dihedral(5,7,9,15), rr = rdf(residue(1:3), element('H'), 8.0) (COM references, groups of different sizes)
 """
 import os
 import subprocess
@@ -67,7 +69,8 @@ def water6(tmp):
     run(SYNTH, "water-gro", str(n), str(seed), gro); run(SYNTH, "water-raw", str(n), str(seed), str(F), raw)
     script = ("r = rdf(element('O'), element('O'), 6.0); rh = rdf(element('O'), element('H'), 1.5:6.0); "
               "v = sdf(residue(1:20), element('O'), 5.0); dz = density_z(element('O')); dx = density_x(element('O')); "
-              "d = distance(1,10); a = angle(1,2,3); t = dihedral(1,4,7,10);")
+              "d = distance(1,10); a = angle(1,2,3); t = dihedral(1,4,7,10); "
+              "rc = rdf(residue(1:20), element('O'), 5.0);")
     o = os.path.join(tmp, "w.out"); si = os.path.join(tmp, "w.sys")
     run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
     run(HARNESS, "sysinfo", "--sys", gro, "--out", si)
@@ -82,7 +85,7 @@ def ala50(tmp):
     raw = os.path.join(tmp, "a.raw"); o = os.path.join(tmp, "a.out"); si = os.path.join(tmp, "a.sys")
     run(HARNESS, "dumptraj", "--sys", pdb, "--traj", "sys", "--frames", f"0:{F}", "--out", raw)
     script = ("d = distance(1,10); rc = rdf(element('C'), element('O'), 10.0); dz = density_z(element('C')); "
-              "a = angle(1,5,9); t = dihedral(5,7,9,15);")
+              "a = angle(1,5,9); t = dihedral(5,7,9,15); rr = rdf(residue(1:3), element('H'), 8.0);")
     # evaluate on the dumped frames so that frame 0 (initial configuration) is identical
     run(HARNESS, "eval", "--sys", pdb, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
     run(HARNESS, "sysinfo", "--sys", pdb, "--out", si)
@@ -112,9 +115,33 @@ def membrane6(tmp):
     np.savez_compressed(os.path.join(HERE, "membrane6.npz"), **out)
 
 
+def tric6(tmp):
+    """water n=6 sheared into a triclinic cell (a = (L,0,0), b = (xy,L,0), c = (xz,yz,L)), the cell changing from frame to frame:
+    pins the triclinic branch of the pair query (md_spatial_acc.c:1498-1647) and the triclinic cell-list build."""
+    n, seed, F = 6, 91, 4
+    gro, raw0, raw = os.path.join(tmp, "t.gro"), os.path.join(tmp, "t0.raw"), os.path.join(tmp, "t.raw")
+    run(SYNTH, "water-gro", str(n), str(seed), gro); run(SYNTH, "water-raw", str(n), str(seed), str(F), raw0)
+    fr, cells, _ = refio.read_raw_traj(raw0)
+    out_fr = np.empty_like(fr); out_cells = np.empty_like(cells); flags = np.full(F, 2 | 4 | 8 | 16, np.uint32)
+    for f in range(F):
+        L = cells[f][0]; xy, xz, yz = 3.1 + 0.2 * f, -2.2 - 0.1 * f, 4.3 - 0.15 * f
+        x, y, z = fr[f].astype(np.float64)
+        out_fr[f, 0] = (x + (xy / L) * y + (xz / L) * z).astype(np.float32)
+        out_fr[f, 1] = (y + (yz / L) * z).astype(np.float32); out_fr[f, 2] = z.astype(np.float32)
+        out_cells[f] = [L, xy, xz, L, yz, L]
+    refio.write_raw_traj(raw, out_fr, out_cells, flags)
+    script = "rt = rdf(element('O'), element('O'), 6.0); rth = rdf(element('O'), element('H'), 2.0:7.0); rtc = rdf(residue(1:30), element('H'), 5.0);"
+    o = os.path.join(tmp, "t.out"); si = os.path.join(tmp, "t.sys")
+    run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
+    run(HARNESS, "sysinfo", "--sys", gro, "--out", si)
+    out = dict(script=np.array(script), frames=out_fr, cells=out_cells, cell_flags=flags, **sysdict(refio.read_sysinfo(si)))
+    pack(out, refio.read_refout(o), list(range(F)))
+    np.savez_compressed(os.path.join(HERE, "tric6.npz"), **out)
+
+
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     with tempfile.TemporaryDirectory() as tmp:
-        water6(tmp); ala50(tmp); membrane6(tmp)
-    for f in ("water6.npz", "ala50.npz", "membrane6.npz"):
+        water6(tmp); ala50(tmp); membrane6(tmp); tric6(tmp)
+    for f in ("water6.npz", "ala50.npz", "membrane6.npz", "tric6.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

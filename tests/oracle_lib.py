@@ -80,6 +80,17 @@ def rdf_frame(x, y, z, ref_idx, trg_idx, cell: UnitCell, min_cutoff, max_cutoff,
     return bins, w, int(total)
 
 
+def group_com(x, y, z, mass, groups):
+    """groups: list of int32 index arrays -> (AoS positions [n,3], offsets, concatenated indices)"""
+    x, y, z, mass = _f32(x), _f32(y), _f32(z), _f32(mass)
+    off = np.zeros(len(groups) + 1, np.uint32); off[1:] = np.cumsum([len(g) for g in groups])
+    idx = np.ascontiguousarray(np.concatenate(groups), np.int32)
+    out = np.zeros((len(groups), 3), np.float32)
+    lib().mdo_group_com(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(mass, C.c_float), _p(idx, C.c_int32), _p(off, C.c_uint32),
+                        C.c_size_t(len(groups)), _p(out, C.c_float))
+    return out, off, idx
+
+
 def sdf_frame(x, y, z, init_xyz, mass, struct_idx, trg_idx, conn_off, conn_idx, cell: UnitCell, cutoff, vol=None, want_matrices=False):
     x, y, z = _f32(x), _f32(y), _f32(z)
     ix, iy, iz = (_f32(a) for a in init_xyz)

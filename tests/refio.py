@@ -117,3 +117,12 @@ def read_raw_traj(path: str):
         flags[i] = struct.unpack("<I", b[o + 48:o + 52].tobytes())[0]
         frames[i] = np.frombuffer(b[o + 56:o + fb].tobytes(), np.float32).reshape(3, N)
     return frames, cells, flags
+
+
+def write_raw_traj(path: str, frames, cells, flags):
+    """inverse of read_raw_traj (MDRAWTRJ container read by oracle/ref_harness.c)"""
+    frames = np.ascontiguousarray(frames, np.float32); F, _, N = frames.shape
+    with open(path, "wb") as f:
+        f.write(b"MDRAWTRJ"); f.write(struct.pack("<QQ", F, N))
+        for i in range(F):
+            f.write(np.asarray(cells[i], np.float64).tobytes()); f.write(struct.pack("<II", int(flags[i]), 0)); f.write(frames[i].tobytes())

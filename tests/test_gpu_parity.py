@@ -54,6 +54,58 @@ def test_golden_water_rdf_per_frame_bitexact():
     plan.close()
 
 
+def test_golden_water_rdf_com_references_bitexact():
+    """rdf(residue(1:20), element('O'), 5.0): array-of-selections reference -> centres of mass + exclusion masks (compute_rdf :5274)."""
+    g = load_golden("water6.npz"); s = golden_system(g)
+    plan, cells = _water_plan(g, s, "rc = rdf(residue(1:20), element('O'), 5.0);", batch_frames=3)
+    F = g["frames"].shape[0]
+    plan.eval_host_frames(g["frames"], cells, 0)
+    for f in range(F):
+        bins, tot = plan.frame_counts("rc", f)
+        assert np.array_equal(bins.astype(np.float32), g["rc__pf"][f, :1024]) and tot == int(g["rc__pf"][f, :1024].sum()) > 0
+    d = plan.property_data("rc")
+    assert np.array_equal(d.weights, g["rc__pf"][F - 1, 1024:])
+    np.testing.assert_allclose(d.values[:1024], g["rc__full"][:1024], rtol=RTOL, atol=1e-6)
+    plan.close()
+
+
+def test_oracle_rdf_com_references_larger():
+    """400 water molecules as centre-of-mass references against all oxygens of a 1536-atom box, device-resident frames, vs the oracle."""
+    vb = _vb()
+    n, seed, F = 8, 4242, 5
+    base, L = vb.synth_water_base(n, seed)
+    frames = vb.synth_water_frames_host(n, seed, base, 0, F)
+    sysm = vb.water_system(n)
+    groups = [np.arange(3 * r, 3 * r + 3, dtype=np.int32) for r in range(50, 450)]
+    trg = np.arange(0, 3 * n ** 3, 3, dtype=np.int32)
+    plan = vb.Plan(sysm, [vb.rdf_com("rc", groups, trg, 9.0, 0.5)], F, keep_frame_results=True, batch_frames=2)
+    cell = vb.UnitCell.from_basis(L, L, L); oc = O.UnitCell.ortho(L, L, L)
+    plan.eval_host_frames(frames, cell, 0)
+    for f in range(F):
+        pos, off, idx = O.group_com(*frames[f], sysm.mass, groups)
+        ob, ow, ot = O.rdf_frame(*frames[f], None, trg, oc, 0.5, 9.0, ref_pos=pos, excl_off=off, excl_idx=idx)
+        bins, tot = plan.frame_counts("rc", f)
+        assert tot == ot > 0 and np.array_equal(bins.astype(np.float32), ob), f"frame {f}"
+    assert np.array_equal(plan.property_data("rc").weights, ow)
+    plan.close()
+
+
+def test_golden_triclinic_rdf_bitexact():
+    """Reference-generated golden in a triclinic cell that changes every frame: plain, min:max and centre-of-mass reference rdf()."""
+    g = load_golden("tric6.npz"); s = golden_system(g)
+    plan, cells = _water_plan(g, s, str(g["script"]), batch_frames=3)
+    F = g["frames"].shape[0]
+    plan.eval_host_frames(g["frames"], cells, 0)
+    for key in ("rt", "rth", "rtc"):
+        for f in range(F):
+            bins, tot = plan.frame_counts(key, f)
+            assert np.array_equal(bins.astype(np.float32), g[f"{key}__pf"][f, :1024]) and tot == int(g[f"{key}__pf"][f, :1024].sum()) > 0, (key, f)
+        d = plan.property_data(key)
+        assert np.array_equal(d.weights, g[f"{key}__pf"][F - 1, 1024:])
+        np.testing.assert_allclose(d.values[:1024], g[f"{key}__full"][:1024], rtol=RTOL, atol=1e-6)
+    plan.close()
+
+
 def test_golden_water_sdf_per_frame_bitexact():
     g = load_golden("water6.npz"); s = golden_system(g)
     plan, cells = _water_plan(g, s, "v = sdf(residue(1:20), element('O'), 5.0);")
@@ -114,8 +166,10 @@ def test_golden_config1_1ala_distance_and_friends():
     np.testing.assert_allclose(plan.property_data("a").values, g["a__full"], rtol=RTOL)
     np.testing.assert_allclose(plan.property_data("t").values, g["t__full"], rtol=RTOL, atol=1e-6)
     for f in range(F):
-        bins, tot = plan.frame_counts("rc", f)
-        assert np.array_equal(bins.astype(np.float32), g["rc__pf"][f, :1024]), f"frame {f}"
+        for key in ("rc", "rr"):   # rr: centre-of-mass references of three residues of different sizes, own atoms excluded
+            bins, tot = plan.frame_counts(key, f)
+            assert np.array_equal(bins.astype(np.float32), g[f"{key}__pf"][f, :1024]) and tot == int(g[f"{key}__pf"][f, :1024].sum()), f"{key} frame {f}"
+    assert np.array_equal(plan.property_data("rr").weights, g["rr__pf"][F - 1, 1024:])
     np.testing.assert_allclose(plan.property_data("dz").values[:1024], g["dz__full"][:1024], rtol=RTOL, atol=1e-3)
     assert plan.frame_mask().all()
     plan.close()

@@ -15,7 +15,8 @@ SHIM = os.path.join(ROOT, "oracle", "_ref", "shim_harness")
 TOOL = os.path.join(ROOT, "oracle", "build", "synth_tool")
 
 SCRIPT = ("r = rdf(element('O'), element('O'), 6.0); v = sdf(residue(1:20), element('O'), 5.0); dz = density_z(element('O')); "
-          "d = distance(1,10); rr = rdf(element('O'), element('H'), 1.5:6.0); a = angle(1,2,3); t = dihedral(1,4,7,10);")
+          "d = distance(1,10); rr = rdf(element('O'), element('H'), 1.5:6.0); a = angle(1,2,3); t = dihedral(1,4,7,10); "
+          "rc = rdf(residue(1:20), element('O'), 5.0);")
 
 
 def _need():
@@ -52,6 +53,8 @@ def test_shim_lowering_matches_python_lowering(tmp_path):
         assert a["op"] == b.op and a["cmin"] == np.float32(b.cutoff_min) and a["cmax"] == np.float32(b.cutoff_max), a["name"]
         if b.op == vb.OP_SDF:
             assert a["ns"] == b.num_structures and a["ss"] == b.structure_size
+        if b.op == vb.OP_RDF:   # array-of-selections reference -> centre-of-mass groups
+            assert a["ns"] == b.num_structures
         for k, arr in enumerate(b.idx):
             assert np.array_equal(a["idx"][k], arr), (a["name"], k)
 
@@ -61,7 +64,7 @@ def test_md_script_api_cpu_vs_gpu_through_the_shim(tmp_path):
     _need()
     gro = str(tmp_path / "w8.gro")
     subprocess.check_call([TOOL, "water-gro", "8", "1008", gro])
-    script = "r = rdf(element('O'), element('O'), 10.0); v = sdf(residue(1:50), element('O'), 6.0); dz = density_z(element('O')); d = distance(1,10);"
+    script = "r = rdf(element('O'), element('O'), 10.0); v = sdf(residue(1:50), element('O'), 6.0); dz = density_z(element('O')); d = distance(1,10); rc = rdf(residue(1:50), element('O'), 6.0);"
     p = subprocess.run([SHIM, "eval", "--sys", gro, "--traj", "synthwater:8:1008:12", "--script", script], capture_output=True, text=True)
     line = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert line, p.stdout + p.stderr

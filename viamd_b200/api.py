@@ -68,7 +68,8 @@ class _SystemDesc(C.Structure):
 
 class _PropertyDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("op", C.c_uint32), ("idx", C.POINTER(C.c_int32) * 4), ("idx_count", C.c_size_t * 4),
-                ("num_structures", C.c_size_t), ("structure_size", C.c_size_t), ("cutoff_min", C.c_float), ("cutoff_max", C.c_float)]
+                ("num_structures", C.c_size_t), ("structure_size", C.c_size_t), ("cutoff_min", C.c_float), ("cutoff_max", C.c_float),
+                ("structure_offsets", C.POINTER(C.c_uint32))]
 
 
 class _PropertyData(C.Structure):
@@ -196,10 +197,20 @@ class Property:
     structure_size: int = 0
     cutoff_min: float = 0.0
     cutoff_max: float = 0.0
+    structure_offsets: Optional[np.ndarray] = None   # rdf_com: CSR offsets of the groups in idx[0]
 
 
 def rdf(name, ref_idx, trg_idx, cutoff, cutoff_min=0.0):
     return Property(name, OP_RDF, [np.asarray(ref_idx, np.int32), np.asarray(trg_idx, np.int32)], cutoff_min=float(cutoff_min), cutoff_max=float(cutoff))
+
+
+def rdf_com(name, groups, trg_idx, cutoff, cutoff_min=0.0):
+    """rdf() whose reference argument is an ARRAY of selections (e.g. residue(1:100)): references are the groups' centres of mass
+    and a group's own atoms are excluded from its pairs (compute_rdf md_script_functions.inl:5274-5275, rdf_cb_excl_mask :5243)."""
+    groups = [np.asarray(g, np.int32) for g in groups]
+    off = np.zeros(len(groups) + 1, np.uint32); off[1:] = np.cumsum([len(g) for g in groups])
+    return Property(name, OP_RDF, [np.concatenate(groups).astype(np.int32), np.asarray(trg_idx, np.int32)], num_structures=len(groups),
+                    cutoff_min=float(cutoff_min), cutoff_max=float(cutoff), structure_offsets=off)
 
 
 def sdf(name, structures, trg_idx, cutoff):
@@ -318,6 +329,9 @@ class Plan:
             d = descs[i]; nm = p.name.encode(); self._keep.append(nm)
             d.name = nm; d.op = p.op; d.num_structures = p.num_structures; d.structure_size = p.structure_size
             d.cutoff_min = p.cutoff_min; d.cutoff_max = p.cutoff_max
+            if p.structure_offsets is not None:
+                so = np.ascontiguousarray(p.structure_offsets, np.uint32); self._keep.append(so)
+                d.structure_offsets = so.ctypes.data_as(C.POINTER(C.c_uint32))
             for k, arr in enumerate(p.idx):
                 a = np.ascontiguousarray(arr, np.int32); self._keep.append(a)
                 d.idx[k] = a.ctypes.data_as(C.POINTER(C.c_int32)); d.idx_count[k] = a.size

@@ -17,7 +17,7 @@ struct RdfArgs {
     const FrameGeom* geom;
     CellList trg, ref;
     float min_cutoff, inv_cutoff_range, min_r2;
-    uint32_t* frame_bins;        // [B][1024], zeroed by the launcher
+    uint32_t* frame_bins;        // [B][1024] + [B] work counters, zeroed by the launcher
     const uint32_t* excl_off;    // structure -> atoms CSR (rdf_cb_excl_mask), or null
     const int32_t* excl_idx;
     uint32_t frame0;             // global index of the batch's first frame
@@ -29,6 +29,7 @@ struct RdfArgs {
     uint32_t* frame_max;
     uint32_t* keep;              // [num_frames][1024] or null
 };
+void launch_group_com(const BatchFrames& fr, const int32_t* d_idx, const uint32_t* d_off, uint32_t n_groups, const float* d_mass, float* d_out, cudaStream_t s);
 void launch_rdf(const RdfArgs& a, int B, bool tri, int variant, int sm_count, cudaStream_t s, cudaEvent_t* ev_beg, cudaEvent_t* ev_end);
 
 unsigned long long run_sqrt_sweep(uint32_t lo_bits, uint32_t hi_bits);

@@ -44,6 +44,7 @@ struct Prop {
     std::string name; uint32_t op = 0;
     std::vector<int32_t> h_idx[4]; int32_t* d_idx[4] = { nullptr, nullptr, nullptr, nullptr };
     size_t n_struct = 0, struct_size = 0;
+    std::vector<uint32_t> h_soff; uint32_t* d_soff = nullptr;   // rdf with centre-of-mass references: CSR offsets of the groups in idx[0]
     float cutoff_min = 0.f, cutoff_max = 0.f;
     // device accumulators
     unsigned long long* d_acc = nullptr;          // rdf: 1024 bins; density: 1024 fixed-point sums
@@ -72,6 +73,7 @@ struct PropScratch {   // per (stream slot, property)
     CellList trg{}, ref{};
     uint32_t* d_frame_bins = nullptr; unsigned long long* d_frame_bins64 = nullptr;
     float4* d_sdf_xyzw = nullptr; float* d_sdf_ref0 = nullptr; float* d_sdf_mats = nullptr;
+    float* d_com = nullptr;   // rdf with centre-of-mass references: [B][n_struct][3]
 };
 
 struct Slot {
@@ -150,7 +152,7 @@ static void destroy_plan(mdgpu_plan* p) {
     for (auto& s : p->slots) {
         for (auto& ps : s.ps) {
             cudaFree(ps.d_geom); cudaFree(ps.d_aabb); free_cell_list(ps.trg); free_cell_list(ps.ref);
-            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats);
+            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com);
         }
         cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
@@ -162,7 +164,7 @@ static void destroy_plan(mdgpu_plan* p) {
         if (pr.values_registered) cudaHostUnregister(pr.values.data());
         cudaFree(pr.d_vol_mean);
         cudaFree(pr.d_acc); cudaFree(pr.d_vol); cudaFree(pr.d_frame_total); cudaFree(pr.d_frame_min); cudaFree(pr.d_frame_max);
-        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap);
+        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap); cudaFree(pr.d_soff);
     }
     for (auto& t : p->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (p->t_begin) cudaEventDestroy(p->t_begin);
@@ -224,7 +226,14 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty reference positions");   // internal_rdf :5396-5403
             if (pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty target positions");
             if (pr.cutoff_min < 0.0f || pr.cutoff_max <= pr.cutoff_min) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': Invalid cutoff");
-            if (pr.n_struct) return bail(MDGPU_ERR_UNSUPPORTED, "rdf '" + pr.name + "': centre-of-mass references with exclusion masks are not implemented yet");
+            if (pr.n_struct) {   // references = centres of mass of atom groups, a group's own atoms excluded (compute_rdf :5274-5275)
+                if (d.structure_offsets) pr.h_soff.assign(d.structure_offsets, d.structure_offsets + pr.n_struct + 1);
+                else { if (!pr.struct_size) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': structure_size or structure_offsets required");
+                       pr.h_soff.resize(pr.n_struct + 1); for (size_t k = 0; k <= pr.n_struct; ++k) pr.h_soff[k] = (uint32_t)(k * pr.struct_size); }
+                if (pr.h_soff.front() != 0 || pr.h_soff.back() != pr.h_idx[0].size()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': structure offsets do not cover idx[0]");
+                for (size_t k = 0; k < pr.n_struct; ++k) if (pr.h_soff[k] > pr.h_soff[k + 1]) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': structure offsets must be non-decreasing");
+                if (upload(&pr.d_soff, pr.h_soff.data(), pr.h_soff.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (structure offsets)");
+            }
             e = dalloc(&pr.d_acc, MDGPU_DIST_BINS);
             if (e == cudaSuccess) e = dalloc(&pr.d_frame_total, num_frames);
             if (e == cudaSuccess) e = dalloc(&pr.d_frame_min, num_frames);
@@ -371,8 +380,9 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)pr.h_idx[1].size(), cap); if (rc) return rc;
                 }
                 if (pr.op == MDGPU_OP_RDF) {
-                    int rc = alloc_cell_list(ps.ref, p->B, (uint32_t)pr.h_idx[0].size(), cap); if (rc) return rc;
-                    CUDA_TRY(dalloc(&ps.d_frame_bins, (size_t)p->B * MDGPU_DIST_BINS));
+                    int rc = alloc_cell_list(ps.ref, p->B, (uint32_t)(pr.n_struct ? pr.n_struct : pr.h_idx[0].size()), cap); if (rc) return rc;
+                    if (pr.n_struct) CUDA_TRY(dalloc(&ps.d_com, (size_t)p->B * pr.n_struct * 3));
+                    CUDA_TRY(dalloc(&ps.d_frame_bins, (size_t)p->B * (MDGPU_DIST_BINS + 1)));   // + one work counter per frame (k_rdf_pairs_v2)
                 } else if (pr.op == MDGPU_OP_SDF) {
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * (pr.n_struct + 1) * pr.struct_size));
                     CUDA_TRY(dalloc(&ps.d_sdf_ref0, (size_t)p->B * 20));
@@ -410,14 +420,20 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
         }
         switch (pr.op) {
         case MDGPU_OP_RDF: {
-            launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), cs.d_geom, ps.ref, 0, s.stream);
+            if (pr.n_struct) {
+                launch_group_com(fr, pr.d_idx[0], pr.d_soff, (uint32_t)pr.n_struct, p->d_mass, ps.d_com, s.stream);
+                launch_cell_list(1, fr, nullptr, ps.d_com, (uint32_t)pr.n_struct, cs.d_geom, ps.ref, 0, s.stream);   // AoS stream: i = position index (:1721)
+            } else {
+                launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), cs.d_geom, ps.ref, 0, s.stream);
+            }
             RdfArgs a{};
             a.geom = cs.d_geom; a.trg = cs.trg; a.ref = ps.ref;
             a.inv_cutoff_range = 1.0f / (pr.cutoff_max - pr.cutoff_min);                 // before the clamp (compute_rdf :5264)
             a.min_cutoff = pr.cutoff_min > 1e-3f ? pr.cutoff_min : 1e-3f;                 // :5269
             a.min_r2 = a.min_cutoff * a.min_cutoff;                                       // rdf_cb :5233
-            a.frame_bins = ps.d_frame_bins; a.excl_off = nullptr; a.excl_idx = nullptr; a.frame0 = frame0;
-            a.symmetric = (pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
+            a.frame_bins = ps.d_frame_bins; a.frame0 = frame0;
+            a.excl_off = pr.n_struct ? pr.d_soff : nullptr; a.excl_idx = pr.n_struct ? pr.d_idx[0] : nullptr;   // md_bitfield_test_bit(&masks[i], j) :5252
+            a.symmetric = (!pr.n_struct && pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
             a.acc = pr.d_acc; a.frame_total = pr.d_frame_total; a.frame_min = pr.d_frame_min; a.frame_max = pr.d_frame_max; a.keep = pr.d_keep;
             TimedLaunch tl{};
             if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); }

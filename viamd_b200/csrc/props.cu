@@ -85,6 +85,35 @@ void launch_density(const DensityArgs& a, int B, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Centres of mass of atom groups, as coordinate_extract() produces them for an array of bitfields
+// (md_script_functions.inl:1496-1507 -> extract_com :857-874): NO periodic treatment, one sequential float pass in ascending atom
+// order, sum += (x*w, y*w, z*w, 1*w), then xyz / w (w == 0 -> 1). One thread per (group, frame): the order of the float additions
+// is the result.
+__global__ void k_group_com(BatchFrames fr, const int32_t* __restrict__ idx, const uint32_t* __restrict__ off, uint32_t n_groups,
+                            const float* __restrict__ mass, float* __restrict__ out /* [B][n_groups][3] */) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (g >= n_groups) return;
+    const float* x = fr.xyz + (size_t)f * fr.frame_stride; const float* y = x + fr.axis_stride; const float* z = y + fr.axis_stride;
+    float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
+    for (uint32_t k = off[g]; k < off[g + 1]; ++k) {
+        const int a = idx[k]; const float w = mass[a];
+        sx = __fadd_rn(sx, __fmul_rn(x[a], w)); sy = __fadd_rn(sy, __fmul_rn(y[a], w)); sz = __fadd_rn(sz, __fmul_rn(z[a], w));
+        sw = __fadd_rn(sw, __fmul_rn(1.0f, w));
+    }
+    if (sw == 0.0f) sw = 1.0f;
+    float* o = out + ((size_t)f * n_groups + g) * 3;
+    o[0] = __fdiv_rn(sx, sw); o[1] = __fdiv_rn(sy, sw); o[2] = __fdiv_rn(sz, sw);
+}
+
+void launch_group_com(const BatchFrames& fr, const int32_t* d_idx, const uint32_t* d_off, uint32_t n_groups, const float* d_mass, float* d_out, cudaStream_t s) {
+    if (!n_groups || !fr.count) return;
+    dim3 grid((n_groups + 127u) / 128u, fr.count);
+    k_group_com<<<grid, 128, 0, s>>>(fr, d_idx, d_off, n_groups, d_mass, d_out);
+    note_launch("k_group_com", s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 MDG_D void normalize3(float v[3]) {   // vec3_normalize core/md_vec_math.h:505-514 (threshold compared in double)
     const float len = __fsqrt_rn(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     if ((double)len > 1.0e-5) { v[0] = v[0] / len; v[1] = v[1] / len; v[2] = v[2] / len; } else { v[0] = v[1] = v[2] = 0.0f; }

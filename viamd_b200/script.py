@@ -135,6 +135,18 @@ class _Parser:
         s = self.selection()
         return s.reshape(1, -1)
 
+    def groups(self):
+        """first argument of rdf(): residue(a:b) covering more than one residue is an ARRAY of bitfields -> one group per residue
+        (centre-of-mass references, compute_rdf :5274); anything else is a plain selection (returns None, position unchanged)"""
+        save = self.i
+        if self.peek() == ("id", "residue"):
+            self.next(); self.expect("ch", "(")
+            off = np.asarray(self.sys.res_atom_offset); lo, hi = self._range(len(off) - 1); self.expect("ch", ")")
+            if self.peek() == ("ch", ",") and hi - lo > 1:
+                return [np.arange(off[r], off[r + 1], dtype=np.int32) for r in range(lo, hi)]
+        self.i = save
+        return None
+
     def number(self) -> float:
         return float(self.expect("num")[1])
 
@@ -145,11 +157,13 @@ class _Parser:
         ident = self.expect("id")[1]; self.expect("ch", "=")
         proc = self.expect("id")[1]; self.expect("ch", "(")
         if proc == "rdf":
-            ref = self.selection(); self.expect("ch", ","); trg = self.selection(); self.expect("ch", ",")
+            grp = self.groups()
+            ref = None if grp is not None else self.selection()
+            self.expect("ch", ","); trg = self.selection(); self.expect("ch", ",")
             a = self.number(); lo, hi = 0.0, a
             if self.peek() == ("ch", ":"):
                 self.next(); lo, hi = a, self.number()
-            p = api.rdf(ident, ref, trg, hi, lo)
+            p = api.rdf_com(ident, grp, trg, hi, lo) if grp is not None else api.rdf(ident, ref, trg, hi, lo)
         elif proc == "sdf":
             st = self.structures(); self.expect("ch", ","); trg = self.selection(); self.expect("ch", ","); c = self.number()
             p = api.sdf(ident, st, trg, c)
