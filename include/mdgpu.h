@@ -95,7 +95,7 @@ typedef enum mdgpu_op {
     MDGPU_OP_DENSITY_X = 3,  /* density_x/_y/_z(atoms)               -> distribution                      :4825-5015 */
     MDGPU_OP_DENSITY_Y = 4,
     MDGPU_OP_DENSITY_Z = 5,
-    MDGPU_OP_DISTANCE = 6,   /* distance(a, b)   single atoms        -> temporal [F,1]                    :3851-3890 */
+    MDGPU_OP_DISTANCE = 6,   /* distance(a, b)   atoms or selections -> temporal [F,1]                    :3851-3890 */
     MDGPU_OP_ANGLE = 7,      /* angle(a, b, c)                       -> temporal                          :4099-4114 */
     MDGPU_OP_DIHEDRAL = 8,   /* dihedral(a, b, c, d)                 -> temporal                          :4171-4196 */
 } mdgpu_op;
@@ -109,7 +109,10 @@ typedef enum mdgpu_op {
  *              by structure_offsets[num_structures+1], or are `structure_size` atoms each when that pointer is NULL.
  *   SDF      : idx[0] = num_structures * structure_size atoms (equivalent structures), idx[1] = target atoms, cutoff_max.
  *   DENSITY_*: idx[0] = atoms.
- *   DISTANCE/ANGLE/DIHEDRAL: idx[k][0] = atom k (0-based). */
+ *   DISTANCE/ANGLE/DIHEDRAL: idx[k] = the atoms of argument k (0-based). A single integer index is that atom's position; an
+ *              argument that was a selection (bit k of com_args set, or more than one index) is its centre of mass as
+ *              coordinate_extract_com evaluates it (:1717 -> md_util_com_compute md_util.c:8163: periodic cells use the
+ *              trigonometric centre of mass _com_pbc_iw :7850, 8-lane float accumulation as in the AVX2 build). */
 typedef struct mdgpu_property_desc_t {
     const char* name;
     uint32_t op;
@@ -120,6 +123,7 @@ typedef struct mdgpu_property_desc_t {
     float cutoff_min;
     float cutoff_max;
     const uint32_t* structure_offsets;   /* optional CSR offsets into idx[0] for groups of different sizes (rdf) */
+    uint32_t com_args;                   /* distance/angle/dihedral: bit k = argument k is a selection (centre of mass even for one atom) */
 } mdgpu_property_desc_t;
 
 /* Result view: the fields of md_script_property_data_t (md_script.h:73-92) that the evaluation fills. */

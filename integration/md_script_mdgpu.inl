@@ -100,7 +100,14 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         const size_t need = dist ? 2 : (ang ? 3 : (dih ? 4 : 0));
         if (need && nargs == need) {
             out->op = dist ? MDGPU_OP_DISTANCE : (ang ? MDGPU_OP_ANGLE : MDGPU_OP_DIHEDRAL);
-            for (size_t k = 0; k < need; ++k) { if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], NULL, NULL, args[k], alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n; }
+            for (size_t k = 0; k < need; ++k) {
+                size_t ns = 0;
+                if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], &ns, NULL, args[k], alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n;
+                if (args[k]->data.type.base_type == TYPE_BITFIELD) {
+                    if (ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections as argument (centre of sub-centres) is not lowered", STR_ARG(ident)); return false; }
+                    out->com_args |= 1u << k;   /* a selection goes through md_util_com_compute even with one atom (coordinate_extract_com :1812) */
+                }
+            }
             return true;
         }
     }

@@ -688,10 +688,129 @@ void mdo_density_frame(const float* x, const float* y, const float* z, const flo
 }
 
 /* ------------------------------------------------------------------------------------------------
- * distance / angle / dihedral for single-atom arguments
+ * Argument positions of distance / angle / dihedral: coordinate_extract_com (md_script_functions.inl:1717-1850).
+ * A single integer index is the atom's position (:1755); a selection (bitfield) or several indices go through
+ * md_util_com_compute (md_util.c:8163): no cell -> com() :7139, otherwise the trigonometric periodic centre of mass
+ * com_pbc :8019 -> _com_pbc_iw :7850. Both are restated for the AVX2 build (8 float lanes + double remainder), which is what
+ * oracle/_ref/ref_harness_strict is compiled as.
  */
-float mdo_distance(const float* x, const float* y, const float* z, int32_t a, int32_t b, const mdo_unitcell_t* cell) {
-    const float pa[3] = { x[a], y[a], z[a] }; float pb[3] = { x[b], y[b], z[b] };
+static float f_from_bits(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static uint32_t bits_from_f(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+/* one lane of md_mm256_sincos_ps (core/md_simd.h:1177-1258; the Cody-Waite variant at :1003 is compiled out by #if 0 :920) */
+static void ref_sincosf(float x, float* out_s, float* out_c) {
+    uint32_t sign_bit_sin = bits_from_f(x) & 0x80000000u;
+    x = fabsf(x);
+    float y = x * 1.27323954473516f;
+    int32_t imm2 = (int32_t)y;                       /* cvttps */
+    imm2 = (imm2 + 1) & ~1;
+    y = (float)imm2;
+    int32_t imm3 = imm2;
+    const uint32_t swap_sign_bit_sin = ((uint32_t)(imm2 & 4)) << 29;
+    const int poly_mask = ((imm2 & 2) == 0);
+    imm3 = imm3 - 2;
+    const uint32_t sign_bit_cos = ((uint32_t)(~imm3 & 4)) << 29;
+    sign_bit_sin ^= swap_sign_bit_sin;
+    x = fmaf(y, -0.78515625f, x);
+    x = fmaf(y, -2.4187564849853515625E-4f, x);
+    x = fmaf(y, -3.77489470793079817668E-8f, x);
+    const float x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
+    y = fmaf(x2, fmaf(x2, 2.443315711809948E-5f, -1.388731625493765E-3f), 4.166664568298827E-2f);
+    y = fmaf(x2, -0.5f, y * x4);
+    y = y + 1.0f;
+    float y2 = fmaf(x2, fmaf(x2, -1.9515295891E-4f, 8.3321608736E-3f), -1.6666654611E-1f);
+    y2 = fmaf(y2, x3, x);
+    const float ysin2 = poly_mask ? y2 : 0.0f, ysin1 = poly_mask ? 0.0f : y;
+    y2 = y2 - ysin2; y = y - ysin1;
+    const float xmm1 = ysin1 + ysin2, xmm2 = y + y2;
+    *out_s = f_from_bits(bits_from_f(xmm1) ^ sign_bit_sin);
+    *out_c = f_from_bits(bits_from_f(xmm2) ^ sign_bit_cos);
+}
+
+/* md_mm256_reduce_add_ps (core/md_simd.h:691) over md_mm_reduce_add_ps (:678): ((l0+l4)+(l1+l5)) + ((l2+l6)+(l3+l7)) */
+static float reduce8(const float v[8]) {
+    const float a0 = v[0] + v[4], a1 = v[1] + v[5], a2 = v[2] + v[6], a3 = v[3] + v[7];
+    return (a0 + a1) + (a2 + a3);
+}
+
+void mdo_com(const float* x, const float* y, const float* z, const float* mass, const int32_t* idx, size_t count,
+             const mdo_unitcell_t* cell, float out[3]) {
+    out[0] = out[1] = out[2] = 0.0f;
+    if (count == 0) return;
+    const size_t simd_count = count & ~(size_t)7;
+    size_t i = 0;
+    if (!cell || cell->flags == 0) {   /* com() md_util.c:7139-7380, indices + weights branch */
+        float vx[8] = {0}, vy[8] = {0}, vz[8] = {0}, vw[8] = {0};
+        for (; i < simd_count; i += 8) for (int l = 0; l < 8; ++l) {
+            const int32_t a = idx[i + l]; const float w = mass[a];
+            volatile float px = x[a] * w, py = y[a] * w, pz = z[a] * w;
+            vx[l] = vx[l] + px; vy[l] = vy[l] + py; vz[l] = vz[l] + pz; vw[l] = vw[l] + w;
+        }
+        double ax = reduce8(vx), ay = reduce8(vy), az = reduce8(vz), aw = reduce8(vw);
+        for (; i < count; ++i) {
+            const int32_t a = idx[i]; const float w = mass[a];
+            volatile float px = x[a] * w, py = y[a] * w, pz = z[a] * w;
+            ax += px; ay += py; az += pz; aw += w;
+        }
+        out[0] = (float)(ax / aw); out[1] = (float)(ay / aw); out[2] = (float)(az / aw);
+        return;
+    }
+    /* com_pbc :8019-8046: M = scale(2pi) * Ai, I = A * scale(1/2pi), float matrices (mat3_mul core/md_vec_math.h:1631) */
+    float A[3][3] = { { (float)cell->x, 0, 0 }, { (float)cell->xy, (float)cell->y, 0 }, { (float)cell->xz, (float)cell->yz, (float)cell->z } };
+    float Ai[3][3];
+    {   /* md_unitcell_I_extract_double md_unitcell.inl:158-176 */
+        const double cx = cell->x, cy = cell->y, cz = cell->z;
+        const double i11 = cx > 0.0 ? 1.0 / cx : 0.0, i22 = cy > 0.0 ? 1.0 / cy : 0.0, i33 = cz > 0.0 ? 1.0 / cz : 0.0;
+        const double i12 = (cx * cy) > 0.0 ? -cell->xy / (cx * cy) : 0.0;
+        const double i13 = (cx * cy * cz) > 0.0 ? (cell->xy * cell->yz - cell->xz * cy) / (cx * cy * cz) : 0.0;
+        const double i23 = (cy * cz) > 0.0 ? -cell->yz / (cy * cz) : 0.0;
+        const double I[3][3] = { { i11, 0, 0 }, { i12, i22, 0 }, { i13, i23, i33 } };
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Ai[r][c] = (float)I[r][c];
+    }
+    const float tp = (float)6.283185307179586, itp = (float)(1.0 / 6.283185307179586);
+    float M[3][3], I[3][3];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { M[r][c] = tp * Ai[r][c]; I[r][c] = A[r][c] * itp; }
+    float vs[3][8] = {{0}}, vc[3][8] = {{0}}, vw[8] = {0};
+    const float* src[3] = { x, y, z };
+    for (; i < simd_count; i += 8) for (int l = 0; l < 8; ++l) {
+        const int32_t a = idx[i + l]; const float w = mass[a];
+        for (int k = 0; k < 3; ++k) {
+            const float p = src[k][a];
+            const float t = fmaf(p, M[k][0], fmaf(p, M[k][1], p * M[k][2]));   /* :7917-7919 */
+            float sn, cs; ref_sincosf(t, &sn, &cs);
+            vs[k][l] = fmaf(sn, w, vs[k][l]); vc[k][l] = fmaf(cs, w, vc[k][l]);
+        }
+        vw[l] = vw[l] + w;
+    }
+    double acc_s[3], acc_c[3], acc_w = reduce8(vw);
+    for (int k = 0; k < 3; ++k) { acc_s[k] = reduce8(vs[k]); acc_c[k] = reduce8(vc[k]); }
+    for (; i < count; ++i) {   /* scalar remainder in double (:7988-8003) */
+        const int32_t a = idx[i]; const double w = mass[a];
+        for (int k = 0; k < 3; ++k) {
+            const double p = src[k][a];
+            const double t = p * M[k][0] + p * M[k][1] + p * M[k][2];
+            acc_c[k] += w * cos(t); acc_s[k] += w * sin(t);
+        }
+        acc_w += w;
+    }
+    const double inv_w = 1.0 / acc_w;
+    for (int k = 0; k < 3; ++k) {
+        double theta = 3.14159265358979323846;
+        const double px = acc_c[k] * inv_w, py = acc_s[k] * inv_w;
+        if (px * px + py * py > 1.0e-8) theta += atan2(-py, -px);   /* TRIG_ATAN2_R2_THRESHOLD :5971 */
+        out[k] = (float)(theta * I[k][0] + theta * I[k][1] + theta * I[k][2]);
+    }
+}
+
+void mdo_arg_position(const float* x, const float* y, const float* z, const float* mass, const int32_t* idx, size_t count, int direct,
+                      const mdo_unitcell_t* cell, float out[3]) {
+    if (direct && count == 1) { out[0] = x[idx[0]]; out[1] = y[idx[0]]; out[2] = z[idx[0]]; return; }
+    mdo_com(x, y, z, mass, idx, count, cell, out);
+}
+
+/* _distance md_script_functions.inl:3851-3890 on two positions */
+float mdo_distance_pos(const float pa[3], const float pb_in[3], const mdo_unitcell_t* cell) {
+    float pb[3] = { pb_in[0], pb_in[1], pb_in[2] };
     if (cell->flags & MDO_CELL_ORTHO) {   /* md_util_deperiodize_vec4 md_util.c:8971-8990 */
         const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
         for (int k = 0; k < 3; ++k) pb[k] = deperiodize1(pb[k], pa[k], ext[k]);
@@ -699,22 +818,31 @@ float mdo_distance(const float* x, const float* y, const float* z, int32_t a, in
     const float d[3] = { pa[0] - pb[0], pa[1] - pb[1], pa[2] - pb[2] };
     return sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
 }
+float mdo_distance(const float* x, const float* y, const float* z, int32_t a, int32_t b, const mdo_unitcell_t* cell) {
+    const float pa[3] = { x[a], y[a], z[a] }, pb[3] = { x[b], y[b], z[b] };
+    return mdo_distance_pos(pa, pb, cell);
+}
 
 static void normalize3(float v[3]) {
     const float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     if (len > 1.0e-5) { v[0] = v[0] / len; v[1] = v[1] / len; v[2] = v[2] / len; } else { v[0] = v[1] = v[2] = 0; }
 }
 
-float mdo_angle(const float* x, const float* y, const float* z, int32_t a, int32_t b, int32_t c) {
-    float v0[3] = { x[a] - x[b], y[a] - y[b], z[a] - z[b] }, v1[3] = { x[c] - x[b], y[c] - y[b], z[c] - z[b] };
+/* _angle :4099-4114 */
+float mdo_angle_pos(const float a[3], const float b[3], const float c[3]) {
+    float v0[3] = { a[0] - b[0], a[1] - b[1], a[2] - b[2] }, v1[3] = { c[0] - b[0], c[1] - b[1], c[2] - b[2] };
     normalize3(v0); normalize3(v1);
     return acosf(v0[0] * v1[0] + v0[1] * v1[1] + v0[2] * v1[2]);
 }
+float mdo_angle(const float* x, const float* y, const float* z, int32_t a, int32_t b, int32_t c) {
+    const float pa[3] = { x[a], y[a], z[a] }, pb[3] = { x[b], y[b], z[b] }, pc[3] = { x[c], y[c], z[c] };
+    return mdo_angle_pos(pa, pb, pc);
+}
 
-float mdo_dihedral(const float* x, const float* y, const float* z, int32_t a, int32_t b, int32_t c, int32_t d, const mdo_unitcell_t* cell) {
-    const int32_t id[4] = { a, b, c, d };
+/* _dihedral :4171-4196 */
+float mdo_dihedral_pos(const float p[4][3], const mdo_unitcell_t* cell) {
     float dx[3][3];
-    for (int k = 0; k < 3; ++k) { dx[k][0] = x[id[k + 1]] - x[id[k]]; dx[k][1] = y[id[k + 1]] - y[id[k]]; dx[k][2] = z[id[k + 1]] - z[id[k]]; }
+    for (int k = 0; k < 3; ++k) for (int i = 0; i < 3; ++i) dx[k][i] = p[k + 1][i] - p[k][i];
     if (cell->flags & MDO_CELL_ORTHO) {   /* md_util_min_image_vec3 -> min_image_ortho md_util.c:8424-8436 */
         const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
         for (int k = 0; k < 3; ++k) for (int i = 0; i < 3; ++i) {
@@ -733,6 +861,11 @@ float mdo_dihedral(const float* x, const float* y, const float* z, int32_t a, in
     const float dot = d1[0] * v2[0] + d1[1] * v2[1] + d1[2] * v2[2];
     if (dot < 0) angle = -angle;
     return angle;
+}
+float mdo_dihedral(const float* x, const float* y, const float* z, int32_t a, int32_t b, int32_t c, int32_t d, const mdo_unitcell_t* cell) {
+    const int32_t id[4] = { a, b, c, d }; float p[4][3];
+    for (int k = 0; k < 4; ++k) { p[k][0] = x[id[k]]; p[k][1] = y[id[k]]; p[k][2] = z[id[k]]; }
+    return mdo_dihedral_pos((const float (*)[3])p, cell);
 }
 
 /* extract_com md_script_functions.inl:857-874: vec4 sum += (x,y,z,1) * w in atom order; w == 0 -> 1; xyz / w (vec3_div1 md_vec_math.h:471) */

@@ -60,6 +60,16 @@ float mdo_distance(const float* x, const float* y, const float* z, int32_t a, in
 float mdo_angle(const float* x, const float* y, const float* z, int32_t a, int32_t b, int32_t c);
 float mdo_dihedral(const float* x, const float* y, const float* z, int32_t a, int32_t b, int32_t c, int32_t d, const mdo_unitcell_t* cell);
 
+/* Arguments that are selections (or several indices): coordinate_extract_com md_script_functions.inl:1717 -> md_util_com_compute
+ * md_util.c:8163 (AVX2 build: 8 float lanes + double remainder; periodic cells use the trigonometric centre of mass _com_pbc_iw :7850
+ * with md_mm256_sincos_ps core/md_simd.h:1177). direct != 0 and count == 1: the atom's own position (:1755). */
+void mdo_com(const float* x, const float* y, const float* z, const float* mass, const int32_t* idx, size_t count, const mdo_unitcell_t* cell, float out[3]);
+void mdo_arg_position(const float* x, const float* y, const float* z, const float* mass, const int32_t* idx, size_t count, int direct,
+                      const mdo_unitcell_t* cell, float out[3]);
+float mdo_distance_pos(const float a[3], const float b[3], const mdo_unitcell_t* cell);
+float mdo_angle_pos(const float a[3], const float b[3], const float c[3]);
+float mdo_dihedral_pos(const float p[4][3], const mdo_unitcell_t* cell);
+
 /* building blocks exposed for unit tests */
 void mdo_svd3(const float A[3][3], float U[3][3], float S[3][3], float V[3][3]); /* ext/svd3/svd3.c */
 uint64_t mdo_count_pairs(const float* x, const float* y, const float* z, const int32_t* ref_idx, size_t n_ref,

@@ -11,6 +11,7 @@ reference's outputs, so the tests need neither the reference nor the harness on 
                dz/dx = density_z / density_x (element('O'))          per-frame bins
                d, a, t = distance(1,10), angle(1,2,3), dihedral(1,4,7,10)
                rc = rdf(residue(1:20), element('O'), 5.0)            centre-of-mass references + exclusion masks (array-of-bitfields form)
+               dc, ac, tc, dg, dm                                     distance/angle/dihedral whose arguments are selections (periodic centre of mass)
   membrane6.npz : synthetic coarse-grained membrane (BASELINE config 4 shape at 1728 atoms: 72 lipids x 12 beads + 864 solvent beads,
                cell 48 x 48 x 75), 4 frames: rt = rdf(name('C2*'), name('C2*'), 12.0), dz = density_z(name('C2*')), dall/dxall = density over all atoms
   tric6.npz  : water n=6 sheared into a TRICLINIC cell that changes every frame, 4 frames: rt, rth (min:max), rtc (centre-of-mass references)
@@ -70,7 +71,9 @@ def water6(tmp):
     script = ("r = rdf(element('O'), element('O'), 6.0); rh = rdf(element('O'), element('H'), 1.5:6.0); "
               "v = sdf(residue(1:20), element('O'), 5.0); dz = density_z(element('O')); dx = density_x(element('O')); "
               "d = distance(1,10); a = angle(1,2,3); t = dihedral(1,4,7,10); "
-              "rc = rdf(residue(1:20), element('O'), 5.0);")
+              "rc = rdf(residue(1:20), element('O'), 5.0); "
+              "dc = distance(residue(1), residue(5)); ac = angle(residue(1), residue(2), residue(3)); "
+              "tc = dihedral(residue(1), residue(2), residue(3), residue(4)); dg = distance(atom(1:30), atom(100:151)); dm = distance(atom(1:30), 200);")
     o = os.path.join(tmp, "w.out"); si = os.path.join(tmp, "w.sys")
     run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
     run(HARNESS, "sysinfo", "--sys", gro, "--out", si)
@@ -85,7 +88,8 @@ def ala50(tmp):
     raw = os.path.join(tmp, "a.raw"); o = os.path.join(tmp, "a.out"); si = os.path.join(tmp, "a.sys")
     run(HARNESS, "dumptraj", "--sys", pdb, "--traj", "sys", "--frames", f"0:{F}", "--out", raw)
     script = ("d = distance(1,10); rc = rdf(element('C'), element('O'), 10.0); dz = density_z(element('C')); "
-              "a = angle(1,5,9); t = dihedral(5,7,9,15); rr = rdf(residue(1:3), element('H'), 8.0);")
+              "a = angle(1,5,9); t = dihedral(5,7,9,15); rr = rdf(residue(1:3), element('H'), 8.0); "
+              "dr = distance(residue(1), residue(15)); ar = angle(residue(1), residue(7), residue(15)); tr = dihedral(residue(1), residue(5), 100, residue(15));")
     # evaluate on the dumped frames so that frame 0 (initial configuration) is identical
     run(HARNESS, "eval", "--sys", pdb, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
     run(HARNESS, "sysinfo", "--sys", pdb, "--out", si)

@@ -50,6 +50,7 @@ def lib():
         _lib.mdo_distance.restype = C.c_float
         _lib.mdo_angle.restype = C.c_float
         _lib.mdo_dihedral.restype = C.c_float
+        for n in ("mdo_distance_pos", "mdo_angle_pos", "mdo_dihedral_pos"): getattr(_lib, n).restype = C.c_float
     return _lib
 
 
@@ -135,3 +136,28 @@ def count_pairs(x, y, z, ref_idx, trg_idx, cell, cell_ext, cutoff):
     x, y, z = _f32(x), _f32(y), _f32(z); ref_idx, trg_idx = _i32(ref_idx), _i32(trg_idx)
     return int(lib().mdo_count_pairs(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(ref_idx, C.c_int32), C.c_size_t(len(ref_idx)),
                                      _p(trg_idx, C.c_int32), C.c_size_t(len(trg_idx)), C.byref(cell), C.c_double(cell_ext), C.c_double(cutoff)))
+
+
+def arg_position(x, y, z, mass, arg, cell):
+    """argument of distance/angle/dihedral: int -> the atom's position, index array -> centre of mass (coordinate_extract_com)"""
+    x, y, z, mass = _f32(x), _f32(y), _f32(z), _f32(mass)
+    direct = np.ndim(arg) == 0
+    idx = np.ascontiguousarray([int(arg)] if direct else arg, np.int32); out = np.zeros(3, np.float32)
+    lib().mdo_arg_position(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(mass, C.c_float), _p(idx, C.c_int32), C.c_size_t(len(idx)),
+                           C.c_int(1 if direct else 0), C.byref(cell), _p(out, C.c_float))
+    return out
+
+
+def distance_args(x, y, z, mass, a, b, cell):
+    pa, pb = arg_position(x, y, z, mass, a, cell), arg_position(x, y, z, mass, b, cell)
+    return np.float32(lib().mdo_distance_pos(_p(pa, C.c_float), _p(pb, C.c_float), C.byref(cell)))
+
+
+def angle_args(x, y, z, mass, a, b, c, cell):
+    p = [arg_position(x, y, z, mass, k, cell) for k in (a, b, c)]
+    return np.float32(lib().mdo_angle_pos(_p(p[0], C.c_float), _p(p[1], C.c_float), _p(p[2], C.c_float)))
+
+
+def dihedral_args(x, y, z, mass, a, b, c, d, cell):
+    p = np.ascontiguousarray(np.stack([arg_position(x, y, z, mass, k, cell) for k in (a, b, c, d)]), np.float32)
+    return np.float32(lib().mdo_dihedral_pos(_p(p, C.c_float), C.byref(cell)))

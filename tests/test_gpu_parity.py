@@ -132,9 +132,16 @@ def test_golden_water_sdf_per_frame_bitexact():
 
 def test_golden_water_density_and_temporals():
     g = load_golden("water6.npz"); s = golden_system(g)
-    plan, cells = _water_plan(g, s, "dz = density_z(element('O')); dx = density_x(element('O')); d = distance(1,10); a = angle(1,2,3); t = dihedral(1,4,7,10);")
+    plan, cells = _water_plan(g, s, "dz = density_z(element('O')); dx = density_x(element('O')); d = distance(1,10); a = angle(1,2,3); t = dihedral(1,4,7,10); "
+                            "dc = distance(residue(1), residue(5)); ac = angle(residue(1), residue(2), residue(3)); "
+                            "tc = dihedral(residue(1), residue(2), residue(3), residue(4)); dg = distance(atom(1:30), atom(100:151)); dm = distance(atom(1:30), 200);")
     F = g["frames"].shape[0]
     plan.eval_host_frames(g["frames"], cells, 0)
+    # arguments that are selections: periodic centre of mass (md_util_com_compute), lane-by-lane restatement of the AVX2 reference
+    for key in ("dc", "dg", "dm"):
+        assert np.array_equal(plan.property_data(key).values, g[f"{key}__full"]), key      # distances: every operation is IEEE on both sides
+    np.testing.assert_allclose(plan.property_data("ac").values, g["ac__full"], rtol=RTOL)
+    np.testing.assert_allclose(plan.property_data("tc").values, g["tc__full"], rtol=RTOL)
     for key in ("dz", "dx"):
         d = plan.property_data(key)
         np.testing.assert_allclose(d.values[:1024], g[f"{key}__full"][:1024], rtol=RTOL, atol=1e-3)
@@ -165,6 +172,9 @@ def test_golden_config1_1ala_distance_and_friends():
     assert np.array_equal(d.values, g["d__full"]) and abs(float(d.values[0]) - 2.770258) < 1e-6
     np.testing.assert_allclose(plan.property_data("a").values, g["a__full"], rtol=RTOL)
     np.testing.assert_allclose(plan.property_data("t").values, g["t__full"], rtol=RTOL, atol=1e-6)
+    assert np.array_equal(plan.property_data("dr").values, g["dr__full"])      # distance between residue centres of mass (periodic, trigonometric)
+    np.testing.assert_allclose(plan.property_data("ar").values, g["ar__full"], rtol=RTOL)
+    np.testing.assert_allclose(plan.property_data("tr").values, g["tr__full"], rtol=RTOL, atol=1e-6)
     for f in range(F):
         for key in ("rc", "rr"):   # rr: centre-of-mass references of three residues of different sizes, own atoms excluded
             bins, tot = plan.frame_counts(key, f)

@@ -69,7 +69,7 @@ class _SystemDesc(C.Structure):
 class _PropertyDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("op", C.c_uint32), ("idx", C.POINTER(C.c_int32) * 4), ("idx_count", C.c_size_t * 4),
                 ("num_structures", C.c_size_t), ("structure_size", C.c_size_t), ("cutoff_min", C.c_float), ("cutoff_max", C.c_float),
-                ("structure_offsets", C.POINTER(C.c_uint32))]
+                ("structure_offsets", C.POINTER(C.c_uint32)), ("com_args", C.c_uint32)]
 
 
 class _PropertyData(C.Structure):
@@ -198,6 +198,7 @@ class Property:
     cutoff_min: float = 0.0
     cutoff_max: float = 0.0
     structure_offsets: Optional[np.ndarray] = None   # rdf_com: CSR offsets of the groups in idx[0]
+    com_args: int = 0                                # distance/angle/dihedral: bit k = argument k is a selection (centre of mass)
 
 
 def rdf(name, ref_idx, trg_idx, cutoff, cutoff_min=0.0):
@@ -223,16 +224,26 @@ def density(name, axis, idx):
     return Property(name, OP_DENSITY_X + int(axis), [np.asarray(idx, np.int32)])
 
 
+def _temporal(name, op, args):
+    """each argument: an int (0-based atom index -> that atom's position) or an index array (a selection -> centre of mass,
+    coordinate_extract_com md_script_functions.inl:1717)"""
+    idx, mask = [], 0
+    for k, a in enumerate(args):
+        if np.ndim(a) == 0: idx.append(np.asarray([int(a)], np.int32))
+        else: idx.append(np.asarray(a, np.int32)); mask |= 1 << k
+    return Property(name, op, idx, com_args=mask)
+
+
 def distance(name, a, b):
-    return Property(name, OP_DISTANCE, [np.asarray([a], np.int32), np.asarray([b], np.int32)])
+    return _temporal(name, OP_DISTANCE, (a, b))
 
 
 def angle(name, a, b, c):
-    return Property(name, OP_ANGLE, [np.asarray([a], np.int32), np.asarray([b], np.int32), np.asarray([c], np.int32)])
+    return _temporal(name, OP_ANGLE, (a, b, c))
 
 
 def dihedral(name, a, b, c, d):
-    return Property(name, OP_DIHEDRAL, [np.asarray([k], np.int32) for k in (a, b, c, d)])
+    return _temporal(name, OP_DIHEDRAL, (a, b, c, d))
 
 
 @dataclass
@@ -329,6 +340,7 @@ class Plan:
             d = descs[i]; nm = p.name.encode(); self._keep.append(nm)
             d.name = nm; d.op = p.op; d.num_structures = p.num_structures; d.structure_size = p.structure_size
             d.cutoff_min = p.cutoff_min; d.cutoff_max = p.cutoff_max
+            d.com_args = p.com_args
             if p.structure_offsets is not None:
                 so = np.ascontiguousarray(p.structure_offsets, np.uint32); self._keep.append(so)
                 d.structure_offsets = so.ctypes.data_as(C.POINTER(C.c_uint32))

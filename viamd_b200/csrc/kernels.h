@@ -71,7 +71,9 @@ void launch_density(const DensityArgs& a, int B, cudaStream_t s);
 
 struct TemporalArgs {
     BatchFrames frames; const mdgpu_unitcell_t* cells; int op; int atom[4]; float* out; uint32_t frame0;
+    const float* pos; uint32_t com_mask;   // [B][4][3] centres of mass (k_arg_com) for the arguments whose bit is set
 };
+void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s);
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned long long n, cudaStream_t s);
 

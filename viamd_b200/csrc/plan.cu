@@ -44,6 +44,7 @@ struct Prop {
     std::string name; uint32_t op = 0;
     std::vector<int32_t> h_idx[4]; int32_t* d_idx[4] = { nullptr, nullptr, nullptr, nullptr };
     size_t n_struct = 0, struct_size = 0;
+    uint32_t com_mask = 0;   // distance/angle/dihedral: bit k = argument k is a selection evaluated through md_util_com_compute
     std::vector<uint32_t> h_soff; uint32_t* d_soff = nullptr;   // rdf with centre-of-mass references: CSR offsets of the groups in idx[0]
     float cutoff_min = 0.f, cutoff_max = 0.f;
     // device accumulators
@@ -74,6 +75,7 @@ struct PropScratch {   // per (stream slot, property)
     uint32_t* d_frame_bins = nullptr; unsigned long long* d_frame_bins64 = nullptr;
     float4* d_sdf_xyzw = nullptr; float* d_sdf_ref0 = nullptr; float* d_sdf_mats = nullptr;
     float* d_com = nullptr;   // rdf with centre-of-mass references: [B][n_struct][3]
+    float* d_argpos = nullptr;   // distance/angle/dihedral with selection arguments: [B][4][3]
 };
 
 struct Slot {
@@ -152,7 +154,7 @@ static void destroy_plan(mdgpu_plan* p) {
     for (auto& s : p->slots) {
         for (auto& ps : s.ps) {
             cudaFree(ps.d_geom); cudaFree(ps.d_aabb); free_cell_list(ps.trg); free_cell_list(ps.ref);
-            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com);
+            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos);
         }
         cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
@@ -268,8 +270,11 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             break;
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
             const int need = pr.op == MDGPU_OP_DISTANCE ? 2 : (pr.op == MDGPU_OP_ANGLE ? 3 : 4);
-            for (int k = 0; k < need; ++k) if (pr.h_idx[k].size() != 1)
-                return bail(MDGPU_ERR_UNSUPPORTED, "'" + pr.name + "': only single-atom arguments are implemented for distance/angle/dihedral");
+            pr.com_mask = d.com_args & ((1u << need) - 1u);
+            for (int k = 0; k < need; ++k) {
+                if (pr.h_idx[k].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
+                if (pr.h_idx[k].size() != 1) pr.com_mask |= 1u << k;   // several indices: centre of mass (coordinate_extract_com :1759)
+            }
             e = dalloc(&pr.d_temporal, num_frames);
             pr.values.assign(num_frames, 0.0f);
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
@@ -389,6 +394,8 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     CUDA_TRY(dalloc(&ps.d_sdf_mats, (size_t)p->B * pr.n_struct * 32));
                 } else if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
                     CUDA_TRY(dalloc(&ps.d_frame_bins64, (size_t)p->B * MDGPU_DIST_BINS));
+                } else if (pr.com_mask) {
+                    CUDA_TRY(dalloc(&ps.d_argpos, (size_t)p->B * 12));
                 }
             }
         }
@@ -470,6 +477,9 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             TemporalArgs a{};
             a.frames = fr; a.cells = s.d_cells; a.op = (int)pr.op; a.out = pr.d_temporal; a.frame0 = frame0;
             for (int k = 0; k < 4; ++k) a.atom[k] = pr.h_idx[k].empty() ? 0 : pr.h_idx[k][0];
+            a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
+            for (int k = 0; k < 4; ++k) if (pr.com_mask & (1u << k))
+                launch_arg_com(fr, s.d_cells, pr.d_idx[k], (uint32_t)pr.h_idx[k].size(), p->d_mass, ps.d_argpos, k, s.stream);
             launch_temporal(a, B, s.stream);
             break; }
         default: break;

@@ -119,27 +119,150 @@ MDG_D void normalize3(float v[3]) {   // vec3_normalize core/md_vec_math.h:505-5
     if ((double)len > 1.0e-5) { v[0] = v[0] / len; v[1] = v[1] / len; v[2] = v[2] / len; } else { v[0] = v[1] = v[2] = 0.0f; }
 }
 
+// One lane of md_mm256_sincos_ps (core/md_simd.h:1177-1258, Cephes polynomials): every operation is an IEEE float op (explicit FMAs
+// where the reference has fmadd intrinsics), so the GPU reproduces the AVX2 build bit for bit.
+MDG_D void ref_sincosf(float x, float& out_s, float& out_c) {
+    uint32_t sign_bit_sin = __float_as_uint(x) & 0x80000000u;
+    x = fabsf(x);
+    float y = __fmul_rn(x, 1.27323954473516f);
+    int imm2 = __float2int_rz(y);
+    imm2 = (imm2 + 1) & ~1;
+    y = (float)imm2;
+    const uint32_t swap_sign_bit_sin = ((uint32_t)(imm2 & 4)) << 29;
+    const bool poly_mask = (imm2 & 2) == 0;
+    const uint32_t sign_bit_cos = ((uint32_t)(~(imm2 - 2) & 4)) << 29;
+    sign_bit_sin ^= swap_sign_bit_sin;
+    x = __fmaf_rn(y, -0.78515625f, x);
+    x = __fmaf_rn(y, -2.4187564849853515625E-4f, x);
+    x = __fmaf_rn(y, -3.77489470793079817668E-8f, x);
+    const float x2 = __fmul_rn(x, x), x3 = __fmul_rn(x2, x), x4 = __fmul_rn(x2, x2);
+    y = __fmaf_rn(x2, __fmaf_rn(x2, 2.443315711809948E-5f, -1.388731625493765E-3f), 4.166664568298827E-2f);
+    y = __fmaf_rn(x2, -0.5f, __fmul_rn(y, x4));
+    y = __fadd_rn(y, 1.0f);
+    float y2 = __fmaf_rn(x2, __fmaf_rn(x2, -1.9515295891E-4f, 8.3321608736E-3f), -1.6666654611E-1f);
+    y2 = __fmaf_rn(y2, x3, x);
+    const float ysin2 = poly_mask ? y2 : 0.0f, ysin1 = poly_mask ? 0.0f : y;
+    y2 = __fsub_rn(y2, ysin2); y = __fsub_rn(y, ysin1);
+    out_s = __uint_as_float(__float_as_uint(__fadd_rn(ysin1, ysin2)) ^ sign_bit_sin);
+    out_c = __uint_as_float(__float_as_uint(__fadd_rn(y, y2)) ^ sign_bit_cos);
+}
+
+// md_mm256_reduce_add_ps (core/md_simd.h:691, :678) over the 8 emulated lanes held by threads 0..7 of the warp
+MDG_D float reduce8(float v) {
+    v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 4));    // (l0+l4, l1+l5, l2+l6, l3+l7)
+    const float a = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1));   // lane0: (l0+l4)+(l1+l5), lane2: (l2+l6)+(l3+l7)
+    return __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 2));
+}
+
+// Position of one argument of distance/angle/dihedral that is a selection: md_util_com_compute (md_util.c:8163) as the reference's
+// AVX2 build evaluates it — threads 0..7 of the warp are the 8 SIMD lanes (element i goes to lane i % 8, sequential per lane), the
+// count % 8 tail and the final atan2 step run in double on thread 0. No cell (flags == 0): com() :7139; otherwise the trigonometric
+// periodic centre of mass com_pbc :8019 -> _com_pbc_iw :7850. One warp per (argument, frame).
+__global__ void k_arg_com(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ idx, uint32_t count,
+                          const float* __restrict__ mass, float* __restrict__ out /* [B][4][3] */, int arg) {
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const float* x = fr.xyz + (size_t)f * fr.frame_stride;
+    const float* src[3] = { x, x + fr.axis_stride, x + 2 * fr.axis_stride };
+    const mdgpu_unitcell_t uc = cells[f];
+    float* o = out + ((size_t)f * 4 + arg) * 3;
+    const uint32_t simd_count = count & ~7u;
+    if (uc.flags == 0) {
+        float v[4] = { 0.f, 0.f, 0.f, 0.f };
+        if (lane < 8) for (uint32_t i = lane; i < simd_count; i += 8) {
+            const int a = idx[i]; const float w = mass[a];
+            v[0] = __fadd_rn(v[0], __fmul_rn(src[0][a], w)); v[1] = __fadd_rn(v[1], __fmul_rn(src[1][a], w));
+            v[2] = __fadd_rn(v[2], __fmul_rn(src[2][a], w)); v[3] = __fadd_rn(v[3], w);
+        }
+        double acc[4];
+        for (int k = 0; k < 4; ++k) acc[k] = (double)reduce8(v[k]);
+        if (lane == 0) {
+            for (uint32_t i = simd_count; i < count; ++i) {
+                const int a = idx[i]; const float w = mass[a];
+                acc[0] += (double)__fmul_rn(src[0][a], w); acc[1] += (double)__fmul_rn(src[1][a], w); acc[2] += (double)__fmul_rn(src[2][a], w); acc[3] += (double)w;
+            }
+            for (int k = 0; k < 3; ++k) o[k] = (float)(acc[k] / acc[3]);
+        }
+        return;
+    }
+    float A[3][3] = { { (float)uc.x, 0.f, 0.f }, { (float)uc.xy, (float)uc.y, 0.f }, { (float)uc.xz, (float)uc.yz, (float)uc.z } };
+    float M[3][3], I[3][3];
+    {   // md_unitcell_I_extract_double md_unitcell.inl:158-176, then float; M = 2pi * Ai, I = A / 2pi element-wise (com_pbc :8027-8030)
+        const double cx = uc.x, cy = uc.y, cz = uc.z;
+        const double i11 = cx > 0.0 ? 1.0 / cx : 0.0, i22 = cy > 0.0 ? 1.0 / cy : 0.0, i33 = cz > 0.0 ? 1.0 / cz : 0.0;
+        const double i12 = (cx * cy) > 0.0 ? -uc.xy / (cx * cy) : 0.0;
+        const double i13 = (cx * cy * cz) > 0.0 ? (uc.xy * uc.yz - uc.xz * cy) / (cx * cy * cz) : 0.0;
+        const double i23 = (cy * cz) > 0.0 ? -uc.yz / (cy * cz) : 0.0;
+        const double Id[3][3] = { { i11, 0, 0 }, { i12, i22, 0 }, { i13, i23, i33 } };
+        const float tp = (float)6.283185307179586, itp = (float)(1.0 / 6.283185307179586);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { M[r][c] = __fmul_rn(tp, (float)Id[r][c]); I[r][c] = __fmul_rn(A[r][c], itp); }
+    }
+    float vs[3] = { 0.f, 0.f, 0.f }, vc[3] = { 0.f, 0.f, 0.f }, vw = 0.f;
+    if (lane < 8) for (uint32_t i = lane; i < simd_count; i += 8) {
+        const int a = idx[i]; const float w = mass[a];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float p = src[k][a];
+            const float t = __fmaf_rn(p, M[k][0], __fmaf_rn(p, M[k][1], __fmul_rn(p, M[k][2])));
+            float sn, cs; ref_sincosf(t, sn, cs);
+            vs[k] = __fmaf_rn(sn, w, vs[k]); vc[k] = __fmaf_rn(cs, w, vc[k]);
+        }
+        vw = __fadd_rn(vw, w);
+    }
+    double acc_s[3], acc_c[3], acc_w = (double)reduce8(vw);
+    for (int k = 0; k < 3; ++k) { acc_s[k] = (double)reduce8(vs[k]); acc_c[k] = (double)reduce8(vc[k]); }
+    if (lane == 0) {
+        for (uint32_t i = simd_count; i < count; ++i) {   // scalar remainder in double (:7988-8003)
+            const int a = idx[i]; const double w = (double)mass[a];
+            for (int k = 0; k < 3; ++k) {
+                const double p = (double)src[k][a];
+                const double t = __dadd_rn(__dadd_rn(__dmul_rn(p, (double)M[k][0]), __dmul_rn(p, (double)M[k][1])), __dmul_rn(p, (double)M[k][2]));
+                acc_c[k] = __dadd_rn(acc_c[k], __dmul_rn(w, cos(t))); acc_s[k] = __dadd_rn(acc_s[k], __dmul_rn(w, sin(t)));
+            }
+            acc_w += w;
+        }
+        const double inv_w = 1.0 / acc_w;
+        for (int k = 0; k < 3; ++k) {
+            double theta = 3.14159265358979323846;
+            const double px = __dmul_rn(acc_c[k], inv_w), py = __dmul_rn(acc_s[k], inv_w);
+            if (__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)) > 1.0e-8) theta += atan2(-py, -px);
+            o[k] = (float)__dadd_rn(__dadd_rn(__dmul_rn(theta, (double)I[k][0]), __dmul_rn(theta, (double)I[k][1])), __dmul_rn(theta, (double)I[k][2]));
+        }
+    }
+}
+
+void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s) {
+    if (!fr.count || !count) return;
+    k_arg_com<<<fr.count, 32, 0, s>>>(fr, d_cells, d_idx, count, d_mass, d_out, arg);
+    note_launch("k_arg_com", s);
+}
+
+// distance / angle / dihedral on the argument positions: an atom's coordinates (single index, coordinate_extract_com :1755) or the
+// centre of mass k_arg_com left in a.pos
 __global__ void k_temporal(TemporalArgs a, int B) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= B) return;
     const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride; const float* y = x + a.frames.axis_stride; const float* z = y + a.frames.axis_stride;
     const mdgpu_unitcell_t uc = a.cells[f];
     const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
+    const int nargs = a.op == MDGPU_OP_DISTANCE ? 2 : (a.op == MDGPU_OP_ANGLE ? 3 : 4);
+    float P[4][3];
+    for (int k = 0; k < nargs; ++k) {
+        if (a.com_mask & (1u << k)) { const float* p = a.pos + ((size_t)f * 4 + k) * 3; P[k][0] = p[0]; P[k][1] = p[1]; P[k][2] = p[2]; }
+        else { const int at = a.atom[k]; P[k][0] = x[at]; P[k][1] = y[at]; P[k][2] = z[at]; }
+    }
     float out = 0.0f;
     if (a.op == MDGPU_OP_DISTANCE) {
-        const int ia = a.atom[0], ib = a.atom[1];
-        const float pa[3] = { x[ia], y[ia], z[ia] }; float pb[3] = { x[ib], y[ib], z[ib] };
+        const float* pa = P[0]; float pb[3] = { P[1][0], P[1][1], P[1][2] };
         if (uc.flags & MDGPU_CELL_ORTHO) for (int k = 0; k < 3; ++k) pb[k] = deperiodize1p(pb[k], pa[k], ext[k]);   // md_util_deperiodize_vec4 md_util.c:8971
         const float d[3] = { pa[0] - pb[0], pa[1] - pb[1], pa[2] - pb[2] };
         out = __fsqrt_rn(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     } else if (a.op == MDGPU_OP_ANGLE) {
-        const int ia = a.atom[0], ib = a.atom[1], ic = a.atom[2];
-        float v0[3] = { x[ia] - x[ib], y[ia] - y[ib], z[ia] - z[ib] }, v1[3] = { x[ic] - x[ib], y[ic] - y[ib], z[ic] - z[ib] };
+        float v0[3] = { P[0][0] - P[1][0], P[0][1] - P[1][1], P[0][2] - P[1][2] }, v1[3] = { P[2][0] - P[1][0], P[2][1] - P[1][1], P[2][2] - P[1][2] };
         normalize3(v0); normalize3(v1);
         out = acosf(v0[0] * v1[0] + v0[1] * v1[1] + v0[2] * v1[2]);
     } else if (a.op == MDGPU_OP_DIHEDRAL) {
         float dx[3][3];
-        for (int k = 0; k < 3; ++k) { const int p = a.atom[k], q = a.atom[k + 1]; dx[k][0] = x[q] - x[p]; dx[k][1] = y[q] - y[p]; dx[k][2] = z[q] - z[p]; }
+        for (int k = 0; k < 3; ++k) for (int i = 0; i < 3; ++i) dx[k][i] = P[k + 1][i] - P[k][i];
         if (uc.flags & MDGPU_CELL_ORTHO) {   // min_image_ortho md_util.c:8424-8436
             for (int k = 0; k < 3; ++k) for (int i = 0; i < 3; ++i) {
                 const float half = ext[i] * 0.5f;

@@ -150,8 +150,11 @@ class _Parser:
     def number(self) -> float:
         return float(self.expect("num")[1])
 
-    def index(self) -> int:
-        return int(float(self.expect("num")[1])) - 1   # md_script atom indices are 1-based
+    def index(self):
+        """argument of distance/angle/dihedral: a 1-based atom index (-> int) or a selection (-> index array, centre of mass)"""
+        if self.peek()[0] == "num":
+            return int(float(self.expect("num")[1])) - 1   # md_script atom indices are 1-based
+        return self.selection()
 
     def statement(self) -> api.Property:
         ident = self.expect("id")[1]; self.expect("ch", "=")
