@@ -316,32 +316,59 @@ MDG_D int wrap_coord(int v, int N) { v += (v < 0) ? N : 0; v -= (v >= N) ? N : 0
 MDG_D int isign(int v) { return (v > 0) - (v < 0); }
 
 // K4: one warp per (structure, frame): target points of the cells overlapping AABB(com, cutoff) -> voxel increments.
-// The cells of the range are flattened into one index range (prefix table in shared memory) so that all 32 lanes stay busy.
+//  * the cells of the range are flattened into one index range (prefix table in shared memory), 32 candidates per warp step; the
+//    segment of each lane's candidate comes from a 32-bit mask of the segment boundaries inside the step (no per-lane search);
+//  * candidates that pass the box test and the exclusion mask are compacted into a per-warp ring in shared memory; the transform +
+//    voxel atomics run on full groups of 32 (the hit rate is ~22 %, so running them in place would leave two thirds of the lanes idle).
 constexpr int SDF_WARPS = 8;
 constexpr int SDF_MAXSEG = 128;
 constexpr int SDF_EXCL_CACHE = 64;
+constexpr int SDF_RING = 64;
+
+struct SdfXform { float M[4][3]; float A00, A11, A22, O0, O1, O2; };
+
+// fractional (image-shifted) point -> cartesian -> structure frame -> voxel (:5664-5697)
+MDG_D void sdf_splat(float vx, float vy, float vz, const SdfXform& X, uint32_t* __restrict__ vol) {
+    // batch_fract_to_cart_ort_256: one fused multiply-add per axis (md_spatial_acc.c:583-592)
+    const float px = __fmaf_rn(vx, X.A00, X.O0), py = __fmaf_rn(vy, X.A11, X.O1), pz = __fmaf_rn(vz, X.A22, X.O2);
+    float c[3];   // mat4_mul_vec4(M, (x,y,z,1)) = ((x*M0 + y*M1) + z*M2) + 1*M3
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float v = __fmul_rn(px, X.M[0][r]);
+        v = __fadd_rn(v, __fmul_rn(py, X.M[1][r]));
+        v = __fadd_rn(v, __fmul_rn(pz, X.M[2][r]));
+        v = __fadd_rn(v, __fmul_rn(1.0f, X.M[3][r]));
+        c[r] = v;
+    }
+    const uint32_t ix = (uint32_t)max(0, min(__float2int_rz(c[0]), MDGPU_VOL_DIM - 1));
+    const uint32_t iy = (uint32_t)max(0, min(__float2int_rz(c[1]), MDGPU_VOL_DIM - 1));
+    const uint32_t iz = (uint32_t)max(0, min(__float2int_rz(c[2]), MDGPU_VOL_DIM - 1));
+    atomicAdd(&vol[(iz * MDGPU_VOL_DIM + iy) * MDGPU_VOL_DIM + ix], 1u);
+}
+
 __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B) {
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t s = blockIdx.x * SDF_WARPS + warp;
     __shared__ uint32_t s_pre[SDF_WARPS][SDF_MAXSEG + 1];
-    __shared__ uint32_t s_start[SDF_WARPS][SDF_MAXSEG];
-    __shared__ uint32_t s_code[SDF_WARPS][SDF_MAXSEG];
+    __shared__ uint2 s_seg[SDF_WARPS][SDF_MAXSEG];        // x: start - pre (first point of the segment minus its flattened offset), y: image code
+    __shared__ float s_ring[SDF_WARPS][3][SDF_RING];
+    __shared__ int32_t s_excl[SDF_WARPS][SDF_EXCL_CACHE];
     if (s >= a.n_struct) return;
     const FrameGeom& g = a.geom[f];
     if (g.valid == -1 || (g.flags & MDGPU_CELL_TRICLINIC)) return;   // triclinic AABB query: rejected by the host
     const float* rec = a.matrices + ((size_t)f * a.n_struct + s) * SDF_REC;
-    float M[4][3];
+    SdfXform X;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) M[i][j] = rec[i * 4 + j];
+        for (int j = 0; j < 3; ++j) X.M[i][j] = rec[i * 4 + j];
+    X.A00 = g.A[0][0]; X.A11 = g.A[1][1]; X.A22 = g.A[2][2]; X.O0 = g.origin[0]; X.O1 = g.origin[1]; X.O2 = g.origin[2];
     const float lo3[3] = { rec[20], rec[21], rec[22] }, hi3[3] = { rec[23], rec[24], rec[25] };
     const int* ri = (const int*)(rec + 26);
     const int cmin[3] = { ri[0], ri[1], ri[2] }, cmax[3] = { ri[3], ri[4], ri[5] };
     const int pbc[3] = { (g.flags & MDGPU_CELL_PBC_X) != 0, (g.flags & MDGPU_CELL_PBC_Y) != 0, (g.flags & MDGPU_CELL_PBC_Z) != 0 };
     const int cd[3] = { g.cdim[0], g.cdim[1], g.cdim[2] };
-    const float A00 = g.A[0][0], A11 = g.A[1][1], A22 = g.A[2][2], O0 = g.origin[0], O1 = g.origin[1], O2 = g.origin[2];
     const float4* __restrict__ pts = a.trg.sorted + (size_t)f * a.trg.max_points;
     const uint32_t* __restrict__ off = a.trg.cell_cnt + (size_t)f * (a.trg.cap + 1);
     const int32_t* sidx = a.struct_idx + (size_t)s * a.struct_size;
@@ -349,10 +376,12 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
     // is tested with one compare; otherwise the list (cached in shared memory when it fits) is scanned.
     const uint32_t ex_lo = (uint32_t)sidx[0], ex_n = a.struct_size;
     const bool ex_contig = ((uint32_t)sidx[a.struct_size - 1] - ex_lo + 1u) == ex_n;
-    __shared__ int32_t s_excl[SDF_WARPS][SDF_EXCL_CACHE];
     if (!ex_contig) { for (uint32_t k = lane; k < min(ex_n, (uint32_t)SDF_EXCL_CACHE); k += 32) s_excl[warp][k] = sidx[k]; }
     const int ex = cmax[0] - cmin[0], ey = cmax[1] - cmin[1], ez = cmax[2] - cmin[2];
     const int ncells = ex * ey * ez;
+    const uint32_t lt = (1u << lane) - 1u;
+    float* rx = s_ring[warp][0]; float* ry = s_ring[warp][1]; float* rz = s_ring[warp][2];
+    uint32_t cnt = 0;                      // candidates waiting in the ring (warp-uniform, < 32 between steps)
     unsigned long long local = 0;
     for (int c0 = 0; c0 < ncells; c0 += SDF_MAXSEG) {   // (:1925-1943) cells of the range, SDF_MAXSEG at a time
         const int nc = min(SDF_MAXSEG, ncells - c0);
@@ -375,55 +404,62 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
             uint32_t incl = len;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (len) { const int slot = nseg + __popc(have & ((1u << lane) - 1u)); s_pre[warp][slot] = base + incl - len; s_start[warp][slot] = start; s_code[warp][slot] = code; }
+            if (len) { const int slot = nseg + __popc(have & lt); const uint32_t pre = base + incl - len; s_pre[warp][slot] = pre; s_seg[warp][slot] = make_uint2(start - pre, code); }
             base += __shfl_sync(0xffffffffu, incl, 31);
             nseg += __popc(have);
         }
         const uint32_t total = base;
         if (lane == 0) s_pre[warp][nseg] = total;
         __syncwarp();
-        int kbase = 0;
+        int kbase = 0;                     // segment that contains candidate j0 (warp-uniform)
         for (uint32_t j0 = 0; j0 < total; j0 += 32) {
-            while (kbase + 1 < nseg && s_pre[warp][kbase + 1] <= j0) ++kbase;   // warp-uniform
+            // segment boundaries inside (j0, j0+32]: bit (b - j0 - 1). Segments are non-empty, so they are among the next 32 table entries.
+            const int kb = kbase + 1 + lane;
+            const uint32_t bnd = (kb <= nseg) ? s_pre[warp][kb] : 0xffffffffu;
+            const uint32_t rel = bnd - j0 - 1u;
+            const uint32_t bm = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
             const uint32_t j = j0 + lane;
-            if (j >= total) continue;
-            int k = kbase;
-            while (s_pre[warp][k + 1] <= j) ++k;
-            const float4 t = pts[s_start[warp][k] + (j - s_pre[warp][k])];
-            const uint32_t code = s_code[warp][k];
-            const float shx = (float)((int)(code & 3u) - 1), shy = (float)((int)((code >> 2) & 3u) - 1), shz = (float)((int)((code >> 4) & 3u) - 1);
-            const float vx = __fadd_rn(t.x, shx), vy = __fadd_rn(t.y, shy), vz = __fadd_rn(t.z, shz);   // (:1962-1964)
-            if (!(vx >= lo3[0] && vy >= lo3[1] && vz >= lo3[2] && vx <= hi3[0] && vy <= hi3[1] && vz <= hi3[2])) continue;
-            const uint32_t idx = __float_as_uint(t.w);
-            bool excluded;
-            if (ex_contig) excluded = (idx - ex_lo) < ex_n;
-            else {
-                excluded = false;
-                const uint32_t nc_ = min(ex_n, (uint32_t)SDF_EXCL_CACHE);
-                for (uint32_t q = 0; q < nc_; ++q) excluded |= ((uint32_t)s_excl[warp][q] == idx);
-                for (uint32_t q = nc_; q < ex_n; ++q) excluded |= ((uint32_t)sidx[q] == idx);
+            bool hit = false; float vx = 0.f, vy = 0.f, vz = 0.f;
+            if (j < total) {
+                const uint2 sg = s_seg[warp][kbase + __popc(bm & lt)];
+                const float4 t = pts[sg.x + j];
+                vx = t.x; vy = t.y; vz = t.z;
+                if (sg.y != 0x15u) {   // periodic image of the cell: + (-1|0|+1), rounded (:1962-1964); +0 is the identity
+                    vx = __fadd_rn(vx, (float)((int)(sg.y & 3u) - 1)); vy = __fadd_rn(vy, (float)((int)((sg.y >> 2) & 3u) - 1)); vz = __fadd_rn(vz, (float)((int)((sg.y >> 4) & 3u) - 1));
+                }
+                hit = vx >= lo3[0] && vy >= lo3[1] && vz >= lo3[2] && vx <= hi3[0] && vy <= hi3[1] && vz <= hi3[2];
+                if (hit) {
+                    const uint32_t idx = __float_as_uint(t.w);
+                    if (ex_contig) hit = (idx - ex_lo) >= ex_n;
+                    else {
+                        bool excluded = false;
+                        const uint32_t nc_ = min(ex_n, (uint32_t)SDF_EXCL_CACHE);
+                        for (uint32_t q = 0; q < nc_; ++q) excluded |= ((uint32_t)s_excl[warp][q] == idx);
+                        for (uint32_t q = nc_; q < ex_n; ++q) excluded |= ((uint32_t)sidx[q] == idx);
+                        hit = !excluded;
+                    }
+                }
             }
-            if (excluded) continue;
-            // batch_fract_to_cart_ort_256: one fused multiply-add per axis (:583-592)
-            const float px = __fmaf_rn(vx, A00, O0), py = __fmaf_rn(vy, A11, O1), pz = __fmaf_rn(vz, A22, O2);
-            float c[3];   // mat4_mul_vec4(M, (x,y,z,1)) = ((x*M0 + y*M1) + z*M2) + 1*M3
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                float v = __fmul_rn(px, M[0][r]);
-                v = __fadd_rn(v, __fmul_rn(py, M[1][r]));
-                v = __fadd_rn(v, __fmul_rn(pz, M[2][r]));
-                v = __fadd_rn(v, __fmul_rn(1.0f, M[3][r]));
-                c[r] = v;
+            kbase += __popc(bm);
+            const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+            if (hit) { const uint32_t p = cnt + __popc(hm & lt); rx[p] = vx; ry[p] = vy; rz[p] = vz; }
+            cnt += __popc(hm);
+            if (cnt >= 32u) {
+                __syncwarp();
+                sdf_splat(rx[lane], ry[lane], rz[lane], X, a.vol);
+                const uint32_t rem = cnt - 32u;
+                float mx = 0.f, my = 0.f, mz = 0.f;
+                if (lane < rem) { mx = rx[32 + lane]; my = ry[32 + lane]; mz = rz[32 + lane]; }
+                __syncwarp();
+                if (lane < rem) { rx[lane] = mx; ry[lane] = my; rz[lane] = mz; }
+                cnt = rem; local += 32;
+                __syncwarp();
             }
-            const int ix = max(0, min(__float2int_rz(c[0]), MDGPU_VOL_DIM - 1));
-            const int iy = max(0, min(__float2int_rz(c[1]), MDGPU_VOL_DIM - 1));
-            const int iz = max(0, min(__float2int_rz(c[2]), MDGPU_VOL_DIM - 1));
-            atomicAdd(&a.vol[((size_t)iz * MDGPU_VOL_DIM + iy) * MDGPU_VOL_DIM + ix], 1u);
-            local += 1;
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __syncwarp();
+    if (lane < cnt) sdf_splat(rx[lane], ry[lane], rz[lane], X, a.vol);
+    local += cnt;
     if (lane == 0 && local) atomicAdd(&a.frame_total[a.frame0 + f], local);
 }
 
