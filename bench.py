@@ -177,17 +177,30 @@ def impl_reference(args):
                  "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
                                   "sample": f"{sample} frames per step x {args.steps} steps of the same workload, in-memory trajectory"},
                  "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the process's real stdout; everything else written to fd 1 meanwhile (NCCL's version banner, library
+    chatter) was redirected to stderr in main()"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None: sys.stdout.write(data.decode()); sys.stdout.flush()
+    else: os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush(); _REAL_STDOUT = os.dup(1); os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=2368)   # 16 x 148 frames
+    ap.add_argument("--frames-per-step", type=int, default=4736)   # 32 x 148 frames
     ap.add_argument("--batch-frames", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--rdf-variant", type=int, default=0)
@@ -217,6 +230,9 @@ def main():
     sysm = vb.water_system(n)
     props = vb.compile_script(SCRIPT, sysm)
     total_steps = W + K
+    # all (warm-up + timed) steps read distinct device-resident frames; keep that shard under ~60 GB of the 180 GB HBM
+    max_fps = int(60e9 // (total_steps * 3 * na * 4)) // 148 * 148
+    FPS = max(148, min(FPS, max_fps))
     frames_local = total_steps * FPS
     plan = vb.Plan(sysm, props, frames_local, device=dev, batch_frames=args.batch_frames, num_streams=args.streams, rdf_variant=args.rdf_variant)
     cell = vb.UnitCell.from_basis(L, L, L)
@@ -339,7 +355,7 @@ def main():
             else:
                 r = oracle_port_sample(4)
                 line["cpu_baseline"] = {"value": r["frames_per_s"], "unit": UNIT, "cores": 1, "kind": "port", "sample": "4 frames, oracle/md_oracle.c scalar port"}
-        print(json.dumps(line))
+        emit(line)
     vb.device_free(dev, d_base); vb.device_free(dev, d_frames)
     plan.close()
     if world > 1:
