@@ -94,6 +94,10 @@ static bool make_traj(md_trajectory_i* out, mem_traj_t* mt, const char* spec, md
         mt->num_frames = nf; mt->num_atoms = mt->memb.num_atoms;
         mt->mbase = malloc(mt->num_atoms * 12); mt->mmol = malloc(mt->num_atoms * 4);
         mdsynth_membrane_base(&mt->memb, mt->mbase, NULL, mt->mmol);
+    } else if (strncmp(spec, "xtc:", 4) == 0) {   /* the reference's own XTC reader (md_xtc.c) */
+        md_trajectory_i* t = md_xtc_trajectory_create((str_t){ spec + 4, strlen(spec + 4) }, md_get_heap_allocator(), MD_TRAJECTORY_FLAG_DISABLE_CACHE_WRITE);
+        if (!t) { fprintf(stderr, "failed to open xtc %s\n", spec + 4); return false; }
+        *out = *t; return true;
     } else if (strcmp(spec, "sys") == 0) {
         if (!sys->trajectory) { fprintf(stderr, "system has no attached trajectory\n"); return false; }
         *out = *sys->trajectory; return true;

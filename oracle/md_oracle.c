@@ -882,3 +882,155 @@ void mdo_group_com(const float* x, const float* y, const float* z, const float* 
         out[3 * g + 0] = sx / sw; out[3 * g + 1] = sy / sw; out[3 * g + 2] = sz / sw;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * XTC frame decode: md_xtc_decode_frame_data_soa_scaled (md_xtc.c:747-931) as xtc_reader_load_frame calls it (:947-993, scale 10:
+ * nm -> Angstrom), restated with a plain bit reader and 128-bit integers. The packed integers are transmitted as whole bytes,
+ * least significant first, followed by the remaining high bits (ext/xtc/xdrfile.c: sendints/receiveints; md_xtc.c:304-315 reads
+ * the same thing with a byte swap).
+ */
+static const uint32_t xtc_magicints[] = {
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512, 645, 812, 1024, 1290, 1625, 2048, 2580, 3250, 4096,
+    5060, 6501, 8192, 10321, 13003, 16384, 20642, 26007, 32768, 41285, 52015, 65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127, 524287,
+    660561, 832255, 1048576, 1321122, 1664510, 2097152, 2642245, 3329021, 4194304, 5284491, 6658042, 8388607, 10568983, 13316085, 16777216 };
+#define XTC_FIRSTIDX 9
+#define XTC_LASTIDX ((int)(sizeof(xtc_magicints) / sizeof(xtc_magicints[0])))
+
+typedef struct { const uint8_t* p; size_t nbits_total; size_t pos; } xtc_bits_t;
+static uint32_t xtc_get(xtc_bits_t* b, unsigned n) {   /* n <= 32 bits, most significant first */
+    uint32_t v = 0;
+    for (unsigned i = 0; i < n; ++i, ++b->pos) {
+        const unsigned bit = b->pos < b->nbits_total ? (b->p[b->pos >> 3] >> (7 - (b->pos & 7))) & 1u : 0u;
+        v = (v << 1) | bit;
+    }
+    return v;
+}
+static uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+static float bef32(const uint8_t* p) { return f_from_bits(be32(p)); }
+
+static int xtc_sizeofint(uint32_t size) {   /* md_xtc.c:157-166 */
+    uint32_t num = 1; int nb = 0;
+    while ((int)size >= (int)num && nb < 32) { nb++; num *= 2; }
+    return nb;
+}
+static int xtc_sizeofints(const uint32_t sizes[3]) {   /* md_xtc.c:168-193: bits of the product of the three sizes */
+    unsigned __int128 prod = (unsigned __int128)sizes[0] * sizes[1]; prod *= sizes[2];
+    int nbytes = 0; unsigned __int128 t = prod; while (t > 0xff) { t >>= 8; nbytes++; }
+    uint32_t top = (uint32_t)t, num = 1; int nb = 0;
+    while (top >= num) { nb++; num *= 2; }
+    return nb + nbytes * 8;
+}
+/* `nbits` wide packed field -> three integers with mixed radix (size_y, size_z) */
+static void xtc_unpack3(xtc_bits_t* b, unsigned nbits, uint32_t size_y, uint32_t size_z, int32_t out[3]) {
+    unsigned __int128 v = 0; unsigned shift = 0, left = nbits;
+    while (left >= 8) { v |= (unsigned __int128)xtc_get(b, 8) << shift; shift += 8; left -= 8; }
+    if (left) v |= (unsigned __int128)xtc_get(b, left) << shift;
+    const unsigned __int128 zy = (unsigned __int128)size_z * size_y;
+    const uint32_t x = (uint32_t)(v / zy);
+    const uint64_t yz = (uint64_t)(v / size_z);
+    out[0] = (int32_t)x; out[1] = (int32_t)(uint32_t)(yz - (uint64_t)x * size_y); out[2] = (int32_t)(uint32_t)((uint64_t)v - yz * size_z);
+}
+/* bitsize == 0 branch (an axis spans more than 0xffffff units): one plain big-endian integer per axis, as the format's writer emits them
+ * (ext/xtc/xdrfile.c: sendbits / receivebits). NOTE: the reference's reader mis-decodes this branch (unpack_uint32 md_xtc.c:295 applies the
+ * byte order of the packed fields and shifts a 32-bit word by a 64-bit alignment) and also the > 64-bit packed field (unpack_coord128 :317);
+ * both only occur for boxes wider than ~2.6 um. Here they follow the file format, checked by round trip against the written coordinates. */
+static uint32_t xtc_unpack1(xtc_bits_t* b, unsigned nbits) { return xtc_get(b, nbits); }
+
+int mdo_xtc_decode_frame(const uint8_t* frame, size_t nbytes, size_t num_atoms, float* x, float* y, float* z,
+                         mdo_unitcell_t* cell, int32_t* step, float* time) {
+    const float scale = 10.0f;   /* xtc_reader_load_frame :976 */
+    if (!frame || nbytes < 56 || be32(frame) != 1995u) return 0;
+    const int32_t natoms = (int32_t)be32(frame + 4);
+    if (step) *step = (int32_t)be32(frame + 8);
+    if (time) *time = bef32(frame + 12);
+    if (cell) {   /* box[i] *= scale (:765-768); md_unitcell_from_matrix_float md_unitcell.inl:109 -> from_basis_parameters :12-31 */
+        float box[9]; for (int i = 0; i < 9; ++i) box[i] = bef32(frame + 16 + 4 * i) * scale;
+        const double cx = box[0], cy = box[4], cz = box[8], xy = box[3], xz = box[6], yz = box[7];
+        uint32_t flags = 0;
+        if (xy == 0.0 && xz == 0.0 && yz == 0.0) { if (!(cx == 0.0 && cy == 0.0 && cz == 0.0) && !(cx == 1.0 && cy == 1.0 && cz == 1.0)) flags |= MDO_CELL_ORTHO; }
+        else flags |= MDO_CELL_TRICLINIC;
+        if (flags) { if (cx != 0.0) flags |= MDO_CELL_PBC_X; if (cy != 0.0) flags |= MDO_CELL_PBC_Y; if (cz != 0.0) flags |= MDO_CELL_PBC_Z; }
+        cell->x = cx; cell->xy = xy; cell->xz = xz; cell->y = cy; cell->yz = yz; cell->z = cz; cell->flags = flags;
+    }
+    if (!x || !y || !z) return 1;
+    if ((int32_t)be32(frame + 52) != (int32_t)num_atoms || natoms != (int32_t)num_atoms) return 0;
+    size_t off = 56;
+    if (natoms <= 9) {
+        if (nbytes < off + 12u * (size_t)natoms) return 0;
+        for (int i = 0; i < natoms; ++i) { x[i] = bef32(frame + off + 12 * i) * scale; y[i] = bef32(frame + off + 12 * i + 4) * scale; z[i] = bef32(frame + off + 12 * i + 8) * scale; }
+        return 1;
+    }
+    if (nbytes < 92) return 0;
+    const float precision = bef32(frame + off); off += 4;
+    int32_t minint[3], maxint[3];
+    for (int k = 0; k < 3; ++k) minint[k] = (int32_t)be32(frame + off + 4 * k);
+    off += 12;
+    for (int k = 0; k < 3; ++k) maxint[k] = (int32_t)be32(frame + off + 4 * k);
+    off += 12;
+    int smallidx = (int32_t)be32(frame + off); off += 4;
+    if (smallidx < XTC_FIRSTIDX || smallidx >= XTC_LASTIDX) return 0;
+    const uint32_t sizeint[3] = { (uint32_t)(maxint[0] - minint[0] + 1), (uint32_t)(maxint[1] - minint[1] + 1), (uint32_t)(maxint[2] - minint[2] + 1) };
+    unsigned bitsize = 0, bitsizeint[3] = { 0, 0, 0 };
+    if ((sizeint[0] | sizeint[1] | sizeint[2]) > 0xffffffu) { for (int k = 0; k < 3; ++k) bitsizeint[k] = (unsigned)xtc_sizeofint(sizeint[k]); }
+    else bitsize = (unsigned)xtc_sizeofints(sizeint);
+    int smaller = (int)(xtc_magicints[smallidx - 1 > XTC_FIRSTIDX ? smallidx - 1 : XTC_FIRSTIDX] / 2);
+    int smallnum = (int)(xtc_magicints[smallidx] / 2);
+    const uint32_t data_bytes = be32(frame + off); off += 4;
+    if (nbytes < off + data_bytes) return 0;
+    xtc_bits_t br = { frame + off, (size_t)data_bytes * 8, 0 };
+    const float coord_scale = scale / precision;
+    int run = 0, run_count = 0, atom = 0;
+    int32_t c[3];
+    while (atom < natoms) {
+        if (bitsize == 0) { for (int k = 0; k < 3; ++k) c[k] = (int32_t)xtc_unpack1(&br, bitsizeint[k]); }
+        else xtc_unpack3(&br, bitsize, sizeint[1], sizeint[2], c);
+        for (int k = 0; k < 3; ++k) c[k] += minint[k];
+        const uint32_t flag = xtc_get(&br, 1);
+        int is_smaller = 0;
+        if (flag) { run = (int)xtc_get(&br, 5); run_count = run / 3; is_smaller = run % 3; run -= is_smaller; is_smaller--; }
+        if (atom + run_count + 1 > natoms) return 0;
+        if (run > 0) {
+            const int32_t prev[3] = { c[0], c[1], c[2] };
+            const uint32_t ss = xtc_magicints[smallidx];
+            int32_t d[3];
+            xtc_unpack3(&br, (unsigned)smallidx, ss, ss, d);
+            for (int k = 0; k < 3; ++k) c[k] = d[k] + (c[k] - smallnum);
+            x[atom] = (float)c[0] * coord_scale; y[atom] = (float)c[1] * coord_scale; z[atom] = (float)c[2] * coord_scale; ++atom;      /* first two swapped (:855-856) */
+            x[atom] = (float)prev[0] * coord_scale; y[atom] = (float)prev[1] * coord_scale; z[atom] = (float)prev[2] * coord_scale; ++atom;
+            for (int i = 1; i < run_count; ++i) {
+                xtc_unpack3(&br, (unsigned)smallidx, ss, ss, d);
+                for (int k = 0; k < 3; ++k) c[k] = d[k] + (c[k] - smallnum);
+                x[atom] = (float)c[0] * coord_scale; y[atom] = (float)c[1] * coord_scale; z[atom] = (float)c[2] * coord_scale; ++atom;
+            }
+        } else {
+            x[atom] = (float)c[0] * coord_scale; y[atom] = (float)c[1] * coord_scale; z[atom] = (float)c[2] * coord_scale; ++atom;
+        }
+        smallidx += is_smaller;
+        if (is_smaller < 0) { smallnum = smaller; smaller = smallidx > XTC_FIRSTIDX ? (int)(xtc_magicints[smallidx - 1] / 2) : 0; }
+        else if (is_smaller > 0) { smaller = smallnum; smallnum = (int)(xtc_magicints[smallidx] / 2); }
+        if (smallidx < XTC_FIRSTIDX || smallidx >= XTC_LASTIDX) return 0;
+    }
+    return atom == natoms;
+}
+
+/* md_xtc_read_frame_offsets_and_times md_xtc.c:436-570 on a file image: offsets[0..n] (offsets[n] = end); returns n */
+size_t mdo_xtc_frame_offsets(const uint8_t* file, size_t nbytes, int64_t* offsets, size_t cap) {
+    if (nbytes < 56 || be32(file) != 1995u || cap < 2) return 0;
+    const int32_t natoms = (int32_t)be32(file + 4);
+    if (natoms <= 0) return 0;
+    size_t n = 0, pos = 0;
+    if (natoms <= 9) {
+        const size_t fb = 56 + 12u * (size_t)natoms;
+        while (pos + fb <= nbytes && n + 1 < cap && be32(file + pos) == 1995u) { offsets[n++] = (int64_t)pos; pos += fb; }
+        offsets[n] = (int64_t)(n * fb);
+        return n;
+    }
+    while (pos != nbytes && n + 1 < cap) {
+        if (pos + 92 > nbytes || be32(file + pos) != 1995u) break;
+        const size_t fb = ((size_t)be32(file + pos + 88) + 3u) & ~(size_t)3;
+        if (pos + 92 + fb > nbytes) break;
+        offsets[n++] = (int64_t)pos; pos += 92 + fb;
+    }
+    offsets[n] = (int64_t)pos;
+    return n;
+}

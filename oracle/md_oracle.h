@@ -70,6 +70,13 @@ float mdo_distance_pos(const float a[3], const float b[3], const mdo_unitcell_t*
 float mdo_angle_pos(const float a[3], const float b[3], const float c[3]);
 float mdo_dihedral_pos(const float p[4][3], const mdo_unitcell_t* cell);
 
+/* XTC frame decode as the reference's trajectory reader does it (md_xtc.c:747-931 with scale 10 nm -> Angstrom, :947-993): coordinates,
+ * unit cell (md_unitcell_from_matrix_float), step and time of ONE frame starting at `frame`. Returns 1 on success.
+ * mdo_xtc_frame_offsets scans a whole file image for the frame starts (md_xtc.c:436-570): offsets[0..n], returns n. */
+int mdo_xtc_decode_frame(const uint8_t* frame, size_t nbytes, size_t num_atoms, float* x, float* y, float* z,
+                         mdo_unitcell_t* cell, int32_t* step, float* time);
+size_t mdo_xtc_frame_offsets(const uint8_t* file, size_t nbytes, int64_t* offsets, size_t cap);
+
 /* building blocks exposed for unit tests */
 void mdo_svd3(const float A[3][3], float U[3][3], float S[3][3], float V[3][3]); /* ext/svd3/svd3.c */
 uint64_t mdo_count_pairs(const float* x, const float* y, const float* z, const int32_t* ref_idx, size_t n_ref,

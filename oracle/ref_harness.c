@@ -28,6 +28,8 @@
 #include <md_gro.h>
 #include <md_pdb.h>
 #include <md_util.h>
+#include <md_xtc.h>
+#include <xdrfile_xtc.h>
 #include <core/md_allocator.h>
 #include <core/md_arena_allocator.h>
 #include <core/md_str.h>
@@ -198,7 +200,33 @@ static int mode_dumptraj(int argc, char** argv) {
     return 0;
 }
 
+/* xtcwrite: frames [B,E) of any trajectory spec -> an .xtc file through the reference's bundled xdrfile writer (ext/xtc/xdrfile_xtc.c:
+ * write_xtc), coordinates Angstrom -> nm. Fixture generation for the XTC decode path. */
+static int mode_xtcwrite(int argc, char** argv) {
+    md_allocator_i* alloc = md_vm_arena_create(GIGABYTES(8));
+    md_system_t sys; if (!load_system(&sys, arg_val(argc, argv, "--sys", ""), alloc)) return 2;
+    md_trajectory_i traj = {0}; mem_traj_t mt;
+    if (!make_traj(&traj, &mt, arg_val(argc, argv, "--traj", "sys"), &sys)) return 2;
+    long b = 0, e = (long)md_trajectory_num_frames(&traj); parse_range(arg_val(argc, argv, "--frames", NULL), &b, &e);
+    const float prec = (float)atof(arg_val(argc, argv, "--precision", "1000"));
+    const size_t n = sys.atom.count;
+    XDRFILE* xd = xdrfile_open(arg_val(argc, argv, "--out", "traj.xtc"), "w"); if (!xd) return 2;
+    float* xyz = malloc(n * 12); rvec* r = malloc(n * sizeof(rvec));
+    md_trajectory_reader_i rd = {0}; md_trajectory_reader_init(&rd, &traj);
+    for (long fr = b; fr < e; ++fr) {
+        md_trajectory_frame_header_t h = {0};
+        if (!md_trajectory_reader_load_frame(rd, fr, &h, xyz, xyz + n, xyz + 2 * n)) return 2;
+        for (size_t i = 0; i < n; ++i) { r[i][0] = xyz[i] * 0.1f; r[i][1] = xyz[n + i] * 0.1f; r[i][2] = xyz[2 * n + i] * 0.1f; }
+        matrix box = { { (float)(h.unitcell.x * 0.1), 0, 0 }, { (float)(h.unitcell.xy * 0.1), (float)(h.unitcell.y * 0.1), 0 },
+                       { (float)(h.unitcell.xz * 0.1), (float)(h.unitcell.yz * 0.1), (float)(h.unitcell.z * 0.1) } };
+        if (write_xtc(xd, (int)n, (int)fr, (float)fr, box, r, prec) != exdrOK) return 2;
+    }
+    md_trajectory_reader_free(&rd); xdrfile_close(xd);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && strcmp(argv[1], "xtcwrite") == 0) return mode_xtcwrite(argc, argv);
     if (argc < 2) { fprintf(stderr, "usage: ref_harness sysinfo|eval|time|dumptraj ...\n"); return 1; }
     if (strcmp(argv[1], "dumptraj") == 0) return mode_dumptraj(argc, argv);
     if (strcmp(argv[1], "sysinfo") == 0) return mode_sysinfo(argc, argv);

@@ -15,6 +15,7 @@ reference's outputs, so the tests need neither the reference nor the harness on 
   membrane6.npz : synthetic coarse-grained membrane (BASELINE config 4 shape at 1728 atoms: 72 lipids x 12 beads + 864 solvent beads,
                cell 48 x 48 x 75), 4 frames: rt = rdf(name('C2*'), name('C2*'), 12.0), dz = density_z(name('C2*')), dall/dxall = density over all atoms
   tric6.npz  : water n=6 sheared into a TRICLINIC cell that changes every frame, 4 frames: rt, rth (min:max), rtc (centre-of-mass references)
+  xtc_cases.npz : XTC byte streams from the reference's writer + the reference reader's decode of them (see xtc_cases below)
   ala50.npz  : first 50 frames of datasets/1ALA-500.pdb (153 atoms, ortho cell 46.645 x 96.666 x 48.362), config 1:
                d = distance(1,10) (BASELINE config 1), rc = rdf(element('C'), element('O'), 10.0), dz = density_z(element('C')),
                a = angle(1,5,9), t = dihedral(5,7,9,15), rr = rdf(residue(1:3), element('H'), 8.0) (COM references, groups of different sizes)
@@ -143,9 +144,55 @@ def tric6(tmp):
     np.savez_compressed(os.path.join(HERE, "tric6.npz"), **out)
 
 
+def _write_gro(path, n, L):
+    with open(path, "w") as f:
+        f.write("synthetic\n%d\n" % n)
+        for i in range(n):
+            f.write("%5d%-5s%5s%5d%8.3f%8.3f%8.3f\n" % (i + 1, "ARG", "AR", i + 1, 0.1 * (i % 7), 0.1 * (i % 5), 0.1 * (i % 3)))
+        f.write("%10.5f%10.5f%10.5f\n" % (L, L, L))
+
+
+def xtc_cases(tmp):
+    """XTC frames written by the reference's bundled xdrfile writer and decoded by the reference's md_xtc reader:
+      water6    4 frames of the water6 trajectory (the common path: packed big + small integers, runs)
+      tric6     4 frames with a triclinic cell that changes every frame (unit cell from the box matrix)
+      water16   2 frames, 12 288 atoms (sha256 of the decoded arrays only)
+      small5    5 atoms: stored uncompressed (natoms <= 9)
+      wide12    12 atoms spread over ~5000 nm per axis: packed field wider than 64 bits
+      huge12    12 atoms spread over ~20000 nm: per-axis integers (sizeint > 0xffffff branch)
+      lowprec   water6 at precision 100 (different small-integer table positions)"""
+    import hashlib
+    out = {}
+
+    def case(name, gro, raw, extra=(), hash_only=False):
+        xtc = os.path.join(tmp, name + ".xtc"); dec = os.path.join(tmp, name + ".dec")
+        run(HARNESS, "xtcwrite", "--sys", gro, "--traj", f"raw:{raw}", "--out", xtc, *extra)
+        run(HARNESS, "dumptraj", "--sys", gro, "--traj", f"xtc:{xtc}", "--out", dec)
+        fr, cells, flags = refio.read_raw_traj(dec)
+        out[name + "__xtc"] = np.fromfile(xtc, np.uint8); out[name + "__cells"] = cells; out[name + "__flags"] = flags
+        out[name + "__na"] = np.int32(fr.shape[2])
+        if hash_only: out[name + "__sha"] = np.array([hashlib.sha256(np.ascontiguousarray(f).tobytes()).hexdigest() for f in fr])
+        else: out[name + "__frames"] = fr
+
+    gro, raw = os.path.join(tmp, "xw.gro"), os.path.join(tmp, "xw.raw")
+    run(SYNTH, "water-gro", "6", "77", gro); run(SYNTH, "water-raw", "6", "77", "4", raw)
+    case("water6", gro, raw); case("lowprec", gro, raw, ("--precision", "100"))
+    g = np.load(os.path.join(HERE, "tric6.npz")); traw = os.path.join(tmp, "xt.raw")
+    refio.write_raw_traj(traw, g["frames"], g["cells"], g["cell_flags"]); case("tric6", gro, traw)
+    gro16, raw16 = os.path.join(tmp, "x16.gro"), os.path.join(tmp, "x16.raw")
+    run(SYNTH, "water-gro", "16", "5", gro16); run(SYNTH, "water-raw", "16", "5", "2", raw16); case("water16", gro16, raw16, hash_only=True)
+    rng = np.random.default_rng(99)
+    for name, n, span in (("small5", 5, 30.0), ("wide12", 12, 5.0e4), ("huge12", 12, 2.0e5)):
+        g2, r2 = os.path.join(tmp, name + ".gro"), os.path.join(tmp, name + ".raw"); _write_gro(g2, n, 3.0)
+        fr = (rng.random((3, 3, n)) * span - span / 2).astype(np.float32)
+        refio.write_raw_traj(r2, fr, np.tile([30.0, 0, 0, 30.0, 0, 30.0], (3, 1)), np.full(3, 29, np.uint32)); case(name, g2, r2)
+        out[name + "__orig"] = fr   # what was written: the reference reader mis-decodes wide12 / huge12, the format's truth is the input
+    np.savez_compressed(os.path.join(HERE, "xtc_cases.npz"), **out)
+
+
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     with tempfile.TemporaryDirectory() as tmp:
-        water6(tmp); ala50(tmp); membrane6(tmp); tric6(tmp)
-    for f in ("water6.npz", "ala50.npz", "membrane6.npz", "tric6.npz"):
+        water6(tmp); ala50(tmp); membrane6(tmp); tric6(tmp); xtc_cases(tmp)
+    for f in ("water6.npz", "ala50.npz", "membrane6.npz", "tric6.npz", "xtc_cases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

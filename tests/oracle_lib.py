@@ -161,3 +161,18 @@ def angle_args(x, y, z, mass, a, b, c, cell):
 def dihedral_args(x, y, z, mass, a, b, c, d, cell):
     p = np.ascontiguousarray(np.stack([arg_position(x, y, z, mass, k, cell) for k in (a, b, c, d)]), np.float32)
     return np.float32(lib().mdo_dihedral_pos(_p(p, C.c_float), C.byref(cell)))
+
+
+def xtc_frame_offsets(blob):
+    blob = np.ascontiguousarray(blob, np.uint8); offs = np.zeros(4096, np.int64)
+    lib().mdo_xtc_frame_offsets.restype = C.c_size_t
+    n = lib().mdo_xtc_frame_offsets(_p(blob, C.c_uint8), C.c_size_t(blob.size), _p(offs, C.c_int64), C.c_size_t(offs.size))
+    return offs[:n + 1].copy()
+
+
+def xtc_decode_frame(blob, beg, end, num_atoms):
+    """-> (ok, xyz [3, n], UnitCell, step, time)"""
+    blob = np.ascontiguousarray(blob, np.uint8); xyz = np.zeros((3, num_atoms), np.float32); cell = UnitCell(); st = C.c_int32(); tm = C.c_float()
+    ok = lib().mdo_xtc_decode_frame(C.c_void_p(blob.ctypes.data + int(beg)), C.c_size_t(int(end - beg)), C.c_size_t(num_atoms),
+                                    C.c_void_p(xyz[0].ctypes.data), C.c_void_p(xyz[1].ctypes.data), C.c_void_p(xyz[2].ctypes.data), C.byref(cell), C.byref(st), C.byref(tm))
+    return bool(ok), xyz, cell, int(st.value), float(tm.value)
