@@ -163,6 +163,17 @@ int mdgpu_plan_set_initial_frame(mdgpu_plan* plan, const float* x, const float* 
 /* md_script_eval_clear_data (md_script.c:6563): zero accumulators, frame mask, interrupt flag. */
 int mdgpu_plan_clear(mdgpu_plan* plan);
 
+/* XTC input (reference: md_xtc.c:747-931 decode, :947-993 reader, :436-570 frame offsets): `h_blob` holds
+ * whole XTC frames as they are in the file, frame i spanning bytes [frame_offsets[i], frame_offsets[i+1]) (offsets are multiples of 4, as
+ * XDR guarantees). The compressed bytes cross PCIe and are expanded on the device with the reader's arithmetic (coordinates in
+ * Angstrom = int * (10 / precision), unit cell from the box matrix * 10); results are those of evaluating the decoded frames. */
+int mdgpu_eval_xtc_frames(mdgpu_plan* plan, const uint8_t* h_blob, const uint64_t* frame_offsets, uint32_t frame_beg, uint32_t count);
+/* Frame starts of an XTC file image: offsets[0..n] (offsets[n] = end of the last complete frame), n and the atom count returned. */
+int mdgpu_xtc_frame_offsets(const uint8_t* file, size_t nbytes, uint64_t* offsets, size_t capacity, size_t* num_frames, size_t* num_atoms);
+/* The same decode without a plan: h_xyz[count][3][num_atoms], optional cells / steps / times per frame. */
+int mdgpu_xtc_decode_frames(int device, const uint8_t* h_blob, const uint64_t* frame_offsets, uint32_t count, size_t num_atoms,
+                            float* h_xyz, mdgpu_unitcell_t* h_cells, int32_t* h_steps, float* h_times);
+
 /* The frame loop. Frames [frame_beg, frame_beg+count) are evaluated and accumulated.
  *  _device: coordinates already in HBM; frame i has x at d_xyz + i*frame_stride, y at + axis_stride, z at + 2*axis_stride (floats).
  *  _host  : same layout in host memory (pinned or pageable); copied host->device batch by batch inside the call.

@@ -396,6 +396,12 @@ class Plan:
         carr, cstride = self._cells_arg(cells, count)
         _check(lib().mdgpu_eval_device_frames(self._h, d_ptr, frame_stride, axis_stride, C.addressof(carr), cstride, frame_beg, count))
 
+    def eval_xtc_frames(self, blob: np.ndarray, offsets: np.ndarray, frame_beg: int = 0):
+        """XTC frames (bytes as in the file + frame offsets): compressed bytes go to the device and are expanded there"""
+        blob = np.ascontiguousarray(blob, np.uint8); offsets = np.ascontiguousarray(offsets, np.uint64)
+        lib().mdgpu_eval_xtc_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        _check(lib().mdgpu_eval_xtc_frames(self._h, blob.ctypes.data, offsets.ctypes.data, frame_beg, len(offsets) - 1))
+
     def eval_frame_range(self, traj: Trajectory, frame_beg: int, frame_end: int, loader_threads: int = 1) -> bool:
         """md_script_eval_frame_range(eval, ir, sys, traj, beg, end) (md_script.c:6573): returns False on failure."""
         t = traj._as_c()
@@ -546,6 +552,24 @@ def membrane_system(nl: int, nw_xy: int, nwz: int, mass_lipid: float = 72.0, mas
     res_off = np.concatenate([np.arange(nlip, dtype=np.int64) * LIPID_BEADS, nlip * LIPID_BEADS + np.arange(nw + 1, dtype=np.int64)])
     mass = np.concatenate([np.full(nlip * LIPID_BEADS, mass_lipid, np.float32), np.full(nw, mass_water, np.float32)])
     return System(na, mass, None, None, element=["X"] * na, name=names, resname=["LIP"] * nlip + ["SOLW"] * nw, res_atom_offset=res_off)
+
+
+def xtc_frame_offsets(blob: np.ndarray):
+    """frame byte offsets [n+1] and the atom count of an XTC file image (md_xtc.c:436-570)"""
+    blob = np.ascontiguousarray(blob, np.uint8); cap = max(2, blob.size // 56 + 2)
+    offs = np.zeros(cap, np.uint64); n = C.c_size_t(); na = C.c_size_t()
+    lib().mdgpu_xtc_frame_offsets.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    _check(lib().mdgpu_xtc_frame_offsets(blob.ctypes.data, blob.size, offs.ctypes.data, cap, C.byref(n), C.byref(na)))
+    return offs[:n.value + 1].copy(), int(na.value)
+
+
+def xtc_decode_frames(blob: np.ndarray, offsets: np.ndarray, num_atoms: int, device: int = 0):
+    """device decode of XTC frames -> (xyz [F,3,N] float32 in Angstrom, cells [F], steps [F], times [F])"""
+    blob = np.ascontiguousarray(blob, np.uint8); offsets = np.ascontiguousarray(offsets, np.uint64); F = len(offsets) - 1
+    xyz = np.zeros((F, 3, num_atoms), np.float32); cells = (UnitCell * F)(); steps = np.zeros(F, np.int32); times = np.zeros(F, np.float32)
+    lib().mdgpu_xtc_decode_frames.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(lib().mdgpu_xtc_decode_frames(device, blob.ctypes.data, offsets.ctypes.data, F, num_atoms, xyz.ctypes.data, C.addressof(cells), steps.ctypes.data, times.ctypes.data))
+    return xyz, list(cells), steps, times
 
 
 def debug_sqrt_sweep(lo_bits: int, hi_bits: int, device: int = 0) -> int:

@@ -77,6 +77,15 @@ void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, cons
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned long long n, cudaStream_t s);
 
+// xtc.cu — compressed trajectory frames expanded on the device
+struct XtcFrameInfo {   // written by k_xtc_scan, one per frame
+    int status;                 // 0 ok, otherwise the frame is malformed
+    uint32_t ngroups, data_off; // groups found by the scan; byte offset of the bit stream inside the frame
+    uint32_t bitsize, bitsizeint[3], sizeint[3]; int minint[3]; float precision;
+};
+void launch_xtc_decode(const uint8_t* d_blob, const unsigned long long* d_frame_off, uint32_t num_atoms, int B, XtcFrameInfo* d_info,
+                       uint2* d_rec, uint16_t* d_rec_state, size_t rec_stride, float* d_out, size_t frame_stride, size_t axis_stride, int* d_err, cudaStream_t s);
+
 // synth.cu
 void launch_synth_frames(uint32_t seed, float Lx, float Ly, float Lz, uint32_t num_atoms, const float* d_base, size_t base_axis_stride,
                          const uint32_t* d_mol_id, uint32_t frame_beg, uint32_t count, float* d_out, size_t frame_stride, size_t axis_stride, cudaStream_t s);

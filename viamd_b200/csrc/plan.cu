@@ -83,6 +83,9 @@ struct Slot {
     float* d_frames = nullptr; float* h_frames = nullptr;      // staging for host-resident frames
     mdgpu_unitcell_t* d_cells = nullptr; mdgpu_unitcell_t* h_cells = nullptr;
     int* d_err = nullptr;
+    // XTC input: compressed bytes of the batch + per-frame offsets, scan records
+    uint8_t* d_xtc = nullptr; size_t xtc_cap = 0; unsigned long long* d_xtc_off = nullptr; unsigned long long* h_xtc_off = nullptr;
+    XtcFrameInfo* d_xtc_info = nullptr; uint2* d_xtc_rec = nullptr; uint16_t* d_xtc_state = nullptr;
     std::vector<PropScratch> ps;
     uint32_t pending_beg = 0, pending_cnt = 0;
 };
@@ -158,6 +161,7 @@ static void destroy_plan(mdgpu_plan* p) {
         }
         cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
+        cudaFree(s.d_xtc); cudaFree(s.d_xtc_off); if (s.h_xtc_off) cudaFreeHost(s.h_xtc_off); cudaFree(s.d_xtc_info); cudaFree(s.d_xtc_rec); cudaFree(s.d_xtc_state);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -572,6 +576,133 @@ int mdgpu_eval_host_frames(mdgpu_plan* p, const float* h_xyz, size_t frame_strid
     return 0;
 }
 
+// ---- XTC input ---------------------------------------------------------------------------------------------------------------
+static uint32_t xtc_be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+static float xtc_bef32(const uint8_t* p) { const uint32_t u = xtc_be32(p); float f; memcpy(&f, &u, 4); return f; }
+
+// frame header -> unit cell as xtc_reader_load_frame builds it: box * 10 in float (md_xtc.c:765-768), md_unitcell_from_matrix_float
+// (md_unitcell.inl:109) -> md_unitcell_from_basis_parameters (:12-31)
+static bool xtc_header_cell(const uint8_t* fr, size_t nbytes, mdgpu_unitcell_t* cell, int32_t* step, float* time) {
+    if (nbytes < 56 || xtc_be32(fr) != 1995u) return false;
+    float box[9]; for (int i = 0; i < 9; ++i) box[i] = xtc_bef32(fr + 16 + 4 * i) * 10.0f;
+    const double cx = box[0], cy = box[4], cz = box[8], xy = box[3], xz = box[6], yz = box[7];
+    uint32_t flags = 0;
+    if (xy == 0.0 && xz == 0.0 && yz == 0.0) { if (!(cx == 0.0 && cy == 0.0 && cz == 0.0) && !(cx == 1.0 && cy == 1.0 && cz == 1.0)) flags |= MDGPU_CELL_ORTHO; }
+    else flags |= MDGPU_CELL_TRICLINIC;
+    if (flags) { if (cx != 0.0) flags |= MDGPU_CELL_PBC_X; if (cy != 0.0) flags |= MDGPU_CELL_PBC_Y; if (cz != 0.0) flags |= MDGPU_CELL_PBC_Z; }
+    cell->x = cx; cell->xy = xy; cell->xz = xz; cell->y = cy; cell->yz = yz; cell->z = cz; cell->flags = flags;
+    if (step) *step = (int32_t)xtc_be32(fr + 8);
+    if (time) *time = xtc_bef32(fr + 12);
+    return true;
+}
+
+static int ensure_xtc_buffers(mdgpu_plan* p, Slot& s, size_t need_bytes) {
+    if (!s.d_xtc_off) {
+        CUDA_TRY(dalloc(&s.d_xtc_off, (size_t)p->B + 1));
+        CUDA_TRY(cudaMallocHost((void**)&s.h_xtc_off, sizeof(unsigned long long) * ((size_t)p->B + 1)));
+        CUDA_TRY(dalloc(&s.d_xtc_info, p->B));
+        CUDA_TRY(dalloc(&s.d_xtc_rec, (size_t)p->B * p->num_atoms));
+        CUDA_TRY(dalloc(&s.d_xtc_state, (size_t)p->B * p->num_atoms));
+    }
+    if (need_bytes + 32 > s.xtc_cap) {
+        cudaFree(s.d_xtc); s.d_xtc = nullptr; s.xtc_cap = 0;
+        const size_t cap = std::max(need_bytes + 32, (size_t)p->B * (p->num_atoms * 6 + 128)) + 4096;
+        CUDA_TRY(cudaMalloc((void**)&s.d_xtc, cap)); s.xtc_cap = cap;
+    }
+    return 0;
+}
+
+int mdgpu_eval_xtc_frames(mdgpu_plan* p, const uint8_t* h_blob, const uint64_t* frame_offsets, uint32_t frame_beg, uint32_t count) {
+    if (!p || !h_blob || !frame_offsets) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_eval_xtc_frames: null argument");
+    if ((size_t)frame_beg + count > p->num_frames) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Invalid frame range");
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (!count) return 0;
+    for (uint32_t i = 0; i < count; ++i) if (frame_offsets[i + 1] <= frame_offsets[i] || (frame_offsets[i] & 3u)) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Invalid frame offset range");
+    mdgpu_unitcell_t first{};
+    if (!xtc_header_cell(h_blob + frame_offsets[0], frame_offsets[1] - frame_offsets[0], &first, nullptr, nullptr)) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Magic number did not match");
+    int rc = ensure_slots(p, &first, true); if (rc) return rc;
+    const size_t AS = p->axis_stride;
+    for (uint32_t b0 = 0; b0 < count; b0 += p->B) {
+        if (p->interrupt.load()) return fail(MDGPU_ERR_INTERRUPTED, "evaluation interrupted");
+        const uint32_t nb = std::min(p->B, count - b0);
+        Slot& s = p->slots[p->next_slot++ % p->slots.size()];
+        rc = retire_slot(p, s); if (rc) return rc;
+        const uint64_t beg = frame_offsets[b0], end = frame_offsets[b0 + nb];
+        rc = ensure_xtc_buffers(p, s, (size_t)(end - beg)); if (rc) return rc;
+        for (uint32_t i = 0; i < nb; ++i) {
+            const uint8_t* fr = h_blob + frame_offsets[b0 + i];
+            if (!xtc_header_cell(fr, (size_t)(frame_offsets[b0 + i + 1] - frame_offsets[b0 + i]), &s.h_cells[i], nullptr, nullptr)) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Magic number did not match");
+            s.h_xtc_off[i] = frame_offsets[b0 + i] - beg;
+        }
+        s.h_xtc_off[nb] = end - beg;
+        CUDA_TRY(cudaMemcpyAsync(s.d_xtc, h_blob + beg, (size_t)(end - beg), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemsetAsync(s.d_xtc + (end - beg), 0, 32, s.stream));   // guard bytes for the word-wise bit reader
+        CUDA_TRY(cudaMemcpyAsync(s.d_xtc_off, s.h_xtc_off, sizeof(unsigned long long) * (nb + 1), cudaMemcpyHostToDevice, s.stream));
+        launch_xtc_decode(s.d_xtc, s.d_xtc_off, (uint32_t)p->num_atoms, (int)nb, s.d_xtc_info, s.d_xtc_rec, s.d_xtc_state, p->num_atoms,
+                          s.d_frames, 3 * AS, AS, s.d_err, s.stream);
+        BatchFrames fr{ s.d_frames, 3 * AS, AS, nb };
+        rc = enqueue_batch(p, s, fr, frame_beg + b0); if (rc) return rc;
+    }
+    return 0;
+}
+
+// frame starts of an XTC file image (md_xtc_read_frame_offsets_and_times md_xtc.c:436-570): offsets[0..n], offsets[n] = end of the last frame
+int mdgpu_xtc_frame_offsets(const uint8_t* file, size_t nbytes, uint64_t* offsets, size_t capacity, size_t* num_frames, size_t* num_atoms) {
+    if (!file || !offsets || capacity < 2) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_xtc_frame_offsets: invalid argument");
+    if (nbytes < 56 || xtc_be32(file) != 1995u) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: File does not appear to be a valid xtc trajectory");
+    const int32_t natoms = (int32_t)xtc_be32(file + 4);
+    if (natoms <= 0) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Invalid number of atoms in header");
+    size_t n = 0, pos = 0;
+    if (natoms <= 9) {
+        const size_t fb = 56 + 12u * (size_t)natoms;
+        while (pos + fb <= nbytes && n + 1 < capacity && xtc_be32(file + pos) == 1995u) { offsets[n++] = pos; pos += fb; }
+    } else {
+        while (pos != nbytes && n + 1 < capacity) {
+            if (pos + 92 > nbytes || xtc_be32(file + pos) != 1995u) break;                 // "encountered corrupted frame header": keep what was found
+            const size_t fb = ((size_t)xtc_be32(file + pos + 88) + 3u) & ~(size_t)3;        // rounding to the next 32-bit boundary
+            if (pos + 92 + fb > nbytes) break;
+            offsets[n++] = pos; pos += 92 + fb;
+        }
+    }
+    offsets[n] = pos;
+    if (num_frames) *num_frames = n; if (num_atoms) *num_atoms = (size_t)natoms;
+    return 0;
+}
+
+// stand-alone decode (tests, tools): frames -> host arrays [count][3][num_atoms], cells, steps, times
+int mdgpu_xtc_decode_frames(int device, const uint8_t* h_blob, const uint64_t* frame_offsets, uint32_t count, size_t num_atoms,
+                            float* h_xyz, mdgpu_unitcell_t* h_cells, int32_t* h_steps, float* h_times) {
+    if (!h_blob || !frame_offsets || !h_xyz) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_xtc_decode_frames: null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    if (!count) return 0;
+    const uint64_t beg = frame_offsets[0], end = frame_offsets[count];
+    std::vector<unsigned long long> off(count + 1);
+    for (uint32_t i = 0; i <= count; ++i) { if ((frame_offsets[i] & 3u) || (i && frame_offsets[i] <= frame_offsets[i - 1])) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Invalid frame offset range"); off[i] = frame_offsets[i] - beg; }
+    for (uint32_t i = 0; i < count; ++i) {
+        mdgpu_unitcell_t c{}; int32_t st = 0; float tm = 0;
+        if (!xtc_header_cell(h_blob + frame_offsets[i], (size_t)(frame_offsets[i + 1] - frame_offsets[i]), &c, &st, &tm)) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Magic number did not match");
+        if (h_cells) h_cells[i] = c; if (h_steps) h_steps[i] = st; if (h_times) h_times[i] = tm;
+    }
+    uint8_t* d_blob = nullptr; unsigned long long* d_off = nullptr; XtcFrameInfo* d_info = nullptr; uint2* d_rec = nullptr; uint16_t* d_state = nullptr; float* d_out = nullptr; int* d_err = nullptr;
+    auto cleanup = [&]() { cudaFree(d_blob); cudaFree(d_off); cudaFree(d_info); cudaFree(d_rec); cudaFree(d_state); cudaFree(d_out); cudaFree(d_err); };
+    int rc = 0;
+    do {
+        if (cudaMalloc((void**)&d_blob, (size_t)(end - beg) + 32) != cudaSuccess || dalloc(&d_off, (size_t)count + 1) != cudaSuccess || dalloc(&d_info, count) != cudaSuccess ||
+            dalloc(&d_rec, (size_t)count * num_atoms) != cudaSuccess || dalloc(&d_state, (size_t)count * num_atoms) != cudaSuccess ||
+            dalloc(&d_out, (size_t)count * 3 * num_atoms) != cudaSuccess || dalloc(&d_err, 1) != cudaSuccess) { rc = fail(MDGPU_ERR_CUDA, "device allocation failed (xtc decode)"); break; }
+        cudaMemset(d_err, 0, sizeof(int)); cudaMemset(d_blob + (end - beg), 0, 32);
+        cudaMemcpy(d_blob, h_blob + beg, (size_t)(end - beg), cudaMemcpyHostToDevice);
+        cudaMemcpy(d_off, off.data(), sizeof(unsigned long long) * (count + 1), cudaMemcpyHostToDevice);
+        launch_xtc_decode(d_blob, d_off, (uint32_t)num_atoms, (int)count, d_info, d_rec, d_state, num_atoms, d_out, 3 * num_atoms, num_atoms, d_err, 0);
+        int err = 0;
+        if (cudaMemcpy(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail(MDGPU_ERR_CUDA, "xtc decode failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        if (err) { rc = fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Failed to decode frame data"); break; }
+        if (cudaMemcpy(h_xyz, d_out, sizeof(float) * (size_t)count * 3 * num_atoms, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail(MDGPU_ERR_CUDA, "xtc decode copy failed"); break; }
+    } while (false);
+    cleanup();
+    return rc;
+}
+
 int mdgpu_eval_trajectory(mdgpu_plan* p, const mdgpu_trajectory_i* traj, uint32_t frame_beg, uint32_t frame_end, uint32_t loader_threads) {
     if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
     if (!traj || !traj->inst || !traj->get_header || !traj->init_reader) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Trajectory was null");
@@ -633,7 +764,7 @@ int mdgpu_plan_sync(mdgpu_plan* p) {
     CUDA_TRY(cudaDeviceSynchronize());
     for (auto& s : p->slots) {
         int err = 0; CUDA_TRY(cudaMemcpy(&err, s.d_err, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) { cudaMemset(s.d_err, 0, sizeof(int)); return fail(err, err == MDGPU_ERR_CAPACITY ? "a frame needs more cells than the plan's cell capacity (%u); raise mdgpu_plan_options_t.cell_capacity" : "device-side error %d", err == MDGPU_ERR_CAPACITY ? p->cell_cap : (uint32_t)err); }
+        if (err) { cudaMemset(s.d_err, 0, sizeof(int)); return fail(err, err == MDGPU_ERR_CAPACITY ? "a frame needs more cells than the plan's cell capacity (%u); raise mdgpu_plan_options_t.cell_capacity" : (err == MDGPU_ERR_FRAME_SOURCE ? "XTC: Failed to decode frame data (%d)" : "device-side error %d"), err == MDGPU_ERR_CAPACITY ? p->cell_cap : (uint32_t)err); }
     }
     for (auto& t : p->timed) { float ms = 0; if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { p->timed_ms[t.kind] += ms; p->timed_n[t.kind] += 1; } cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     p->timed.clear();
