@@ -402,6 +402,12 @@ class Plan:
         lib().mdgpu_eval_xtc_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         _check(lib().mdgpu_eval_xtc_frames(self._h, blob.ctypes.data, offsets.ctypes.data, frame_beg, len(offsets) - 1))
 
+    def eval_xtc_ptr(self, blob_ptr: int, offsets: np.ndarray, frame_beg: int = 0):
+        """as eval_xtc_frames, the bytes given as a raw host pointer (e.g. pinned memory)"""
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        lib().mdgpu_eval_xtc_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        _check(lib().mdgpu_eval_xtc_frames(self._h, blob_ptr, offsets.ctypes.data, frame_beg, len(offsets) - 1))
+
     def eval_frame_range(self, traj: Trajectory, frame_beg: int, frame_end: int, loader_threads: int = 1) -> bool:
         """md_script_eval_frame_range(eval, ir, sys, traj, beg, end) (md_script.c:6573): returns False on failure."""
         t = traj._as_c()

@@ -82,6 +82,7 @@ struct XtcFrameInfo {   // written by k_xtc_scan, one per frame
     int status;                 // 0 ok, otherwise the frame is malformed
     uint32_t ngroups, data_off; // groups found by the scan; byte offset of the bit stream inside the frame
     uint32_t bitsize, bitsizeint[3], sizeint[3]; int minint[3]; float precision;
+    uint32_t rounds, restages;  // scan statistics (diagnostics)
 };
 void launch_xtc_decode(const uint8_t* d_blob, const unsigned long long* d_frame_off, uint32_t num_atoms, int B, XtcFrameInfo* d_info,
                        uint2* d_rec, uint16_t* d_rec_state, size_t rec_stride, float* d_out, size_t frame_stride, size_t axis_stride, int* d_err, cudaStream_t s);
