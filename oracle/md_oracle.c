@@ -470,12 +470,34 @@ static inline float deperiodize1(float x, float r, float ext) {
  */
 typedef float v4[4];
 
+/* minimum_image_triclinic md_util.c:1677-1718: the 27 images, double comparison; note the mixed precision of the sums as written
+ * there (float products, some float sums) */
+static void min_image_triclinic(float dx[3], const float box[3][3]) {
+    double dx_min[3] = { 0.0, 0.0, 0.0 }, dsq_min = FLT_MAX;
+    for (int ix = -1; ix < 2; ++ix) {
+        const double rx = (float)(dx[0] + box[0][0] * ix);
+        for (int iy = -1; iy < 2; ++iy) {
+            const double ry0 = rx + (float)(box[1][0] * iy);
+            const double ry1 = (float)(dx[1] + box[1][1] * iy);
+            for (int iz = -1; iz < 2; ++iz) {
+                const double rz0 = ry0 + (float)(box[2][0] * iz), rz1 = ry1 + (float)(box[2][1] * iz), rz2 = (float)(dx[2] + box[2][2] * iz);
+                const double dsq = rz0 * rz0 + rz1 * rz1 + rz2 * rz2;
+                if (dsq < dsq_min) { dsq_min = dsq; dx_min[0] = rz0; dx_min[1] = rz1; dx_min[2] = rz2; }
+            }
+        }
+    }
+    dx[0] = (float)dx_min[0]; dx[1] = (float)dx_min[1]; dx[2] = (float)dx_min[2];
+}
+
 /* unwrap_topology_vec4 with indices == NULL (md_util.c:8738-8819): NB the BFS runs over the bonds of GLOBAL atoms
- * 0..count-1 (seed = local index used as a global atom index) — replicated as is. Ortho only. */
+ * 0..count-1 (seed = local index used as a global atom index) — replicated as is. Ortho: unwrap_atom_ortho_vec4; triclinic:
+ * deperiodize_triclinic :1754-1766 with the float basis (md_unitcell_A_extract_float). */
 static void unwrap_vec4(v4* xyzw, size_t count, const uint32_t* conn_off, const int32_t* conn_idx, size_t conn_off_count, const mdo_unitcell_t* cell) {
     if (count == 0 || !conn_off || conn_off_count == 0) return;
-    if (!(cell->flags & MDO_CELL_ORTHO)) return;   /* triclinic: deperiodize_triclinic, not restated yet */
+    const int ortho = (cell->flags & MDO_CELL_ORTHO) != 0, tri = (cell->flags & MDO_CELL_TRICLINIC) != 0;
+    if (!ortho && !tri) return;
     const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
+    const float box[3][3] = { { (float)cell->x, 0, 0 }, { (float)cell->xy, (float)cell->y, 0 }, { (float)cell->xz, (float)cell->yz, (float)cell->z } };
     const size_t atom_count = conn_off_count - 1;
     unsigned char* visited = calloc(atom_count + 1, 1);
     int* queue = malloc(sizeof(int) * (count + 1));
@@ -490,7 +512,12 @@ static void unwrap_vec4(v4* xyzw, size_t count, const uint32_t* conn_off, const 
                 const int next = conn_idx[k];
                 if ((size_t)next >= count) continue;
                 if (visited[next]) continue;
-                for (int a = 0; a < 3; ++a) xyzw[next][a] = deperiodize1(xyzw[next][a], xyzw[cur][a], ext[a]);
+                if (ortho) { for (int a = 0; a < 3; ++a) xyzw[next][a] = deperiodize1(xyzw[next][a], xyzw[cur][a], ext[a]); }
+                else {
+                    float d[3] = { xyzw[next][0] - xyzw[cur][0], xyzw[next][1] - xyzw[cur][1], xyzw[next][2] - xyzw[cur][2] };
+                    min_image_triclinic(d, box);
+                    for (int a = 0; a < 3; ++a) xyzw[next][a] = xyzw[cur][a] + d[a];
+                }
                 visited[next] = 1; queue[qt++] = next;
             }
         }
@@ -597,6 +624,63 @@ static void acc_points_in_aabb_ortho(const acc_t* acc, const double cen[3], cons
     } } }
 }
 
+/* for_each_point_in_aabb_triclinic (core/md_spatial_acc.c:2009-2150): same cell range, the box test in CARTESIAN coordinates of the
+ * image-shifted point (fract_to_cart_tri_256 :594-603), all axes periodic */
+static void acc_points_in_aabb_triclinic(const acc_t* acc, const double cen[3], const double rad[3], point_cb_t cb, void* user) {
+    if (acc->num_elems == 0) return;
+    const int cd[3] = { (int)acc->cell_dim[0], (int)acc->cell_dim[1], (int)acc->cell_dim[2] };
+    double sc[3], cc[3];
+    {
+        const double px = cen[0] - acc->origin[0], py = cen[1] - acc->origin[1], pz = cen[2] - acc->origin[2];
+        sc[0] = acc->I[0][0] * px + acc->I[1][0] * py + acc->I[2][0] * pz;
+        sc[1] = acc->I[0][1] * px + acc->I[1][1] * py + acc->I[2][1] * pz;
+        sc[2] = acc->I[0][2] * px + acc->I[1][2] * py + acc->I[2][2] * pz;
+    }
+    const int pbc[3] = { (acc->flags & MDO_CELL_PBC_X) != 0, (acc->flags & MDO_CELL_PBC_Y) != 0, (acc->flags & MDO_CELL_PBC_Z) != 0 };
+    for (int a = 0; a < 3; ++a) if (pbc[a]) sc[a] = sc[a] - floor(sc[a]);
+    cc[0] = acc->A[0][0] * sc[0] + acc->A[1][0] * sc[1] + acc->A[2][0] * sc[2] + acc->origin[0];
+    cc[1] = acc->A[0][1] * sc[0] + acc->A[1][1] * sc[1] + acc->A[2][1] * sc[2] + acc->origin[1];
+    cc[2] = acc->A[0][2] * sc[0] + acc->A[1][2] * sc[1] + acc->A[2][2] * sc[2] + acc->origin[2];
+    double fmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, fmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+    for (int iz = 0; iz < 2; ++iz) { const double pz = cc[2] + (iz ? +rad[2] : -rad[2]);
+    for (int iy = 0; iy < 2; ++iy) { const double py = cc[1] + (iy ? +rad[1] : -rad[1]);
+    for (int ix = 0; ix < 2; ++ix) { const double px = cc[0] + (ix ? +rad[0] : -rad[0]);
+        const double qx = px - acc->origin[0], qy = py - acc->origin[1], qz = pz - acc->origin[2];
+        double s[3];
+        s[0] = acc->I[0][0] * qx + acc->I[1][0] * qy + acc->I[2][0] * qz;
+        s[1] = acc->I[0][1] * qx + acc->I[1][1] * qy + acc->I[2][1] * qz;
+        s[2] = acc->I[0][2] * qx + acc->I[1][2] * qy + acc->I[2][2] * qz;
+        for (int a = 0; a < 3; ++a) { fmin[a] = MINV(fmin[a], s[a]); fmax[a] = MAXV(fmax[a], s[a]); }
+    } } }
+    int cmin[3], cmax[3];
+    for (int a = 0; a < 3; ++a) {
+        int lo = (int)floor(fmin[a] * (double)cd[a]), hi = (int)ceil(fmax[a] * (double)cd[a]);
+        if (hi <= lo) hi = lo + 1;
+        if (!pbc[a]) { lo = CLAMPV(lo, 0, cd[a]); hi = CLAMPV(hi, 0, cd[a]); if (hi <= lo) hi = MINV(lo + 1, cd[a]); }
+        cmin[a] = lo; cmax[a] = hi;
+    }
+    const float lo3[3] = { (float)(cc[0] - rad[0]), (float)(cc[1] - rad[1]), (float)(cc[2] - rad[2]) };   /* :2041-2047 */
+    const float hi3[3] = { (float)(cc[0] + rad[0]), (float)(cc[1] + rad[1]), (float)(cc[2] + rad[2]) };
+    const float A00 = acc->A[0][0], A10 = acc->A[1][0], A11 = acc->A[1][1], A20 = acc->A[2][0], A21 = acc->A[2][1], A22 = acc->A[2][2];
+    const float O0 = acc->origin[0], O1 = acc->origin[1], O2 = acc->origin[2];
+    const uint32_t c0 = acc->cell_dim[0], c01 = acc->cell_dim[0] * acc->cell_dim[1];
+    for (int icz = cmin[2]; icz < cmax[2]; ++icz) { const int cz = wrap_coord(icz, cd[2]); const float shz = (float)isign(icz - cz);
+    for (int icy = cmin[1]; icy < cmax[1]; ++icy) { const int cy = wrap_coord(icy, cd[1]); const float shy = (float)isign(icy - cy);
+    for (int icx = cmin[0]; icx < cmax[0]; ++icx) { const int cx = wrap_coord(icx, cd[0]); const float shx = (float)isign(icx - cx);
+        if (cx < 0 || cx >= cd[0] || cy < 0 || cy >= cd[1] || cz < 0 || cz >= cd[2]) continue;   /* single wrap only; the reference would index out of range */
+        const size_t ci = (size_t)cz * c01 + (size_t)cy * c0 + (size_t)cx;
+        const uint32_t o = acc->cell_off[ci], len = acc->cell_off[ci + 1] - o;
+        for (uint32_t j = 0; j < len; ++j) {
+            const float vx = acc->ex[o + j] + shx, vy = acc->ey[o + j] + shy, vz = acc->ez[o + j] + shz;
+            const float px = fmaf(vx, A00, fmaf(vy, A10, fmaf(vz, A20, O0))), py = fmaf(vy, A11, fmaf(vz, A21, O1)), pz = fmaf(vz, A22, O2);
+            if (px >= lo3[0] && py >= lo3[1] && pz >= lo3[2] && px <= hi3[0] && py <= hi3[1] && pz <= hi3[2])
+                cb(acc->eidx[o + j], vx, vy, vz, user);   /* REFERENCE QUIRK: the buffer holds the FRACTIONAL image-shifted coordinates (:2122-2130) and
+                                                            * POSSIBLY_INVOKE_CALLBACK_POINT_CART_TRI / FLUSH_TAIL_POINT_CART_TRI (:715-737) hand it to the callback without
+                                                            * the fract->cart conversion the ortho path does — the callback sees fractional numbers. Replicated. */
+        }
+    } } }
+}
+
 typedef struct sdf_payload_t { m4 M; float* vol; const int32_t* excl; size_t n_excl; uint64_t count; } sdf_payload_t;
 static void sdf_point(uint32_t idx, float px, float py, float pz, void* user) {   /* sdf_cb :5664-5697 */
     sdf_payload_t* p = user;
@@ -652,7 +736,7 @@ uint64_t mdo_sdf_frame(const float* x, const float* y, const float* z,
         if (out_matrices) memcpy(out_matrices + 16 * i, p.M.e, sizeof(float) * 16);
         const double cen[3] = { com1[0], com1[1], com1[2] }, rad[3] = { cutoff, cutoff, cutoff };
         if (vol) {
-            if (acc.flags & MDO_CELL_TRICLINIC) { /* for_each_point_in_aabb_triclinic: not restated yet */ }
+            if (acc.flags & MDO_CELL_TRICLINIC) acc_points_in_aabb_triclinic(&acc, cen, rad, sdf_point, &p);
             else acc_points_in_aabb_ortho(&acc, cen, rad, sdf_point, &p);
         }
         total += p.count;

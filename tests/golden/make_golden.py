@@ -135,7 +135,7 @@ def tric6(tmp):
         out_fr[f, 1] = (y + (yz / L) * z).astype(np.float32); out_fr[f, 2] = z.astype(np.float32)
         out_cells[f] = [L, xy, xz, L, yz, L]
     refio.write_raw_traj(raw, out_fr, out_cells, flags)
-    script = "rt = rdf(element('O'), element('O'), 6.0); rth = rdf(element('O'), element('H'), 2.0:7.0); rtc = rdf(residue(1:30), element('H'), 5.0);"
+    script = "rt = rdf(element('O'), element('O'), 6.0); rth = rdf(element('O'), element('H'), 2.0:7.0); rtc = rdf(residue(1:30), element('H'), 5.0); vt = sdf(residue(1:20), element('O'), 5.0);"
     o = os.path.join(tmp, "t.out"); si = os.path.join(tmp, "t.sys")
     run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
     run(HARNESS, "sysinfo", "--sys", gro, "--out", si)

@@ -95,7 +95,15 @@ def test_golden_triclinic_rdf_bitexact():
     g = load_golden("tric6.npz"); s = golden_system(g)
     plan, cells = _water_plan(g, s, str(g["script"]), batch_frames=3)
     F = g["frames"].shape[0]
+    total = np.zeros(128 ** 3, np.float64)
+    for f in range(F):   # sdf() in a triclinic cell, per-frame raw voxels (incl. the reference's fractional-coordinate callback quirk)
+        plan.clear(); plan.eval_host_frames(g["frames"][f:f + 1], [cells[f]], f)
+        ref = dense_from_sparse(g[f"vt__pf{f}_idx"], g[f"vt__pf{f}_val"]); got = plan.counts("vt")
+        assert int(got.sum()) == int(ref.sum()) > 0 and np.array_equal(got.astype(np.float32), ref), f"vt frame {f}"
+        total += ref
+    plan.clear()
     plan.eval_host_frames(g["frames"], cells, 0)
+    assert np.array_equal(plan.counts("vt").astype(np.float64), total)
     for key in ("rt", "rth", "rtc"):
         for f in range(F):
             bins, tot = plan.frame_counts(key, f)

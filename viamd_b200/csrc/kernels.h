@@ -55,7 +55,7 @@ struct SdfArgs {
     unsigned long long* frame_total; // [num_frames]
     uint32_t frame0;
 };
-void launch_sdf(const SdfArgs& a, int B, cudaStream_t s);
+void launch_sdf(const SdfArgs& a, int B, bool tri, cudaStream_t s);
 
 // props.cu
 struct DensityArgs {

@@ -453,7 +453,6 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             break; }
         case MDGPU_OP_SDF: {
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "sdf '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
-            if (tri) return fail(MDGPU_ERR_UNSUPPORTED, "sdf '%s': triclinic unit cells are not implemented yet", pr.name.c_str());
             SdfArgs a{};
             a.geom = cs.d_geom; a.trg = cs.trg; a.frames = fr; a.cells = s.d_cells;
             a.init_xyz = p->d_init; a.init_axis_stride = p->axis_stride; a.mass = p->d_mass;
@@ -463,7 +462,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.vol = pr.d_vol; a.frame_total = pr.d_frame_total; a.frame0 = frame0;
             TimedLaunch tl{};
             if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); cudaEventRecord(tl.a, s.stream); }
-            launch_sdf(a, B, s.stream);
+            launch_sdf(a, B, tri, s.stream);
             if (p->timing) { cudaEventRecord(tl.b, s.stream); tl.kind = 1; p->timed.push_back(tl); }
             break; }
         case MDGPU_OP_DENSITY_X: case MDGPU_OP_DENSITY_Y: case MDGPU_OP_DENSITY_Z: {

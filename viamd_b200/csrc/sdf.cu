@@ -172,6 +172,26 @@ MDG_D float deperiodize1(float x, float r, float ext) {
     return __fadd_rn(r, __fmul_rn(dxp, ext));
 }
 
+// minimum_image_triclinic md_util.c:1677-1718: the 27 images, squared length compared in double, first minimum in loop order wins.
+// The sums are mixed precision as written there: float products (box * int) and float sums where both operands are float.
+MDG_D void min_image_triclinic(float dx[3], const float box[3][3]) {
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, dsq_min = (double)3.402823466e+38f;
+    for (int ix = -1; ix < 2; ++ix) {
+        const double rx = (double)__fadd_rn(dx[0], __fmul_rn(box[0][0], (float)ix));
+        for (int iy = -1; iy < 2; ++iy) {
+            const double ry0 = __dadd_rn(rx, (double)__fmul_rn(box[1][0], (float)iy));
+            const double ry1 = (double)__fadd_rn(dx[1], __fmul_rn(box[1][1], (float)iy));
+            for (int iz = -1; iz < 2; ++iz) {
+                const double rz0 = __dadd_rn(ry0, (double)__fmul_rn(box[2][0], (float)iz)), rz1 = __dadd_rn(ry1, (double)__fmul_rn(box[2][1], (float)iz));
+                const double rz2 = (double)__fadd_rn(dx[2], __fmul_rn(box[2][2], (float)iz));
+                const double dsq = __dadd_rn(__dadd_rn(__dmul_rn(rz0, rz0), __dmul_rn(rz1, rz1)), __dmul_rn(rz2, rz2));
+                if (dsq < dsq_min) { dsq_min = dsq; m0 = rz0; m1 = rz1; m2 = rz2; }
+            }
+        }
+    }
+    dx[0] = (float)m0; dx[1] = (float)m1; dx[2] = (float)m2;
+}
+
 // extract + unwrap + centre of mass of one structure into scratch (xyz, mass)
 MDG_D void load_unwrap_com(float4* p, const float* x, const float* y, const float* z, const float* mass, const int32_t* sidx, uint32_t n,
                            const int2* pairs, uint32_t n_pairs, const mdgpu_unitcell_t& uc, float com[3]) {
@@ -182,6 +202,16 @@ MDG_D void load_unwrap_com(float4* p, const float* x, const float* y, const floa
             const int2 pr = pairs[k];
             const float4 ref = p[pr.y]; float4 v = p[pr.x];
             v.x = deperiodize1(v.x, ref.x, ext[0]); v.y = deperiodize1(v.y, ref.y, ext[1]); v.z = deperiodize1(v.z, ref.z, ext[2]);
+            p[pr.x] = v;
+        }
+    } else if (uc.flags & MDGPU_CELL_TRICLINIC) {   // unwrap_atom_triclinic_vec4 -> deperiodize_triclinic md_util.c:1754-1766
+        const float box[3][3] = { { (float)uc.x, 0.f, 0.f }, { (float)uc.xy, (float)uc.y, 0.f }, { (float)uc.xz, (float)uc.yz, (float)uc.z } };
+        for (uint32_t k = 0; k < n_pairs; ++k) {
+            const int2 pr = pairs[k];
+            const float4 ref = p[pr.y]; float4 v = p[pr.x];
+            float d[3] = { __fsub_rn(v.x, ref.x), __fsub_rn(v.y, ref.y), __fsub_rn(v.z, ref.z) };
+            min_image_triclinic(d, box);
+            v.x = __fadd_rn(ref.x, d[0]); v.y = __fadd_rn(ref.y, d[1]); v.z = __fadd_rn(ref.z, d[2]);
             p[pr.x] = v;
         }
     }
@@ -307,7 +337,8 @@ __global__ void k_sdf_fit(SdfArgs a, int B) {
         if (hi <= lo) hi = lo + 1;
         if (!pbc[k]) { lo = max(0, min(lo, cdk)); hi = max(0, min(hi, cdk)); if (hi <= lo) hi = min(lo + 1, cdk); }
         frad = fmin(frad, 0.5);
-        o[20 + k] = (float)(sc[k] - frad); o[23 + k] = (float)(sc[k] + frad);
+        if (g.flags & MDGPU_CELL_TRICLINIC) { o[20 + k] = (float)(ccen[k] - rad); o[23 + k] = (float)(ccen[k] + rad); }   // cartesian bounds (:2041-2047)
+        else { o[20 + k] = (float)(sc[k] - frad); o[23 + k] = (float)(sc[k] + frad); }                                   // fractional bounds (:1913-1923)
         oi[k] = lo; oi[3 + k] = hi;
     }
 }
@@ -325,12 +356,15 @@ constexpr int SDF_MAXSEG = 128;
 constexpr int SDF_EXCL_CACHE = 64;
 constexpr int SDF_RING = 64;
 
-struct SdfXform { float M[4][3]; float A00, A11, A22, O0, O1, O2; };
+struct SdfXform { float M[4][3]; float A00, A11, A22, O0, O1, O2, A10, A20, A21; };
 
 // fractional (image-shifted) point -> cartesian -> structure frame -> voxel (:5664-5697)
+template <bool TRI>
 MDG_D void sdf_splat(float vx, float vy, float vz, const SdfXform& X, uint32_t* __restrict__ vol) {
-    // batch_fract_to_cart_ort_256: one fused multiply-add per axis (md_spatial_acc.c:583-592)
-    const float px = __fmaf_rn(vx, X.A00, X.O0), py = __fmaf_rn(vy, X.A11, X.O1), pz = __fmaf_rn(vz, X.A22, X.O2);
+    // ortho: batch_fract_to_cart_ort_256, one fused multiply-add per axis (md_spatial_acc.c:583-592).
+    // triclinic: REFERENCE QUIRK — for_each_point_in_aabb_triclinic buffers the fractional image-shifted coordinates (:2122-2130) and its
+    // *_CART_TRI callback macros (:715-737) skip the conversion, so sdf_cb transforms fractional numbers. Reproduced for parity.
+    const float px = TRI ? vx : __fmaf_rn(vx, X.A00, X.O0), py = TRI ? vy : __fmaf_rn(vy, X.A11, X.O1), pz = TRI ? vz : __fmaf_rn(vz, X.A22, X.O2);
     float c[3];   // mat4_mul_vec4(M, (x,y,z,1)) = ((x*M0 + y*M1) + z*M2) + 1*M3
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -346,6 +380,7 @@ MDG_D void sdf_splat(float vx, float vy, float vz, const SdfXform& X, uint32_t* 
     atomicAdd(&vol[(iz * MDGPU_VOL_DIM + iy) * MDGPU_VOL_DIM + ix], 1u);
 }
 
+template <bool TRI>
 __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B) {
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -356,7 +391,7 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
     __shared__ int32_t s_excl[SDF_WARPS][SDF_EXCL_CACHE];
     if (s >= a.n_struct) return;
     const FrameGeom& g = a.geom[f];
-    if (g.valid == -1 || (g.flags & MDGPU_CELL_TRICLINIC)) return;   // triclinic AABB query: rejected by the host
+    if (g.valid == -1) return;
     const float* rec = a.matrices + ((size_t)f * a.n_struct + s) * SDF_REC;
     SdfXform X;
 #pragma unroll
@@ -364,6 +399,7 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
 #pragma unroll
         for (int j = 0; j < 3; ++j) X.M[i][j] = rec[i * 4 + j];
     X.A00 = g.A[0][0]; X.A11 = g.A[1][1]; X.A22 = g.A[2][2]; X.O0 = g.origin[0]; X.O1 = g.origin[1]; X.O2 = g.origin[2];
+    X.A10 = g.A[1][0]; X.A20 = g.A[2][0]; X.A21 = g.A[2][1];
     const float lo3[3] = { rec[20], rec[21], rec[22] }, hi3[3] = { rec[23], rec[24], rec[25] };
     const int* ri = (const int*)(rec + 26);
     const int cmin[3] = { ri[0], ri[1], ri[2] }, cmax[3] = { ri[3], ri[4], ri[5] };
@@ -427,7 +463,10 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
                 if (sg.y != 0x15u) {   // periodic image of the cell: + (-1|0|+1), rounded (:1962-1964); +0 is the identity
                     vx = __fadd_rn(vx, (float)((int)(sg.y & 3u) - 1)); vy = __fadd_rn(vy, (float)((int)((sg.y >> 2) & 3u) - 1)); vz = __fadd_rn(vz, (float)((int)((sg.y >> 4) & 3u) - 1));
                 }
-                hit = vx >= lo3[0] && vy >= lo3[1] && vz >= lo3[2] && vx <= hi3[0] && vy <= hi3[1] && vz <= hi3[2];
+                if (TRI) {   // box test on the cartesian image (fract_to_cart_tri_256 md_spatial_acc.c:594-603), all axes periodic (:2009)
+                    const float cx_ = __fmaf_rn(vx, X.A00, __fmaf_rn(vy, X.A10, __fmaf_rn(vz, X.A20, X.O0))), cy_ = __fmaf_rn(vy, X.A11, __fmaf_rn(vz, X.A21, X.O1)), cz_ = __fmaf_rn(vz, X.A22, X.O2);
+                    hit = cx_ >= lo3[0] && cy_ >= lo3[1] && cz_ >= lo3[2] && cx_ <= hi3[0] && cy_ <= hi3[1] && cz_ <= hi3[2];
+                } else hit = vx >= lo3[0] && vy >= lo3[1] && vz >= lo3[2] && vx <= hi3[0] && vy <= hi3[1] && vz <= hi3[2];
                 if (hit) {
                     const uint32_t idx = __float_as_uint(t.w);
                     if (ex_contig) hit = (idx - ex_lo) >= ex_n;
@@ -446,7 +485,7 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
             cnt += __popc(hm);
             if (cnt >= 32u) {
                 __syncwarp();
-                sdf_splat(rx[lane], ry[lane], rz[lane], X, a.vol);
+                sdf_splat<TRI>(rx[lane], ry[lane], rz[lane], X, a.vol);
                 const uint32_t rem = cnt - 32u;
                 float mx = 0.f, my = 0.f, mz = 0.f;
                 if (lane < rem) { mx = rx[32 + lane]; my = ry[32 + lane]; mz = rz[32 + lane]; }
@@ -458,19 +497,19 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
         }
     }
     __syncwarp();
-    if (lane < cnt) sdf_splat(rx[lane], ry[lane], rz[lane], X, a.vol);
+    if (lane < cnt) sdf_splat<TRI>(rx[lane], ry[lane], rz[lane], X, a.vol);
     local += cnt;
     if (lane == 0 && local) atomicAdd(&a.frame_total[a.frame0 + f], local);
 }
 
-void launch_sdf(const SdfArgs& a, int B, cudaStream_t s) {
+void launch_sdf(const SdfArgs& a, int B, bool tri, cudaStream_t s) {
     k_sdf_ref0<<<(B + 31) / 32, 32, 0, s>>>(a, B);
     note_launch("k_sdf_ref0", s);
     dim3 g1((a.n_struct + 63) / 64, B);
     k_sdf_fit<<<g1, 64, 0, s>>>(a, B);
     note_launch("k_sdf_fit", s);
     dim3 g2((a.n_struct + SDF_WARPS - 1) / SDF_WARPS, B);
-    k_sdf_scatter<<<g2, SDF_WARPS * 32, 0, s>>>(a, B);
+    if (tri) k_sdf_scatter<true><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); else k_sdf_scatter<false><<<g2, SDF_WARPS * 32, 0, s>>>(a, B);
     note_launch("k_sdf_scatter", s);
 }
 
