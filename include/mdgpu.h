@@ -98,6 +98,8 @@ typedef enum mdgpu_op {
     MDGPU_OP_DISTANCE = 6,   /* distance(a, b)   atoms or selections -> temporal [F,1]                    :3851-3890 */
     MDGPU_OP_ANGLE = 7,      /* angle(a, b, c)                       -> temporal                          :4099-4114 */
     MDGPU_OP_DIHEDRAL = 8,   /* dihedral(a, b, c, d)                 -> temporal                          :4171-4196 */
+    MDGPU_OP_DISTANCE_MIN = 9,  /* distance_min(a, b) over the atoms of two selections -> temporal        :3892-3928 */
+    MDGPU_OP_DISTANCE_MAX = 10, /* distance_max(a, b): the reference evaluates md_util_min_distance here too (:3944) */
 } mdgpu_op;
 
 /* One property = one `ident = proc(args);` statement whose selections were evaluated statically at compile time
@@ -109,6 +111,7 @@ typedef enum mdgpu_op {
  *              by structure_offsets[num_structures+1], or are `structure_size` atoms each when that pointer is NULL.
  *   SDF      : idx[0] = num_structures * structure_size atoms (equivalent structures), idx[1] = target atoms, cutoff_max.
  *   DENSITY_*: idx[0] = atoms.
+ *   DISTANCE_MIN/_MAX: idx[0], idx[1] = the atoms of the two selections (brute force over all pairs, md_util_min_distance md_util.c:8242).
  *   DISTANCE/ANGLE/DIHEDRAL: idx[k] = the atoms of argument k (0-based). A single integer index is that atom's position; an
  *              argument that was a selection (bit k of com_args set, or more than one index) is its centre of mass as
  *              coordinate_extract_com evaluates it (:1717 -> md_util_com_compute md_util.c:8163: periodic cells use the

@@ -95,6 +95,15 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         out->idx_count[0] = w;
         return true;
     }
+    if ((str_eq(pname, STR_LIT("distance_min")) || str_eq(pname, STR_LIT("distance_max"))) && nargs == 2) {
+        out->op = str_eq(pname, STR_LIT("distance_min")) ? MDGPU_OP_DISTANCE_MIN : MDGPU_OP_DISTANCE_MAX;
+        for (size_t k = 0; k < 2; ++k) {
+            size_t ns = 0;
+            if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], &ns, NULL, args[k], alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n;
+            if (args[k]->data.type.base_type == TYPE_BITFIELD && ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (per-selection centres of mass) is not lowered for distance_min/max", STR_ARG(ident)); return false; }
+        }
+        return true;
+    }
     {
         const bool dist = str_eq(pname, STR_LIT("distance")), ang = str_eq(pname, STR_LIT("angle")), dih = str_eq(pname, STR_LIT("dihedral"));
         const size_t need = dist ? 2 : (ang ? 3 : (dih ? 4 : 0));

@@ -912,6 +912,26 @@ static void normalize3(float v[3]) {
     if (len > 1.0e-5) { v[0] = v[0] / len; v[1] = v[1] / len; v[2] = v[2] / len; } else { v[0] = v[1] = v[2] = 0; }
 }
 
+/* distance_min(a, b) / distance_max(a, b): _distance_min / _distance_max md_script_functions.inl:3892-3968 over the atoms of two selections.
+ * Both call md_util_min_distance (md_util.c:8242-8297; _distance_max calling the MIN function is the reference's behaviour, :3944):
+ * brute force over all pairs, vec4_periodic_distance (core/md_vec_math.h:1268-1273) in ortho cells, minimum_image_triclinic in triclinic. */
+float mdo_min_distance(const float* x, const float* y, const float* z, const int32_t* ia, size_t na, const int32_t* ib, size_t nb, const mdo_unitcell_t* cell) {
+    float min_dist = FLT_MAX;
+    const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
+    const float box[3][3] = { { (float)cell->x, 0, 0 }, { (float)cell->xy, (float)cell->y, 0 }, { (float)cell->xz, (float)cell->yz, (float)cell->z } };
+    for (size_t i = 0; i < na; ++i) for (size_t j = 0; j < nb; ++j) {
+        const float a[3] = { x[ia[i]], y[ia[i]], z[ia[i]] }, b[3] = { x[ib[j]], y[ib[j]], z[ib[j]] };
+        float d[3] = { a[0] - b[0], a[1] - b[1], a[2] - b[2] }, dist;
+        if (cell->flags == 0) dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);             /* vec3_distance */
+        else if (cell->flags & MDO_CELL_ORTHO) {
+            for (int k = 0; k < 3; ++k) if (ext[k] != 0.0f) d[k] = d[k] - rintf(d[k] / ext[k]) * ext[k];
+            dist = sqrtf((d[0] * d[0] + d[1] * d[1]) + (d[2] * d[2] + 0.0f));                        /* vec4_dot: md_mm_reduce_add_ps order */
+        } else { min_image_triclinic(d, box); dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]); }   /* vec3_length */
+        if (dist < min_dist) min_dist = dist;
+    }
+    return min_dist;
+}
+
 /* _angle :4099-4114 */
 float mdo_angle_pos(const float a[3], const float b[3], const float c[3]) {
     float v0[3] = { a[0] - b[0], a[1] - b[1], a[2] - b[2] }, v1[3] = { c[0] - b[0], c[1] - b[1], c[2] - b[2] };

@@ -77,6 +77,9 @@ int mdo_xtc_decode_frame(const uint8_t* frame, size_t nbytes, size_t num_atoms, 
                          mdo_unitcell_t* cell, int32_t* step, float* time);
 size_t mdo_xtc_frame_offsets(const uint8_t* file, size_t nbytes, int64_t* offsets, size_t cap);
 
+/* distance_min / distance_max over two atom selections (md_script_functions.inl:3892-3968; both evaluate md_util_min_distance md_util.c:8242) */
+float mdo_min_distance(const float* x, const float* y, const float* z, const int32_t* ia, size_t na, const int32_t* ib, size_t nb, const mdo_unitcell_t* cell);
+
 /* building blocks exposed for unit tests */
 void mdo_svd3(const float A[3][3], float U[3][3], float S[3][3], float V[3][3]); /* ext/svd3/svd3.c */
 uint64_t mdo_count_pairs(const float* x, const float* y, const float* z, const int32_t* ref_idx, size_t n_ref,

@@ -74,7 +74,8 @@ def water6(tmp):
               "d = distance(1,10); a = angle(1,2,3); t = dihedral(1,4,7,10); "
               "rc = rdf(residue(1:20), element('O'), 5.0); "
               "dc = distance(residue(1), residue(5)); ac = angle(residue(1), residue(2), residue(3)); "
-              "tc = dihedral(residue(1), residue(2), residue(3), residue(4)); dg = distance(atom(1:30), atom(100:151)); dm = distance(atom(1:30), 200);")
+              "tc = dihedral(residue(1), residue(2), residue(3), residue(4)); dg = distance(atom(1:30), atom(100:151)); dm = distance(atom(1:30), 200); "
+              "dmn = distance_min(residue(1), atom(100:648)); dmx = distance_max(atom(1:30), atom(100:151)); dmh = distance_min(element('H'), atom(300:400));")
     o = os.path.join(tmp, "w.out"); si = os.path.join(tmp, "w.sys")
     run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
     run(HARNESS, "sysinfo", "--sys", gro, "--out", si)
@@ -135,7 +136,7 @@ def tric6(tmp):
         out_fr[f, 1] = (y + (yz / L) * z).astype(np.float32); out_fr[f, 2] = z.astype(np.float32)
         out_cells[f] = [L, xy, xz, L, yz, L]
     refio.write_raw_traj(raw, out_fr, out_cells, flags)
-    script = "rt = rdf(element('O'), element('O'), 6.0); rth = rdf(element('O'), element('H'), 2.0:7.0); rtc = rdf(residue(1:30), element('H'), 5.0); vt = sdf(residue(1:20), element('O'), 5.0);"
+    script = "rt = rdf(element('O'), element('O'), 6.0); rth = rdf(element('O'), element('H'), 2.0:7.0); rtc = rdf(residue(1:30), element('H'), 5.0); vt = sdf(residue(1:20), element('O'), 5.0); dmt = distance_min(atom(1:30), atom(100:151)); dmxt = distance_max(element('O'), atom(7:9));"
     o = os.path.join(tmp, "t.out"); si = os.path.join(tmp, "t.sys")
     run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
     run(HARNESS, "sysinfo", "--sys", gro, "--out", si)

@@ -50,7 +50,7 @@ def lib():
         _lib.mdo_distance.restype = C.c_float
         _lib.mdo_angle.restype = C.c_float
         _lib.mdo_dihedral.restype = C.c_float
-        for n in ("mdo_distance_pos", "mdo_angle_pos", "mdo_dihedral_pos"): getattr(_lib, n).restype = C.c_float
+        for n in ("mdo_distance_pos", "mdo_angle_pos", "mdo_dihedral_pos", "mdo_min_distance"): getattr(_lib, n).restype = C.c_float
     return _lib
 
 
@@ -176,3 +176,8 @@ def xtc_decode_frame(blob, beg, end, num_atoms):
     ok = lib().mdo_xtc_decode_frame(C.c_void_p(blob.ctypes.data + int(beg)), C.c_size_t(int(end - beg)), C.c_size_t(num_atoms),
                                     C.c_void_p(xyz[0].ctypes.data), C.c_void_p(xyz[1].ctypes.data), C.c_void_p(xyz[2].ctypes.data), C.byref(cell), C.byref(st), C.byref(tm))
     return bool(ok), xyz, cell, int(st.value), float(tm.value)
+
+
+def min_distance(x, y, z, a, b, cell):
+    x, y, z = _f32(x), _f32(y), _f32(z); a, b = _i32(a), _i32(b)
+    return np.float32(lib().mdo_min_distance(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(a, C.c_int32), C.c_size_t(len(a)), _p(b, C.c_int32), C.c_size_t(len(b)), C.byref(cell)))

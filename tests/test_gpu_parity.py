@@ -104,6 +104,8 @@ def test_golden_triclinic_rdf_bitexact():
     plan.clear()
     plan.eval_host_frames(g["frames"], cells, 0)
     assert np.array_equal(plan.counts("vt").astype(np.float64), total)
+    for key in ("dmt", "dmxt"):   # distance_min / distance_max with the 27-image triclinic minimum
+        assert np.array_equal(plan.property_data(key).values, g[f"{key}__full"]), key
     for key in ("rt", "rth", "rtc"):
         for f in range(F):
             bins, tot = plan.frame_counts(key, f)
@@ -142,9 +144,12 @@ def test_golden_water_density_and_temporals():
     g = load_golden("water6.npz"); s = golden_system(g)
     plan, cells = _water_plan(g, s, "dz = density_z(element('O')); dx = density_x(element('O')); d = distance(1,10); a = angle(1,2,3); t = dihedral(1,4,7,10); "
                             "dc = distance(residue(1), residue(5)); ac = angle(residue(1), residue(2), residue(3)); "
-                            "tc = dihedral(residue(1), residue(2), residue(3), residue(4)); dg = distance(atom(1:30), atom(100:151)); dm = distance(atom(1:30), 200);")
+                            "tc = dihedral(residue(1), residue(2), residue(3), residue(4)); dg = distance(atom(1:30), atom(100:151)); dm = distance(atom(1:30), 200); "
+                            "dmn = distance_min(residue(1), atom(100:648)); dmx = distance_max(atom(1:30), atom(100:151)); dmh = distance_min(element('H'), atom(300:400));")
     F = g["frames"].shape[0]
     plan.eval_host_frames(g["frames"], cells, 0)
+    for key in ("dmn", "dmx", "dmh"):   # brute-force pair minimum (distance_max evaluates the minimum in the reference too)
+        assert np.array_equal(plan.property_data(key).values, g[f"{key}__full"]), key
     # arguments that are selections: periodic centre of mass (md_util_com_compute), lane-by-lane restatement of the AVX2 reference
     for key in ("dc", "dg", "dm"):
         assert np.array_equal(plan.property_data(key).values, g[f"{key}__full"]), key      # distances: every operation is IEEE on both sides

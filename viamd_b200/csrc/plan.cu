@@ -272,6 +272,12 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.values.assign(2 * MDGPU_DIST_BINS, 0.0f);
             pr.data.dim[0] = 1; pr.data.dim[1] = 2; pr.data.dim[2] = MDGPU_DIST_BINS; pr.data.dim[3] = 0;
             break;
+        case MDGPU_OP_DISTANCE_MIN: case MDGPU_OP_DISTANCE_MAX:
+            if (pr.h_idx[0].empty() || pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
+            e = dalloc(&pr.d_temporal, num_frames);
+            pr.values.assign(num_frames, 0.0f);
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break;
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
             const int need = pr.op == MDGPU_OP_DISTANCE ? 2 : (pr.op == MDGPU_OP_ANGLE ? 3 : 4);
             pr.com_mask = d.com_args & ((1u << need) - 1u);
@@ -476,6 +482,9 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             launch_density(a, B, s.stream);
             if (p->timing) { cudaEventRecord(tl.b, s.stream); tl.kind = 2; p->timed.push_back(tl); }
             break; }
+        case MDGPU_OP_DISTANCE_MIN: case MDGPU_OP_DISTANCE_MAX:   // both evaluate md_util_min_distance (md_script_functions.inl:3904, 3944)
+            launch_min_distance(fr, s.d_cells, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), pr.d_idx[1], (uint32_t)pr.h_idx[1].size(), pr.d_temporal, frame0, s.stream);
+            break;
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
             TemporalArgs a{};
             a.frames = fr; a.cells = s.d_cells; a.op = (int)pr.op; a.out = pr.d_temporal; a.frame0 = frame0;
@@ -820,7 +829,7 @@ int mdgpu_plan_sync(mdgpu_plan* p) {
             CUDA_TRY(cudaMemcpy(pr.values.data(), pr.d_temporal, sizeof(float) * F, cudaMemcpyDeviceToHost));
             pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;
             for (uint32_t f : done) { pr.data.min_value = std::min(pr.data.min_value, pr.values[f]); pr.data.max_value = std::max(pr.data.max_value, pr.values[f]); }
-            if (pr.op == MDGPU_OP_DISTANCE) { pr.data.min_range[0] = 0.0f; pr.data.max_range[0] = pr.data.max_value; }   // value_range {0, FLT_MAX} (:3884)
+            if (pr.op == MDGPU_OP_DISTANCE || pr.op == MDGPU_OP_DISTANCE_MIN || pr.op == MDGPU_OP_DISTANCE_MAX) { pr.data.min_range[0] = 0.0f; pr.data.max_range[0] = pr.data.max_value; }   // value_range {0, FLT_MAX} (:3884)
             else { pr.data.min_range[0] = pr.data.min_value; pr.data.max_range[0] = pr.data.max_value; }
         }
     }

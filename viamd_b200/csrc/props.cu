@@ -119,6 +119,25 @@ MDG_D void normalize3(float v[3]) {   // vec3_normalize core/md_vec_math.h:505-5
     if ((double)len > 1.0e-5) { v[0] = v[0] / len; v[1] = v[1] / len; v[2] = v[2] / len; } else { v[0] = v[1] = v[2] = 0.0f; }
 }
 
+// minimum_image_triclinic md_util.c:1677-1718 (27 images, double comparison, mixed float/double sums as written there)
+MDG_D void min_image_triclinic_p(float dx[3], const float box[3][3]) {
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, dsq_min = (double)3.402823466e+38f;
+    for (int ix = -1; ix < 2; ++ix) {
+        const double rx = (double)__fadd_rn(dx[0], __fmul_rn(box[0][0], (float)ix));
+        for (int iy = -1; iy < 2; ++iy) {
+            const double ry0 = __dadd_rn(rx, (double)__fmul_rn(box[1][0], (float)iy));
+            const double ry1 = (double)__fadd_rn(dx[1], __fmul_rn(box[1][1], (float)iy));
+            for (int iz = -1; iz < 2; ++iz) {
+                const double rz0 = __dadd_rn(ry0, (double)__fmul_rn(box[2][0], (float)iz)), rz1 = __dadd_rn(ry1, (double)__fmul_rn(box[2][1], (float)iz));
+                const double rz2 = (double)__fadd_rn(dx[2], __fmul_rn(box[2][2], (float)iz));
+                const double dsq = __dadd_rn(__dadd_rn(__dmul_rn(rz0, rz0), __dmul_rn(rz1, rz1)), __dmul_rn(rz2, rz2));
+                if (dsq < dsq_min) { dsq_min = dsq; m0 = rz0; m1 = rz1; m2 = rz2; }
+            }
+        }
+    }
+    dx[0] = (float)m0; dx[1] = (float)m1; dx[2] = (float)m2;
+}
+
 // One lane of md_mm256_sincos_ps (core/md_simd.h:1177-1258, Cephes polynomials): every operation is an IEEE float op (explicit FMAs
 // where the reference has fmadd intrinsics), so the GPU reproduces the AVX2 build bit for bit.
 MDG_D void ref_sincosf(float x, float& out_s, float& out_c) {
@@ -285,6 +304,41 @@ __global__ void k_temporal(TemporalArgs a, int B) {
         out = angle;
     }
     a.out[a.frame0 + f] = out;
+}
+
+// distance_min / distance_max (both md_util_min_distance, md_util.c:8242-8297): all pairs of two selections, one CTA per frame.
+// The minimum of floats is order independent, so the pairs are spread over the threads and reduced.
+__global__ void __launch_bounds__(256) k_min_distance(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ ia, uint32_t na,
+                                                      const int32_t* __restrict__ ib, uint32_t nb, float* __restrict__ out, uint32_t frame0) {
+    const int f = blockIdx.x;
+    const float* x = fr.xyz + (size_t)f * fr.frame_stride; const float* y = x + fr.axis_stride; const float* z = y + fr.axis_stride;
+    const mdgpu_unitcell_t uc = cells[f];
+    const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
+    const float box[3][3] = { { (float)uc.x, 0.f, 0.f }, { (float)uc.xy, (float)uc.y, 0.f }, { (float)uc.xz, (float)uc.yz, (float)uc.z } };
+    float best = 3.402823466e+38f;
+    const unsigned long long npairs = (unsigned long long)na * nb;
+    for (unsigned long long p = threadIdx.x; p < npairs; p += blockDim.x) {
+        const int a = ia[p / nb], b = ib[p % nb];
+        float d[3] = { __fsub_rn(x[a], x[b]), __fsub_rn(y[a], y[b]), __fsub_rn(z[a], z[b]) }, dist;
+        if (uc.flags == 0) dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));   // vec3_distance
+        else if (uc.flags & MDGPU_CELL_ORTHO) {   // vec4_periodic_distance core/md_vec_math.h:1268-1273; vec4_dot sums (x+y)+(z+w)
+            for (int k = 0; k < 3; ++k) if (ext[k] != 0.0f) d[k] = __fsub_rn(d[k], __fmul_rn(rintf(__fdiv_rn(d[k], ext[k])), ext[k]));
+            dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fadd_rn(__fmul_rn(d[2], d[2]), 0.0f)));
+        } else { min_image_triclinic_p(d, box); dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]))); }
+        best = fminf(best, dist);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    __shared__ float s_best[8];
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int w = 1; w < 8; ++w) best = fminf(best, s_best[w]); out[frame0 + f] = best; }
+}
+
+void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s) {
+    if (!fr.count) return;
+    k_min_distance<<<fr.count, 256, 0, s>>>(fr, d_cells, d_ia, na, d_ib, nb, d_out, frame0);
+    note_launch("k_min_distance", s);
 }
 
 // fold of an integer accumulator into the float mean the property data exposes: (float)((double)count / (double)n), IEEE on the device

@@ -172,6 +172,9 @@ class _Parser:
             p = api.sdf(ident, st, trg, c)
         elif proc in ("density_x", "density_y", "density_z"):
             p = api.density(ident, "xyz".index(proc[-1]), self.selection())
+        elif proc in ("distance_min", "distance_max"):
+            a = self.selection(); self.expect("ch", ","); b = self.selection()
+            p = (api.distance_min if proc == "distance_min" else api.distance_max)(ident, a, b)
         elif proc == "distance":
             a = self.index(); self.expect("ch", ","); b = self.index(); p = api.distance(ident, a, b)
         elif proc == "angle":
