@@ -88,6 +88,11 @@ struct XtcFrameInfo {   // written by k_xtc_scan, one per frame
 void launch_xtc_decode(const uint8_t* d_blob, const unsigned long long* d_frame_off, uint32_t num_atoms, int B, XtcFrameInfo* d_info,
                        uint2* d_rec, uint16_t* d_rec_state, size_t rec_stride, float* d_out, size_t frame_stride, size_t axis_stride, int* d_err, cudaStream_t s);
 
+void launch_xtc_scan(const uint8_t* d_blob, const unsigned long long* d_frame_off, uint32_t num_atoms, int nframes, XtcFrameInfo* d_info,
+                     uint2* d_rec, uint16_t* d_rec_state, size_t rec_stride, cudaStream_t s);
+void launch_xtc_expand(const uint8_t* d_blob, const unsigned long long* d_frame_off, uint32_t num_atoms, int nframes, const XtcFrameInfo* d_info,
+                       const uint2* d_rec, const uint16_t* d_rec_state, size_t rec_stride, float* d_out, size_t frame_stride, size_t axis_stride, int* d_err, cudaStream_t s);
+
 // synth.cu
 void launch_synth_frames(uint32_t seed, float Lx, float Ly, float Lz, uint32_t num_atoms, const float* d_base, size_t base_axis_stride,
                          const uint32_t* d_mol_id, uint32_t frame_beg, uint32_t count, float* d_out, size_t frame_stride, size_t axis_stride, cudaStream_t s);

@@ -83,11 +83,19 @@ struct Slot {
     float* d_frames = nullptr; float* h_frames = nullptr;      // staging for host-resident frames
     mdgpu_unitcell_t* d_cells = nullptr; mdgpu_unitcell_t* h_cells = nullptr;
     int* d_err = nullptr;
-    // XTC input: compressed bytes of the batch + per-frame offsets, scan records
-    uint8_t* d_xtc = nullptr; size_t xtc_cap = 0; unsigned long long* d_xtc_off = nullptr; unsigned long long* h_xtc_off = nullptr;
-    XtcFrameInfo* d_xtc_info = nullptr; uint2* d_xtc_rec = nullptr; uint16_t* d_xtc_state = nullptr;
     std::vector<PropScratch> ps;
     uint32_t pending_beg = 0, pending_cnt = 0;
+};
+
+// XTC input stage: compressed bytes + scan records of XTC_SUPER batches, scanned by ONE launch on the stage's own stream. The walk over a
+// frame's stream is a latency-bound serial chain (one warp per frame), so its throughput comes from scanning many frames at once and from
+// running two super-batches ahead of the expand + property kernels that consume it.
+constexpr uint32_t XTC_SUPER = 2;   // 2 scan warps per SM: with more, their registers take the third CTA slot of the pair kernel running on another stream
+constexpr uint32_t XTC_STAGES = 3;   // the scan of super-batch k+2 is in flight while the batches of k are expanded and evaluated
+struct XtcStage {
+    cudaStream_t stream = nullptr; cudaEvent_t ready = nullptr; cudaEvent_t consumed[XTC_SUPER] = {}; uint32_t n_consumed = 0;
+    uint8_t* d_blob = nullptr; size_t cap = 0; unsigned long long* d_off = nullptr; unsigned long long* h_off = nullptr;
+    XtcFrameInfo* d_info = nullptr; uint2* d_rec = nullptr; uint16_t* d_state = nullptr;
 };
 
 struct TimedLaunch { cudaEvent_t a, b; int kind; };   // kind: 0 rdf pair kernel, 1 sdf (all three kernels), 2 density (+finalize)
@@ -111,6 +119,7 @@ struct mdgpu_plan {
     bool timing = false; std::vector<TimedLaunch> timed; double timed_ms[3] = {0, 0, 0}; uint64_t timed_n[3] = {0, 0, 0};
     bool tri_seen = false, ortho_seen = false;
     cudaEvent_t t_begin = nullptr; std::vector<cudaEvent_t> t_end;
+    XtcStage xtc[XTC_STAGES]; uint64_t next_xtc = 0;
     bool dirty = true;   // device accumulators changed since the last fold into the host-visible property data
 };
 
@@ -161,9 +170,14 @@ static void destroy_plan(mdgpu_plan* p) {
         }
         cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
-        cudaFree(s.d_xtc); cudaFree(s.d_xtc_off); if (s.h_xtc_off) cudaFreeHost(s.h_xtc_off); cudaFree(s.d_xtc_info); cudaFree(s.d_xtc_rec); cudaFree(s.d_xtc_state);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (auto& st : p->xtc) {
+        cudaFree(st.d_blob); cudaFree(st.d_off); if (st.h_off) cudaFreeHost(st.h_off); cudaFree(st.d_info); cudaFree(st.d_rec); cudaFree(st.d_state);
+        if (st.ready) cudaEventDestroy(st.ready);
+        for (auto& e : st.consumed) if (e) cudaEventDestroy(e);
+        if (st.stream) cudaStreamDestroy(st.stream);
     }
     for (auto& pr : p->props) {
         for (int k = 0; k < 4; ++k) cudaFree(pr.d_idx[k]);
@@ -604,18 +618,22 @@ static bool xtc_header_cell(const uint8_t* fr, size_t nbytes, mdgpu_unitcell_t* 
     return true;
 }
 
-static int ensure_xtc_buffers(mdgpu_plan* p, Slot& s, size_t need_bytes) {
-    if (!s.d_xtc_off) {
-        CUDA_TRY(dalloc(&s.d_xtc_off, (size_t)p->B + 1));
-        CUDA_TRY(cudaMallocHost((void**)&s.h_xtc_off, sizeof(unsigned long long) * ((size_t)p->B + 1)));
-        CUDA_TRY(dalloc(&s.d_xtc_info, p->B));
-        CUDA_TRY(dalloc(&s.d_xtc_rec, (size_t)p->B * p->num_atoms));
-        CUDA_TRY(dalloc(&s.d_xtc_state, (size_t)p->B * p->num_atoms));
+static int ensure_xtc_stage(mdgpu_plan* p, XtcStage& st, size_t need_bytes) {
+    const size_t nf = (size_t)p->B * XTC_SUPER;
+    if (!st.stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&st.ready, cudaEventDisableTiming));
+        for (auto& e : st.consumed) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_TRY(dalloc(&st.d_off, nf + 1));
+        CUDA_TRY(cudaMallocHost((void**)&st.h_off, sizeof(unsigned long long) * (nf + 1)));
+        CUDA_TRY(dalloc(&st.d_info, nf));
+        CUDA_TRY(dalloc(&st.d_rec, nf * p->num_atoms));
+        CUDA_TRY(dalloc(&st.d_state, nf * p->num_atoms));
     }
-    if (need_bytes + 32 > s.xtc_cap) {
-        cudaFree(s.d_xtc); s.d_xtc = nullptr; s.xtc_cap = 0;
-        const size_t cap = std::max(need_bytes + 32, (size_t)p->B * (p->num_atoms * 6 + 128)) + 4096;
-        CUDA_TRY(cudaMalloc((void**)&s.d_xtc, cap)); s.xtc_cap = cap;
+    if (need_bytes + 32 > st.cap) {
+        cudaFree(st.d_blob); st.d_blob = nullptr; st.cap = 0;
+        const size_t cap = std::max(need_bytes + 32, nf * (p->num_atoms * 6 + 128)) + 4096;
+        CUDA_TRY(cudaMalloc((void**)&st.d_blob, cap)); st.cap = cap;
     }
     return 0;
 }
@@ -629,28 +647,49 @@ int mdgpu_eval_xtc_frames(mdgpu_plan* p, const uint8_t* h_blob, const uint64_t* 
     mdgpu_unitcell_t first{};
     if (!xtc_header_cell(h_blob + frame_offsets[0], frame_offsets[1] - frame_offsets[0], &first, nullptr, nullptr)) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Magic number did not match");
     int rc = ensure_slots(p, &first, true); if (rc) return rc;
-    const size_t AS = p->axis_stride;
-    for (uint32_t b0 = 0; b0 < count; b0 += p->B) {
-        if (p->interrupt.load()) return fail(MDGPU_ERR_INTERRUPTED, "evaluation interrupted");
-        const uint32_t nb = std::min(p->B, count - b0);
-        Slot& s = p->slots[p->next_slot++ % p->slots.size()];
-        rc = retire_slot(p, s); if (rc) return rc;
-        const uint64_t beg = frame_offsets[b0], end = frame_offsets[b0 + nb];
-        rc = ensure_xtc_buffers(p, s, (size_t)(end - beg)); if (rc) return rc;
-        for (uint32_t i = 0; i < nb; ++i) {
-            const uint8_t* fr = h_blob + frame_offsets[b0 + i];
-            if (!xtc_header_cell(fr, (size_t)(frame_offsets[b0 + i + 1] - frame_offsets[b0 + i]), &s.h_cells[i], nullptr, nullptr)) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Magic number did not match");
-            s.h_xtc_off[i] = frame_offsets[b0 + i] - beg;
+    const size_t AS = p->axis_stride, NA = p->num_atoms;
+    const uint32_t SB = p->B * XTC_SUPER;
+    const uint32_t nsuper = (count + SB - 1) / SB;
+    // stage k+1 (copy + scan, on its own stream) is issued BEFORE the batches of stage k are enqueued, so it overlaps their kernels
+    auto issue = [&](uint32_t k) -> int {
+        const uint32_t s0 = k * SB, ns = std::min(SB, count - s0);
+        XtcStage& st = p->xtc[(p->next_xtc + k) % XTC_STAGES];
+        const uint64_t beg = frame_offsets[s0], end = frame_offsets[s0 + ns];
+        int r = ensure_xtc_stage(p, st, (size_t)(end - beg)); if (r) return r;
+        CUDA_TRY(cudaEventSynchronize(st.ready));                                   // the pinned offset table of its previous use has been read
+        for (uint32_t q = 0; q < st.n_consumed; ++q) CUDA_TRY(cudaStreamWaitEvent(st.stream, st.consumed[q], 0));   // ... and its bytes expanded
+        st.n_consumed = 0;
+        for (uint32_t i = 0; i <= ns; ++i) st.h_off[i] = frame_offsets[s0 + i] - beg;
+        CUDA_TRY(cudaMemcpyAsync(st.d_blob, h_blob + beg, (size_t)(end - beg), cudaMemcpyHostToDevice, st.stream));
+        CUDA_TRY(cudaMemsetAsync(st.d_blob + (end - beg), 0, 32, st.stream));   // guard bytes for the word-wise bit reader
+        CUDA_TRY(cudaMemcpyAsync(st.d_off, st.h_off, sizeof(unsigned long long) * (ns + 1), cudaMemcpyHostToDevice, st.stream));
+        launch_xtc_scan(st.d_blob, st.d_off, (uint32_t)NA, (int)ns, st.d_info, st.d_rec, st.d_state, NA, st.stream);
+        CUDA_TRY(cudaEventRecord(st.ready, st.stream));
+        return 0;
+    };
+    for (uint32_t k = 0; k + 1 < XTC_STAGES && k < nsuper; ++k) { rc = issue(k); if (rc) return rc; }
+    for (uint32_t k = 0; k < nsuper; ++k) {
+        if (k + XTC_STAGES - 1 < nsuper) { rc = issue(k + XTC_STAGES - 1); if (rc) return rc; }
+        const uint32_t s0 = k * SB, ns = std::min(SB, count - s0);
+        XtcStage& st = p->xtc[(p->next_xtc + k) % XTC_STAGES];
+        for (uint32_t b0 = 0; b0 < ns; b0 += p->B) {
+            if (p->interrupt.load()) return fail(MDGPU_ERR_INTERRUPTED, "evaluation interrupted");
+            const uint32_t nb = std::min(p->B, ns - b0);
+            Slot& s = p->slots[p->next_slot++ % p->slots.size()];
+            rc = retire_slot(p, s); if (rc) return rc;
+            for (uint32_t i = 0; i < nb; ++i) {
+                const uint64_t o = frame_offsets[s0 + b0 + i];
+                if (!xtc_header_cell(h_blob + o, (size_t)(frame_offsets[s0 + b0 + i + 1] - o), &s.h_cells[i], nullptr, nullptr)) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Magic number did not match");
+            }
+            CUDA_TRY(cudaStreamWaitEvent(s.stream, st.ready, 0));
+            launch_xtc_expand(st.d_blob, st.d_off + b0, (uint32_t)NA, (int)nb, st.d_info + b0, st.d_rec + (size_t)b0 * NA, st.d_state + (size_t)b0 * NA, NA,
+                              s.d_frames, 3 * AS, AS, s.d_err, s.stream);
+            CUDA_TRY(cudaEventRecord(st.consumed[st.n_consumed++], s.stream));
+            BatchFrames fr{ s.d_frames, 3 * AS, AS, nb };
+            rc = enqueue_batch(p, s, fr, frame_beg + s0 + b0); if (rc) return rc;
         }
-        s.h_xtc_off[nb] = end - beg;
-        CUDA_TRY(cudaMemcpyAsync(s.d_xtc, h_blob + beg, (size_t)(end - beg), cudaMemcpyHostToDevice, s.stream));
-        CUDA_TRY(cudaMemsetAsync(s.d_xtc + (end - beg), 0, 32, s.stream));   // guard bytes for the word-wise bit reader
-        CUDA_TRY(cudaMemcpyAsync(s.d_xtc_off, s.h_xtc_off, sizeof(unsigned long long) * (nb + 1), cudaMemcpyHostToDevice, s.stream));
-        launch_xtc_decode(s.d_xtc, s.d_xtc_off, (uint32_t)p->num_atoms, (int)nb, s.d_xtc_info, s.d_xtc_rec, s.d_xtc_state, p->num_atoms,
-                          s.d_frames, 3 * AS, AS, s.d_err, s.stream);
-        BatchFrames fr{ s.d_frames, 3 * AS, AS, nb };
-        rc = enqueue_batch(p, s, fr, frame_beg + b0); if (rc) return rc;
     }
+    p->next_xtc += nsuper;
     return 0;
 }
 

@@ -89,7 +89,7 @@ MDG_D int sizeofints_dev(const uint32_t sizes[3]) {   // md_xtc.c:168-193: bit l
 //    Lane j parses the group that would start j predicted lengths ahead; a ballot finds how many leading predictions held, those groups
 //    are committed at once (up to 32 per round), and the first lane whose group differs is still a correctly placed group — it is
 //    committed as well and updates the state and the prediction. Irregular streams degrade to one group per round, never to a wrong result.
-constexpr uint32_t SCAN_CHUNK = 2048;   // bytes staged per round (small: the CTA has to fit beside the shared-memory-heavy pair kernel of another stream)
+constexpr uint32_t SCAN_CHUNK = 1024;   // bytes staged per round (small: the CTA has to fit beside the shared-memory-heavy pair kernel of another stream)
 constexpr uint32_t SCAN_SLACK = 128;
 
 __global__ void __launch_bounds__(32) k_xtc_scan(const uint8_t* __restrict__ blob, const unsigned long long* __restrict__ frame_off, uint32_t num_atoms, int B,
@@ -259,6 +259,22 @@ __global__ void k_xtc_decode(const uint8_t* __restrict__ blob, const unsigned lo
             x[atom] = __fmul_rn((float)c[0], cs); y[atom] = __fmul_rn((float)c[1], cs); z[atom] = __fmul_rn((float)c[2], cs);
         }
     }
+}
+
+// scan and expand as separate launches (the plan scans several batches at once on its own stream, then expands per batch)
+void launch_xtc_scan(const uint8_t* d_blob, const unsigned long long* d_frame_off, uint32_t num_atoms, int nframes, XtcFrameInfo* d_info,
+                     uint2* d_rec, uint16_t* d_rec_state, size_t rec_stride, cudaStream_t s) {
+    if (nframes <= 0) return;
+    k_xtc_scan<<<nframes, 32, 0, s>>>(d_blob, d_frame_off, num_atoms, nframes, d_info, d_rec, d_rec_state, rec_stride);
+    note_launch("k_xtc_scan", s);
+}
+void launch_xtc_expand(const uint8_t* d_blob, const unsigned long long* d_frame_off, uint32_t num_atoms, int nframes, const XtcFrameInfo* d_info,
+                       const uint2* d_rec, const uint16_t* d_rec_state, size_t rec_stride, float* d_out, size_t frame_stride, size_t axis_stride, int* d_err, cudaStream_t s) {
+    if (nframes <= 0) return;
+    const uint32_t per_frame = num_atoms <= 9 ? 1u : min((num_atoms + 255u) / 256u, 64u);
+    dim3 grid(per_frame, nframes);
+    k_xtc_decode<<<grid, 256, 0, s>>>(d_blob, d_frame_off, num_atoms, d_info, d_rec, d_rec_state, rec_stride, d_out, frame_stride, axis_stride, d_err);
+    note_launch("k_xtc_decode", s);
 }
 
 void launch_xtc_decode(const uint8_t* d_blob, const unsigned long long* d_frame_off, uint32_t num_atoms, int B, XtcFrameInfo* d_info,
