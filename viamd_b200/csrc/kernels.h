@@ -22,6 +22,9 @@ struct RdfArgs {
     const int32_t* excl_idx;
     uint32_t frame0;             // global index of the batch's first frame
     int symmetric;               // reference selection == target selection
+    // candidate lists (k_rdf_cull -> k_rdf_pairs_v2): per frame `list_stride` entries (target position | image code << 26), per home cell a
+    // header {first entry, entries of class 0, 1, 2}; one cursor per frame (zeroed by the launcher); err receives MDGPU_ERR_CAPACITY on overflow
+    uint32_t* pair_list; uint4* list_hdr; uint32_t* list_cursor; size_t list_stride; size_t hdr_stride; int* err;
     // finalize
     unsigned long long* acc;     // [1024] accumulated bins
     unsigned long long* frame_total;  // [num_frames]

@@ -76,6 +76,8 @@ struct PropScratch {   // per (stream slot, property)
     float4* d_sdf_xyzw = nullptr; float* d_sdf_ref0 = nullptr; float* d_sdf_mats = nullptr;
     float* d_com = nullptr;   // rdf with centre-of-mass references: [B][n_struct][3]
     float* d_argpos = nullptr;   // distance/angle/dihedral with selection arguments: [B][4][3]
+    // rdf candidate lists (k_rdf_cull): [B][list_stride] entries, [B][cap] headers, [B] cursors
+    uint32_t* d_pair_list = nullptr; uint4* d_list_hdr = nullptr; uint32_t* d_list_cursor = nullptr; size_t list_stride = 0;
 };
 
 struct Slot {
@@ -166,7 +168,7 @@ static void destroy_plan(mdgpu_plan* p) {
     for (auto& s : p->slots) {
         for (auto& ps : s.ps) {
             cudaFree(ps.d_geom); cudaFree(ps.d_aabb); free_cell_list(ps.trg); free_cell_list(ps.ref);
-            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos);
+            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
         }
         cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
@@ -411,6 +413,15 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                 if (pr.op == MDGPU_OP_RDF) {
                     int rc = alloc_cell_list(ps.ref, p->B, (uint32_t)(pr.n_struct ? pr.n_struct : pr.h_idx[0].size()), cap); if (rc) return rc;
                     if (pr.n_struct) CUDA_TRY(dalloc(&ps.d_com, (size_t)p->B * pr.n_struct * 3));
+                    else {   // candidate lists of the packed pair kernel: every target appears in at most (2n+1)^3 home cells' lists
+                        FrameGeom g; host_frame_geom(&g, first_cell, pr.cutoff_max, pr.cutoff_max, nullptr, 0xffffffffu);
+                        size_t nn = (size_t)(2 * std::max(g.ncell[0], 1) + 1) * (2 * std::max(g.ncell[1], 1) + 1) * (2 * std::max(g.ncell[2], 1) + 1);
+                        if (g.valid <= 0 || (first_cell->flags & MDGPU_CELL_PBC_ALL) != MDGPU_CELL_PBC_ALL) nn = 125;   // grid from the data (AABB fit): size for the widest reach the reference allows
+                        ps.list_stride = std::min<size_t>(nn, 125) * pr.h_idx[1].size() + 1024;
+                        CUDA_TRY(dalloc(&ps.d_pair_list, (size_t)p->B * ps.list_stride));
+                        CUDA_TRY(dalloc(&ps.d_list_hdr, (size_t)p->B * cap));
+                        CUDA_TRY(dalloc(&ps.d_list_cursor, p->B));
+                    }
                     CUDA_TRY(dalloc(&ps.d_frame_bins, (size_t)p->B * (MDGPU_DIST_BINS + 1)));   // + one work counter per frame (k_rdf_pairs_v2)
                 } else if (pr.op == MDGPU_OP_SDF) {
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * (pr.n_struct + 1) * pr.struct_size));
@@ -463,6 +474,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.min_cutoff = pr.cutoff_min > 1e-3f ? pr.cutoff_min : 1e-3f;                 // :5269
             a.min_r2 = a.min_cutoff * a.min_cutoff;                                       // rdf_cb :5233
             a.frame_bins = ps.d_frame_bins; a.frame0 = frame0;
+            a.pair_list = ps.d_pair_list; a.list_hdr = ps.d_list_hdr; a.list_cursor = ps.d_list_cursor; a.list_stride = ps.list_stride; a.hdr_stride = p->cell_cap; a.err = s.d_err;
             a.excl_off = pr.n_struct ? pr.d_soff : nullptr; a.excl_idx = pr.n_struct ? pr.d_idx[0] : nullptr;   // md_bitfield_test_bit(&masks[i], j) :5252
             a.symmetric = (!pr.n_struct && pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
             a.acc = pr.d_acc; a.frame_total = pr.d_frame_total; a.frame_min = pr.d_frame_min; a.frame_max = pr.d_frame_max; a.keep = pr.d_keep;
