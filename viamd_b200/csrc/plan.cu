@@ -92,10 +92,16 @@ struct Slot {
 // XTC input stage: compressed bytes + scan records of XTC_SUPER batches, scanned by ONE launch on the stage's own stream. The walk over a
 // frame's stream is a latency-bound serial chain (one warp per frame), so its throughput comes from scanning many frames at once and from
 // running two super-batches ahead of the expand + property kernels that consume it.
-constexpr uint32_t XTC_SUPER = 2;   // 2 scan warps per SM: with more, their registers take the third CTA slot of the pair kernel running on another stream
+constexpr uint32_t XTC_SUPER_MAX = 8;
+static uint32_t xtc_super() {   // batches per scan stage; MDGPU_XTC_SUPER overrides (tuning)
+    static const uint32_t v = []() { const char* e = getenv("MDGPU_XTC_SUPER"); const long n = e ? atol(e) : 2; return (uint32_t)std::min<long>(std::max<long>(n, 1), XTC_SUPER_MAX); }();
+    return v;
+}
+#define XTC_SUPER xtc_super()
+
 constexpr uint32_t XTC_STAGES = 3;   // the scan of super-batch k+2 is in flight while the batches of k are expanded and evaluated
 struct XtcStage {
-    cudaStream_t stream = nullptr; cudaEvent_t ready = nullptr; cudaEvent_t consumed[XTC_SUPER] = {}; uint32_t n_consumed = 0;
+    cudaStream_t stream = nullptr; cudaEvent_t ready = nullptr; cudaEvent_t consumed[XTC_SUPER_MAX] = {}; uint32_t n_consumed = 0;
     uint8_t* d_blob = nullptr; size_t cap = 0; unsigned long long* d_off = nullptr; unsigned long long* h_off = nullptr;
     XtcFrameInfo* d_info = nullptr; uint2* d_rec = nullptr; uint16_t* d_state = nullptr;
 };
