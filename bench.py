@@ -340,7 +340,8 @@ def main():
                          "algorithmic_bytes_per_launch": algo_bytes_per_frame * frames_per_launch,
                          "note": "k_rdf_pairs is FP32-ALU/shared-atomic bound, not DRAM bound (SURVEY.md §7): see alu",
                          "kernel_share_of_step": (k_ms / max(ms_dev, 1e-9)),
-                         "alu": {"pair_tests_per_s": pair_tests_per_frame * frames_per_launch / max(avg_launch_s, 1e-12),
+                         "alu": {"pair_tests_definition": "the reference's enumeration (refs x 27 neighbour cells x mean cell population); tests avoided by the symmetric mode and the exact cull count as done",
+                                 "pair_tests_per_s": pair_tests_per_frame * frames_per_launch / max(avg_launch_s, 1e-12),
                                  "avg_launch_ms": avg_launch_s * 1e3, "launches_timed": k_n}},
         }
         if e2e:
