@@ -43,23 +43,52 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). In-process NVML (pynvml) when available:
+    spawning nvidia-smi several times a second on an 8-GPU box perturbs the driver and slowed the sampled rank; nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.idx, self.rows, self.stop_ev, self.th = gpu_index, [], threading.Event(), None
+        self.nv = None; self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            phys = self.idx
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try: phys = int(vis.split(",")[self.idx])
+                except Exception: phys = self.idx
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys); self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _sample_nvml(self):
+        nv = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM); mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        try: r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception: r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        def bit(name_new, name_old):
+            m = getattr(nv, name_new, None) or getattr(nv, name_old, 0)
+            return "Active" if (r & m) else "Not Active"
+        self.rows.append([str(self.idx), str(sm), str(mx), "0",
+                          bit("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                          bit("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                          bit("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                          bit("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")])
 
     def _run(self):
         while not self.stop_ev.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nv is not None: self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop_ev.wait(0.2)
+            self.stop_ev.wait(0.05 if self.nv is not None else 0.5)
 
     def start(self):
         self.th = threading.Thread(target=self._run, daemon=True); self.th.start()
@@ -75,7 +104,8 @@ class ClockSampler:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows),
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def measured_peaks():
