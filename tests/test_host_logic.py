@@ -136,3 +136,23 @@ def test_rdf_weights_python_matches_reference():
     for key, lo, hi in (("r", 0.0, 6.0), ("rh", 1.5, 6.0)):
         tot = int(g[f"{key}__pf"][3, :1024].sum())
         assert np.array_equal(rdf_weights(tot, lo, hi), g[f"{key}__pf"][3, 1024:])
+
+
+def test_xtc_frame_offsets_host_side(vb):
+    """mdgpu_xtc_frame_offsets (md_xtc_read_frame_offsets_and_times md_xtc.c:436-570) runs on the host: the product's scan of the golden XTC
+    byte streams agrees with the oracle's and ends at the file size; a truncated file yields the complete frames only; garbage is refused."""
+    import numpy as np
+    import oracle_lib as O
+    from helpers import load_golden
+    g = load_golden("xtc_cases.npz")
+    for case in ("water6", "tric6", "water16", "small5", "wide12", "huge12", "lowprec"):
+        blob = g[case + "__xtc"]
+        offs, na = vb.xtc_frame_offsets(blob)
+        assert na == int(g[case + "__na"]) and int(offs[-1]) == blob.size
+        assert np.array_equal(offs.astype(np.int64), O.xtc_frame_offsets(blob))
+        assert len(offs) - 1 == len(g[case + "__cells"])
+    blob = g["water6__xtc"]; full, _ = vb.xtc_frame_offsets(blob)
+    cut, _ = vb.xtc_frame_offsets(blob[: int(full[2]) + 100])          # third frame incomplete
+    assert list(cut) == list(full[:3])
+    with pytest.raises(vb.MdgpuError):
+        vb.xtc_frame_offsets(np.zeros(200, np.uint8))
