@@ -171,6 +171,9 @@ int mdgpu_plan_clear(mdgpu_plan* plan);
  * XDR guarantees). The compressed bytes cross PCIe and are expanded on the device with the reader's arithmetic (coordinates in
  * Angstrom = int * (10 / precision), unit cell from the box matrix * 10); results are those of evaluating the decoded frames. */
 int mdgpu_eval_xtc_frames(mdgpu_plan* plan, const uint8_t* h_blob, const uint64_t* frame_offsets, uint32_t frame_beg, uint32_t count);
+/* The same from a file: reads `path` into pinned memory, finds the frame starts, takes frame 0 as the initial configuration if none was set
+ * (md_script.c:5808), evaluates frames [frame_beg, frame_end) and waits for them. */
+int mdgpu_eval_xtc_file(mdgpu_plan* plan, const char* path, uint32_t frame_beg, uint32_t frame_end);
 /* Frame starts of an XTC file image: offsets[0..n] (offsets[n] = end of the last complete frame), n and the atom count returned. */
 int mdgpu_xtc_frame_offsets(const uint8_t* file, size_t nbytes, uint64_t* offsets, size_t capacity, size_t* num_frames, size_t* num_atoms);
 /* The same decode without a plan: h_xyz[count][3][num_atoms], optional cells / steps / times per frame. */

@@ -485,3 +485,18 @@ def test_xtc_input_gives_the_results_of_the_decoded_frames():
         plan.close()
     for a, b in zip(*res): assert np.array_equal(a, b)
     assert res[0][0].sum() > 0 and res[0][1].sum() > 0
+
+
+def test_xtc_file_input(tmp_path):
+    """mdgpu_eval_xtc_file: the bytes of an .xtc file on disk -> results; frame 0 becomes the initial configuration when none was set."""
+    vb = _vb(); g = load_golden("xtc_cases.npz"); w = load_golden("water6.npz"); s = golden_system(w)
+    path = str(tmp_path / "w6.xtc"); g["water6__xtc"].tofile(path)
+    sysm = vb_system(s); F = len(g["water6__cells"])
+    src = "r = rdf(element('O'), element('O'), 6.0); v = sdf(residue(1:20), element('O'), 5.0); d = distance(1,10);"
+    frames = g["water6__frames"]; cells = [vb_cell(g["water6__cells"][f], g["water6__flags"][f]) for f in range(F)]
+    a = vb.Plan(sysm, vb.compile_script(src, sysm), F, batch_frames=3); a.eval_xtc_file(path, 0, F)
+    b = vb.Plan(sysm, vb.compile_script(src, sysm), F, batch_frames=3); b.set_initial_frame(*frames[0], cells[0]); b.eval_host_frames(frames, cells, 0)
+    for key in ("r", "v"): assert np.array_equal(a.counts(key), b.counts(key)) and a.counts(key).sum() > 0
+    assert np.array_equal(a.property_data("d").values, b.property_data("d").values) and a.frame_mask().all()
+    with pytest.raises(vb.MdgpuError): a.eval_xtc_file(str(tmp_path / "missing.xtc"), 0, 1)
+    a.close(); b.close()

@@ -412,6 +412,11 @@ class Plan:
         lib().mdgpu_eval_xtc_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         _check(lib().mdgpu_eval_xtc_frames(self._h, blob.ctypes.data, offsets.ctypes.data, frame_beg, len(offsets) - 1))
 
+    def eval_xtc_file(self, path: str, frame_beg: int, frame_end: int):
+        """evaluate frames [frame_beg, frame_end) of an .xtc file (decoded on the device)"""
+        lib().mdgpu_eval_xtc_file.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32]
+        _check(lib().mdgpu_eval_xtc_file(self._h, path.encode(), frame_beg, frame_end))
+
     def eval_xtc_ptr(self, blob_ptr: int, offsets: np.ndarray, frame_beg: int = 0):
         """as eval_xtc_frames, the bytes given as a raw host pointer (e.g. pinned memory)"""
         offsets = np.ascontiguousarray(offsets, np.uint64)

@@ -711,6 +711,37 @@ int mdgpu_eval_xtc_frames(mdgpu_plan* p, const uint8_t* h_blob, const uint64_t* 
     return 0;
 }
 
+// whole-file convenience: read (a range of) an .xtc file into pinned memory, find the frame starts, evaluate frames [frame_beg, frame_end)
+int mdgpu_eval_xtc_file(mdgpu_plan* p, const char* path, uint32_t frame_beg, uint32_t frame_end) {
+    if (!p || !path) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_eval_xtc_file: null argument");
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Failed to open file '%s'", path);
+    fseek(fp, 0, SEEK_END); const long fsz = ftell(fp); fseek(fp, 0, SEEK_SET);
+    if (fsz <= 0) { fclose(fp); return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Failed extract filesize"); }
+    CUDA_TRY(cudaSetDevice(p->device));
+    uint8_t* buf = nullptr;
+    if (cudaMallocHost((void**)&buf, (size_t)fsz) != cudaSuccess) { fclose(fp); return fail(MDGPU_ERR_CUDA, "pinned allocation of %ld bytes failed", fsz); }
+    const size_t got = fread(buf, 1, (size_t)fsz, fp); fclose(fp);
+    int rc = 0;
+    std::vector<uint64_t> offs((size_t)fsz / 56 + 2);
+    size_t nf = 0, na = 0;
+    do {
+        if (got != (size_t)fsz) { rc = fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Failed to read frame data from file, expected %ld bytes, got %zu bytes", fsz, got); break; }
+        rc = mdgpu_xtc_frame_offsets(buf, (size_t)fsz, offs.data(), offs.size(), &nf, &na); if (rc) break;
+        if (na != p->num_atoms) { rc = fail(MDGPU_ERR_INVALID_ARG, "XTC: Number of atoms in frame header does not match expected number of atoms"); break; }
+        if (frame_beg > frame_end || frame_end > nf) { rc = fail(MDGPU_ERR_INVALID_ARG, "Script eval: Invalid frame range"); break; }
+        if (!p->have_init && nf) {   // initial configuration = frame 0 of the trajectory (md_script.c:5808)
+            std::vector<float> f0(3 * na); mdgpu_unitcell_t c0{};
+            rc = mdgpu_xtc_decode_frames(p->device, buf, offs.data(), 1, na, f0.data(), &c0, nullptr, nullptr); if (rc) break;
+            rc = mdgpu_plan_set_initial_frame(p, f0.data(), f0.data() + na, f0.data() + 2 * na, &c0); if (rc) break;
+        }
+        rc = mdgpu_eval_xtc_frames(p, buf, offs.data() + frame_beg, frame_beg, frame_end - frame_beg); if (rc) break;
+        rc = mdgpu_plan_sync(p);   // the pinned file image must outlive the copies
+    } while (false);
+    cudaFreeHost(buf);
+    return rc;
+}
+
 // frame starts of an XTC file image (md_xtc_read_frame_offsets_and_times md_xtc.c:436-570): offsets[0..n], offsets[n] = end of the last frame
 int mdgpu_xtc_frame_offsets(const uint8_t* file, size_t nbytes, uint64_t* offsets, size_t capacity, size_t* num_frames, size_t* num_atoms) {
     if (!file || !offsets || capacity < 2) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_xtc_frame_offsets: invalid argument");
