@@ -746,6 +746,47 @@ uint64_t mdo_sdf_frame(const float* x, const float* y, const float* z,
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * rmsd(selection): _rmsd md_script_functions.inl:4287-4345. Both the INITIAL frame's and the current frame's atoms of the (flattened)
+ * selection are wrapped into the cell about its centre (md_util_pbc_vec4 -> pbc_ortho_vec4 md_util.c:8506-8512), unwrapped along the bonds
+ * (the same global-index quirk as in _sdf), centred on their plain centres of mass, optimally rotated (Kabsch through svd3) and compared:
+ * sqrt(sum w |u - R v|^2 / sum w) in double (md_util_rmsd_compute_vec4 :9038-9068). Orthorhombic cells (the triclinic wrap is not restated).
+ */
+double mdo_rmsd_frame(const float* x, const float* y, const float* z, const float* init_x, const float* init_y, const float* init_z,
+                      const float* mass, const int32_t* idx, size_t n, const uint32_t* conn_off, const int32_t* conn_idx, size_t conn_off_count,
+                      const mdo_unitcell_t* cell) {
+    if (n == 0) return 0.0;
+    v4* p[2] = { malloc(sizeof(v4) * n), malloc(sizeof(v4) * n) };
+    for (size_t k = 0; k < n; ++k) {
+        const int32_t a = idx[k]; const float w = mass ? mass[a] : 1.0f;
+        p[0][k][0] = init_x[a]; p[0][k][1] = init_y[a]; p[0][k][2] = init_z[a]; p[0][k][3] = w;
+        p[1][k][0] = x[a];      p[1][k][1] = y[a];      p[1][k][2] = z[a];      p[1][k][3] = w;
+    }
+    float com[2][3];
+    for (int s = 0; s < 2; ++s) {
+        if (cell->flags & MDO_CELL_ORTHO) {   /* pbc_ortho_vec4: deperiodize about ext * 0.5 */
+            const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
+            for (size_t k = 0; k < n; ++k) for (int a = 0; a < 3; ++a) p[s][k][a] = deperiodize1(p[s][k][a], ext[a] * 0.5f, ext[a]);
+        }
+        unwrap_vec4(p[s], n, conn_off, conn_idx, conn_off_count, cell);
+        com_v4(com[s], p[s], n);
+    }
+    const m3 R = m3_extract_rotation(cross_covariance_v4(p[0], p[1], n, com[0], com[1]));   /* mat3_optimal_rotation_vec4 core/md_vec_math.c:337 */
+    double d_sum = 0.0, w_sum = 0.0;
+    for (size_t k = 0; k < n; ++k) {
+        const float u[3] = { p[0][k][0] - com[0][0], p[0][k][1] - com[0][1], p[0][k][2] - com[0][2] };
+        const float v[3] = { p[1][k][0] - com[1][0], p[1][k][1] - com[1][1], p[1][k][2] - com[1][2] };
+        float vp[3];   /* mat3_mul_vec3 core/md_vec_math.h:1623: col-major, (x*c0 + y*c1) + z*c2 */
+        for (int r = 0; r < 3; ++r) vp[r] = R.e[0][r] * v[0] + R.e[1][r] * v[1] + R.e[2][r] * v[2];
+        const float d[3] = { u[0] - vp[0], u[1] - vp[1], u[2] - vp[2] };
+        const float w = (p[0][k][3] + p[1][k][3]) * 0.5f;
+        const float dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        d_sum += w * dd; w_sum += w;
+    }
+    free(p[0]); free(p[1]);
+    return sqrt(d_sum / w_sum);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * density_x/_y/_z: _internal_density (md_script_functions.inl:4825-4947), axis in 0..2
  */
 void mdo_density_frame(const float* x, const float* y, const float* z, const float* mass,

@@ -75,7 +75,7 @@ def water6(tmp):
               "rc = rdf(residue(1:20), element('O'), 5.0); "
               "dc = distance(residue(1), residue(5)); ac = angle(residue(1), residue(2), residue(3)); "
               "tc = dihedral(residue(1), residue(2), residue(3), residue(4)); dg = distance(atom(1:30), atom(100:151)); dm = distance(atom(1:30), 200); "
-              "dmn = distance_min(residue(1), atom(100:648)); dmx = distance_max(atom(1:30), atom(100:151)); dmh = distance_min(element('H'), atom(300:400));")
+              "dmn = distance_min(residue(1), atom(100:648)); dmx = distance_max(atom(1:30), atom(100:151)); dmh = distance_min(element('H'), atom(300:400)); rm = rmsd(residue(1:10));")
     o = os.path.join(tmp, "w.out"); si = os.path.join(tmp, "w.sys")
     run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
     run(HARNESS, "sysinfo", "--sys", gro, "--out", si)
@@ -91,7 +91,7 @@ def ala50(tmp):
     run(HARNESS, "dumptraj", "--sys", pdb, "--traj", "sys", "--frames", f"0:{F}", "--out", raw)
     script = ("d = distance(1,10); rc = rdf(element('C'), element('O'), 10.0); dz = density_z(element('C')); "
               "a = angle(1,5,9); t = dihedral(5,7,9,15); rr = rdf(residue(1:3), element('H'), 8.0); "
-              "dr = distance(residue(1), residue(15)); ar = angle(residue(1), residue(7), residue(15)); tr = dihedral(residue(1), residue(5), 100, residue(15));")
+              "dr = distance(residue(1), residue(15)); ar = angle(residue(1), residue(7), residue(15)); tr = dihedral(residue(1), residue(5), 100, residue(15)); rma = rmsd(residue(1:15));")
     # evaluate on the dumped frames so that frame 0 (initial configuration) is identical
     run(HARNESS, "eval", "--sys", pdb, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
     run(HARNESS, "sysinfo", "--sys", pdb, "--out", si)

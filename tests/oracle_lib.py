@@ -181,3 +181,11 @@ def xtc_decode_frame(blob, beg, end, num_atoms):
 def min_distance(x, y, z, a, b, cell):
     x, y, z = _f32(x), _f32(y), _f32(z); a, b = _i32(a), _i32(b)
     return np.float32(lib().mdo_min_distance(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(a, C.c_int32), C.c_size_t(len(a)), _p(b, C.c_int32), C.c_size_t(len(b)), C.byref(cell)))
+
+
+def rmsd_frame(x, y, z, init_xyz, mass, idx, conn_off, conn_idx, cell):
+    x, y, z, mass = _f32(x), _f32(y), _f32(z), _f32(mass); ix, iy, iz = _f32(init_xyz[0]), _f32(init_xyz[1]), _f32(init_xyz[2])
+    idx = _i32(idx); co = np.ascontiguousarray(conn_off, np.uint32); ci = _i32(conn_idx)
+    lib().mdo_rmsd_frame.restype = C.c_double
+    return np.float32(lib().mdo_rmsd_frame(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(ix, C.c_float), _p(iy, C.c_float), _p(iz, C.c_float),
+                                           _p(mass, C.c_float), _p(idx, C.c_int32), C.c_size_t(len(idx)), _p(co, C.c_uint32), _p(ci, C.c_int32), C.c_size_t(len(co)), C.byref(cell)))
