@@ -36,6 +36,8 @@ METRIC = "frames/sec RDF+SDF eval, 100k-atom synthetic traj"
 UNIT = "frames/s"
 SCRIPT = "r = rdf(element('O'), element('O'), 10.0); v = sdf(residue(1:1000), element('O'), 10.0);"
 WATER_N, WATER_SEED = 32, 1234
+WORKLOAD = (f"BASELINE configs[1]+[2] on one trajectory: synthetic water n={WATER_N} ({3 * WATER_N ** 3} atoms, {WATER_N ** 3} O, "
+            f"L={WATER_N * 3.104:.3f} A), script: {SCRIPT}")
 
 
 def dist_env():
@@ -188,7 +190,7 @@ def impl_reference(args):
     sample = max(2 * threads, 16)
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic water n={WATER_N} (98304 atoms), script: {SCRIPT}", "frames_per_step": sample, "threads": threads}}
+            "config": {"workload": WORKLOAD, "frames_per_step": sample, "threads": threads}}
     if os.path.exists(harness_path("fast")):
         for _ in range(args.warmup):
             run_reference_sample(sample, threads)
@@ -358,7 +360,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[1]+[2] on one trajectory: synthetic water n={n} ({na} atoms, 32768 O, L={L:.3f} A), script: {SCRIPT}",
+            "config": {"workload": WORKLOAD,
                        "frames_per_step": FPS, "batch_frames": B, "parallelism": f"frame-sharded x{world}",
                        "l2_policy": "every step reads fresh frames; one step's input (%.2f GB) exceeds the 126 MB L2" % (FPS * fstride * 4 / 1e9)},
             "gpu_launches": launches,
