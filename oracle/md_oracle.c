@@ -746,6 +746,30 @@ uint64_t mdo_sdf_frame(const float* x, const float* y, const float* z,
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * within(radius, selection): _within_expl_flt md_script_functions.inl:2485-2533 — every atom of the system within `radius` of any atom of
+ * the selection, the selection's own atoms removed (:2521-2525). The system-wide cell list comes from get_spatial_acc (:734-753): cell
+ * extent ceil(radius / 6) * 6; the positions are an AoS stream (coordinate_extract of one bitfield). out_mask: one byte per atom.
+ * Returns the number of atoms set. Groundwork for dynamic selections: the GPU path does not lower them yet.
+ */
+static void within_pair(uint32_t i, uint32_t j, float d2, void* user) { (void)i; (void)d2; ((uint8_t*)user)[j] = 1; }   /* within_float_cb :2478 */
+size_t mdo_within(const float* x, const float* y, const float* z, size_t num_atoms, const int32_t* sel, size_t n_sel, float radius,
+                  const mdo_unitcell_t* cell, uint8_t* out_mask) {
+    memset(out_mask, 0, num_atoms);
+    if (n_sel == 0 || num_atoms == 0) return 0;
+    const double cell_ext = ceil((double)radius / 6.0) * 6.0;
+    stream_t all = { x, y, z, NULL, NULL, num_atoms };
+    acc_t acc; acc_init(&acc, &all, cell_ext, cell, false);
+    float* pos = malloc(sizeof(float) * 3 * n_sel);
+    for (size_t k = 0; k < n_sel; ++k) { pos[3 * k] = x[sel[k]]; pos[3 * k + 1] = y[sel[k]]; pos[3 * k + 2] = z[sel[k]]; }
+    stream_t ext = { x, y, z, NULL, pos, n_sel };
+    acc_ext_pairs(&acc, &ext, (double)radius, false, within_pair, out_mask);
+    for (size_t k = 0; k < n_sel; ++k) out_mask[sel[k]] = 0;
+    size_t n = 0; for (size_t a = 0; a < num_atoms; ++a) n += out_mask[a];
+    acc_free(&acc); free(pos);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * rmsd(selection): _rmsd md_script_functions.inl:4287-4345. Both the INITIAL frame's and the current frame's atoms of the (flattened)
  * selection are wrapped into the cell about its centre (md_util_pbc_vec4 -> pbc_ortho_vec4 md_util.c:8506-8512), unwrapped along the bonds
  * (the same global-index quirk as in _sdf), centred on their plain centres of mass, optimally rotated (Kabsch through svd3) and compared:

@@ -75,7 +75,8 @@ def water6(tmp):
               "rc = rdf(residue(1:20), element('O'), 5.0); "
               "dc = distance(residue(1), residue(5)); ac = angle(residue(1), residue(2), residue(3)); "
               "tc = dihedral(residue(1), residue(2), residue(3), residue(4)); dg = distance(atom(1:30), atom(100:151)); dm = distance(atom(1:30), 200); "
-              "dmn = distance_min(residue(1), atom(100:648)); dmx = distance_max(atom(1:30), atom(100:151)); dmh = distance_min(element('H'), atom(300:400)); rm = rmsd(residue(1:10));")
+              "dmn = distance_min(residue(1), atom(100:648)); dmx = distance_max(atom(1:30), atom(100:151)); dmh = distance_min(element('H'), atom(300:400)); rm = rmsd(residue(1:10)); "
+              "cw = count(within(4.0, residue(1))); cw2 = count(within(7.5, atom(10:12))); rw = rdf(within(4.0, residue(1)), element('O'), 6.0);")
     o = os.path.join(tmp, "w.out"); si = os.path.join(tmp, "w.sys")
     run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
     run(HARNESS, "sysinfo", "--sys", gro, "--out", si)
