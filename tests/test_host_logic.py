@@ -63,6 +63,15 @@ def test_script_lowering(vb):
     assert rr.cutoff_min == 2.0 and rr.cutoff_max == 8.0 and len(rr.idx[1]) == 128
     with pytest.raises(vb.ScriptError):
         vb.compile_script("x = rmsd(all);", s)
+    # array-of-selections reference -> centre-of-mass groups with offsets; selection arguments of the temporals -> com_args; pair minimum
+    rc, dc, dm, dmin = vb.compile_script("rc = rdf(residue(2:5), element('O'), 5.0); dc = distance(residue(1), residue(3)); "
+                                         "dm = distance(atom(1:6), 10); dmin = distance_min(residue(1), element('H'));", s)
+    assert rc.op == vb.OP_RDF and rc.num_structures == 4 and list(rc.structure_offsets) == [0, 3, 6, 9, 12] and np.array_equal(rc.idx[0], np.arange(3, 15))
+    assert dc.op == vb.OP_DISTANCE and dc.com_args == 3 and list(dc.idx[0]) == [0, 1, 2] and list(dc.idx[1]) == [6, 7, 8]
+    assert dm.com_args == 1 and list(dm.idx[0]) == [0, 1, 2, 3, 4, 5] and list(dm.idx[1]) == [9]
+    assert dmin.op == vb.OP_DISTANCE_MIN and list(dmin.idx[0]) == [0, 1, 2] and len(dmin.idx[1]) == 128
+    single = vb.compile_script("r1 = rdf(residue(2), element('O'), 5.0);", s)[0]       # one selection: plain atom references, no groups
+    assert single.num_structures == 0 and list(single.idx[0]) == [3, 4, 5]
 
 
 def test_synth_determinism_and_tool_agreement(vb, tmp_path):
