@@ -165,3 +165,18 @@ def test_xtc_frame_offsets_host_side(vb):
     assert list(cut) == list(full[:3])
     with pytest.raises(vb.MdgpuError):
         vb.xtc_frame_offsets(np.zeros(200, np.uint8))
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` prints exactly one JSON line on stdout with the contract's keys (runs the reference CPU harness when
+    oracle/_ref is present, the oracle port otherwise): a bounded sample, so this stays a few seconds."""
+    import json, subprocess, sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-500:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "frames/s" and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]

@@ -860,7 +860,7 @@ int mdgpu_plan_sync(mdgpu_plan* p) {
     CUDA_TRY(cudaDeviceSynchronize());
     for (auto& s : p->slots) {
         int err = 0; CUDA_TRY(cudaMemcpy(&err, s.d_err, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) { cudaMemset(s.d_err, 0, sizeof(int)); return fail(err, err == MDGPU_ERR_CAPACITY ? "a frame needs more cells than the plan's cell capacity (%u); raise mdgpu_plan_options_t.cell_capacity" : (err == MDGPU_ERR_FRAME_SOURCE ? "XTC: Failed to decode frame data (%d)" : "device-side error %d"), err == MDGPU_ERR_CAPACITY ? p->cell_cap : (uint32_t)err); }
+        if (err) { cudaMemset(s.d_err, 0, sizeof(int)); return fail(err, err == MDGPU_ERR_CAPACITY ? "a frame needs more cells (or, with a shrinking cell, more rdf candidate-list space) than the plan reserved from its first frame (cell capacity %u); raise mdgpu_plan_options_t.cell_capacity" : (err == MDGPU_ERR_FRAME_SOURCE ? "XTC: Failed to decode frame data (%d)" : "device-side error %d"), err == MDGPU_ERR_CAPACITY ? p->cell_cap : (uint32_t)err); }
     }
     for (auto& t : p->timed) { float ms = 0; if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { p->timed_ms[t.kind] += ms; p->timed_n[t.kind] += 1; } cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     p->timed.clear();
