@@ -746,6 +746,22 @@ uint64_t mdo_sdf_frame(const float* x, const float* y, const float* z,
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Cell-grid geometry of md_spatial_acc_init (core/md_spatial_acc.c:155-438) + the neighbour reach of the pair query (:1656-1662), exported so
+ * that the product's host-side geometry code (mdgpu_debug_frame_geom, the same code its device kernels run) can be checked without a GPU.
+ * out_i[7] = cell_dim[3], ncell[3], num_cells; out_f[10] = G00, G11, G22, H01, H02, H12, r2, origin[3].
+ */
+void mdo_debug_geom(const float* x, const float* y, const float* z, size_t n, const mdo_unitcell_t* cell, double cell_ext, double cutoff,
+                    int32_t* out_i, float* out_f) {
+    stream_t st = { x, y, z, NULL, NULL, n };
+    acc_t acc; acc_init(&acc, &st, cell_ext, cell, false);
+    for (int k = 0; k < 3; ++k) { out_i[k] = (int32_t)acc.cell_dim[k]; out_i[3 + k] = (int32_t)ceil(cutoff * (double)acc.inv_cell_ext[k] * acc.cell_dim[k]); }
+    out_i[6] = (int32_t)acc.num_cells;
+    out_f[0] = acc.G00; out_f[1] = acc.G11; out_f[2] = acc.G22; out_f[3] = acc.H01; out_f[4] = acc.H02; out_f[5] = acc.H12; out_f[6] = calc_r2(cutoff);
+    for (int k = 0; k < 3; ++k) out_f[7 + k] = acc.origin[k];
+    acc_free(&acc);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * within(radius, selection): _within_expl_flt md_script_functions.inl:2485-2533 — every atom of the system within `radius` of any atom of
  * the selection, the selection's own atoms removed (:2521-2525). The system-wide cell list comes from get_spatial_acc (:734-753): cell
  * extent ceil(radius / 6) * 6; the positions are an AoS stream (coordinate_extract of one bitfield). out_mask: one byte per atom.

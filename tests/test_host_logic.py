@@ -180,3 +180,37 @@ def test_bench_reference_arm_json_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "frames/s" and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_frame_geometry_matches_the_oracle(vb):
+    """The product's per-frame cell-grid geometry (compute_frame_geom: the code its device kernels run, evaluated on the host through
+    mdgpu_debug_frame_geom) against the oracle's md_spatial_acc_init restatement on random cells: orthorhombic, anisotropic, one or more
+    axes non-periodic (grid fitted to the points' bounding box), triclinic. Grid dimensions, neighbour reach, metric and r2 bit for bit."""
+    import numpy as np
+    import oracle_lib as O
+    L = vb.lib()
+    L.mdgpu_debug_frame_geom.argtypes = [C.POINTER(vb.UnitCell), C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    for case in range(300):
+        ext = rng.uniform(8.0, 120.0, 3); kind = rng.integers(0, 4)
+        flags = vb.CELL_ORTHO | vb.CELL_PBC_ALL; xy = xz = yz = 0.0
+        if kind == 1: flags &= ~int(rng.choice([vb.CELL_PBC_X, vb.CELL_PBC_Y, vb.CELL_PBC_Z, vb.CELL_PBC_X | vb.CELL_PBC_Z, vb.CELL_PBC_ALL]))
+        if kind == 2: flags = vb.CELL_TRICLINIC | vb.CELL_PBC_ALL; xy, xz, yz = rng.uniform(-0.3, 0.3, 3) * ext.min()
+        cutoff = float(rng.uniform(2.0, 0.7 * ext.min())); cell_ext = cutoff if rng.random() < 0.7 else float(rng.uniform(3.0, 12.0))
+        n = 200
+        pts = (rng.random((3, n)) * ext[:, None] * rng.uniform(0.5, 1.0) + rng.uniform(-5, 5, 3)[:, None]).astype(np.float32)
+        cell = vb.UnitCell(float(ext[0]), float(xy), float(xz), float(ext[1]), float(yz), float(ext[2]), int(flags))
+        ocell = O.UnitCell.from_params(ext[0], xy, xz, ext[1], yz, ext[2], int(flags))
+        # the reference starts its bounding box from {0} (md_spatial_acc.c:204): the origin is always inside; k_aabb does the same on the device
+        aabb = np.concatenate([np.minimum(pts.min(axis=1), 0.0), np.maximum(pts.max(axis=1), 0.0)]).astype(np.float32)
+        gi = np.zeros(13, np.int32); gf = np.zeros(7, np.float32)
+        assert L.mdgpu_debug_frame_geom(C.byref(cell), cell_ext, cutoff, aabb.ctypes.data, gi.ctypes.data, gf.ctypes.data) == 0
+        oi = np.zeros(7, np.int32); of = np.zeros(10, np.float32)
+        x, y, z = (np.ascontiguousarray(p) for p in pts)
+        O.lib().mdo_debug_geom(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), C.c_size_t(n), C.byref(ocell),
+                               C.c_double(cell_ext), C.c_double(cutoff), oi.ctypes.data_as(C.c_void_p), of.ctypes.data_as(C.c_void_p))
+        tag = (case, int(flags), cutoff, cell_ext, list(ext))
+        assert list(gi[:3]) == list(oi[:3]), ("cdim", tag, gi[:3], oi[:3])
+        assert list(gi[3:6]) == list(oi[3:6]), ("ncell", tag, gi[3:6], oi[3:6])
+        assert np.array_equal(gf[:7], of[:7]), ("metric/r2", tag, gf, of[:7])
+        assert (gi[12] > 0) == all(2 * int(v) + 1 <= 5 for v in oi[3:6]), ("valid", tag, gi[12], oi[3:6])
