@@ -14,6 +14,29 @@
  * This file is written against the reference's private API on purpose and contains no reference code.
  */
 #include <mdgpu.h>
+#include <stddef.h>
+
+/* The C ABI passes the reference's own structs through casts (md_unitcell_t, the frame header, the trajectory interfaces): pin their
+ * layouts against this mdlib at compile time, so a change upstream breaks the build here instead of corrupting frames at run time. */
+_Static_assert(sizeof(mdgpu_unitcell_t) == sizeof(md_unitcell_t), "md_unitcell_t layout");
+_Static_assert(offsetof(mdgpu_unitcell_t, x) == offsetof(md_unitcell_t, x) && offsetof(mdgpu_unitcell_t, xy) == offsetof(md_unitcell_t, xy) &&
+               offsetof(mdgpu_unitcell_t, xz) == offsetof(md_unitcell_t, xz) && offsetof(mdgpu_unitcell_t, y) == offsetof(md_unitcell_t, y) &&
+               offsetof(mdgpu_unitcell_t, yz) == offsetof(md_unitcell_t, yz) && offsetof(mdgpu_unitcell_t, z) == offsetof(md_unitcell_t, z) &&
+               offsetof(mdgpu_unitcell_t, flags) == offsetof(md_unitcell_t, flags), "md_unitcell_t fields");
+_Static_assert(MDGPU_CELL_ORTHO == MD_UNITCELL_ORTHO && MDGPU_CELL_TRICLINIC == MD_UNITCELL_TRICLINIC && MDGPU_CELL_PBC_X == MD_UNITCELL_PBC_X &&
+               MDGPU_CELL_PBC_Y == MD_UNITCELL_PBC_Y && MDGPU_CELL_PBC_Z == MD_UNITCELL_PBC_Z, "md_unitcell_flags_t values");
+_Static_assert(sizeof(mdgpu_frame_header_t) == sizeof(md_trajectory_frame_header_t) &&
+               offsetof(mdgpu_frame_header_t, num_atoms) == offsetof(md_trajectory_frame_header_t, num_atoms) &&
+               offsetof(mdgpu_frame_header_t, index) == offsetof(md_trajectory_frame_header_t, index) &&
+               offsetof(mdgpu_frame_header_t, timestamp) == offsetof(md_trajectory_frame_header_t, timestamp) &&
+               offsetof(mdgpu_frame_header_t, unitcell) == offsetof(md_trajectory_frame_header_t, unitcell), "md_trajectory_frame_header_t layout");
+_Static_assert(sizeof(mdgpu_trajectory_reader_i) == sizeof(md_trajectory_reader_i) && offsetof(mdgpu_trajectory_reader_i, load_frame) == offsetof(md_trajectory_reader_i, load_frame) &&
+               offsetof(mdgpu_trajectory_reader_i, free) == offsetof(md_trajectory_reader_i, free), "md_trajectory_reader_i layout");
+_Static_assert(sizeof(mdgpu_trajectory_i) == sizeof(md_trajectory_i) && offsetof(mdgpu_trajectory_i, get_header) == offsetof(md_trajectory_i, get_header) &&
+               offsetof(mdgpu_trajectory_i, init_reader) == offsetof(md_trajectory_i, init_reader), "md_trajectory_i layout");
+_Static_assert(sizeof(mdgpu_trajectory_header_t) == sizeof(md_trajectory_header_t) && offsetof(mdgpu_trajectory_header_t, num_frames) == offsetof(md_trajectory_header_t, num_frames) &&
+               offsetof(mdgpu_trajectory_header_t, num_atoms) == offsetof(md_trajectory_header_t, num_atoms) &&
+               offsetof(mdgpu_trajectory_header_t, frame_times) == offsetof(md_trajectory_header_t, frame_times), "md_trajectory_header_t layout");
 
 typedef struct md_script_gpu_lowered_t {
     size_t num_props;
