@@ -789,7 +789,8 @@ size_t mdo_within(const float* x, const float* y, const float* z, size_t num_ato
  * rmsd(selection): _rmsd md_script_functions.inl:4287-4345. Both the INITIAL frame's and the current frame's atoms of the (flattened)
  * selection are wrapped into the cell about its centre (md_util_pbc_vec4 -> pbc_ortho_vec4 md_util.c:8506-8512), unwrapped along the bonds
  * (the same global-index quirk as in _sdf), centred on their plain centres of mass, optimally rotated (Kabsch through svd3) and compared:
- * sqrt(sum w |u - R v|^2 / sum w) in double (md_util_rmsd_compute_vec4 :9038-9068). Orthorhombic cells (the triclinic wrap is not restated).
+ * sqrt(sum w |u - R v|^2 / sum w) in double (md_util_rmsd_compute_vec4 :9038-9068). The wrap is md_util_pbc_vec4 (md_util.c:8603): about the box
+ * centre for orthorhombic cells, A * fract(I * r) for triclinic ones.
  */
 double mdo_rmsd_frame(const float* x, const float* y, const float* z, const float* init_x, const float* init_y, const float* init_z,
                       const float* mass, const int32_t* idx, size_t n, const uint32_t* conn_off, const int32_t* conn_idx, size_t conn_off_count,
@@ -806,6 +807,18 @@ double mdo_rmsd_frame(const float* x, const float* y, const float* z, const floa
         if (cell->flags & MDO_CELL_ORTHO) {   /* pbc_ortho_vec4: deperiodize about ext * 0.5 */
             const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
             for (size_t k = 0; k < n; ++k) for (int a = 0; a < 3; ++a) p[s][k][a] = deperiodize1(p[s][k][a], ext[a] * 0.5f, ext[a]);
+        } else if (cell->flags & MDO_CELL_TRICLINIC) {   /* pbc_triclinic_vec4 md_util.c:8554-8574: c = A * fract(I * c) on the periodic axes */
+            double Ad[3][3], Id[3][3]; cell_A(Ad, cell); cell_I(Id, cell);
+            float A[3][3], I[3][3];
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] = (float)Ad[i][j]; I[i][j] = (float)Id[i][j]; }
+            const int pbc[3] = { (cell->flags & MDO_CELL_PBC_X) != 0, (cell->flags & MDO_CELL_PBC_Y) != 0, (cell->flags & MDO_CELL_PBC_Z) != 0 };
+            for (size_t k = 0; k < n; ++k) {
+                const float c[3] = { p[s][k][0], p[s][k][1], p[s][k][2] };
+                float f[3], r[3];   /* linear_combine_3 core/md_vec_math.h:1521: (x*col0 + y*col1) + z*col2 */
+                for (int a = 0; a < 3; ++a) { f[a] = (c[0] * I[0][a] + c[1] * I[1][a]) + c[2] * I[2][a]; f[a] = f[a] - floorf(f[a]); }
+                for (int a = 0; a < 3; ++a) r[a] = (f[0] * A[0][a] + f[1] * A[1][a]) + f[2] * A[2][a];
+                for (int a = 0; a < 3; ++a) if (pbc[a]) p[s][k][a] = r[a];
+            }
         }
         unwrap_vec4(p[s], n, conn_off, conn_idx, conn_off_count, cell);
         com_v4(com[s], p[s], n);

@@ -39,7 +39,7 @@ def main(cases=40, seed=3):
             sdf_ok = (fl & 28) == 28
             script = (f"r = rdf(element('O'), element('O'), {cut}); rh = rdf(element('H'), element('O'), {cmin}:{cut}); rc = rdf(residue(1:{nres}), element('H'), {cut}); "
                       f"dz = density_z(element('O')); dy = density_y(element('H')); d = distance({a1},{a2}); dg = distance(atom({a1}:{a2}), residue(2)); "
-                      f"an = angle({a1},{a1 + 1},{a2}); dmn = distance_min(atom({a1}:{a2}), residue(1)); " + ("" if tri else f"rm = rmsd(residue(1:{nres})); ") + f"cw = count(within({min(cut, 6.0)}, residue(1)));"
+                      f"an = angle({a1},{a1 + 1},{a2}); dmn = distance_min(atom({a1}:{a2}), residue(1)); " + f"rm = rmsd(residue(1:{nres})); " + f"cw = count(within({min(cut, 6.0)}, residue(1)));"
                       + (f" v = sdf(residue(1:{nres}), element('O'), {min(cut, 0.45 * L):.2f});" if sdf_ok else ""))
             p = subprocess.run([HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", out, "--perframe", f"0:{F}", "--full", f"0:{F}"], capture_output=True, text=True)
             if p.returncode != 0: print("reference failed on case", c, script); bad += 1; continue
@@ -65,7 +65,7 @@ def main(cases=40, seed=3):
                 chk(O.distance_args(x, y, zz, s["mass"], A(a1, a2), groups[1], cell) == R["dg"].full[f], "dg", f)
                 chk(np.float32(O.angle(x, y, zz, a1 - 1, a1, a2 - 1)) == R["an"].full[f], "an", f)
                 chk(O.min_distance(x, y, zz, A(a1, a2), groups[0], cell) == R["dmn"].full[f], "dmn", f)
-                if not tri: chk(O.rmsd_frame(x, y, zz, fr2[0], s["mass"], np.concatenate(groups), s["conn_off"], s["conn_idx"], cell) == R["rm"].full[f], "rm", f)
+                chk(O.rmsd_frame(x, y, zz, fr2[0], s["mass"], np.concatenate(groups), s["conn_off"], s["conn_idx"], cell) == R["rm"].full[f], "rm", f)
                 chk(len(O.within(x, y, zz, groups[0], min(cut, 6.0), cell)) == int(R["cw"].full[f]), "cw", f)
                 if sdf_ok:
                     vol, nn = O.sdf_frame(x, y, zz, fr2[0], s["mass"], np.stack(groups), o, s["conn_off"], s["conn_idx"], cell, float(f"{min(cut, 0.45 * L):.2f}"))

@@ -15,6 +15,8 @@ reference's outputs, so the tests need neither the reference nor the harness on 
   membrane6.npz : synthetic coarse-grained membrane (BASELINE config 4 shape at 1728 atoms: 72 lipids x 12 beads + 864 solvent beads,
                cell 48 x 48 x 75), 4 frames: rt = rdf(name('C2*'), name('C2*'), 12.0), dz = density_z(name('C2*')), dall/dxall = density over all atoms
   tric6.npz  : water n=6 sheared into a TRICLINIC cell that changes every frame, 4 frames: rt, rth (min:max), rtc (centre-of-mass references)
+  tric6_rmsd.npz : the tric6 frames again: rmt = rmsd(residue(1:10)), rma = rmsd(atom(100:160)), rmo = rmsd(element('O')) — the triclinic wrap
+               A * fract(I * r) of md_util_pbc_vec4, the triclinic bond-walk unwrap, non-contiguous selections
   xtc_cases.npz : XTC byte streams from the reference's writer + the reference reader's decode of them (see xtc_cases below)
   ala50.npz  : first 50 frames of datasets/1ALA-500.pdb (153 atoms, ortho cell 46.645 x 96.666 x 48.362), config 1:
                d = distance(1,10) (BASELINE config 1), rc = rdf(element('C'), element('O'), 10.0), dz = density_z(element('C')),
@@ -146,6 +148,19 @@ def tric6(tmp):
     np.savez_compressed(os.path.join(HERE, "tric6.npz"), **out)
 
 
+def tric6_rmsd(tmp):
+    """rmsd() in the changing triclinic cell of tric6 (its frames are reused): md_util_pbc_vec4's triclinic wrap + unwrap + Kabsch."""
+    g = np.load(os.path.join(HERE, "tric6.npz")); F = g["frames"].shape[0]
+    gro, raw = os.path.join(tmp, "tr.gro"), os.path.join(tmp, "tr.raw")
+    run(SYNTH, "water-gro", "6", "91", gro); refio.write_raw_traj(raw, g["frames"], g["cells"], g["cell_flags"])
+    script = "rmt = rmsd(residue(1:10)); rma = rmsd(atom(100:160)); rmo = rmsd(element('O'));"
+    o = os.path.join(tmp, "tr.out")
+    run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--full", f"0:{F}")
+    out = dict(script=np.array(script))
+    pack(out, refio.read_refout(o), list(range(F)))
+    np.savez_compressed(os.path.join(HERE, "tric6_rmsd.npz"), **out)
+
+
 def _write_gro(path, n, L):
     with open(path, "w") as f:
         f.write("synthetic\n%d\n" % n)
@@ -195,6 +210,6 @@ def xtc_cases(tmp):
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     with tempfile.TemporaryDirectory() as tmp:
-        water6(tmp); ala50(tmp); membrane6(tmp); tric6(tmp); xtc_cases(tmp)
-    for f in ("water6.npz", "ala50.npz", "membrane6.npz", "tric6.npz", "xtc_cases.npz"):
+        water6(tmp); ala50(tmp); membrane6(tmp); tric6(tmp); tric6_rmsd(tmp); xtc_cases(tmp)
+    for f in ("water6.npz", "ala50.npz", "membrane6.npz", "tric6.npz", "tric6_rmsd.npz", "xtc_cases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
