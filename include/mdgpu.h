@@ -83,7 +83,7 @@ typedef struct mdgpu_trajectory_i {
 typedef struct mdgpu_system_desc_t {
     size_t num_atoms;
     const float* atom_mass;            /* [num_atoms] */
-    const uint32_t* bond_conn_offset;  /* [bond_conn_offset_count] (= num_atoms + 1), may be NULL if no sdf property */
+    const uint32_t* bond_conn_offset;  /* [bond_conn_offset_count] (= num_atoms + 1), may be NULL if no sdf / rmsd property */
     const int32_t* bond_conn_atom_idx;
     size_t bond_conn_offset_count;
 } mdgpu_system_desc_t;
@@ -100,6 +100,7 @@ typedef enum mdgpu_op {
     MDGPU_OP_DIHEDRAL = 8,   /* dihedral(a, b, c, d)                 -> temporal                          :4171-4196 */
     MDGPU_OP_DISTANCE_MIN = 9,  /* distance_min(a, b) over the atoms of two selections -> temporal        :3892-3928 */
     MDGPU_OP_DISTANCE_MAX = 10, /* distance_max(a, b): the reference evaluates md_util_min_distance here too (:3944) */
+    MDGPU_OP_RMSD = 11,      /* rmsd(selection) against the initial frame -> temporal                     :4287-4345 */
 } mdgpu_op;
 
 /* One property = one `ident = proc(args);` statement whose selections were evaluated statically at compile time
@@ -112,6 +113,7 @@ typedef enum mdgpu_op {
  *   SDF      : idx[0] = num_structures * structure_size atoms (equivalent structures), idx[1] = target atoms, cutoff_max.
  *   DENSITY_*: idx[0] = atoms.
  *   DISTANCE_MIN/_MAX: idx[0], idx[1] = the atoms of the two selections (brute force over all pairs, md_util_min_distance md_util.c:8242).
+ *   RMSD     : idx[0] = the atoms of the (flattened) selection; needs the initial frame and, to make molecules whole, the bond connectivity.
  *   DISTANCE/ANGLE/DIHEDRAL: idx[k] = the atoms of argument k (0-based). A single integer index is that atom's position; an
  *              argument that was a selection (bit k of com_args set, or more than one index) is its centre of mass as
  *              coordinate_extract_com evaluates it (:1717 -> md_util_com_compute md_util.c:8163: periodic cells use the
@@ -160,7 +162,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
                               size_t num_frames, const mdgpu_plan_options_t* opts);
 void mdgpu_plan_destroy(mdgpu_plan* plan);
 
-/* Frame 0 of the trajectory ("initial configuration", md_script.c:5808): reference structure of sdf(), reference cell of density_*(). */
+/* Frame 0 of the trajectory ("initial configuration", md_script.c:5808): reference structure of sdf() and rmsd(), reference cell of density_*(). */
 int mdgpu_plan_set_initial_frame(mdgpu_plan* plan, const float* x, const float* y, const float* z, const mdgpu_unitcell_t* cell);
 
 /* md_script_eval_clear_data (md_script.c:6563): zero accumulators, frame mask, interrupt flag. */

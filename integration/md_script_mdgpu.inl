@@ -76,6 +76,14 @@ static int64_t mdgpu__arg_indices(int32_t** out, size_t* out_num_sets, size_t* o
     return -1;
 }
 
+/* _internal_flatten_bf: union of an array of bitfields. The concatenated index lists of disjoint sets are already that union; sort + unique
+ * covers overlapping ones. Returns the new count. */
+static size_t mdgpu__flatten(int32_t* v, size_t n) {
+    for (size_t i = 1; i < n; ++i) { int32_t t = v[i]; size_t j = i; while (j > 0 && v[j - 1] > t) { v[j] = v[j - 1]; --j; } v[j] = t; }
+    size_t w = 0; for (size_t i = 0; i < n; ++i) if (w == 0 || v[i] != v[w - 1]) v[w++] = v[i];
+    return w;
+}
+
 static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const ast_node_t* node, md_allocator_i* alloc) {
     const ast_node_t* rhs = mdgpu__rhs(node);
     if (rhs->type != AST_PROC_CALL || !rhs->proc) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "' is not a direct procedure call", STR_ARG(ident)); return false; }
@@ -111,11 +119,13 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
     if ((str_eq(pname, STR_LIT("density_x")) || str_eq(pname, STR_LIT("density_y")) || str_eq(pname, STR_LIT("density_z"))) && nargs == 1) {
         out->op = MDGPU_OP_DENSITY_X + (uint32_t)(pname.ptr[8] - 'x');
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], NULL, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
-        /* _internal_flatten_bf: union of the bitfields; concatenated lists of disjoint sets are already that union. Sort + unique for safety. */
-        int32_t* v = (int32_t*)out->idx[0];
-        for (size_t i = 1; i < out->idx_count[0]; ++i) { int32_t t = v[i]; size_t j = i; while (j > 0 && v[j - 1] > t) { v[j] = v[j - 1]; --j; } v[j] = t; }
-        size_t w = 0; for (size_t i = 0; i < out->idx_count[0]; ++i) if (w == 0 || v[i] != v[w - 1]) v[w++] = v[i];
-        out->idx_count[0] = w;
+        out->idx_count[0] = mdgpu__flatten((int32_t*)out->idx[0], out->idx_count[0]);
+        return true;
+    }
+    if (str_eq(pname, STR_LIT("rmsd")) && nargs == 1) {   /* _rmsd :4287: the (flattened) selection against the initial configuration */
+        out->op = MDGPU_OP_RMSD;
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], NULL, NULL, args[0], alloc)) < 0) goto dynamic;
+        out->idx_count[0] = mdgpu__flatten((int32_t*)out->idx[0], (size_t)n);
         return true;
     }
     if ((str_eq(pname, STR_LIT("distance_min")) || str_eq(pname, STR_LIT("distance_max"))) && nargs == 2) {

@@ -1,0 +1,67 @@
+"""Kernels whose threads do not cooperate, EXECUTED on the CPU from the product's own .cu source (tests/emul: g++ + a small CUDA shim) and
+compared with the reference's golden values. This is how device code written without GPU time left is checked before its first launch:
+it proves the source's logic and operation order (every operation on these paths is IEEE add/mul/div/sqrt, identical on host and device);
+it cannot prove launch configuration or memory behaviour, which is what tests/pending_gpu_round2.py is for."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+from helpers import load_golden, golden_system, sel_element  # noqa: E402
+
+
+class _Cell(C.Structure):   # mdgpu_unitcell_t
+    _fields_ = [("x", C.c_double), ("xy", C.c_double), ("xz", C.c_double), ("y", C.c_double), ("yz", C.c_double), ("z", C.c_double), ("flags", C.c_uint32)]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    import build_emul
+    return C.CDLL(build_emul.build())
+
+
+def unwrap_pairs(count, conn_off, conn_idx):
+    """(child, parent) pairs in the order md_util_unwrap_vec4(xyzw, NULL, count, bond, cell) visits them (md_util.c:8738-8819): breadth
+    first over the bonds of GLOBAL atoms 0..count-1 (the local index is used as the atom index there), neighbours >= count skipped."""
+    na = len(conn_off) - 1; visited = np.zeros(na + 1, bool); out = []
+    for seed in range(count):
+        if seed >= na or visited[seed]: continue
+        visited[seed] = True; queue = [seed]; qh = 0
+        while qh < len(queue):
+            cur = queue[qh]; qh += 1
+            for k in range(conn_off[cur], conn_off[cur + 1]):
+                nx = int(conn_idx[k])
+                if nx < 0 or nx >= count or visited[nx]: continue
+                out.append((nx, cur)); visited[nx] = True; queue.append(nx)
+    return np.asarray(out, np.int32).reshape(-1, 2)
+
+
+def run_rmsd(lib, g, s, idx):
+    frames = np.ascontiguousarray(g["frames"], np.float32); F, _, na = frames.shape
+    cells = (_Cell * F)()
+    for f in range(F):
+        x, xy, xz, y, yz, z = (float(v) for v in g["cells"][f]); cells[f] = _Cell(x, xy, xz, y, yz, z, int(g["cell_flags"][f]))
+    idx = np.ascontiguousarray(idx, np.int32); mass = np.ascontiguousarray(s["mass"], np.float32)
+    pairs = np.ascontiguousarray(unwrap_pairs(len(idx), s["conn_off"], s["conn_idx"]))
+    out = np.zeros(F, np.float32); fp = C.POINTER(C.c_float); ip = C.POINTER(C.c_int32)
+    lib.emul_rmsd.argtypes = [fp, C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(_Cell), fp, C.c_size_t, fp, ip, C.c_uint32, ip, C.c_uint32, fp]
+    rc = lib.emul_rmsd(frames.ctypes.data_as(fp), 3 * na, na, F, cells, frames[0].ctypes.data_as(fp), na, mass.ctypes.data_as(fp),
+                       idx.ctypes.data_as(ip), len(idx), pairs.ctypes.data_as(ip), len(pairs), out.ctypes.data_as(fp))
+    assert rc == 0
+    return out
+
+
+def test_k_rmsd_source_matches_the_reference(emul):
+    """k_rmsd (viamd_b200/csrc/sdf.cu) run on the CPU: bit-equal to the reference's rmsd() on the orthorhombic water box, the 1ALA
+    trajectory (50 frames, 153 atoms) and the triclinic cell that changes every frame (contiguous and scattered selections)."""
+    g = load_golden("water6.npz"); s = golden_system(g)
+    assert np.array_equal(run_rmsd(emul, g, s, np.arange(30)), g["rm__full"])
+    g = load_golden("ala50.npz"); s = golden_system(g)
+    assert np.array_equal(run_rmsd(emul, g, s, np.arange(153)), g["rma__full"])
+    g = load_golden("tric6.npz"); s = golden_system(g); r = load_golden("tric6_rmsd.npz")
+    for key, idx in (("rmt", np.arange(30)), ("rma", np.arange(99, 160)), ("rmo", sel_element(s, 8))):
+        assert np.array_equal(run_rmsd(emul, g, s, idx), r[f"{key}__full"]), key
+    assert np.array_equal(run_rmsd(emul, g, s, np.zeros(0, np.int32)), np.zeros(g["frames"].shape[0], np.float32))

@@ -62,7 +62,9 @@ def test_script_lowering(vb):
     assert d.op == vb.OP_DISTANCE and d.idx[0][0] == 0 and d.idx[1][0] == 9          # 1-based script indices
     assert rr.cutoff_min == 2.0 and rr.cutoff_max == 8.0 and len(rr.idx[1]) == 128
     with pytest.raises(vb.ScriptError):
-        vb.compile_script("x = rmsd(all);", s)
+        vb.compile_script("x = com(all);", s)
+    rm = vb.compile_script("rm = rmsd(residue(2:4));", s)[0]                           # array of selections -> their union
+    assert rm.op == vb.OP_RMSD and list(rm.idx[0]) == list(range(3, 12))
     # array-of-selections reference -> centre-of-mass groups with offsets; selection arguments of the temporals -> com_args; pair minimum
     rc, dc, dm, dmin = vb.compile_script("rc = rdf(residue(2:5), element('O'), 5.0); dc = distance(residue(1), residue(3)); "
                                          "dm = distance(atom(1:6), 10); dmin = distance_min(residue(1), element('H'));", s)

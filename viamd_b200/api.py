@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libmdgpu.so")
 DIST_BINS = 1024
 VOL_DIM = 128
 
-OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
 CELL_ORTHO, CELL_TRICLINIC, CELL_PBC_X, CELL_PBC_Y, CELL_PBC_Z, CELL_PBC_ALL = 1, 2, 4, 8, 16, 28
 
 
@@ -246,6 +246,12 @@ def distance_min(name, a_idx, b_idx):
 def distance_max(name, a_idx, b_idx):
     """distance_max(a, b): the reference evaluates md_util_min_distance here as well (md_script_functions.inl:3944) — reproduced"""
     return Property(name, OP_DISTANCE_MAX, [np.asarray(a_idx, np.int32), np.asarray(b_idx, np.int32)])
+
+
+def rmsd(name, idx):
+    """rmsd(selection): mass-weighted RMSD of the selection's atoms against the initial frame after wrap, bond-walk unwrap and an optimal
+    rotation (_rmsd md_script_functions.inl:4287). Needs System.conn_offset / conn_idx to make molecules whole, as the reference does."""
+    return Property(name, OP_RMSD, [np.asarray(idx, np.int32)])
 
 
 def angle(name, a, b, c):

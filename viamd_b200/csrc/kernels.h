@@ -60,6 +60,19 @@ struct SdfArgs {
 };
 void launch_sdf(const SdfArgs& a, int B, bool tri, cudaStream_t s);
 
+struct RmsdArgs {                    // rmsd(selection) against the initial frame, one value per frame
+    BatchFrames frames;
+    const mdgpu_unitcell_t* cells;   // [B]
+    const float* init_xyz; size_t init_axis_stride;
+    const float* mass;
+    const int32_t* idx; uint32_t n;  // the selection's atoms, ascending
+    const int2* unwrap_pairs; uint32_t n_unwrap;
+    float4* scratch_xyzw;            // [B][2][n]
+    float* out;                      // [num_frames]
+    uint32_t frame0;
+};
+void launch_rmsd(const RmsdArgs& a, int B, cudaStream_t s);
+
 // props.cu
 struct DensityArgs {
     BatchFrames frames; const int32_t* idx; uint32_t n; const float* mass; int axis;

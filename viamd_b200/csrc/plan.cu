@@ -311,6 +311,15 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.values.assign(num_frames, 0.0f);
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
             break; }
+        case MDGPU_OP_RMSD: {   // an empty selection is valid and evaluates to 0 (_rmsd :4311, :4336-4338)
+            std::vector<int2> pairs;   // without bonds md_util_unwrap_vec4 fails and its result is ignored (:4327): nothing is unwrapped
+            build_unwrap_pairs(pairs, pr.h_idx[0].size(), p->conn_off, p->conn_idx);
+            pr.n_unwrap = (uint32_t)pairs.size();
+            e = upload(&pr.d_unwrap, pairs.data(), pairs.size());
+            if (e == cudaSuccess) e = dalloc(&pr.d_temporal, num_frames);
+            pr.values.assign(num_frames, 0.0f);
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break; }
         default:
             return bail(MDGPU_ERR_UNSUPPORTED, "property '" + pr.name + "': unsupported operation " + std::to_string(pr.op));
         }
@@ -433,6 +442,8 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * (pr.n_struct + 1) * pr.struct_size));
                     CUDA_TRY(dalloc(&ps.d_sdf_ref0, (size_t)p->B * 20));
                     CUDA_TRY(dalloc(&ps.d_sdf_mats, (size_t)p->B * pr.n_struct * 32));
+                } else if (pr.op == MDGPU_OP_RMSD) {
+                    CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * 2 * pr.h_idx[0].size()));   // [B][initial, current][atoms]
                 } else if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
                     CUDA_TRY(dalloc(&ps.d_frame_bins64, (size_t)p->B * MDGPU_DIST_BINS));
                 } else if (pr.com_mask) {
@@ -513,6 +524,14 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); cudaEventRecord(tl.a, s.stream); }
             launch_density(a, B, s.stream);
             if (p->timing) { cudaEventRecord(tl.b, s.stream); tl.kind = 2; p->timed.push_back(tl); }
+            break; }
+        case MDGPU_OP_RMSD: {
+            if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "rmsd '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
+            RmsdArgs a{};
+            a.frames = fr; a.cells = s.d_cells; a.init_xyz = p->d_init; a.init_axis_stride = p->axis_stride; a.mass = p->d_mass;
+            a.idx = pr.d_idx[0]; a.n = (uint32_t)pr.h_idx[0].size(); a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap;
+            a.scratch_xyzw = ps.d_sdf_xyzw; a.out = pr.d_temporal; a.frame0 = frame0;
+            launch_rmsd(a, B, s.stream);
             break; }
         case MDGPU_OP_DISTANCE_MIN: case MDGPU_OP_DISTANCE_MAX:   // both evaluate md_util_min_distance (md_script_functions.inl:3904, 3944)
             launch_min_distance(fr, s.d_cells, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), pr.d_idx[1], (uint32_t)pr.h_idx[1].size(), pr.d_temporal, frame0, s.stream);

@@ -502,6 +502,123 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
     if (lane == 0 && local) atomicAdd(&a.frame_total[a.frame0 + f], local);
 }
 
+// ------------------------------------------------------------------------------------------------- rmsd(selection)
+// _rmsd (md_script_functions.inl:4287-4345): the selection's atoms of the INITIAL frame and of the current frame, both wrapped into the
+// current cell (md_util_pbc_vec4 md_util.c:8603), made whole along the bonds (md_util_unwrap_vec4 :8938, same local-index-as-atom quirk as
+// in _sdf), centred on their plain centres of mass, fitted with mat3_optimal_rotation_vec4 (core/md_vec_math.c:337) and compared:
+// sqrt(sum w |u - R v|^2 / sum w) with double sums (md_util_rmsd_compute_vec4 md_util.c:9037-9068).
+//
+// One warp per frame. The lanes extract and wrap the atoms (independent per atom); lane 0 then runs the parts whose result depends on
+// the order of operations — the bond walk, the float centre-of-mass sums, the double covariance and deviation sums — exactly in the
+// reference's order. Selections of rmsd() are one molecule or its backbone (10^2..10^4 atoms), a serial pass over them costs microseconds.
+MDG_D float4 pbc_wrap(float4 v, const mdgpu_unitcell_t& uc) {
+    if (uc.flags & MDGPU_CELL_ORTHO) {            // pbc_ortho_vec4 :8506-8512: vec4_deperiodize_ortho about the box centre
+        const float ex = (float)uc.x, ey = (float)uc.y, ez = (float)uc.z;
+        v.x = deperiodize1(v.x, ex * 0.5f, ex); v.y = deperiodize1(v.y, ey * 0.5f, ey); v.z = deperiodize1(v.z, ez * 0.5f, ez);
+    } else if (uc.flags & MDGPU_CELL_TRICLINIC) {  // pbc_triclinic_vec4 :8554-8574: A * fract(I * r) on the periodic axes, float matrices
+        const double i11 = uc.x > 0.0 ? 1.0 / uc.x : 0.0, i22 = uc.y > 0.0 ? 1.0 / uc.y : 0.0, i33 = uc.z > 0.0 ? 1.0 / uc.z : 0.0;   // md_unitcell.inl:158-176
+        const double i12 = (uc.x * uc.y) > 0.0 ? -uc.xy / (uc.x * uc.y) : 0.0;
+        const double i13 = (uc.x * uc.y * uc.z) > 0.0 ? (uc.xy * uc.yz - uc.xz * uc.y) / (uc.x * uc.y * uc.z) : 0.0;
+        const double i23 = (uc.y * uc.z) > 0.0 ? -uc.yz / (uc.y * uc.z) : 0.0;
+        const float I00 = (float)i11, I10 = (float)i12, I11 = (float)i22, I20 = (float)i13, I21 = (float)i23, I22 = (float)i33;
+        const float A00 = (float)uc.x, A10 = (float)uc.xy, A11 = (float)uc.y, A20 = (float)uc.xz, A21 = (float)uc.yz, A22 = (float)uc.z;
+        // linear_combine_3 (core/md_vec_math.h:1521): (x * col0 + y * col1) + z * col2, the zero entries of the matrices included
+        float f0 = (v.x * I00 + v.y * I10) + v.z * I20;
+        float f1 = (v.x * 0.0f + v.y * I11) + v.z * I21;
+        float f2 = (v.x * 0.0f + v.y * 0.0f) + v.z * I22;
+        f0 = f0 - floorf(f0); f1 = f1 - floorf(f1); f2 = f2 - floorf(f2);
+        const float r0 = (f0 * A00 + f1 * A10) + f2 * A20;
+        const float r1 = (f0 * 0.0f + f1 * A11) + f2 * A21;
+        const float r2 = (f0 * 0.0f + f1 * 0.0f) + f2 * A22;
+        if (uc.flags & MDGPU_CELL_PBC_X) v.x = r0;
+        if (uc.flags & MDGPU_CELL_PBC_Y) v.y = r1;
+        if (uc.flags & MDGPU_CELL_PBC_Z) v.z = r2;
+    }
+    return v;
+}
+
+// bond walk over (child, parent) pairs in BFS order + com_vec4, on atoms already in scratch (the second half of load_unwrap_com)
+MDG_D void unwrap_com(float4* p, uint32_t n, const int2* pairs, uint32_t n_pairs, const mdgpu_unitcell_t& uc, float com[3]) {
+    if (uc.flags & MDGPU_CELL_ORTHO) {
+        const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
+        for (uint32_t k = 0; k < n_pairs; ++k) {
+            const int2 pr = pairs[k];
+            const float4 ref = p[pr.y]; float4 v = p[pr.x];
+            v.x = deperiodize1(v.x, ref.x, ext[0]); v.y = deperiodize1(v.y, ref.y, ext[1]); v.z = deperiodize1(v.z, ref.z, ext[2]);
+            p[pr.x] = v;
+        }
+    } else if (uc.flags & MDGPU_CELL_TRICLINIC) {
+        const float box[3][3] = { { (float)uc.x, 0.f, 0.f }, { (float)uc.xy, (float)uc.y, 0.f }, { (float)uc.xz, (float)uc.yz, (float)uc.z } };
+        for (uint32_t k = 0; k < n_pairs; ++k) {
+            const int2 pr = pairs[k];
+            const float4 ref = p[pr.y]; float4 v = p[pr.x];
+            float d[3] = { __fsub_rn(v.x, ref.x), __fsub_rn(v.y, ref.y), __fsub_rn(v.z, ref.z) };
+            min_image_triclinic(d, box);
+            v.x = __fadd_rn(ref.x, d[0]); v.y = __fadd_rn(ref.y, d[1]); v.z = __fadd_rn(ref.z, d[2]);
+            p[pr.x] = v;
+        }
+    }
+    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;   // com_vec4 md_util.c:8048-8061
+    for (uint32_t k = 0; k < n; ++k) { const float4 v = p[k]; ax = ax + v.x * v.w; ay = ay + v.y * v.w; az = az + v.z * v.w; aw = aw + v.w * 1.0f; }
+    com[0] = ax / aw; com[1] = ay / aw; com[2] = az / aw;
+}
+
+__global__ void __launch_bounds__(32) k_rmsd(RmsdArgs a, int B) {
+    const int f = blockIdx.x, lane = threadIdx.x;
+    if (f >= B) return;
+    const uint32_t n = a.n;
+    const mdgpu_unitcell_t uc = a.cells[f];
+    const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride;
+    float4* p0 = a.scratch_xyzw + (size_t)f * 2 * n;   // initial frame
+    float4* p1 = p0 + n;                               // current frame
+    for (uint32_t k = lane; k < n; k += 32) {           // extract_xyzw_vec4 (:966) + md_util_pbc_vec4
+        const int at = a.idx[k]; const float w = a.mass[at];
+        p0[k] = pbc_wrap(make_float4(a.init_xyz[at], a.init_xyz[a.init_axis_stride + at], a.init_xyz[2 * a.init_axis_stride + at], w), uc);
+        p1[k] = pbc_wrap(make_float4(x[at], x[a.frames.axis_stride + at], x[2 * a.frames.axis_stride + at], w), uc);
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    float com0[3], com1[3];
+    unwrap_com(p0, n, a.unwrap_pairs, a.n_unwrap, uc, com0);
+    unwrap_com(p1, n, a.unwrap_pairs, a.n_unwrap, uc, com1);
+    double C[3][3] = { { 0 } }; double ws = 0.0;   // mat3_cross_covariance_matrix_vec4 (core/md_vec_math.c:256-289)
+    for (uint32_t k = 0; k < n; ++k) {
+        const float4 u = p0[k], v = p1[k];
+        const float px = u.x - com0[0], py = u.y - com0[1], pz = u.z - com0[2], pw = u.w - 0.0f;
+        const float qx = v.x - com1[0], qy = v.y - com1[1], qz = v.z - com1[2], qw = v.w - 0.0f;
+        const float w = (pw + qw) * 0.5f;
+        C[0][0] += w * px * qx; C[0][1] += w * px * qy; C[0][2] += w * px * qz;
+        C[1][0] += w * py * qx; C[1][1] += w * py * qy; C[1][2] += w * py * qz;
+        C[2][0] += w * pz * qx; C[2][1] += w * pz * qy; C[2][2] += w * pz * qz;
+        ws += w;
+    }
+    M3 cc; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) cc.e[i][j] = (float)(C[i][j] / ws);
+    const Svd sv = m3_svd(cc);                      // mat3_extract_rotation (core/md_vec_math.c:292-300)
+    const M3 Ut = m3_transpose(sv.U);
+    const float det = m3_det(m3_mul(sv.V, Ut));
+    M3 D; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) D.e[i][j] = 0.0f; D.e[0][0] = 1.0f; D.e[1][1] = 1.0f; D.e[2][2] = (float)((det > 0.0f) - (det < 0.0f));
+    const M3 R = m3_mul(m3_mul(sv.V, D), Ut);
+    double d_sum = 0.0, w_sum = 0.0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const float4 u4 = p0[k], v4 = p1[k];
+        const float u[3] = { u4.x - com0[0], u4.y - com0[1], u4.z - com0[2] };
+        const float v[3] = { v4.x - com1[0], v4.y - com1[1], v4.z - com1[2] };
+        float d[3];   // mat3_mul_vec3 (core/md_vec_math.h:1623): (x * col0 + y * col1) + z * col2
+        for (int r = 0; r < 3; ++r) d[r] = u[r] - ((R.e[0][r] * v[0] + R.e[1][r] * v[1]) + R.e[2][r] * v[2]);
+        const float w = (u4.w + v4.w) * 0.5f;
+        const float dd = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+        d_sum += (double)(w * dd); w_sum += (double)w;
+    }
+    a.out[a.frame0 + f] = (float)sqrt(d_sum / w_sum);
+}
+
+#ifndef MDG_HOST_EMULATION   // tests/emul compiles this file with g++ to run the one-thread-per-item kernels on the CPU; it has no launchers
+void launch_rmsd(const RmsdArgs& a, int B, cudaStream_t s) {
+    if (!a.n || B <= 0) return;   // empty selection: the property stays 0 (:4311)
+    k_rmsd<<<B, 32, 0, s>>>(a, B);
+    note_launch("k_rmsd", s);
+}
+
 void launch_sdf(const SdfArgs& a, int B, bool tri, cudaStream_t s) {
     k_sdf_ref0<<<(B + 31) / 32, 32, 0, s>>>(a, B);
     note_launch("k_sdf_ref0", s);
@@ -512,5 +629,6 @@ void launch_sdf(const SdfArgs& a, int B, bool tri, cudaStream_t s) {
     if (tri) k_sdf_scatter<true><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); else k_sdf_scatter<false><<<g2, SDF_WARPS * 32, 0, s>>>(a, B);
     note_launch("k_sdf_scatter", s);
 }
+#endif
 
 }  // namespace mdg

@@ -175,6 +175,8 @@ class _Parser:
         elif proc in ("distance_min", "distance_max"):
             a = self.selection(); self.expect("ch", ","); b = self.selection()
             p = (api.distance_min if proc == "distance_min" else api.distance_max)(ident, a, b)
+        elif proc == "rmsd":
+            p = api.rmsd(ident, self.selection())   # an array of selections is flattened into their union (_internal_flatten_bf :4305)
         elif proc == "distance":
             a = self.index(); self.expect("ch", ","); b = self.index(); p = api.distance(ident, a, b)
         elif proc == "angle":
