@@ -1009,21 +1009,47 @@ static void normalize3(float v[3]) {
 /* distance_min(a, b) / distance_max(a, b): _distance_min / _distance_max md_script_functions.inl:3892-3968 over the atoms of two selections.
  * Both call md_util_min_distance (md_util.c:8242-8297; _distance_max calling the MIN function is the reference's behaviour, :3944):
  * brute force over all pairs, vec4_periodic_distance (core/md_vec_math.h:1268-1273) in ortho cells, minimum_image_triclinic in triclinic. */
-float mdo_min_distance(const float* x, const float* y, const float* z, const int32_t* ia, size_t na, const int32_t* ib, size_t nb, const mdo_unitcell_t* cell) {
-    float min_dist = FLT_MAX;
+static float pair_distance(const float a[3], const float b[3], const mdo_unitcell_t* cell) {
     const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
     const float box[3][3] = { { (float)cell->x, 0, 0 }, { (float)cell->xy, (float)cell->y, 0 }, { (float)cell->xz, (float)cell->yz, (float)cell->z } };
+    float d[3] = { a[0] - b[0], a[1] - b[1], a[2] - b[2] };
+    if (cell->flags == 0) return sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);                  /* vec3_distance */
+    if (cell->flags & MDO_CELL_ORTHO) {
+        for (int k = 0; k < 3; ++k) if (ext[k] != 0.0f) d[k] = d[k] - rintf(d[k] / ext[k]) * ext[k];
+        return sqrtf((d[0] * d[0] + d[1] * d[1]) + (d[2] * d[2] + 0.0f));                          /* vec4_dot: md_mm_reduce_add_ps order */
+    }
+    min_image_triclinic(d, box); return sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);            /* vec3_length */
+}
+
+float mdo_min_distance(const float* x, const float* y, const float* z, const int32_t* ia, size_t na, const int32_t* ib, size_t nb, const mdo_unitcell_t* cell) {
+    float min_dist = FLT_MAX;
     for (size_t i = 0; i < na; ++i) for (size_t j = 0; j < nb; ++j) {
         const float a[3] = { x[ia[i]], y[ia[i]], z[ia[i]] }, b[3] = { x[ib[j]], y[ib[j]], z[ib[j]] };
-        float d[3] = { a[0] - b[0], a[1] - b[1], a[2] - b[2] }, dist;
-        if (cell->flags == 0) dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);             /* vec3_distance */
-        else if (cell->flags & MDO_CELL_ORTHO) {
-            for (int k = 0; k < 3; ++k) if (ext[k] != 0.0f) d[k] = d[k] - rintf(d[k] / ext[k]) * ext[k];
-            dist = sqrtf((d[0] * d[0] + d[1] * d[1]) + (d[2] * d[2] + 0.0f));                        /* vec4_dot: md_mm_reduce_add_ps order */
-        } else { min_image_triclinic(d, box); dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]); }   /* vec3_length */
+        const float dist = pair_distance(a, b, cell);
         if (dist < min_dist) min_dist = dist;
     }
     return min_dist;
+}
+
+/* distance_pair(a, b): _distance_pair md_script_functions.inl:3972-4064 -> md_util_distance_array (md_util.c:8210-8240): the na x nb
+ * matrix out[i * nb + j] of the same three per-pair forms as above, a and b being the atoms of two selections (coordinate_extract). */
+void mdo_distance_pair(const float* x, const float* y, const float* z, const int32_t* ia, size_t na, const int32_t* ib, size_t nb, const mdo_unitcell_t* cell, float* out) {
+    for (size_t i = 0; i < na; ++i) for (size_t j = 0; j < nb; ++j) {
+        const float a[3] = { x[ia[i]], y[ia[i]], z[ia[i]] }, b[3] = { x[ib[j]], y[ib[j]], z[ib[j]] };
+        out[i * nb + j] = pair_distance(a, b, cell);
+    }
+}
+
+/* Per-frame aggregates of a multi-valued temporal: compute_min_max_mean_variance (md_script.c:5646-5677), two passes in float.
+ * out[4] = min, max, mean, population variance. */
+void mdo_aggregate(const float* data, size_t count, float out[4]) {
+    const float N = (float)count;
+    float mn = FLT_MAX, mx = -FLT_MAX, s1 = 0, s2 = 0;
+    for (size_t i = 0; i < count; ++i) { s1 += data[i]; mn = MINV(mn, data[i]); mx = MAXV(mx, data[i]); }
+    s1 = s1 / N;
+    for (size_t i = 0; i < count; ++i) s2 += (data[i] - s1) * (data[i] - s1);
+    s2 = s2 / N;
+    out[0] = mn; out[1] = mx; out[2] = s1; out[3] = s2;
 }
 
 /* _angle :4099-4114 */

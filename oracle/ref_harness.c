@@ -46,7 +46,7 @@ static void wr_u32(FILE* f, uint32_t v) { wr(f, &v, 4); }
 static void wr_i64(FILE* f, int64_t v) { wr(f, &v, 8); }
 static void wr_u64(FILE* f, uint64_t v) { wr(f, &v, 8); }
 
-/* record: kind(0 perframe,1 full) prop beg end  min_value max_value min_range[2] max_range[2]  storage(0 dense,1 sparse) count payload */
+/* record: kind(0 perframe,1 full,2 aggregates of a full evaluation) prop beg end  min_value max_value min_range[2] max_range[2]  storage(0 dense,1 sparse) count payload */
 static void write_record(FILE* f, uint32_t kind, uint32_t prop, int64_t beg, int64_t end, const md_script_property_data_t* d, const float* vals, size_t n) {
     wr_u32(f, kind); wr_u32(f, prop); wr_i64(f, beg); wr_i64(f, end);
     wr(f, &d->min_value, 4); wr(f, &d->max_value, 4); wr(f, d->min_range, 8); wr(f, d->max_range, 8);
@@ -170,6 +170,14 @@ static int mode_eval(int argc, char** argv, bool timing) {
         for (size_t p = 0; p < np; ++p) {
             const md_script_property_data_t* d = md_script_eval_property_data(eval, names[p]);
             write_record(f, 1, (uint32_t)p, fb, fe, d, d->values, d->num_values);
+            if (d->aggregate && d->aggregate->num_values) {   /* kind 2: per-frame mean | variance | (min,max) of a multi-valued temporal (md_script.c:5886-5890) */
+                const size_t na = d->aggregate->num_values; float* agg = malloc(na * 16);
+                memcpy(agg, d->aggregate->population_mean, na * 4); memcpy(agg + na, d->aggregate->population_var, na * 4);
+                memcpy(agg + 2 * na, d->aggregate->population_ext, na * 8);
+                wr_u32(f, 2); wr_u32(f, (uint32_t)p); wr_i64(f, fb); wr_i64(f, fe);
+                wr(f, &d->min_value, 4); wr(f, &d->max_value, 4); wr(f, d->min_range, 8); wr(f, d->max_range, 8);
+                wr_u32(f, 0); wr_u64(f, na * 4); wr(f, agg, na * 16); free(agg);
+            }
         }
     }
     fclose(f);

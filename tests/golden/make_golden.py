@@ -17,6 +17,8 @@ reference's outputs, so the tests need neither the reference nor the harness on 
   tric6.npz  : water n=6 sheared into a TRICLINIC cell that changes every frame, 4 frames: rt, rth (min:max), rtc (centre-of-mass references)
   tric6_rmsd.npz : the tric6 frames again: rmt = rmsd(residue(1:10)), rma = rmsd(atom(100:160)), rmo = rmsd(element('O')) — the triclinic wrap
                A * fract(I * r) of md_util_pbc_vec4, the triclinic bond-walk unwrap, non-contiguous selections
+  pairs6.npz : distance_pair() matrices (5 x 11 and 3 x 216 per frame) with the per-frame aggregates of a multi-valued temporal, on the
+               water6 and the tric6 frames
   xtc_cases.npz : XTC byte streams from the reference's writer + the reference reader's decode of them (see xtc_cases below)
   ala50.npz  : first 50 frames of datasets/1ALA-500.pdb (153 atoms, ortho cell 46.645 x 96.666 x 48.362), config 1:
                d = distance(1,10) (BASELINE config 1), rc = rdf(element('C'), element('O'), 10.0), dz = density_z(element('C')),
@@ -161,6 +163,26 @@ def tric6_rmsd(tmp):
     np.savez_compressed(os.path.join(HERE, "tric6_rmsd.npz"), **out)
 
 
+def pairs6(tmp):
+    """Multi-valued temporals: distance_pair() matrices with their per-frame aggregates (mean / variance / extent, md_script.c:5646-5677),
+    on the water6 frames (orthorhombic) and the tric6 frames (triclinic cell changing every frame)."""
+    out = {}
+    script = "dp = distance_pair(atom(1:5), atom(20:30)); dpo = distance_pair(residue(1), element('O'));"
+    w = np.load(os.path.join(HERE, "water6.npz")); t = np.load(os.path.join(HERE, "tric6.npz"))
+    for tag, g, seed in (("w", w, "77"), ("t", t, "91")):
+        gro, raw, o = os.path.join(tmp, tag + "p.gro"), os.path.join(tmp, tag + "p.raw"), os.path.join(tmp, tag + "p.out")
+        F = g["frames"].shape[0]
+        run(SYNTH, "water-gro", "6", seed, gro); refio.write_raw_traj(raw, g["frames"], g["cells"], g["cell_flags"])
+        run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--full", f"0:{F}")
+        for name, p in refio.read_refout(o).items():
+            k = f"{tag}_{name}"
+            out[k + "__dim"] = np.array(p.dim, np.int32); out[k + "__full"] = p.full
+            m = p.meta[(1, 0)]; out[k + "__meta"] = np.array([m["min_value"], m["max_value"], m["min_range"][0], m["max_range"][0]], np.float32)
+            out[k + "__mean"] = p.aggregate["mean"]; out[k + "__var"] = p.aggregate["var"]; out[k + "__ext"] = p.aggregate["ext"]
+    out["script"] = np.array(script)
+    np.savez_compressed(os.path.join(HERE, "pairs6.npz"), **out)
+
+
 def _write_gro(path, n, L):
     with open(path, "w") as f:
         f.write("synthetic\n%d\n" % n)
@@ -210,6 +232,6 @@ def xtc_cases(tmp):
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     with tempfile.TemporaryDirectory() as tmp:
-        water6(tmp); ala50(tmp); membrane6(tmp); tric6(tmp); tric6_rmsd(tmp); xtc_cases(tmp)
-    for f in ("water6.npz", "ala50.npz", "membrane6.npz", "tric6.npz", "tric6_rmsd.npz", "xtc_cases.npz"):
+        water6(tmp); ala50(tmp); membrane6(tmp); tric6(tmp); tric6_rmsd(tmp); pairs6(tmp); xtc_cases(tmp)
+    for f in ("water6.npz", "ala50.npz", "membrane6.npz", "tric6.npz", "tric6_rmsd.npz", "pairs6.npz", "xtc_cases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

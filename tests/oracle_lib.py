@@ -183,6 +183,19 @@ def min_distance(x, y, z, a, b, cell):
     return np.float32(lib().mdo_min_distance(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(a, C.c_int32), C.c_size_t(len(a)), _p(b, C.c_int32), C.c_size_t(len(b)), C.byref(cell)))
 
 
+def distance_pair(x, y, z, a, b, cell):
+    x, y, z = _f32(x), _f32(y), _f32(z); a, b = _i32(a), _i32(b); out = np.zeros(len(a) * len(b), np.float32)
+    lib().mdo_distance_pair(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(a, C.c_int32), C.c_size_t(len(a)), _p(b, C.c_int32), C.c_size_t(len(b)), C.byref(cell), _p(out, C.c_float))
+    return out
+
+
+def aggregate(values):
+    """-> (min, max, mean, var) as the reference folds one frame of a multi-valued temporal"""
+    v = _f32(values); out = np.zeros(4, np.float32)
+    lib().mdo_aggregate(_p(v, C.c_float), C.c_size_t(len(v)), _p(out, C.c_float))
+    return out
+
+
 def rmsd_frame(x, y, z, init_xyz, mass, idx, conn_off, conn_idx, cell):
     x, y, z, mass = _f32(x), _f32(y), _f32(z), _f32(mass); ix, iy, iz = _f32(init_xyz[0]), _f32(init_xyz[1]), _f32(init_xyz[2])
     idx = _i32(idx); co = np.ascontiguousarray(conn_off, np.uint32); ci = _i32(conn_idx)

@@ -22,6 +22,7 @@ class RefProperty:
     full: np.ndarray | None = None
     full_range: tuple | None = None
     meta: dict = field(default_factory=dict)  # (kind, beg) -> dict(min_value,...)
+    aggregate: dict | None = None  # multi-valued temporals: per-frame mean / var / ext
 
 
 def read_refout(path: str) -> dict:
@@ -52,6 +53,8 @@ def read_refout(path: str) -> dict:
         meta = dict(min_value=mn, max_value=mx, min_range=(r0, r1), max_range=(r2, r3))
         if kind == 0:
             p.perframe[beg] = vals
+        elif kind == 2:   # per-frame aggregates of a multi-valued temporal: mean[F] | var[F] | (min, max)[F]
+            na = cnt // 4; p.aggregate = dict(mean=vals[:na], var=vals[na:2 * na], ext=vals[2 * na:].reshape(na, 2))
         else:
             p.full = vals; p.full_range = (beg, end)
         p.meta[(kind, beg)] = meta
