@@ -100,6 +100,7 @@ typedef enum mdgpu_op {
     MDGPU_OP_DIHEDRAL = 8,   /* dihedral(a, b, c, d)                 -> temporal                          :4171-4196 */
     MDGPU_OP_DISTANCE_MIN = 9,  /* distance_min(a, b) over the atoms of two selections -> temporal        :3892-3928 */
     MDGPU_OP_DISTANCE_MAX = 10, /* distance_max(a, b): the reference evaluates md_util_min_distance here too (:3944) */
+    MDGPU_OP_DISTANCE_PAIR = 12, /* distance_pair(a, b): |a| x |b| pair distances per frame -> temporal [F, |a|*|b|]  :3972-4064 */
     MDGPU_OP_RMSD = 11,      /* rmsd(selection) against the initial frame -> temporal                     :4287-4345 */
 } mdgpu_op;
 
@@ -113,6 +114,9 @@ typedef enum mdgpu_op {
  *   SDF      : idx[0] = num_structures * structure_size atoms (equivalent structures), idx[1] = target atoms, cutoff_max.
  *   DENSITY_*: idx[0] = atoms.
  *   DISTANCE_MIN/_MAX: idx[0], idx[1] = the atoms of the two selections (brute force over all pairs, md_util_min_distance md_util.c:8242).
+ *   DISTANCE_PAIR: idx[0], idx[1] as for DISTANCE_MIN; row f of the property holds out[i * |b| + j] (md_util_distance_array md_util.c:8210);
+ *              at most 1 000 000 values per frame (:4056). Properties with more than one value per frame also carry per-frame aggregates
+ *              (mdgpu_plan_property_aggregate).
  *   RMSD     : idx[0] = the atoms of the (flattened) selection; needs the initial frame and, to make molecules whole, the bond connectivity.
  *   DISTANCE/ANGLE/DIHEDRAL: idx[k] = the atoms of argument k (0-based). A single integer index is that atom's position; an
  *              argument that was a selection (bit k of com_args set, or more than one index) is its centre of mass as
@@ -201,6 +205,10 @@ size_t mdgpu_plan_property_count(const mdgpu_plan* plan);
 int mdgpu_plan_property_index(const mdgpu_plan* plan, const char* name);
 int mdgpu_plan_property_data(mdgpu_plan* plan, size_t prop, mdgpu_property_data_t* out);   /* implies mdgpu_plan_sync */
 
+/* Per-frame aggregates of a temporal with several values per frame (md_script_aggregate_t md_script.h:63-70, filled at md_script.c:5886-5890):
+ * out_mean[num_frames], out_var[num_frames] (population variance), out_ext[num_frames][2] (min, max); any may be NULL. Implies mdgpu_plan_sync. */
+int mdgpu_plan_property_aggregate(mdgpu_plan* plan, size_t prop, float* out_mean, float* out_var, float* out_ext, size_t num_frames);
+
 /* Exact integer results (what parity is asserted on).
  *  _counts: accumulated counts over all evaluated frames: RDF 1024 x u64 bins; SDF 128^3 x u64 voxels (widened from u32);
  *           DENSITY 1024 x u64 fixed-point mass sums (unit 2^-24 Da).
@@ -231,6 +239,9 @@ int mdgpu_plan_kernel_time_ms(mdgpu_plan* plan, const char* kernel, double* tota
  * CPU-side tests and for sizing. out_i[13] = cdim[3], ncell[3], hlo[3], hdim[3], valid; out_f[7] = G00,G11,G22,H01,H02,H12,r2. */
 int mdgpu_debug_frame_geom(const mdgpu_unitcell_t* cell, double cell_ext, double cutoff, const float* aabb_min_max /* 6 floats or NULL */,
                            int32_t* out_i, float* out_f);
+
+/* Host fold of one frame of a multi-valued temporal, as mdgpu_plan_sync applies it (no device needed): out4 = min, max, mean, variance. */
+int mdgpu_debug_aggregate(const float* values, size_t count, float* out4);
 
 /* Self-check of the branch-free correctly-rounded sqrt used when binning RDF hits: compares it with the IEEE sqrt for every
  * float whose bit pattern lies in [lo_bits, hi_bits) and returns the number of mismatches (must be 0 in the normal range). */

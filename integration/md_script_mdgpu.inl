@@ -128,12 +128,12 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         out->idx_count[0] = mdgpu__flatten((int32_t*)out->idx[0], (size_t)n);
         return true;
     }
-    if ((str_eq(pname, STR_LIT("distance_min")) || str_eq(pname, STR_LIT("distance_max"))) && nargs == 2) {
-        out->op = str_eq(pname, STR_LIT("distance_min")) ? MDGPU_OP_DISTANCE_MIN : MDGPU_OP_DISTANCE_MAX;
+    if ((str_eq(pname, STR_LIT("distance_min")) || str_eq(pname, STR_LIT("distance_max")) || str_eq(pname, STR_LIT("distance_pair"))) && nargs == 2) {
+        out->op = str_eq(pname, STR_LIT("distance_min")) ? MDGPU_OP_DISTANCE_MIN : (str_eq(pname, STR_LIT("distance_max")) ? MDGPU_OP_DISTANCE_MAX : MDGPU_OP_DISTANCE_PAIR);
         for (size_t k = 0; k < 2; ++k) {
             size_t ns = 0;
             if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], &ns, NULL, args[k], alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n;
-            if (args[k]->data.type.base_type == TYPE_BITFIELD && ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (per-selection centres of mass) is not lowered for distance_min/max", STR_ARG(ident)); return false; }
+            if (args[k]->data.type.base_type == TYPE_BITFIELD && ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (per-selection centres of mass) is not lowered for distance_min/max/pair", STR_ARG(ident)); return false; }
         }
         return true;
     }
@@ -208,6 +208,10 @@ static bool md_script_gpu_eval_frame_range(mdgpu_plan* plan, md_script_eval_t* e
         MEMCPY(p->values, d.values, sizeof(float) * d.num_values);
         p->min_value = d.min_value; p->max_value = d.max_value;
         p->min_range[0] = d.min_range[0]; p->max_range[0] = d.max_range[0];
+        if (p->aggregate && p->aggregate->num_values == eval->frame_count &&   /* several values per frame: per-frame mean / variance / extent (md_script.c:5886-5890) */
+            mdgpu_plan_property_aggregate(plan, i, p->aggregate->population_mean, p->aggregate->population_var, (float*)p->aggregate->population_ext, eval->frame_count) != 0) {
+            MD_LOG_ERROR("mdgpu: %s", mdgpu_last_error()); return false;
+        }
     }
     const size_t nwords = (eval->frame_count + 63) / 64;
     uint64_t* words = (uint64_t*)md_alloc(md_get_heap_allocator(), sizeof(uint64_t) * (nwords ? nwords : 1));

@@ -1,22 +1,38 @@
-"""Build tests/emul/build/libemul_sdf.so: product .cu sources compiled by g++ for CPU execution of thread-independent kernels (test infrastructure)."""
+"""Build tests/emul/build/libemul_<name>.so: a product .cu file compiled by g++ (cuda_emul.h) so that its thread-independent kernels can be
+executed on the CPU (test infrastructure). The kernel launch statements `k<<<grid, block, smem, stream>>>(args);` are the one construct
+g++ cannot parse; they are blanked in a scratch copy of the source (build/<name>_nolaunch.cu) — kernels and device functions are
+compiled exactly as written."""
 import os
+import re
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-OUT = os.path.join(HERE, "build", "libemul_sdf.so")
-CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+CSRC = os.path.join(HERE, "..", "..", "viamd_b200", "csrc")
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+CUDA_INC = os.path.join(CUDA_HOME, "include")
+CUDA_LIB = os.path.join(CUDA_HOME, "lib64")
+LAUNCH = re.compile(r"[A-Za-z_]\w*\s*(?:<[^<>;(){}]*>)?\s*<<<.*?>>>\s*\([^;]*?\)\s*;", re.S)
 
 
-def build() -> str:
-    deps = [os.path.join(HERE, f) for f in ("emul_sdf.cpp", "cuda_emul.h")] + [os.path.join(HERE, "..", "..", "viamd_b200", "csrc", f) for f in ("sdf.cu", "kernels.h", "common.cuh")]
-    if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
-        return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+def build(name: str) -> str:
+    """name: 'sdf' or 'props' -> path of libemul_<name>.so"""
+    out = os.path.join(HERE, "build", f"libemul_{name}.so"); src = os.path.join(CSRC, f"{name}.cu"); wrap = os.path.join(HERE, f"emul_{name}.cpp")
+    deps = [src, wrap, os.path.join(HERE, "cuda_emul.h"), os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "common.cuh"), __file__]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    text = open(src).read()
+    stripped, n = LAUNCH.subn("/* launch removed for host emulation */;", text)
+    assert n > 0 and "<<<" not in stripped, f"{name}.cu: {n} launches removed, some left"
+    stripped = stripped.replace('#include "common.cuh"', f'#include "{os.path.join(CSRC, "common.cuh")}"').replace('#include "kernels.h"', f'#include "{os.path.join(CSRC, "kernels.h")}"')
+    with open(os.path.join(HERE, "build", f"{name}_nolaunch.cu"), "w") as f:
+        f.write(stripped)
     # no -mfma / -march: a*b+c must stay two roundings, as under nvcc --fmad=false
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", f"-I{CUDA_INC}", f"-I{HERE}",
-                           os.path.join(HERE, "emul_sdf.cpp"), "-o", OUT])
-    return OUT
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", "-x", "c++", f"-I{CUDA_INC}", f"-I{HERE}",
+                           f"-I{os.path.join(HERE, 'build')}", wrap, "-o", out,
+                           f"-L{CUDA_LIB}", f"-Wl,-rpath,{CUDA_LIB}", "-lcudart"])   # the (never called) launchers reference cudaMemsetAsync etc.
+    return out
 
 
 if __name__ == "__main__":
-    print(build())
+    print(build("sdf")); print(build("props"))

@@ -36,6 +36,8 @@ static inline unsigned __float_as_uint(float a) { unsigned u; memcpy(&u, &a, 4);
 static inline float __uint_as_float(unsigned u) { float a; memcpy(&a, &u, 4); return a; }
 static inline int __float_as_int(float a) { int u; memcpy(&u, &a, 4); return u; }
 static inline float __int_as_float(int u) { float a; memcpy(&a, &u, 4); return a; }
+static inline unsigned long long __float2ull_rn(float a) { return (unsigned long long)rintf(a); }
+static inline int __float2int_rn(float a) { return (int)rintf(a); }
 static inline int __float2int_rz(float a) { return (int)a; }
 static inline int __float2int_rd(float a) { return (int)floorf(a); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}

@@ -2,7 +2,9 @@
 // only extract, lane 0 does the ordered work — runs on the CPU exactly as written. Lanes 31..1 are run before lane 0, which is one legal
 // schedule of the warp (the kernel's only cross-lane dependency is the __syncwarp between extraction and lane 0's serial part).
 #include "cuda_emul.h"
-#include "../../viamd_b200/csrc/sdf.cu"
+#include "sdf_nolaunch.cu"   // viamd_b200/csrc/sdf.cu with its <<<>>> launch statements blanked (build_emul.py)
+
+namespace mdg { void note_launch(const char*, cudaStream_t) {} }   // the launchers are compiled (their launch statements blanked) but never called
 #include <vector>
 
 extern "C" int emul_rmsd(const float* frames, size_t frame_stride, size_t axis_stride, uint32_t num_frames, const mdgpu_unitcell_t* cells,

@@ -81,3 +81,35 @@ def test_rmsd_empty_selection_and_missing_initial_frame():
     with pytest.raises(vb.MdgpuError):
         plan.eval_host_frames(frames, [cell] * 3, 0)
     plan.close()
+
+
+def test_distance_pair_goldens_and_aggregates():
+    """distance_pair(a, b) (k_distance_pair, props.cu) -> [F, |a|*|b|] with the per-frame aggregates of a multi-valued temporal, against the
+    reference (pairs6.npz), orthorhombic and triclinic; through the script lowering."""
+    p = load_golden("pairs6.npz")
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        g = load_golden(name); s = golden_system(g); F = g["frames"].shape[0]
+        plan, cells = _plan(g, s, str(p["script"]), batch_frames=3)
+        plan.eval_host_frames(g["frames"], cells, 0)
+        for key in ("dp", "dpo"):
+            k = f"{tag}_{key}"; d = plan.property_data(key)
+            assert tuple(d.dim[:2]) == tuple(p[k + "__dim"][:2])
+            assert np.array_equal(d.values, p[k + "__full"]), k
+            mn, mx, r0, r1 = p[k + "__meta"]
+            assert d.min_value == mn and d.max_value == mx and d.min_range[0] == r0 and d.max_range[0] == r1
+            agg = plan.aggregate(key)
+            assert np.array_equal(agg["mean"], p[k + "__mean"]) and np.array_equal(agg["var"], p[k + "__var"]) and np.array_equal(agg["ext"], p[k + "__ext"]), k
+        plan.close()
+
+
+def test_distance_pair_limits():
+    import viamd_b200 as vb
+    sysm = vb.water_system(8)
+    with pytest.raises(vb.MdgpuError):   # 1 536 x 1 536 pairs > 1 000 000 values per frame (md_script_functions.inl:4056)
+        vb.Plan(sysm, [vb.distance_pair("big", np.arange(1536), np.arange(1536))], 2)
+    with pytest.raises(vb.MdgpuError):
+        vb.Plan(sysm, [vb.distance_pair("e", np.zeros(0, np.int32), np.arange(3))], 2)
+    plan = vb.Plan(sysm, [vb.distance("d", 0, 1)], 2)
+    with pytest.raises(vb.MdgpuError):   # one value per frame: no aggregate
+        plan.aggregate("d")
+    plan.close()

@@ -20,7 +20,20 @@ class _Cell(C.Structure):   # mdgpu_unitcell_t
 @pytest.fixture(scope="module")
 def emul():
     import build_emul
-    return C.CDLL(build_emul.build())
+    return C.CDLL(build_emul.build("sdf"))
+
+
+@pytest.fixture(scope="module")
+def emul_props():
+    import build_emul
+    return C.CDLL(build_emul.build("props"))
+
+
+def _cells(g):
+    F = g["frames"].shape[0]; cells = (_Cell * F)()
+    for f in range(F):
+        x, xy, xz, y, yz, z = (float(v) for v in g["cells"][f]); cells[f] = _Cell(x, xy, xz, y, yz, z, int(g["cell_flags"][f]))
+    return cells
 
 
 def unwrap_pairs(count, conn_off, conn_idx):
@@ -65,3 +78,30 @@ def test_k_rmsd_source_matches_the_reference(emul):
     for key, idx in (("rmt", np.arange(30)), ("rma", np.arange(99, 160)), ("rmo", sel_element(s, 8))):
         assert np.array_equal(run_rmsd(emul, g, s, idx), r[f"{key}__full"]), key
     assert np.array_equal(run_rmsd(emul, g, s, np.zeros(0, np.int32)), np.zeros(g["frames"].shape[0], np.float32))
+
+
+FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+
+
+def test_emulation_reproduces_a_gpu_validated_kernel(emul_props):
+    """Check of the emulation itself: k_temporal has passed on the B200 against these goldens; run on the CPU from the same source it must
+    reproduce them too (distance bit-equal; angle / dihedral bit-equal as well here, because host and reference share glibc's acosf / atan2f)."""
+    g = load_golden("water6.npz"); frames = np.ascontiguousarray(g["frames"], np.float32); F, _, na = frames.shape; cells = _cells(g)
+    emul_props.emul_temporal.argtypes = [FP, C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(_Cell), C.c_int, IP, FP]
+    for key, op, atoms in (("d", 6, (0, 9, 0, 0)), ("a", 7, (0, 1, 2, 0)), ("t", 8, (0, 3, 6, 9))):
+        out = np.zeros(F, np.float32); at = np.asarray(atoms, np.int32)
+        assert emul_props.emul_temporal(frames.ctypes.data_as(FP), 3 * na, na, F, cells, op, at.ctypes.data_as(IP), out.ctypes.data_as(FP)) == 0
+        assert np.array_equal(out, g[f"{key}__full"]), key
+
+
+def test_k_distance_pair_source_matches_the_reference(emul_props):
+    """k_distance_pair (viamd_b200/csrc/props.cu) run on the CPU thread by thread: bit-equal to the reference's distance_pair() matrices in the
+    orthorhombic box and in the triclinic cell that changes every frame (5 x 11 and 3 x 216 pairs per frame)."""
+    p = load_golden("pairs6.npz")
+    emul_props.emul_distance_pair.argtypes = [FP, C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(_Cell), IP, C.c_uint32, IP, C.c_uint32, FP]
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        g = load_golden(name); s = golden_system(g); frames = np.ascontiguousarray(g["frames"], np.float32); F, _, na = frames.shape; cells = _cells(g)
+        for key, a, b in (("dp", np.arange(0, 5, dtype=np.int32), np.arange(19, 30, dtype=np.int32)), ("dpo", np.arange(0, 3, dtype=np.int32), sel_element(s, 8))):
+            a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32); out = np.zeros(F * len(a) * len(b), np.float32)
+            assert emul_props.emul_distance_pair(frames.ctypes.data_as(FP), 3 * na, na, F, cells, a.ctypes.data_as(IP), len(a), b.ctypes.data_as(IP), len(b), out.ctypes.data_as(FP)) == 0
+            assert np.array_equal(out, p[f"{tag}_{key}__full"]), (tag, key)

@@ -63,6 +63,8 @@ def test_script_lowering(vb):
     assert rr.cutoff_min == 2.0 and rr.cutoff_max == 8.0 and len(rr.idx[1]) == 128
     with pytest.raises(vb.ScriptError):
         vb.compile_script("x = com(all);", s)
+    dp = vb.compile_script("dp = distance_pair(residue(1), element('O'));", s)[0]
+    assert dp.op == vb.OP_DISTANCE_PAIR and list(dp.idx[0]) == [0, 1, 2] and len(dp.idx[1]) == 64
     rm = vb.compile_script("rm = rmsd(residue(2:4));", s)[0]                           # array of selections -> their union
     assert rm.op == vb.OP_RMSD and list(rm.idx[0]) == list(range(3, 12))
     # array-of-selections reference -> centre-of-mass groups with offsets; selection arguments of the temporals -> com_args; pair minimum
@@ -216,3 +218,17 @@ def test_frame_geometry_matches_the_oracle(vb):
         assert list(gi[3:6]) == list(oi[3:6]), ("ncell", tag, gi[3:6], oi[3:6])
         assert np.array_equal(gf[:7], of[:7]), ("metric/r2", tag, gf, of[:7])
         assert (gi[12] > 0) == all(2 * int(v) + 1 <= 5 for v in oi[3:6]), ("valid", tag, gi[12], oi[3:6])
+
+
+def test_host_fold_of_multi_valued_temporals_matches_the_reference(vb):
+    """mdgpu_plan_sync's per-frame fold (min / max / mean / population variance, two float passes) on the reference's distance_pair() rows:
+    equal to the aggregates the reference stored (pairs6.npz)."""
+    from helpers import load_golden
+    L = vb.lib(); L.mdgpu_debug_aggregate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    p = load_golden("pairs6.npz")
+    for k in ("w_dp", "w_dpo", "t_dp", "t_dpo"):
+        F, n = (int(v) for v in p[k + "__dim"][:2]); vals = np.ascontiguousarray(p[k + "__full"], np.float32)
+        for f in range(F):
+            row = np.ascontiguousarray(vals[f * n:(f + 1) * n]); out = np.zeros(4, np.float32)
+            assert L.mdgpu_debug_aggregate(row.ctypes.data, n, out.ctypes.data) == 0
+            assert out[0] == p[k + "__ext"][f, 0] and out[1] == p[k + "__ext"][f, 1] and out[2] == p[k + "__mean"][f] and out[3] == p[k + "__var"][f], (k, f)

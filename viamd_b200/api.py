@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libmdgpu.so")
 DIST_BINS = 1024
 VOL_DIM = 128
 
-OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
+OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
 CELL_ORTHO, CELL_TRICLINIC, CELL_PBC_X, CELL_PBC_Y, CELL_PBC_Z, CELL_PBC_ALL = 1, 2, 4, 8, 16, 28
 
 
@@ -135,6 +135,7 @@ def lib() -> C.CDLL:
         L.mdgpu_plan_property_index.argtypes = [C.c_void_p, C.c_char_p]
         L.mdgpu_plan_property_data.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(_PropertyData)]
         L.mdgpu_plan_property_counts.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.mdgpu_plan_property_aggregate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.mdgpu_plan_property_frame_counts.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
         L.mdgpu_plan_frame_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.mdgpu_plan_property_accum_ptr.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
@@ -246,6 +247,11 @@ def distance_min(name, a_idx, b_idx):
 def distance_max(name, a_idx, b_idx):
     """distance_max(a, b): the reference evaluates md_util_min_distance here as well (md_script_functions.inl:3944) — reproduced"""
     return Property(name, OP_DISTANCE_MAX, [np.asarray(a_idx, np.int32), np.asarray(b_idx, np.int32)])
+
+
+def distance_pair(name, a_idx, b_idx):
+    """distance_pair(a, b): all |a| x |b| pair distances per frame, a temporal with |a|*|b| values per frame (md_script_functions.inl:3972)"""
+    return Property(name, OP_DISTANCE_PAIR, [np.asarray(a_idx, np.int32), np.asarray(b_idx, np.int32)])
 
 
 def rmsd(name, idx):
@@ -456,6 +462,13 @@ class Plan:
         dim = tuple(d.dim)
         weights = vals[dim[2]:2 * dim[2]].copy() if bool(d.weights) else None
         return PropertyData(self._names[i], dim, vals, weights, float(d.min_value), float(d.max_value), tuple(d.min_range), tuple(d.max_range), int(d.frames_accumulated))
+
+    def aggregate(self, name) -> dict:
+        """per-frame mean / population variance / (min, max) of a temporal with several values per frame (md_script_aggregate_t)"""
+        i = self._index(name); F = self.num_frames
+        mean = np.zeros(F, np.float32); var = np.zeros(F, np.float32); ext = np.zeros((F, 2), np.float32)
+        _check(lib().mdgpu_plan_property_aggregate(self._h, i, mean.ctypes.data, var.ctypes.data, ext.ctypes.data, F))
+        return dict(mean=mean, var=var, ext=ext)
 
     def counts(self, name) -> np.ndarray:
         i = self._index(name); op = self.properties[i].op

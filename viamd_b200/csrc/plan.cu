@@ -55,7 +55,9 @@ struct Prop {
     uint32_t* d_frame_min = nullptr; uint32_t* d_frame_max = nullptr;             // rdf
     unsigned long long* d_frame_min64 = nullptr; unsigned long long* d_frame_max64 = nullptr;   // density
     uint32_t* d_keep = nullptr; unsigned long long* d_keep64 = nullptr;
-    float* d_temporal = nullptr;                  // [num_frames]
+    float* d_temporal = nullptr;                  // [num_frames][len]
+    size_t len = 1;                               // values per frame of a temporal (distance_pair: |a| * |b|)
+    std::vector<float> agg_mean, agg_var, agg_ext;   // len > 1: per-frame mean / population variance / (min, max) (md_script_aggregate_t)
     // sdf statics
     int2* d_unwrap = nullptr; uint32_t n_unwrap = 0;
     // density statics (from the initial frame's cell)
@@ -165,6 +167,17 @@ static void build_unwrap_pairs(std::vector<int2>& out, size_t count, const std::
             }
         }
     }
+}
+
+// compute_min_max_mean_variance (md_script.c:5646-5677): min, max, mean and population variance of one frame's values, two passes in float
+static void fold_frame_values(const float* v, size_t len, float& mn, float& mx, float& mean, float& var) {
+    const float N = (float)len;
+    mn = FLT_MAX; mx = -FLT_MAX; float s1 = 0.0f, s2 = 0.0f;
+    for (size_t i = 0; i < len; ++i) { s1 += v[i]; mn = std::min(mn, v[i]); mx = std::max(mx, v[i]); }
+    s1 = s1 / N;
+    for (size_t i = 0; i < len; ++i) s2 += (v[i] - s1) * (v[i] - s1);
+    s2 = s2 / N;
+    mean = s1; var = s2;
 }
 
 static void destroy_plan(mdgpu_plan* p) {
@@ -311,6 +324,15 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.values.assign(num_frames, 0.0f);
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
             break; }
+        case MDGPU_OP_DISTANCE_PAIR: {
+            if (pr.h_idx[0].empty() || pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
+            pr.len = pr.h_idx[0].size() * pr.h_idx[1].size();
+            if (pr.len > 1000000) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': The size produced by the operation is " + std::to_string(pr.len) + ", which exceeds the upper limit of 1'000'000");   // :4056
+            e = dalloc(&pr.d_temporal, num_frames * pr.len);
+            pr.values.assign(num_frames * pr.len, 0.0f);
+            if (pr.len > 1) { pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f); }   // allocate_property_data :5618-5640
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = (int32_t)pr.len; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break; }
         case MDGPU_OP_RMSD: {   // an empty selection is valid and evaluates to 0 (_rmsd :4311, :4336-4338)
             std::vector<int2> pairs;   // without bonds md_util_unwrap_vec4 fails and its result is ignored (:4327): nothing is unwrapped
             build_unwrap_pairs(pairs, pr.h_idx[0].size(), p->conn_off, p->conn_idx);
@@ -352,7 +374,8 @@ int mdgpu_plan_clear(mdgpu_plan* p) {
         if (pr.d_frame_max) CUDA_TRY(cudaMemset(pr.d_frame_max, 0, sizeof(uint32_t) * p->num_frames));
         if (pr.d_frame_min64) CUDA_TRY(cudaMemset(pr.d_frame_min64, 0, sizeof(unsigned long long) * p->num_frames));
         if (pr.d_frame_max64) CUDA_TRY(cudaMemset(pr.d_frame_max64, 0, sizeof(unsigned long long) * p->num_frames));
-        if (pr.d_temporal) CUDA_TRY(cudaMemset(pr.d_temporal, 0, sizeof(float) * p->num_frames));
+        if (pr.d_temporal) CUDA_TRY(cudaMemset(pr.d_temporal, 0, sizeof(float) * p->num_frames * pr.len));
+        std::fill(pr.agg_mean.begin(), pr.agg_mean.end(), 0.0f); std::fill(pr.agg_var.begin(), pr.agg_var.end(), 0.0f); std::fill(pr.agg_ext.begin(), pr.agg_ext.end(), 0.0f);
         if (pr.d_keep) CUDA_TRY(cudaMemset(pr.d_keep, 0, sizeof(uint32_t) * p->num_frames * MDGPU_DIST_BINS));
         if (pr.d_keep64) CUDA_TRY(cudaMemset(pr.d_keep64, 0, sizeof(unsigned long long) * p->num_frames * MDGPU_DIST_BINS));
         std::fill(pr.values.begin(), pr.values.end(), 0.0f);
@@ -525,6 +548,9 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             launch_density(a, B, s.stream);
             if (p->timing) { cudaEventRecord(tl.b, s.stream); tl.kind = 2; p->timed.push_back(tl); }
             break; }
+        case MDGPU_OP_DISTANCE_PAIR:
+            launch_distance_pair(fr, s.d_cells, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), pr.d_idx[1], (uint32_t)pr.h_idx[1].size(), pr.d_temporal, frame0, s.stream);
+            break;
         case MDGPU_OP_RMSD: {
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "rmsd '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
             RmsdArgs a{};
@@ -933,10 +959,14 @@ int mdgpu_plan_sync(mdgpu_plan* p) {
             const float rad = pr.re * 0.5f;   // value_range {-rad, rad} (:4983-4995)
             pr.data.min_range[0] = -rad; pr.data.max_range[0] = rad;
         } else {
-            CUDA_TRY(cudaMemcpy(pr.values.data(), pr.d_temporal, sizeof(float) * F, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(pr.values.data(), pr.d_temporal, sizeof(float) * F * pr.len, cudaMemcpyDeviceToHost));
             pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;
-            for (uint32_t f : done) { pr.data.min_value = std::min(pr.data.min_value, pr.values[f]); pr.data.max_value = std::max(pr.data.max_value, pr.values[f]); }
-            if (pr.op == MDGPU_OP_DISTANCE || pr.op == MDGPU_OP_DISTANCE_MIN || pr.op == MDGPU_OP_DISTANCE_MAX) { pr.data.min_range[0] = 0.0f; pr.data.max_range[0] = pr.data.max_value; }   // value_range {0, FLT_MAX} (:3884)
+            for (uint32_t f : done) {   // compute_min_max_mean_variance (md_script.c:5646-5677): two passes over the frame's values, in float
+                float mn, mx, s1, s2; fold_frame_values(pr.values.data() + (size_t)f * pr.len, pr.len, mn, mx, s1, s2);
+                pr.data.min_value = std::min(pr.data.min_value, mn); pr.data.max_value = std::max(pr.data.max_value, mx);
+                if (pr.len > 1) { pr.agg_mean[f] = s1; pr.agg_var[f] = s2; pr.agg_ext[2 * f] = mn; pr.agg_ext[2 * f + 1] = mx; }
+            }
+            if (pr.op == MDGPU_OP_DISTANCE || pr.op == MDGPU_OP_DISTANCE_MIN || pr.op == MDGPU_OP_DISTANCE_MAX || pr.op == MDGPU_OP_DISTANCE_PAIR) { pr.data.min_range[0] = 0.0f; pr.data.max_range[0] = pr.data.max_value; }   // value_range {0, FLT_MAX} (:3884)
             else { pr.data.min_range[0] = pr.data.min_value; pr.data.max_range[0] = pr.data.max_value; }
         }
     }
@@ -985,6 +1015,23 @@ int mdgpu_plan_property_frame_counts(mdgpu_plan* p, size_t prop, uint32_t frame,
         CUDA_TRY(cudaMemcpy(out_bins, pr.d_keep + (size_t)frame * MDGPU_DIST_BINS, sizeof(uint32_t) * MDGPU_DIST_BINS, cudaMemcpyDeviceToHost));
     }
     if (out_total) { unsigned long long t = 0; CUDA_TRY(cudaMemcpy(&t, pr.d_frame_total + frame, sizeof(t), cudaMemcpyDeviceToHost)); *out_total = t; }
+    return 0;
+}
+
+int mdgpu_plan_property_aggregate(mdgpu_plan* p, size_t prop, float* out_mean, float* out_var, float* out_ext, size_t num_frames) {
+    if (!p || prop >= p->props.size() || num_frames > p->num_frames) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_property_aggregate: invalid argument");
+    int rc = mdgpu_plan_sync(p); if (rc) return rc;
+    const Prop& pr = p->props[prop];
+    if (pr.agg_mean.empty()) return fail(MDGPU_ERR_INVALID_ARG, "property '%s' has one value per frame: no aggregate (md_script.c:5618)", pr.name.c_str());
+    if (out_mean) memcpy(out_mean, pr.agg_mean.data(), sizeof(float) * num_frames);
+    if (out_var) memcpy(out_var, pr.agg_var.data(), sizeof(float) * num_frames);
+    if (out_ext) memcpy(out_ext, pr.agg_ext.data(), sizeof(float) * 2 * num_frames);
+    return 0;
+}
+
+int mdgpu_debug_aggregate(const float* values, size_t count, float* out4) {
+    if (!values || !out4 || !count) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_debug_aggregate: invalid argument");
+    fold_frame_values(values, count, out4[0], out4[1], out4[2], out4[3]);
     return 0;
 }
 

@@ -306,6 +306,19 @@ __global__ void k_temporal(TemporalArgs a, int B) {
     a.out[a.frame0 + f] = out;
 }
 
+// One pair of md_util_min_distance / md_util_distance_array (md_util.c:8210-8297): no cell -> vec3_distance; orthorhombic ->
+// vec4_periodic_distance (core/md_vec_math.h:1268-1273, vec4_dot sums (x+y)+(z+w)); triclinic -> the 27-image minimum + vec3_length.
+MDG_D float pair_distance(float ax, float ay, float az, float bx, float by, float bz, uint32_t flags, const float ext[3], const float box[3][3]) {
+    float d[3] = { __fsub_rn(ax, bx), __fsub_rn(ay, by), __fsub_rn(az, bz) };
+    if (flags == 0) return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    if (flags & MDGPU_CELL_ORTHO) {
+        for (int k = 0; k < 3; ++k) if (ext[k] != 0.0f) d[k] = __fsub_rn(d[k], __fmul_rn(rintf(__fdiv_rn(d[k], ext[k])), ext[k]));
+        return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fadd_rn(__fmul_rn(d[2], d[2]), 0.0f)));
+    }
+    min_image_triclinic_p(d, box);
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+}
+
 // distance_min / distance_max (both md_util_min_distance, md_util.c:8242-8297): all pairs of two selections, one CTA per frame.
 // The minimum of floats is order independent, so the pairs are spread over the threads and reduced.
 __global__ void __launch_bounds__(256) k_min_distance(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ ia, uint32_t na,
@@ -318,7 +331,7 @@ __global__ void __launch_bounds__(256) k_min_distance(BatchFrames fr, const mdgp
     float best = 3.402823466e+38f;
     const unsigned long long npairs = (unsigned long long)na * nb;
     for (unsigned long long p = threadIdx.x; p < npairs; p += blockDim.x) {
-        const int a = ia[p / nb], b = ib[p % nb];
+        const int a = ia[p / nb], b = ib[p % nb];   // the three forms of pair_distance, written out (this kernel predates it; its SASS is the GPU-validated one)
         float d[3] = { __fsub_rn(x[a], x[b]), __fsub_rn(y[a], y[b]), __fsub_rn(z[a], z[b]) }, dist;
         if (uc.flags == 0) dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));   // vec3_distance
         else if (uc.flags & MDGPU_CELL_ORTHO) {   // vec4_periodic_distance core/md_vec_math.h:1268-1273; vec4_dot sums (x+y)+(z+w)
@@ -335,10 +348,32 @@ __global__ void __launch_bounds__(256) k_min_distance(BatchFrames fr, const mdgp
     if (threadIdx.x == 0) { for (int w = 1; w < 8; ++w) best = fminf(best, s_best[w]); out[frame0 + f] = best; }
 }
 
+// distance_pair(a, b) (_distance_pair md_script_functions.inl:3972 -> md_util_distance_array md_util.c:8210): the na x nb matrix of a frame,
+// row (frame0 + f) of a [num_frames][na*nb] temporal; one thread per pair.
+__global__ void __launch_bounds__(256) k_distance_pair(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ ia, uint32_t na,
+                                                       const int32_t* __restrict__ ib, uint32_t nb, float* __restrict__ out, uint32_t frame0) {
+    const int f = blockIdx.y;
+    const unsigned long long npairs = (unsigned long long)na * nb, p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const float* x = fr.xyz + (size_t)f * fr.frame_stride; const float* y = x + fr.axis_stride; const float* z = y + fr.axis_stride;
+    const mdgpu_unitcell_t uc = cells[f];
+    const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
+    const float box[3][3] = { { (float)uc.x, 0.f, 0.f }, { (float)uc.xy, (float)uc.y, 0.f }, { (float)uc.xz, (float)uc.yz, (float)uc.z } };
+    const int a = ia[p / nb], b = ib[p % nb];
+    out[(size_t)(frame0 + f) * npairs + p] = pair_distance(x[a], y[a], z[a], x[b], y[b], z[b], uc.flags, ext, box);
+}
+
 void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s) {
     if (!fr.count) return;
     k_min_distance<<<fr.count, 256, 0, s>>>(fr, d_cells, d_ia, na, d_ib, nb, d_out, frame0);
     note_launch("k_min_distance", s);
+}
+
+void launch_distance_pair(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s) {
+    const unsigned long long npairs = (unsigned long long)na * nb;
+    if (!fr.count || !npairs) return;
+    k_distance_pair<<<dim3((unsigned)((npairs + 255) / 256), fr.count), 256, 0, s>>>(fr, d_cells, d_ia, na, d_ib, nb, d_out, frame0);
+    note_launch("k_distance_pair", s);
 }
 
 // fold of an integer accumulator into the float mean the property data exposes: (float)((double)count / (double)n), IEEE on the device

@@ -612,7 +612,6 @@ __global__ void __launch_bounds__(32) k_rmsd(RmsdArgs a, int B) {
     a.out[a.frame0 + f] = (float)sqrt(d_sum / w_sum);
 }
 
-#ifndef MDG_HOST_EMULATION   // tests/emul compiles this file with g++ to run the one-thread-per-item kernels on the CPU; it has no launchers
 void launch_rmsd(const RmsdArgs& a, int B, cudaStream_t s) {
     if (!a.n || B <= 0) return;   // empty selection: the property stays 0 (:4311)
     k_rmsd<<<B, 32, 0, s>>>(a, B);
@@ -629,6 +628,5 @@ void launch_sdf(const SdfArgs& a, int B, bool tri, cudaStream_t s) {
     if (tri) k_sdf_scatter<true><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); else k_sdf_scatter<false><<<g2, SDF_WARPS * 32, 0, s>>>(a, B);
     note_launch("k_sdf_scatter", s);
 }
-#endif
 
 }  // namespace mdg

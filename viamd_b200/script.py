@@ -172,9 +172,9 @@ class _Parser:
             p = api.sdf(ident, st, trg, c)
         elif proc in ("density_x", "density_y", "density_z"):
             p = api.density(ident, "xyz".index(proc[-1]), self.selection())
-        elif proc in ("distance_min", "distance_max"):
+        elif proc in ("distance_min", "distance_max", "distance_pair"):
             a = self.selection(); self.expect("ch", ","); b = self.selection()
-            p = (api.distance_min if proc == "distance_min" else api.distance_max)(ident, a, b)
+            p = {"distance_min": api.distance_min, "distance_max": api.distance_max, "distance_pair": api.distance_pair}[proc](ident, a, b)
         elif proc == "rmsd":
             p = api.rmsd(ident, self.selection())   # an array of selections is flattened into their union (_internal_flatten_bf :4305)
         elif proc == "distance":
