@@ -840,6 +840,24 @@ double mdo_rmsd_frame(const float* x, const float* y, const float* z, const floa
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * plane(selection): _plane md_script_functions.inl:4755-4822. The atoms' positions with unit weights, made whole along the bonds (same
+ * local-index quirk), plain centre, covariance, eigenvectors sorted by eigenvalue (mat3_eigen); out = (normalised third axis, normal . com).
+ */
+static void normalize3(float v[3]);   /* vec3_normalize, defined with the temporals below */
+void mdo_plane_frame(const float* x, const float* y, const float* z, const int32_t* idx, size_t n, const uint32_t* conn_off, const int32_t* conn_idx,
+                     size_t conn_off_count, const mdo_unitcell_t* cell, float out[4]) {
+    v4* p = malloc(sizeof(v4) * (n ? n : 1));
+    for (size_t k = 0; k < n; ++k) { const int32_t a = idx[k]; p[k][0] = x[a]; p[k][1] = y[a]; p[k][2] = z[a]; p[k][3] = 1.0f; }
+    unwrap_vec4(p, n, conn_off, conn_idx, conn_off_count, cell);
+    float com[3]; com_v4(com, p, n);
+    const m3 E = m3_eigen_vectors(covariance_v4(p, n, com));
+    float nrm[3] = { E.e[2][0], E.e[2][1], E.e[2][2] };
+    normalize3(nrm);
+    out[0] = nrm[0]; out[1] = nrm[1]; out[2] = nrm[2]; out[3] = nrm[0] * com[0] + nrm[1] * com[1] + nrm[2] * com[2];
+    free(p);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * density_x/_y/_z: _internal_density (md_script_functions.inl:4825-4947), axis in 0..2
  */
 void mdo_density_frame(const float* x, const float* y, const float* z, const float* mass,

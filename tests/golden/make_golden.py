@@ -17,8 +17,8 @@ reference's outputs, so the tests need neither the reference nor the harness on 
   tric6.npz  : water n=6 sheared into a TRICLINIC cell that changes every frame, 4 frames: rt, rth (min:max), rtc (centre-of-mass references)
   tric6_rmsd.npz : the tric6 frames again: rmt = rmsd(residue(1:10)), rma = rmsd(atom(100:160)), rmo = rmsd(element('O')) — the triclinic wrap
                A * fract(I * r) of md_util_pbc_vec4, the triclinic bond-walk unwrap, non-contiguous selections
-  pairs6.npz : distance_pair() matrices (5 x 11 and 3 x 216 per frame) with the per-frame aggregates of a multi-valued temporal, on the
-               water6 and the tric6 frames
+  pairs6.npz : multi-valued temporals on the water6 and the tric6 frames, each with its per-frame aggregates: distance_pair() matrices
+               (5 x 11 and 3 x 216 per frame), com() of a residue / 30 atoms / one atom, plane() of 30 atoms / all oxygens
   xtc_cases.npz : XTC byte streams from the reference's writer + the reference reader's decode of them (see xtc_cases below)
   ala50.npz  : first 50 frames of datasets/1ALA-500.pdb (153 atoms, ortho cell 46.645 x 96.666 x 48.362), config 1:
                d = distance(1,10) (BASELINE config 1), rc = rdf(element('C'), element('O'), 10.0), dz = density_z(element('C')),
@@ -167,7 +167,8 @@ def pairs6(tmp):
     """Multi-valued temporals: distance_pair() matrices with their per-frame aggregates (mean / variance / extent, md_script.c:5646-5677),
     on the water6 frames (orthorhombic) and the tric6 frames (triclinic cell changing every frame)."""
     out = {}
-    script = "dp = distance_pair(atom(1:5), atom(20:30)); dpo = distance_pair(residue(1), element('O'));"
+    script = ("dp = distance_pair(atom(1:5), atom(20:30)); dpo = distance_pair(residue(1), element('O')); "
+              "c = com(residue(1)); ca = com(atom(1:30)); ci = com(5); pl = plane(atom(1:30)); plo = plane(element('O'));")
     w = np.load(os.path.join(HERE, "water6.npz")); t = np.load(os.path.join(HERE, "tric6.npz"))
     for tag, g, seed in (("w", w, "77"), ("t", t, "91")):
         gro, raw, o = os.path.join(tmp, tag + "p.gro"), os.path.join(tmp, tag + "p.raw"), os.path.join(tmp, tag + "p.out")
