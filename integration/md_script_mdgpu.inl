@@ -122,6 +122,17 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         out->idx_count[0] = mdgpu__flatten((int32_t*)out->idx[0], out->idx_count[0]);
         return true;
     }
+    if ((str_eq(pname, STR_LIT("com")) || str_eq(pname, STR_LIT("plane"))) && nargs == 1) {   /* _com :4726, _plane :4755: [F,3] / [F,4] temporals */
+        size_t ns = 0;
+        const bool is_com = str_eq(pname, STR_LIT("com"));
+        out->op = is_com ? MDGPU_OP_COM : MDGPU_OP_PLANE;
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
+        if (args[0]->data.type.base_type == TYPE_BITFIELD) {
+            if (ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false; }
+            if (is_com) out->com_args = 1u;
+        }
+        return true;
+    }
     if (str_eq(pname, STR_LIT("rmsd")) && nargs == 1) {   /* _rmsd :4287: the (flattened) selection against the initial configuration */
         out->op = MDGPU_OP_RMSD;
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], NULL, NULL, args[0], alloc)) < 0) goto dynamic;

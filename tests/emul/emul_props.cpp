@@ -31,3 +31,16 @@ extern "C" int emul_temporal(const float* frames, size_t frame_stride, size_t ax
     }
     return 0;
 }
+
+// k_com_rows: com(x) rows; pos (may be NULL) holds the [num_frames][4][3] argument positions k_arg_com would have left
+extern "C" int emul_com_rows(const float* frames, size_t frame_stride, size_t axis_stride, uint32_t num_frames, int atom, const float* pos, float* out) {
+    mdg::TemporalArgs a{};
+    a.frames.xyz = frames; a.frames.frame_stride = frame_stride; a.frames.axis_stride = axis_stride; a.frames.count = num_frames;
+    a.atom[0] = atom; a.out = out; a.frame0 = 0; a.pos = pos; a.com_mask = pos ? 1u : 0u;
+    blockDim = dim3(64, 1, 1); gridDim = dim3((num_frames + 63) / 64, 1, 1);   // launch_com_rows
+    for (unsigned bx = 0; bx < gridDim.x; ++bx) for (unsigned t = 0; t < 64; ++t) {
+        blockIdx.x = bx; blockIdx.y = 0; blockIdx.z = 0; threadIdx.x = t; threadIdx.y = 0; threadIdx.z = 0;
+        mdg::k_com_rows(a, (int)num_frames);
+    }
+    return 0;
+}

@@ -113,3 +113,24 @@ def test_distance_pair_limits():
     with pytest.raises(vb.MdgpuError):   # one value per frame: no aggregate
         plan.aggregate("d")
     plan.close()
+
+
+def test_com_and_plane_goldens():
+    """com(x) -> [F, 3] (k_arg_com + k_com_rows) and plane(selection) -> [F, 4] (k_plane), with aggregates, against pairs6.npz."""
+    p = load_golden("pairs6.npz")
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        g = load_golden(name); s = golden_system(g)
+        plan, cells = _plan(g, s, "c = com(residue(1)); ca = com(atom(1:30)); ci = com(5); pl = plane(atom(1:30)); plo = plane(element('O'));", batch_frames=3)
+        plan.eval_host_frames(g["frames"], cells, 0)
+        for key in ("c", "ca", "ci", "pl", "plo"):
+            k = f"{tag}_{key}"; d = plan.property_data(key)
+            assert tuple(d.dim[:2]) == tuple(p[k + "__dim"][:2])
+            assert np.array_equal(d.values, p[k + "__full"]), (k, d.values[:8], p[k + "__full"][:8])
+            mn, mx, r0, r1 = p[k + "__meta"]
+            assert d.min_value == mn and d.max_value == mx and d.min_range[0] == r0 and d.max_range[0] == r1
+            agg = plan.aggregate(key)
+            assert np.array_equal(agg["mean"], p[k + "__mean"]) and np.array_equal(agg["var"], p[k + "__var"]) and np.array_equal(agg["ext"], p[k + "__ext"]), k
+        plan.close()
+    import viamd_b200 as vb
+    with pytest.raises(vb.MdgpuError):   # "need at least 3 to compute a plane" (:4815)
+        vb.Plan(vb.water_system(4), [vb.plane("p", np.arange(2))], 2)

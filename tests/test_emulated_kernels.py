@@ -105,3 +105,24 @@ def test_k_distance_pair_source_matches_the_reference(emul_props):
             a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32); out = np.zeros(F * len(a) * len(b), np.float32)
             assert emul_props.emul_distance_pair(frames.ctypes.data_as(FP), 3 * na, na, F, cells, a.ctypes.data_as(IP), len(a), b.ctypes.data_as(IP), len(b), out.ctypes.data_as(FP)) == 0
             assert np.array_equal(out, p[f"{tag}_{key}__full"]), (tag, key)
+
+
+def test_k_plane_and_k_com_rows_sources_match_the_reference(emul, emul_props):
+    """k_plane (sdf.cu) and k_com_rows (props.cu) run on the CPU: plane() of 30 bonded atoms and of all oxygens, com() of one atom, ortho and
+    triclinic — bit-equal to the reference. (com() of a selection takes its position from k_arg_com, which is GPU-validated through distance();
+    here that slot is fed with the reference's own values to check the row store.)"""
+    p = load_golden("pairs6.npz")
+    emul.emul_plane.argtypes = [FP, C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(_Cell), IP, C.c_uint32, IP, C.c_uint32, FP]
+    emul_props.emul_com_rows.argtypes = [FP, C.c_size_t, C.c_size_t, C.c_uint32, C.c_int, FP, FP]
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        g = load_golden(name); s = golden_system(g); frames = np.ascontiguousarray(g["frames"], np.float32); F, _, na = frames.shape; cells = _cells(g)
+        for key, idx in (("pl", np.arange(30, dtype=np.int32)), ("plo", sel_element(s, 8))):
+            idx = np.ascontiguousarray(idx, np.int32); pairs = np.ascontiguousarray(unwrap_pairs(len(idx), s["conn_off"], s["conn_idx"])); out = np.zeros(4 * F, np.float32)
+            assert emul.emul_plane(frames.ctypes.data_as(FP), 3 * na, na, F, cells, idx.ctypes.data_as(IP), len(idx), pairs.ctypes.data_as(IP), len(pairs), out.ctypes.data_as(FP)) == 0
+            assert np.array_equal(out, p[f"{tag}_{key}__full"]), (tag, key)
+        out = np.zeros(3 * F, np.float32)
+        assert emul_props.emul_com_rows(frames.ctypes.data_as(FP), 3 * na, na, F, 4, None, out.ctypes.data_as(FP)) == 0
+        assert np.array_equal(out, p[f"{tag}_ci__full"])
+        pos = np.zeros((F, 4, 3), np.float32); pos[:, 0, :] = p[f"{tag}_ca__full"].reshape(F, 3); out = np.zeros(3 * F, np.float32)
+        assert emul_props.emul_com_rows(frames.ctypes.data_as(FP), 3 * na, na, F, 0, pos.ctypes.data_as(FP), out.ctypes.data_as(FP)) == 0
+        assert np.array_equal(out, p[f"{tag}_ca__full"])

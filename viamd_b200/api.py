@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libmdgpu.so")
 DIST_BINS = 1024
 VOL_DIM = 128
 
-OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
+OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14
 CELL_ORTHO, CELL_TRICLINIC, CELL_PBC_X, CELL_PBC_Y, CELL_PBC_Z, CELL_PBC_ALL = 1, 2, 4, 8, 16, 28
 
 
@@ -252,6 +252,16 @@ def distance_max(name, a_idx, b_idx):
 def distance_pair(name, a_idx, b_idx):
     """distance_pair(a, b): all |a| x |b| pair distances per frame, a temporal with |a|*|b| values per frame (md_script_functions.inl:3972)"""
     return Property(name, OP_DISTANCE_PAIR, [np.asarray(a_idx, np.int32), np.asarray(b_idx, np.int32)])
+
+
+def com(name, a):
+    """com(x): [F, 3] — the position of an atom (int) or the periodic centre of mass of a selection (index array), as distance() sees its arguments"""
+    return _temporal(name, OP_COM, (a,))
+
+
+def plane(name, idx):
+    """plane(selection): [F, 4] — unit normal of the best-fit plane through the atoms (third principal axis) and normal . centre (_plane :4755)"""
+    return Property(name, OP_PLANE, [np.asarray(idx, np.int32)])
 
 
 def rmsd(name, idx):

@@ -72,6 +72,7 @@ struct RmsdArgs {                    // rmsd(selection) against the initial fram
     uint32_t frame0;
 };
 void launch_rmsd(const RmsdArgs& a, int B, cudaStream_t s);
+void launch_plane(const RmsdArgs& a, int B, cudaStream_t s);   // plane(selection): out is [num_frames][4], scratch [B][n], init_xyz unused
 
 // props.cu
 struct DensityArgs {
@@ -91,6 +92,7 @@ struct TemporalArgs {
 };
 void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s);
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s);
+void launch_com_rows(const TemporalArgs& a, int B, cudaStream_t s);   // com(x): row (frame0 + f) of a [num_frames][3] temporal = position of argument 0
 void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s);
 void launch_distance_pair(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s);
 void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned long long n, cudaStream_t s);

@@ -333,6 +333,26 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             if (pr.len > 1) { pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f); }   // allocate_property_data :5618-5640
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = (int32_t)pr.len; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
             break; }
+        case MDGPU_OP_COM: {   // com(x): a [F, 3] temporal (TI_FLOAT3)
+            if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
+            pr.com_mask = (d.com_args & 1u) | (pr.h_idx[0].size() != 1 ? 1u : 0u);
+            pr.len = 3;
+            e = dalloc(&pr.d_temporal, num_frames * pr.len);
+            pr.values.assign(num_frames * pr.len, 0.0f);
+            pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f);
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 3; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break; }
+        case MDGPU_OP_PLANE: {   // plane(selection): a [F, 4] temporal (TI_FLOAT4)
+            if (pr.h_idx[0].size() < 3) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': Invalid number of positions, need at least 3 to compute a plane");   // :4815
+            std::vector<int2> pairs; build_unwrap_pairs(pairs, pr.h_idx[0].size(), p->conn_off, p->conn_idx);
+            pr.n_unwrap = (uint32_t)pairs.size();
+            e = upload(&pr.d_unwrap, pairs.data(), pairs.size());
+            pr.len = 4;
+            if (e == cudaSuccess) e = dalloc(&pr.d_temporal, num_frames * pr.len);
+            pr.values.assign(num_frames * pr.len, 0.0f);
+            pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f);
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 4; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break; }
         case MDGPU_OP_RMSD: {   // an empty selection is valid and evaluates to 0 (_rmsd :4311, :4336-4338)
             std::vector<int2> pairs;   // without bonds md_util_unwrap_vec4 fails and its result is ignored (:4327): nothing is unwrapped
             build_unwrap_pairs(pairs, pr.h_idx[0].size(), p->conn_off, p->conn_idx);
@@ -467,6 +487,8 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     CUDA_TRY(dalloc(&ps.d_sdf_mats, (size_t)p->B * pr.n_struct * 32));
                 } else if (pr.op == MDGPU_OP_RMSD) {
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * 2 * pr.h_idx[0].size()));   // [B][initial, current][atoms]
+                } else if (pr.op == MDGPU_OP_PLANE) {
+                    CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * pr.h_idx[0].size()));
                 } else if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
                     CUDA_TRY(dalloc(&ps.d_frame_bins64, (size_t)p->B * MDGPU_DIST_BINS));
                 } else if (pr.com_mask) {
@@ -547,6 +569,19 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); cudaEventRecord(tl.a, s.stream); }
             launch_density(a, B, s.stream);
             if (p->timing) { cudaEventRecord(tl.b, s.stream); tl.kind = 2; p->timed.push_back(tl); }
+            break; }
+        case MDGPU_OP_COM: {
+            TemporalArgs a{};
+            a.frames = fr; a.cells = s.d_cells; a.op = (int)pr.op; a.out = pr.d_temporal; a.frame0 = frame0;
+            a.atom[0] = pr.h_idx[0][0]; a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
+            if (pr.com_mask & 1u) launch_arg_com(fr, s.d_cells, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), p->d_mass, ps.d_argpos, 0, s.stream);
+            launch_com_rows(a, B, s.stream);
+            break; }
+        case MDGPU_OP_PLANE: {
+            RmsdArgs a{};
+            a.frames = fr; a.cells = s.d_cells; a.mass = p->d_mass; a.idx = pr.d_idx[0]; a.n = (uint32_t)pr.h_idx[0].size();
+            a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap; a.scratch_xyzw = ps.d_sdf_xyzw; a.out = pr.d_temporal; a.frame0 = frame0;
+            launch_plane(a, B, s.stream);
             break; }
         case MDGPU_OP_DISTANCE_PAIR:
             launch_distance_pair(fr, s.d_cells, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), pr.d_idx[1], (uint32_t)pr.h_idx[1].size(), pr.d_temporal, frame0, s.stream);

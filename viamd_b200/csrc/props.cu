@@ -306,6 +306,19 @@ __global__ void k_temporal(TemporalArgs a, int B) {
     a.out[a.frame0 + f] = out;
 }
 
+// com(x) (_com md_script_functions.inl:4726): the position coordinate_extract_com yields for the argument — an atom's coordinates or the
+// centre of mass k_arg_com left in a.pos — stored as the frame's 3 values.
+__global__ void k_com_rows(TemporalArgs a, int B) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= B) return;
+    float* o = a.out + (size_t)(a.frame0 + f) * 3;
+    if (a.com_mask & 1u) { const float* p = a.pos + (size_t)f * 4 * 3; o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; }
+    else {
+        const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride; const int at = a.atom[0];
+        o[0] = x[at]; o[1] = x[a.frames.axis_stride + at]; o[2] = x[2 * a.frames.axis_stride + at];
+    }
+}
+
 // One pair of md_util_min_distance / md_util_distance_array (md_util.c:8210-8297): no cell -> vec3_distance; orthorhombic ->
 // vec4_periodic_distance (core/md_vec_math.h:1268-1273, vec4_dot sums (x+y)+(z+w)); triclinic -> the 27-image minimum + vec3_length.
 MDG_D float pair_distance(float ax, float ay, float az, float bx, float by, float bz, uint32_t flags, const float ext[3], const float box[3][3]) {
@@ -385,6 +398,11 @@ __global__ void k_mean_u32(const uint32_t* __restrict__ in, float* __restrict__ 
 void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned long long n, cudaStream_t s) {
     k_mean_u32<<<148 * 4, 256, 0, s>>>(d_in, d_out, count, n);
     note_launch("k_mean_u32", s);
+}
+
+void launch_com_rows(const TemporalArgs& a, int B, cudaStream_t s) {
+    k_com_rows<<<(B + 63) / 64, 64, 0, s>>>(a, B);
+    note_launch("k_com_rows", s);
 }
 
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s) {

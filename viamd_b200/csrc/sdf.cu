@@ -612,6 +612,51 @@ __global__ void __launch_bounds__(32) k_rmsd(RmsdArgs a, int B) {
     a.out[a.frame0 + f] = (float)sqrt(d_sum / w_sum);
 }
 
+// plane(selection) (_plane md_script_functions.inl:4755-4822): positions with unit weights, bond walk, plain centre, covariance
+// (mat3_covariance_matrix_vec4 core/md_vec_math.c:101-156), eigenvectors sorted by eigenvalue (mat3_eigen :22-42); the frame's row is
+// (normalised third axis, normal . centre). One warp per frame, lane 0 does the ordered part, as in k_rmsd (init_xyz is not used).
+__global__ void __launch_bounds__(32) k_plane(RmsdArgs a, int B) {
+    const int f = blockIdx.x, lane = threadIdx.x;
+    if (f >= B) return;
+    const uint32_t n = a.n;
+    const mdgpu_unitcell_t uc = a.cells[f];
+    const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride;
+    float4* p = a.scratch_xyzw + (size_t)f * n;
+    for (uint32_t k = lane; k < n; k += 32) { const int at = a.idx[k]; p[k] = make_float4(x[at], x[a.frames.axis_stride + at], x[2 * a.frames.axis_stride + at], 1.0f); }
+    __syncwarp();
+    if (lane != 0) return;
+    float com[3];
+    unwrap_com(p, n, a.unwrap_pairs, a.n_unwrap, uc, com);
+    double C[3][3] = { { 0 } }; double ws = 0.0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const float4 v = p[k];
+        const float px = v.x - com[0], py = v.y - com[1], pz = v.z - com[2], w = v.w;
+        C[0][0] += w * px * px; C[0][1] += w * px * py; C[0][2] += w * px * pz;
+        C[1][0] += w * py * px; C[1][1] += w * py * py; C[1][2] += w * py * pz;
+        C[2][0] += w * pz * px; C[2][1] += w * pz * py; C[2][2] += w * pz * pz;
+        ws += w;
+    }
+    M3 cov; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) cov.e[i][j] = (float)(C[i][j] / ws);
+    const Svd s = m3_svd(cov);
+    const float mx = fmaxf(s.s[0], fmaxf(s.s[1], s.s[2]));
+    const float ev[3] = { s.s[0] / mx, s.s[1] / mx, s.s[2] / mx };
+    int l0 = 0, l1 = 1, l2 = 2, t;
+    if (ev[l0] < ev[l1]) { t = l0; l0 = l1; l1 = t; }
+    if (ev[l1] < ev[l2]) { t = l1; l1 = l2; l2 = t; }
+    if (ev[l0] < ev[l1]) { t = l0; l0 = l1; l1 = t; }
+    float nx = s.U.e[l2][0], ny = s.U.e[l2][1], nz = s.U.e[l2][2];
+    const float len = __fsqrt_rn((nx * nx + ny * ny) + nz * nz);   // vec3_normalize core/md_vec_math.h:505-514 (the threshold is a double literal)
+    if ((double)len > 1.0e-5) { nx = nx / len; ny = ny / len; nz = nz / len; } else { nx = ny = nz = 0.0f; }
+    float* o = a.out + (size_t)(a.frame0 + f) * 4;
+    o[0] = nx; o[1] = ny; o[2] = nz; o[3] = (nx * com[0] + ny * com[1]) + nz * com[2];
+}
+
+void launch_plane(const RmsdArgs& a, int B, cudaStream_t s) {
+    if (!a.n || B <= 0) return;
+    k_plane<<<B, 32, 0, s>>>(a, B);
+    note_launch("k_plane", s);
+}
+
 void launch_rmsd(const RmsdArgs& a, int B, cudaStream_t s) {
     if (!a.n || B <= 0) return;   // empty selection: the property stays 0 (:4311)
     k_rmsd<<<B, 32, 0, s>>>(a, B);

@@ -147,6 +147,18 @@ class _Parser:
         self.i = save
         return None
 
+    def single_selection(self) -> np.ndarray:
+        """a selection argument where the reference would treat an ARRAY of selections differently from their union (one position per
+        selection: coordinate_extract :1414): residue(a:b) over several residues standing alone is rejected instead of being flattened"""
+        save = self.i
+        if self.peek() == ("id", "residue"):
+            self.next(); self.expect("ch", "(")
+            lo, hi = self._range(len(np.asarray(self.sys.res_atom_offset)) - 1); self.expect("ch", ")")
+            if self.peek() in (("ch", ","), ("ch", ")")) and hi - lo > 1:
+                raise ScriptError("an array of selections as one argument (one centre of mass per selection) is not lowered")
+        self.i = save
+        return self.selection()
+
     def number(self) -> float:
         return float(self.expect("num")[1])
 
@@ -154,7 +166,7 @@ class _Parser:
         """argument of distance/angle/dihedral: a 1-based atom index (-> int) or a selection (-> index array, centre of mass)"""
         if self.peek()[0] == "num":
             return int(float(self.expect("num")[1])) - 1   # md_script atom indices are 1-based
-        return self.selection()
+        return self.single_selection()
 
     def statement(self) -> api.Property:
         ident = self.expect("id")[1]; self.expect("ch", "=")
@@ -173,8 +185,12 @@ class _Parser:
         elif proc in ("density_x", "density_y", "density_z"):
             p = api.density(ident, "xyz".index(proc[-1]), self.selection())
         elif proc in ("distance_min", "distance_max", "distance_pair"):
-            a = self.selection(); self.expect("ch", ","); b = self.selection()
+            a = self.single_selection(); self.expect("ch", ","); b = self.single_selection()
             p = {"distance_min": api.distance_min, "distance_max": api.distance_max, "distance_pair": api.distance_pair}[proc](ident, a, b)
+        elif proc == "com":
+            p = api.com(ident, self.index())
+        elif proc == "plane":
+            p = api.plane(ident, self.single_selection())
         elif proc == "rmsd":
             p = api.rmsd(ident, self.selection())   # an array of selections is flattened into their union (_internal_flatten_bf :4305)
         elif proc == "distance":
