@@ -28,9 +28,9 @@ def build(name: str) -> str:
     with open(os.path.join(HERE, "build", f"{name}_nolaunch.cu"), "w") as f:
         f.write(stripped)
     # no -mfma / -march: a*b+c must stay two roundings, as under nvcc --fmad=false
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", "-x", "c++", f"-I{CUDA_INC}", f"-I{HERE}",
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", "-x", "c++", f"-I{CUDA_INC}", f"-I{HERE}",
                            f"-I{os.path.join(HERE, 'build')}", wrap, "-o", out,
-                           f"-L{CUDA_LIB}", f"-Wl,-rpath,{CUDA_LIB}", "-lcudart"])   # the (never called) launchers reference cudaMemsetAsync etc.
+                           f"-L{CUDA_LIB}", f"-Wl,-rpath,{CUDA_LIB}", "-lcudart", "-lpthread"])   # the (never called) launchers reference cudaMemsetAsync etc.
     return out
 
 

@@ -1,10 +1,15 @@
 // cuda_emul.h — TEST INFRASTRUCTURE: lets g++ compile a .cu file of the product as plain C++ so that kernels whose threads do not
 // cooperate (one thread, or one leading lane, per work item) can be EXECUTED on the CPU, single-source, against the oracle.
 //
-// Under g++ cuda_runtime.h already turns __device__/__global__/__host__/__shared__ into nothing and provides float4/int2/dim3 and the
-// make_* helpers. What is added here: the built-in index variables, the IEEE-rounded arithmetic intrinsics (the host build uses
-// -O2 -ffp-contract=off -fno-fast-math without -mfma, so a*b+c is never fused, as with nvcc --fmad=false), and compile-only stubs
-// for the warp-cooperative intrinsics (kernels that use them are compiled but must not be called through this header).
+// Under g++ cuda_runtime.h already turns __device__/__global__/__host__ into nothing and provides float4/int2/dim3 and the make_*
+// helpers. What is added here: the built-in index variables, the IEEE-rounded arithmetic intrinsics (the host build uses
+// -O2 -ffp-contract=off -fno-fast-math without -mfma, so a*b+c is never fused, as with nvcc --fmad=false), atomics, and two ways to run a kernel:
+//   * thread by thread (the caller loops over blockIdx / threadIdx and calls the kernel function): enough for kernels whose threads do
+//     not cooperate; the warp/block collectives abort if reached;
+//   * emul_launch(grid, block, fn): every thread of a block is a host thread, blocks run one after the other; __syncthreads / __syncwarp
+//     are barriers, the warp collectives (__shfl_*_sync, __ballot_sync, __any/__all_sync, __reduce_*_sync) exchange through a per-warp
+//     buffer, `__shared__` variables are function-local statics (one block at a time, so one copy is what a block sees). Threads that
+//     return drop out of the barriers, as exited threads do on the device. Lanes named in a collective's mask must all reach it.
 #pragma once
 #define MDG_HOST_EMULATION 1
 #include <cuda_runtime.h>
@@ -13,6 +18,14 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <barrier>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#undef __shared__
+#define __shared__ static
 
 #undef __noinline__
 #define __noinline__ __attribute__((noinline))
@@ -40,27 +53,73 @@ static inline unsigned long long __float2ull_rn(float a) { return (unsigned long
 static inline int __float2int_rn(float a) { return (int)rintf(a); }
 static inline int __float2int_rz(float a) { return (int)a; }
 static inline int __float2int_rd(float a) { return (int)floorf(a); }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
 
-// compile-only stubs (abort when executed)
-#define MDG_EMUL_STUB { abort(); }
-static inline void __syncthreads() MDG_EMUL_STUB
-template <typename T> static inline T __shfl_sync(unsigned, T, int, int = 32) MDG_EMUL_STUB
-template <typename T> static inline T __shfl_up_sync(unsigned, T, unsigned, int = 32) MDG_EMUL_STUB
-template <typename T> static inline T __shfl_down_sync(unsigned, T, unsigned, int = 32) MDG_EMUL_STUB
-template <typename T> static inline T __shfl_xor_sync(unsigned, T, int, int = 32) MDG_EMUL_STUB
-static inline unsigned __ballot_sync(unsigned, int) MDG_EMUL_STUB
-static inline int __any_sync(unsigned, int) MDG_EMUL_STUB
-static inline int __all_sync(unsigned, int) MDG_EMUL_STUB
-static inline unsigned __reduce_or_sync(unsigned, unsigned) MDG_EMUL_STUB
-static inline unsigned __reduce_add_sync(unsigned, unsigned) MDG_EMUL_STUB
-static inline unsigned __reduce_max_sync(unsigned, unsigned) MDG_EMUL_STUB
-static inline unsigned __reduce_min_sync(unsigned, unsigned) MDG_EMUL_STUB
-static inline unsigned __activemask() MDG_EMUL_STUB
+// ---------------------------------------------------------------------------------------------- block / warp cooperation (emul_launch)
+struct EmulWarp { std::unique_ptr<std::barrier<>> bar; unsigned long long slot[32]; };
+struct EmulBlock { std::unique_ptr<std::barrier<>> bar; std::vector<EmulWarp> warps; };
+static thread_local EmulBlock* emul_block = nullptr;
+static thread_local int emul_lane = 0, emul_warp = 0;
+
+static inline EmulWarp& emul_w() { if (!emul_block) abort(); /* collective reached in thread-by-thread mode */ return emul_block->warps[emul_warp]; }
+static inline void __syncthreads() { if (!emul_block) abort(); emul_block->bar->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { if (emul_block) emul_w().bar->arrive_and_wait(); }   // thread-by-thread mode: lanes run one after the other
+
+// every lane publishes a value, then reads the slot of `src` (two warp barriers: publish | read)
+template <typename T> static inline T emul_exchange(T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle of more than 8 bytes");
+    EmulWarp& w = emul_w(); unsigned long long bits = 0; memcpy(&bits, &v, sizeof(T)); w.slot[emul_lane] = bits;
+    w.bar->arrive_and_wait();
+    T r; const unsigned long long got = w.slot[src & 31]; memcpy(&r, &got, sizeof(T));
+    w.bar->arrive_and_wait();
+    return r;
+}
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32) { return emul_exchange(v, (emul_lane & ~(width - 1)) | (src & (width - 1))); }
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32) { const int s = emul_lane - (int)d; return emul_exchange(v, s >= (emul_lane & ~(width - 1)) ? s : emul_lane); }
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned d, int width = 32) { const int s = emul_lane + (int)d; return emul_exchange(v, s <= (emul_lane | (width - 1)) ? s : emul_lane); }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) { const int s = emul_lane ^ m; return emul_exchange(v, s <= (emul_lane | (width - 1)) ? s : emul_lane); }
+// gather of one value per lane over the lanes of `mask`, folded by f
+template <typename F> static inline unsigned emul_fold(unsigned mask, unsigned v, unsigned init, F f) {
+    EmulWarp& w = emul_w(); w.slot[emul_lane] = v;
+    w.bar->arrive_and_wait();
+    unsigned r = init; for (int l = 0; l < 32; ++l) if (mask >> l & 1u) r = f(r, (unsigned)w.slot[l], l);
+    w.bar->arrive_and_wait();
+    return r;
+}
+static inline unsigned __ballot_sync(unsigned mask, int pred) { return emul_fold(mask, pred ? 1u : 0u, 0u, [](unsigned r, unsigned v, int l) { return r | (v << l); }); }
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) { return emul_fold(mask, v, 0u, [](unsigned r, unsigned x, int) { return r | x; }); }
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return emul_fold(mask, v, 0u, [](unsigned r, unsigned x, int) { return r + x; }); }
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return emul_fold(mask, v, 0u, [](unsigned r, unsigned x, int) { return r > x ? r : x; }); }
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) { return emul_fold(mask, v, 0xffffffffu, [](unsigned r, unsigned x, int) { return r < x ? r : x; }); }
+
+// run fn() as every thread of every block of the grid; blocks one after the other, the threads of a block concurrently
+static inline void emul_launch(dim3 grid, dim3 block, const std::function<void()>& fn) {
+    const int nthreads = (int)(block.x * block.y * block.z), nwarps = (nthreads + 31) / 32;
+    for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
+        EmulBlock blk; blk.bar = std::make_unique<std::barrier<>>(nthreads); blk.warps.resize(nwarps);
+        for (int w = 0; w < nwarps; ++w) { blk.warps[w].bar = std::make_unique<std::barrier<>>(std::min(32, nthreads - 32 * w)); memset(blk.warps[w].slot, 0, sizeof(blk.warps[w].slot)); }
+        std::vector<std::thread> th; th.reserve(nthreads);
+        for (int t = 0; t < nthreads; ++t) th.emplace_back([&, t]() {
+            gridDim = grid; blockDim = block; blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+            threadIdx.x = t % block.x; threadIdx.y = (t / block.x) % block.y; threadIdx.z = t / (block.x * block.y);
+            emul_block = &blk; emul_lane = t & 31; emul_warp = t >> 5;
+            fn();
+            blk.warps[emul_warp].slot[emul_lane] = 0;        // an exited lane contributes 0 to later ballots
+            blk.warps[emul_warp].bar->arrive_and_drop(); blk.bar->arrive_and_drop();
+            emul_block = nullptr;
+        });
+        for (auto& t : th) t.join();
+    }
+}
+
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
-template <typename T, typename U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = (T)(o + (T)v); return o; }
-template <typename T> static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
-template <typename T> static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
-template <typename T> static inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+template <typename T, typename U> static inline T atomicAdd(T* p, U v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_RELAXED); }
+static inline float atomicAdd(float* p, float v) { float o = *p, n; do { n = o + v; } while (!__atomic_compare_exchange(p, &o, &n, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)); return o; }
+template <typename T> static inline T atomicMax(T* p, T v) { T o = *p; while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+template <typename T> static inline T atomicMin(T* p, T v) { T o = *p; while (o > v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+template <typename T> static inline T atomicExch(T* p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+template <typename T> static inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+template <typename T> static inline T atomicCAS(T* p, T cmp, T v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED); return cmp; }

@@ -44,3 +44,12 @@ extern "C" int emul_com_rows(const float* frames, size_t frame_stride, size_t ax
     }
     return 0;
 }
+
+// k_min_distance: a block-cooperative kernel (warp shuffles + shared memory + __syncthreads) that has passed on the GPU, run through
+// emul_launch as a check of the cooperative emulation.
+extern "C" int emul_min_distance(const float* frames, size_t frame_stride, size_t axis_stride, uint32_t num_frames, const mdgpu_unitcell_t* cells,
+                                 const int32_t* ia, uint32_t na, const int32_t* ib, uint32_t nb, float* out) {
+    mdg::BatchFrames fr{}; fr.xyz = frames; fr.frame_stride = frame_stride; fr.axis_stride = axis_stride; fr.count = num_frames;
+    emul_launch(dim3(num_frames, 1, 1), dim3(256, 1, 1), [&]() { mdg::k_min_distance(fr, cells, ia, na, ib, nb, out, 0); });   // launch_min_distance
+    return 0;
+}

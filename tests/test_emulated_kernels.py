@@ -126,3 +126,19 @@ def test_k_plane_and_k_com_rows_sources_match_the_reference(emul, emul_props):
         pos = np.zeros((F, 4, 3), np.float32); pos[:, 0, :] = p[f"{tag}_ca__full"].reshape(F, 3); out = np.zeros(3 * F, np.float32)
         assert emul_props.emul_com_rows(frames.ctypes.data_as(FP), 3 * na, na, F, 0, pos.ctypes.data_as(FP), out.ctypes.data_as(FP)) == 0
         assert np.array_equal(out, p[f"{tag}_ca__full"])
+
+
+def test_cooperative_emulation_reproduces_a_gpu_validated_kernel(emul_props):
+    """Check of emul_launch (threads of a block as host threads, barriers, warp shuffles): k_min_distance has passed on the B200 against
+    these goldens and must reproduce them when run this way (256 threads per block, shuffle reduction, shared memory, __syncthreads)."""
+    emul_props.emul_min_distance.argtypes = [FP, C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(_Cell), IP, C.c_uint32, IP, C.c_uint32, FP]
+    g = load_golden("water6.npz"); s = golden_system(g); frames = np.ascontiguousarray(g["frames"], np.float32); F, _, na = frames.shape; cells = _cells(g)
+    h = np.nonzero(np.asarray(s["z"]) == 1)[0].astype(np.int32)
+    for key, a, b in (("dmn", np.arange(0, 3), np.arange(99, 648)), ("dmx", np.arange(0, 30), np.arange(99, 151)), ("dmh", h, np.arange(299, 400))):
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32); out = np.zeros(F, np.float32)
+        assert emul_props.emul_min_distance(frames.ctypes.data_as(FP), 3 * na, na, F, cells, a.ctypes.data_as(IP), len(a), b.ctypes.data_as(IP), len(b), out.ctypes.data_as(FP)) == 0
+        assert np.array_equal(out, g[f"{key}__full"]), key
+    g = load_golden("tric6.npz"); frames = np.ascontiguousarray(g["frames"], np.float32); F, _, na = frames.shape; cells = _cells(g)
+    a = np.arange(0, 30, dtype=np.int32); b = np.arange(99, 151, dtype=np.int32); out = np.zeros(F, np.float32)
+    assert emul_props.emul_min_distance(frames.ctypes.data_as(FP), 3 * na, na, F, cells, a.ctypes.data_as(IP), len(a), b.ctypes.data_as(IP), len(b), out.ctypes.data_as(FP)) == 0
+    assert np.array_equal(out, g["dmt__full"])
