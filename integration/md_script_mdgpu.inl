@@ -133,6 +133,16 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         }
         return true;
     }
+    if (str_eq(pname, STR_LIT("count")) && nargs == 1 && args[0]->type == AST_PROC_CALL && args[0]->proc && str_eq(args[0]->proc->name, STR_LIT("within")) &&
+        md_array_size(args[0]->children) == 2) {   /* count(within(radius, selection)): _within_expl_flt :2485 evaluated per frame on the device, _count :2868 */
+        ast_node_t** w = args[0]->children; size_t ns = 0;
+        if (!(w[0]->flags & FLAG_CONSTANT) || w[0]->data.type.base_type != TYPE_FLOAT) goto dynamic;
+        out->op = MDGPU_OP_WITHIN_COUNT; out->cutoff_max = *(const float*)w[0]->data.ptr;
+        if (w[1]->data.type.base_type != TYPE_BITFIELD) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': within() is lowered for a selection argument only", STR_ARG(ident)); return false; }
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, w[1], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
+        if (ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false; }
+        return true;
+    }
     if (str_eq(pname, STR_LIT("rmsd")) && nargs == 1) {   /* _rmsd :4287: the (flattened) selection against the initial configuration */
         out->op = MDGPU_OP_RMSD;
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], NULL, NULL, args[0], alloc)) < 0) goto dynamic;

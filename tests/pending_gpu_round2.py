@@ -134,3 +134,27 @@ def test_com_and_plane_goldens():
     import viamd_b200 as vb
     with pytest.raises(vb.MdgpuError):   # "need at least 3 to compute a plane" (:4815)
         vb.Plan(vb.water_system(4), [vb.plane("p", np.arange(2))], 2)
+
+
+def test_count_within_goldens_and_oracle():
+    """count(within(radius, selection)) (cells.cu cell lists over all atoms + k_within_mark / k_within_count): the reference's counts on the
+    water goldens, the oracle in the triclinic cell and with a non-periodic axis; together with an rdf in the same plan (shared slots)."""
+    g = load_golden("water6.npz"); s = golden_system(g)
+    plan, cells = _plan(g, s, "cw = count(within(4.0, residue(1))); cw2 = count(within(7.5, atom(10:12))); r = rdf(element('O'), element('O'), 6.0);", batch_frames=3)
+    plan.eval_host_frames(g["frames"], cells, 0)
+    assert np.array_equal(plan.property_data("cw").values, g["cw__full"]) and np.array_equal(plan.property_data("cw2").values, g["cw2__full"])
+    assert np.array_equal(plan.property_data("r").values[:1024], g["r__full"][:1024]) or np.allclose(plan.property_data("r").values[:1024], g["r__full"][:1024], rtol=1e-5, atol=1e-6)
+    plan.close()
+    import viamd_b200 as vb
+    for name, flags, sel, radius in (("tric6.npz", None, np.arange(0, 30), 5.0), ("water6.npz", 1 | 4 | 8, np.arange(0, 12), 6.5)):
+        g = load_golden(name); s = golden_system(g); F = g["frames"].shape[0]
+        fl = g["cell_flags"] if flags is None else np.full(F, flags, np.uint32)
+        plan = vb.Plan(vb_system(s), [vb.count_within("c", radius, sel)], F)
+        cells = [vb_cell(g["cells"][f], fl[f]) for f in range(F)]
+        plan.eval_host_frames(g["frames"], cells, 0)
+        got = plan.property_data("c").values
+        for f in range(F):
+            assert got[f] == len(O.within(*g["frames"][f], np.asarray(sel, np.int32), radius, cell_from_row(g["cells"][f], fl[f]))), (name, f)
+        plan.close()
+    with pytest.raises(vb.MdgpuError):
+        vb.Plan(vb.water_system(4), [vb.count_within("c", 0.0, np.arange(3))], 2)

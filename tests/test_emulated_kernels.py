@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
-from helpers import load_golden, golden_system, sel_element  # noqa: E402
+import oracle_lib as O  # noqa: E402
+from helpers import load_golden, golden_system, sel_element, cell_from_row  # noqa: E402
 
 
 class _Cell(C.Structure):   # mdgpu_unitcell_t
@@ -142,3 +143,38 @@ def test_cooperative_emulation_reproduces_a_gpu_validated_kernel(emul_props):
     a = np.arange(0, 30, dtype=np.int32); b = np.arange(99, 151, dtype=np.int32); out = np.zeros(F, np.float32)
     assert emul_props.emul_min_distance(frames.ctypes.data_as(FP), 3 * na, na, F, cells, a.ctypes.data_as(IP), len(a), b.ctypes.data_as(IP), len(b), out.ctypes.data_as(FP)) == 0
     assert np.array_equal(out, g["dmt__full"])
+
+
+@pytest.fixture(scope="module")
+def emul_within():
+    import build_emul
+    lib = C.CDLL(build_emul.build("within", ["cells", "within"]))
+    lib.emul_within_count.argtypes = [FP, C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(_Cell), C.c_uint32, IP, C.c_uint32, C.c_float, C.c_uint32, FP]
+    return lib
+
+
+def _within(lib, g, sel, radius, flags=None):
+    frames = np.ascontiguousarray(g["frames"], np.float32); F, _, na = frames.shape; cells = _cells(g)
+    if flags is not None:
+        for f in range(F): cells[f].flags = flags
+    sel = np.ascontiguousarray(sel, np.int32); out = np.zeros(F, np.float32)
+    rc = lib.emul_within_count(frames.ctypes.data_as(FP), 3 * na, na, F, cells, na, sel.ctypes.data_as(IP), len(sel), radius, 1 << 16, out.ctypes.data_as(FP))
+    assert rc == 0
+    return out
+
+
+def test_count_within_pipeline_matches_the_reference(emul_within):
+    """count(within(radius, selection)) end to end on the CPU: the cell-list kernels of cells.cu (k_frame_geom, k_bin_points, k_scan_cells,
+    k_scatter_points, k_aabb — GPU-validated) followed by the new k_within_mark / k_within_count, with the launch sequences of the product.
+    Equal to the reference's counts on the water goldens; equal to the (reference-pinned) oracle in the triclinic cell that changes every
+    frame, with one axis non-periodic (grid fitted to the data), and for an empty selection."""
+    g = load_golden("water6.npz")
+    assert np.array_equal(_within(emul_within, g, np.arange(0, 3), 4.0), g["cw__full"])
+    assert np.array_equal(_within(emul_within, g, np.arange(9, 12), 7.5), g["cw2__full"])
+    assert np.array_equal(_within(emul_within, g, np.zeros(0, np.int32), 4.0), np.zeros(g["frames"].shape[0], np.float32))
+    for name, flags, sel, radius in (("tric6.npz", None, np.arange(0, 30), 5.0), ("tric6.npz", None, np.arange(100, 103), 8.5),
+                                     ("water6.npz", 1 | 4 | 8, np.arange(0, 12), 6.5), ("water6.npz", 1 | 8 | 16, np.arange(300, 340), 3.0)):
+        g = load_golden(name); got = _within(emul_within, g, sel, radius, flags)
+        for f in range(g["frames"].shape[0]):
+            x, y, z = g["frames"][f]; cell = cell_from_row(g["cells"][f], g["cell_flags"][f] if flags is None else flags)
+            assert got[f] == len(O.within(x, y, z, np.asarray(sel, np.int32), radius, cell)), (name, flags, radius, f)

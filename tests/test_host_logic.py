@@ -71,6 +71,10 @@ def test_script_lowering(vb):
     for src in ("x = com(residue(1:3));", "x = plane(residue(1:3));", "x = distance(residue(1:2), 5);", "x = distance_pair(residue(1:2), element('O'));"):
         with pytest.raises(vb.ScriptError):   # one position per selection in the reference: not lowered, never flattened silently
             vb.compile_script(src, s)
+    cw = vb.compile_script("cw = count(within(4.5, residue(2)));", s)[0]
+    assert cw.op == vb.OP_WITHIN_COUNT and cw.cutoff_max == 4.5 and list(cw.idx[0]) == [3, 4, 5]
+    with pytest.raises(vb.ScriptError):
+        vb.compile_script("x = count(element('O'));", s)
     rm = vb.compile_script("rm = rmsd(residue(2:4));", s)[0]                           # array of selections -> their union
     assert rm.op == vb.OP_RMSD and list(rm.idx[0]) == list(range(3, 12))
     # array-of-selections reference -> centre-of-mass groups with offsets; selection arguments of the temporals -> com_args; pair minimum

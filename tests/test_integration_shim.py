@@ -17,6 +17,9 @@ TOOL = os.path.join(ROOT, "oracle", "build", "synth_tool")
 SCRIPT = ("r = rdf(element('O'), element('O'), 6.0); v = sdf(residue(1:20), element('O'), 5.0); dz = density_z(element('O')); "
           "d = distance(1,10); rr = rdf(element('O'), element('H'), 1.5:6.0); a = angle(1,2,3); t = dihedral(1,4,7,10); "
           "rc = rdf(residue(1:20), element('O'), 5.0);")
+# forms added after the last GPU run: lowered identically by the shim and the Python mirror (CPU check); their GPU tests are in pending_gpu_round2.py
+SCRIPT_NEW = ("rm = rmsd(residue(1:10)); dp = distance_pair(atom(1:5), atom(20:30)); c = com(residue(1)); ci = com(5); pl = plane(atom(1:30)); "
+              "cw = count(within(4.0, residue(1))); dmn = distance_min(residue(1), atom(100:648)); dc = distance(residue(1), residue(5));")
 
 
 def _need():
@@ -45,9 +48,10 @@ def test_shim_lowering_matches_python_lowering(tmp_path):
     import viamd_b200 as vb
     gro = str(tmp_path / "w6.gro"); out = str(tmp_path / "low.bin")
     subprocess.check_call([TOOL, "water-gro", "6", "77", gro])
-    subprocess.check_call([SHIM, "lower", "--sys", gro, "--script", SCRIPT, "--out", out], stdout=subprocess.DEVNULL)
+    script = SCRIPT + " " + SCRIPT_NEW
+    subprocess.check_call([SHIM, "lower", "--sys", gro, "--script", script, "--out", out], stdout=subprocess.DEVNULL)
     low = _read_lowered(out)
-    props = vb.compile_script(SCRIPT, vb.water_system(6))
+    props = vb.compile_script(script, vb.water_system(6))
     assert [p["name"] for p in low] == [p.name for p in props]
     for a, b in zip(low, props):
         assert a["op"] == b.op and a["cmin"] == np.float32(b.cutoff_min) and a["cmax"] == np.float32(b.cutoff_max), a["name"]

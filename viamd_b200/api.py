@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libmdgpu.so")
 DIST_BINS = 1024
 VOL_DIM = 128
 
-OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14
+OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE, OP_WITHIN_COUNT = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15
 CELL_ORTHO, CELL_TRICLINIC, CELL_PBC_X, CELL_PBC_Y, CELL_PBC_Z, CELL_PBC_ALL = 1, 2, 4, 8, 16, 28
 
 
@@ -262,6 +262,12 @@ def com(name, a):
 def plane(name, idx):
     """plane(selection): [F, 4] — unit normal of the best-fit plane through the atoms (third principal axis) and normal . centre (_plane :4755)"""
     return Property(name, OP_PLANE, [np.asarray(idx, np.int32)])
+
+
+def count_within(name, radius, sel_idx):
+    """count(within(radius, selection)): per frame, the number of atoms of the system within `radius` of any atom of the selection, the
+    selection itself excluded (_within_expl_flt md_script_functions.inl:2485, _count :2868) — a dynamic selection evaluated on the device"""
+    return Property(name, OP_WITHIN_COUNT, [np.asarray(sel_idx, np.int32)], cutoff_max=float(radius))
 
 
 def rmsd(name, idx):

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmdgpu.so")
-SOURCES = ["cells.cu", "rdf.cu", "sdf.cu", "props.cu", "synth.cu", "xtc.cu", "plan.cu"]
+SOURCES = ["cells.cu", "rdf.cu", "sdf.cu", "props.cu", "within.cu", "synth.cu", "xtc.cu", "plan.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",            # no implicit FMA contraction: float results must match the reference's scalar/AVX code

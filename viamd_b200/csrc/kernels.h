@@ -74,6 +74,18 @@ struct RmsdArgs {                    // rmsd(selection) against the initial fram
 void launch_rmsd(const RmsdArgs& a, int B, cudaStream_t s);
 void launch_plane(const RmsdArgs& a, int B, cudaStream_t s);   // plane(selection): out is [num_frames][4], scratch [B][n], init_xyz unused
 
+// within.cu — count(within(radius, selection))
+struct WithinArgs {
+    const FrameGeom* geom;           // grid of ALL atoms: cell extent ceil(radius/6)*6, cutoff = radius (get_spatial_acc)
+    CellList trg, ref;               // all atoms (clamped cells) / the selection's atoms (home grid)
+    const int32_t* sel; uint32_t n_sel;
+    uint32_t num_atoms;
+    uint8_t* flags;                  // [B][num_atoms], zeroed by the launcher
+    float* out;                      // [num_frames]
+    uint32_t frame0;
+};
+void launch_within_count(const WithinArgs& a, int B, bool tri, int sm_count, cudaStream_t s);
+
 // props.cu
 struct DensityArgs {
     BatchFrames frames; const int32_t* idx; uint32_t n; const float* mass; int axis;

@@ -78,6 +78,7 @@ struct PropScratch {   // per (stream slot, property)
     float4* d_sdf_xyzw = nullptr; float* d_sdf_ref0 = nullptr; float* d_sdf_mats = nullptr;
     float* d_com = nullptr;   // rdf with centre-of-mass references: [B][n_struct][3]
     float* d_argpos = nullptr;   // distance/angle/dihedral with selection arguments: [B][4][3]
+    uint8_t* d_flags = nullptr;  // count(within()): [B][num_atoms]
     // rdf candidate lists (k_rdf_cull): [B][list_stride] entries, [B][cap] headers, [B] cursors
     uint32_t* d_pair_list = nullptr; uint4* d_list_hdr = nullptr; uint32_t* d_list_cursor = nullptr; size_t list_stride = 0;
 };
@@ -133,6 +134,9 @@ struct mdgpu_plan {
     bool dirty = true;   // device accumulators changed since the last fold into the host-visible property data
 };
 
+// get_spatial_acc (md_script_functions.inl:734-760): the system-wide grid of within() has cells of ceil(radius / 6) * 6
+static double within_cell_ext(float radius) { return ceil((double)radius / 6.0) * 6.0; }
+
 static int alloc_cell_list(CellList& cl, uint32_t B, uint32_t max_points, uint32_t cap) {
     cl.max_points = max_points; cl.cap = cap;
     CUDA_TRY(dalloc(&cl.sorted, (size_t)B * max_points));
@@ -187,7 +191,7 @@ static void destroy_plan(mdgpu_plan* p) {
     for (auto& s : p->slots) {
         for (auto& ps : s.ps) {
             cudaFree(ps.d_geom); cudaFree(ps.d_aabb); free_cell_list(ps.trg); free_cell_list(ps.ref);
-            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
+            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_flags); cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
         }
         cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
@@ -333,6 +337,12 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             if (pr.len > 1) { pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f); }   // allocate_property_data :5618-5640
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = (int32_t)pr.len; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
             break; }
+        case MDGPU_OP_WITHIN_COUNT:   // count(within(radius, selection)); an empty selection is valid (nothing is within reach of nothing)
+            if (!(pr.cutoff_max > 0.0f)) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': The supplied radius is negative or zero, please supply a positive value");   // :2528
+            e = dalloc(&pr.d_temporal, num_frames);
+            pr.values.assign(num_frames, 0.0f);
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break;
         case MDGPU_OP_COM: {   // com(x): a [F, 3] temporal (TI_FLOAT3)
             if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
             pr.com_mask = (d.com_args & 1u) | (pr.h_idx[0].size() != 1 ? 1u : 0u);
@@ -447,8 +457,8 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
         uint32_t cap = p->cell_cap;
         if (!cap) {
             uint64_t need = 1u << 16;   // floor: non-periodic axes get their extent from the data (AABB fit), unknown here
-            for (auto& pr : p->props) if (pr.needs_cells()) {
-                FrameGeom g; host_frame_geom(&g, first_cell, pr.cutoff_max, pr.cutoff_max, nullptr, 0xffffffffu);
+            for (auto& pr : p->props) if (pr.needs_cells() || pr.op == MDGPU_OP_WITHIN_COUNT) {
+                FrameGeom g; host_frame_geom(&g, first_cell, pr.op == MDGPU_OP_WITHIN_COUNT ? within_cell_ext(pr.cutoff_max) : (double)pr.cutoff_max, pr.cutoff_max, nullptr, 0xffffffffu);
                 need = std::max<uint64_t>(need, 2ull * std::max<uint64_t>(g.num_cells, g.num_home) + 2);
             }
             cap = (uint32_t)std::min<uint64_t>(need, 1u << 26);
@@ -485,6 +495,11 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * (pr.n_struct + 1) * pr.struct_size));
                     CUDA_TRY(dalloc(&ps.d_sdf_ref0, (size_t)p->B * 20));
                     CUDA_TRY(dalloc(&ps.d_sdf_mats, (size_t)p->B * pr.n_struct * 32));
+                } else if (pr.op == MDGPU_OP_WITHIN_COUNT) {
+                    CUDA_TRY(dalloc(&ps.d_geom, p->B)); CUDA_TRY(dalloc(&ps.d_aabb, (size_t)6 * p->B));
+                    int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)p->num_atoms, cap); if (rc) return rc;
+                    rc = alloc_cell_list(ps.ref, p->B, (uint32_t)std::max<size_t>(pr.h_idx[0].size(), 1), cap); if (rc) return rc;
+                    CUDA_TRY(dalloc(&ps.d_flags, (size_t)p->B * p->num_atoms));
                 } else if (pr.op == MDGPU_OP_RMSD) {
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * 2 * pr.h_idx[0].size()));   // [B][initial, current][atoms]
                 } else if (pr.op == MDGPU_OP_PLANE) {
@@ -569,6 +584,17 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); cudaEventRecord(tl.a, s.stream); }
             launch_density(a, B, s.stream);
             if (p->timing) { cudaEventRecord(tl.b, s.stream); tl.kind = 2; p->timed.push_back(tl); }
+            break; }
+        case MDGPU_OP_WITHIN_COUNT: {
+            const float* aabb = nullptr;
+            if (!all_pbc) { launch_aabb(fr, nullptr, (uint32_t)p->num_atoms, ps.d_aabb, s.stream); aabb = ps.d_aabb; }   // every atom of the system
+            launch_geom(s.d_cells, aabb, ps.d_geom, within_cell_ext(pr.cutoff_max), (double)pr.cutoff_max, p->cell_cap, B, s.d_err, s.stream);
+            launch_cell_list(0, fr, nullptr, nullptr, (uint32_t)p->num_atoms, ps.d_geom, ps.trg, 0, s.stream);
+            launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_geom, ps.ref, 0, s.stream);
+            WithinArgs a{};
+            a.geom = ps.d_geom; a.trg = ps.trg; a.ref = ps.ref; a.sel = pr.d_idx[0]; a.n_sel = (uint32_t)pr.h_idx[0].size();
+            a.num_atoms = (uint32_t)p->num_atoms; a.flags = ps.d_flags; a.out = pr.d_temporal; a.frame0 = frame0;
+            launch_within_count(a, B, tri, p->sm_count, s.stream);
             break; }
         case MDGPU_OP_COM: {
             TemporalArgs a{};

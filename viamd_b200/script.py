@@ -187,6 +187,10 @@ class _Parser:
         elif proc in ("distance_min", "distance_max", "distance_pair"):
             a = self.single_selection(); self.expect("ch", ","); b = self.single_selection()
             p = {"distance_min": api.distance_min, "distance_max": api.distance_max, "distance_pair": api.distance_pair}[proc](ident, a, b)
+        elif proc == "count":   # count(within(radius, selection)): the one dynamic selection the device path evaluates
+            if self.peek() != ("id", "within"): raise ScriptError("count() is lowered for within(radius, selection) only")
+            self.next(); self.expect("ch", "("); r = self.number(); self.expect("ch", ","); sel = self.single_selection(); self.expect("ch", ")")
+            p = api.count_within(ident, r, sel)
         elif proc == "com":
             p = api.com(ident, self.index())
         elif proc == "plane":
