@@ -38,4 +38,4 @@ def build(name: str, sources=None) -> str:
 
 
 if __name__ == "__main__":
-    print(build("sdf")); print(build("props")); print(build("within", ["cells", "within"]))
+    print(build("sdf")); print(build("props")); print(build("within", ["cells", "within"])); print(build("sdfpipe", ["cells", "sdf"])); print(build("xtc"))

@@ -113,6 +113,25 @@ static inline void emul_launch(dim3 grid, dim3 block, const std::function<void()
     }
 }
 
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {   // prmt.b32, default mode
+    const unsigned long long v = ((unsigned long long)y << 32) | x; unsigned r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned n = (sel >> (4 * i)) & 0xfu; unsigned b = (unsigned)(v >> (8 * (n & 7u))) & 0xffu;
+        if (n & 8u) b = (b & 0x80u) ? 0xffu : 0x00u;   // msb replication
+        r |= b << (8 * i);
+    }
+    return r;
+}
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { sh &= 31u; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi; }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { sh &= 31u; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
+static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned sh) { return sh >= 32u ? lo : __funnelshift_l(lo, hi, sh); }
+static inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned sh) { return sh >= 32u ? hi : __funnelshift_r(lo, hi, sh); }
+static inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }

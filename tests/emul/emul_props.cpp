@@ -2,6 +2,7 @@
 // the CPU exactly as written, thread by thread.
 #include "cuda_emul.h"
 #include "props_nolaunch.cu"   // viamd_b200/csrc/props.cu with its <<<>>> launch statements blanked (build_emul.py)
+#include <vector>
 
 namespace mdg { void note_launch(const char*, cudaStream_t) {} }   // the launchers are compiled (their launch statements blanked) but never called
 
@@ -51,5 +52,32 @@ extern "C" int emul_min_distance(const float* frames, size_t frame_stride, size_
                                  const int32_t* ia, uint32_t na, const int32_t* ib, uint32_t nb, float* out) {
     mdg::BatchFrames fr{}; fr.xyz = frames; fr.frame_stride = frame_stride; fr.axis_stride = axis_stride; fr.count = num_frames;
     emul_launch(dim3(num_frames, 1, 1), dim3(256, 1, 1), [&]() { mdg::k_min_distance(fr, cells, ia, na, ib, nb, out, 0); });   // launch_min_distance
+    return 0;
+}
+
+// distance / angle / dihedral whose arguments are selections: k_arg_com (8 lanes of a warp replay the AVX2 reference's accumulation, warp
+// shuffles) per selection argument, then k_temporal — the launch sequence of plan.cu. args: idx[k] / count[k]; count 1 with direct[k] != 0
+// means the atom's own position.
+extern "C" int emul_temporal_args(const float* frames, size_t frame_stride, size_t axis_stride, uint32_t num_frames, const mdgpu_unitcell_t* cells,
+                                  const float* mass, int op, const int32_t* const idx[4], const uint32_t count[4], const int direct[4], float* out) {
+    mdg::BatchFrames fr{}; fr.xyz = frames; fr.frame_stride = frame_stride; fr.axis_stride = axis_stride; fr.count = num_frames;
+    std::vector<float> pos((size_t)num_frames * 12, 0.0f);
+    mdg::TemporalArgs a{}; a.frames = fr; a.cells = cells; a.op = op; a.out = out; a.frame0 = 0; a.pos = pos.data(); a.com_mask = 0;
+    const int nargs = op == MDGPU_OP_DISTANCE ? 2 : (op == MDGPU_OP_ANGLE ? 3 : 4);
+    for (int k = 0; k < nargs; ++k) {
+        a.atom[k] = idx[k][0];
+        if (direct[k]) continue;
+        a.com_mask |= 1u << k;
+        emul_launch(dim3(num_frames), dim3(32), [&]() { mdg::k_arg_com(fr, cells, idx[k], count[k], mass, pos.data(), k); });   // launch_arg_com
+    }
+    emul_launch(dim3((num_frames + 63) / 64), dim3(64), [&]() { mdg::k_temporal(a, (int)num_frames); });
+    return 0;
+}
+
+// centres of mass of atom groups (rdf with an array of selections as reference): k_group_com
+extern "C" int emul_group_com(const float* frames, size_t frame_stride, size_t axis_stride, uint32_t num_frames, const int32_t* idx, const uint32_t* off,
+                              uint32_t n_groups, const float* mass, float* out /* [num_frames][n_groups][3] */) {
+    mdg::BatchFrames fr{}; fr.xyz = frames; fr.frame_stride = frame_stride; fr.axis_stride = axis_stride; fr.count = num_frames;
+    emul_launch(dim3((n_groups + 127u) / 128u, num_frames), dim3(128), [&]() { mdg::k_group_com(fr, idx, off, n_groups, mass, out); });   // launch_group_com
     return 0;
 }

@@ -11,7 +11,7 @@ import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
 import oracle_lib as O  # noqa: E402
-from helpers import load_golden, golden_system, sel_element, cell_from_row  # noqa: E402
+from helpers import load_golden, golden_system, sel_element, cell_from_row, dense_from_sparse  # noqa: E402
 
 
 class _Cell(C.Structure):   # mdgpu_unitcell_t
@@ -178,3 +178,90 @@ def test_count_within_pipeline_matches_the_reference(emul_within):
         for f in range(g["frames"].shape[0]):
             x, y, z = g["frames"][f]; cell = cell_from_row(g["cells"][f], g["cell_flags"][f] if flags is None else flags)
             assert got[f] == len(O.within(x, y, z, np.asarray(sel, np.int32), radius, cell)), (name, flags, radius, f)
+
+
+def test_sdf_pipeline_emulated_matches_the_reference_voxels():
+    """sdf() end to end on the CPU from the product's sources: target cell list (cells.cu), reference-frame fit per structure (k_sdf_ref0,
+    k_sdf_fit: unwrap, covariance, svd3, Kabsch) and the AABB gather + voxel scatter (k_sdf_scatter: ballots, shuffles, REDUX.OR, ring
+    compaction) — all GPU-validated kernels, here as a CPU regression net. Per-frame voxels bit-equal to the reference, orthorhombic and
+    triclinic; a batch of all frames gives their sum."""
+    import build_emul
+    lib = C.CDLL(build_emul.build("sdfpipe", ["cells", "sdf"]))
+    UP = C.POINTER(C.c_uint32)
+    lib.emul_sdf.argtypes = [FP, C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(_Cell), FP, C.c_size_t, FP, IP, C.c_uint32, C.c_uint32, IP, C.c_uint32, IP, C.c_uint32,
+                             C.c_float, C.c_uint32, UP, C.POINTER(C.c_ulonglong)]
+    for name, key in (("water6.npz", "v"), ("tric6.npz", "vt")):
+        g = load_golden(name); s = golden_system(g); frames = np.ascontiguousarray(g["frames"], np.float32); F, _, na = frames.shape; cells = _cells(g)
+        structs = np.ascontiguousarray(np.arange(60, dtype=np.int32)); trg = np.ascontiguousarray(sel_element(s, 8), np.int32); mass = np.ascontiguousarray(s["mass"], np.float32)
+        pairs = np.ascontiguousarray(unwrap_pairs(3, s["conn_off"], s["conn_idx"]))
+        init = np.ascontiguousarray(frames[0])
+
+        def run(fr, cl, nf):
+            vol = np.zeros(128 ** 3, np.uint32); tot = (C.c_ulonglong * nf)()
+            rc = lib.emul_sdf(fr.ctypes.data_as(FP), 3 * na, na, nf, cl, init.ctypes.data_as(FP), na, mass.ctypes.data_as(FP), structs.ctypes.data_as(IP), 20, 3,
+                              trg.ctypes.data_as(IP), len(trg), pairs.ctypes.data_as(IP), len(pairs), 5.0, 1 << 16, vol.ctypes.data_as(UP), tot)
+            assert rc == 0
+            return vol, np.array(list(tot), np.uint64)
+
+        total = np.zeros(128 ** 3, np.uint64)
+        for f in range(F):
+            one = (_Cell * 1)(cells[f])
+            vol, tot = run(np.ascontiguousarray(frames[f:f + 1]), one, 1)
+            ref = dense_from_sparse(g[f"{key}__pf{f}_idx"], g[f"{key}__pf{f}_val"])
+            assert np.array_equal(vol.astype(np.float32), ref), (name, f)
+            assert tot[0] == int(ref.sum()); total += vol
+        vol, tot = run(frames, cells, F)
+        assert np.array_equal(vol.astype(np.uint64), total) and tot.sum() == total.sum()
+
+
+def test_selection_arguments_and_group_centres_emulated(emul_props):
+    """k_arg_com (the 8-lane replay of the AVX2 reference's periodic centre of mass, warp shuffles, Cephes sincos) + k_temporal, and
+    k_group_com — GPU-validated kernels as a CPU regression net: distances between centres of mass bit-equal to the reference (water and
+    1ALA goldens), angles / dihedrals too (host libm = the reference's), group centres equal to the oracle."""
+    PP = C.POINTER(C.c_int32) * 4
+    emul_props.emul_temporal_args.argtypes = [FP, C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(_Cell), FP, C.c_int, PP, C.c_uint32 * 4, C.c_int * 4, FP]
+    emul_props.emul_group_com.argtypes = [FP, C.c_size_t, C.c_size_t, C.c_uint32, IP, C.POINTER(C.c_uint32), C.c_uint32, FP, FP]
+
+    def run(g, s, op, args):
+        frames = np.ascontiguousarray(g["frames"], np.float32); F, _, na = frames.shape; cells = _cells(g); mass = np.ascontiguousarray(s["mass"], np.float32)
+        arrs = [np.ascontiguousarray([a] if np.ndim(a) == 0 else a, np.int32) for a in args] + [np.zeros(1, np.int32)] * (4 - len(args))
+        ptrs = PP(*[a.ctypes.data_as(IP) for a in arrs]); cnt = (C.c_uint32 * 4)(*[len(a) for a in arrs]); direct = (C.c_int * 4)(*([int(np.ndim(a) == 0) for a in args] + [1] * (4 - len(args))))
+        out = np.zeros(F, np.float32)
+        assert emul_props.emul_temporal_args(frames.ctypes.data_as(FP), 3 * na, na, F, cells, mass.ctypes.data_as(FP), op, ptrs, cnt, direct, out.ctypes.data_as(FP)) == 0
+        return out
+
+    g = load_golden("water6.npz"); s = golden_system(g); co = s["comp_off"]; res = lambda r: np.arange(co[r - 1], co[r], dtype=np.int32)
+    assert np.array_equal(run(g, s, 6, (res(1), res(5))), g["dc__full"])
+    assert np.array_equal(run(g, s, 6, (np.arange(0, 30), np.arange(99, 151))), g["dg__full"])
+    assert np.array_equal(run(g, s, 6, (np.arange(0, 30), 199)), g["dm__full"])
+    assert np.array_equal(run(g, s, 7, (res(1), res(2), res(3))), g["ac__full"])
+    assert np.array_equal(run(g, s, 8, (res(1), res(2), res(3), res(4))), g["tc__full"])
+    g = load_golden("ala50.npz"); s = golden_system(g); co = s["comp_off"]
+    assert np.array_equal(run(g, s, 6, (res(1), res(15))), g["dr__full"])
+    assert np.array_equal(run(g, s, 8, (res(1), res(5), 99, res(15))), g["tr__full"])
+
+    g = load_golden("water6.npz"); s = golden_system(g); frames = np.ascontiguousarray(g["frames"], np.float32); F, _, na = frames.shape
+    groups = [np.arange(co0, co1, dtype=np.int32) for co0, co1 in zip(s["comp_off"][:20], s["comp_off"][1:21])]
+    idx = np.ascontiguousarray(np.concatenate(groups)); off = np.zeros(21, np.uint32); off[1:] = np.cumsum([len(x) for x in groups])
+    mass = np.ascontiguousarray(s["mass"], np.float32); out = np.zeros((F, 20, 3), np.float32)
+    assert emul_props.emul_group_com(frames.ctypes.data_as(FP), 3 * na, na, F, idx.ctypes.data_as(IP), off.ctypes.data_as(C.POINTER(C.c_uint32)), 20, mass.ctypes.data_as(FP), out.ctypes.data_as(FP)) == 0
+    for f in range(F):
+        pos, _, _ = O.group_com(*g["frames"][f], s["mass"], groups)
+        assert np.array_equal(out[f], np.asarray(pos, np.float32).reshape(20, 3)), f
+
+
+@pytest.mark.parametrize("case", ("water6", "lowprec", "tric6", "small5", "wide12", "huge12"))
+def test_xtc_decode_emulated(case):
+    """The device XTC decoder (k_xtc_scan: warp per frame, shared-memory staged stream, speculative 32-group rounds with a serial fallback;
+    k_xtc_decode: thread per group, 64/128-bit unpacking) run on the CPU from xtc.cu: equal to the reference reader's decode on the five
+    stream classes it decodes correctly, to the written data on the two it does not — GPU-validated kernels as a CPU regression net."""
+    import build_emul
+    lib = C.CDLL(build_emul.build("xtc"))
+    lib.emul_xtc_decode.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, FP]
+    g = load_golden("xtc_cases.npz"); blob = np.ascontiguousarray(g[case + "__xtc"]); na = int(g[case + "__na"]); F = len(g[case + "__cells"])
+    offs = O.xtc_frame_offsets(blob); assert len(offs) == F + 1
+    offs = np.ascontiguousarray(offs, np.uint64); out = np.zeros((F, 3, na), np.float32)
+    assert lib.emul_xtc_decode(blob.ctypes.data, offs.ctypes.data_as(C.POINTER(C.c_uint64)), F, na, out.ctypes.data_as(FP)) == 0
+    for f in range(F):
+        if case in ("wide12", "huge12"): assert np.abs(out[f] - g[case + "__orig"][f]).max() <= 0.02
+        else: assert np.array_equal(out[f], g[case + "__frames"][f]), (case, f)
