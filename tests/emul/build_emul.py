@@ -14,6 +14,31 @@ CUDA_LIB = os.path.join(CUDA_HOME, "lib64")
 LAUNCH = re.compile(r"[A-Za-z_]\w*\s*(?:<[^<>;(){}]*>)?\s*<<<.*?>>>\s*\([^;]*?\)\s*;", re.S)
 
 
+# rdf.cu reaches for inline PTX (packed f32x2 arithmetic, shared-window addressing, red.shared, the MUFU-based sqrt). For the host build
+# those few helper definitions are swapped for plain C++ with the same semantics; everything else — the enumeration, the cull bound, the
+# class logic, the queue discipline, the symmetric counting — is compiled as written. (pattern, replacement, expected number of matches)
+RDF_PATCHES = [
+    (r'^MDG_D u64 pk\(float a, float b\) \{.*$', 'MDG_D u64 pk(float a, float b) { uint32_t x, y; memcpy(&x, &a, 4); memcpy(&y, &b, 4); return (u64)x | ((u64)y << 32); }', 1),
+    (r'^MDG_D u64 pkv\(float a, float b\) \{.*$', 'MDG_D u64 pkv(float a, float b) { return pk(a, b); }', 1),
+    (r'^MDG_D void upk\(u64 v, float& a, float& b\) \{.*$', 'MDG_D void upk(u64 v, float& a, float& b) { const uint32_t x = (uint32_t)v, y = (uint32_t)(v >> 32); memcpy(&a, &x, 4); memcpy(&b, &y, 4); }', 1),
+    (r'^MDG_D u64 sub2\(u64 a, u64 b\) \{.*$', 'MDG_D u64 sub2(u64 a, u64 b) { float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1); return pk(a0 - b0, a1 - b1); }', 1),
+    (r'^MDG_D u64 add2\(u64 a, u64 b\) \{.*$', 'MDG_D u64 add2(u64 a, u64 b) { float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1); return pk(a0 + b0, a1 + b1); }', 1),
+    (r'^MDG_D u64 mul2\(u64 a, u64 b\) \{.*$', 'MDG_D u64 mul2(u64 a, u64 b) { float a0, a1, b0, b1; upk(a, a0, a1); upk(b, b0, b1); return pk(a0 * b0, a1 * b1); }', 1),
+    (r'^MDG_D u64 fma2\(u64 a, u64 b, u64 c\) \{.*$', 'MDG_D u64 fma2(u64 a, u64 b, u64 c) { float a0, a1, b0, b1, c0, c1; upk(a, a0, a1); upk(b, b0, b1); upk(c, c0, c1); return pk(fmaf(a0, b0, c0), fmaf(a1, b1, c1)); }', 1),
+    (r'^MDG_D void q_push\(uint32_t& qaddr, float v\) \{.*$', 'MDG_D void q_push(uint32_t& qaddr, float v) { *(float*)(emul_dyn_smem + qaddr) = v; qaddr += 128u; }', 1),
+    (r'^MDG_D float q_load\(uint32_t addr\) \{.*$', 'MDG_D float q_load(uint32_t addr) { return *(const float*)(emul_dyn_smem + addr); }', 1),
+    (r'MDG_D float sqrt_rn_normal\(float x\) \{.*?\n\}', 'MDG_D float sqrt_rn_normal(float x) { return sqrtf(x); }   /* the device sequence is swept against IEEE sqrt on the GPU */', 1),
+    (r'^    asm volatile\("red\.shared\.add\.u32 \[%0\], %1;".*$', '    __atomic_fetch_add((uint32_t*)(emul_dyn_smem + hist_saddr + 4u * (uint32_t)bin), w, __ATOMIC_RELAXED);', 1),
+    (r'^    asm volatile\("\{ \.reg \.pred q;.*$', '    if (p) __atomic_fetch_add((uint32_t*)(emul_dyn_smem + hist_saddr + 4u * (uint32_t)bin), w, __ATOMIC_RELAXED);', 1),
+    (r'float4 rf; asm volatile\("ld\.shared\.v4\.f32.*$', 'const float4 rf = *(const float4*)(emul_dyn_smem + sref_saddr + 16u * (uint32_t)(gi * V2_UNROLL + u));', 1),
+    (r'^    extern __shared__ __align__\(16\) unsigned char smem_raw\[\];$', '    unsigned char* smem_raw = emul_dyn_smem;', 1),
+    (r'^    asm volatile\("mov\.u32 %0, %0;".*$', '', 3),
+    (r'cudaFuncSetAttribute\(k_rdf_pairs_v2<\w+>, [^;]*;', ';', 2),                       # launcher-only runtime calls on kernel symbols
+    (r'cudaOccupancyMaxActiveBlocksPerMultiprocessor\(&bpsm\[\d\], k_rdf_pairs_v2<\w+>, [^;]*;', ';', 2),
+]
+PATCHES = {"rdf": RDF_PATCHES}
+
+
 def build(name: str, sources=None) -> str:
     """name: wrapper emul_<name>.cpp -> libemul_<name>.so; sources: the product .cu files it includes (default [name])"""
     sources = sources or [name]
@@ -27,6 +52,10 @@ def build(name: str, sources=None) -> str:
         text = open(src).read()
         stripped, n = LAUNCH.subn("/* launch removed for host emulation */;", text)
         assert n > 0 and "<<<" not in stripped, f"{sname}.cu: {n} launches removed, some left"
+        for pat, rep, want in PATCHES.get(sname, []):
+            stripped, k = re.subn(pat, lambda m, rep=rep: rep, stripped, flags=re.M | re.S if "\\n" in pat else re.M)
+            assert k == want, f"{sname}.cu: patch {pat!r} matched {k} times, expected {want}"
+        assert "asm" not in re.sub(r"//.*", "", stripped), f"{sname}.cu: inline asm left after patching"
         stripped = stripped.replace('#include "common.cuh"', f'#include "{os.path.join(CSRC, "common.cuh")}"').replace('#include "kernels.h"', f'#include "{os.path.join(CSRC, "kernels.h")}"')
         with open(os.path.join(HERE, "build", f"{sname}_nolaunch.cu"), "w") as f:
             f.write(stripped)
@@ -38,4 +67,4 @@ def build(name: str, sources=None) -> str:
 
 
 if __name__ == "__main__":
-    print(build("sdf")); print(build("props")); print(build("within", ["cells", "within"])); print(build("sdfpipe", ["cells", "sdf"])); print(build("xtc"))
+    print(build("sdf")); print(build("props")); print(build("within", ["cells", "within"])); print(build("sdfpipe", ["cells", "sdf"])); print(build("xtc")); print(build("rdfpipe", ["cells", "props", "rdf"]))

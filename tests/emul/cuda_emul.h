@@ -54,6 +54,10 @@ static inline int __float2int_rn(float a) { return (int)rintf(a); }
 static inline int __float2int_rz(float a) { return (int)a; }
 static inline int __float2int_rd(float a) { return (int)floorf(a); }
 
+// dynamic shared memory (extern __shared__) and 32-bit shared-window addresses: one arena, offsets into it are the "addresses"
+alignas(16) static unsigned char emul_dyn_smem[228 * 1024];
+template <typename T> static inline size_t __cvta_generic_to_shared(const T* p) { return (size_t)((const unsigned char*)p - emul_dyn_smem); }
+
 // ---------------------------------------------------------------------------------------------- block / warp cooperation (emul_launch)
 struct EmulWarp { std::unique_ptr<std::barrier<>> bar; unsigned long long slot[32]; };
 struct EmulBlock { std::unique_ptr<std::barrier<>> bar; std::vector<EmulWarp> warps; };
