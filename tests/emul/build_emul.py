@@ -66,5 +66,57 @@ def build(name: str, sources=None) -> str:
     return out
 
 
+def _split_top(s: str):
+    """split at top-level commas (parentheses / brackets / angle brackets of casts are balanced in the launch configurations used here)"""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{": depth += 1
+        elif ch in ")]}": depth -= 1
+        if ch == "," and depth == 0: out.append(cur.strip()); cur = ""
+        else: cur += ch
+    out.append(cur.strip())
+    return out
+
+
+LAUNCH_FULL = re.compile(r"([A-Za-z_]\w*)\s*(<[^<>;(){}]*>)?\s*<<<(.*?)>>>\s*\(([^;]*?)\)\s*;", re.S)
+
+
+def _launch_to_emul(m):
+    name, tmpl, cfg, args = m.group(1), m.group(2) or "", _split_top(m.group(3)), m.group(4)
+    return f"emul_launch(dim3({cfg[0]}), dim3({cfg[1]}), [&]() {{ {name}{tmpl}({args}); }});"
+
+
+def build_library() -> str:
+    """tests/emul/build/libmdgpu_emul.so: every source of libmdgpu.so compiled by g++ — each `k<<<grid, block, smem, stream>>>(args);` turned into
+    `emul_launch(grid, block, [&]{ k(args); })`, rdf.cu's PTX helpers patched as above — and linked with fake_cudart.cpp instead of libcudart:
+    the product's C ABI, host logic and kernels, executing on the CPU. Test infrastructure only."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mdgpu_build", os.path.join(CSRC, "..", "build.py")); b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    out = os.path.join(HERE, "build", "libmdgpu_emul.so"); bdir = os.path.join(HERE, "build")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ("cuda_emul.h", "fake_cudart.cpp")] + [__file__, os.path.join(CSRC, "..", "..", "include", "mdgpu.h")]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    os.makedirs(bdir, exist_ok=True)
+    flags = ["-std=c++20", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w", f"-I{CUDA_INC}", f"-I{HERE}", f"-I{CSRC}", "-include", os.path.join(HERE, "cuda_emul.h")]
+    objs, procs = [], []
+    for src in b.SOURCES:
+        sname = src[:-3]; text = open(os.path.join(CSRC, src)).read()
+        text, n = LAUNCH_FULL.subn(_launch_to_emul, text)
+        assert "<<<" not in text, f"{src}: launch statement not converted"
+        for pat, rep, want in PATCHES.get(sname, []):
+            text, k = re.subn(pat, lambda m, rep=rep: rep, text, flags=re.M | re.S if "\\n" in pat else re.M)
+            assert k == want, f"{src}: patch {pat!r} matched {k} times, expected {want}"
+        text = text.replace('#include "common.cuh"', f'#include "{os.path.join(CSRC, "common.cuh")}"').replace('#include "kernels.h"', f'#include "{os.path.join(CSRC, "kernels.h")}"').replace('#include "synth.h"', f'#include "{os.path.join(CSRC, "synth.h")}"')
+        gen = os.path.join(bdir, f"{sname}_emullib.cpp"); open(gen, "w").write(text)
+        obj = os.path.join(bdir, f"{sname}_emullib.o"); objs.append(obj)
+        procs.append((src, subprocess.Popen(["g++", *flags, "-c", gen, "-o", obj])))
+    fobj = os.path.join(bdir, "fake_cudart.o"); objs.append(fobj)
+    procs.append(("fake_cudart.cpp", subprocess.Popen(["g++", *flags[:6], f"-I{CUDA_INC}", "-c", os.path.join(HERE, "fake_cudart.cpp"), "-o", fobj])))
+    for src, p in procs:
+        if p.wait() != 0: raise RuntimeError(f"g++ failed on {src}")
+    subprocess.check_call(["g++", "-shared", "-o", out, *objs, "-lpthread", "-lm"])
+    return out
+
+
 if __name__ == "__main__":
-    print(build("sdf")); print(build("props")); print(build("within", ["cells", "within"])); print(build("sdfpipe", ["cells", "sdf"])); print(build("xtc")); print(build("rdfpipe", ["cells", "props", "rdf"]))
+    print(build("sdf")); print(build("props")); print(build("within", ["cells", "within"])); print(build("sdfpipe", ["cells", "sdf"])); print(build("xtc")); print(build("rdfpipe", ["cells", "props", "rdf"])); print(build_library())

@@ -54,9 +54,9 @@ def test_rmsd_goldens_bitexact():
 def test_rmsd_oracle_larger_and_batched():
     """A 3 000-atom selection over 40 frames in batches of 7 (ragged last batch), two stream slots: oracle vs device, value by value."""
     import viamd_b200 as vb
-    n = 10; sysm = vb.water_system(n); base = vb.synth_water_base(n, 5)
+    n = 10; sysm = vb.water_system(n); base, L = vb.synth_water_base(n, 5)
     F = 40; frames = vb.synth_water_frames_host(n, 5, base, 0, F)
-    _, L = vb.synth_water_desc(n, 5); cell = vb.UnitCell.from_basis(L, L, L); ocell = cell_from_row([L, 0, 0, L, 0, L], 29)
+    cell = vb.UnitCell.from_basis(L, L, L); ocell = cell_from_row([L, 0, 0, L, 0, L], 29)
     idx = np.arange(0, 3000, dtype=np.int32)
     plan = vb.Plan(sysm, [vb.rmsd("rm", idx)], F, batch_frames=7, num_streams=2)
     plan.set_initial_frame(*frames[0], cell)
@@ -71,8 +71,8 @@ def test_rmsd_oracle_larger_and_batched():
 
 def test_rmsd_empty_selection_and_missing_initial_frame():
     import viamd_b200 as vb
-    sysm = vb.water_system(4); base = vb.synth_water_base(4, 1); frames = vb.synth_water_frames_host(4, 1, base, 0, 3)
-    _, L = vb.synth_water_desc(4, 1); cell = vb.UnitCell.from_basis(L, L, L)
+    sysm = vb.water_system(4); base, L = vb.synth_water_base(4, 1); frames = vb.synth_water_frames_host(4, 1, base, 0, 3)
+    cell = vb.UnitCell.from_basis(L, L, L)
     plan = vb.Plan(sysm, [vb.rmsd("e", np.zeros(0, np.int32))], 3)
     plan.set_initial_frame(*frames[0], cell); plan.eval_host_frames(frames, [cell] * 3, 0)
     assert np.array_equal(plan.property_data("e").values, np.zeros(3, np.float32))   # _rmsd :4311: nothing written for an empty selection

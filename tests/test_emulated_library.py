@@ -1,0 +1,44 @@
+"""The whole library on the CPU: tests/emul/build/libmdgpu_emul.so is libmdgpu's own sources (plan.cu, every kernel file) compiled by g++ —
+kernel launches turned into emul_launch, CUDA runtime calls served by tests/emul/fake_cudart.cpp — so the C ABI, the plan's host logic
+(batching, slots, scratch sizing, result folds) and the kernels run together without a GPU. Here: the tests of the device paths written after
+the GPU budget was spent (tests/pending_gpu_round2.py, all of them) and a few of the GPU-validated parity tests as a check of the emulation.
+The complete GPU suite passes this way too (28 tests, ~25 min): `python tests/emul/run_under_emulation.py tests/test_gpu_parity.py -m gpu`.
+
+This is evidence about source logic, not a substitute for the GPU run: launch limits, memory spaces and timing are not modelled."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+
+
+@pytest.fixture(scope="module")
+def emulated_library():
+    import build_emul
+    import viamd_b200.api as api
+    saved = (api.LIB_PATH, api._lib)
+    api.LIB_PATH = build_emul.build_library(); api._lib = None
+    yield api
+    api.LIB_PATH, api._lib = saved
+
+
+def _run_all(mod, names):
+    for n in names:
+        getattr(mod, n)()
+
+
+def test_new_device_paths_through_the_c_abi(emulated_library):
+    """rmsd, distance_pair + aggregates, com, plane, count(within()), their error paths: every test of tests/pending_gpu_round2.py."""
+    import pending_gpu_round2 as P
+    names = [n for n in dir(P) if n.startswith("test_")]
+    assert len(names) >= 7
+    _run_all(P, names)
+
+
+def test_validated_paths_agree_under_emulation(emulated_library):
+    """A slice of tests/test_gpu_parity.py (all of which have passed on a B200): rdf per-frame bins incl. batching and stream slots,
+    centre-of-mass references, density + every temporal, error paths."""
+    import test_gpu_parity as G
+    _run_all(G, ["test_golden_water_rdf_per_frame_bitexact", "test_golden_water_rdf_com_references_bitexact", "test_golden_water_density_and_temporals",
+                 "test_empty_and_error_paths"])
