@@ -2,7 +2,7 @@
 executed by host threads, fake CUDA runtime) instead of libmdgpu.so — on a machine without a GPU:
 
     python tests/emul/run_under_emulation.py tests/test_gpu_parity.py -m gpu -q          # ~25 min, the two full-size tests take 9 min each
-    python tests/emul/run_under_emulation.py tests/pending_gpu_round2.py -m gpu -q       # ~15 s
+    python tests/emul/run_under_emulation.py tests/test_zz_gpu_new_ops.py -m gpu -q       # ~15 s
 
 Test infrastructure: it swaps the library path inside THIS process's viamd_b200.api before pytest starts; the product has no such switch."""
 import os

@@ -1,7 +1,7 @@
 """Kernels whose threads do not cooperate, EXECUTED on the CPU from the product's own .cu source (tests/emul: g++ + a small CUDA shim) and
 compared with the reference's golden values. This is how device code written without GPU time left is checked before its first launch:
 it proves the source's logic and operation order (every operation on these paths is IEEE add/mul/div/sqrt, identical on host and device);
-it cannot prove launch configuration or memory behaviour, which is what tests/pending_gpu_round2.py is for."""
+it cannot prove launch configuration or memory behaviour, which is what tests/test_zz_gpu_new_ops.py is for."""
 import ctypes as C
 import os
 import sys

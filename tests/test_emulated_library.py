@@ -1,7 +1,7 @@
 """The whole library on the CPU: tests/emul/build/libmdgpu_emul.so is libmdgpu's own sources (plan.cu, every kernel file) compiled by g++ —
 kernel launches turned into emul_launch, CUDA runtime calls served by tests/emul/fake_cudart.cpp — so the C ABI, the plan's host logic
 (batching, slots, scratch sizing, result folds) and the kernels run together without a GPU. Here: the tests of the device paths written after
-the GPU budget was spent (tests/pending_gpu_round2.py, all of them) and a few of the GPU-validated parity tests as a check of the emulation.
+the GPU budget was spent (tests/test_zz_gpu_new_ops.py, all of them) and a few of the GPU-validated parity tests as a check of the emulation.
 The complete GPU suite passes this way too (28 tests, ~25 min): `python tests/emul/run_under_emulation.py tests/test_gpu_parity.py -m gpu`.
 
 This is evidence about source logic, not a substitute for the GPU run: launch limits, memory spaces and timing are not modelled."""
@@ -29,8 +29,8 @@ def _run_all(mod, names):
 
 
 def test_new_device_paths_through_the_c_abi(emulated_library):
-    """rmsd, distance_pair + aggregates, com, plane, count(within()), their error paths: every test of tests/pending_gpu_round2.py."""
-    import pending_gpu_round2 as P
+    """rmsd, distance_pair + aggregates, com, plane, count(within()), their error paths: every test of tests/test_zz_gpu_new_ops.py."""
+    import test_zz_gpu_new_ops as P
     names = [n for n in dir(P) if n.startswith("test_")]
     assert len(names) >= 7
     _run_all(P, names)

@@ -17,7 +17,7 @@ TOOL = os.path.join(ROOT, "oracle", "build", "synth_tool")
 SCRIPT = ("r = rdf(element('O'), element('O'), 6.0); v = sdf(residue(1:20), element('O'), 5.0); dz = density_z(element('O')); "
           "d = distance(1,10); rr = rdf(element('O'), element('H'), 1.5:6.0); a = angle(1,2,3); t = dihedral(1,4,7,10); "
           "rc = rdf(residue(1:20), element('O'), 5.0);")
-# forms added after the last GPU run: lowered identically by the shim and the Python mirror (CPU check); their GPU tests are in pending_gpu_round2.py
+# forms added after the last GPU run: lowered identically by the shim and the Python mirror (CPU check); their GPU tests are in test_zz_gpu_new_ops.py
 SCRIPT_NEW = ("rm = rmsd(residue(1:10)); dp = distance_pair(atom(1:5), atom(20:30)); c = com(residue(1)); ci = com(5); pl = plane(atom(1:30)); "
               "cw = count(within(4.0, residue(1))); dmn = distance_min(residue(1), atom(100:648)); dc = distance(residue(1), residue(5));")
 

@@ -1,9 +1,8 @@
-"""Device paths written after this round's GPU budget ran out: compiled and wired (C ABI, Python mirror, integration shim), checked on the
-CPU as far as that goes (oracle pinned against the reference, SASS of the older kernels unchanged), but NOT yet run on a GPU.
-
-The file name keeps it out of the default collection (`pytest tests -m gpu` must only hold tests that have passed on a B200). First GPU
-call of the next round:   python -m pytest tests/pending_gpu_round2.py -m gpu -x -q
-and, once green, the tests move into test_gpu_parity.py.
+"""GPU tests of the device paths written after this round's GPU budget was spent: rmsd, distance_pair + the multi-valued temporal container,
+com, plane, count(within()). At the time of writing they have not run on a B200; what stands behind them is the CPU execution of the same
+sources: every test here passes through the C ABI against tests/emul's emulated build of the whole library (tests/test_emulated_library.py;
+the complete, GPU-validated tests/test_gpu_parity.py passes under that emulation too), also with AddressSanitizer watching the "device"
+buffers. The file sorts last on purpose: with `pytest -x` every test that has already passed on the GPU runs before these.
 """
 import numpy as np
 import pytest
