@@ -75,3 +75,31 @@ def test_md_script_api_cpu_vs_gpu_through_the_shim(tmp_path):
     res = json.loads(line[-1])
     assert p.returncode == 0 and res["parity"] is True, res
     assert all(q["out_of_tol"] == 0 and q["frame_mask_equal"] for q in res["properties"])
+
+
+def test_md_script_api_through_the_shim_against_the_emulated_library(tmp_path):
+    """The drop-in boundary on the CPU: the reference's own md_script.c + the shim, with the library behind the C ABI replaced by its emulated
+    build (tests/emul: same sources, kernels run by host threads). md_script_eval_frame_range (reference CPU path) vs
+    md_script_gpu_eval_frame_range on one script that holds the GPU-validated ops and every op added since (rmsd, distance_pair, com, plane,
+    count(within())): values within tolerance (the new temporals: equal), frame masks equal. The binary finds `libmdgpu.so` through
+    LD_LIBRARY_PATH, which the loader searches before the binary's RUNPATH."""
+    _need()
+    import shutil
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+    import build_emul
+    libdir = tmp_path / "lib"; libdir.mkdir(); shutil.copy(build_emul.build_library(), str(libdir / "libmdgpu.so"))
+    gro = str(tmp_path / "w6.gro")
+    subprocess.check_call([TOOL, "water-gro", "6", "1008", gro])
+    script = ("r = rdf(element('O'), element('O'), 6.0); d = distance(1,10); rc = rdf(residue(1:20), element('O'), 5.0); v = sdf(residue(1:20), element('O'), 5.0); "
+              "dz = density_z(element('O')); " + SCRIPT_NEW)
+    env = dict(os.environ, LD_LIBRARY_PATH=str(libdir))
+    p = subprocess.run([SHIM, "eval", "--sys", gro, "--traj", "synthwater:6:1008:5", "--script", script], capture_output=True, text=True, env=env)
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert line, p.stdout + p.stderr
+    res = json.loads(line[-1])
+    assert p.returncode == 0 and res["parity"] is True, res
+    assert all(q["out_of_tol"] == 0 and q["frame_mask_equal"] for q in res["properties"])
+    exact = {q["name"]: q["max_abs"] for q in res["properties"]}
+    assert all(exact[k] == 0 for k in ("d", "rm", "dp", "c", "ci", "pl", "cw", "dmn", "dc", "v")), exact
+

@@ -157,3 +157,20 @@ def test_count_within_goldens_and_oracle():
         plan.close()
     with pytest.raises(vb.MdgpuError):
         vb.Plan(vb.water_system(4), [vb.count_within("c", 0.0, np.arange(3))], 2)
+
+
+def test_new_ops_through_the_md_script_shim(tmp_path):
+    """md_script_eval_frame_range (reference CPU path) vs md_script_gpu_eval_frame_range on a script made of the new ops, through the
+    reference's own md_script.c + integration/md_script_mdgpu.inl (oracle/_ref/shim_harness)."""
+    import json, os, subprocess
+    import test_integration_shim as T
+    T._need()
+    gro = str(tmp_path / "w6.gro")
+    subprocess.check_call([T.TOOL, "water-gro", "6", "1008", gro])
+    p = subprocess.run([T.SHIM, "eval", "--sys", gro, "--traj", "synthwater:6:1008:9", "--script", "r = rdf(element('O'), element('O'), 6.0); " + T.SCRIPT_NEW], capture_output=True, text=True)
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert line, p.stdout + p.stderr
+    res = json.loads(line[-1])
+    assert p.returncode == 0 and res["parity"] is True, res
+    assert all(q["out_of_tol"] == 0 and q["frame_mask_equal"] for q in res["properties"])
+
