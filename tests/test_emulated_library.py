@@ -31,7 +31,8 @@ def _run_all(mod, names):
 def test_new_device_paths_through_the_c_abi(emulated_library):
     """rmsd, distance_pair + aggregates, com, plane, count(within()), their error paths: every test of tests/test_zz_gpu_new_ops.py."""
     import test_zz_gpu_new_ops as P
-    names = [n for n in dir(P) if n.startswith("test_")]
+    import inspect
+    names = [n for n in dir(P) if n.startswith("test_") and not inspect.signature(getattr(P, n)).parameters]   # the shim test (tmp_path) drives a binary linked to the real library
     assert len(names) >= 7
     _run_all(P, names)
 
