@@ -114,6 +114,8 @@ typedef enum mdgpu_op {
  *              the centres of mass of `num_structures` atom groups stored back to back in idx[0] (extract_com :857, no periodic
  *              treatment) and a group's own atoms are excluded from its pairs (rdf_cb_excl_mask :5243). Groups are delimited
  *              by structure_offsets[num_structures+1], or are `structure_size` atoms each when that pointer is NULL.
+ *              If ref_within_radius > 0 the reference argument was the dynamic selection within(radius, selection): idx[0] holds that
+ *              selection and the references of a frame are the atoms of the system within `radius` of it, itself excluded (:2485-2533).
  *   SDF      : idx[0] = num_structures * structure_size atoms (equivalent structures), idx[1] = target atoms, cutoff_max.
  *   DENSITY_*: idx[0] = atoms.
  *   DISTANCE_MIN/_MAX: idx[0], idx[1] = the atoms of the two selections (brute force over all pairs, md_util_min_distance md_util.c:8242).
@@ -139,6 +141,7 @@ typedef struct mdgpu_property_desc_t {
     float cutoff_max;
     const uint32_t* structure_offsets;   /* optional CSR offsets into idx[0] for groups of different sizes (rdf) */
     uint32_t com_args;                   /* distance/angle/dihedral: bit k = argument k is a selection (centre of mass even for one atom) */
+    float ref_within_radius;             /* rdf: > 0 -> the reference argument was within(radius, idx[0]): the dynamic selection is evaluated per frame */
 } mdgpu_property_desc_t;
 
 /* Result view: the fields of md_script_property_data_t (md_script.h:73-92) that the evaluation fills. */

@@ -94,7 +94,14 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
     size_t nsets = 0, set_size = 0; int64_t n;
     if (str_eq(pname, STR_LIT("rdf")) && nargs == 3) {
         out->op = MDGPU_OP_RDF;
-        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &nsets, &set_size, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
+        if (args[0]->type == AST_PROC_CALL && args[0]->proc && str_eq(args[0]->proc->name, STR_LIT("within")) && md_array_size(args[0]->children) == 2) {
+            /* dynamic reference set within(radius, selection) (_within_expl_flt :2485): evaluated per frame on the device */
+            ast_node_t** w = args[0]->children; size_t ns = 0;
+            if (!(w[0]->flags & FLAG_CONSTANT) || w[0]->data.type.base_type != TYPE_FLOAT || w[1]->data.type.base_type != TYPE_BITFIELD) goto dynamic;
+            out->ref_within_radius = *(const float*)w[0]->data.ptr;
+            if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, w[1], alloc)) < 0 || ns > 1) goto dynamic; out->idx_count[0] = (size_t)n;
+        } else
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &nsets, &set_size, args[0], alloc)) < 0) goto dynamic; else out->idx_count[0] = (size_t)n;
         if (args[0]->data.type.base_type == TYPE_BITFIELD && nsets > 1) {   /* array of bitfields: COM references + exclusion masks (:5275) */
             const md_bitfield_t* bf = (const md_bitfield_t*)args[0]->data.ptr;
             uint32_t* off = (uint32_t*)md_alloc(alloc, sizeof(uint32_t) * (nsets + 1));

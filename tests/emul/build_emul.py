@@ -44,7 +44,7 @@ def build(name: str, sources=None) -> str:
     sources = sources or [name]
     out = os.path.join(HERE, "build", f"libemul_{name}.so"); wrap = os.path.join(HERE, f"emul_{name}.cpp")
     srcs = [os.path.join(CSRC, f"{s}.cu") for s in sources]
-    deps = srcs + [wrap, os.path.join(HERE, "cuda_emul.h"), os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "common.cuh"), __file__]
+    deps = srcs + [wrap, os.path.join(HERE, "cuda_emul.h"), os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "cellmath.cuh"), __file__]
     if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -61,7 +61,7 @@ def build(name: str, sources=None) -> str:
             f.write(stripped)
     # no -mfma / -march: a*b+c must stay two roundings, as under nvcc --fmad=false
     subprocess.check_call(["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", "-x", "c++", f"-I{CUDA_INC}", f"-I{HERE}",
-                           f"-I{os.path.join(HERE, 'build')}", wrap, "-o", out,
+                           f"-I{os.path.join(HERE, 'build')}", f"-I{CSRC}", wrap, "-o", out,
                            f"-L{CUDA_LIB}", f"-Wl,-rpath,{CUDA_LIB}", "-lcudart", "-lpthread"])   # the (never called) launchers reference cudaMemsetAsync etc.
     return out
 

@@ -71,6 +71,8 @@ def test_script_lowering(vb):
     for src in ("x = com(residue(1:3));", "x = plane(residue(1:3));", "x = distance(residue(1:2), 5);", "x = distance_pair(residue(1:2), element('O'));"):
         with pytest.raises(vb.ScriptError):   # one position per selection in the reference: not lowered, never flattened silently
             vb.compile_script(src, s)
+    rwp = vb.compile_script("rw = rdf(within(4.0, residue(2)), element('O'), 2.0:6.0);", s)[0]
+    assert rwp.op == vb.OP_RDF and rwp.ref_within == 4.0 and list(rwp.idx[0]) == [3, 4, 5] and rwp.cutoff_min == 2.0 and rwp.num_structures == 0
     cw = vb.compile_script("cw = count(within(4.5, residue(2)));", s)[0]
     assert cw.op == vb.OP_WITHIN_COUNT and cw.cutoff_max == 4.5 and list(cw.idx[0]) == [3, 4, 5]
     with pytest.raises(vb.ScriptError):

@@ -159,6 +159,35 @@ def test_count_within_goldens_and_oracle():
         vb.Plan(vb.water_system(4), [vb.count_within("c", 0.0, np.arange(3))], 2)
 
 
+def test_rdf_with_a_dynamic_within_reference_set():
+    """rdf(within(radius, selection), targets, cutoff): the reference atoms change every frame (marks -> per-frame index list -> home-grid cell
+    list -> the usual cull + pair kernels). Per-frame bins, weights and the mean against the reference (golden rw); a second property in
+    the same plan shares the target cell list; triclinic + a larger radius against the oracle."""
+    g = load_golden("water6.npz"); s = golden_system(g); F = g["frames"].shape[0]
+    plan, cells = _plan(g, s, "rw = rdf(within(4.0, residue(1)), element('O'), 6.0); r = rdf(element('O'), element('O'), 6.0);", keep_frame_results=True, batch_frames=3)
+    plan.eval_host_frames(g["frames"], cells, 0)
+    for f in range(F):
+        for key in ("rw", "r"):
+            bins, tot = plan.frame_counts(key, f)
+            assert np.array_equal(bins.astype(np.float32), g[f"{key}__pf"][f, :1024]) and tot == int(g[f"{key}__pf"][f, :1024].sum()), (key, f)
+    d = plan.property_data("rw")
+    assert np.array_equal(d.weights, g["rw__pf"][F - 1, 1024:])
+    np.testing.assert_allclose(d.values[:1024], g["rw__full"][:1024], rtol=1e-5, atol=1e-6)
+    plan.close()
+    import viamd_b200 as vb
+    g = load_golden("tric6.npz"); s = golden_system(g); F = g["frames"].shape[0]; o = sel_element(s, 8); sel = np.arange(30, 39, dtype=np.int32)
+    plan = vb.Plan(vb_system(s), [vb.rdf_within("rw", 6.5, sel, o, 7.0, 1.0)], F, keep_frame_results=True)
+    cells = [vb_cell(g["cells"][f], g["cell_flags"][f]) for f in range(F)]
+    plan.eval_host_frames(g["frames"], cells, 0)
+    for f in range(F):
+        x, y, z = g["frames"][f]; cell = cell_from_row(g["cells"][f], g["cell_flags"][f])
+        ref = O.within(x, y, z, sel, 6.5, cell)
+        want, _, tot_w = O.rdf_frame(x, y, z, ref, o, cell, 1.0, 7.0)
+        bins, tot = plan.frame_counts("rw", f)
+        assert np.array_equal(bins.astype(np.float32), want) and tot == tot_w, f
+    plan.close()
+
+
 def test_new_ops_through_the_md_script_shim(tmp_path):
     """md_script_eval_frame_range (reference CPU path) vs md_script_gpu_eval_frame_range on a script made of the new ops, through the
     reference's own md_script.c + integration/md_script_mdgpu.inl (oracle/_ref/shim_harness)."""

@@ -10,6 +10,7 @@
 // consumer on the path (histogram / voxel increments) is order independent.
 #include "common.cuh"
 #include "kernels.h"
+#include "cellmath.cuh"
 
 namespace mdg {
 
@@ -146,20 +147,6 @@ __global__ void k_aabb(BatchFrames fr, const int32_t* __restrict__ idx, uint32_t
     if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; ++k) { atomic_min_f(aabb + 6 * f + k, mn[k]); atomic_max_f(aabb + 6 * f + 3 + k, mx[k]); }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Point binning. vec4_linear_combine_3(r - origin, I) (core/md_vec_math.h:1323): ((I0*a.x) + (I1*a.y)) + (I2*a.z).
-// ---------------------------------------------------------------------------------------------------------------
-MDG_D void cart_to_fract(float s[3], const float r[3], const FrameGeom& g) {
-    const float ax = __fsub_rn(r[0], g.origin[0]), ay = __fsub_rn(r[1], g.origin[1]), az = __fsub_rn(r[2], g.origin[2]);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float v = __fmul_rn(g.I[0][k], ax);
-        v = __fadd_rn(v, __fmul_rn(g.I[1][k], ay));
-        v = __fadd_rn(v, __fmul_rn(g.I[2][k], az));
-        s[k] = v;
-    }
-}
-
 // MODE 0: internal (target) points -> clamped cell index (:341-371)
 // MODE 1: external (reference) points -> unclamped home cell (:1713-1719 ortho wraps periodic axes, :1561-1566 triclinic does not)
 template <int MODE>
@@ -276,6 +263,11 @@ void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float*
     dim3 grid(min((n + 255u) / 256u, 64u), fr.count);
     k_aabb<<<grid, 256, 0, s>>>(fr, d_idx, n, d_aabb);
     note_launch("k_aabb", s);
+}
+
+void launch_scan_home_cells(const FrameGeom* d_geom, const CellList& cl, int B, cudaStream_t s) {
+    k_scan_cells<1><<<B, 1024, 0, s>>>(d_geom, cl);
+    note_launch("k_scan_cells", s);
 }
 
 void launch_cell_list(int mode, const BatchFrames& fr, const int32_t* d_idx, const float* d_aos, uint32_t n, const FrameGeom* d_geom,

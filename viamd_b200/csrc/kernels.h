@@ -85,6 +85,10 @@ struct WithinArgs {
     uint32_t frame0;
 };
 void launch_within_count(const WithinArgs& a, int B, bool tri, int sm_count, cudaStream_t s);
+// the same marks as a per-frame ascending index list (dyn_idx [B][num_atoms], dyn_n [B]) and the home-grid cell list built from it
+void launch_within_list(const WithinArgs& a, int B, bool tri, int sm_count, int32_t* d_dyn_idx, uint32_t* d_dyn_n, cudaStream_t s);
+void launch_cell_list_dyn(const BatchFrames& fr, const int32_t* d_dyn_idx, const uint32_t* d_dyn_n, uint32_t max_n, const FrameGeom* d_geom, const CellList& cl, cudaStream_t s);
+void launch_scan_home_cells(const FrameGeom* d_geom, const CellList& cl, int B, cudaStream_t s);   // cells.cu: k_scan_cells<1> alone
 
 // props.cu
 struct DensityArgs {

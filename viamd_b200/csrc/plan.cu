@@ -47,6 +47,7 @@ struct Prop {
     uint32_t com_mask = 0;   // distance/angle/dihedral: bit k = argument k is a selection evaluated through md_util_com_compute
     std::vector<uint32_t> h_soff; uint32_t* d_soff = nullptr;   // rdf with centre-of-mass references: CSR offsets of the groups in idx[0]
     float cutoff_min = 0.f, cutoff_max = 0.f;
+    float ref_within = 0.f;   // rdf: > 0 -> the reference atoms are within(ref_within, idx[0]), evaluated per frame
     // device accumulators
     unsigned long long* d_acc = nullptr;          // rdf: 1024 bins; density: 1024 fixed-point sums
     uint32_t* d_vol = nullptr;                    // sdf: 128^3
@@ -78,7 +79,9 @@ struct PropScratch {   // per (stream slot, property)
     float4* d_sdf_xyzw = nullptr; float* d_sdf_ref0 = nullptr; float* d_sdf_mats = nullptr;
     float* d_com = nullptr;   // rdf with centre-of-mass references: [B][n_struct][3]
     float* d_argpos = nullptr;   // distance/angle/dihedral with selection arguments: [B][4][3]
-    uint8_t* d_flags = nullptr;  // count(within()): [B][num_atoms]
+    uint8_t* d_flags = nullptr;  // count(within()) / rdf(within(), ...): [B][num_atoms]
+    // rdf whose reference set is within(radius, selection): the system-wide grid + lists of the within() query, and the per-frame reference list
+    FrameGeom* d_wgeom = nullptr; float* d_waabb = nullptr; CellList wtrg{}, wref{}; int32_t* d_dyn_idx = nullptr; uint32_t* d_dyn_n = nullptr;
     // rdf candidate lists (k_rdf_cull): [B][list_stride] entries, [B][cap] headers, [B] cursors
     uint32_t* d_pair_list = nullptr; uint4* d_list_hdr = nullptr; uint32_t* d_list_cursor = nullptr; size_t list_stride = 0;
 };
@@ -191,7 +194,7 @@ static void destroy_plan(mdgpu_plan* p) {
     for (auto& s : p->slots) {
         for (auto& ps : s.ps) {
             cudaFree(ps.d_geom); cudaFree(ps.d_aabb); free_cell_list(ps.trg); free_cell_list(ps.ref);
-            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_flags); cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
+            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_flags); cudaFree(ps.d_wgeom); cudaFree(ps.d_waabb); free_cell_list(ps.wtrg); free_cell_list(ps.wref); cudaFree(ps.d_dyn_idx); cudaFree(ps.d_dyn_n); cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
         }
         cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
@@ -271,6 +274,8 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty reference positions");   // internal_rdf :5396-5403
             if (pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty target positions");
             if (pr.cutoff_min < 0.0f || pr.cutoff_max <= pr.cutoff_min) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': Invalid cutoff");
+            pr.ref_within = d.ref_within_radius;
+            if (pr.ref_within < 0.0f || (pr.ref_within > 0.0f && pr.n_struct)) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': invalid within() reference");
             if (pr.n_struct) {   // references = centres of mass of atom groups, a group's own atoms excluded (compute_rdf :5274-5275)
                 if (d.structure_offsets) pr.h_soff.assign(d.structure_offsets, d.structure_offsets + pr.n_struct + 1);
                 else { if (!pr.struct_size) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': structure_size or structure_offsets required");
@@ -460,6 +465,10 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
             for (auto& pr : p->props) if (pr.needs_cells() || pr.op == MDGPU_OP_WITHIN_COUNT) {
                 FrameGeom g; host_frame_geom(&g, first_cell, pr.op == MDGPU_OP_WITHIN_COUNT ? within_cell_ext(pr.cutoff_max) : (double)pr.cutoff_max, pr.cutoff_max, nullptr, 0xffffffffu);
                 need = std::max<uint64_t>(need, 2ull * std::max<uint64_t>(g.num_cells, g.num_home) + 2);
+                if (pr.ref_within > 0.0f) {
+                    host_frame_geom(&g, first_cell, within_cell_ext(pr.ref_within), pr.ref_within, nullptr, 0xffffffffu);
+                    need = std::max<uint64_t>(need, 2ull * std::max<uint64_t>(g.num_cells, g.num_home) + 2);
+                }
             }
             cap = (uint32_t)std::min<uint64_t>(need, 1u << 26);
             p->cell_cap = cap;
@@ -479,7 +488,14 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)pr.h_idx[1].size(), cap); if (rc) return rc;
                 }
                 if (pr.op == MDGPU_OP_RDF) {
-                    int rc = alloc_cell_list(ps.ref, p->B, (uint32_t)(pr.n_struct ? pr.n_struct : pr.h_idx[0].size()), cap); if (rc) return rc;
+                    int rc = alloc_cell_list(ps.ref, p->B, (uint32_t)(pr.ref_within > 0.0f ? p->num_atoms : (pr.n_struct ? pr.n_struct : pr.h_idx[0].size())), cap); if (rc) return rc;
+                    if (pr.ref_within > 0.0f) {
+                        CUDA_TRY(dalloc(&ps.d_wgeom, p->B)); CUDA_TRY(dalloc(&ps.d_waabb, (size_t)6 * p->B));
+                        rc = alloc_cell_list(ps.wtrg, p->B, (uint32_t)p->num_atoms, cap); if (rc) return rc;
+                        rc = alloc_cell_list(ps.wref, p->B, (uint32_t)pr.h_idx[0].size(), cap); if (rc) return rc;
+                        CUDA_TRY(dalloc(&ps.d_flags, (size_t)p->B * p->num_atoms));
+                        CUDA_TRY(dalloc(&ps.d_dyn_idx, (size_t)p->B * p->num_atoms)); CUDA_TRY(dalloc(&ps.d_dyn_n, p->B));
+                    }
                     if (pr.n_struct) CUDA_TRY(dalloc(&ps.d_com, (size_t)p->B * pr.n_struct * 3));
                     else {   // candidate lists of the packed pair kernel: every target appears in at most (2n+1)^3 home cells' lists
                         FrameGeom g; host_frame_geom(&g, first_cell, pr.cutoff_max, pr.cutoff_max, nullptr, 0xffffffffu);
@@ -539,7 +555,18 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
         }
         switch (pr.op) {
         case MDGPU_OP_RDF: {
-            if (pr.n_struct) {
+            if (pr.ref_within > 0.0f) {   // references = within(radius, idx[0]) of this frame (_within_expl_flt :2485), then compute_rdf as usual
+                const float* waabb = nullptr;
+                if (!all_pbc) { launch_aabb(fr, nullptr, (uint32_t)p->num_atoms, ps.d_waabb, s.stream); waabb = ps.d_waabb; }
+                launch_geom(s.d_cells, waabb, ps.d_wgeom, within_cell_ext(pr.ref_within), (double)pr.ref_within, p->cell_cap, B, s.d_err, s.stream);
+                launch_cell_list(0, fr, nullptr, nullptr, (uint32_t)p->num_atoms, ps.d_wgeom, ps.wtrg, 0, s.stream);
+                launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_wgeom, ps.wref, 0, s.stream);
+                WithinArgs w{};
+                w.geom = ps.d_wgeom; w.trg = ps.wtrg; w.ref = ps.wref; w.sel = pr.d_idx[0]; w.n_sel = (uint32_t)pr.h_idx[0].size();
+                w.num_atoms = (uint32_t)p->num_atoms; w.flags = ps.d_flags; w.out = nullptr; w.frame0 = frame0;
+                launch_within_list(w, B, tri, p->sm_count, ps.d_dyn_idx, ps.d_dyn_n, s.stream);
+                launch_cell_list_dyn(fr, ps.d_dyn_idx, ps.d_dyn_n, (uint32_t)p->num_atoms, cs.d_geom, ps.ref, s.stream);
+            } else if (pr.n_struct) {
                 launch_group_com(fr, pr.d_idx[0], pr.d_soff, (uint32_t)pr.n_struct, p->d_mass, ps.d_com, s.stream);
                 launch_cell_list(1, fr, nullptr, ps.d_com, (uint32_t)pr.n_struct, cs.d_geom, ps.ref, 0, s.stream);   // AoS stream: i = position index (:1721)
             } else {
@@ -553,7 +580,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.frame_bins = ps.d_frame_bins; a.frame0 = frame0;
             a.pair_list = ps.d_pair_list; a.list_hdr = ps.d_list_hdr; a.list_cursor = ps.d_list_cursor; a.list_stride = ps.list_stride; a.hdr_stride = p->cell_cap; a.err = s.d_err;
             a.excl_off = pr.n_struct ? pr.d_soff : nullptr; a.excl_idx = pr.n_struct ? pr.d_idx[0] : nullptr;   // md_bitfield_test_bit(&masks[i], j) :5252
-            a.symmetric = (!pr.n_struct && pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
+            a.symmetric = (!pr.n_struct && pr.ref_within == 0.0f && pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
             a.acc = pr.d_acc; a.frame_total = pr.d_frame_total; a.frame_min = pr.d_frame_min; a.frame_max = pr.d_frame_max; a.keep = pr.d_keep;
             TimedLaunch tl{};
             if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); }

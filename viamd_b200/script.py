@@ -172,13 +172,17 @@ class _Parser:
         ident = self.expect("id")[1]; self.expect("ch", "=")
         proc = self.expect("id")[1]; self.expect("ch", "(")
         if proc == "rdf":
-            grp = self.groups()
-            ref = None if grp is not None else self.selection()
+            wr = None
+            if self.peek() == ("id", "within"):   # dynamic reference set: within(radius, selection)
+                self.next(); self.expect("ch", "("); wr = self.number(); self.expect("ch", ","); wsel = self.single_selection(); self.expect("ch", ")")
+            grp = self.groups() if wr is None else None
+            ref = None if (grp is not None or wr is not None) else self.selection()
             self.expect("ch", ","); trg = self.selection(); self.expect("ch", ",")
             a = self.number(); lo, hi = 0.0, a
             if self.peek() == ("ch", ":"):
                 self.next(); lo, hi = a, self.number()
-            p = api.rdf_com(ident, grp, trg, hi, lo) if grp is not None else api.rdf(ident, ref, trg, hi, lo)
+            if wr is not None: p = api.rdf_within(ident, wr, wsel, trg, hi, lo)
+            else: p = api.rdf_com(ident, grp, trg, hi, lo) if grp is not None else api.rdf(ident, ref, trg, hi, lo)
         elif proc == "sdf":
             st = self.structures(); self.expect("ch", ","); trg = self.selection(); self.expect("ch", ","); c = self.number()
             p = api.sdf(ident, st, trg, c)
