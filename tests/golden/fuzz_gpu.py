@@ -1,4 +1,5 @@
 """Fuzz of the device path against the oracle (no reference needed; run on a B200 box):  python tests/golden/fuzz_gpu.py [cases] [seed]
+Without a GPU:  python tests/golden/fuzz_gpu.py [cases] [seed] --emulated   (the library's sources executed on the CPU, ~1 min per case)
 Random water boxes with anisotropic per-frame cells (one axis non-periodic or a sheared triclinic cell in part of the cases), random cutoffs
 and selections; per-frame rdf bins (plain, min:max, centre-of-mass references), sdf voxels, density sums, temporals have to equal the oracle's
 (bit-exact for integers and distances, 1e-5 for angles). Not collected by pytest: it is a search tool, the fixed cases live in tests/."""
@@ -8,6 +9,11 @@ HERE = os.path.dirname(os.path.abspath(__file__)); ROOT = os.path.dirname(os.pat
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O
 import viamd_b200 as vb
+
+if "--emulated" in sys.argv:   # no GPU: the library's own sources compiled for the CPU (tests/emul) — test infrastructure, swapped in inside this process only
+    sys.argv.remove("--emulated"); sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+    import build_emul, viamd_b200.api as _api
+    _api.LIB_PATH = build_emul.build_library(); _api._lib = None
 
 
 def main(cases=40, seed=1):
@@ -36,6 +42,9 @@ def main(cases=40, seed=1):
         scut = float(np.round(min(cut, 0.45 * L), 2))
         props = [vb.rdf("r", o, o, cut), vb.rdf("rh", h, o, cut, cmin), vb.rdf_com("rc", groups, h, cut), vb.density("dz", 2, o),
                  vb.distance("d", a1, a2), vb.distance("dg", np.arange(a1, a2 + 1), groups[1]), vb.angle("an", a1, a1 + 1, a2), vb.distance_min("dmn", np.arange(a1, a2 + 1), groups[0])]
+        sel = np.arange(a1, a2 + 1, dtype=np.int32); wr = float(np.round(min(cut, rng.uniform(2.0, 7.0)), 2)); allg = np.concatenate(groups)
+        props += [vb.rmsd("rm", allg), vb.distance_pair("dp", sel[:5], groups[0]), vb.com("cm", sel), vb.plane("pl", sel), vb.count_within("cw", wr, groups[0]),
+                  vb.rdf_within("rw", wr, groups[0], o, cut, cmin)]
         if full_pbc: props.append(vb.sdf("v", np.stack(groups), o, scut))
         cells = [vb.UnitCell(*cellp[f], flags) for f in range(F)]; ocells = [O.UnitCell.from_params(*cellp[f], flags) for f in range(F)]
         plan = vb.Plan(sysm, props, F, keep_frame_results=True, batch_frames=int(rng.choice([1, 3, 4])))
@@ -57,6 +66,16 @@ def main(cases=40, seed=1):
             chk(plan.property_data("dg").values[f] == O.distance_args(x, y, z, sysm.mass, np.arange(a1, a2 + 1), groups[1], oc), "dg", f)
             chk(abs(plan.property_data("an").values[f] - O.angle(x, y, z, a1, a1 + 1, a2)) <= 1e-5 * 3.2, "an", f)
             chk(plan.property_data("dmn").values[f] == O.min_distance(x, y, z, np.arange(a1, a2 + 1), groups[0], oc), "dmn", f)
+            co, ci = np.asarray(sysm.conn_offset, np.uint32), np.asarray(sysm.conn_idx, np.int32)
+            chk(plan.property_data("rm").values[f] == O.rmsd_frame(x, y, z, fr[0], sysm.mass, allg, co, ci, oc), "rm", f)
+            chk(np.array_equal(plan.property_data("dp").values[15 * f:15 * f + 15], O.distance_pair(x, y, z, sel[:5], groups[0], oc)), "dp", f)
+            chk(np.array_equal(plan.property_data("cm").values[3 * f:3 * f + 3], O.arg_position(x, y, z, sysm.mass, sel, oc)), "cm", f)
+            chk(np.array_equal(plan.property_data("pl").values[4 * f:4 * f + 4], O.plane_frame(x, y, z, sel, co, ci, oc)), "pl", f)
+            wref = O.within(x, y, z, groups[0], wr, oc)
+            chk(plan.property_data("cw").values[f] == len(wref), "cw", f)
+            if len(wref):
+                b, w, t = O.rdf_frame(x, y, z, wref, o, oc, cmin, cut); gb, gt = plan.frame_counts("rw", f)
+                chk(gt == t and np.array_equal(gb.astype(np.float32), b), "rw", f)
             if full_pbc:
                 vol, nn = O.sdf_frame(x, y, z, fr[0], sysm.mass, np.stack(groups), o, sysm.conn_offset, sysm.conn_idx, oc, scut)
                 chk(np.array_equal(plan.counts("v").astype(np.float32), vol), "v", f)
