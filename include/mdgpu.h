@@ -123,7 +123,7 @@ typedef enum mdgpu_op {
  *              at most 1 000 000 values per frame (:4056). Properties with more than one value per frame also carry per-frame aggregates
  *              (mdgpu_plan_property_aggregate).
  *   COM      : idx[0] as argument 0 of DISTANCE (bit 0 of com_args = it was a selection).   PLANE: idx[0] = the atoms (at least 3).
- *   WITHIN_COUNT: idx[0] = the selection's atoms, cutoff_max = radius (> 0). The dynamic selection within() is evaluated per frame over the
+ *   WITHIN_COUNT: idx[0] = the selection's atoms, cutoff_max = radius (> 0), cutoff_min = lower bound of the min:max form (else 0). The dynamic selection within() is evaluated per frame over the
  *              system-wide cell list (get_spatial_acc :734); so far its only consumer on the device is count().
  *   RMSD     : idx[0] = the atoms of the (flattened) selection; needs the initial frame and, to make molecules whole, the bond connectivity.
  *   DISTANCE/ANGLE/DIHEDRAL: idx[k] = the atoms of argument k (0-based). A single integer index is that atom's position; an
@@ -142,6 +142,7 @@ typedef struct mdgpu_property_desc_t {
     const uint32_t* structure_offsets;   /* optional CSR offsets into idx[0] for groups of different sizes (rdf) */
     uint32_t com_args;                   /* distance/angle/dihedral: bit k = argument k is a selection (centre of mass even for one atom) */
     float ref_within_radius;             /* rdf: > 0 -> the reference argument was within(radius, idx[0]): the dynamic selection is evaluated per frame */
+    float ref_within_min;                /* ... within(min:radius, idx[0]) (_within_expl_frng :2609); 0 for the plain form */
 } mdgpu_property_desc_t;
 
 /* Result view: the fields of md_script_property_data_t (md_script.h:73-92) that the evaluation fills. */

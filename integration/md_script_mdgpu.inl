@@ -97,8 +97,10 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         if (args[0]->type == AST_PROC_CALL && args[0]->proc && str_eq(args[0]->proc->name, STR_LIT("within")) && md_array_size(args[0]->children) == 2) {
             /* dynamic reference set within(radius, selection) (_within_expl_flt :2485): evaluated per frame on the device */
             ast_node_t** w = args[0]->children; size_t ns = 0;
-            if (!(w[0]->flags & FLAG_CONSTANT) || w[0]->data.type.base_type != TYPE_FLOAT || w[1]->data.type.base_type != TYPE_BITFIELD) goto dynamic;
-            out->ref_within_radius = *(const float*)w[0]->data.ptr;
+            if (!(w[0]->flags & FLAG_CONSTANT) || w[1]->data.type.base_type != TYPE_BITFIELD) goto dynamic;
+            if (w[0]->data.type.base_type == TYPE_FRANGE) { const frange_t r = *(const frange_t*)w[0]->data.ptr; out->ref_within_min = r.beg; out->ref_within_radius = r.end; }   /* _within_expl_frng :2609 */
+            else if (w[0]->data.type.base_type == TYPE_FLOAT) out->ref_within_radius = *(const float*)w[0]->data.ptr;
+            else goto dynamic;
             if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, w[1], alloc)) < 0 || ns > 1) goto dynamic; out->idx_count[0] = (size_t)n;
         } else
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &nsets, &set_size, args[0], alloc)) < 0) goto dynamic; else out->idx_count[0] = (size_t)n;
@@ -143,8 +145,11 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
     if (str_eq(pname, STR_LIT("count")) && nargs == 1 && args[0]->type == AST_PROC_CALL && args[0]->proc && str_eq(args[0]->proc->name, STR_LIT("within")) &&
         md_array_size(args[0]->children) == 2) {   /* count(within(radius, selection)): _within_expl_flt :2485 evaluated per frame on the device, _count :2868 */
         ast_node_t** w = args[0]->children; size_t ns = 0;
-        if (!(w[0]->flags & FLAG_CONSTANT) || w[0]->data.type.base_type != TYPE_FLOAT) goto dynamic;
-        out->op = MDGPU_OP_WITHIN_COUNT; out->cutoff_max = *(const float*)w[0]->data.ptr;
+        if (!(w[0]->flags & FLAG_CONSTANT)) goto dynamic;
+        out->op = MDGPU_OP_WITHIN_COUNT;
+        if (w[0]->data.type.base_type == TYPE_FRANGE) { const frange_t r = *(const frange_t*)w[0]->data.ptr; out->cutoff_min = r.beg; out->cutoff_max = r.end; }   /* _within_expl_frng :2609 */
+        else if (w[0]->data.type.base_type == TYPE_FLOAT) out->cutoff_max = *(const float*)w[0]->data.ptr;
+        else goto dynamic;
         if (w[1]->data.type.base_type != TYPE_BITFIELD) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': within() is lowered for a selection argument only", STR_ARG(ident)); return false; }
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, w[1], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
         if (ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false; }

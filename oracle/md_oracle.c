@@ -767,9 +767,19 @@ void mdo_debug_geom(const float* x, const float* y, const float* z, size_t n, co
  * extent ceil(radius / 6) * 6; the positions are an AoS stream (coordinate_extract of one bitfield). out_mask: one byte per atom.
  * Returns the number of atoms set. Groundwork for dynamic selections: the GPU path does not lower them yet.
  */
-static void within_pair(uint32_t i, uint32_t j, float d2, void* user) { (void)i; (void)d2; ((uint8_t*)user)[j] = 1; }   /* within_float_cb :2478 */
+typedef struct { uint8_t* mask; float min_r2; } within_user_t;
+static void within_pair(uint32_t i, uint32_t j, float d2, void* user) {   /* within_float_cb :2478, within_frng_cb :2599 (d2 >= min_r2) */
+    (void)i; const within_user_t* u = user; if (d2 >= u->min_r2) u->mask[j] = 1;
+}
+size_t mdo_within_range(const float* x, const float* y, const float* z, size_t num_atoms, const int32_t* sel, size_t n_sel, float rmin, float radius,
+                        const mdo_unitcell_t* cell, uint8_t* out_mask);
 size_t mdo_within(const float* x, const float* y, const float* z, size_t num_atoms, const int32_t* sel, size_t n_sel, float radius,
                   const mdo_unitcell_t* cell, uint8_t* out_mask) {
+    return mdo_within_range(x, y, z, num_atoms, sel, n_sel, 0.0f, radius, cell, out_mask);   /* every d2 is >= 0 */
+}
+/* within(min:max, selection): _within_expl_frng :2609-2661 — the grid and the query use max, a pair counts when d2 >= min * min (float) */
+size_t mdo_within_range(const float* x, const float* y, const float* z, size_t num_atoms, const int32_t* sel, size_t n_sel, float rmin, float radius,
+                        const mdo_unitcell_t* cell, uint8_t* out_mask) {
     memset(out_mask, 0, num_atoms);
     if (n_sel == 0 || num_atoms == 0) return 0;
     const double cell_ext = ceil((double)radius / 6.0) * 6.0;
@@ -778,7 +788,8 @@ size_t mdo_within(const float* x, const float* y, const float* z, size_t num_ato
     float* pos = malloc(sizeof(float) * 3 * n_sel);
     for (size_t k = 0; k < n_sel; ++k) { pos[3 * k] = x[sel[k]]; pos[3 * k + 1] = y[sel[k]]; pos[3 * k + 2] = z[sel[k]]; }
     stream_t ext = { x, y, z, NULL, pos, n_sel };
-    acc_ext_pairs(&acc, &ext, (double)radius, false, within_pair, out_mask);
+    within_user_t user = { out_mask, rmin * rmin };
+    acc_ext_pairs(&acc, &ext, (double)radius, false, within_pair, &user);
     for (size_t k = 0; k < n_sel; ++k) out_mask[sel[k]] = 0;
     size_t n = 0; for (size_t a = 0; a < num_atoms; ++a) n += out_mask[a];
     acc_free(&acc); free(pos);

@@ -47,6 +47,7 @@ def main(cases=40, seed=1):
                   vb.rdf_within("rw", wr, groups[0], o, cut, cmin)]
         if full_pbc: props.append(vb.sdf("v", np.stack(groups), o, scut))
         cells = [vb.UnitCell(*cellp[f], flags) for f in range(F)]; ocells = [O.UnitCell.from_params(*cellp[f], flags) for f in range(F)]
+        print("case", c, dict(n=n, seed=sd, cut=cut, cmin=cmin, flags=flags, nres=nres, wr=wr, tri=bool(tri)), flush=True)
         plan = vb.Plan(sysm, props, F, keep_frame_results=True, batch_frames=int(rng.choice([1, 3, 4])))
         plan.set_initial_frame(*fr[0], cells[0])
         def chk(ok, what, f):

@@ -18,7 +18,7 @@ reference's outputs, so the tests need neither the reference nor the harness on 
   tric6_rmsd.npz : the tric6 frames again: rmt = rmsd(residue(1:10)), rma = rmsd(atom(100:160)), rmo = rmsd(element('O')) — the triclinic wrap
                A * fract(I * r) of md_util_pbc_vec4, the triclinic bond-walk unwrap, non-contiguous selections
   pairs6.npz : multi-valued temporals on the water6 and the tric6 frames, each with its per-frame aggregates: distance_pair() matrices
-               (5 x 11 and 3 x 216 per frame), com() of a residue / 30 atoms / one atom, plane() of 30 atoms / all oxygens
+               (5 x 11 and 3 x 216 per frame), com() of a residue / 30 atoms / one atom, plane() of 30 atoms / all oxygens; count(within(min:max, sel))
   xtc_cases.npz : XTC byte streams from the reference's writer + the reference reader's decode of them (see xtc_cases below)
   ala50.npz  : first 50 frames of datasets/1ALA-500.pdb (153 atoms, ortho cell 46.645 x 96.666 x 48.362), config 1:
                d = distance(1,10) (BASELINE config 1), rc = rdf(element('C'), element('O'), 10.0), dz = density_z(element('C')),
@@ -168,7 +168,8 @@ def pairs6(tmp):
     on the water6 frames (orthorhombic) and the tric6 frames (triclinic cell changing every frame)."""
     out = {}
     script = ("dp = distance_pair(atom(1:5), atom(20:30)); dpo = distance_pair(residue(1), element('O')); "
-              "c = com(residue(1)); ca = com(atom(1:30)); ci = com(5); pl = plane(atom(1:30)); plo = plane(element('O'));")
+              "c = com(residue(1)); ca = com(atom(1:30)); ci = com(5); pl = plane(atom(1:30)); plo = plane(element('O')); "
+              "cwr = count(within(2.5:5.0, residue(1))); cwr2 = count(within(3.0:8.0, atom(10:40)));")
     w = np.load(os.path.join(HERE, "water6.npz")); t = np.load(os.path.join(HERE, "tric6.npz"))
     for tag, g, seed in (("w", w, "77"), ("t", t, "91")):
         gro, raw, o = os.path.join(tmp, tag + "p.gro"), os.path.join(tmp, tag + "p.raw"), os.path.join(tmp, tag + "p.out")
@@ -179,7 +180,7 @@ def pairs6(tmp):
             k = f"{tag}_{name}"
             out[k + "__dim"] = np.array(p.dim, np.int32); out[k + "__full"] = p.full
             m = p.meta[(1, 0)]; out[k + "__meta"] = np.array([m["min_value"], m["max_value"], m["min_range"][0], m["max_range"][0]], np.float32)
-            out[k + "__mean"] = p.aggregate["mean"]; out[k + "__var"] = p.aggregate["var"]; out[k + "__ext"] = p.aggregate["ext"]
+            if p.aggregate is not None: out[k + "__mean"] = p.aggregate["mean"]; out[k + "__var"] = p.aggregate["var"]; out[k + "__ext"] = p.aggregate["ext"]
     out["script"] = np.array(script)
     np.savez_compressed(os.path.join(HERE, "pairs6.npz"), **out)
 

@@ -211,10 +211,10 @@ def rmsd_frame(x, y, z, init_xyz, mass, idx, conn_off, conn_idx, cell):
                                            _p(mass, C.c_float), _p(idx, C.c_int32), C.c_size_t(len(idx)), _p(co, C.c_uint32), _p(ci, C.c_int32), C.c_size_t(len(co)), C.byref(cell)))
 
 
-def within(x, y, z, sel, radius, cell):
-    """-> ascending atom indices within `radius` of any atom of `sel` (sel itself removed)"""
+def within(x, y, z, sel, radius, cell, rmin=0.0):
+    """-> ascending atom indices within `radius` (and at least `rmin`) of any atom of `sel` (sel itself removed)"""
     x, y, z = _f32(x), _f32(y), _f32(z); sel = _i32(sel); mask = np.zeros(len(x), np.uint8)
-    lib().mdo_within.restype = C.c_size_t
-    n = lib().mdo_within(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), C.c_size_t(len(x)), _p(sel, C.c_int32), C.c_size_t(len(sel)), C.c_float(radius), C.byref(cell), _p(mask, C.c_uint8))
+    lib().mdo_within_range.restype = C.c_size_t
+    n = lib().mdo_within_range(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), C.c_size_t(len(x)), _p(sel, C.c_int32), C.c_size_t(len(sel)), C.c_float(rmin), C.c_float(radius), C.byref(cell), _p(mask, C.c_uint8))
     idx = np.nonzero(mask)[0].astype(np.int32); assert len(idx) == n
     return idx

@@ -159,6 +159,27 @@ def test_count_within_goldens_and_oracle():
         vb.Plan(vb.water_system(4), [vb.count_within("c", 0.0, np.arange(3))], 2)
 
 
+def test_within_min_max_form():
+    """within(min:max, selection) (_within_expl_frng :2609): as the argument of count() against the reference (pairs6.npz, ortho + triclinic) and
+    as the reference set of an rdf against the oracle."""
+    import viamd_b200 as vb
+    p = load_golden("pairs6.npz")
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        g = load_golden(name); s = golden_system(g); F = g["frames"].shape[0]; o = sel_element(s, 8)
+        plan, cells = _plan(g, s, "cwr = count(within(2.5:5.0, residue(1))); cwr2 = count(within(3.0:8.0, atom(10:40))); rwr = rdf(within(3.0:6.0, residue(2)), element('O'), 1.0:6.5);", keep_frame_results=True)
+        plan.eval_host_frames(g["frames"], cells, 0)
+        assert np.array_equal(plan.property_data("cwr").values, p[f"{tag}_cwr__full"]) and np.array_equal(plan.property_data("cwr2").values, p[f"{tag}_cwr2__full"])
+        for f in range(F):
+            x, y, z = g["frames"][f]; cell = cell_from_row(g["cells"][f], g["cell_flags"][f])
+            ref = O.within(x, y, z, np.arange(3, 6, dtype=np.int32), 6.0, cell, rmin=3.0)
+            want, _, tot_w = O.rdf_frame(x, y, z, ref, o, cell, 1.0, 6.5)
+            bins, tot = plan.frame_counts("rwr", f)
+            assert np.array_equal(bins.astype(np.float32), want) and tot == tot_w, (tag, f)
+        plan.close()
+    with pytest.raises(vb.MdgpuError):
+        vb.Plan(vb.water_system(4), [vb.count_within("c", 3.0, np.arange(3), radius_min=4.0)], 2)
+
+
 def test_rdf_with_a_dynamic_within_reference_set():
     """rdf(within(radius, selection), targets, cutoff): the reference atoms change every frame (marks -> per-frame index list -> home-grid cell
     list -> the usual cull + pair kernels). Per-frame bins, weights and the mean against the reference (golden rw); a second property in

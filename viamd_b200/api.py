@@ -69,7 +69,7 @@ class _SystemDesc(C.Structure):
 class _PropertyDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("op", C.c_uint32), ("idx", C.POINTER(C.c_int32) * 4), ("idx_count", C.c_size_t * 4),
                 ("num_structures", C.c_size_t), ("structure_size", C.c_size_t), ("cutoff_min", C.c_float), ("cutoff_max", C.c_float),
-                ("structure_offsets", C.POINTER(C.c_uint32)), ("com_args", C.c_uint32), ("ref_within_radius", C.c_float)]
+                ("structure_offsets", C.POINTER(C.c_uint32)), ("com_args", C.c_uint32), ("ref_within_radius", C.c_float), ("ref_within_min", C.c_float)]
 
 
 class _PropertyData(C.Structure):
@@ -200,17 +200,18 @@ class Property:
     cutoff_max: float = 0.0
     structure_offsets: Optional[np.ndarray] = None   # rdf_com: CSR offsets of the groups in idx[0]
     com_args: int = 0                                # distance/angle/dihedral: bit k = argument k is a selection (centre of mass)
-    ref_within: float = 0.0                          # rdf: > 0 -> references = within(ref_within, idx[0]) evaluated per frame
+    ref_within: float = 0.0                          # rdf: > 0 -> references = within([ref_within_min:]ref_within, idx[0]) evaluated per frame
+    ref_within_min: float = 0.0
 
 
 def rdf(name, ref_idx, trg_idx, cutoff, cutoff_min=0.0):
     return Property(name, OP_RDF, [np.asarray(ref_idx, np.int32), np.asarray(trg_idx, np.int32)], cutoff_min=float(cutoff_min), cutoff_max=float(cutoff))
 
 
-def rdf_within(name, radius, sel_idx, trg_idx, cutoff, cutoff_min=0.0):
+def rdf_within(name, radius, sel_idx, trg_idx, cutoff, cutoff_min=0.0, radius_min=0.0):
     """rdf(within(radius, selection), targets, cutoff): the reference atoms are the dynamic selection within() of each frame — every atom of the
     system within `radius` of the selection, the selection itself excluded (md_script_functions.inl:2485) — then compute_rdf as usual."""
-    return Property(name, OP_RDF, [np.asarray(sel_idx, np.int32), np.asarray(trg_idx, np.int32)], cutoff_min=float(cutoff_min), cutoff_max=float(cutoff), ref_within=float(radius))
+    return Property(name, OP_RDF, [np.asarray(sel_idx, np.int32), np.asarray(trg_idx, np.int32)], cutoff_min=float(cutoff_min), cutoff_max=float(cutoff), ref_within=float(radius), ref_within_min=float(radius_min))
 
 
 def rdf_com(name, groups, trg_idx, cutoff, cutoff_min=0.0):
@@ -271,10 +272,10 @@ def plane(name, idx):
     return Property(name, OP_PLANE, [np.asarray(idx, np.int32)])
 
 
-def count_within(name, radius, sel_idx):
+def count_within(name, radius, sel_idx, radius_min=0.0):
     """count(within(radius, selection)): per frame, the number of atoms of the system within `radius` of any atom of the selection, the
     selection itself excluded (_within_expl_flt md_script_functions.inl:2485, _count :2868) — a dynamic selection evaluated on the device"""
-    return Property(name, OP_WITHIN_COUNT, [np.asarray(sel_idx, np.int32)], cutoff_max=float(radius))
+    return Property(name, OP_WITHIN_COUNT, [np.asarray(sel_idx, np.int32)], cutoff_min=float(radius_min), cutoff_max=float(radius))   # min:max form: _within_expl_frng :2609
 
 
 def rmsd(name, idx):
@@ -385,7 +386,7 @@ class Plan:
             d = descs[i]; nm = p.name.encode(); self._keep.append(nm)
             d.name = nm; d.op = p.op; d.num_structures = p.num_structures; d.structure_size = p.structure_size
             d.cutoff_min = p.cutoff_min; d.cutoff_max = p.cutoff_max
-            d.com_args = p.com_args; d.ref_within_radius = p.ref_within
+            d.com_args = p.com_args; d.ref_within_radius = p.ref_within; d.ref_within_min = p.ref_within_min
             if p.structure_offsets is not None:
                 so = np.ascontiguousarray(p.structure_offsets, np.uint32); self._keep.append(so)
                 d.structure_offsets = so.ctypes.data_as(C.POINTER(C.c_uint32))

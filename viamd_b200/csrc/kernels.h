@@ -79,6 +79,7 @@ struct WithinArgs {
     const FrameGeom* geom;           // grid of ALL atoms: cell extent ceil(radius/6)*6, cutoff = radius (get_spatial_acc)
     CellList trg, ref;               // all atoms (clamped cells) / the selection's atoms (home grid)
     const int32_t* sel; uint32_t n_sel;
+    float min_r2;                    // within(min:max, ...): a pair counts from d2 >= min * min on; 0 for within(radius, ...)
     uint32_t num_atoms;
     uint8_t* flags;                  // [B][num_atoms], zeroed by the launcher
     float* out;                      // [num_frames]

@@ -47,7 +47,7 @@ struct Prop {
     uint32_t com_mask = 0;   // distance/angle/dihedral: bit k = argument k is a selection evaluated through md_util_com_compute
     std::vector<uint32_t> h_soff; uint32_t* d_soff = nullptr;   // rdf with centre-of-mass references: CSR offsets of the groups in idx[0]
     float cutoff_min = 0.f, cutoff_max = 0.f;
-    float ref_within = 0.f;   // rdf: > 0 -> the reference atoms are within(ref_within, idx[0]), evaluated per frame
+    float ref_within = 0.f, ref_within_min = 0.f;   // rdf: ref_within > 0 -> the reference atoms are within([min:]ref_within, idx[0]), evaluated per frame
     // device accumulators
     unsigned long long* d_acc = nullptr;          // rdf: 1024 bins; density: 1024 fixed-point sums
     uint32_t* d_vol = nullptr;                    // sdf: 128^3
@@ -274,8 +274,8 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty reference positions");   // internal_rdf :5396-5403
             if (pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty target positions");
             if (pr.cutoff_min < 0.0f || pr.cutoff_max <= pr.cutoff_min) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': Invalid cutoff");
-            pr.ref_within = d.ref_within_radius;
-            if (pr.ref_within < 0.0f || (pr.ref_within > 0.0f && pr.n_struct)) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': invalid within() reference");
+            pr.ref_within = d.ref_within_radius; pr.ref_within_min = d.ref_within_min;
+            if (pr.ref_within < 0.0f || (pr.ref_within > 0.0f && pr.n_struct) || pr.ref_within_min < 0.0f || (pr.ref_within > 0.0f && pr.ref_within < pr.ref_within_min)) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': invalid within() reference");
             if (pr.n_struct) {   // references = centres of mass of atom groups, a group's own atoms excluded (compute_rdf :5274-5275)
                 if (d.structure_offsets) pr.h_soff.assign(d.structure_offsets, d.structure_offsets + pr.n_struct + 1);
                 else { if (!pr.struct_size) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': structure_size or structure_offsets required");
@@ -344,6 +344,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             break; }
         case MDGPU_OP_WITHIN_COUNT:   // count(within(radius, selection)); an empty selection is valid (nothing is within reach of nothing)
             if (!(pr.cutoff_max > 0.0f)) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': The supplied radius is negative or zero, please supply a positive value");   // :2528
+            if (pr.cutoff_min < 0.0f || pr.cutoff_max < pr.cutoff_min) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': The supplied radius range is invalid");          // :2654
             e = dalloc(&pr.d_temporal, num_frames);
             pr.values.assign(num_frames, 0.0f);
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
@@ -563,7 +564,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
                 launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_wgeom, ps.wref, 0, s.stream);
                 WithinArgs w{};
                 w.geom = ps.d_wgeom; w.trg = ps.wtrg; w.ref = ps.wref; w.sel = pr.d_idx[0]; w.n_sel = (uint32_t)pr.h_idx[0].size();
-                w.num_atoms = (uint32_t)p->num_atoms; w.flags = ps.d_flags; w.out = nullptr; w.frame0 = frame0;
+                w.num_atoms = (uint32_t)p->num_atoms; w.flags = ps.d_flags; w.out = nullptr; w.frame0 = frame0; w.min_r2 = pr.ref_within_min * pr.ref_within_min;
                 launch_within_list(w, B, tri, p->sm_count, ps.d_dyn_idx, ps.d_dyn_n, s.stream);
                 launch_cell_list_dyn(fr, ps.d_dyn_idx, ps.d_dyn_n, (uint32_t)p->num_atoms, cs.d_geom, ps.ref, s.stream);
             } else if (pr.n_struct) {
@@ -620,7 +621,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_geom, ps.ref, 0, s.stream);
             WithinArgs a{};
             a.geom = ps.d_geom; a.trg = ps.trg; a.ref = ps.ref; a.sel = pr.d_idx[0]; a.n_sel = (uint32_t)pr.h_idx[0].size();
-            a.num_atoms = (uint32_t)p->num_atoms; a.flags = ps.d_flags; a.out = pr.d_temporal; a.frame0 = frame0;
+            a.num_atoms = (uint32_t)p->num_atoms; a.flags = ps.d_flags; a.out = pr.d_temporal; a.frame0 = frame0; a.min_r2 = pr.cutoff_min * pr.cutoff_min;   // :2641
             launch_within_count(a, B, tri, p->sm_count, s.stream);
             break; }
         case MDGPU_OP_COM: {

@@ -2,7 +2,8 @@
 //
 // Replaces _within_expl_flt + within_float_cb (reference md_script_functions.inl:2478-2533) over the system-wide cell list of
 // get_spatial_acc (:734-760: every atom of the system, cell extent ceil(radius / 6) * 6), and _count (:2868) on the result:
-// the atoms of the system within `radius` of any atom of the selection, the selection's own atoms excluded (:2521-2525).
+// the atoms of the system within `radius` of any atom of the selection, the selection's own atoms excluded (:2521-2525); the min:max form
+// (_within_expl_frng :2609) queries at max and accepts a pair from d2 >= min * min on.
 //
 // The cell lists come from cells.cu exactly as for rdf(): targets = all atoms (clamped cells), references = the selection's atoms in
 // the home grid. The pair enumeration is the reference's (core/md_spatial_acc.c:1649-1803 / :1498-1647): (2n+1)^3 neighbour offsets of
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(WITHIN_WARPS * 32) k_within_mark(WithinArgs a)
     const int cd0 = g.cdim[0], cd1 = g.cdim[1], cd2 = g.cdim[2], n0 = g.ncell[0], n1 = g.ncell[1], n2 = g.ncell[2];
     const int w0 = 2 * n0 + 1, w1 = 2 * n1 + 1, w2 = 2 * n2 + 1, nn = w0 * w1 * w2;
     const uint32_t hd0 = (uint32_t)g.hdim[0], hd1 = (uint32_t)g.hdim[1];
-    const float r2 = g.r2;
+    const float r2 = g.r2, min_r2 = a.min_r2;
     for (uint32_t h = blockIdx.x * WITHIN_WARPS + warp; h < g.num_home; h += gridDim.x * WITHIN_WARPS) {
         const uint32_t rb = ref_off[h], re = ref_off[h + 1];
         if (rb == re) continue;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(WITHIN_WARPS * 32) k_within_mark(WithinArgs a)
                     const float4 rf = ref[i];
                     const float fx = __fadd_rn(rf.x, shx), fy = __fadd_rn(rf.y, shy), fz = __fadd_rn(rf.z, shz);   // f + image shift (:1755)
                     const float d2 = within_d2<TRI>(__fsub_rn(fx, t.x), __fsub_rn(fy, t.y), __fsub_rn(fz, t.z), g);
-                    hit = d2 <= r2;
+                    hit = d2 <= r2 && d2 >= min_r2;   // within_frng_cb (:2599-2607); min_r2 = 0 for the plain form
                 }
                 if (hit) flags[tj] = 1;
             }

@@ -162,6 +162,13 @@ class _Parser:
     def number(self) -> float:
         return float(self.expect("num")[1])
 
+    def radius(self):
+        """radius | min:max -> (min, max)"""
+        a = self.number()
+        if self.peek() == ("ch", ":"):
+            self.next(); return a, self.number()
+        return 0.0, a
+
     def index(self):
         """argument of distance/angle/dihedral: a 1-based atom index (-> int) or a selection (-> index array, centre of mass)"""
         if self.peek()[0] == "num":
@@ -174,14 +181,14 @@ class _Parser:
         if proc == "rdf":
             wr = None
             if self.peek() == ("id", "within"):   # dynamic reference set: within(radius, selection)
-                self.next(); self.expect("ch", "("); wr = self.number(); self.expect("ch", ","); wsel = self.single_selection(); self.expect("ch", ")")
+                self.next(); self.expect("ch", "("); wlo, wr = self.radius(); self.expect("ch", ","); wsel = self.single_selection(); self.expect("ch", ")")
             grp = self.groups() if wr is None else None
             ref = None if (grp is not None or wr is not None) else self.selection()
             self.expect("ch", ","); trg = self.selection(); self.expect("ch", ",")
             a = self.number(); lo, hi = 0.0, a
             if self.peek() == ("ch", ":"):
                 self.next(); lo, hi = a, self.number()
-            if wr is not None: p = api.rdf_within(ident, wr, wsel, trg, hi, lo)
+            if wr is not None: p = api.rdf_within(ident, wr, wsel, trg, hi, lo, wlo)
             else: p = api.rdf_com(ident, grp, trg, hi, lo) if grp is not None else api.rdf(ident, ref, trg, hi, lo)
         elif proc == "sdf":
             st = self.structures(); self.expect("ch", ","); trg = self.selection(); self.expect("ch", ","); c = self.number()
@@ -193,8 +200,8 @@ class _Parser:
             p = {"distance_min": api.distance_min, "distance_max": api.distance_max, "distance_pair": api.distance_pair}[proc](ident, a, b)
         elif proc == "count":   # count(within(radius, selection)): the one dynamic selection the device path evaluates
             if self.peek() != ("id", "within"): raise ScriptError("count() is lowered for within(radius, selection) only")
-            self.next(); self.expect("ch", "("); r = self.number(); self.expect("ch", ","); sel = self.single_selection(); self.expect("ch", ")")
-            p = api.count_within(ident, r, sel)
+            self.next(); self.expect("ch", "("); rlo, r = self.radius(); self.expect("ch", ","); sel = self.single_selection(); self.expect("ch", ")")
+            p = api.count_within(ident, r, sel, rlo)
         elif proc == "com":
             p = api.com(ident, self.index())
         elif proc == "plane":
