@@ -159,6 +159,28 @@ def test_count_within_goldens_and_oracle():
         vb.Plan(vb.water_system(4), [vb.count_within("c", 0.0, np.arange(3))], 2)
 
 
+def test_rdf_candidate_lists_follow_a_cell_whose_neighbour_reach_grows():
+    """Regression (found by tests/golden/fuzz_gpu.py --emulated): a sheared cell can take the pair query from 27 to 45+ neighbour offsets in a
+    later frame; the candidate lists were sized from the first frame's cell and the evaluation failed with MDGPU_ERR_CAPACITY. They now grow
+    with the batch's cells. Frame 0: shear 0.05 L (reach 1,1,1); frames 1-3: shear 0.25 L (reach 2,1,1). Bins against the oracle."""
+    import viamd_b200 as vb
+    n = 6; sysm = vb.water_system(n); base, L = vb.synth_water_base(n, 9725); F = 4
+    fr = vb.synth_water_frames_host(n, 9725, base, 0, F).astype(np.float64); o = np.arange(0, 3 * n ** 3, 3, dtype=np.int32)
+    cells, ocells = [], []
+    for f in range(F):
+        sh = (0.05 if f == 0 else 0.25) * L; xy, xz, yz = sh, -sh, sh
+        X, Y, Z = fr[f].copy(); fr[f, 0] = X + (xy / L) * Y + (xz / L) * Z; fr[f, 1] = Y + (yz / L) * Z
+        cells.append(vb.UnitCell(L, xy, xz, L, yz, L, vb.CELL_TRICLINIC | vb.CELL_PBC_ALL)); ocells.append(O.UnitCell.from_params(L, xy, xz, L, yz, L, vb.CELL_TRICLINIC | vb.CELL_PBC_ALL))
+    fr = fr.astype(np.float32)
+    for bf in (1, 4):   # growth between batches and inside one batch
+        plan = vb.Plan(sysm, [vb.rdf("r", o, o, 3.59)], F, keep_frame_results=True, batch_frames=bf)
+        plan.eval_host_frames(fr, cells, 0)
+        for f in range(F):
+            want, _, tot_w = O.rdf_frame(*fr[f], o, o, ocells[f], 0.0, 3.59); bins, tot = plan.frame_counts("r", f)
+            assert np.array_equal(bins.astype(np.float32), want) and tot == tot_w, (bf, f)
+        plan.close()
+
+
 def test_within_min_max_form():
     """within(min:max, selection) (_within_expl_frng :2609): as the argument of count() against the reference (pairs6.npz, ortho + triclinic) and
     as the reference set of an rdf against the oracle."""

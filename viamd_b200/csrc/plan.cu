@@ -84,6 +84,7 @@ struct PropScratch {   // per (stream slot, property)
     FrameGeom* d_wgeom = nullptr; float* d_waabb = nullptr; CellList wtrg{}, wref{}; int32_t* d_dyn_idx = nullptr; uint32_t* d_dyn_n = nullptr;
     // rdf candidate lists (k_rdf_cull): [B][list_stride] entries, [B][cap] headers, [B] cursors
     uint32_t* d_pair_list = nullptr; uint4* d_list_hdr = nullptr; uint32_t* d_list_cursor = nullptr; size_t list_stride = 0;
+    mdgpu_unitcell_t nn_cell{}; size_t nn_of_cell = 0; bool nn_valid = false;   // neighbour-offset count of the last cell seen (list sizing)
 };
 
 struct Slot {
@@ -573,6 +574,24 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             } else {
                 launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), cs.d_geom, ps.ref, 0, s.stream);
             }
+            if (!pr.n_struct) {   // candidate lists: the neighbour reach follows the frame's cell (an NPT or sheared cell can cross from 27 to 125 offsets)
+                size_t nn_max = 0;
+                for (int i = 0; i < B; ++i) {
+                    if (!ps.nn_valid || memcmp(&ps.nn_cell, &s.h_cells[i], sizeof(mdgpu_unitcell_t)) != 0) {   // constant-cell trajectories: one evaluation
+                        FrameGeom g; host_frame_geom(&g, &s.h_cells[i], pr.cutoff_max, pr.cutoff_max, nullptr, 0xffffffffu);
+                        size_t nn = (size_t)(2 * std::max(g.ncell[0], 1) + 1) * (2 * std::max(g.ncell[1], 1) + 1) * (2 * std::max(g.ncell[2], 1) + 1);
+                        if (g.valid <= 0 || (s.h_cells[i].flags & MDGPU_CELL_PBC_ALL) != MDGPU_CELL_PBC_ALL) nn = 125;
+                        ps.nn_cell = s.h_cells[i]; ps.nn_of_cell = std::min<size_t>(nn, 125); ps.nn_valid = true;
+                    }
+                    nn_max = std::max(nn_max, ps.nn_of_cell);
+                }
+                const size_t need = nn_max * pr.h_idx[1].size() + 1024;
+                if (need > ps.list_stride) {   // the slot was retired before this batch: its buffers are idle
+                    CUDA_TRY(cudaStreamSynchronize(s.stream));
+                    cudaFree(ps.d_pair_list); ps.d_pair_list = nullptr; ps.list_stride = need;
+                    CUDA_TRY(dalloc(&ps.d_pair_list, (size_t)p->B * ps.list_stride));
+                }
+            }
             RdfArgs a{};
             a.geom = cs.d_geom; a.trg = cs.trg; a.ref = ps.ref;
             a.inv_cutoff_range = 1.0f / (pr.cutoff_max - pr.cutoff_min);                 // before the clamp (compute_rdf :5264)
@@ -994,7 +1013,7 @@ int mdgpu_plan_sync(mdgpu_plan* p) {
     CUDA_TRY(cudaDeviceSynchronize());
     for (auto& s : p->slots) {
         int err = 0; CUDA_TRY(cudaMemcpy(&err, s.d_err, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) { cudaMemset(s.d_err, 0, sizeof(int)); return fail(err, err == MDGPU_ERR_CAPACITY ? "a frame needs more cells (or, with a shrinking cell, more rdf candidate-list space) than the plan reserved from its first frame (cell capacity %u); raise mdgpu_plan_options_t.cell_capacity" : (err == MDGPU_ERR_FRAME_SOURCE ? "XTC: Failed to decode frame data (%d)" : "device-side error %d"), err == MDGPU_ERR_CAPACITY ? p->cell_cap : (uint32_t)err); }
+        if (err) { cudaMemset(s.d_err, 0, sizeof(int)); return fail(err, err == MDGPU_ERR_CAPACITY ? "a frame needs more cells than the plan reserved from its first frame (cell capacity %u); raise mdgpu_plan_options_t.cell_capacity" : (err == MDGPU_ERR_FRAME_SOURCE ? "XTC: Failed to decode frame data (%d)" : "device-side error %d"), err == MDGPU_ERR_CAPACITY ? p->cell_cap : (uint32_t)err); }
     }
     for (auto& t : p->timed) { float ms = 0; if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { p->timed_ms[t.kind] += ms; p->timed_n[t.kind] += 1; } cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     p->timed.clear();
