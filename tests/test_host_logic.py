@@ -49,6 +49,11 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "md_oracle" not in src and "oracle_lib" not in src and "liboracle" not in src, f
+                # nor the CPU emulation the tests use (tests/emul): the product has no switch that could load it
+                assert "libmdgpu_emul" not in src and "fake_cudart" not in src and "emul_launch" not in src and "MDG_HOST_EMULATION" not in src, f
+    for f in ("bench.py", "__graft_entry__.py"):
+        src = open(os.path.join(ROOT, f)).read()
+        assert "libmdgpu_emul" not in src and "build_emul" not in src and "tests/emul" not in src and "tests.emul" not in src, f
 
 
 def test_script_lowering(vb):
