@@ -170,15 +170,19 @@ __global__ void k_scatter_dyn(const uint32_t* __restrict__ dyn_n, CellList cl) {
     cl.sorted[(size_t)f * cl.max_points + dst] = cl.scratch[o];
 }
 
+// zero the flags, mark: a few CTAs per frame, enough to fill the SMs across the batch
+static void launch_mark(const WithinArgs& a, int B, bool tri, int sm_count, cudaStream_t s) {
+    cudaMemsetAsync(a.flags, 0, (size_t)B * a.num_atoms, s);
+    if (!a.n_sel) return;
+    const dim3 grid((unsigned)max(1, (4 * sm_count) / max(B, 1) + 1), (unsigned)B);
+    if (tri) k_within_mark<true><<<grid, WITHIN_WARPS * 32, 0, s>>>(a); else k_within_mark<false><<<grid, WITHIN_WARPS * 32, 0, s>>>(a);
+    note_launch("k_within_mark", s);
+}
+
 // within() marks -> per-frame reference list (dyn_idx [B][num_atoms], dyn_n [B])
 void launch_within_list(const WithinArgs& a, int B, bool tri, int sm_count, int32_t* d_dyn_idx, uint32_t* d_dyn_n, cudaStream_t s) {
     if (B <= 0) return;
-    cudaMemsetAsync(a.flags, 0, (size_t)B * a.num_atoms, s);
-    if (a.n_sel) {
-        const dim3 grid((unsigned)max(1, (4 * sm_count) / max(B, 1) + 1), (unsigned)B);
-        if (tri) k_within_mark<true><<<grid, WITHIN_WARPS * 32, 0, s>>>(a); else k_within_mark<false><<<grid, WITHIN_WARPS * 32, 0, s>>>(a);
-        note_launch("k_within_mark", s);
-    }
+    launch_mark(a, B, tri, sm_count, s);
     k_within_compact<<<B, 256, 0, s>>>(a, d_dyn_idx, d_dyn_n);
     note_launch("k_within_compact", s);
 }
@@ -196,12 +200,7 @@ void launch_cell_list_dyn(const BatchFrames& fr, const int32_t* d_dyn_idx, const
 
 void launch_within_count(const WithinArgs& a, int B, bool tri, int sm_count, cudaStream_t s) {
     if (B <= 0) return;
-    cudaMemsetAsync(a.flags, 0, (size_t)B * a.num_atoms, s);
-    if (a.n_sel) {
-        const dim3 grid((unsigned)max(1, (4 * sm_count) / max(B, 1) + 1), (unsigned)B);
-        if (tri) k_within_mark<true><<<grid, WITHIN_WARPS * 32, 0, s>>>(a); else k_within_mark<false><<<grid, WITHIN_WARPS * 32, 0, s>>>(a);
-        note_launch("k_within_mark", s);
-    }
+    launch_mark(a, B, tri, sm_count, s);
     k_within_count<<<B, 256, 0, s>>>(a);
     note_launch("k_within_count", s);
 }
