@@ -122,6 +122,8 @@ typedef enum mdgpu_op {
  *   DISTANCE_PAIR: idx[0], idx[1] as for DISTANCE_MIN; row f of the property holds out[i * |b| + j] (md_util_distance_array md_util.c:8210);
  *              at most 1 000 000 values per frame (:4056). Properties with more than one value per frame also carry per-frame aggregates
  *              (mdgpu_plan_property_aggregate).
+ *              With num_structures = n > 0 the statement was `expr in <n contexts>` (evaluate_context md_script.c:3418) with integer arguments:
+ *              idx[k] holds n atoms, argument k remapped into each context (first atom of the context + k - 1); the property is [F, n].
  *   COM      : idx[0] as argument 0 of DISTANCE (bit 0 of com_args = it was a selection).   PLANE: idx[0] = the atoms (at least 3).
  *   WITHIN_COUNT: idx[0] = the selection's atoms, cutoff_max = radius (> 0), cutoff_min = lower bound of the min:max form (else 0). The dynamic selection within() is evaluated per frame over the
  *              system-wide cell list (get_spatial_acc :734); so far its only consumer on the device is count().

@@ -86,8 +86,18 @@ static size_t mdgpu__flatten(int32_t* v, size_t n) {
 
 static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const ast_node_t* node, md_allocator_i* alloc) {
     const ast_node_t* rhs = mdgpu__rhs(node);
+    const md_bitfield_t* ctx_bf = NULL; size_t n_ctx = 0;
+    if (rhs->type == AST_CONTEXT && rhs->children && md_array_size(rhs->children) == 2) {   /* `expr in contexts` (evaluate_context md_script.c:3418) */
+        const ast_node_t* cn = rhs->children[1];
+        if (!cn->data.ptr || cn->data.type.base_type != TYPE_BITFIELD) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': the contexts of `in` are not a static selection array", STR_ARG(ident)); return false; }
+        ctx_bf = (const md_bitfield_t*)cn->data.ptr; n_ctx = element_count(cn->data); rhs = rhs->children[0];
+        if (!n_ctx) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': no contexts", STR_ARG(ident)); return false; }
+    }
     if (rhs->type != AST_PROC_CALL || !rhs->proc) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "' is not a direct procedure call", STR_ARG(ident)); return false; }
     const str_t pname = rhs->proc->name;
+    if (n_ctx && !(str_eq(pname, STR_LIT("distance")) || str_eq(pname, STR_LIT("angle")) || str_eq(pname, STR_LIT("dihedral")))) {
+        MD_LOG_ERROR("mdgpu: property '" STR_FMT "': `in` is lowered for distance / angle / dihedral only", STR_ARG(ident)); return false;
+    }
     const size_t nargs = md_array_size(rhs->children);
     ast_node_t** args = rhs->children;
     memset(out, 0, sizeof(*out));
@@ -173,6 +183,20 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
     {
         const bool dist = str_eq(pname, STR_LIT("distance")), ang = str_eq(pname, STR_LIT("angle")), dih = str_eq(pname, STR_LIT("dihedral"));
         const size_t need = dist ? 2 : (ang ? 3 : (dih ? 4 : 0));
+        if (need && nargs == need && n_ctx) {   /* integer arguments remapped into every context: first atom of the context + i - 1 (remap_index_to_context :1023) */
+            out->op = dist ? MDGPU_OP_DISTANCE : (ang ? MDGPU_OP_ANGLE : MDGPU_OP_DIHEDRAL);
+            out->num_structures = n_ctx;
+            for (size_t k = 0; k < need; ++k) {
+                if (!(args[k]->flags & FLAG_CONSTANT) || args[k]->data.type.base_type != TYPE_INT || element_count(args[k]->data) != 1) {
+                    MD_LOG_ERROR("mdgpu: property '" STR_FMT "': `in` is lowered for integer arguments only", STR_ARG(ident)); return false;
+                }
+                const int32_t v = *(const int32_t*)args[k]->data.ptr;
+                int32_t* idx = (int32_t*)md_alloc(alloc, sizeof(int32_t) * n_ctx);
+                for (size_t c = 0; c < n_ctx; ++c) idx[c] = (int32_t)ctx_bf[c].beg_bit + v - 1;
+                out->idx[k] = idx; out->idx_count[k] = n_ctx;
+            }
+            return true;
+        }
         if (need && nargs == need) {
             out->op = dist ? MDGPU_OP_DISTANCE : (ang ? MDGPU_OP_ANGLE : MDGPU_OP_DIHEDRAL);
             for (size_t k = 0; k < need; ++k) {

@@ -18,7 +18,7 @@ reference's outputs, so the tests need neither the reference nor the harness on 
   tric6_rmsd.npz : the tric6 frames again: rmt = rmsd(residue(1:10)), rma = rmsd(atom(100:160)), rmo = rmsd(element('O')) — the triclinic wrap
                A * fract(I * r) of md_util_pbc_vec4, the triclinic bond-walk unwrap, non-contiguous selections
   pairs6.npz : multi-valued temporals on the water6 and the tric6 frames, each with its per-frame aggregates: distance_pair() matrices
-               (5 x 11 and 3 x 216 per frame), com() of a residue / 30 atoms / one atom, plane() of 30 atoms / all oxygens; count(within(min:max, sel))
+               (5 x 11 and 3 x 216 per frame), com() of a residue / 30 atoms / one atom, plane() of 30 atoms / all oxygens; count(within(min:max, sel)); angle / distance / dihedral evaluated `in` residue contexts
   xtc_cases.npz : XTC byte streams from the reference's writer + the reference reader's decode of them (see xtc_cases below)
   ala50.npz  : first 50 frames of datasets/1ALA-500.pdb (153 atoms, ortho cell 46.645 x 96.666 x 48.362), config 1:
                d = distance(1,10) (BASELINE config 1), rc = rdf(element('C'), element('O'), 10.0), dz = density_z(element('C')),
@@ -169,7 +169,8 @@ def pairs6(tmp):
     out = {}
     script = ("dp = distance_pair(atom(1:5), atom(20:30)); dpo = distance_pair(residue(1), element('O')); "
               "c = com(residue(1)); ca = com(atom(1:30)); ci = com(5); pl = plane(atom(1:30)); plo = plane(element('O')); "
-              "cwr = count(within(2.5:5.0, residue(1))); cwr2 = count(within(3.0:8.0, atom(10:40)));")
+              "cwr = count(within(2.5:5.0, residue(1))); cwr2 = count(within(3.0:8.0, atom(10:40))); "
+              "anc = angle(2,1,3) in residue(1:10); ddc = distance(1,3) in residue(:); dhc = dihedral(1,2,3,1) in residue(3:4);")
     w = np.load(os.path.join(HERE, "water6.npz")); t = np.load(os.path.join(HERE, "tric6.npz"))
     for tag, g, seed in (("w", w, "77"), ("t", t, "91")):
         gro, raw, o = os.path.join(tmp, tag + "p.gro"), os.path.join(tmp, tag + "p.raw"), os.path.join(tmp, tag + "p.out")

@@ -78,6 +78,10 @@ def test_script_lowering(vb):
             vb.compile_script(src, s)
     rwp = vb.compile_script("rw = rdf(within(4.0, residue(2)), element('O'), 2.0:6.0);", s)[0]
     assert rwp.op == vb.OP_RDF and rwp.ref_within == 4.0 and list(rwp.idx[0]) == [3, 4, 5] and rwp.cutoff_min == 2.0 and rwp.num_structures == 0
+    inc = vb.compile_script("x = dihedral(1,2,3,1) in residue(2:4);", s)[0]
+    assert inc.op == vb.OP_DIHEDRAL and inc.num_structures == 3 and [list(i) for i in inc.idx] == [[3, 6, 9], [4, 7, 10], [5, 8, 11], [3, 6, 9]]
+    with pytest.raises(vb.ScriptError):
+        vb.compile_script("x = distance(residue(1), 2) in residue(2:4);", s)
     cw = vb.compile_script("cw = count(within(4.5, residue(2)));", s)[0]
     assert cw.op == vb.OP_WITHIN_COUNT and cw.cutoff_max == 4.5 and list(cw.idx[0]) == [3, 4, 5]
     with pytest.raises(vb.ScriptError):

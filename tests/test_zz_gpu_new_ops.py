@@ -181,6 +181,25 @@ def test_rdf_candidate_lists_follow_a_cell_whose_neighbour_reach_grows():
         plan.close()
 
 
+def test_expressions_in_contexts():
+    """`expr in contexts` for distance / angle / dihedral with integer arguments (k_temporal_ctx): [F, n_contexts] rows and aggregates against
+    the reference (pairs6.npz), ortho + triclinic; distances equal, angles / dihedrals within the libm tolerance."""
+    p = load_golden("pairs6.npz")
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        g = load_golden(name); s = golden_system(g)
+        plan, cells = _plan(g, s, "anc = angle(2,1,3) in residue(1:10); ddc = distance(1,3) in residue(:); dhc = dihedral(1,2,3,1) in residue(3:4);", batch_frames=3)
+        plan.eval_host_frames(g["frames"], cells, 0)
+        d = plan.property_data("ddc")
+        assert tuple(d.dim[:2]) == tuple(p[f"{tag}_ddc__dim"][:2]) and np.array_equal(d.values, p[f"{tag}_ddc__full"])
+        agg = plan.aggregate("ddc")
+        assert np.array_equal(agg["mean"], p[f"{tag}_ddc__mean"]) and np.array_equal(agg["var"], p[f"{tag}_ddc__var"]) and np.array_equal(agg["ext"], p[f"{tag}_ddc__ext"])
+        mn, mx, r0, r1 = p[f"{tag}_ddc__meta"]
+        assert d.min_value == mn and d.max_value == mx and d.min_range[0] == r0 and d.max_range[0] == r1
+        np.testing.assert_allclose(plan.property_data("anc").values, p[f"{tag}_anc__full"], rtol=1e-5)
+        np.testing.assert_allclose(plan.property_data("dhc").values, p[f"{tag}_dhc__full"], rtol=1e-5, atol=1e-6)
+        plan.close()
+
+
 def test_within_min_max_form():
     """within(min:max, selection) (_within_expl_frng :2609): as the argument of count() against the reference (pairs6.npz, ortho + triclinic) and
     as the reference set of an rdf against the oracle."""

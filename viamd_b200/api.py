@@ -233,6 +233,13 @@ def density(name, axis, idx):
     return Property(name, OP_DENSITY_X + int(axis), [np.asarray(idx, np.int32)])
 
 
+def in_contexts(name, op, local_idx, context_first_atoms):
+    """`name = distance|angle|dihedral(i, j, ...) in <contexts>`: the integer arguments (0-based here) are relative to each context's first atom
+    (remap_index_to_context); one value per context and frame -> [F, n_contexts] (evaluate_context md_script.c:3418)."""
+    beg = np.asarray(context_first_atoms, np.int64)
+    return Property(name, op, [(beg + int(a)).astype(np.int32) for a in local_idx], num_structures=len(beg))
+
+
 def _temporal(name, op, args):
     """each argument: an int (0-based atom index -> that atom's position) or an index array (a selection -> centre of mass,
     coordinate_extract_com md_script_functions.inl:1717)"""

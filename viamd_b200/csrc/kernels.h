@@ -106,7 +106,9 @@ void launch_density(const DensityArgs& a, int B, cudaStream_t s);
 struct TemporalArgs {
     BatchFrames frames; const mdgpu_unitcell_t* cells; int op; int atom[4]; float* out; uint32_t frame0;
     const float* pos; uint32_t com_mask;   // [B][4][3] centres of mass (k_arg_com) for the arguments whose bit is set
+    const int32_t* ctx_idx[4]; uint32_t n_ctx;   // `expr in contexts`: per-context atom of each argument (k_temporal_ctx), out is [num_frames][n_ctx]
 };
+void launch_temporal_ctx(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s);
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_com_rows(const TemporalArgs& a, int B, cudaStream_t s);   // com(x): row (frame0 + f) of a [num_frames][3] temporal = position of argument 0

@@ -325,6 +325,16 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             break;
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
             const int need = pr.op == MDGPU_OP_DISTANCE ? 2 : (pr.op == MDGPU_OP_ANGLE ? 3 : 4);
+            if (pr.n_struct) {   // `expr in contexts` (evaluate_context md_script.c:3418): idx[k][c] = argument k's atom in context c, one value per context
+                if (d.com_args) return bail(MDGPU_ERR_UNSUPPORTED, "'" + pr.name + "': selection arguments inside a context expression are not lowered");
+                for (int k = 0; k < need; ++k) if (pr.h_idx[k].size() != pr.n_struct) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': one atom per context and argument expected");
+                pr.len = pr.n_struct;
+                e = dalloc(&pr.d_temporal, num_frames * pr.len);
+                pr.values.assign(num_frames * pr.len, 0.0f);
+                if (pr.len > 1) { pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f); }
+                pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = (int32_t)pr.len; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+                break;
+            }
             pr.com_mask = d.com_args & ((1u << need) - 1u);
             for (int k = 0; k < need; ++k) {
                 if (pr.h_idx[k].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
@@ -673,6 +683,12 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
             TemporalArgs a{};
             a.frames = fr; a.cells = s.d_cells; a.op = (int)pr.op; a.out = pr.d_temporal; a.frame0 = frame0;
+            if (pr.n_struct) {
+                for (int k = 0; k < 4; ++k) a.ctx_idx[k] = pr.d_idx[k];
+                a.n_ctx = (uint32_t)pr.n_struct;
+                launch_temporal_ctx(a, B, s.stream);
+                break;
+            }
             for (int k = 0; k < 4; ++k) a.atom[k] = pr.h_idx[k].empty() ? 0 : pr.h_idx[k][0];
             a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
             for (int k = 0; k < 4; ++k) if (pr.com_mask & (1u << k))

@@ -257,29 +257,20 @@ void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, cons
 
 // distance / angle / dihedral on the argument positions: an atom's coordinates (single index, coordinate_extract_com :1755) or the
 // centre of mass k_arg_com left in a.pos
-__global__ void k_temporal(TemporalArgs a, int B) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= B) return;
-    const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride; const float* y = x + a.frames.axis_stride; const float* z = y + a.frames.axis_stride;
-    const mdgpu_unitcell_t uc = a.cells[f];
+// distance (:3851-3890) / angle (:4099-4114) / dihedral (:4171-4196) of up to four positions in one cell
+MDG_D float temporal_value(int op, const float P[4][3], const mdgpu_unitcell_t& uc) {
     const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
-    const int nargs = a.op == MDGPU_OP_DISTANCE ? 2 : (a.op == MDGPU_OP_ANGLE ? 3 : 4);
-    float P[4][3];
-    for (int k = 0; k < nargs; ++k) {
-        if (a.com_mask & (1u << k)) { const float* p = a.pos + ((size_t)f * 4 + k) * 3; P[k][0] = p[0]; P[k][1] = p[1]; P[k][2] = p[2]; }
-        else { const int at = a.atom[k]; P[k][0] = x[at]; P[k][1] = y[at]; P[k][2] = z[at]; }
-    }
     float out = 0.0f;
-    if (a.op == MDGPU_OP_DISTANCE) {
+    if (op == MDGPU_OP_DISTANCE) {
         const float* pa = P[0]; float pb[3] = { P[1][0], P[1][1], P[1][2] };
         if (uc.flags & MDGPU_CELL_ORTHO) for (int k = 0; k < 3; ++k) pb[k] = deperiodize1p(pb[k], pa[k], ext[k]);   // md_util_deperiodize_vec4 md_util.c:8971
         const float d[3] = { pa[0] - pb[0], pa[1] - pb[1], pa[2] - pb[2] };
         out = __fsqrt_rn(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    } else if (a.op == MDGPU_OP_ANGLE) {
+    } else if (op == MDGPU_OP_ANGLE) {
         float v0[3] = { P[0][0] - P[1][0], P[0][1] - P[1][1], P[0][2] - P[1][2] }, v1[3] = { P[2][0] - P[1][0], P[2][1] - P[1][1], P[2][2] - P[1][2] };
         normalize3(v0); normalize3(v1);
         out = acosf(v0[0] * v1[0] + v0[1] * v1[1] + v0[2] * v1[2]);
-    } else if (a.op == MDGPU_OP_DIHEDRAL) {
+    } else if (op == MDGPU_OP_DIHEDRAL) {
         float dx[3][3];
         for (int k = 0; k < 3; ++k) for (int i = 0; i < 3; ++i) dx[k][i] = P[k + 1][i] - P[k][i];
         if (uc.flags & MDGPU_CELL_ORTHO) {   // min_image_ortho md_util.c:8424-8436
@@ -303,7 +294,34 @@ __global__ void k_temporal(TemporalArgs a, int B) {
         if (dot < 0.0f) angle = -angle;
         out = angle;
     }
-    a.out[a.frame0 + f] = out;
+    return out;
+}
+
+__global__ void k_temporal(TemporalArgs a, int B) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= B) return;
+    const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride; const float* y = x + a.frames.axis_stride; const float* z = y + a.frames.axis_stride;
+    const mdgpu_unitcell_t uc = a.cells[f];
+    const int nargs = a.op == MDGPU_OP_DISTANCE ? 2 : (a.op == MDGPU_OP_ANGLE ? 3 : 4);
+    float P[4][3];
+    for (int k = 0; k < nargs; ++k) {
+        if (a.com_mask & (1u << k)) { const float* p = a.pos + ((size_t)f * 4 + k) * 3; P[k][0] = p[0]; P[k][1] = p[1]; P[k][2] = p[2]; }
+        else { const int at = a.atom[k]; P[k][0] = x[at]; P[k][1] = y[at]; P[k][2] = z[at]; }
+    }
+    a.out[a.frame0 + f] = temporal_value(a.op, P, uc);
+}
+
+// the same expression evaluated `in` n contexts (evaluate_context md_script.c:3418: the integer arguments are relative to each context's
+// first atom, remap_index_to_context): ctx_idx[k][c] is argument k's atom in context c; row (frame0 + f) holds the n values
+__global__ void k_temporal_ctx(TemporalArgs a, int B) {
+    const int f = blockIdx.y;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_ctx) return;
+    const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride; const float* y = x + a.frames.axis_stride; const float* z = y + a.frames.axis_stride;
+    const int nargs = a.op == MDGPU_OP_DISTANCE ? 2 : (a.op == MDGPU_OP_ANGLE ? 3 : 4);
+    float P[4][3];
+    for (int k = 0; k < nargs; ++k) { const int at = a.ctx_idx[k][c]; P[k][0] = x[at]; P[k][1] = y[at]; P[k][2] = z[at]; }
+    a.out[(size_t)(a.frame0 + f) * a.n_ctx + c] = temporal_value(a.op, P, a.cells[f]);
 }
 
 // com(x) (_com md_script_functions.inl:4726): the position coordinate_extract_com yields for the argument — an atom's coordinates or the
@@ -403,6 +421,12 @@ void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned 
 void launch_com_rows(const TemporalArgs& a, int B, cudaStream_t s) {
     k_com_rows<<<(B + 63) / 64, 64, 0, s>>>(a, B);
     note_launch("k_com_rows", s);
+}
+
+void launch_temporal_ctx(const TemporalArgs& a, int B, cudaStream_t s) {
+    if (!a.n_ctx || B <= 0) return;
+    k_temporal_ctx<<<dim3((a.n_ctx + 63u) / 64u, (unsigned)B), 64, 0, s>>>(a, B);
+    note_launch("k_temporal_ctx", s);
 }
 
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s) {
