@@ -93,13 +93,16 @@ def build_library() -> str:
     import importlib.util
     spec = importlib.util.spec_from_file_location("mdgpu_build", os.path.join(CSRC, "..", "build.py")); b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
     asan = bool(os.environ.get("MDGPU_EMUL_ASAN"))   # AddressSanitizer build: out-of-bounds accesses of "device" buffers become hard errors
-    out = os.path.join(HERE, "build", "libmdgpu_emul_asan.so" if asan else "libmdgpu_emul.so"); bdir = os.path.join(HERE, "build", "asan") if asan else os.path.join(HERE, "build")
+    tsan = bool(os.environ.get("MDGPU_EMUL_TSAN"))   # ThreadSanitizer build: accesses of the threads of a block that no barrier / atomic orders are reported
+    tag = "asan" if asan else ("tsan" if tsan else "")
+    out = os.path.join(HERE, "build", f"libmdgpu_emul_{tag}.so" if tag else "libmdgpu_emul.so"); bdir = os.path.join(HERE, "build", tag) if tag else os.path.join(HERE, "build")
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in ("cuda_emul.h", "fake_cudart.cpp")] + [__file__, os.path.join(CSRC, "..", "..", "include", "mdgpu.h")]
     if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
         return out
     os.makedirs(bdir, exist_ok=True)
     flags = ["-std=c++20", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w", f"-I{CUDA_INC}", f"-I{HERE}", f"-I{CSRC}", "-include", os.path.join(HERE, "cuda_emul.h")]
     if asan: flags += ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"]
+    if tsan: flags += ["-fsanitize=thread", "-fno-omit-frame-pointer", "-g"]
     objs, procs = [], []
     for src in b.SOURCES:
         sname = src[:-3]; text = open(os.path.join(CSRC, src)).read()
@@ -113,10 +116,10 @@ def build_library() -> str:
         obj = os.path.join(bdir, f"{sname}_emullib.o"); objs.append(obj)
         procs.append((src, subprocess.Popen(["g++", *flags, "-c", gen, "-o", obj])))
     fobj = os.path.join(bdir, "fake_cudart.o"); objs.append(fobj)
-    procs.append(("fake_cudart.cpp", subprocess.Popen(["g++", *flags[:6], f"-I{CUDA_INC}", *(["-fsanitize=address", "-g"] if asan else []), "-c", os.path.join(HERE, "fake_cudart.cpp"), "-o", fobj])))
+    procs.append(("fake_cudart.cpp", subprocess.Popen(["g++", *flags[:6], f"-I{CUDA_INC}", *(["-fsanitize=address", "-g"] if asan else []), *(["-fsanitize=thread", "-g"] if tsan else []), "-c", os.path.join(HERE, "fake_cudart.cpp"), "-o", fobj])))
     for src, p in procs:
         if p.wait() != 0: raise RuntimeError(f"g++ failed on {src}")
-    subprocess.check_call(["g++", "-shared", "-o", out, *objs, "-lpthread", "-lm"] + (["-fsanitize=address"] if asan else []))
+    subprocess.check_call(["g++", "-shared", "-o", out, *objs, "-lpthread", "-lm"] + (["-fsanitize=address"] if asan else []) + (["-fsanitize=thread"] if tsan else []))
     return out
 
 
