@@ -905,7 +905,11 @@ static float f_from_bits(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static uint32_t bits_from_f(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
 /* one lane of md_mm256_sincos_ps (core/md_simd.h:1177-1258; the Cody-Waite variant at :1003 is compiled out by #if 0 :920) */
-static void ref_sincosf(float x, float* out_s, float* out_c) {
+static void ref_sincosf_dp3(float x, float dp3, float* out_s, float* out_c);
+static void ref_sincosf(float x, float* out_s, float* out_c) { ref_sincosf_dp3(x, -3.77489470793079817668E-8f, out_s, out_c); }
+/* the 4-lane md_mm_sincos_ps (core/md_simd.h:1093-1176) is the same sequence with a differently rounded third Cody-Waite constant (:1137) */
+static void ref_sincosf4(float x, float* out_s, float* out_c) { ref_sincosf_dp3(x, -3.77489497744594108e-8f, out_s, out_c); }
+static void ref_sincosf_dp3(float x, float dp3, float* out_s, float* out_c) {
     uint32_t sign_bit_sin = bits_from_f(x) & 0x80000000u;
     x = fabsf(x);
     float y = x * 1.27323954473516f;
@@ -920,7 +924,7 @@ static void ref_sincosf(float x, float* out_s, float* out_c) {
     sign_bit_sin ^= swap_sign_bit_sin;
     x = fmaf(y, -0.78515625f, x);
     x = fmaf(y, -2.4187564849853515625E-4f, x);
-    x = fmaf(y, -3.77489470793079817668E-8f, x);
+    x = fmaf(y, dp3, x);
     const float x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
     y = fmaf(x2, fmaf(x2, 2.443315711809948E-5f, -1.388731625493765E-3f), 4.166664568298827E-2f);
     y = fmaf(x2, -0.5f, y * x4);
@@ -1079,6 +1083,92 @@ void mdo_aggregate(const float* data, size_t count, float out[4]) {
     for (size_t i = 0; i < count; ++i) s2 += (data[i] - s1) * (data[i] - s1);
     s2 = s2 / N;
     out[0] = mn; out[1] = mx; out[2] = s1; out[3] = s2;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Shape weights of a structure: the loop body of VIAMD's shape-space component (src/components/shapespace/shapespace.cpp:418-431) and of
+ * _shape_weights (md_script_functions.inl:6033-6040): xyzw (mass or 1) -> md_util_com_compute_vec4 with the cell (com_pbc_vec4
+ * md_util.c:8063-8162: serial float accumulation of w*sin, w*cos per axis, 4-lane sincos, double atan2) -> md_util_deperiodize_vec4 about it
+ * (:8971-9005; the triclinic branch starts at atom 1 and the triclinic centre goes through the 1/2pi-scaled inverse twice — both as written)
+ * -> mat3_covariance_matrix_vec4 about that centre -> md_util_shape_weights (:9070-9076): eigenvalues e0 >= e1 >= e2 (normalised by the
+ * largest) -> ((e0 - e1), 2 (e1 - e2), 3 e2) / (e0 + e1 + e2).
+ */
+static float m3_eigen_values(m3 M, float ev_sorted[3]) {
+    svd_t s = m3_svd(M);
+    const float mx = MAXV(s.s[0], MAXV(s.s[1], s.s[2]));
+    const float ev[3] = { s.s[0] / mx, s.s[1] / mx, s.s[2] / mx };
+    int l[3] = { 0, 1, 2 }, t;
+    if (ev[l[0]] < ev[l[1]]) { t = l[0]; l[0] = l[1]; l[1] = t; }
+    if (ev[l[1]] < ev[l[2]]) { t = l[1]; l[1] = l[2]; l[2] = t; }
+    if (ev[l[0]] < ev[l[1]]) { t = l[0]; l[0] = l[1]; l[1] = t; }
+    ev_sorted[0] = ev[l[0]]; ev_sorted[1] = ev[l[1]]; ev_sorted[2] = ev[l[2]];
+    return mx;
+}
+void mdo_shape_weights(const float* x, const float* y, const float* z, const float* mass, const int32_t* idx, size_t n, const mdo_unitcell_t* cell, float out[3]) {
+    out[0] = out[1] = out[2] = 0.0f;
+    if (n == 0) return;
+    v4* p = malloc(sizeof(v4) * n);
+    for (size_t k = 0; k < n; ++k) { const int32_t a = idx[k]; p[k][0] = x[a]; p[k][1] = y[a]; p[k][2] = z[a]; p[k][3] = mass ? mass[a] : 1.0f; }
+    float com[3];
+    const double TWO_PI_D = 2.0 * 3.1415926535897932, PI_D = 3.1415926535897932;
+    if (cell->flags & MDO_CELL_ORTHO) {
+        const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
+        const float tp = (float)TWO_PI_D;
+        const float scl[4] = { tp / ext[0], tp / ext[1], tp / ext[2], tp / tp };
+        float as[4] = { 0 }, ac[4] = { 0 }, ax[4] = { 0 };
+        for (size_t k = 0; k < n; ++k) {
+            const float www1[4] = { p[k][3], p[k][3], p[k][3], 1.0f };
+            for (int a = 0; a < 4; ++a) {
+                float sn, cs; ref_sincosf4(p[k][a] * scl[a], &sn, &cs);
+                as[a] = as[a] + sn * www1[a]; ac[a] = ac[a] + cs * www1[a]; ax[a] = ax[a] + p[k][a] * www1[a];
+            }
+        }
+        const float w = ax[3];
+        for (int a = 0; a < 3; ++a) {
+            const double yy = as[a] / w, xx = ac[a] / w, r2 = xx * xx + yy * yy;
+            double theta = PI_D; if (r2 > 1.0e-15) theta += atan2(-yy, -xx);
+            com[a] = (float)((theta / TWO_PI_D) * ext[a]);
+        }
+        for (size_t k = 0; k < n; ++k) for (int a = 0; a < 3; ++a) p[k][a] = deperiodize1(p[k][a], com[a], ext[a]);
+    } else if (cell->flags & MDO_CELL_TRICLINIC) {
+        double Ad[3][3], Id[3][3]; cell_A(Ad, cell); cell_I(Id, cell);
+        float A[3][3], I[3][3];   /* I = mat3_mul(mat3_scale(1/2pi), Ai): C[col][row] = S[row][row] * Ai[col][row] (core/md_vec_math.h:1631) */
+        const float inv_tp = 1.0f / (float)TWO_PI_D;
+        for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) A[c][r] = (float)Ad[c][r];
+        for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) {   /* exact form of MULT(col,row): A.e[0][row]*B.e[col][0] + A.e[1][row]*B.e[col][1] + A.e[2][row]*B.e[col][2] with A = scale */
+            const float S[3][3] = { { inv_tp, 0, 0 }, { 0, inv_tp, 0 }, { 0, 0, inv_tp } };
+            const float Ai[3] = { (float)Id[c][0], (float)Id[c][1], (float)Id[c][2] };
+            I[c][r] = S[0][r] * Ai[0] + S[1][r] * Ai[1] + S[2][r] * Ai[2];
+        }
+        float as[4] = { 0 }, ac[4] = { 0 }, ax[4] = { 0 };
+        for (size_t k = 0; k < n; ++k) {
+            const float www1[4] = { p[k][3], p[k][3], p[k][3], 1.0f };
+            float th[4];   /* mat4x3_mul_vec4(I, xyzw) (in_idx == NULL branch :8138): linear_combine_3, w lane = 0 */
+            for (int a = 0; a < 3; ++a) th[a] = (p[k][0] * I[0][a] + p[k][1] * I[1][a]) + p[k][2] * I[2][a];
+            th[3] = (p[k][0] * 0.0f + p[k][1] * 0.0f) + p[k][2] * 0.0f;
+            for (int a = 0; a < 4; ++a) {
+                float sn, cs; ref_sincosf4(th[a], &sn, &cs);
+                as[a] = as[a] + sn * www1[a]; ac[a] = ac[a] + cs * www1[a]; ax[a] = ax[a] + p[k][a] * www1[a];
+            }
+        }
+        for (int a = 0; a < 3; ++a) {
+            const double yy = as[a] / ax[3], xx = ac[a] / ax[3], r2 = xx * xx + yy * yy;
+            double theta = PI_D; if (r2 > 1.0e-8) theta += atan2(-yy, -xx);
+            com[a] = (float)(theta * I[a][0] + theta * I[a][1] + theta * I[a][2]);   /* :8158, I.elem[i][0..2] */
+        }
+        const float box[3][3] = { { A[0][0], 0, 0 }, { A[1][0], A[1][1], 0 }, { A[2][0], A[2][1], A[2][2] } };
+        for (size_t k = 1; k < n; ++k) {   /* deperiodize_triclinic from atom 1 on (:8993) */
+            float d[3] = { p[k][0] - com[0], p[k][1] - com[1], p[k][2] - com[2] };
+            min_image_triclinic(d, box);
+            p[k][0] = com[0] + d[0]; p[k][1] = com[1] + d[1]; p[k][2] = com[2] + d[2];
+        }
+    } else {
+        com_v4(com, p, n);   /* no cell: com_vec4; md_util_deperiodize_vec4 does nothing */
+    }
+    float ev[3]; m3_eigen_values(covariance_v4(p, n, com), ev);
+    const float scl = 1.0f / (ev[0] + ev[1] + ev[2]);
+    out[0] = (ev[0] - ev[1]) * scl; out[1] = 2.0f * (ev[1] - ev[2]) * scl; out[2] = 3.0f * ev[2] * scl;
+    free(p);
 }
 
 /* _angle :4099-4114 */

@@ -208,6 +208,42 @@ static int mode_dumptraj(int argc, char** argv) {
     return 0;
 }
 
+/* shapespace: the per-frame loop body of VIAMD's shape-space component (src/components/shapespace/shapespace.cpp:404-431) and of
+ * _shape_weights (md_script_functions.inl:6005-6050), written against the reference's own functions: for every frame and every structure
+ * (here: components [R0,R1) of the system, i.e. residues) xyzw -> md_util_com_compute_vec4 (periodic) -> md_util_deperiodize_vec4 ->
+ * mat3_covariance_matrix_vec4 -> md_util_shape_weights. Output: MDSHAPES, frames, structures, then weights[frame][structure][3]. */
+static int mode_shapespace(int argc, char** argv) {
+    md_allocator_i* alloc = md_vm_arena_create(GIGABYTES(8));
+    md_system_t sys; if (!load_system(&sys, arg_val(argc, argv, "--sys", ""), alloc)) return 2;
+    md_trajectory_i traj = {0}; mem_traj_t mt;
+    if (!make_traj(&traj, &mt, arg_val(argc, argv, "--traj", "sys"), &sys)) return 2;
+    long b = 0, e = (long)md_trajectory_num_frames(&traj); parse_range(arg_val(argc, argv, "--frames", NULL), &b, &e);
+    long r0 = 0, r1 = (long)sys.component.count; parse_range(arg_val(argc, argv, "--res", NULL), &r0, &r1);
+    const bool use_mass = atoi(arg_val(argc, argv, "--mass", "1")) != 0;
+    const size_t n = sys.atom.count;
+    float* xyz = malloc(n * 12); float* x = xyz; float* y = xyz + n; float* z = xyz + 2 * n;
+    float* w = malloc(n * 4); md_atom_extract_masses(w, 0, n, &sys.atom);
+    vec4_t* xyzw = malloc(n * sizeof(vec4_t));
+    FILE* f = fopen(arg_val(argc, argv, "--out", "shapes.bin"), "wb"); if (!f) return 2;
+    wr(f, "MDSHAPES", 8); wr_u64(f, (uint64_t)(e - b)); wr_u64(f, (uint64_t)(r1 - r0));
+    md_trajectory_reader_i rd = {0}; md_trajectory_reader_init(&rd, &traj);
+    for (long fr = b; fr < e; ++fr) {
+        md_trajectory_frame_header_t h = {0};
+        if (!md_trajectory_reader_load_frame(rd, fr, &h, x, y, z)) return 2;
+        for (long r = r0; r < r1; ++r) {
+            const size_t a0 = sys.component.atom_offset[r], a1 = sys.component.atom_offset[r + 1], count = a1 - a0;
+            for (size_t k = 0; k < count; ++k) xyzw[k] = vec4_set(x[a0 + k], y[a0 + k], z[a0 + k], use_mass ? w[a0 + k] : 1.0f);
+            const vec3_t com = md_util_com_compute_vec4(xyzw, 0, count, &h.unitcell);
+            md_util_deperiodize_vec4(xyzw, count, com, &h.unitcell);
+            const mat3_t M = mat3_covariance_matrix_vec4(xyzw, 0, count, com);
+            const vec3_t weights = md_util_shape_weights(&M);
+            wr(f, &weights, 12);
+        }
+    }
+    md_trajectory_reader_free(&rd); fclose(f);
+    return 0;
+}
+
 /* xtcwrite: frames [B,E) of any trajectory spec -> an .xtc file through the reference's bundled xdrfile writer (ext/xtc/xdrfile_xtc.c:
  * write_xtc), coordinates Angstrom -> nm. Fixture generation for the XTC decode path. */
 static int mode_xtcwrite(int argc, char** argv) {
@@ -237,6 +273,7 @@ int main(int argc, char** argv) {
     if (argc >= 2 && strcmp(argv[1], "xtcwrite") == 0) return mode_xtcwrite(argc, argv);
     if (argc < 2) { fprintf(stderr, "usage: ref_harness sysinfo|eval|time|dumptraj ...\n"); return 1; }
     if (strcmp(argv[1], "dumptraj") == 0) return mode_dumptraj(argc, argv);
+    if (strcmp(argv[1], "shapespace") == 0) return mode_shapespace(argc, argv);
     if (strcmp(argv[1], "sysinfo") == 0) return mode_sysinfo(argc, argv);
     if (strcmp(argv[1], "eval") == 0) return mode_eval(argc, argv, false);
     if (strcmp(argv[1], "time") == 0) return mode_eval(argc, argv, true);

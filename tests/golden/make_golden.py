@@ -19,6 +19,8 @@ reference's outputs, so the tests need neither the reference nor the harness on 
                A * fract(I * r) of md_util_pbc_vec4, the triclinic bond-walk unwrap, non-contiguous selections
   pairs6.npz : multi-valued temporals on the water6 and the tric6 frames, each with its per-frame aggregates: distance_pair() matrices
                (5 x 11 and 3 x 216 per frame), com() of a residue / 30 atoms / one atom, plane() of 30 atoms / all oxygens; count(within(min:max, sel)); angle / distance / dihedral evaluated `in` residue contexts
+  shapes.npz : shape weights (linear, planar, isotropic) per structure and frame through the reference's md_util functions, as VIAMD's shape-space
+               component calls them: 1ALA residues (mass-weighted), water6 residues (unit weights), tric6 residues
   xtc_cases.npz : XTC byte streams from the reference's writer + the reference reader's decode of them (see xtc_cases below)
   ala50.npz  : first 50 frames of datasets/1ALA-500.pdb (153 atoms, ortho cell 46.645 x 96.666 x 48.362), config 1:
                d = distance(1,10) (BASELINE config 1), rc = rdf(element('C'), element('O'), 10.0), dz = density_z(element('C')),
@@ -186,6 +188,23 @@ def pairs6(tmp):
     np.savez_compressed(os.path.join(HERE, "pairs6.npz"), **out)
 
 
+def shapes(tmp):
+    """Shape weights per structure and frame from the reference's own functions (harness mode `shapespace`: the loop body of VIAMD's shape-space
+    component): 1ALA residues (15 structures of 9-12 atoms, orthorhombic, mass-weighted), water6 residues with unit weights, tric6 residues."""
+    out = {}
+    a = np.load(os.path.join(HERE, "ala50.npz")); w = np.load(os.path.join(HERE, "water6.npz")); t = np.load(os.path.join(HERE, "tric6.npz"))
+    for tag, g, sysarg, res, mass in (("a", a, "/root/reference/datasets/1ALA-500.pdb", "0:15", "1"), ("w", w, None, "0:40", "0"), ("t", t, None, "0:40", "1")):
+        raw, o = os.path.join(tmp, tag + "s.raw"), os.path.join(tmp, tag + "s.bin")
+        if sysarg is None:
+            sysarg = os.path.join(tmp, tag + "s.gro"); run(SYNTH, "water-gro", "6", "77" if tag == "w" else "91", sysarg)
+        refio.write_raw_traj(raw, g["frames"], g["cells"], g["cell_flags"])
+        run(HARNESS, "shapespace", "--sys", sysarg, "--traj", f"raw:{raw}", "--res", res, "--mass", mass, "--out", o)
+        b = open(o, "rb").read(); assert b[:8] == b"MDSHAPES"
+        F, n = np.frombuffer(b, np.uint64, 2, 8)
+        out[tag + "__weights"] = np.frombuffer(b, np.float32, -1, 24).reshape(int(F), int(n), 3).copy(); out[tag + "__res"] = np.array(res); out[tag + "__mass"] = np.int32(int(mass))
+    np.savez_compressed(os.path.join(HERE, "shapes.npz"), **out)
+
+
 def _write_gro(path, n, L):
     with open(path, "w") as f:
         f.write("synthetic\n%d\n" % n)
@@ -235,6 +254,6 @@ def xtc_cases(tmp):
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     with tempfile.TemporaryDirectory() as tmp:
-        water6(tmp); ala50(tmp); membrane6(tmp); tric6(tmp); tric6_rmsd(tmp); pairs6(tmp); xtc_cases(tmp)
-    for f in ("water6.npz", "ala50.npz", "membrane6.npz", "tric6.npz", "tric6_rmsd.npz", "pairs6.npz", "xtc_cases.npz"):
+        water6(tmp); ala50(tmp); membrane6(tmp); tric6(tmp); tric6_rmsd(tmp); pairs6(tmp); shapes(tmp); xtc_cases(tmp)
+    for f in ("water6.npz", "ala50.npz", "membrane6.npz", "tric6.npz", "tric6_rmsd.npz", "pairs6.npz", "shapes.npz", "xtc_cases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -183,6 +183,13 @@ def min_distance(x, y, z, a, b, cell):
     return np.float32(lib().mdo_min_distance(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(a, C.c_int32), C.c_size_t(len(a)), _p(b, C.c_int32), C.c_size_t(len(b)), C.byref(cell)))
 
 
+def shape_weights(x, y, z, mass, idx, cell):
+    x, y, z = _f32(x), _f32(y), _f32(z); idx = _i32(idx); out = np.zeros(3, np.float32)
+    m = None if mass is None else _f32(mass)
+    lib().mdo_shape_weights(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), None if m is None else _p(m, C.c_float), _p(idx, C.c_int32), C.c_size_t(len(idx)), C.byref(cell), _p(out, C.c_float))
+    return out
+
+
 def plane_frame(x, y, z, idx, conn_off, conn_idx, cell):
     x, y, z = _f32(x), _f32(y), _f32(z); idx = _i32(idx); co = np.ascontiguousarray(conn_off, np.uint32); ci = _i32(conn_idx); out = np.zeros(4, np.float32)
     lib().mdo_plane_frame(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(idx, C.c_int32), C.c_size_t(len(idx)), _p(co, C.c_uint32), _p(ci, C.c_int32),
