@@ -104,6 +104,8 @@ typedef enum mdgpu_op {
     MDGPU_OP_COM = 13,       /* com(x): position of an atom / centre of mass of a selection -> temporal [F, 3]        :4726-4753 */
     MDGPU_OP_PLANE = 14,     /* plane(selection): (unit normal, normal . centre) of the best-fit plane -> temporal [F, 4] :4755-4822 */
     MDGPU_OP_WITHIN_COUNT = 15, /* count(within(radius, selection)): atoms of the system within radius of the selection -> temporal :2485-2533, :2868 */
+    MDGPU_OP_SHAPE_WEIGHTS = 16, /* (linear, planar, isotropic) weights of n structures per frame -> temporal [F, n*3]: VIAMD's shape-space loop
+                                  * (src/components/shapespace/shapespace.cpp:404-431) and _shape_weights (md_script_functions.inl:6005-6050) */
     MDGPU_OP_RMSD = 11,      /* rmsd(selection) against the initial frame -> temporal                     :4287-4345 */
 } mdgpu_op;
 
@@ -127,6 +129,8 @@ typedef enum mdgpu_op {
  *   COM      : idx[0] as argument 0 of DISTANCE (bit 0 of com_args = it was a selection).   PLANE: idx[0] = the atoms (at least 3).
  *   WITHIN_COUNT: idx[0] = the selection's atoms, cutoff_max = radius (> 0), cutoff_min = lower bound of the min:max form (else 0). The dynamic selection within() is evaluated per frame over the
  *              system-wide cell list (get_spatial_acc :734); so far its only consumer on the device is count().
+ *   SHAPE_WEIGHTS: idx[0] = the atoms of num_structures structures back to back (structure_offsets, or structure_size each), bit 0 of com_args
+ *              = weights are the atom masses (shapespace's use_mass; _shape_weights always uses them), else 1.
  *   RMSD     : idx[0] = the atoms of the (flattened) selection; needs the initial frame and, to make molecules whole, the bond connectivity.
  *   DISTANCE/ANGLE/DIHEDRAL: idx[k] = the atoms of argument k (0-based). A single integer index is that atom's position; an
  *              argument that was a selection (bit k of com_args set, or more than one index) is its centre of mass as

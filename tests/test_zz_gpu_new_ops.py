@@ -200,6 +200,26 @@ def test_expressions_in_contexts():
         plan.close()
 
 
+def test_shape_weights_of_structures():
+    """Shape weights per structure and frame (k_shape_weights) against the reference's functions (shapes.npz): 1ALA residues mass-weighted
+    through the frame-source interface, water with unit weights, the triclinic cell. The double atan2 of the periodic centre is libm on the
+    reference side and CUDA's on the device: 1e-5 relative (equal under the CPU emulation)."""
+    import viamd_b200 as vb
+    W = load_golden("shapes.npz")
+    for tag, name in (("a", "ala50.npz"), ("w", "water6.npz"), ("t", "tric6.npz")):
+        g = load_golden(name); s = golden_system(g); co = s["comp_off"]; w = W[tag + "__weights"]; F, n = w.shape[:2]
+        groups = [np.arange(co[r], co[r + 1], dtype=np.int32) for r in range(n)]
+        plan = vb.Plan(vb_system(s), [vb.shape_weights("sw", groups, use_mass=bool(int(W[tag + "__mass"])))], F, batch_frames=7)
+        cells = [vb_cell(g["cells"][f], g["cell_flags"][f]) for f in range(F)]
+        assert plan.eval_frame_range(vb.ArrayTrajectory(g["frames"], cells), 0, F)
+        d = plan.property_data("sw")
+        assert tuple(d.dim[:2]) == (F, 3 * n)
+        np.testing.assert_allclose(d.values.reshape(F, n, 3), w, rtol=1e-5, atol=1e-7)
+        plan.close()
+    with pytest.raises(vb.MdgpuError):
+        vb.Plan(vb.water_system(4), [vb.Property("x", vb.OP_SHAPE_WEIGHTS, [np.zeros(0, np.int32)])], 2)
+
+
 def test_within_min_max_form():
     """within(min:max, selection) (_within_expl_frng :2609): as the argument of count() against the reference (pairs6.npz, ortho + triclinic) and
     as the reference set of an rdf against the oracle."""

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libmdgpu.so")
 DIST_BINS = 1024
 VOL_DIM = 128
 
-OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE, OP_WITHIN_COUNT = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15
+OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE, OP_WITHIN_COUNT, OP_SHAPE_WEIGHTS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16
 CELL_ORTHO, CELL_TRICLINIC, CELL_PBC_X, CELL_PBC_Y, CELL_PBC_Z, CELL_PBC_ALL = 1, 2, 4, 8, 16, 28
 
 
@@ -283,6 +283,14 @@ def count_within(name, radius, sel_idx, radius_min=0.0):
     """count(within(radius, selection)): per frame, the number of atoms of the system within `radius` of any atom of the selection, the
     selection itself excluded (_within_expl_flt md_script_functions.inl:2485, _count :2868) — a dynamic selection evaluated on the device"""
     return Property(name, OP_WITHIN_COUNT, [np.asarray(sel_idx, np.int32)], cutoff_min=float(radius_min), cutoff_max=float(radius))   # min:max form: _within_expl_frng :2609
+
+
+def shape_weights(name, groups, use_mass=True):
+    """(linear, planar, isotropic) shape weights of every structure and frame -> [F, n*3]: what VIAMD's shape-space component evaluates per frame
+    (shapespace.cpp:404-431; `use_mass` is its checkbox) and what _shape_weights returns (md_script_functions.inl:6005)."""
+    groups = [np.asarray(g, np.int32) for g in groups]
+    off = np.zeros(len(groups) + 1, np.uint32); off[1:] = np.cumsum([len(g) for g in groups])
+    return Property(name, OP_SHAPE_WEIGHTS, [np.concatenate(groups).astype(np.int32)], num_structures=len(groups), structure_offsets=off, com_args=1 if use_mass else 0)
 
 
 def rmsd(name, idx):

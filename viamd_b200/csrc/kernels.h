@@ -60,6 +60,17 @@ struct SdfArgs {
 };
 void launch_sdf(const SdfArgs& a, int B, bool tri, cudaStream_t s);
 
+struct ShapeArgs {                   // shape weights of n_struct structures per frame (VIAMD shape space / _shape_weights)
+    BatchFrames frames;
+    const mdgpu_unitcell_t* cells;   // [B]
+    const float* mass; int use_mass; // weights: atom masses or 1
+    const int32_t* idx; const uint32_t* soff; uint32_t n_struct, n_atoms_total;   // CSR: structure s = idx[soff[s] .. soff[s+1])
+    float4* scratch_xyzw;            // [B][n_atoms_total]
+    float* out;                      // [num_frames][n_struct][3]
+    uint32_t frame0;
+};
+void launch_shape_weights(const ShapeArgs& a, int B, cudaStream_t s);
+
 struct RmsdArgs {                    // rmsd(selection) against the initial frame, one value per frame
     BatchFrames frames;
     const mdgpu_unitcell_t* cells;   // [B]

@@ -360,6 +360,21 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.values.assign(num_frames, 0.0f);
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
             break;
+        case MDGPU_OP_SHAPE_WEIGHTS: {   // shape weights of n structures: [F, n*3]; groups as for rdf's centre-of-mass references
+            if (!pr.n_struct || pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': No structures present");   // shapespace.cpp:371
+            if (d.structure_offsets) pr.h_soff.assign(d.structure_offsets, d.structure_offsets + pr.n_struct + 1);
+            else { if (!pr.struct_size) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': structure_size or structure_offsets required");
+                   pr.h_soff.resize(pr.n_struct + 1); for (size_t k = 0; k <= pr.n_struct; ++k) pr.h_soff[k] = (uint32_t)(k * pr.struct_size); }
+            if (pr.h_soff.front() != 0 || pr.h_soff.back() != pr.h_idx[0].size()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': structure offsets do not cover idx[0]");
+            for (size_t k = 0; k < pr.n_struct; ++k) if (pr.h_soff[k] > pr.h_soff[k + 1]) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': structure offsets must be non-decreasing");
+            if (upload(&pr.d_soff, pr.h_soff.data(), pr.h_soff.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (structure offsets)");
+            pr.com_mask = d.com_args & 1u;   // bit 0: weights are the atom masses (else 1)
+            pr.len = 3 * pr.n_struct;
+            e = dalloc(&pr.d_temporal, num_frames * pr.len);
+            pr.values.assign(num_frames * pr.len, 0.0f);
+            pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f);
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = (int32_t)pr.len; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break; }
         case MDGPU_OP_COM: {   // com(x): a [F, 3] temporal (TI_FLOAT3)
             if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
             pr.com_mask = (d.com_args & 1u) | (pr.h_idx[0].size() != 1 ? 1u : 0u);
@@ -530,7 +545,7 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     CUDA_TRY(dalloc(&ps.d_flags, (size_t)p->B * p->num_atoms));
                 } else if (pr.op == MDGPU_OP_RMSD) {
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * 2 * pr.h_idx[0].size()));   // [B][initial, current][atoms]
-                } else if (pr.op == MDGPU_OP_PLANE) {
+                } else if (pr.op == MDGPU_OP_PLANE || pr.op == MDGPU_OP_SHAPE_WEIGHTS) {
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * pr.h_idx[0].size()));
                 } else if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
                     CUDA_TRY(dalloc(&ps.d_frame_bins64, (size_t)p->B * MDGPU_DIST_BINS));
@@ -659,6 +674,13 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.atom[0] = pr.h_idx[0][0]; a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
             if (pr.com_mask & 1u) launch_arg_com(fr, s.d_cells, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), p->d_mass, ps.d_argpos, 0, s.stream);
             launch_com_rows(a, B, s.stream);
+            break; }
+        case MDGPU_OP_SHAPE_WEIGHTS: {
+            ShapeArgs a{};
+            a.frames = fr; a.cells = s.d_cells; a.mass = p->d_mass; a.use_mass = (int)(pr.com_mask & 1u);
+            a.idx = pr.d_idx[0]; a.soff = pr.d_soff; a.n_struct = (uint32_t)pr.n_struct; a.n_atoms_total = (uint32_t)pr.h_idx[0].size();
+            a.scratch_xyzw = ps.d_sdf_xyzw; a.out = pr.d_temporal; a.frame0 = frame0;
+            launch_shape_weights(a, B, s.stream);
             break; }
         case MDGPU_OP_PLANE: {
             RmsdArgs a{};

@@ -651,6 +651,142 @@ __global__ void __launch_bounds__(32) k_plane(RmsdArgs a, int B) {
     o[0] = nx; o[1] = ny; o[2] = nz; o[3] = (nx * com[0] + ny * com[1]) + nz * com[2];
 }
 
+// ------------------------------------------------------------------------------------------------- shape weights of structures
+// The loop body of VIAMD's shape-space component (src/components/shapespace/shapespace.cpp:418-431) and of _shape_weights
+// (md_script_functions.inl:6033-6040): xyzw (mass or 1) -> md_util_com_compute_vec4 with the cell (com_pbc_vec4 md_util.c:8063-8162) ->
+// md_util_deperiodize_vec4 about that centre (:8971-9005) -> mat3_covariance_matrix_vec4 -> md_util_shape_weights (:9070-9076).
+// One lane of the 4-lane md_mm_sincos_ps (core/md_simd.h:1093-1176): the Cephes sequence of props.cu's ref_sincosf with the third
+// Cody-Waite constant as that variant spells it (:1137).
+MDG_D void sincos_cephes4(float x, float& out_s, float& out_c) {
+    uint32_t sign_bit_sin = __float_as_uint(x) & 0x80000000u;
+    x = fabsf(x);
+    float y = __fmul_rn(x, 1.27323954473516f);
+    int imm2 = __float2int_rz(y);
+    imm2 = (imm2 + 1) & ~1;
+    y = (float)imm2;
+    const uint32_t swap_sign_bit_sin = ((uint32_t)(imm2 & 4)) << 29;
+    const bool poly_mask = (imm2 & 2) == 0;
+    const uint32_t sign_bit_cos = ((uint32_t)(~(imm2 - 2) & 4)) << 29;
+    sign_bit_sin ^= swap_sign_bit_sin;
+    x = __fmaf_rn(y, -0.78515625f, x);
+    x = __fmaf_rn(y, -2.4187564849853515625e-4f, x);
+    x = __fmaf_rn(y, -3.77489497744594108e-8f, x);
+    const float x2 = __fmul_rn(x, x), x3 = __fmul_rn(x2, x), x4 = __fmul_rn(x2, x2);
+    y = __fmaf_rn(x2, __fmaf_rn(x2, 2.443315711809948E-005f, -1.388731625493765E-003f), 4.166664568298827E-002f);
+    y = __fmaf_rn(x2, -0.5f, __fmul_rn(y, x4));
+    y = __fadd_rn(y, 1.0f);
+    float y2 = __fmaf_rn(x2, __fmaf_rn(x2, -1.9515295891E-4f, 8.3321608736E-3f), -1.6666654611E-1f);
+    y2 = __fmaf_rn(y2, x3, x);
+    const float ysin2 = poly_mask ? y2 : 0.0f, ysin1 = poly_mask ? 0.0f : y;
+    y2 = __fsub_rn(y2, ysin2); y = __fsub_rn(y, ysin1);
+    out_s = __uint_as_float(__float_as_uint(__fadd_rn(ysin1, ysin2)) ^ sign_bit_sin);
+    out_c = __uint_as_float(__float_as_uint(__fadd_rn(y, y2)) ^ sign_bit_cos);
+}
+
+// One warp per (structure, frame): the lanes extract, lane 0 does the ordered work (float sums over the atoms in index order, double
+// covariance). Row (frame0 + f) of the property holds n_struct x (linear, planar, isotropic).
+__global__ void __launch_bounds__(32) k_shape_weights(ShapeArgs a, int B) {
+    const int f = blockIdx.y, lane = threadIdx.x;
+    const uint32_t sidx = blockIdx.x;
+    if (f >= B || sidx >= a.n_struct) return;
+    const uint32_t beg = a.soff[sidx], n = a.soff[sidx + 1] - beg;
+    float* o = a.out + ((size_t)(a.frame0 + f) * a.n_struct + sidx) * 3;
+    if (n == 0) { if (lane == 0) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; } return; }   // count == 0: the entry keeps its zero (:6029)
+    const mdgpu_unitcell_t uc = a.cells[f];
+    const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride;
+    float4* p = a.scratch_xyzw + (size_t)f * a.n_atoms_total + beg;
+    for (uint32_t k = lane; k < n; k += 32) { const int at = a.idx[beg + k]; p[k] = make_float4(x[at], x[a.frames.axis_stride + at], x[2 * a.frames.axis_stride + at], a.use_mass ? a.mass[at] : 1.0f); }
+    __syncwarp();
+    if (lane != 0) return;
+    const double TWO_PI_D = 2.0 * 3.1415926535897932, PI_D = 3.1415926535897932;
+    float com[3];
+    if (uc.flags & MDGPU_CELL_ORTHO) {
+        const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
+        const float tp = (float)TWO_PI_D;
+        const float scl[4] = { tp / ext[0], tp / ext[1], tp / ext[2], tp / tp };
+        float as[4] = { 0.f, 0.f, 0.f, 0.f }, ac[4] = { 0.f, 0.f, 0.f, 0.f }, ax[4] = { 0.f, 0.f, 0.f, 0.f };
+        for (uint32_t k = 0; k < n; ++k) {
+            const float4 v = p[k]; const float e[4] = { v.x, v.y, v.z, v.w }, www1[4] = { v.w, v.w, v.w, 1.0f };
+            for (int c = 0; c < 4; ++c) {
+                float sn, cs; sincos_cephes4(e[c] * scl[c], sn, cs);
+                as[c] = as[c] + sn * www1[c]; ac[c] = ac[c] + cs * www1[c]; ax[c] = ax[c] + e[c] * www1[c];
+            }
+        }
+        const float w = ax[3];
+        for (int c = 0; c < 3; ++c) {
+            const double yy = (double)(as[c] / w), xx = (double)(ac[c] / w), r2 = xx * xx + yy * yy;
+            double theta = PI_D; if (r2 > 1.0e-15) theta += atan2(-yy, -xx);
+            com[c] = (float)((theta / TWO_PI_D) * (double)ext[c]);
+        }
+        for (uint32_t k = 0; k < n; ++k) { float4 v = p[k]; v.x = deperiodize1(v.x, com[0], ext[0]); v.y = deperiodize1(v.y, com[1], ext[1]); v.z = deperiodize1(v.z, com[2], ext[2]); p[k] = v; }
+    } else if (uc.flags & MDGPU_CELL_TRICLINIC) {
+        const double i11 = uc.x > 0.0 ? 1.0 / uc.x : 0.0, i22 = uc.y > 0.0 ? 1.0 / uc.y : 0.0, i33 = uc.z > 0.0 ? 1.0 / uc.z : 0.0;   // md_unitcell.inl:158-176
+        const double i12 = (uc.x * uc.y) > 0.0 ? -uc.xy / (uc.x * uc.y) : 0.0;
+        const double i13 = (uc.x * uc.y * uc.z) > 0.0 ? (uc.xy * uc.yz - uc.xz * uc.y) / (uc.x * uc.y * uc.z) : 0.0;
+        const double i23 = (uc.y * uc.z) > 0.0 ? -uc.yz / (uc.y * uc.z) : 0.0;
+        const float Ai[3][3] = { { (float)i11, 0.f, 0.f }, { (float)i12, (float)i22, 0.f }, { (float)i13, (float)i23, (float)i33 } };   // [col][row]
+        const float inv_tp = 1.0f / (float)TWO_PI_D;
+        float I[3][3];   // mat3_mul(mat3_scale(1/2pi), Ai) (core/md_vec_math.h:1631): the three products of MULT(col,row), two of them with a zero factor
+        for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) {
+            const float s0 = (r == 0) ? inv_tp : 0.0f, s1 = (r == 1) ? inv_tp : 0.0f, s2 = (r == 2) ? inv_tp : 0.0f;
+            I[c][r] = (s0 * Ai[c][0] + s1 * Ai[c][1]) + s2 * Ai[c][2];
+        }
+        float as[4] = { 0.f, 0.f, 0.f, 0.f }, ac[4] = { 0.f, 0.f, 0.f, 0.f }, ax[4] = { 0.f, 0.f, 0.f, 0.f };
+        for (uint32_t k = 0; k < n; ++k) {
+            const float4 v = p[k]; const float e[4] = { v.x, v.y, v.z, v.w }, www1[4] = { v.w, v.w, v.w, 1.0f };
+            float th[4];   // mat4x3_mul_vec4(I, xyzw), the in_idx == NULL branch (:8138)
+            for (int c = 0; c < 3; ++c) th[c] = (v.x * I[0][c] + v.y * I[1][c]) + v.z * I[2][c];
+            th[3] = (v.x * 0.0f + v.y * 0.0f) + v.z * 0.0f;
+            for (int c = 0; c < 4; ++c) {
+                float sn, cs; sincos_cephes4(th[c], sn, cs);
+                as[c] = as[c] + sn * www1[c]; ac[c] = ac[c] + cs * www1[c]; ax[c] = ax[c] + e[c] * www1[c];
+            }
+        }
+        for (int c = 0; c < 3; ++c) {
+            const double yy = (double)(as[c] / ax[3]), xx = (double)(ac[c] / ax[3]), r2 = xx * xx + yy * yy;
+            double theta = PI_D; if (r2 > 1.0e-8) theta += atan2(-yy, -xx);
+            com[c] = (float)(theta * (double)I[c][0] + theta * (double)I[c][1] + theta * (double)I[c][2]);   // :8158, as written
+        }
+        const float box[3][3] = { { (float)uc.x, 0.f, 0.f }, { (float)uc.xy, (float)uc.y, 0.f }, { (float)uc.xz, (float)uc.yz, (float)uc.z } };
+        for (uint32_t k = 1; k < n; ++k) {   // deperiodize_triclinic from atom 1 on (:8993)
+            float4 v = p[k];
+            float d[3] = { __fsub_rn(v.x, com[0]), __fsub_rn(v.y, com[1]), __fsub_rn(v.z, com[2]) };
+            min_image_triclinic(d, box);
+            v.x = __fadd_rn(com[0], d[0]); v.y = __fadd_rn(com[1], d[1]); v.z = __fadd_rn(com[2], d[2]); p[k] = v;
+        }
+    } else {   // no cell: com_vec4, nothing to deperiodize
+        float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+        for (uint32_t k = 0; k < n; ++k) { const float4 v = p[k]; ax = ax + v.x * v.w; ay = ay + v.y * v.w; az = az + v.z * v.w; aw = aw + v.w * 1.0f; }
+        com[0] = ax / aw; com[1] = ay / aw; com[2] = az / aw;
+    }
+    double C[3][3] = { { 0 } }; double ws = 0.0;   // mat3_covariance_matrix_vec4 (core/md_vec_math.c:101-156)
+    for (uint32_t k = 0; k < n; ++k) {
+        const float4 v = p[k];
+        const float px = v.x - com[0], py = v.y - com[1], pz = v.z - com[2], w = v.w;
+        C[0][0] += w * px * px; C[0][1] += w * px * py; C[0][2] += w * px * pz;
+        C[1][0] += w * py * px; C[1][1] += w * py * py; C[1][2] += w * py * pz;
+        C[2][0] += w * pz * px; C[2][1] += w * pz * py; C[2][2] += w * pz * pz;
+        ws += w;
+    }
+    M3 cov; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) cov.e[i][j] = (float)(C[i][j] / ws);
+    const Svd sv = m3_svd(cov);   // mat3_eigen (:22-42): values normalised by the largest, sorted descending
+    const float mx = fmaxf(sv.s[0], fmaxf(sv.s[1], sv.s[2]));
+    const float ev[3] = { sv.s[0] / mx, sv.s[1] / mx, sv.s[2] / mx };
+    int l0 = 0, l1 = 1, l2 = 2, t;
+    if (ev[l0] < ev[l1]) { t = l0; l0 = l1; l1 = t; }
+    if (ev[l1] < ev[l2]) { t = l1; l1 = l2; l2 = t; }
+    if (ev[l0] < ev[l1]) { t = l0; l0 = l1; l1 = t; }
+    const float e0 = ev[l0], e1 = ev[l1], e2 = ev[l2];
+    const float sc = 1.0f / ((e0 + e1) + e2);   // md_util_shape_weights md_util.c:9070-9076
+    o[0] = (e0 - e1) * sc; o[1] = 2.0f * (e1 - e2) * sc; o[2] = 3.0f * e2 * sc;
+}
+
+void launch_shape_weights(const ShapeArgs& a, int B, cudaStream_t s) {
+    if (!a.n_struct || B <= 0) return;
+    k_shape_weights<<<dim3(a.n_struct, (unsigned)B), 32, 0, s>>>(a, B);
+    note_launch("k_shape_weights", s);
+}
+
 void launch_plane(const RmsdArgs& a, int B, cudaStream_t s) {
     if (!a.n || B <= 0) return;
     k_plane<<<B, 32, 0, s>>>(a, B);
