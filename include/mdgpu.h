@@ -106,6 +106,7 @@ typedef enum mdgpu_op {
     MDGPU_OP_WITHIN_COUNT = 15, /* count(within(radius, selection)): atoms of the system within radius of the selection -> temporal :2485-2533, :2868 */
     MDGPU_OP_SHAPE_WEIGHTS = 16, /* (linear, planar, isotropic) weights of n structures per frame -> temporal [F, n*3]: VIAMD's shape-space loop
                                   * (src/components/shapespace/shapespace.cpp:404-431) and _shape_weights (md_script_functions.inl:6005-6050) */
+    MDGPU_OP_COORD_X = 17, MDGPU_OP_COORD_Y = 18, MDGPU_OP_COORD_Z = 19,   /* coord_x/_y/_z(selection): the atoms' coordinates -> temporal [F, n]  :5077-5169 */
     MDGPU_OP_RMSD = 11,      /* rmsd(selection) against the initial frame -> temporal                     :4287-4345 */
 } mdgpu_op;
 
@@ -131,6 +132,7 @@ typedef enum mdgpu_op {
  *              system-wide cell list (get_spatial_acc :734); so far its only consumer on the device is count().
  *   SHAPE_WEIGHTS: idx[0] = the atoms of num_structures structures back to back (structure_offsets, or structure_size each), bit 0 of com_args
  *              = weights are the atom masses (shapespace's use_mass; _shape_weights always uses them), else 1.
+ *   COORD_X/_Y/_Z: idx[0] = the atoms.
  *   RMSD     : idx[0] = the atoms of the (flattened) selection; needs the initial frame and, to make molecules whole, the bond connectivity.
  *   DISTANCE/ANGLE/DIHEDRAL: idx[k] = the atoms of argument k (0-based). A single integer index is that atom's position; an
  *              argument that was a selection (bit k of com_args set, or more than one index) is its centre of mass as

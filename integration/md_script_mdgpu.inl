@@ -141,6 +141,13 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         out->idx_count[0] = mdgpu__flatten((int32_t*)out->idx[0], out->idx_count[0]);
         return true;
     }
+    if ((str_eq(pname, STR_LIT("coord_x")) || str_eq(pname, STR_LIT("coord_y")) || str_eq(pname, STR_LIT("coord_z"))) && nargs == 1) {   /* _coordinate_x/_y/_z :5077 */
+        size_t ns = 0;
+        out->op = MDGPU_OP_COORD_X + (uint32_t)(pname.ptr[6] - 'x');
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
+        if (args[0]->data.type.base_type == TYPE_BITFIELD && ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false; }
+        return true;
+    }
     if ((str_eq(pname, STR_LIT("com")) || str_eq(pname, STR_LIT("plane"))) && nargs == 1) {   /* _com :4726, _plane :4755: [F,3] / [F,4] temporals */
         size_t ns = 0;
         const bool is_com = str_eq(pname, STR_LIT("com"));

@@ -220,6 +220,23 @@ def test_shape_weights_of_structures():
         vb.Plan(vb.water_system(4), [vb.Property("x", vb.OP_SHAPE_WEIGHTS, [np.zeros(0, np.int32)])], 2)
 
 
+def test_coord_rows():
+    """coord_x / coord_y / coord_z (k_coord_rows): the atoms' coordinates as [F, n] temporals with aggregates, against the reference (pairs6.npz)."""
+    p = load_golden("pairs6.npz")
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        g = load_golden(name); s = golden_system(g)
+        plan, cells = _plan(g, s, "cx = coord_x(residue(1)); cz = coord_z(atom(5:40)); cyi = coord_y(7);", batch_frames=3)
+        plan.eval_host_frames(g["frames"], cells, 0)
+        for key in ("cx", "cz", "cyi"):
+            k = f"{tag}_{key}"; d = plan.property_data(key)
+            assert tuple(d.dim[:2]) == tuple(p[k + "__dim"][:2]) and np.array_equal(d.values, p[k + "__full"]), k
+            mn, mx, r0, r1 = p[k + "__meta"]
+            assert d.min_value == mn and d.max_value == mx and d.min_range[0] == r0 and d.max_range[0] == r1
+        agg = plan.aggregate("cz")
+        assert np.array_equal(agg["mean"], p[f"{tag}_cz__mean"]) and np.array_equal(agg["var"], p[f"{tag}_cz__var"]) and np.array_equal(agg["ext"], p[f"{tag}_cz__ext"])
+        plan.close()
+
+
 def test_within_min_max_form():
     """within(min:max, selection) (_within_expl_frng :2609): as the argument of count() against the reference (pairs6.npz, ortho + triclinic) and
     as the reference set of an rdf against the oracle."""

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libmdgpu.so")
 DIST_BINS = 1024
 VOL_DIM = 128
 
-OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE, OP_WITHIN_COUNT, OP_SHAPE_WEIGHTS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16
+OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE, OP_WITHIN_COUNT, OP_SHAPE_WEIGHTS, OP_COORD_X, OP_COORD_Y, OP_COORD_Z = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19
 CELL_ORTHO, CELL_TRICLINIC, CELL_PBC_X, CELL_PBC_Y, CELL_PBC_Z, CELL_PBC_ALL = 1, 2, 4, 8, 16, 28
 
 
@@ -291,6 +291,11 @@ def shape_weights(name, groups, use_mass=True):
     groups = [np.asarray(g, np.int32) for g in groups]
     off = np.zeros(len(groups) + 1, np.uint32); off[1:] = np.cumsum([len(g) for g in groups])
     return Property(name, OP_SHAPE_WEIGHTS, [np.concatenate(groups).astype(np.int32)], num_structures=len(groups), structure_offsets=off, com_args=1 if use_mass else 0)
+
+
+def coord(name, axis, idx):
+    """coord_x / coord_y / coord_z(selection): the atoms' coordinates along `axis` -> [F, n] (md_script_functions.inl:5077)"""
+    return Property(name, OP_COORD_X + int(axis), [np.asarray(idx, np.int32)])
 
 
 def rmsd(name, idx):

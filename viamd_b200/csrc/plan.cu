@@ -375,6 +375,14 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f);
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = (int32_t)pr.len; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
             break; }
+        case MDGPU_OP_COORD_X: case MDGPU_OP_COORD_Y: case MDGPU_OP_COORD_Z:   // coord_x/_y/_z(selection): [F, n]
+            if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
+            pr.len = pr.h_idx[0].size();
+            e = dalloc(&pr.d_temporal, num_frames * pr.len);
+            pr.values.assign(num_frames * pr.len, 0.0f);
+            if (pr.len > 1) { pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f); }
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = (int32_t)pr.len; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break;
         case MDGPU_OP_COM: {   // com(x): a [F, 3] temporal (TI_FLOAT3)
             if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
             pr.com_mask = (d.com_args & 1u) | (pr.h_idx[0].size() != 1 ? 1u : 0u);
@@ -675,6 +683,9 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             if (pr.com_mask & 1u) launch_arg_com(fr, s.d_cells, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), p->d_mass, ps.d_argpos, 0, s.stream);
             launch_com_rows(a, B, s.stream);
             break; }
+        case MDGPU_OP_COORD_X: case MDGPU_OP_COORD_Y: case MDGPU_OP_COORD_Z:
+            launch_coord_rows(fr, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), (int)pr.op - MDGPU_OP_COORD_X, pr.d_temporal, frame0, s.stream);
+            break;
         case MDGPU_OP_SHAPE_WEIGHTS: {
             ShapeArgs a{};
             a.frames = fr; a.cells = s.d_cells; a.mass = p->d_mass; a.use_mass = (int)(pr.com_mask & 1u);

@@ -337,6 +337,15 @@ __global__ void k_com_rows(TemporalArgs a, int B) {
     }
 }
 
+// coord_x / coord_y / coord_z(selection) (_coordinate_x/_y/_z md_script_functions.inl:5077-5169): the atoms' coordinates along one axis, row
+// (frame0 + f) of a [num_frames][n] temporal
+__global__ void k_coord_rows(BatchFrames fr, const int32_t* __restrict__ idx, uint32_t n, int axis, float* __restrict__ out, uint32_t frame0) {
+    const int f = blockIdx.y;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    out[(size_t)(frame0 + f) * n + k] = fr.xyz[(size_t)f * fr.frame_stride + (size_t)axis * fr.axis_stride + idx[k]];
+}
+
 // One pair of md_util_min_distance / md_util_distance_array (md_util.c:8210-8297): no cell -> vec3_distance; orthorhombic ->
 // vec4_periodic_distance (core/md_vec_math.h:1268-1273, vec4_dot sums (x+y)+(z+w)); triclinic -> the 27-image minimum + vec3_length.
 MDG_D float pair_distance(float ax, float ay, float az, float bx, float by, float bz, uint32_t flags, const float ext[3], const float box[3][3]) {
@@ -416,6 +425,12 @@ __global__ void k_mean_u32(const uint32_t* __restrict__ in, float* __restrict__ 
 void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned long long n, cudaStream_t s) {
     k_mean_u32<<<148 * 4, 256, 0, s>>>(d_in, d_out, count, n);
     note_launch("k_mean_u32", s);
+}
+
+void launch_coord_rows(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, int axis, float* d_out, uint32_t frame0, cudaStream_t s) {
+    if (!n || !fr.count) return;
+    k_coord_rows<<<dim3((n + 255u) / 256u, fr.count), 256, 0, s>>>(fr, d_idx, n, axis, d_out, frame0);
+    note_launch("k_coord_rows", s);
 }
 
 void launch_com_rows(const TemporalArgs& a, int B, cudaStream_t s) {

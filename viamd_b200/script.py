@@ -202,6 +202,8 @@ class _Parser:
             if self.peek() != ("id", "within"): raise ScriptError("count() is lowered for within(radius, selection) only")
             self.next(); self.expect("ch", "("); rlo, r = self.radius(); self.expect("ch", ","); sel = self.single_selection(); self.expect("ch", ")")
             p = api.count_within(ident, r, sel, rlo)
+        elif proc in ("coord_x", "coord_y", "coord_z"):
+            a = self.index(); p = api.coord(ident, "xyz".index(proc[-1]), [a] if np.ndim(a) == 0 else a)
         elif proc == "com":
             p = api.com(ident, self.index())
         elif proc == "plane":
