@@ -214,7 +214,8 @@ def test_shape_weights_of_structures():
         assert plan.eval_frame_range(vb.ArrayTrajectory(g["frames"], cells), 0, F)
         d = plan.property_data("sw")
         assert tuple(d.dim[:2]) == (F, 3 * n)
-        np.testing.assert_allclose(d.values.reshape(F, n, 3), w, rtol=1e-5, atol=1e-7)
+        # weights live in [0, 1]; the third one of a planar structure is rounding noise (~1e-6) that a last-bit difference in the centre moves freely
+        np.testing.assert_allclose(d.values.reshape(F, n, 3), w, rtol=1e-5, atol=1e-5)
         plan.close()
     with pytest.raises(vb.MdgpuError):
         vb.Plan(vb.water_system(4), [vb.Property("x", vb.OP_SHAPE_WEIGHTS, [np.zeros(0, np.int32)])], 2)
