@@ -208,8 +208,12 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
             out->op = dist ? MDGPU_OP_DISTANCE : (ang ? MDGPU_OP_ANGLE : MDGPU_OP_DIHEDRAL);
             for (size_t k = 0; k < need; ++k) {
                 size_t ns = 0;
-                if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], &ns, NULL, args[k], alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n;
-                if (args[k]->data.type.base_type == TYPE_BITFIELD) {
+                const ast_node_t* a = args[k];
+                /* com(x) as an argument is the position coordinate_extract_com yields for x (_com :4726), which is what the argument x itself
+                 * contributes (:1717): distance(com(sel), 5) == distance(sel, 5) */
+                if (a->type == AST_PROC_CALL && a->proc && str_eq(a->proc->name, STR_LIT("com")) && md_array_size(a->children) == 1) a = a->children[0];
+                if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], &ns, NULL, a, alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n;
+                if (a->data.type.base_type == TYPE_BITFIELD) {
                     if (ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections as argument (centre of sub-centres) is not lowered", STR_ARG(ident)); return false; }
                     out->com_args |= 1u << k;   /* a selection goes through md_util_com_compute even with one atom (coordinate_extract_com :1812) */
                 }

@@ -82,6 +82,8 @@ def test_script_lowering(vb):
     assert inc.op == vb.OP_DIHEDRAL and inc.num_structures == 3 and [list(i) for i in inc.idx] == [[3, 6, 9], [4, 7, 10], [5, 8, 11], [3, 6, 9]]
     with pytest.raises(vb.ScriptError):
         vb.compile_script("x = distance(residue(1), 2) in residue(2:4);", s)
+    dcm = vb.compile_script("x = distance(com(atom(1:6)), 10);", s)[0]
+    assert dcm.op == vb.OP_DISTANCE and dcm.com_args == 1 and list(dcm.idx[0]) == [0, 1, 2, 3, 4, 5] and list(dcm.idx[1]) == [9]
     cw = vb.compile_script("cw = count(within(4.5, residue(2)));", s)[0]
     assert cw.op == vb.OP_WITHIN_COUNT and cw.cutoff_max == 4.5 and list(cw.idx[0]) == [3, 4, 5]
     with pytest.raises(vb.ScriptError):

@@ -173,6 +173,9 @@ class _Parser:
         """argument of distance/angle/dihedral: a 1-based atom index (-> int) or a selection (-> index array, centre of mass)"""
         if self.peek()[0] == "num":
             return int(float(self.expect("num")[1])) - 1   # md_script atom indices are 1-based
+        if self.peek() == ("id", "com"):   # com(x) as an argument contributes the position x itself would (_com :4726 = coordinate_extract_com)
+            self.next(); self.expect("ch", "("); a = self.index(); self.expect("ch", ")")
+            return a
         return self.single_selection()
 
     def statement(self) -> api.Property:
