@@ -128,6 +128,8 @@ typedef enum mdgpu_op {
  *              With num_structures = n > 0 the statement was `expr in <n contexts>` (evaluate_context md_script.c:3418) with integer arguments:
  *              idx[k] holds n atoms, argument k remapped into each context (first atom of the context + k - 1); the property is [F, n].
  *   COM      : idx[0] as argument 0 of DISTANCE (bit 0 of com_args = it was a selection).   PLANE: idx[0] = the atoms (at least 3).
+ *              For both within() consumers (WITHIN_COUNT and RDF with ref_within_radius): bit 0 of com_args set = the expression was
+ *              `selection and within(...)` (_and :1975) and idx[2] holds that static selection's atoms (possibly none).
  *   WITHIN_COUNT: idx[0] = the selection's atoms, cutoff_max = radius (> 0), cutoff_min = lower bound of the min:max form (else 0). The dynamic selection within() is evaluated per frame over the
  *              system-wide cell list (get_spatial_acc :734); so far its only consumer on the device is count().
  *   SHAPE_WEIGHTS: idx[0] = the atoms of num_structures structures back to back (structure_offsets, or structure_size each), bit 0 of com_args

@@ -84,6 +84,38 @@ static size_t mdgpu__flatten(int32_t* v, size_t n) {
     return w;
 }
 
+/* `within([min:]max, selection)` or `static_selection and within(...)` (either order; _and md_script_functions.inl:1975 flattens arrays): the
+ * dynamic selection the device evaluates per frame. Returns the within() call and, through out_mask, the static side (NULL if none). */
+static const ast_node_t* mdgpu__within_expr(const ast_node_t* node, const ast_node_t** out_mask) {
+    *out_mask = NULL;
+    if (node->type != AST_PROC_CALL || !node->proc || md_array_size(node->children) != 2) return NULL;
+    if (str_eq(node->proc->name, STR_LIT("within"))) return node;
+    if (str_eq(node->proc->name, STR_LIT("and"))) {
+        for (int side = 0; side < 2; ++side) {
+            const ast_node_t* w = node->children[side]; const ast_node_t* m = node->children[1 - side];
+            if (w->type == AST_PROC_CALL && w->proc && str_eq(w->proc->name, STR_LIT("within")) && md_array_size(w->children) == 2 &&
+                (m->flags & FLAG_CONSTANT) && m->data.type.base_type == TYPE_BITFIELD) { *out_mask = m; return w; }
+        }
+    }
+    return NULL;
+}
+
+/* fills radius (and lower bound), the within() selection into idx[0] and the optional AND mask into idx[2] + com_args bit 0 */
+static bool mdgpu__lower_within(mdgpu_property_desc_t* out, const ast_node_t* w, const ast_node_t* mask, float* rmin, float* rmax, md_allocator_i* alloc) {
+    ast_node_t** c = w->children; size_t ns = 0; int64_t n;
+    if (!(c[0]->flags & FLAG_CONSTANT) || c[1]->data.type.base_type != TYPE_BITFIELD) return false;
+    if (c[0]->data.type.base_type == TYPE_FRANGE) { const frange_t r = *(const frange_t*)c[0]->data.ptr; *rmin = r.beg; *rmax = r.end; }   /* _within_expl_frng :2609 */
+    else if (c[0]->data.type.base_type == TYPE_FLOAT) { *rmin = 0.0f; *rmax = *(const float*)c[0]->data.ptr; }
+    else return false;
+    if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, c[1], alloc)) < 0 || ns > 1) return false;
+    out->idx_count[0] = (size_t)n;
+    if (mask) {
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[2], NULL, NULL, mask, alloc)) < 0) return false;
+        out->idx_count[2] = mdgpu__flatten((int32_t*)out->idx[2], (size_t)n); out->com_args |= 1u;
+    }
+    return true;
+}
+
 static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const ast_node_t* node, md_allocator_i* alloc) {
     const ast_node_t* rhs = mdgpu__rhs(node);
     const md_bitfield_t* ctx_bf = NULL; size_t n_ctx = 0;
@@ -104,14 +136,9 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
     size_t nsets = 0, set_size = 0; int64_t n;
     if (str_eq(pname, STR_LIT("rdf")) && nargs == 3) {
         out->op = MDGPU_OP_RDF;
-        if (args[0]->type == AST_PROC_CALL && args[0]->proc && str_eq(args[0]->proc->name, STR_LIT("within")) && md_array_size(args[0]->children) == 2) {
-            /* dynamic reference set within(radius, selection) (_within_expl_flt :2485): evaluated per frame on the device */
-            ast_node_t** w = args[0]->children; size_t ns = 0;
-            if (!(w[0]->flags & FLAG_CONSTANT) || w[1]->data.type.base_type != TYPE_BITFIELD) goto dynamic;
-            if (w[0]->data.type.base_type == TYPE_FRANGE) { const frange_t r = *(const frange_t*)w[0]->data.ptr; out->ref_within_min = r.beg; out->ref_within_radius = r.end; }   /* _within_expl_frng :2609 */
-            else if (w[0]->data.type.base_type == TYPE_FLOAT) out->ref_within_radius = *(const float*)w[0]->data.ptr;
-            else goto dynamic;
-            if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, w[1], alloc)) < 0 || ns > 1) goto dynamic; out->idx_count[0] = (size_t)n;
+        const ast_node_t* wmask = NULL; const ast_node_t* wnode = mdgpu__within_expr(args[0], &wmask);
+        if (wnode) {   /* dynamic reference set (_within_expl_flt :2485 / _frng :2609), optionally `and` a static selection: evaluated per frame on the device */
+            if (!mdgpu__lower_within(out, wnode, wmask, &out->ref_within_min, &out->ref_within_radius, alloc)) goto dynamic;
         } else
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &nsets, &set_size, args[0], alloc)) < 0) goto dynamic; else out->idx_count[0] = (size_t)n;
         if (args[0]->data.type.base_type == TYPE_BITFIELD && nsets > 1) {   /* array of bitfields: COM references + exclusion masks (:5275) */
@@ -159,17 +186,11 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         }
         return true;
     }
-    if (str_eq(pname, STR_LIT("count")) && nargs == 1 && args[0]->type == AST_PROC_CALL && args[0]->proc && str_eq(args[0]->proc->name, STR_LIT("within")) &&
-        md_array_size(args[0]->children) == 2) {   /* count(within(radius, selection)): _within_expl_flt :2485 evaluated per frame on the device, _count :2868 */
-        ast_node_t** w = args[0]->children; size_t ns = 0;
-        if (!(w[0]->flags & FLAG_CONSTANT)) goto dynamic;
+    if (str_eq(pname, STR_LIT("count")) && nargs == 1) {   /* count(<within expression>): _count :2868 on the per-frame selection */
+        const ast_node_t* wmask = NULL; const ast_node_t* wnode = mdgpu__within_expr(args[0], &wmask);
+        if (!wnode) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': count() is lowered for within(...) expressions only", STR_ARG(ident)); return false; }
         out->op = MDGPU_OP_WITHIN_COUNT;
-        if (w[0]->data.type.base_type == TYPE_FRANGE) { const frange_t r = *(const frange_t*)w[0]->data.ptr; out->cutoff_min = r.beg; out->cutoff_max = r.end; }   /* _within_expl_frng :2609 */
-        else if (w[0]->data.type.base_type == TYPE_FLOAT) out->cutoff_max = *(const float*)w[0]->data.ptr;
-        else goto dynamic;
-        if (w[1]->data.type.base_type != TYPE_BITFIELD) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': within() is lowered for a selection argument only", STR_ARG(ident)); return false; }
-        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, w[1], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
-        if (ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false; }
+        if (!mdgpu__lower_within(out, wnode, wmask, &out->cutoff_min, &out->cutoff_max, alloc)) goto dynamic;
         return true;
     }
     if (str_eq(pname, STR_LIT("rmsd")) && nargs == 1) {   /* _rmsd :4287: the (flattened) selection against the initial configuration */

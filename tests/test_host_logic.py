@@ -84,6 +84,12 @@ def test_script_lowering(vb):
         vb.compile_script("x = distance(residue(1), 2) in residue(2:4);", s)
     dcm = vb.compile_script("x = distance(com(atom(1:6)), 10);", s)[0]
     assert dcm.op == vb.OP_DISTANCE and dcm.com_args == 1 and list(dcm.idx[0]) == [0, 1, 2, 3, 4, 5] and list(dcm.idx[1]) == [9]
+    cwo, rwo = vb.compile_script("cwo = count(element('O') and within(2.0:4.0, residue(2))); rwo = rdf(within(5.0, residue(1)) and not element('O'), element('O'), 6.0);", s)
+    assert cwo.op == vb.OP_WITHIN_COUNT and cwo.com_args == 1 and (cwo.cutoff_min, cwo.cutoff_max) == (2.0, 4.0) and list(cwo.idx[0]) == [3, 4, 5] and np.array_equal(cwo.idx[2], np.arange(0, 192, 3))
+    assert rwo.op == vb.OP_RDF and rwo.ref_within == 5.0 and rwo.com_args == 1 and len(rwo.idx[2]) == 128 and list(rwo.idx[0]) == [0, 1, 2]
+    for src in ("x = count(element('O') or within(4.0, residue(1)));", "x = count(not within(4.0, residue(1)));"):
+        with pytest.raises(vb.ScriptError):
+            vb.compile_script(src, s)
     cw = vb.compile_script("cw = count(within(4.5, residue(2)));", s)[0]
     assert cw.op == vb.OP_WITHIN_COUNT and cw.cutoff_max == 4.5 and list(cw.idx[0]) == [3, 4, 5]
     with pytest.raises(vb.ScriptError):

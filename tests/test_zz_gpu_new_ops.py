@@ -259,6 +259,25 @@ def test_within_min_max_form():
         vb.Plan(vb.water_system(4), [vb.count_within("c", 3.0, np.arange(3), radius_min=4.0)], 2)
 
 
+def test_static_selection_and_within():
+    """`selection and within(...)` (_and :1975) — e.g. the oxygens in the first shell of a residue: the static side masks the per-frame set.
+    Counts against the reference (pairs6.npz, either operand order, min:max form), the masked set as an rdf reference against the oracle."""
+    p = load_golden("pairs6.npz")
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        g = load_golden(name); s = golden_system(g); F = g["frames"].shape[0]; o = sel_element(s, 8); h = sel_element(s, 1)
+        plan, cells = _plan(g, s, "cwo = count(element('O') and within(4.0, residue(1))); cwh = count(within(2.5:5.0, residue(1)) and element('H')); "
+                                  "rwo = rdf(element('H') and within(5.0, residue(2)), element('O'), 6.0);", keep_frame_results=True)
+        plan.eval_host_frames(g["frames"], cells, 0)
+        assert np.array_equal(plan.property_data("cwo").values, p[f"{tag}_cwo__full"]) and np.array_equal(plan.property_data("cwh").values, p[f"{tag}_cwh__full"])
+        for f in range(F):
+            x, y, z = g["frames"][f]; cell = cell_from_row(g["cells"][f], g["cell_flags"][f])
+            ref = np.intersect1d(O.within(x, y, z, np.arange(3, 6, dtype=np.int32), 5.0, cell), h).astype(np.int32)
+            want, _, tot_w = O.rdf_frame(x, y, z, ref, o, cell, 0.0, 6.0)
+            bins, tot = plan.frame_counts("rwo", f)
+            assert np.array_equal(bins.astype(np.float32), want) and tot == tot_w, (tag, f)
+        plan.close()
+
+
 def test_rdf_with_a_dynamic_within_reference_set():
     """rdf(within(radius, selection), targets, cutoff): the reference atoms change every frame (marks -> per-frame index list -> home-grid cell
     list -> the usual cull + pair kernels). Per-frame bins, weights and the mean against the reference (golden rw); a second property in

@@ -208,10 +208,12 @@ def rdf(name, ref_idx, trg_idx, cutoff, cutoff_min=0.0):
     return Property(name, OP_RDF, [np.asarray(ref_idx, np.int32), np.asarray(trg_idx, np.int32)], cutoff_min=float(cutoff_min), cutoff_max=float(cutoff))
 
 
-def rdf_within(name, radius, sel_idx, trg_idx, cutoff, cutoff_min=0.0, radius_min=0.0):
+def rdf_within(name, radius, sel_idx, trg_idx, cutoff, cutoff_min=0.0, radius_min=0.0, and_idx=None):
     """rdf(within(radius, selection), targets, cutoff): the reference atoms are the dynamic selection within() of each frame — every atom of the
     system within `radius` of the selection, the selection itself excluded (md_script_functions.inl:2485) — then compute_rdf as usual."""
-    return Property(name, OP_RDF, [np.asarray(sel_idx, np.int32), np.asarray(trg_idx, np.int32)], cutoff_min=float(cutoff_min), cutoff_max=float(cutoff), ref_within=float(radius), ref_within_min=float(radius_min))
+    idx = [np.asarray(sel_idx, np.int32), np.asarray(trg_idx, np.int32)] + ([np.asarray(and_idx, np.int32)] if and_idx is not None else [])
+    return Property(name, OP_RDF, idx, cutoff_min=float(cutoff_min), cutoff_max=float(cutoff), ref_within=float(radius), ref_within_min=float(radius_min),
+                    com_args=0 if and_idx is None else 1)   # and_idx: the static side of `selection and within(...)`
 
 
 def rdf_com(name, groups, trg_idx, cutoff, cutoff_min=0.0):
@@ -279,10 +281,11 @@ def plane(name, idx):
     return Property(name, OP_PLANE, [np.asarray(idx, np.int32)])
 
 
-def count_within(name, radius, sel_idx, radius_min=0.0):
+def count_within(name, radius, sel_idx, radius_min=0.0, and_idx=None):
     """count(within(radius, selection)): per frame, the number of atoms of the system within `radius` of any atom of the selection, the
     selection itself excluded (_within_expl_flt md_script_functions.inl:2485, _count :2868) — a dynamic selection evaluated on the device"""
-    return Property(name, OP_WITHIN_COUNT, [np.asarray(sel_idx, np.int32)], cutoff_min=float(radius_min), cutoff_max=float(radius))   # min:max form: _within_expl_frng :2609
+    idx = [np.asarray(sel_idx, np.int32)] + ([np.zeros(0, np.int32), np.asarray(and_idx, np.int32)] if and_idx is not None else [])
+    return Property(name, OP_WITHIN_COUNT, idx, cutoff_min=float(radius_min), cutoff_max=float(radius), com_args=0 if and_idx is None else 1)   # min:max form: _within_expl_frng :2609
 
 
 def shape_weights(name, groups, use_mass=True):

@@ -91,6 +91,7 @@ struct WithinArgs {
     CellList trg, ref;               // all atoms (clamped cells) / the selection's atoms (home grid)
     const int32_t* sel; uint32_t n_sel;
     float min_r2;                    // within(min:max, ...): a pair counts from d2 >= min * min on; 0 for within(radius, ...)
+    const uint8_t* and_mask;         // `selection and within(...)` (_and md_script_functions.inl:1975): [num_atoms] bytes, or null
     uint32_t num_atoms;
     uint8_t* flags;                  // [B][num_atoms], zeroed by the launcher
     float* out;                      // [num_frames]

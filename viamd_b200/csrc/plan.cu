@@ -47,6 +47,7 @@ struct Prop {
     uint32_t com_mask = 0;   // distance/angle/dihedral: bit k = argument k is a selection evaluated through md_util_com_compute
     std::vector<uint32_t> h_soff; uint32_t* d_soff = nullptr;   // rdf with centre-of-mass references: CSR offsets of the groups in idx[0]
     float cutoff_min = 0.f, cutoff_max = 0.f;
+    uint8_t* d_and_mask = nullptr;   // `selection and within(...)`: one byte per atom of the static side (count(within()) / rdf(within()))
     float ref_within = 0.f, ref_within_min = 0.f;   // rdf: ref_within > 0 -> the reference atoms are within([min:]ref_within, idx[0]), evaluated per frame
     // device accumulators
     unsigned long long* d_acc = nullptr;          // rdf: 1024 bins; density: 1024 fixed-point sums
@@ -213,7 +214,7 @@ static void destroy_plan(mdgpu_plan* p) {
         if (pr.values_registered) cudaHostUnregister(pr.values.data());
         cudaFree(pr.d_vol_mean);
         cudaFree(pr.d_acc); cudaFree(pr.d_vol); cudaFree(pr.d_frame_total); cudaFree(pr.d_frame_min); cudaFree(pr.d_frame_max);
-        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap); cudaFree(pr.d_soff);
+        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap); cudaFree(pr.d_soff); cudaFree(pr.d_and_mask);
     }
     for (auto& t : p->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (p->t_begin) cudaEventDestroy(p->t_begin);
@@ -268,6 +269,10 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
                 for (int32_t a : pr.h_idx[k]) if (a < 0 || (size_t)a >= sys->num_atoms) return bail(MDGPU_ERR_INVALID_ARG, "property '" + pr.name + "': atom index out of range");
                 if (upload(&pr.d_idx[k], pr.h_idx[k].data(), pr.h_idx[k].size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (indices)");
             }
+        }
+        if ((pr.op == MDGPU_OP_WITHIN_COUNT || (pr.op == MDGPU_OP_RDF && d.ref_within_radius > 0.0f)) && (d.com_args & 1u)) {   // idx[2] = static side of `sel and within(...)`
+            std::vector<uint8_t> m(sys->num_atoms, 0); for (int32_t a : pr.h_idx[2]) m[(size_t)a] = 1;
+            if (upload(&pr.d_and_mask, m.data(), m.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (selection mask)");
         }
         cudaError_t e = cudaSuccess;
         switch (pr.op) {
@@ -598,7 +603,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
                 launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_wgeom, ps.wref, 0, s.stream);
                 WithinArgs w{};
                 w.geom = ps.d_wgeom; w.trg = ps.wtrg; w.ref = ps.wref; w.sel = pr.d_idx[0]; w.n_sel = (uint32_t)pr.h_idx[0].size();
-                w.num_atoms = (uint32_t)p->num_atoms; w.flags = ps.d_flags; w.out = nullptr; w.frame0 = frame0; w.min_r2 = pr.ref_within_min * pr.ref_within_min;
+                w.num_atoms = (uint32_t)p->num_atoms; w.flags = ps.d_flags; w.out = nullptr; w.frame0 = frame0; w.min_r2 = pr.ref_within_min * pr.ref_within_min; w.and_mask = pr.d_and_mask;
                 launch_within_list(w, B, tri, p->sm_count, ps.d_dyn_idx, ps.d_dyn_n, s.stream);
                 launch_cell_list_dyn(fr, ps.d_dyn_idx, ps.d_dyn_n, (uint32_t)p->num_atoms, cs.d_geom, ps.ref, s.stream);
             } else if (pr.n_struct) {
@@ -673,7 +678,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_geom, ps.ref, 0, s.stream);
             WithinArgs a{};
             a.geom = ps.d_geom; a.trg = ps.trg; a.ref = ps.ref; a.sel = pr.d_idx[0]; a.n_sel = (uint32_t)pr.h_idx[0].size();
-            a.num_atoms = (uint32_t)p->num_atoms; a.flags = ps.d_flags; a.out = pr.d_temporal; a.frame0 = frame0; a.min_r2 = pr.cutoff_min * pr.cutoff_min;   // :2641
+            a.num_atoms = (uint32_t)p->num_atoms; a.flags = ps.d_flags; a.out = pr.d_temporal; a.frame0 = frame0; a.min_r2 = pr.cutoff_min * pr.cutoff_min; a.and_mask = pr.d_and_mask;   // :2641
             launch_within_count(a, B, tri, p->sm_count, s.stream);
             break; }
         case MDGPU_OP_COM: {

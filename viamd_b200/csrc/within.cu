@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_within_count(WithinArgs a) {
     for (uint32_t k = threadIdx.x; k < a.n_sel; k += blockDim.x) flags[a.sel[k]] = 0;
     __syncthreads();
     uint32_t c = 0;
-    for (uint32_t i = threadIdx.x; i < a.num_atoms; i += blockDim.x) c += flags[i];
+    for (uint32_t i = threadIdx.x; i < a.num_atoms; i += blockDim.x) c += (flags[i] != 0 && (!a.and_mask || a.and_mask[i] != 0)) ? 1u : 0u;
     __shared__ uint32_t total;
     if (threadIdx.x == 0) total = 0;
     __syncthreads();
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) k_within_compact(WithinArgs a, int32_t* _
     int32_t* out = dyn_idx + (size_t)f * a.num_atoms;
     for (uint32_t i0 = 0; i0 < a.num_atoms; i0 += 256u) {
         const uint32_t i = i0 + threadIdx.x;
-        const bool on = i < a.num_atoms && flags[i] != 0;
+        const bool on = i < a.num_atoms && flags[i] != 0 && (!a.and_mask || a.and_mask[i] != 0);
         const uint32_t m = __ballot_sync(0xffffffffu, on);
         if (lane == 0) s_warp[warp] = (uint32_t)__popc(m);
         __syncthreads();

@@ -55,10 +55,14 @@ class _Parser:
         return tok
 
     # ---- selections -> boolean masks
+    _within = None   # (min, max, selection) of the one dynamic within() met while parsing a selection expression, see dyn_selection()
+
     def sel_or(self):
         m = self.sel_and()
         while self.peek() == ("id", "or"):
+            if self._within is not None: raise ScriptError("within() is lowered as `selection and within(...)` only, not under `or`")
             self.next(); m = m | self.sel_and()
+            if self._within is not None: raise ScriptError("within() is lowered as `selection and within(...)` only, not under `or`")
         return m
 
     def sel_and(self):
@@ -69,8 +73,20 @@ class _Parser:
 
     def sel_not(self):
         if self.peek() == ("id", "not"):
-            self.next(); return ~self.sel_not()
+            had = self._within
+            self.next(); m = ~self.sel_not()
+            if self._within is not had: raise ScriptError("`not within(...)` is not lowered")
+            return m
         return self.sel_atom()
+
+    def dyn_selection(self):
+        """`within([min:]max, sel)` or `static and within(...)` (either order) -> (min, max, within's selection, static side's atoms or None);
+        the dynamic part is evaluated per frame on the device, the static side becomes its AND mask (_and md_script_functions.inl:1975)"""
+        self._within = None; self._static_seen = False
+        m = self.sel_or()
+        if self._within is None: raise ScriptError("a within(...) expression was expected")
+        lo, hi, sel = self._within; self._within = None
+        return lo, hi, sel, (np.nonzero(m)[0].astype(np.int32) if self._static_seen else None)
 
     def _range(self, count):
         """a | a:b | : (1-based inclusive, as in md_script) -> python slice bounds (0-based, exclusive end)"""
@@ -90,6 +106,12 @@ class _Parser:
         if tok[0] != "id":
             raise ScriptError(f"unexpected token {tok[1]!r} in selection")
         f = tok[1]
+        if f == "within":   # only inside dyn_selection(): stands for "every atom" in the static mask, the device supplies the real set
+            if self._within is not None: raise ScriptError("one within() per expression")
+            self.expect("ch", "("); lo, hi = self.radius(); self.expect("ch", ",")
+            sel = self.single_selection(); self.expect("ch", ")")
+            self._within = (lo, hi, sel); return np.ones(n, bool)
+        self._static_seen = True
         if f == "all": return np.ones(n, bool)
         self.expect("ch", "(")
         if f in ("element", "name", "label", "resname"):
@@ -159,6 +181,18 @@ class _Parser:
         self.i = save
         return self.selection()
 
+    def _has_within_before_comma(self) -> bool:
+        """does the argument that starts here (up to its top-level `,` or `)`) contain a within(...) call"""
+        depth = 0
+        for t in self.t[self.i:]:
+            if t == ("ch", "("): depth += 1
+            elif t == ("ch", ")"):
+                if depth == 0: return False
+                depth -= 1
+            elif t == ("ch", ",") and depth == 0: return False
+            elif t == ("id", "within"): return True
+        return False
+
     def number(self) -> float:
         return float(self.expect("num")[1])
 
@@ -183,15 +217,15 @@ class _Parser:
         proc = self.expect("id")[1]; self.expect("ch", "(")
         if proc == "rdf":
             wr = None
-            if self.peek() == ("id", "within"):   # dynamic reference set: within(radius, selection)
-                self.next(); self.expect("ch", "("); wlo, wr = self.radius(); self.expect("ch", ","); wsel = self.single_selection(); self.expect("ch", ")")
+            if self._has_within_before_comma():   # dynamic reference set: within([min:]max, selection), optionally `and` a static selection
+                wlo, wr, wsel, wand = self.dyn_selection()
             grp = self.groups() if wr is None else None
             ref = None if (grp is not None or wr is not None) else self.selection()
             self.expect("ch", ","); trg = self.selection(); self.expect("ch", ",")
             a = self.number(); lo, hi = 0.0, a
             if self.peek() == ("ch", ":"):
                 self.next(); lo, hi = a, self.number()
-            if wr is not None: p = api.rdf_within(ident, wr, wsel, trg, hi, lo, wlo)
+            if wr is not None: p = api.rdf_within(ident, wr, wsel, trg, hi, lo, wlo, wand)
             else: p = api.rdf_com(ident, grp, trg, hi, lo) if grp is not None else api.rdf(ident, ref, trg, hi, lo)
         elif proc == "sdf":
             st = self.structures(); self.expect("ch", ","); trg = self.selection(); self.expect("ch", ","); c = self.number()
@@ -202,9 +236,9 @@ class _Parser:
             a = self.single_selection(); self.expect("ch", ","); b = self.single_selection()
             p = {"distance_min": api.distance_min, "distance_max": api.distance_max, "distance_pair": api.distance_pair}[proc](ident, a, b)
         elif proc == "count":   # count(within(radius, selection)): the one dynamic selection the device path evaluates
-            if self.peek() != ("id", "within"): raise ScriptError("count() is lowered for within(radius, selection) only")
-            self.next(); self.expect("ch", "("); rlo, r = self.radius(); self.expect("ch", ","); sel = self.single_selection(); self.expect("ch", ")")
-            p = api.count_within(ident, r, sel, rlo)
+            if not self._has_within_before_comma(): raise ScriptError("count() is lowered for within(radius, selection) expressions only")
+            rlo, r, sel, cand = self.dyn_selection()
+            p = api.count_within(ident, r, sel, rlo, cand)
         elif proc in ("coord_x", "coord_y", "coord_z"):
             a = self.index(); p = api.coord(ident, "xyz".index(proc[-1]), [a] if np.ndim(a) == 0 else a)
         elif proc == "com":
