@@ -55,6 +55,7 @@ class _Parser:
         return tok
 
     # ---- selections -> boolean masks
+    _static_seen = False
     _within = None   # (min, max, selection) of the one dynamic within() met while parsing a selection expression, see dyn_selection()
 
     def sel_or(self):
@@ -109,7 +110,7 @@ class _Parser:
         if f == "within":   # only inside dyn_selection(): stands for "every atom" in the static mask, the device supplies the real set
             if self._within is not None: raise ScriptError("one within() per expression")
             self.expect("ch", "("); lo, hi = self.radius(); self.expect("ch", ",")
-            sel = self.single_selection(); self.expect("ch", ")")
+            seen = self._static_seen; sel = self.single_selection(); self._static_seen = seen; self.expect("ch", ")")   # within's own argument is not the static side
             self._within = (lo, hi, sel); return np.ones(n, bool)
         self._static_seen = True
         if f == "all": return np.ones(n, bool)
