@@ -107,8 +107,8 @@ static bool mdgpu__lower_within(mdgpu_property_desc_t* out, const ast_node_t* w,
     if (c[0]->data.type.base_type == TYPE_FRANGE) { const frange_t r = *(const frange_t*)c[0]->data.ptr; *rmin = r.beg; *rmax = r.end; }   /* _within_expl_frng :2609 */
     else if (c[0]->data.type.base_type == TYPE_FLOAT) { *rmin = 0.0f; *rmax = *(const float*)c[0]->data.ptr; }
     else return false;
-    if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, c[1], alloc)) < 0 || ns > 1) return false;
-    out->idx_count[0] = (size_t)n;
+    if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, c[1], alloc)) < 0) return false;
+    out->idx_count[0] = mdgpu__flatten((int32_t*)out->idx[0], (size_t)n);   /* within is FLAG_FLATTEN (:673): an array of selections is their union */
     if (mask) {
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[2], NULL, NULL, mask, alloc)) < 0) return false;
         out->idx_count[2] = mdgpu__flatten((int32_t*)out->idx[2], (size_t)n); out->com_args |= 1u;

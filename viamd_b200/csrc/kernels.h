@@ -122,6 +122,7 @@ struct TemporalArgs {
 };
 void launch_temporal_ctx(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s);
+void launch_groups_com_pbc(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, const uint32_t* d_off, uint32_t n_groups, const float* d_mass, float* d_out /* [B][n_groups][3] */, cudaStream_t s);
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_com_rows(const TemporalArgs& a, int B, cudaStream_t s);   // com(x): row (frame0 + f) of a [num_frames][3] temporal = position of argument 0
 void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s);

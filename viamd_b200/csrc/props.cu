@@ -177,13 +177,8 @@ MDG_D float reduce8(float v) {
 // AVX2 build evaluates it — threads 0..7 of the warp are the 8 SIMD lanes (element i goes to lane i % 8, sequential per lane), the
 // count % 8 tail and the final atan2 step run in double on thread 0. No cell (flags == 0): com() :7139; otherwise the trigonometric
 // periodic centre of mass com_pbc :8019 -> _com_pbc_iw :7850. One warp per (argument, frame).
-__global__ void k_arg_com(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ idx, uint32_t count,
-                          const float* __restrict__ mass, float* __restrict__ out /* [B][4][3] */, int arg) {
-    const int f = blockIdx.x, lane = threadIdx.x;
-    const float* x = fr.xyz + (size_t)f * fr.frame_stride;
-    const float* src[3] = { x, x + fr.axis_stride, x + 2 * fr.axis_stride };
-    const mdgpu_unitcell_t uc = cells[f];
-    float* o = out + ((size_t)f * 4 + arg) * 3;
+MDG_D void periodic_com_warp(const float* const src[3], const mdgpu_unitcell_t& uc, const int32_t* __restrict__ idx, uint32_t count,
+                             const float* __restrict__ mass, float* __restrict__ o, int lane) {
     const uint32_t simd_count = count & ~7u;
     if (uc.flags == 0) {
         float v[4] = { 0.f, 0.f, 0.f, 0.f };
@@ -247,6 +242,33 @@ __global__ void k_arg_com(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ c
             o[k] = (float)__dadd_rn(__dadd_rn(__dmul_rn(theta, (double)I[k][0]), __dmul_rn(theta, (double)I[k][1])), __dmul_rn(theta, (double)I[k][2]));
         }
     }
+}
+
+__global__ void k_arg_com(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ idx, uint32_t count,
+                          const float* __restrict__ mass, float* __restrict__ out /* [B][4][3] */, int arg) {
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const float* x = fr.xyz + (size_t)f * fr.frame_stride;
+    const float* src[3] = { x, x + fr.axis_stride, x + 2 * fr.axis_stride };
+    periodic_com_warp(src, cells[f], idx, count, mass, out + ((size_t)f * 4 + arg) * 3, lane);
+}
+
+// The same centre for every selection of an ARRAY of selections (coordinate_extract :1496-1507 on several bitfields: one
+// md_util_com_compute per bitfield): groups in CSR form, one warp per (group, frame), positions [B][n_groups][3].
+__global__ void k_groups_com_pbc(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ idx, const uint32_t* __restrict__ off,
+                                 uint32_t n_groups, const float* __restrict__ mass, float* __restrict__ out) {
+    const int f = blockIdx.y, lane = threadIdx.x; const uint32_t g = blockIdx.x;
+    const float* x = fr.xyz + (size_t)f * fr.frame_stride;
+    const float* src[3] = { x, x + fr.axis_stride, x + 2 * fr.axis_stride };
+    float* o = out + ((size_t)f * n_groups + g) * 3;
+    const uint32_t b = off[g], count = off[g + 1] - b;
+    if (count == 0) { if (lane == 0) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; } return; }   // md_util_com_compute :8168
+    periodic_com_warp(src, cells[f], idx + b, count, mass, o, lane);
+}
+
+void launch_groups_com_pbc(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, const uint32_t* d_off, uint32_t n_groups, const float* d_mass, float* d_out, cudaStream_t s) {
+    if (!fr.count || !n_groups) return;
+    k_groups_com_pbc<<<dim3(n_groups, fr.count), 32, 0, s>>>(fr, d_cells, d_idx, d_off, n_groups, d_mass, d_out);
+    note_launch("k_groups_com_pbc", s);
 }
 
 void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s) {

@@ -110,7 +110,7 @@ class _Parser:
         if f == "within":   # only inside dyn_selection(): stands for "every atom" in the static mask, the device supplies the real set
             if self._within is not None: raise ScriptError("one within() per expression")
             self.expect("ch", "("); lo, hi = self.radius(); self.expect("ch", ",")
-            seen = self._static_seen; sel = self.single_selection(); self._static_seen = seen; self.expect("ch", ")")   # within's own argument is not the static side
+            seen = self._static_seen; sel = self.selection(); self._static_seen = seen; self.expect("ch", ")")   # within's own argument is not the static side; FLAG_FLATTEN (:673): an array of selections is their union
             self._within = (lo, hi, sel); return np.ones(n, bool)
         self._static_seen = True
         if f == "all": return np.ones(n, bool)
