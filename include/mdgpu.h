@@ -122,7 +122,9 @@ typedef enum mdgpu_op {
  *   SDF      : idx[0] = num_structures * structure_size atoms (equivalent structures), idx[1] = target atoms, cutoff_max.
  *   DENSITY_*: idx[0] = atoms.
  *   DISTANCE_MIN/_MAX: idx[0], idx[1] = the atoms of the two selections (brute force over all pairs, md_util_min_distance md_util.c:8242).
- *   DISTANCE_PAIR: idx[0], idx[1] as for DISTANCE_MIN; row f of the property holds out[i * |b| + j] (md_util_distance_array md_util.c:8210);
+ *   DISTANCE_PAIR: an argument that was an ARRAY of selections contributes one position per selection, its centre of mass as for rdf's group references (extract_com :857): groups of
+ *              argument 0 in structure_offsets[num_structures + 1], of argument 1 in structure_offsets_b[num_structures_b + 1]. Otherwise
+ *              idx[0], idx[1] as for DISTANCE_MIN; row f of the property holds out[i * |b| + j] (md_util_distance_array md_util.c:8210);
  *              at most 1 000 000 values per frame (:4056). Properties with more than one value per frame also carry per-frame aggregates
  *              (mdgpu_plan_property_aggregate).
  *              With num_structures = n > 0 the statement was `expr in <n contexts>` (evaluate_context md_script.c:3418) with integer arguments:
@@ -153,6 +155,8 @@ typedef struct mdgpu_property_desc_t {
     uint32_t com_args;                   /* distance/angle/dihedral: bit k = argument k is a selection (centre of mass even for one atom) */
     float ref_within_radius;             /* rdf: > 0 -> the reference argument was within(radius, idx[0]): the dynamic selection is evaluated per frame */
     float ref_within_min;                /* ... within(min:radius, idx[0]) (_within_expl_frng :2609); 0 for the plain form */
+    const uint32_t* structure_offsets_b; /* distance_pair: CSR groups of argument 1 when it was an array of selections (argument 0 uses structure_offsets) */
+    size_t num_structures_b;
 } mdgpu_property_desc_t;
 
 /* Result view: the fields of md_script_property_data_t (md_script.h:73-92) that the evaluation fills. */

@@ -199,8 +199,22 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         out->idx_count[0] = mdgpu__flatten((int32_t*)out->idx[0], (size_t)n);
         return true;
     }
-    if ((str_eq(pname, STR_LIT("distance_min")) || str_eq(pname, STR_LIT("distance_max")) || str_eq(pname, STR_LIT("distance_pair"))) && nargs == 2) {
-        out->op = str_eq(pname, STR_LIT("distance_min")) ? MDGPU_OP_DISTANCE_MIN : (str_eq(pname, STR_LIT("distance_max")) ? MDGPU_OP_DISTANCE_MAX : MDGPU_OP_DISTANCE_PAIR);
+    if (str_eq(pname, STR_LIT("distance_pair")) && nargs == 2) {   /* _distance_pair :3972; an array of bitfields = one centre of mass per bitfield (coordinate_extract :1503 -> extract_com :857) */
+        out->op = MDGPU_OP_DISTANCE_PAIR;
+        for (size_t k = 0; k < 2; ++k) {
+            size_t ns = 0;
+            if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], &ns, NULL, args[k], alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n;
+            if (args[k]->data.type.base_type == TYPE_BITFIELD && ns > 1) {
+                const md_bitfield_t* bf = (const md_bitfield_t*)args[k]->data.ptr;
+                uint32_t* off = (uint32_t*)md_alloc(alloc, sizeof(uint32_t) * (ns + 1));
+                off[0] = 0; for (size_t i = 0; i < ns; ++i) off[i + 1] = off[i] + (uint32_t)md_bitfield_popcount(&bf[i]);
+                if (k == 0) { out->structure_offsets = off; out->num_structures = ns; } else { out->structure_offsets_b = off; out->num_structures_b = ns; }
+            }
+        }
+        return true;
+    }
+    if ((str_eq(pname, STR_LIT("distance_min")) || str_eq(pname, STR_LIT("distance_max"))) && nargs == 2) {
+        out->op = str_eq(pname, STR_LIT("distance_min")) ? MDGPU_OP_DISTANCE_MIN : MDGPU_OP_DISTANCE_MAX;
         for (size_t k = 0; k < 2; ++k) {
             size_t ns = 0;
             if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], &ns, NULL, args[k], alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n;

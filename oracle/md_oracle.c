@@ -1073,6 +1073,11 @@ void mdo_distance_pair(const float* x, const float* y, const float* z, const int
     }
 }
 
+/* The same matrix between given positions [na][3] x [nb][3] (arguments that were arrays of selections: one extract_com centre each) */
+void mdo_distance_pair_pos(const float* pa, size_t na, const float* pb, size_t nb, const mdo_unitcell_t* cell, float* out) {
+    for (size_t i = 0; i < na; ++i) for (size_t j = 0; j < nb; ++j) out[i * nb + j] = pair_distance(pa + 3 * i, pb + 3 * j, cell);
+}
+
 /* Per-frame aggregates of a multi-valued temporal: compute_min_max_mean_variance (md_script.c:5646-5677), two passes in float.
  * out[4] = min, max, mean, population variance. */
 void mdo_aggregate(const float* data, size_t count, float out[4]) {

@@ -14,7 +14,7 @@ extern "C" int emul_distance_pair(const float* frames, size_t frame_stride, size
     blockDim = dim3(256, 1, 1); gridDim = dim3((unsigned)((npairs + 255) / 256), num_frames, 1);   // launch_distance_pair
     for (unsigned by = 0; by < gridDim.y; ++by) for (unsigned bx = 0; bx < gridDim.x; ++bx) for (unsigned t = 0; t < 256; ++t) {
         blockIdx.x = bx; blockIdx.y = by; blockIdx.z = 0; threadIdx.x = t; threadIdx.y = 0; threadIdx.z = 0;
-        mdg::k_distance_pair(fr, cells, ia, na, ib, nb, out, 0);
+        mdg::k_distance_pair(fr, cells, ia, na, ib, nb, nullptr, nullptr, out, 0);
     }
     return 0;
 }

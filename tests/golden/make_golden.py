@@ -175,7 +175,8 @@ def pairs6(tmp):
               "anc = angle(2,1,3) in residue(1:10); ddc = distance(1,3) in residue(:); dhc = dihedral(1,2,3,1) in residue(3:4); "
               "cx = coord_x(residue(1)); cz = coord_z(atom(5:40)); cyi = coord_y(7); "
               "cwo = count(element('O') and within(4.0, residue(1))); cwh = count(within(2.5:5.0, residue(1)) and element('H')); "
-              "cwg = count(within(6.0, residue(1:5))); cwg2 = count(within(2.0:4.5, residue(10:40)));")
+              "cwg = count(within(6.0, residue(1:5))); cwg2 = count(within(2.0:4.5, residue(10:40))); "
+              "dpg = distance_pair(residue(1:4), residue(10:15)); dpm = distance_pair(residue(2:5), atom(100:103));")
     w = np.load(os.path.join(HERE, "water6.npz")); t = np.load(os.path.join(HERE, "tric6.npz"))
     for tag, g, seed in (("w", w, "77"), ("t", t, "91")):
         gro, raw, o = os.path.join(tmp, tag + "p.gro"), os.path.join(tmp, tag + "p.raw"), os.path.join(tmp, tag + "p.out")

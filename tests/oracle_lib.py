@@ -203,6 +203,16 @@ def distance_pair(x, y, z, a, b, cell):
     return out
 
 
+def distance_pair_args(x, y, z, mass, a, b, cell):
+    """distance_pair(a, b) where a / b is an index array (atoms) or a list of index arrays (array of selections -> one extract_com centre each)"""
+    def positions(arg):
+        if isinstance(arg, (list, tuple)): return np.asarray(group_com(x, y, z, mass, arg)[0], np.float32).reshape(-1, 3)   # extract_com :857
+        arg = np.asarray(arg, np.int32); return np.stack([_f32(x)[arg], _f32(y)[arg], _f32(z)[arg]], axis=1)
+    pa, pb = np.ascontiguousarray(positions(a), np.float32), np.ascontiguousarray(positions(b), np.float32); out = np.zeros(len(pa) * len(pb), np.float32)
+    lib().mdo_distance_pair_pos(_p(pa, C.c_float), C.c_size_t(len(pa)), _p(pb, C.c_float), C.c_size_t(len(pb)), C.byref(cell), _p(out, C.c_float))
+    return out
+
+
 def aggregate(values):
     """-> (min, max, mean, var) as the reference folds one frame of a multi-valued temporal"""
     v = _f32(values); out = np.zeros(4, np.float32)

@@ -68,12 +68,14 @@ def test_script_lowering(vb):
     assert rr.cutoff_min == 2.0 and rr.cutoff_max == 8.0 and len(rr.idx[1]) == 128
     with pytest.raises(vb.ScriptError):
         vb.compile_script("x = shape_weights(all);", s)
+    dpg = vb.compile_script("dpg = distance_pair(residue(1:3), residue(5));", s)[0]   # array of selections x one selection
+    assert dpg.op == vb.OP_DISTANCE_PAIR and dpg.num_structures == 3 and list(dpg.structure_offsets) == [0, 3, 6, 9] and dpg.structure_offsets_b is None and list(dpg.idx[1]) == [12, 13, 14]
     dp = vb.compile_script("dp = distance_pair(residue(1), element('O'));", s)[0]
     assert dp.op == vb.OP_DISTANCE_PAIR and list(dp.idx[0]) == [0, 1, 2] and len(dp.idx[1]) == 64
     c, ci, pl = vb.compile_script("c = com(residue(2)); ci = com(7); pl = plane(atom(1:9));", s)
     assert c.op == vb.OP_COM and c.com_args == 1 and list(c.idx[0]) == [3, 4, 5] and ci.com_args == 0 and list(ci.idx[0]) == [6]
     assert pl.op == vb.OP_PLANE and list(pl.idx[0]) == list(range(9))
-    for src in ("x = com(residue(1:3));", "x = plane(residue(1:3));", "x = distance(residue(1:2), 5);", "x = distance_pair(residue(1:2), element('O'));"):
+    for src in ("x = com(residue(1:3));", "x = plane(residue(1:3));", "x = distance(residue(1:2), 5);", "x = distance_min(residue(1:2), element('O'));"):
         with pytest.raises(vb.ScriptError):   # one position per selection in the reference: not lowered, never flattened silently
             vb.compile_script(src, s)
     rwp = vb.compile_script("rw = rdf(within(4.0, residue(2)), element('O'), 2.0:6.0);", s)[0]

@@ -21,7 +21,7 @@ SCRIPT = ("r = rdf(element('O'), element('O'), 6.0); v = sdf(residue(1:20), elem
 SCRIPT_NEW = ("rm = rmsd(residue(1:10)); dp = distance_pair(atom(1:5), atom(20:30)); c = com(residue(1)); ci = com(5); pl = plane(atom(1:30)); "
               "cw = count(within(4.0, residue(1))); dmn = distance_min(residue(1), atom(100:648)); dc = distance(residue(1), residue(5)); "
               "rw = rdf(within(4.0, residue(1)), element('O'), 6.0); cwr = count(within(2.5:5.0, residue(1))); rwr = rdf(within(3.0:6.0, residue(2)), element('O'), 1.0:6.5); "
-              "anc = angle(2,1,3) in residue(1:10); ddc = distance(1,3) in residue(:); cz = coord_z(atom(5:40)); cwg = count(within(6.0, residue(1:5))); cwo = count(element('O') and within(4.0, residue(1))); rwo = rdf(element('H') and within(5.0, residue(2)), element('O'), 6.0); dcm = distance(com(atom(1:30)), 200); acm = angle(com(residue(1)), com(residue(2)), residue(3));")
+              "anc = angle(2,1,3) in residue(1:10); ddc = distance(1,3) in residue(:); cz = coord_z(atom(5:40)); dpg = distance_pair(residue(1:4), residue(10:15)); cwg = count(within(6.0, residue(1:5))); cwo = count(element('O') and within(4.0, residue(1))); rwo = rdf(element('H') and within(5.0, residue(2)), element('O'), 6.0); dcm = distance(com(atom(1:30)), 200); acm = angle(com(residue(1)), com(residue(2)), residue(3));")
 
 
 def _need():

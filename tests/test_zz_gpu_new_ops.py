@@ -101,6 +101,22 @@ def test_distance_pair_goldens_and_aggregates():
         plan.close()
 
 
+def test_distance_pair_between_arrays_of_selections():
+    """distance_pair whose arguments are arrays of selections (k_group_com -> k_distance_pair on positions): the residue contact map,
+    groups x groups and groups x atoms, against the reference (pairs6.npz), ortho + triclinic."""
+    p = load_golden("pairs6.npz")
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        g = load_golden(name); s = golden_system(g)
+        plan, cells = _plan(g, s, "dpg = distance_pair(residue(1:4), residue(10:15)); dpm = distance_pair(residue(2:5), atom(100:103));", batch_frames=3)
+        plan.eval_host_frames(g["frames"], cells, 0)
+        for key in ("dpg", "dpm"):
+            k = f"{tag}_{key}"; d = plan.property_data(key)
+            assert tuple(d.dim[:2]) == tuple(p[k + "__dim"][:2]) and np.array_equal(d.values, p[k + "__full"]), k
+            agg = plan.aggregate(key)
+            assert np.array_equal(agg["mean"], p[k + "__mean"]) and np.array_equal(agg["var"], p[k + "__var"])
+        plan.close()
+
+
 def test_distance_pair_limits():
     import viamd_b200 as vb
     sysm = vb.water_system(8)

@@ -69,7 +69,8 @@ class _SystemDesc(C.Structure):
 class _PropertyDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("op", C.c_uint32), ("idx", C.POINTER(C.c_int32) * 4), ("idx_count", C.c_size_t * 4),
                 ("num_structures", C.c_size_t), ("structure_size", C.c_size_t), ("cutoff_min", C.c_float), ("cutoff_max", C.c_float),
-                ("structure_offsets", C.POINTER(C.c_uint32)), ("com_args", C.c_uint32), ("ref_within_radius", C.c_float), ("ref_within_min", C.c_float)]
+                ("structure_offsets", C.POINTER(C.c_uint32)), ("com_args", C.c_uint32), ("ref_within_radius", C.c_float), ("ref_within_min", C.c_float),
+                ("structure_offsets_b", C.POINTER(C.c_uint32)), ("num_structures_b", C.c_size_t)]
 
 
 class _PropertyData(C.Structure):
@@ -202,6 +203,7 @@ class Property:
     com_args: int = 0                                # distance/angle/dihedral: bit k = argument k is a selection (centre of mass)
     ref_within: float = 0.0                          # rdf: > 0 -> references = within([ref_within_min:]ref_within, idx[0]) evaluated per frame
     ref_within_min: float = 0.0
+    structure_offsets_b: Optional[np.ndarray] = None  # distance_pair: CSR groups of argument 1 (argument 0 uses structure_offsets)
 
 
 def rdf(name, ref_idx, trg_idx, cutoff, cutoff_min=0.0):
@@ -266,9 +268,16 @@ def distance_max(name, a_idx, b_idx):
     return Property(name, OP_DISTANCE_MAX, [np.asarray(a_idx, np.int32), np.asarray(b_idx, np.int32)])
 
 
-def distance_pair(name, a_idx, b_idx):
-    """distance_pair(a, b): all |a| x |b| pair distances per frame, a temporal with |a|*|b| values per frame (md_script_functions.inl:3972)"""
-    return Property(name, OP_DISTANCE_PAIR, [np.asarray(a_idx, np.int32), np.asarray(b_idx, np.int32)])
+def distance_pair(name, a, b):
+    """distance_pair(a, b): all |a| x |b| pair distances per frame, a temporal with |a|*|b| values per frame (md_script_functions.inl:3972).
+    a / b: an index array (the atoms of one selection) or a LIST of index arrays (an array of selections: one centre of mass each, extract_com :857)."""
+    idx, offs = [], []
+    for arg in (a, b):
+        if isinstance(arg, (list, tuple)):
+            g = [np.asarray(x, np.int32) for x in arg]; off = np.zeros(len(g) + 1, np.uint32); off[1:] = np.cumsum([len(x) for x in g])
+            idx.append(np.concatenate(g).astype(np.int32)); offs.append(off)
+        else: idx.append(np.asarray(arg, np.int32)); offs.append(None)
+    return Property(name, OP_DISTANCE_PAIR, idx, num_structures=0 if offs[0] is None else len(offs[0]) - 1, structure_offsets=offs[0], structure_offsets_b=offs[1])
 
 
 def com(name, a):
@@ -413,6 +422,9 @@ class Plan:
             if p.structure_offsets is not None:
                 so = np.ascontiguousarray(p.structure_offsets, np.uint32); self._keep.append(so)
                 d.structure_offsets = so.ctypes.data_as(C.POINTER(C.c_uint32))
+            if p.structure_offsets_b is not None:
+                sb = np.ascontiguousarray(p.structure_offsets_b, np.uint32); self._keep.append(sb)
+                d.structure_offsets_b = sb.ctypes.data_as(C.POINTER(C.c_uint32)); d.num_structures_b = len(sb) - 1
             for k, arr in enumerate(p.idx):
                 a = np.ascontiguousarray(arr, np.int32); self._keep.append(a)
                 d.idx[k] = a.ctypes.data_as(C.POINTER(C.c_int32)); d.idx_count[k] = a.size

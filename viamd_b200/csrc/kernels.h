@@ -122,11 +122,11 @@ struct TemporalArgs {
 };
 void launch_temporal_ctx(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s);
-void launch_groups_com_pbc(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, const uint32_t* d_off, uint32_t n_groups, const float* d_mass, float* d_out /* [B][n_groups][3] */, cudaStream_t s);
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_com_rows(const TemporalArgs& a, int B, cudaStream_t s);   // com(x): row (frame0 + f) of a [num_frames][3] temporal = position of argument 0
 void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s);
-void launch_distance_pair(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s);
+void launch_distance_pair(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb,
+                          const float* d_posa, const float* d_posb, float* d_out, uint32_t frame0, cudaStream_t s);   // d_pos*: [B][n][3] group centres or null (atoms)
 void launch_coord_rows(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, int axis, float* d_out, uint32_t frame0, cudaStream_t s);   // coord_x/_y/_z
 void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned long long n, cudaStream_t s);
 

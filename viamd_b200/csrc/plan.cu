@@ -47,6 +47,7 @@ struct Prop {
     uint32_t com_mask = 0;   // distance/angle/dihedral: bit k = argument k is a selection evaluated through md_util_com_compute
     std::vector<uint32_t> h_soff; uint32_t* d_soff = nullptr;   // rdf with centre-of-mass references: CSR offsets of the groups in idx[0]
     float cutoff_min = 0.f, cutoff_max = 0.f;
+    std::vector<uint32_t> h_goff[2]; uint32_t* d_goff[2] = { nullptr, nullptr };   // distance_pair: CSR groups of argument 0 / 1 (arrays of selections)
     uint8_t* d_and_mask = nullptr;   // `selection and within(...)`: one byte per atom of the static side (count(within()) / rdf(within()))
     float ref_within = 0.f, ref_within_min = 0.f;   // rdf: ref_within > 0 -> the reference atoms are within([min:]ref_within, idx[0]), evaluated per frame
     // device accumulators
@@ -80,6 +81,7 @@ struct PropScratch {   // per (stream slot, property)
     float4* d_sdf_xyzw = nullptr; float* d_sdf_ref0 = nullptr; float* d_sdf_mats = nullptr;
     float* d_com = nullptr;   // rdf with centre-of-mass references: [B][n_struct][3]
     float* d_argpos = nullptr;   // distance/angle/dihedral with selection arguments: [B][4][3]
+    float* d_gpos[2] = { nullptr, nullptr };   // distance_pair with arrays of selections: [B][n_groups][3] per argument
     uint8_t* d_flags = nullptr;  // count(within()) / rdf(within(), ...): [B][num_atoms]
     // rdf whose reference set is within(radius, selection): the system-wide grid + lists of the within() query, and the per-frame reference list
     FrameGeom* d_wgeom = nullptr; float* d_waabb = nullptr; CellList wtrg{}, wref{}; int32_t* d_dyn_idx = nullptr; uint32_t* d_dyn_n = nullptr;
@@ -196,7 +198,7 @@ static void destroy_plan(mdgpu_plan* p) {
     for (auto& s : p->slots) {
         for (auto& ps : s.ps) {
             cudaFree(ps.d_geom); cudaFree(ps.d_aabb); free_cell_list(ps.trg); free_cell_list(ps.ref);
-            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_flags); cudaFree(ps.d_wgeom); cudaFree(ps.d_waabb); free_cell_list(ps.wtrg); free_cell_list(ps.wref); cudaFree(ps.d_dyn_idx); cudaFree(ps.d_dyn_n); cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
+            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_gpos[0]); cudaFree(ps.d_gpos[1]); cudaFree(ps.d_flags); cudaFree(ps.d_wgeom); cudaFree(ps.d_waabb); free_cell_list(ps.wtrg); free_cell_list(ps.wref); cudaFree(ps.d_dyn_idx); cudaFree(ps.d_dyn_n); cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
         }
         cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
@@ -214,7 +216,7 @@ static void destroy_plan(mdgpu_plan* p) {
         if (pr.values_registered) cudaHostUnregister(pr.values.data());
         cudaFree(pr.d_vol_mean);
         cudaFree(pr.d_acc); cudaFree(pr.d_vol); cudaFree(pr.d_frame_total); cudaFree(pr.d_frame_min); cudaFree(pr.d_frame_max);
-        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap); cudaFree(pr.d_soff); cudaFree(pr.d_and_mask);
+        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap); cudaFree(pr.d_soff); cudaFree(pr.d_and_mask); cudaFree(pr.d_goff[0]); cudaFree(pr.d_goff[1]);
     }
     for (auto& t : p->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (p->t_begin) cudaEventDestroy(p->t_begin);
@@ -351,7 +353,17 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             break; }
         case MDGPU_OP_DISTANCE_PAIR: {
             if (pr.h_idx[0].empty() || pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
-            pr.len = pr.h_idx[0].size() * pr.h_idx[1].size();
+            // an argument that was an ARRAY of selections contributes one position per selection: extract_com (:857, no periodic treatment; coordinate_extract :1503)
+            size_t cnt[2] = { pr.h_idx[0].size(), pr.h_idx[1].size() };
+            const uint32_t* goff[2] = { d.structure_offsets, d.structure_offsets_b }; const size_t gn[2] = { d.num_structures, d.num_structures_b };
+            for (int k = 0; k < 2; ++k) if (gn[k]) {
+                if (!goff[k] || goff[k][0] != 0 || goff[k][gn[k]] != pr.h_idx[k].size()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': group offsets do not cover the index list");
+                for (size_t g = 0; g < gn[k]; ++g) if (goff[k][g] > goff[k][g + 1]) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': group offsets must be non-decreasing");
+                pr.h_goff[k].assign(goff[k], goff[k] + gn[k] + 1); cnt[k] = gn[k];
+                if (upload(&pr.d_goff[k], pr.h_goff[k].data(), pr.h_goff[k].size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (group offsets)");
+            }
+            pr.n_struct = 0;   // num_structures described argument 0's groups here, not structures
+            pr.len = cnt[0] * cnt[1];
             if (pr.len > 1000000) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': The size produced by the operation is " + std::to_string(pr.len) + ", which exceeds the upper limit of 1'000'000");   // :4056
             e = dalloc(&pr.d_temporal, num_frames * pr.len);
             pr.values.assign(num_frames * pr.len, 0.0f);
@@ -551,6 +563,8 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * (pr.n_struct + 1) * pr.struct_size));
                     CUDA_TRY(dalloc(&ps.d_sdf_ref0, (size_t)p->B * 20));
                     CUDA_TRY(dalloc(&ps.d_sdf_mats, (size_t)p->B * pr.n_struct * 32));
+                } else if (pr.op == MDGPU_OP_DISTANCE_PAIR) {
+                    for (int k = 0; k < 2; ++k) if (!pr.h_goff[k].empty()) CUDA_TRY(dalloc(&ps.d_gpos[k], (size_t)p->B * (pr.h_goff[k].size() - 1) * 3));
                 } else if (pr.op == MDGPU_OP_WITHIN_COUNT) {
                     CUDA_TRY(dalloc(&ps.d_geom, p->B)); CUDA_TRY(dalloc(&ps.d_aabb, (size_t)6 * p->B));
                     int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)p->num_atoms, cap); if (rc) return rc;
@@ -704,9 +718,14 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap; a.scratch_xyzw = ps.d_sdf_xyzw; a.out = pr.d_temporal; a.frame0 = frame0;
             launch_plane(a, B, s.stream);
             break; }
-        case MDGPU_OP_DISTANCE_PAIR:
-            launch_distance_pair(fr, s.d_cells, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), pr.d_idx[1], (uint32_t)pr.h_idx[1].size(), pr.d_temporal, frame0, s.stream);
-            break;
+        case MDGPU_OP_DISTANCE_PAIR: {
+            uint32_t cnt[2];
+            for (int k = 0; k < 2; ++k) {
+                cnt[k] = (uint32_t)(pr.h_goff[k].empty() ? pr.h_idx[k].size() : pr.h_goff[k].size() - 1);
+                if (!pr.h_goff[k].empty()) launch_group_com(fr, pr.d_idx[k], pr.d_goff[k], cnt[k], p->d_mass, ps.d_gpos[k], s.stream);   // extract_com :857, as for rdf's group references
+            }
+            launch_distance_pair(fr, s.d_cells, pr.d_idx[0], cnt[0], pr.d_idx[1], cnt[1], ps.d_gpos[0], ps.d_gpos[1], pr.d_temporal, frame0, s.stream);
+            break; }
         case MDGPU_OP_RMSD: {
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "rmsd '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
             RmsdArgs a{};

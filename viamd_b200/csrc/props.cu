@@ -252,25 +252,6 @@ __global__ void k_arg_com(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ c
     periodic_com_warp(src, cells[f], idx, count, mass, out + ((size_t)f * 4 + arg) * 3, lane);
 }
 
-// The same centre for every selection of an ARRAY of selections (coordinate_extract :1496-1507 on several bitfields: one
-// md_util_com_compute per bitfield): groups in CSR form, one warp per (group, frame), positions [B][n_groups][3].
-__global__ void k_groups_com_pbc(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ idx, const uint32_t* __restrict__ off,
-                                 uint32_t n_groups, const float* __restrict__ mass, float* __restrict__ out) {
-    const int f = blockIdx.y, lane = threadIdx.x; const uint32_t g = blockIdx.x;
-    const float* x = fr.xyz + (size_t)f * fr.frame_stride;
-    const float* src[3] = { x, x + fr.axis_stride, x + 2 * fr.axis_stride };
-    float* o = out + ((size_t)f * n_groups + g) * 3;
-    const uint32_t b = off[g], count = off[g + 1] - b;
-    if (count == 0) { if (lane == 0) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; } return; }   // md_util_com_compute :8168
-    periodic_com_warp(src, cells[f], idx + b, count, mass, o, lane);
-}
-
-void launch_groups_com_pbc(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, const uint32_t* d_off, uint32_t n_groups, const float* d_mass, float* d_out, cudaStream_t s) {
-    if (!fr.count || !n_groups) return;
-    k_groups_com_pbc<<<dim3(n_groups, fr.count), 32, 0, s>>>(fr, d_cells, d_idx, d_off, n_groups, d_mass, d_out);
-    note_launch("k_groups_com_pbc", s);
-}
-
 void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s) {
     if (!fr.count || !count) return;
     k_arg_com<<<fr.count, 32, 0, s>>>(fr, d_cells, d_idx, count, d_mass, d_out, arg);
@@ -412,8 +393,10 @@ __global__ void __launch_bounds__(256) k_min_distance(BatchFrames fr, const mdgp
 
 // distance_pair(a, b) (_distance_pair md_script_functions.inl:3972 -> md_util_distance_array md_util.c:8210): the na x nb matrix of a frame,
 // row (frame0 + f) of a [num_frames][na*nb] temporal; one thread per pair.
+// posa / posb (may be null): [B][na][3] / [B][nb][3] centres of mass when the argument was an ARRAY of selections (k_group_com: extract_com, no periodic treatment)
 __global__ void __launch_bounds__(256) k_distance_pair(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ ia, uint32_t na,
-                                                       const int32_t* __restrict__ ib, uint32_t nb, float* __restrict__ out, uint32_t frame0) {
+                                                       const int32_t* __restrict__ ib, uint32_t nb, const float* __restrict__ posa, const float* __restrict__ posb,
+                                                       float* __restrict__ out, uint32_t frame0) {
     const int f = blockIdx.y;
     const unsigned long long npairs = (unsigned long long)na * nb, p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
@@ -421,8 +404,11 @@ __global__ void __launch_bounds__(256) k_distance_pair(BatchFrames fr, const mdg
     const mdgpu_unitcell_t uc = cells[f];
     const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
     const float box[3][3] = { { (float)uc.x, 0.f, 0.f }, { (float)uc.xy, (float)uc.y, 0.f }, { (float)uc.xz, (float)uc.yz, (float)uc.z } };
-    const int a = ia[p / nb], b = ib[p % nb];
-    out[(size_t)(frame0 + f) * npairs + p] = pair_distance(x[a], y[a], z[a], x[b], y[b], z[b], uc.flags, ext, box);
+    const uint32_t i = (uint32_t)(p / nb), j = (uint32_t)(p % nb);
+    float pa[3], pb[3];
+    if (posa) { const float* q = posa + ((size_t)f * na + i) * 3; pa[0] = q[0]; pa[1] = q[1]; pa[2] = q[2]; } else { const int a = ia[i]; pa[0] = x[a]; pa[1] = y[a]; pa[2] = z[a]; }
+    if (posb) { const float* q = posb + ((size_t)f * nb + j) * 3; pb[0] = q[0]; pb[1] = q[1]; pb[2] = q[2]; } else { const int b = ib[j]; pb[0] = x[b]; pb[1] = y[b]; pb[2] = z[b]; }
+    out[(size_t)(frame0 + f) * npairs + p] = pair_distance(pa[0], pa[1], pa[2], pb[0], pb[1], pb[2], uc.flags, ext, box);
 }
 
 void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s) {
@@ -431,10 +417,11 @@ void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells,
     note_launch("k_min_distance", s);
 }
 
-void launch_distance_pair(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s) {
+void launch_distance_pair(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb,
+                          const float* d_posa, const float* d_posb, float* d_out, uint32_t frame0, cudaStream_t s) {
     const unsigned long long npairs = (unsigned long long)na * nb;
     if (!fr.count || !npairs) return;
-    k_distance_pair<<<dim3((unsigned)((npairs + 255) / 256), fr.count), 256, 0, s>>>(fr, d_cells, d_ia, na, d_ib, nb, d_out, frame0);
+    k_distance_pair<<<dim3((unsigned)((npairs + 255) / 256), fr.count), 256, 0, s>>>(fr, d_cells, d_ia, na, d_ib, nb, d_posa, d_posb, d_out, frame0);
     note_launch("k_distance_pair", s);
 }
 

@@ -194,6 +194,17 @@ class _Parser:
             elif t == ("id", "within"): return True
         return False
 
+    def groups_or_selection(self):
+        """residue(a:b) over several residues standing alone -> list of index arrays (array of selections); anything else -> one index array"""
+        save = self.i
+        if self.peek() == ("id", "residue"):
+            self.next(); self.expect("ch", "(")
+            off = np.asarray(self.sys.res_atom_offset); lo, hi = self._range(len(off) - 1); self.expect("ch", ")")
+            if self.peek() in (("ch", ","), ("ch", ")")) and hi - lo > 1:
+                return [np.arange(off[r], off[r + 1], dtype=np.int32) for r in range(lo, hi)]
+        self.i = save
+        return self.selection()
+
     def number(self) -> float:
         return float(self.expect("num")[1])
 
@@ -233,7 +244,10 @@ class _Parser:
             p = api.sdf(ident, st, trg, c)
         elif proc in ("density_x", "density_y", "density_z"):
             p = api.density(ident, "xyz".index(proc[-1]), self.selection())
-        elif proc in ("distance_min", "distance_max", "distance_pair"):
+        elif proc == "distance_pair":   # an array of selections (residue(a:b) over several residues) is one centre of mass per selection
+            a = self.groups_or_selection(); self.expect("ch", ","); b = self.groups_or_selection()
+            p = api.distance_pair(ident, a, b)
+        elif proc in ("distance_min", "distance_max"):
             a = self.single_selection(); self.expect("ch", ","); b = self.single_selection()
             p = {"distance_min": api.distance_min, "distance_max": api.distance_max, "distance_pair": api.distance_pair}[proc](ident, a, b)
         elif proc == "count":   # count(within(radius, selection)): the one dynamic selection the device path evaluates
