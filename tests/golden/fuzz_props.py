@@ -39,7 +39,9 @@ def main(cases=40, seed=3):
             sdf_ok = (fl & 28) == 28
             script = (f"r = rdf(element('O'), element('O'), {cut}); rh = rdf(element('H'), element('O'), {cmin}:{cut}); rc = rdf(residue(1:{nres}), element('H'), {cut}); "
                       f"dz = density_z(element('O')); dy = density_y(element('H')); d = distance({a1},{a2}); dg = distance(atom({a1}:{a2}), residue(2)); "
-                      f"an = angle({a1},{a1 + 1},{a2}); dmn = distance_min(atom({a1}:{a2}), residue(1)); " + f"rm = rmsd(residue(1:{nres})); " + f"cw = count(within({min(cut, 6.0)}, residue(1)));"
+                      f"an = angle({a1},{a1 + 1},{a2}); dmn = distance_min(atom({a1}:{a2}), residue(1)); " + f"rm = rmsd(residue(1:{nres})); " + f"cw = count(within({min(cut, 6.0)}, residue(1))); "
+                      f"dp = distance_pair(atom({a1}:{a1 + 4}), residue(1)); cm = com(atom({a1}:{a2})); pl = plane(atom({a1}:{a2})); cwr = count(within({cmin}:{min(cut, 6.0)}, residue(1))); "
+                      f"cwo = count(element('O') and within({min(cut, 6.0)}, residue(2))); anc = angle(2,1,3) in residue(1:{nres}); dpg = distance_pair(residue(1:{nres}), residue({nres + 1}:{nres + 3}));"
                       + (f" v = sdf(residue(1:{nres}), element('O'), {min(cut, 0.45 * L):.2f});" if sdf_ok else ""))
             p = subprocess.run([HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", out, "--perframe", f"0:{F}", "--full", f"0:{F}"], capture_output=True, text=True)
             if p.returncode != 0: print("reference failed on case", c, script); bad += 1; continue
@@ -67,6 +69,14 @@ def main(cases=40, seed=3):
                 chk(O.min_distance(x, y, zz, A(a1, a2), groups[0], cell) == R["dmn"].full[f], "dmn", f)
                 chk(O.rmsd_frame(x, y, zz, fr2[0], s["mass"], np.concatenate(groups), s["conn_off"], s["conn_idx"], cell) == R["rm"].full[f], "rm", f)
                 chk(len(O.within(x, y, zz, groups[0], min(cut, 6.0), cell)) == int(R["cw"].full[f]), "cw", f)
+                chk(np.array_equal(O.distance_pair(x, y, zz, A(a1, a1 + 4), groups[0], cell), R["dp"].full[15 * f:15 * f + 15]), "dp", f)
+                chk(np.array_equal(O.arg_position(x, y, zz, s["mass"], A(a1, a2), cell), R["cm"].full[3 * f:3 * f + 3]), "cm", f)
+                chk(np.array_equal(O.plane_frame(x, y, zz, A(a1, a2), s["conn_off"], s["conn_idx"], cell), R["pl"].full[4 * f:4 * f + 4]), "pl", f)
+                chk(len(O.within(x, y, zz, groups[0], min(cut, 6.0), cell, rmin=cmin)) == int(R["cwr"].full[f]), "cwr", f)
+                chk(len(np.intersect1d(O.within(x, y, zz, np.arange(co[1], co[2], dtype=np.int32), min(cut, 6.0), cell), o)) == int(R["cwo"].full[f]), "cwo", f)
+                chk(np.array_equal(np.array([O.angle(x, y, zz, co[r] + 1, co[r], co[r] + 2) for r in range(nres)], np.float32), R["anc"].full[nres * f:nres * f + nres]), "anc", f)
+                g2 = [np.arange(co[r], co[r + 1], dtype=np.int32) for r in range(nres, nres + 3)]
+                chk(np.array_equal(O.distance_pair_args(x, y, zz, s["mass"], groups, g2, cell), R["dpg"].full[3 * nres * f:3 * nres * (f + 1)]), "dpg", f)
                 if sdf_ok:
                     vol, nn = O.sdf_frame(x, y, zz, fr2[0], s["mass"], np.stack(groups), o, s["conn_off"], s["conn_idx"], cell, float(f"{min(cut, 0.45 * L):.2f}"))
                     chk(np.array_equal(vol, R["v"].perframe[f]), "v", f)
