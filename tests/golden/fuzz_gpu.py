@@ -69,7 +69,8 @@ def main(cases=40, seed=1):
             chk(plan.property_data("dmn").values[f] == O.min_distance(x, y, z, np.arange(a1, a2 + 1), groups[0], oc), "dmn", f)
             co, ci = np.asarray(sysm.conn_offset, np.uint32), np.asarray(sysm.conn_idx, np.int32)
             chk(plan.property_data("rm").values[f] == O.rmsd_frame(x, y, z, fr[0], sysm.mass, allg, co, ci, oc), "rm", f)
-            chk(np.array_equal(plan.property_data("dp").values[15 * f:15 * f + 15], O.distance_pair(x, y, z, sel[:5], groups[0], oc)), "dp", f)
+            npp = 3 * len(sel[:5])   # sel holds 4..30 atoms
+            chk(np.array_equal(plan.property_data("dp").values[npp * f:npp * f + npp], O.distance_pair(x, y, z, sel[:5], groups[0], oc)), "dp", f)
             chk(np.array_equal(plan.property_data("cm").values[3 * f:3 * f + 3], O.arg_position(x, y, z, sysm.mass, sel, oc)), "cm", f)
             chk(np.array_equal(plan.property_data("pl").values[4 * f:4 * f + 4], O.plane_frame(x, y, z, sel, co, ci, oc)), "pl", f)
             wref = O.within(x, y, z, groups[0], wr, oc)
