@@ -243,9 +243,17 @@ int mdgpu_plan_property_frame_counts(mdgpu_plan* plan, size_t prop, uint32_t fra
 /* Completed-frame bitmask (md_script_eval_frame_mask :6655): 1 bit per frame, little-endian u64 words. */
 int mdgpu_plan_frame_mask(mdgpu_plan* plan, uint64_t* out_words, size_t num_words);
 
-/* Multi-GPU: device pointer + byte size of a property's integer accumulator so the caller's communicator
+/* Multi-GPU: device pointer + byte size of a property's accumulator (u64 bins, u32 voxels, f32 temporal rows) so the caller's communicator
  * (NCCL via torch.distributed in bench.py) can all-reduce it in place; then mdgpu_plan_set_frames_accumulated. */
 int mdgpu_plan_property_accum_ptr(mdgpu_plan* plan, size_t prop, void** d_ptr, size_t* bytes, uint32_t* elem_bytes);
+/* Temporals shard by rows: accum_ptr returns their float32 [num_frames][len] buffer (rows of frames this plan did not evaluate are zero, so a
+ * SUM all-reduce merges the shards exactly); afterwards the frames the other ranks evaluated are declared done, so that min/max, ranges and
+ * the per-frame aggregates cover them. */
+int mdgpu_plan_mark_frames_done(mdgpu_plan* plan, uint32_t frame_beg, uint32_t count);
+/* Per-frame integer rows of a distribution / volume property — which = 0: pair / hit total per frame (rdf weights come from the last frame's),
+ * 1 / 2: smallest / largest bin of the frame (min_value / max_value). [num_frames] entries of elem_bytes each, zero where this plan did not
+ * evaluate, so the same SUM all-reduce merges them when every rank's plan spans the global frame range. d_ptr = NULL if the property has none. */
+int mdgpu_plan_property_frame_rows(mdgpu_plan* plan, size_t prop, uint32_t which, void** d_ptr, size_t* bytes, uint32_t* elem_bytes);
 int mdgpu_plan_set_frames_accumulated(mdgpu_plan* plan, size_t prop, uint64_t frames);
 
 /* Kernel bookkeeping for bench.py: launches issued by this library since the counter was last reset, and

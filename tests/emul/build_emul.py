@@ -119,7 +119,9 @@ def build_library() -> str:
     procs.append(("fake_cudart.cpp", subprocess.Popen(["g++", *flags[:6], f"-I{CUDA_INC}", *(["-fsanitize=address", "-g"] if asan else []), *(["-fsanitize=thread", "-g"] if tsan else []), "-c", os.path.join(HERE, "fake_cudart.cpp"), "-o", fobj])))
     for src, p in procs:
         if p.wait() != 0: raise RuntimeError(f"g++ failed on {src}")
-    subprocess.check_call(["g++", "-shared", "-o", out, *objs, "-lpthread", "-lm"] + (["-fsanitize=address"] if asan else []) + (["-fsanitize=thread"] if tsan else []))
+    # -Bsymbolic: the library's CUDA runtime calls must bind to fake_cudart.o inside it even when the process already holds the real
+    # libcudart in its global scope (torch does that)
+    subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", out, *objs, "-lpthread", "-lm"] + (["-fsanitize=address"] if asan else []) + (["-fsanitize=thread"] if tsan else []))
     return out
 
 

@@ -139,6 +139,8 @@ def lib() -> C.CDLL:
         L.mdgpu_plan_property_aggregate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.mdgpu_plan_property_frame_counts.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
         L.mdgpu_plan_frame_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.mdgpu_plan_mark_frames_done.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.mdgpu_plan_property_frame_rows.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
         L.mdgpu_plan_property_accum_ptr.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
         L.mdgpu_plan_set_frames_accumulated.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64]
         L.mdgpu_launch_count.argtypes = [C.c_bool]
@@ -551,6 +553,16 @@ class Plan:
         i = self._index(name); p = C.c_void_p(); b = C.c_size_t(); e = C.c_uint32()
         _check(lib().mdgpu_plan_property_accum_ptr(self._h, i, C.byref(p), C.byref(b), C.byref(e)))
         return int(p.value), int(b.value), int(e.value)
+
+    def frame_rows(self, name, which: int):
+        """(device pointer, bytes, element bytes) of a per-frame integer row (0: totals, 1: frame minimum, 2: frame maximum), or (0, 0, 0)"""
+        p = C.c_void_p(); n = C.c_size_t(); eb = C.c_uint32()
+        _check(lib().mdgpu_plan_property_frame_rows(self._h, self._index(name), int(which), C.byref(p), C.byref(n), C.byref(eb)))
+        return int(p.value or 0), int(n.value), int(eb.value)
+
+    def mark_frames_done(self, frame_beg: int, count: int):
+        """declare frames evaluated by other ranks done (after their temporal rows were reduced into this plan's buffers)"""
+        _check(lib().mdgpu_plan_mark_frames_done(self._h, int(frame_beg), int(count)))
 
     def set_frames_accumulated(self, name, frames: int):
         _check(lib().mdgpu_plan_set_frames_accumulated(self._h, self._index(name), frames))

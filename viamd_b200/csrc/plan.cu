@@ -1228,7 +1228,28 @@ int mdgpu_plan_property_accum_ptr(mdgpu_plan* p, size_t prop, void** d_ptr, size
     Prop& pr = p->props[prop];
     if (pr.d_acc) { *d_ptr = pr.d_acc; *bytes = sizeof(unsigned long long) * MDGPU_DIST_BINS; if (elem_bytes) *elem_bytes = 8; }
     else if (pr.d_vol) { *d_ptr = pr.d_vol; *bytes = sizeof(uint32_t) * MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM; if (elem_bytes) *elem_bytes = 4; }
-    else return fail(MDGPU_ERR_UNSUPPORTED, "property '%s' has no integer accumulator", pr.name.c_str());
+    else if (pr.d_temporal) { *d_ptr = pr.d_temporal; *bytes = sizeof(float) * p->num_frames * pr.len; if (elem_bytes) *elem_bytes = 4; }   // float rows, zero where not evaluated
+    else return fail(MDGPU_ERR_UNSUPPORTED, "property '%s' has no accumulator", pr.name.c_str());
+    return 0;
+}
+
+int mdgpu_plan_property_frame_rows(mdgpu_plan* p, size_t prop, uint32_t which, void** d_ptr, size_t* bytes, uint32_t* elem_bytes) {
+    if (!p || prop >= p->props.size() || !d_ptr || !bytes || !elem_bytes) return fail(MDGPU_ERR_INVALID_ARG, "invalid argument");
+    Prop& pr = p->props[prop]; const size_t F = p->num_frames;
+    *d_ptr = nullptr; *bytes = 0; *elem_bytes = 0;
+    if (which == 0 && pr.d_frame_total) { *d_ptr = pr.d_frame_total; *elem_bytes = 8; }
+    else if (which == 1 && pr.d_frame_min) { *d_ptr = pr.d_frame_min; *elem_bytes = 4; }
+    else if (which == 1 && pr.d_frame_min64) { *d_ptr = pr.d_frame_min64; *elem_bytes = 8; }
+    else if (which == 2 && pr.d_frame_max) { *d_ptr = pr.d_frame_max; *elem_bytes = 4; }
+    else if (which == 2 && pr.d_frame_max64) { *d_ptr = pr.d_frame_max64; *elem_bytes = 8; }
+    *bytes = (size_t)*elem_bytes * F;
+    return 0;   // a property without that row returns a null pointer
+}
+
+int mdgpu_plan_mark_frames_done(mdgpu_plan* p, uint32_t frame_beg, uint32_t count) {
+    if (!p || (size_t)frame_beg + count > p->num_frames) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_mark_frames_done: frame range out of bounds");
+    { std::lock_guard<std::mutex> lk(p->mask_mutex); for (uint32_t f = frame_beg; f < frame_beg + count; ++f) p->frame_mask[f >> 6] |= 1ull << (f & 63); }
+    p->dirty = true;
     return 0;
 }
 

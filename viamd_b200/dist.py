@@ -45,21 +45,36 @@ def rdf_weights(total_pairs: int, cutoff_min: float, cutoff_max: float) -> np.nd
     return w
 
 
-def allreduce_plan(plan: api.Plan, total_frames: int, group=None, device=None):
-    """The single exchange step for a frame-sharded evaluation. Reduces every distribution/volume accumulator of `plan`
-    in place on the device (NCCL) and tells the plan the global frame count. Returns {name: merged extras}."""
+def allreduce_plan(plan: api.Plan, total_frames: int, group=None, device=None, view=None):
+    """The single exchange step for a frame-sharded evaluation. Reduces every accumulator of `plan` (integer bins / voxels / mass sums; float rows
+    of temporals, which are disjoint between ranks)
+    in place on the device (NCCL) and tells the plan the global frame count. Returns {name: merged extras}.
+    `view(ptr, count, typestr)` turns an accumulator into the tensor handed to all_reduce; the default wraps device memory."""
     import torch
     import torch.distributed as dist
     plan.sync()
     extras = {}
-    dev = torch.device("cuda", plan.device if device is None else device)
+    dev = torch.device("cuda", plan.device if device is None else device) if view is None else None
+    if view is None:
+        view = lambda ptr, n, typestr: torch.as_tensor(_CudaView(ptr, n, typestr), device=dev)
+    integer_ops = (api.OP_RDF, api.OP_SDF, api.OP_DENSITY_X, api.OP_DENSITY_Y, api.OP_DENSITY_Z)
+    have_temporal = any(p.op not in integer_ops for p in plan.properties)
+    if have_temporal and plan.num_frames != int(total_frames):
+        raise ValueError("temporal properties are exchanged by global frame index: create every rank's plan with the global frame count "
+                         "and evaluate its shard at its global offsets (frame_shard)")
     for p in plan.properties:
-        if p.op not in (api.OP_RDF, api.OP_SDF, api.OP_DENSITY_X, api.OP_DENSITY_Y, api.OP_DENSITY_Z):
-            continue
         ptr, nbytes, eb = plan.accum_ptr(p.name)
-        view = _CudaView(ptr, nbytes // eb, "<i8" if eb == 8 else "<i4")
-        t = torch.as_tensor(view, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        plan.set_frames_accumulated(p.name, int(total_frames))
-    torch.cuda.synchronize(dev)
+        if p.op in integer_ops:   # bins / voxels / fixed-point sums: exact integer sums, then the mean over the global frame count
+            t = view(ptr, nbytes // eb, "<i8" if eb == 8 else "<i4")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            plan.set_frames_accumulated(p.name, int(total_frames))
+            if plan.num_frames == int(total_frames):   # plans over the global frame range: the per-frame rows (totals -> rdf weights, frame min / max) are disjoint too
+                for which in (0, 1, 2):
+                    rptr, rbytes, reb = plan.frame_rows(p.name, which)
+                    if rptr: dist.all_reduce(view(rptr, rbytes // reb, "<i8" if reb == 8 else "<i4"), op=dist.ReduceOp.SUM, group=group)
+        else:                     # temporals: disjoint rows, zero elsewhere -> x + 0 merges them exactly
+            t = view(ptr, nbytes // 4, "<f4")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    if have_temporal: plan.mark_frames_done(0, int(total_frames))
+    if dev is not None: torch.cuda.synchronize(dev)
     return extras
