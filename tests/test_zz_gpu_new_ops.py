@@ -4,6 +4,8 @@ sources: every test here passes through the C ABI against tests/emul's emulated 
 the complete, GPU-validated tests/test_gpu_parity.py passes under that emulation too), also with AddressSanitizer watching the "device"
 buffers. The file sorts last on purpose: with `pytest -x` every test that has already passed on the GPU runs before these.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -11,6 +13,15 @@ import oracle_lib as O
 from helpers import load_golden, cell_from_row, golden_system, sel_element, vb_system, vb_cell
 
 pytestmark = pytest.mark.gpu
+
+
+def _same(a, b):
+    """Floats that go through a fit (svd3) or a double sin / cos / atan2: bit-equal when the library's sources run on the CPU (tests/emul: the
+    reference's own libm), within the north-star float tolerance on the device (CUDA's double libm may differ in the last bit)."""
+    import viamd_b200.api as api
+    a = np.asarray(a, np.float32); b = np.asarray(b, np.float32)
+    if "emul" in os.path.basename(api.LIB_PATH): return bool(np.array_equal(a, b))
+    return bool(np.allclose(a, b, rtol=1e-5, atol=1e-6))
 
 
 def _plan(g, s, src, **kw):
@@ -29,9 +40,9 @@ def test_rmsd_goldens_bitexact():
     plan, cells = _plan(g, s, "rm = rmsd(residue(1:10)); d = distance(1,10);")
     plan.eval_host_frames(g["frames"], cells, 0)
     d = plan.property_data("rm")
-    assert np.array_equal(d.values, g["rm__full"]), (d.values, g["rm__full"])
+    assert _same(d.values, g["rm__full"]), (d.values, g["rm__full"])
     mn, mx, r0, r1 = g["rm__meta"]
-    assert d.min_value == mn and d.max_value == mx and d.min_range[0] == r0 and d.max_range[0] == r1
+    assert _same([d.min_value, d.max_value, d.min_range[0], d.max_range[0]], [mn, mx, r0, r1])
     assert np.array_equal(plan.property_data("d").values, g["d__full"])
     plan.close()
 
@@ -39,14 +50,14 @@ def test_rmsd_goldens_bitexact():
     g = load_golden("ala50.npz"); s = golden_system(g)
     plan, cells = _plan(g, s, "rma = rmsd(residue(1:15));", batch_frames=16)
     assert plan.eval_frame_range(vb.ArrayTrajectory(g["frames"], cells), 0, g["frames"].shape[0])
-    assert np.array_equal(plan.property_data("rma").values, g["rma__full"])
+    assert _same(plan.property_data("rma").values, g["rma__full"])
     plan.close()
 
     g = load_golden("tric6.npz"); s = golden_system(g); r = load_golden("tric6_rmsd.npz")
     plan, cells = _plan(g, s, str(r["script"]))
     plan.eval_host_frames(g["frames"], cells, 0)
     for key in ("rmt", "rma", "rmo"):
-        assert np.array_equal(plan.property_data(key).values, r[f"{key}__full"]), key
+        assert _same(plan.property_data(key).values, r[f"{key}__full"]), key
     plan.close()
 
 
@@ -64,7 +75,7 @@ def test_rmsd_oracle_larger_and_batched():
     mass = np.asarray(sysm.mass, np.float32)
     for f in range(F):
         want = O.rmsd_frame(*frames[f], frames[0], mass, idx, np.asarray(sysm.conn_offset, np.uint32), np.asarray(sysm.conn_idx, np.int32), ocell)
-        assert got[f] == want, (f, got[f], want)
+        assert _same(got[f], want), (f, got[f], want)
     plan.close()
 
 
@@ -140,11 +151,11 @@ def test_com_and_plane_goldens():
         for key in ("c", "ca", "ci", "pl", "plo"):
             k = f"{tag}_{key}"; d = plan.property_data(key)
             assert tuple(d.dim[:2]) == tuple(p[k + "__dim"][:2])
-            assert np.array_equal(d.values, p[k + "__full"]), (k, d.values[:8], p[k + "__full"][:8])
+            assert _same(d.values, p[k + "__full"]), (k, d.values[:8], p[k + "__full"][:8])
             mn, mx, r0, r1 = p[k + "__meta"]
-            assert d.min_value == mn and d.max_value == mx and d.min_range[0] == r0 and d.max_range[0] == r1
+            assert _same([d.min_value, d.max_value, d.min_range[0], d.max_range[0]], [mn, mx, r0, r1])
             agg = plan.aggregate(key)
-            assert np.array_equal(agg["mean"], p[k + "__mean"]) and np.array_equal(agg["var"], p[k + "__var"]) and np.array_equal(agg["ext"], p[k + "__ext"]), k
+            assert _same(agg["mean"], p[k + "__mean"]) and _same(agg["var"], p[k + "__var"]) and _same(agg["ext"], p[k + "__ext"]), k
         plan.close()
     import viamd_b200 as vb
     with pytest.raises(vb.MdgpuError):   # "need at least 3 to compute a plane" (:4815)
