@@ -1,5 +1,5 @@
 """GPU tests of the device paths written after this round's GPU budget was spent: rmsd, distance_pair + the multi-valued temporal container,
-com, plane, count(within()). At the time of writing they have not run on a B200; what stands behind them is the CPU execution of the same
+com, plane, count(within()). They first ran on a B200 in the round's last GPU call (profiles/r03a_newops_gpu_tests.log, 16 passed); they were written against the CPU execution of the same
 sources: every test here passes through the C ABI against tests/emul's emulated build of the whole library (tests/test_emulated_library.py;
 the complete, GPU-validated tests/test_gpu_parity.py passes under that emulation too), also with AddressSanitizer watching the "device"
 buffers. The file sorts last on purpose: with `pytest -x` every test that has already passed on the GPU runs before these.
