@@ -209,6 +209,46 @@ def shapes(tmp):
     np.savez_compressed(os.path.join(HERE, "shapes.npz"), **out)
 
 
+def water32_full(tmp):
+    """BASELINE configs 2 + 3 at FULL size from the strict reference: water n=32 (98 304 atoms), seed 1234, frames 0..1:
+    r = rdf(element('O'), element('O'), 10.0) per-frame raw bins + weights, v = sdf(residue(1:1000), element('O'), 10.0) per-frame raw
+    voxels (sparse: ~3e5 of 2 097 152 per frame). Coordinates are not stored — the tests regenerate them with the same generator
+    (viamd_b200/csrc/synth.h) and check the sha256 kept here."""
+    import hashlib
+    n, seed, F = 32, 1234, 2
+    gro, raw = os.path.join(tmp, "w32.gro"), os.path.join(tmp, "w32.raw")
+    run(SYNTH, "water-gro", str(n), str(seed), gro); run(SYNTH, "water-raw", str(n), str(seed), str(F), raw)
+    script = "r = rdf(element('O'), element('O'), 10.0); v = sdf(residue(1:1000), element('O'), 10.0);"
+    o = os.path.join(tmp, "w32.out")
+    run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
+    frames, cells, flags = refio.read_raw_traj(raw)
+    out = dict(script=np.array(script), n=np.int32(n), seed=np.int32(seed), cells=cells, cell_flags=flags,
+               frames_sha256=np.array([hashlib.sha256(np.ascontiguousarray(f).tobytes()).hexdigest() for f in frames]))
+    pack(out, refio.read_refout(o), list(range(F)))
+    np.savez_compressed(os.path.join(HERE, "water32_full.npz"), **out)
+
+
+def water12_avg(tmp):
+    """Long-run AVERAGED results (the reference's float cumulative moving average, md_script.c:5909-5955, one thread = frame order):
+    water n=12 (5184 atoms), seed 4242, 4096 frames: rdf bins + weights, density_z bins, sdf voxels (every 16th non-zero voxel + the sum
+    over all voxels, to keep the fixture small). Pins the 1e-5 bar of averaged values at the frame counts BASELINE's configs use."""
+    n, seed, F = 12, 4242, 4096
+    gro, raw = os.path.join(tmp, "w12.gro"), os.path.join(tmp, "w12.raw")
+    run(SYNTH, "water-gro", str(n), str(seed), gro); run(SYNTH, "water-raw", str(n), str(seed), str(F), raw)
+    script = "r = rdf(element('O'), element('O'), 8.0); v = sdf(residue(1:100), element('O'), 6.0); dz = density_z(element('O'));"
+    o = os.path.join(tmp, "w12.out")
+    run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", script, "--out", o, "--full", f"0:{F}", "--threads", "1")
+    props = refio.read_refout(o)
+    out = dict(script=np.array(script), n=np.int32(n), seed=np.int32(seed), num_frames=np.int32(F))
+    for name in ("r", "dz"):
+        out[f"{name}__full"] = props[name].full
+        m = props[name].meta[(1, 0)]; out[f"{name}__meta"] = np.array([m["min_value"], m["max_value"], m["min_range"][0], m["max_range"][0]], np.float32)
+    v = props["v"].full; nz = np.nonzero(v)[0].astype(np.uint32)
+    out["v__nnz"] = np.int64(len(nz)); out["v__sum"] = np.float64(v.astype(np.float64).sum())
+    out["v__sample_idx"] = nz[::16]; out["v__sample_val"] = v[nz[::16]]
+    np.savez_compressed(os.path.join(HERE, "water12_avg.npz"), **out)
+
+
 def _write_gro(path, n, L):
     with open(path, "w") as f:
         f.write("synthetic\n%d\n" % n)
@@ -257,7 +297,11 @@ def xtc_cases(tmp):
 
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    only = sys.argv[1:]   # e.g. `python make_golden.py water32_full water12_avg` regenerates just those
+    gens = dict(water6=water6, ala50=ala50, membrane6=membrane6, tric6=tric6, tric6_rmsd=tric6_rmsd, pairs6=pairs6, shapes=shapes, xtc_cases=xtc_cases,
+                water32_full=water32_full, water12_avg=water12_avg)
     with tempfile.TemporaryDirectory() as tmp:
-        water6(tmp); ala50(tmp); membrane6(tmp); tric6(tmp); tric6_rmsd(tmp); pairs6(tmp); shapes(tmp); xtc_cases(tmp)
-    for f in ("water6.npz", "ala50.npz", "membrane6.npz", "tric6.npz", "tric6_rmsd.npz", "pairs6.npz", "shapes.npz", "xtc_cases.npz"):
+        for name, fn in gens.items():
+            if not only or name in only: fn(tmp)
+    for f in (n + ".npz" for n in gens if not only or n in only):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

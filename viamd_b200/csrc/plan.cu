@@ -13,6 +13,9 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <condition_variable>
+#include <functional>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -92,6 +95,9 @@ struct PropScratch {   // per (stream slot, property)
 
 struct Slot {
     cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; bool busy = false;
+    bool owned = false;                        // a caller thread holds the slot (acquire_slot / release_slot); guarded by mdgpu_plan::slot_mutex
+    cudaEvent_t copied = nullptr;              // recorded after the batch's host->device copy: the caller's source buffer is free again
+    int* h_err = nullptr;                      // pinned mirror of d_err, copied at the end of every batch (read when the slot is retired)
     float* d_frames = nullptr; float* h_frames = nullptr;      // staging for host-resident frames
     mdgpu_unitcell_t* d_cells = nullptr; mdgpu_unitcell_t* h_cells = nullptr;
     int* d_err = nullptr;

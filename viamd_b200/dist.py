@@ -75,6 +75,8 @@ def allreduce_plan(plan: api.Plan, total_frames: int, group=None, device=None, v
         else:                     # temporals: disjoint rows, zero elsewhere -> x + 0 merges them exactly
             t = view(ptr, nbytes // 4, "<f4")
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    if have_temporal: plan.mark_frames_done(0, int(total_frames))
+    # plans over the global frame range: every rank now holds every frame's rows, so min / max, ranges, aggregates and the rdf weights (pair
+    # total of the globally last frame) must cover all of them — also when the plan has no temporal property
+    if plan.num_frames == int(total_frames): plan.mark_frames_done(0, int(total_frames))
     if dev is not None: torch.cuda.synchronize(dev)
     return extras
