@@ -179,7 +179,12 @@ typedef struct mdgpu_plan_options_t {
     uint32_t keep_frame_results;  /* 1: retain raw per-frame integer bins of distributions (parity tests) */
     uint32_t cell_capacity;       /* cells per frame the cell lists are sized for; 0 = 2x the initial frame's grid */
     uint32_t rdf_variant;         /* kernel variant selector for experiments; 0 = default */
-    uint32_t reserved[3];
+    uint32_t ingest_mode;         /* host ingest (mdgpu_eval_host_frames / _trajectory): 0 = copy only the atoms the properties read when they are
+                                   * less than 3/4 of the system (gathered into pinned staging by the ingest threads), 1 = always whole frames */
+    uint32_t ingest_threads;      /* host threads that gather frames into pinned staging; 0 = default (min(16, cores / 2)) */
+    uint32_t num_devices;         /* > 1: ONE process drives several GPUs (VIAMD is one process): contiguous frame blocks per device, accumulators
+                                   * merged onto devices[0] by one NCCL reduce at mdgpu_plan_sync; `device` is then ignored */
+    int32_t  devices[16];         /* CUDA ordinals when num_devices > 1 */
 } mdgpu_plan_options_t;
 
 const char* mdgpu_last_error(void);
@@ -212,7 +217,9 @@ int mdgpu_xtc_decode_frames(int device, const uint8_t* h_blob, const uint64_t* f
 
 /* The frame loop. Frames [frame_beg, frame_beg+count) are evaluated and accumulated.
  *  _device: coordinates already in HBM; frame i has x at d_xyz + i*frame_stride, y at + axis_stride, z at + 2*axis_stride (floats).
- *  _host  : same layout in host memory (pinned or pageable); copied host->device batch by batch inside the call.
+ *  _host  : same layout in host memory (pinned or pageable); copied host->device batch by batch inside the call — when it returns the
+ *            buffer has been read and may be refilled (the kernels may still be running: mdgpu_plan_sync waits for them). When the
+ *            properties read less than 3/4 of the atoms, only those atoms cross PCIe (options.ingest_mode).
  *  _trajectory: pulls frames through the md_trajectory_i-compatible interface with `loader_threads` readers
  *               (md_script_eval_frame_range semantics, md_script.c:6573-6612). */
 int mdgpu_eval_device_frames(mdgpu_plan* plan, const float* d_xyz, size_t frame_stride, size_t axis_stride,
@@ -223,11 +230,38 @@ int mdgpu_eval_trajectory(mdgpu_plan* plan, const mdgpu_trajectory_i* traj, uint
 
 /* Wait for all enqueued batches and fold device accumulators into the host-visible property data. */
 int mdgpu_plan_sync(mdgpu_plan* plan);
+
+/* Threading (md_script_eval_frame_range is re-entrant on one eval from many threads with disjoint ranges, src/task_system.cpp:73-87,
+ * mdlib/unittest/test_script.c:1352-1417): mdgpu_eval_trajectory / _host_frames / _device_frames and mdgpu_plan_sync may be called
+ * concurrently on one plan with disjoint frame ranges. Each call takes stream slots as they become free; results do not depend on the
+ * interleaving (integer accumulators, disjoint temporal rows).
+ *
+ * Result storage: by default the plan owns `values`. mdgpu_plan_bind_property_storage makes it write a property's values (and the per-frame
+ * aggregate arrays of a multi-valued temporal: mean[F], variance[F], extent[F][2]; may be NULL) into the caller's arrays instead — the
+ * md_script shim binds md_script_property_data_t::values (md_script.h:73-92), which VIAMD reads directly (src/main.cpp:1286-1303, 1524).
+ *
+ * Progress: with a callback installed, every completed batch publishes at once — its temporal rows are copied to the host values, running
+ * means of distributions / volumes are refreshed at most every 100 ms — and the callback is invoked (from the thread that retired the batch)
+ * with the batch's frame range; the shim sets md_script_eval_t::frame_mask bits there (md_script.c:5962-5964), so the UI sees partial
+ * results while the evaluation runs (src/main.cpp:1513-1524). */
+typedef void (*mdgpu_progress_fn)(void* user, uint32_t frame_beg, uint32_t frame_count);
+int mdgpu_plan_bind_property_storage(mdgpu_plan* plan, size_t prop, float* values, size_t num_values, float* agg_mean, float* agg_var, float* agg_ext);
+int mdgpu_plan_set_progress_callback(mdgpu_plan* plan, mdgpu_progress_fn fn, void* user);
+
+/* Pin the calling thread (and the threads it creates afterwards) to the CPUs next to `device` (sysfs local_cpulist of its PCI function), so
+ * that pinned staging it allocates and the ingest threads sit on the GPU's NUMA node. Returns the number of CPUs, or a negative status. */
+int mdgpu_bind_host_to_device(int device);
+
+/* Multi-device plans: milliseconds the last exchange step (NCCL reduce onto devices[0]) took on the root device, and how many ran. */
+int mdgpu_plan_exchange_stats(mdgpu_plan* plan, double* last_ms, uint64_t* count);
+/* Host-ingest facts of a plan: atoms copied per frame (= num_atoms unless the compact ingest is active) and the ingest thread count. */
+int mdgpu_plan_ingest_info(mdgpu_plan* plan, size_t* atoms_per_frame, uint32_t* threads);
 void mdgpu_plan_interrupt(mdgpu_plan* plan);   /* md_script_eval_interrupt :6663 */
 
 size_t mdgpu_plan_property_count(const mdgpu_plan* plan);
 int mdgpu_plan_property_index(const mdgpu_plan* plan, const char* name);
 int mdgpu_plan_property_data(mdgpu_plan* plan, size_t prop, mdgpu_property_data_t* out);   /* implies mdgpu_plan_sync */
+int mdgpu_plan_property_peek(mdgpu_plan* plan, size_t prop, mdgpu_property_data_t* out);   /* as last folded, waits for nothing (for progress callbacks) */
 
 /* Per-frame aggregates of a temporal with several values per frame (md_script_aggregate_t md_script.h:63-70, filled at md_script.c:5886-5890):
  * out_mean[num_frames], out_var[num_frames] (population variance), out_ext[num_frames][2] (min, max); any may be NULL. Implies mdgpu_plan_sync. */

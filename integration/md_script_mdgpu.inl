@@ -147,7 +147,13 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
             off[0] = 0; for (size_t i = 0; i < nsets; ++i) off[i + 1] = off[i] + (uint32_t)md_bitfield_popcount(&bf[i]);
             out->num_structures = nsets; out->structure_size = set_size; out->structure_offsets = off;
         }
-        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[1], NULL, NULL, args[1], alloc)) < 0) goto dynamic; out->idx_count[1] = (size_t)n;
+        {
+            size_t tsets = 0;
+            if ((n = mdgpu__arg_indices((int32_t**)&out->idx[1], &tsets, NULL, args[1], alloc)) < 0) goto dynamic; out->idx_count[1] = (size_t)n;
+            if (args[1]->data.type.base_type == TYPE_BITFIELD && tsets > 1) {   /* compute_rdf would use one centre of mass per bitfield (coordinate_extract) */
+                MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections as rdf target (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false;
+            }
+        }
         if (!(args[2]->flags & FLAG_CONSTANT)) goto dynamic;
         if (args[2]->data.type.base_type == TYPE_FRANGE) { const frange_t r = *(const frange_t*)args[2]->data.ptr; out->cutoff_min = r.beg; out->cutoff_max = r.end; }
         else { out->cutoff_min = 0.0f; out->cutoff_max = *(const float*)args[2]->data.ptr; }
@@ -234,7 +240,12 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
                 }
                 const int32_t v = *(const int32_t*)args[k]->data.ptr;
                 int32_t* idx = (int32_t*)md_alloc(alloc, sizeof(int32_t) * n_ctx);
-                for (size_t c = 0; c < n_ctx; ++c) idx[c] = (int32_t)ctx_bf[c].beg_bit + v - 1;
+                for (size_t c = 0; c < n_ctx; ++c) {   /* remap_index_to_context rejects indices outside the context (md_script_functions.inl:1023-1040) */
+                    if (v < 1 || (int64_t)ctx_bf[c].beg_bit + v - 1 >= (int64_t)ctx_bf[c].end_bit) {
+                        MD_LOG_ERROR("mdgpu: property '" STR_FMT "': supplied index (%d) is not within the range of context %zu", STR_ARG(ident), v, c); return false;
+                    }
+                    idx[c] = (int32_t)ctx_bf[c].beg_bit + v - 1;
+                }
                 out->idx[k] = idx; out->idx_count[k] = n_ctx;
             }
             return true;
@@ -328,3 +339,188 @@ static bool md_script_gpu_eval_frame_range(mdgpu_plan* plan, md_script_eval_t* e
     for (size_t i = 0; i < np; ++i) eval->property_data[i].fingerprint = fingerprint;
     return true;
 }
+
+
+/* =============================================================================================================================
+ * The dispatcher: md_script_eval_frame_range itself runs on libmdgpu (zero edits in md_script.c and in VIAMD).
+ * Active when md_script_mdgpu_pre.h was included before md_script.c (see md_script_mdgpu.c).
+ *
+ * One plan per md_script_eval_t, created lazily by the first md_script_eval_frame_range call on that eval (the eval does not know the system
+ * or the trajectory before, md_script.c:6506), kept in a small table keyed by the eval pointer, destroyed by md_script_eval_free.
+ *  - The plan writes straight into eval->property_data[i].values (mdgpu_plan_bind_property_storage): VIAMD keeps reading the arrays it
+ *    always read (src/main.cpp:1286-1303, 1524; density_volume.cpp:149-151).
+ *  - Re-entrant like the reference: N enkiTS threads call with disjoint ranges on one eval (src/task_system.cpp:73-87); each call creates its
+ *    own readers (md_script.c:5754), takes stream slots as they free up, and returns when its frames are evaluated.
+ *  - Every completed batch sets its bits in eval->frame_mask under eval->frame_lock (md_script.c:5962-5964) and refreshes min/max/ranges,
+ *    so the UI's concurrent reads (src/main.cpp:1513-1524) see progress; distributions / volumes are refreshed at most every 100 ms.
+ *  - md_script_eval_interrupt (:6663) also interrupts the plan (polled between batches); md_script_eval_clear_data (:6563) clears it.
+ *  - A script with a statement outside the lowered set is an error (MD_LOG_ERROR, false): the library has no CPU fallback. A host that wants
+ *    such scripts evaluated by the reference's own CPU code sets MDGPU_ALLOW_CPU_SCRIPTS=1; MDGPU_DISABLE=1 routes everything there.
+ *  - MDGPU_DEVICES="0,1,2,3" makes the plan span several GPUs of the box from this one process (frame blocks per device, one NCCL reduce).
+ * ============================================================================================================================= */
+#ifdef MD_SCRIPT_MDGPU_DROPIN
+#undef md_script_eval_frame_range
+#undef md_script_eval_clear_data
+#undef md_script_eval_free
+#undef md_script_eval_interrupt
+
+typedef struct mdgpu__entry_t {
+    md_script_eval_t* eval;
+    mdgpu_plan* plan;
+    int state;              /* 0 = free slot, 1 = GPU plan, 2 = this eval's script is evaluated by the reference's CPU code */
+} mdgpu__entry_t;
+
+#define MDGPU__MAX_EVALS 64
+static mdgpu__entry_t mdgpu__entries[MDGPU__MAX_EVALS];
+static md_mutex_t mdgpu__table_lock;
+static volatile int mdgpu__table_state = 0;   /* 0 = untouched, 1 = being initialised, 2 = ready */
+
+static void mdgpu__table_init(void) {
+    if (__sync_bool_compare_and_swap(&mdgpu__table_state, 0, 1)) { md_mutex_init(&mdgpu__table_lock); __sync_synchronize(); mdgpu__table_state = 2; }
+    while (mdgpu__table_state != 2) { /* another thread is initialising the lock */ }
+}
+
+static mdgpu__entry_t* mdgpu__find(const md_script_eval_t* eval) {   /* table lock held */
+    for (int i = 0; i < MDGPU__MAX_EVALS; ++i) if (mdgpu__entries[i].state && mdgpu__entries[i].eval == eval) return &mdgpu__entries[i];
+    return NULL;
+}
+
+static void mdgpu__copy_scalars(md_script_eval_t* eval, mdgpu_plan* plan) {
+    const size_t np = md_array_size(eval->property_data);
+    for (size_t i = 0; i < np; ++i) {
+        mdgpu_property_data_t d;
+        if (mdgpu_plan_property_peek(plan, i, &d) != 0) continue;
+        md_script_property_data_t* p = &eval->property_data[i];
+        p->min_value = d.min_value; p->max_value = d.max_value;
+        p->min_range[0] = d.min_range[0]; p->max_range[0] = d.max_range[0];
+    }
+}
+
+/* mdgpu_progress_fn: a batch has completed and its results are in eval->property_data */
+static void mdgpu__on_batch(void* user, uint32_t frame_beg, uint32_t frame_count) {
+    mdgpu__entry_t* e = (mdgpu__entry_t*)user;
+    md_script_eval_t* eval = e->eval;
+    mdgpu__copy_scalars(eval, e->plan);
+    md_mutex_lock(&eval->frame_lock);
+    for (uint32_t f = frame_beg; f < frame_beg + frame_count && f < eval->frame_count; ++f) md_bitfield_set_bit(&eval->frame_mask, f);
+    md_mutex_unlock(&eval->frame_lock);
+}
+
+static size_t mdgpu__device_list(int32_t* out, size_t cap) {
+    const char* env = getenv("MDGPU_DEVICES"); size_t n = 0;
+    if (!env) return 0;
+    while (*env && n < cap) { char* end = NULL; const long v = strtol(env, &end, 10); if (end == env) break; out[n++] = (int32_t)v; env = (*end == ',') ? end + 1 : end; }
+    return n;
+}
+
+/* the plan of this eval, created on first use; NULL with *cpu = true when the reference's own code evaluates this eval */
+static mdgpu_plan* mdgpu__plan_for(md_script_eval_t* eval, const md_script_ir_t* ir, const md_system_t* mol, bool* cpu, bool* failed) {
+    *cpu = false; *failed = false;
+    mdgpu__table_init();
+    md_mutex_lock(&mdgpu__table_lock);
+    mdgpu__entry_t* e = mdgpu__find(eval);
+    if (!e) {
+        for (int i = 0; i < MDGPU__MAX_EVALS && !e; ++i) if (!mdgpu__entries[i].state) e = &mdgpu__entries[i];
+        if (!e) { md_mutex_unlock(&mdgpu__table_lock); MD_LOG_ERROR("mdgpu: more than %d live md_script_eval_t objects", MDGPU__MAX_EVALS); *failed = true; return NULL; }
+        e->eval = eval; e->plan = NULL; e->state = 2;
+        const char* off = getenv("MDGPU_DISABLE");
+        if (!(off && off[0] == '1')) {
+            md_allocator_i* tmp = md_arena_allocator_create(md_get_heap_allocator(), MEGABYTES(1));
+            md_script_gpu_lowered_t low = {0};
+            mdgpu_plan* plan = NULL;
+            if (md_script_gpu_lower(&low, ir, tmp)) {
+                float* mass = (float*)md_alloc(tmp, sizeof(float) * (mol->atom.count ? mol->atom.count : 1));
+                md_atom_extract_masses(mass, 0, mol->atom.count, &mol->atom);                       /* as eval_properties does, md_script.c:5764 */
+                mdgpu_system_desc_t sd = {0};
+                sd.num_atoms = mol->atom.count; sd.atom_mass = mass;
+                sd.bond_conn_offset = mol->bond.conn.offset; sd.bond_conn_atom_idx = mol->bond.conn.atom_idx; sd.bond_conn_offset_count = mol->bond.conn.offset_count;
+                mdgpu_plan_options_t opt = {0};
+                opt.num_streams = 6;   /* concurrent callers each hold a slot while they decode their frames */
+                const size_t nd = mdgpu__device_list(opt.devices, 16);
+                if (nd > 1) opt.num_devices = (uint32_t)nd; else if (nd == 1) opt.device = opt.devices[0];
+                plan = mdgpu_plan_create(&sd, low.props, low.num_props, eval->frame_count, &opt);
+                if (!plan) MD_LOG_ERROR("mdgpu: %s", mdgpu_last_error());
+                const size_t np = md_array_size(eval->property_data);
+                for (size_t i = 0; plan && i < np; ++i) {   /* results go where VIAMD reads them */
+                    md_script_property_data_t* p = &eval->property_data[i];
+                    const bool agg = p->aggregate && p->aggregate->num_values == eval->frame_count;
+                    if (mdgpu_plan_bind_property_storage(plan, i, p->values, p->num_values, agg ? p->aggregate->population_mean : NULL,
+                                                         agg ? p->aggregate->population_var : NULL, agg ? (float*)p->aggregate->population_ext : NULL) != 0) {
+                        MD_LOG_ERROR("mdgpu: %s", mdgpu_last_error()); mdgpu_plan_destroy(plan); plan = NULL;
+                    }
+                }
+            }
+            md_arena_allocator_destroy(tmp);
+            if (plan) { e->plan = plan; e->state = 1; mdgpu_plan_set_progress_callback(plan, mdgpu__on_batch, e); }
+            else {
+                const char* allow = getenv("MDGPU_ALLOW_CPU_SCRIPTS");
+                if (!(allow && allow[0] == '1')) { e->state = 0; md_mutex_unlock(&mdgpu__table_lock); *failed = true; return NULL; }   /* no CPU fallback */
+                MD_LOG_INFO("mdgpu: this script is evaluated by the reference's CPU code (MDGPU_ALLOW_CPU_SCRIPTS=1)");
+            }
+        }
+    }
+    mdgpu_plan* plan = e->plan; *cpu = (e->state == 2);
+    md_mutex_unlock(&mdgpu__table_lock);
+    return plan;
+}
+
+bool md_script_eval_frame_range(md_script_eval_t* eval, const struct md_script_ir_t* ir, const struct md_system_t* mol, const struct md_trajectory_i* traj, uint32_t frame_beg, uint32_t frame_end) {
+    ASSERT(eval);
+    /* argument checks and messages of the reference (md_script.c:6576-6602) */
+    if (!ir)   { MD_LOG_ERROR("Script eval: Immediate representation was null"); return false; }
+    if (!mol)  { MD_LOG_ERROR("Script eval: Molecule was null"); return false; }
+    if (!traj) { MD_LOG_ERROR("Script eval: Trajectory was null"); return false; }
+    const uint32_t num_frames = (uint32_t)md_trajectory_num_frames(traj);
+    if (num_frames == 0) { MD_LOG_ERROR("Script eval: Trajectory was empty"); return false; }
+    if (frame_beg > frame_end || frame_end > num_frames) { MD_LOG_ERROR("Script eval: Invalid frame range"); return false; }
+    if (md_array_size(eval->property_data) == 0) { MD_LOG_INFO("Script eval: No properties present, nothing to evaluate"); return false; }
+
+    bool cpu = false, failed = false;
+    mdgpu_plan* plan = mdgpu__plan_for(eval, ir, mol, &cpu, &failed);
+    if (failed) return false;
+    if (cpu) return md_script_eval_frame_range__cpu(eval, ir, mol, traj, frame_beg, frame_end);
+
+    bool result = true;
+    if (!eval->interrupt && frame_end > frame_beg) {
+        const uint32_t span = frame_end - frame_beg;
+        const uint32_t readers = span >= 256 ? 8 : (span >= 64 ? 2 : 1);   /* a call over a short range is one of many concurrent ones: it is its own loader */
+        int rc = mdgpu_eval_trajectory(plan, (const mdgpu_trajectory_i*)traj, frame_beg, frame_end, readers);
+        if (rc == 0) rc = mdgpu_plan_sync(plan);                            /* this call's frames are evaluated and folded when it returns */
+        if (rc != 0 && rc != MDGPU_ERR_INTERRUPTED) { MD_LOG_ERROR("mdgpu: %s", mdgpu_last_error()); result = false; }
+        mdgpu__copy_scalars(eval, plan);
+        /* the frame-mask bits were set batch by batch (mdgpu__on_batch) */
+    }
+    const uint64_t fingerprint = generate_fingerprint();                    /* md_script.c:6604-6609 */
+    for (size_t i = 0; i < md_array_size(eval->property_data); ++i) eval->property_data[i].fingerprint = fingerprint;
+    return result;
+}
+
+void md_script_eval_clear_data(md_script_eval_t* eval) {
+    ASSERT(eval);
+    mdgpu__table_init();
+    md_mutex_lock(&mdgpu__table_lock);
+    mdgpu__entry_t* e = mdgpu__find(eval); mdgpu_plan* plan = e ? e->plan : NULL;
+    md_mutex_unlock(&mdgpu__table_lock);
+    if (plan) mdgpu_plan_clear(plan);          /* zeroes the device accumulators, the bound arrays and the plan's interrupt flag */
+    md_script_eval_clear_data__cpu(eval);      /* the reference's own clear has the last word on the host-side state */
+}
+
+void md_script_eval_interrupt(md_script_eval_t* eval) {
+    md_script_eval_interrupt__cpu(eval);
+    mdgpu__table_init();
+    md_mutex_lock(&mdgpu__table_lock);
+    mdgpu__entry_t* e = mdgpu__find(eval); mdgpu_plan* plan = e ? e->plan : NULL;
+    md_mutex_unlock(&mdgpu__table_lock);
+    if (plan) mdgpu_plan_interrupt(plan);
+}
+
+void md_script_eval_free(md_script_eval_t* eval) {
+    mdgpu__table_init();
+    md_mutex_lock(&mdgpu__table_lock);
+    mdgpu__entry_t* e = mdgpu__find(eval); mdgpu_plan* plan = NULL;
+    if (e) { plan = e->plan; e->plan = NULL; e->eval = NULL; e->state = 0; }
+    md_mutex_unlock(&mdgpu__table_lock);
+    if (plan) mdgpu_plan_destroy(plan);        /* before the arena that holds the bound arrays goes away */
+    md_script_eval_free__cpu(eval);
+}
+#endif /* MD_SCRIPT_MDGPU_DROPIN */

@@ -121,7 +121,16 @@ def build_library() -> str:
         if p.wait() != 0: raise RuntimeError(f"g++ failed on {src}")
     # -Bsymbolic: the library's CUDA runtime calls must bind to fake_cudart.o inside it even when the process already holds the real
     # libcudart in its global scope (torch does that)
-    subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", out, *objs, "-lpthread", "-lm"] + (["-fsanitize=address"] if asan else []) + (["-fsanitize=thread"] if tsan else []))
+    subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", out, *objs, "-lpthread", "-lm", "-ldl"] + (["-fsanitize=address"] if asan else []) + (["-fsanitize=thread"] if tsan else []))
+    return out
+
+
+def build_fake_nccl() -> str:
+    """tests/emul/build/libfakenccl.so: host-memory stand-in for the NCCL entry points the multi-device exchange binds (see fake_nccl.cpp)"""
+    out = os.path.join(HERE, "build", "libfakenccl.so"); src = os.path.join(HERE, "fake_nccl.cpp")
+    if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-o", out, src])
     return out
 
 

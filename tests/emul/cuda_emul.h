@@ -21,6 +21,7 @@
 #include <barrier>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -98,7 +99,11 @@ static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return emu
 static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) { return emul_fold(mask, v, 0xffffffffu, [](unsigned r, unsigned x, int) { return r < x ? r : x; }); }
 
 // run fn() as every thread of every block of the grid; blocks one after the other, the threads of a block concurrently
+// One launch at a time, process-wide: `__shared__` variables are single static copies, so kernels enqueued by different host threads
+// (concurrent callers of one plan, the per-device threads of a multi-device plan) must not overlap here as they may on a device.
+inline std::mutex& emul_launch_mutex() { static std::mutex m; return m; }
 static inline void emul_launch(dim3 grid, dim3 block, const std::function<void()>& fn) {
+    std::lock_guard<std::mutex> emul_guard(emul_launch_mutex());
     const int nthreads = (int)(block.x * block.y * block.z), nwarps = (nthreads + 31) / 32;
     for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
         EmulBlock blk; blk.bar = std::make_unique<std::barrier<>>(nthreads); blk.warps.resize(nwarps);

@@ -7,7 +7,8 @@
 #include <string.h>
 
 extern "C" {
-cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int* n) { const char* e = getenv("MDGPU_EMUL_DEVICES"); *n = e ? atoi(e) : 1; if (*n < 1) *n = 1; return cudaSuccess; }   // several "devices" share the heap
+cudaError_t cudaDeviceGetPCIBusId(char*, int, int) { return cudaErrorNotSupported; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) { *v = (a == cudaDevAttrMultiProcessorCount) ? 4 : 0; return cudaSuccess; }   // 4 "SMs": default batch of 4 frames
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }

@@ -105,3 +105,123 @@ def test_two_rank_frame_shards_merge_through_the_exchange_step():
         assert np.array_equal(o["dp_mean"], pz["w_dp__mean"]) and o["d_minmax"][0] == g["d__meta"][0] and o["d_minmax"][1] == g["d__meta"][1]
         assert o["mask"].all()
     assert np.array_equal(res[0]["r"], res[1]["r"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------------
+# Round-2 host logic: compact ingest, concurrent callers, per-batch publication into bound storage, several devices in one process.
+# ---------------------------------------------------------------------------------------------------------------------------------------------
+SCRIPT_MIX = ("r = rdf(element('O'), element('O'), 6.0); v = sdf(residue(1:20), element('O'), 5.0); dz = density_z(element('O')); "
+              "d = distance(1,10); dp = distance_pair(atom(1:5), atom(20:30)); rm = rmsd(residue(1:10)); a = angle(1,2,3) in residue(1:10); "
+              "dfar = distance(200, 401); cfar = com(500);")   # single atoms beyond the dense part of the compact space
+
+
+def _mix_results(plan):
+    import numpy as np
+    out = {k: plan.counts(k) for k in ("r", "v", "dz")}
+    for k in ("d", "dp", "rm", "a", "dfar", "cfar"): out[k] = plan.property_data(k).values.copy()
+    out["r_w"] = plan.property_data("r").weights.copy(); out["mask"] = plan.frame_mask()
+    out["dp_mean"] = plan.aggregate("dp")["mean"].copy()
+    out["minmax"] = np.array([[plan.property_data(k).min_value, plan.property_data(k).max_value] for k in ("r", "dz", "d", "dp")], np.float32)
+    return out
+
+
+def _golden_mix(api):
+    import viamd_b200 as vb
+    from helpers import load_golden, golden_system, vb_system, vb_cell
+    g = load_golden("water6.npz"); s = golden_system(g); sysm = vb_system(s); F = g["frames"].shape[0]
+    cells = [vb_cell(g["cells"][f], g["cell_flags"][f]) for f in range(F)]
+    return vb, g, sysm, F, cells
+
+
+def _same(a, b):
+    import numpy as np
+    assert a.keys() == b.keys()
+    for k in a: assert np.array_equal(a[k], b[k]), k
+
+
+def test_compact_ingest_copies_only_the_atoms_the_properties_read(emulated_library):
+    """Host ingest gathers the atoms the properties read (here the O atoms + the first residues: 224 of 648) into the staging buffers and the
+    kernels run on index lists remapped into that compact space: results identical to whole-frame ingest (ingest_mode=1), for host frames
+    and for the md_trajectory_i frame source, pageable memory."""
+    vb, g, sysm, F, cells = _golden_mix(emulated_library)
+    res = {}
+    for mode in (0, 1):
+        for src in ("host", "traj"):
+            plan = vb.Plan(sysm, vb.compile_script(SCRIPT_MIX, sysm), F, batch_frames=3, ingest_mode=mode)
+            na, nt = plan.ingest_info()
+            assert (60 < na < 300 and nt >= 1) if mode == 0 else (na == 648)
+            plan.set_initial_frame(*g["frames"][0], cells[0])
+            if src == "host": plan.eval_host_frames(g["frames"], cells, 0)
+            else: assert plan.eval_frame_range(vb.ArrayTrajectory(g["frames"], cells), 0, F, loader_threads=2)
+            res[(mode, src)] = _mix_results(plan); plan.close()
+    for k in ((0, "traj"), (1, "host"), (1, "traj")): _same(res[(0, "host")], res[k])
+    assert res[(0, "host")]["r"].sum() > 0 and res[(0, "host")]["v"].sum() > 0
+
+
+def test_concurrent_disjoint_ranges_on_one_plan(emulated_library):
+    """md_script_eval_frame_range is re-entrant on one eval from many threads with disjoint ranges (VIAMD's enkiTS range task,
+    src/task_system.cpp:73-87; mdlib/unittest/test_script.c:1352-1417 `parallel_evaluation` demands exact equality): four threads, one frame
+    each, one plan, two stream slots -> the results of a single call over the whole range."""
+    import threading
+    vb, g, sysm, F, cells = _golden_mix(emulated_library)
+    traj = vb.ArrayTrajectory(g["frames"], cells); traj._as_c()
+    ref = vb.Plan(sysm, vb.compile_script(SCRIPT_MIX, sysm), F); ref.eval_frame_range(traj, 0, F); want = _mix_results(ref); ref.close()
+    for rep in range(3):
+        plan = vb.Plan(sysm, vb.compile_script(SCRIPT_MIX, sysm), F, batch_frames=1, num_streams=2)
+        plan.set_initial_frame(*g["frames"][0], cells[0])
+        ok = [False] * F
+        def work(f): ok[f] = plan.eval_frame_range(traj, f, f + 1, loader_threads=1) and (plan.sync() is None)
+        th = [threading.Thread(target=work, args=(f,)) for f in range(F)]
+        for t in th: t.start()
+        for t in th: t.join()
+        assert all(ok)
+        _same(want, _mix_results(plan)); plan.close()
+
+
+def test_progress_callback_publishes_batches_into_bound_storage(emulated_library):
+    """The md_script shim's contract: values are written into caller-owned arrays (md_script_property_data_t::values), and after every
+    completed batch the callback fires with that batch's frames while their temporal rows are already in place (src/main.cpp:1513-1524 reads
+    them while the evaluation runs)."""
+    import numpy as np
+    vb, g, sysm, F, cells = _golden_mix(emulated_library)
+    plan = vb.Plan(sysm, vb.compile_script(SCRIPT_MIX, sysm), F, batch_frames=1)
+    plan.set_initial_frame(*g["frames"][0], cells[0])
+    d_vals = np.full(F, -1.0, np.float32); dp_vals = np.zeros(F * 55, np.float32); r_vals = np.zeros(2048, np.float32)
+    dp_mean = np.zeros(F, np.float32); dp_var = np.zeros(F, np.float32); dp_ext = np.zeros(2 * F, np.float32)
+    plan.bind_property_storage("d", d_vals); plan.bind_property_storage("dp", dp_vals, dp_mean, dp_var, dp_ext); plan.bind_property_storage("r", r_vals)
+    seen = []
+    def on_batch(beg, cnt):
+        seen.append((beg, cnt, d_vals[beg:beg + cnt].copy(), dp_mean[beg:beg + cnt].copy()))
+    plan.set_progress_callback(on_batch)
+    plan.eval_host_frames(g["frames"], cells, 0); plan.sync()
+    assert sorted(b for b, _, _, _ in seen) == list(range(F)) and all(c == 1 for _, c, _, _ in seen)
+    pz = __import__("helpers").load_golden("pairs6.npz")
+    for beg, cnt, dv, dm in seen:
+        assert dv[0] == g["d__full"][beg] and dm[0] == pz["w_dp__mean"][beg]        # the row was in place when the callback ran
+    assert np.array_equal(d_vals, g["d__full"]) and np.array_equal(dp_vals, pz["w_dp__full"]) and np.array_equal(dp_mean, pz["w_dp__mean"])
+    np.testing.assert_allclose(r_vals[:1024], g["r__full"][:1024], rtol=1e-5, atol=1e-6)
+    plan.close()
+
+
+def test_several_devices_in_one_process_merge_at_sync(emulated_library, monkeypatch):
+    """mdgpu_plan_options_t.num_devices = 2 (SURVEY 8(e) inside the C++ library, for the one-process VIAMD): contiguous frame blocks per device,
+    every accumulator reduced onto devices[0] by the exchange step at sync (NCCL bound at run time; here tests/emul/fake_nccl.cpp on the
+    emulated runtime's shared heap). Results, frame mask, weights and min/max equal the single-device evaluation; a second sync changes nothing;
+    evaluating the second half later merges exactly once."""
+    import build_emul
+    monkeypatch.setenv("MDGPU_EMUL_DEVICES", "2"); monkeypatch.setenv("MDGPU_NCCL_LIB", build_emul.build_fake_nccl())
+    vb, g, sysm, F, cells = _golden_mix(emulated_library)
+    one = vb.Plan(sysm, vb.compile_script(SCRIPT_MIX, sysm), F, keep_frame_results=True); one.set_initial_frame(*g["frames"][0], cells[0])
+    one.eval_host_frames(g["frames"], cells, 0); want = _mix_results(one); one.close()
+    for src in ("host", "traj"):
+        plan = vb.Plan(sysm, vb.compile_script(SCRIPT_MIX, sysm), F, keep_frame_results=True, devices=[0, 1])
+        plan.set_initial_frame(*g["frames"][0], cells[0])
+        if src == "host": plan.eval_host_frames(g["frames"], cells, 0)
+        else: assert plan.eval_frame_range(vb.ArrayTrajectory(g["frames"], cells), 0, F, loader_threads=2)
+        _same(want, _mix_results(plan)); plan.sync(); _same(want, _mix_results(plan))
+        assert plan.exchange_stats()[1] == 1
+        bins, tot = plan.frame_counts("r", F - 1); assert tot == int(bins.sum()) > 0       # a frame the second device evaluated
+        plan.clear()
+        plan.eval_host_frames(g["frames"][:2], cells[:2], 0); plan.sync(); plan.eval_host_frames(g["frames"][2:], cells[2:], 2)
+        _same(want, _mix_results(plan))
+        plan.close()

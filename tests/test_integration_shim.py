@@ -105,3 +105,47 @@ def test_md_script_api_through_the_shim_against_the_emulated_library(tmp_path):
     exact = {q["name"]: q["max_abs"] for q in res["properties"]}
     assert all(exact[k] == 0 for k in ("d", "rm", "dp", "c", "ci", "pl", "cw", "dmn", "dc", "v")), exact
 
+
+
+DROPIN_SCRIPT = "r = rdf(element('O'), element('O'), 6.0); d = distance(1,10); dz = density_z(element('O')); dp = distance_pair(atom(1:5), atom(20:30)); v = sdf(residue(1:20), element('O'), 5.0);"
+
+
+def _run_dropin(args, env=None):
+    p = subprocess.run([SHIM, "dropin", *args], capture_output=True, text=True, env=env)
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert line, p.stdout + p.stderr
+    return p.returncode, json.loads(line[-1])
+
+
+def test_zero_edit_dropin_viamd_call_pattern_against_the_emulated_library(tmp_path):
+    """integration/md_script_mdgpu.c = md_script_mdgpu_pre.h + the UNMODIFIED md_script.c + md_script_mdgpu.inl: the public
+    md_script_eval_frame_range IS the dispatcher. The harness drives it the way VIAMD does (src/main.cpp:993-997 via task_system.cpp:73-87,
+    à la mdlib/unittest/test_script.c:1352-1417): 4 threads pull disjoint 1-frame ranges on ONE eval while the main thread polls the frame
+    mask; then md_script_eval_interrupt mid-run, md_script_eval_clear_data, a full re-evaluation, md_script_eval_free. Results equal the
+    reference's own evaluation (`__cpu` symbols of the same TU); partial frame masks were visible while it ran. CPU: emulated library."""
+    _need()
+    import shutil
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+    import build_emul
+    libdir = tmp_path / "lib"; libdir.mkdir(); shutil.copy(build_emul.build_library(), str(libdir / "libmdgpu.so"))
+    gro = str(tmp_path / "w6.gro"); subprocess.check_call([TOOL, "water-gro", "6", "1008", gro])
+    rc, res = _run_dropin(["--sys", gro, "--traj", "synthwater:6:1008:6", "--script", DROPIN_SCRIPT.split(" v = ")[0], "--threads", "4", "--chunk", "1", "--interrupt-at", "2"],
+                          env=dict(os.environ, LD_LIBRARY_PATH=str(libdir)))
+    assert rc == 0 and res["parity"] is True, res
+    assert res["frames_done"] == 6 and res["partial_mask_views"] >= 2 and res["frames_done_at_interrupt"] < 6 and res["frames_done_after_restart"] == 6
+    exact = {q["name"]: q["max_abs"] for q in res["properties"]}
+    assert exact["d"] == 0 and exact["dp"] == 0 and all(q["out_of_tol"] == 0 and q["min_max_equal"] for q in res["properties"] + res["after_restart"])
+
+
+@pytest.mark.gpu
+def test_zero_edit_dropin_viamd_call_pattern_on_the_gpu(tmp_path):
+    """The same on the B200 with libmdgpu.so itself: 8 threads x enkiTS-sized ranges over 192 frames of a 1536-atom box, interrupt, restart."""
+    _need()
+    gro = str(tmp_path / "w8.gro"); subprocess.check_call([TOOL, "water-gro", "8", "1008", gro])
+    rc, res = _run_dropin(["--sys", gro, "--traj", "synthwater:8:1008:192", "--script", DROPIN_SCRIPT, "--threads", "8", "--interrupt-at", "40"])
+    assert rc == 0 and res["parity"] is True, res
+    assert res["frames_done"] == 192 and res["frames_done_after_restart"] == 192 and res["frames_done_at_interrupt"] <= 192
+    assert all(q["out_of_tol"] == 0 and q["min_max_equal"] for q in res["properties"] + res["after_restart"])
+    rc, res = _run_dropin(["--sys", gro, "--traj", "synthwater:8:1008:64", "--script", DROPIN_SCRIPT, "--threads", "1", "--chunk", "64"])   # one call over the whole range
+    assert rc == 0 and res["parity"] is True and res["partial_mask_views"] >= 0, res

@@ -81,7 +81,8 @@ class _PropertyData(C.Structure):
 
 class _PlanOptions(C.Structure):
     _fields_ = [("device", C.c_int), ("batch_frames", C.c_uint32), ("num_streams", C.c_uint32), ("keep_frame_results", C.c_uint32),
-                ("cell_capacity", C.c_uint32), ("rdf_variant", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("cell_capacity", C.c_uint32), ("rdf_variant", C.c_uint32), ("ingest_mode", C.c_uint32), ("ingest_threads", C.c_uint32),
+                ("num_devices", C.c_uint32), ("devices", C.c_int32 * 16)]
 
 
 # md_trajectory_i-compatible callback table (md_trajectory.h:49-67)
@@ -108,6 +109,7 @@ _INIT_READER = C.CFUNCTYPE(C.c_bool, C.POINTER(_Reader), C.c_void_p)
 _TRAJ_FREE = C.CFUNCTYPE(None, C.POINTER(_Traj))
 _Traj._fields_ = [("inst", C.c_void_p), ("free", _TRAJ_FREE), ("get_header", _GET_HEADER), ("init_reader", _INIT_READER)]
 
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32)   # mdgpu_progress_fn
 _lib = None
 
 
@@ -160,6 +162,11 @@ def lib() -> C.CDLL:
         L.mdgpu_memcpy_h2d.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
         L.mdgpu_memcpy_d2h.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
         L.mdgpu_device_synchronize.argtypes = [C.c_int]
+        L.mdgpu_plan_bind_property_storage.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mdgpu_plan_set_progress_callback.argtypes = [C.c_void_p, PROGRESS_FN, C.c_void_p]
+        L.mdgpu_bind_host_to_device.argtypes = [C.c_int]
+        L.mdgpu_plan_exchange_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.mdgpu_plan_ingest_info.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
 
@@ -167,6 +174,11 @@ def lib() -> C.CDLL:
 def _check(rc: int) -> None:
     if rc != 0:
         raise MdgpuError(f"mdgpu error {rc}: {lib().mdgpu_last_error().decode(errors='replace')}")
+
+
+def bind_host_to_device(device: int = 0) -> int:
+    """pin this thread (and threads created later) to the CPUs next to `device`; returns the CPU count, or a negative status when sysfs has none"""
+    return int(lib().mdgpu_bind_host_to_device(int(device)))
 
 
 def device_count() -> int:
@@ -349,6 +361,8 @@ class Trajectory:
     def load_frame(self, idx: int): raise NotImplementedError
 
     def _as_c(self):
+        if getattr(self, "_c_traj", None) is not None:   # one vtable per trajectory object: concurrent evaluations share it (the callbacks must outlive every call)
+            return self._c_traj
         n = self.num_atoms()
 
         def get_header(inst, hdr):
@@ -383,6 +397,7 @@ class Trajectory:
 
         self._cb_hdr = _GET_HEADER(get_header); self._cb_init = _INIT_READER(init_reader); self._cb_tfree = _TRAJ_FREE(traj_free)
         t = _Traj(); t.inst = 1; t.free = self._cb_tfree; t.get_header = self._cb_hdr; t.init_reader = self._cb_init
+        self._c_traj = t
         return t
 
 
@@ -405,9 +420,12 @@ class Plan:
     """md_script_eval_t equivalent: owns device accumulators and the host-visible property data."""
 
     def __init__(self, system: System, properties: Sequence[Property], num_frames: int, device: int = 0, batch_frames: int = 0,
-                 num_streams: int = 0, keep_frame_results: bool = False, cell_capacity: int = 0, rdf_variant: int = 0):
+                 num_streams: int = 0, keep_frame_results: bool = False, cell_capacity: int = 0, rdf_variant: int = 0,
+                 ingest_mode: int = 0, ingest_threads: int = 0, devices: Optional[Sequence[int]] = None):
+        """devices: more than one CUDA ordinal -> ONE process drives several GPUs (frame blocks per device, one NCCL reduce at sync)."""
         L = lib()
-        self.system, self.properties, self.num_frames, self.device = system, list(properties), int(num_frames), int(device)
+        if devices is not None and len(devices) == 1: device, devices = int(devices[0]), None
+        self.system, self.properties, self.num_frames, self.device = system, list(properties), int(num_frames), int(devices[0] if devices else device)
         self._keep = []
         mass = np.ascontiguousarray(system.mass, np.float32); self._keep.append(mass)
         sd = _SystemDesc(); sd.num_atoms = system.num_atoms; sd.atom_mass = mass.ctypes.data_as(C.POINTER(C.c_float))
@@ -432,6 +450,10 @@ class Plan:
                 d.idx[k] = a.ctypes.data_as(C.POINTER(C.c_int32)); d.idx_count[k] = a.size
         o = _PlanOptions(); o.device = device; o.batch_frames = batch_frames; o.num_streams = num_streams
         o.keep_frame_results = 1 if keep_frame_results else 0; o.cell_capacity = cell_capacity; o.rdf_variant = rdf_variant
+        o.ingest_mode = ingest_mode; o.ingest_threads = ingest_threads
+        if devices:
+            o.num_devices = len(devices)
+            for g, dv in enumerate(devices): o.devices[g] = int(dv)
         self._h = L.mdgpu_plan_create(C.byref(sd), descs, len(self.properties), self.num_frames, C.byref(o))
         if not self._h:
             raise MdgpuError(L.mdgpu_last_error().decode(errors="replace"))
@@ -454,6 +476,24 @@ class Plan:
     def clear(self): _check(lib().mdgpu_plan_clear(self._h))
     def interrupt(self): lib().mdgpu_plan_interrupt(self._h)
     def sync(self): _check(lib().mdgpu_plan_sync(self._h))
+
+    def set_progress_callback(self, fn):
+        """fn(frame_beg, frame_count) after every completed batch (mdgpu_plan_set_progress_callback); None removes it."""
+        self._progress = PROGRESS_FN(lambda user, b, n: fn(int(b), int(n))) if fn else PROGRESS_FN(0)
+        _check(lib().mdgpu_plan_set_progress_callback(self._h, self._progress, None))
+
+    def bind_property_storage(self, name, values: np.ndarray, agg_mean=None, agg_var=None, agg_ext=None):
+        """results of `name` are written into `values` (float32, C-contiguous) from now on (mdgpu_plan_bind_property_storage)"""
+        assert values.dtype == np.float32 and values.flags.c_contiguous
+        self._keep += [values, agg_mean, agg_var, agg_ext]
+        ptr = lambda a: None if a is None else a.ctypes.data
+        _check(lib().mdgpu_plan_bind_property_storage(self._h, self._index(name), values.ctypes.data, values.size, ptr(agg_mean), ptr(agg_var), ptr(agg_ext)))
+
+    def exchange_stats(self):
+        ms = C.c_double(); n = C.c_uint64(); _check(lib().mdgpu_plan_exchange_stats(self._h, C.byref(ms), C.byref(n))); return ms.value, int(n.value)
+
+    def ingest_info(self):
+        a = C.c_size_t(); t = C.c_uint32(); _check(lib().mdgpu_plan_ingest_info(self._h, C.byref(a), C.byref(t))); return int(a.value), int(t.value)
 
     def set_initial_frame(self, x, y, z, cell: UnitCell):
         x, y, z = (np.ascontiguousarray(a, np.float32) for a in (x, y, z))

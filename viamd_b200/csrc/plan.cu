@@ -21,6 +21,9 @@
 #include <vector>
 #include <map>
 #include <algorithm>
+#include <sched.h>
+#include <dlfcn.h>
+#include <ctype.h>
 
 namespace mdg {
 
@@ -46,6 +49,8 @@ template <typename T> static cudaError_t upload(T** p, const T* h, size_t n) {
 struct Prop {
     std::string name; uint32_t op = 0;
     std::vector<int32_t> h_idx[4]; int32_t* d_idx[4] = { nullptr, nullptr, nullptr, nullptr };
+    int32_t* d_idx_c[4] = { nullptr, nullptr, nullptr, nullptr };   // the same lists in the plan's compact atom space (host ingest of selected atoms)
+    int32_t first_c[4] = { 0, 0, 0, 0 };                            // compact index of each list's first atom (single-atom arguments are passed by value)
     size_t n_struct = 0, struct_size = 0;
     uint32_t com_mask = 0;   // distance/angle/dihedral: bit k = argument k is a selection evaluated through md_util_com_compute
     std::vector<uint32_t> h_soff; uint32_t* d_soff = nullptr;   // rdf with centre-of-mass references: CSR offsets of the groups in idx[0]
@@ -68,8 +73,10 @@ struct Prop {
     int2* d_unwrap = nullptr; uint32_t n_unwrap = 0;
     // density statics (from the initial frame's cell)
     float rc = 0, re = 0, inv_ext = 0, min_point = 0; double dens_factor = 0;
-    // results
+    // results: `values` is the default storage; mdgpu_plan_bind_property_storage points vptr (and the aggregate rows) at the caller's arrays
+    // (the md_script shim binds md_script_property_data_t::values, so results are written where VIAMD reads them)
     std::vector<float> values; mdgpu_property_data_t data{};
+    float* vptr = nullptr; float* amean = nullptr; float* avar = nullptr; float* aext = nullptr; bool bound = false;
     uint64_t frames_accumulated = 0;    // may be overridden after a cross-GPU reduction
     bool frames_overridden = false;
     bool is_dist() const { return op == MDGPU_OP_RDF || (op >= MDGPU_OP_DENSITY_X && op <= MDGPU_OP_DENSITY_Z); }
@@ -98,7 +105,8 @@ struct Slot {
     bool owned = false;                        // a caller thread holds the slot (acquire_slot / release_slot); guarded by mdgpu_plan::slot_mutex
     cudaEvent_t copied = nullptr;              // recorded after the batch's host->device copy: the caller's source buffer is free again
     int* h_err = nullptr;                      // pinned mirror of d_err, copied at the end of every batch (read when the slot is retired)
-    float* d_frames = nullptr; float* h_frames = nullptr;      // staging for host-resident frames
+    float* d_frames = nullptr; float* h_frames = nullptr;      // staging for host-resident frames (ingest atom space)
+    float* d_xtc_frames = nullptr;                             // whole decoded frames (XTC input)
     mdgpu_unitcell_t* d_cells = nullptr; mdgpu_unitcell_t* h_cells = nullptr;
     int* d_err = nullptr;
     std::vector<PropScratch> ps;
@@ -124,27 +132,59 @@ struct XtcStage {
 
 struct TimedLaunch { cudaEvent_t a, b; int kind; };   // kind: 0 rdf pair kernel, 1 sdf (all three kernels), 2 density (+finalize)
 
+typedef struct ncclComm* nccl_comm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*GroupStart)() = nullptr; int (*GroupEnd)() = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+enum { NCCL_UINT32 = 3, NCCL_UINT64 = 5, NCCL_FLOAT32 = 7, NCCL_SUM = 0 };   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+struct MultiDevice {
+    std::vector<mdgpu_plan*> peers;    // devices[1..]; the root plan is devices[0]
+    std::vector<int> devices;
+    NcclApi nccl; std::vector<nccl_comm_t> comms;
+    double last_reduce_ms = 0.0; uint64_t reduces = 0;
+};
+
+
 }  // namespace mdg
 
 using namespace mdg;
 
+struct IngestPool;
 struct mdgpu_plan {
     int device = 0; int sm_count = 148;
     size_t num_atoms = 0, num_frames = 0; size_t axis_stride = 0;   // staging layout: [frame][3][axis_stride]
     uint32_t B = 148; uint32_t S = 2; uint32_t cell_cap = 0; bool keep = false; uint32_t rdf_variant = 0;
     std::vector<float> h_mass; float* d_mass = nullptr;
+    // Compact atom space: the union of the atoms any property reads, ascending. When it is well below the system size, host ingest copies
+    // only those atoms (gathered into pinned staging by the ingest threads) and the kernels run on index lists remapped into that space.
+    bool compact = false; std::vector<int32_t> needed; size_t num_atoms_c = 0, axis_stride_c = 0; float* d_mass_c = nullptr; float* d_init_c = nullptr;
+    uint32_t ingest_mode = 0, ingest_threads = 0; IngestPool* pool = nullptr;
     std::vector<uint32_t> conn_off; std::vector<int32_t> conn_idx;
     std::vector<Prop> props;
     std::vector<Slot> slots;
     bool have_init = false; float* d_init = nullptr; mdgpu_unitcell_t init_cell{};
-    std::vector<uint64_t> frame_mask; std::mutex mask_mutex;
+    std::vector<uint64_t> frame_mask; std::mutex mask_mutex; std::mutex init_mutex;
     std::atomic<bool> interrupt{false};
     uint64_t next_slot = 0;
+    // Concurrency (md_script_eval_frame_range is re-entrant on one eval from many threads with disjoint ranges, task_system.cpp:73-87):
+    // a caller thread owns a slot from acquire_slot to release_slot (staging buffers + stream); enqueue_batch runs under submit_mutex;
+    // one fold at a time (sync_mutex).
+    std::mutex slot_mutex; std::condition_variable slot_cv; std::mutex submit_mutex; std::mutex sync_mutex;
+    mdgpu_progress_fn progress_fn = nullptr; void* progress_user = nullptr; cudaStream_t pub_stream = nullptr;
+    std::chrono::steady_clock::time_point last_pub{};
     bool timing = false; std::vector<TimedLaunch> timed; double timed_ms[3] = {0, 0, 0}; uint64_t timed_n[3] = {0, 0, 0};
     bool tri_seen = false, ortho_seen = false;
     cudaEvent_t t_begin = nullptr; std::vector<cudaEvent_t> t_end;
-    XtcStage xtc[XTC_STAGES]; uint64_t next_xtc = 0;
-    bool dirty = true;   // device accumulators changed since the last fold into the host-visible property data
+    XtcStage xtc[XTC_STAGES]; uint64_t next_xtc = 0; std::mutex xtc_mutex;
+    std::atomic<bool> dirty{true};   // device accumulators changed since the last fold into the host-visible property data
+    std::atomic<uint64_t> frames_retired{0};   // frame evaluations of retired batches: the divisor of the running means
+    mdg::MultiDevice* multi = nullptr;   // frame blocks on several GPUs from this one process (mdgpu_plan_options_t.num_devices > 1)
 };
 
 // get_spatial_acc (md_script_functions.inl:734-760): the system-wide grid of within() has cells of ceil(radius / 6) * 6
@@ -197,8 +237,55 @@ static void fold_frame_values(const float* v, size_t len, float& mn, float& mx, 
     mean = s1; var = s2;
 }
 
+
+// Host threads that gather the atoms a plan reads out of whole frames into pinned staging (and, for mdgpu_eval_trajectory, pull frames through
+// the frame source). One parallel_for at a time; callers that arrive while it is busy run their items themselves.
+struct IngestPool {
+    std::vector<std::thread> th; std::mutex m, job_m; std::condition_variable cv, done_cv;
+    std::function<void(uint32_t)> fn; uint32_t n = 0; std::atomic<uint32_t> next{0}; uint32_t active = 0, arrived = 0; uint64_t gen = 0; bool stop = false;
+    explicit IngestPool(uint32_t threads) {
+        for (uint32_t t = 0; t + 1 < threads; ++t) th.emplace_back([this]() {
+            uint64_t seen = 0;
+            for (;;) {
+                { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return stop || gen != seen; }); if (stop) return; seen = gen; ++active; ++arrived; }
+                for (uint32_t i; (i = next.fetch_add(1)) < n; ) fn(i);
+                { std::lock_guard<std::mutex> lk(m); --active; done_cv.notify_all(); }
+            }
+        });
+    }
+    ~IngestPool() { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); for (auto& t : th) t.join(); }
+    // every worker takes part in every job (and has left it before the call returns), so `fn` / `n` are never touched while a worker reads them
+    void parallel_for(uint32_t count, const std::function<void(uint32_t)>& f) {
+        if (count == 0) return;
+        std::unique_lock<std::mutex> job(job_m, std::try_to_lock);
+        if (!job.owns_lock() || th.empty() || count == 1) { for (uint32_t i = 0; i < count; ++i) f(i); return; }   // pool busy with another caller: that caller IS a thread
+        { std::lock_guard<std::mutex> lk(m); fn = f; n = count; next = 0; arrived = 0; ++gen; }
+        cv.notify_all();
+        for (uint32_t i; (i = next.fetch_add(1)) < count; ) f(i);
+        std::unique_lock<std::mutex> lk(m); done_cv.wait(lk, [&] { return arrived == (uint32_t)th.size() && active == 0; });
+    }
+};
+
+static IngestPool* ingest_pool(mdgpu_plan* p) {
+    std::lock_guard<std::mutex> guard(p->slot_mutex);
+    if (!p->pool) {
+        uint32_t t = p->ingest_threads;
+        if (!t) { const char* e = getenv("MDGPU_INGEST_THREADS"); t = e ? (uint32_t)atoi(e) : 0; }
+        if (!t) { const uint32_t hw = std::thread::hardware_concurrency(); t = std::min(16u, std::max(2u, hw / 2)); }
+        p->pool = new IngestPool(std::min(t, 64u));
+    }
+    return p->pool;
+}
+
+// dst[j] = src[needed[j]] for one axis of one frame
+static inline void gather_axis(float* __restrict__ dst, const float* __restrict__ src, const int32_t* __restrict__ idx, size_t n) {
+    for (size_t j = 0; j < n; ++j) dst[j] = src[idx[j]];
+}
+
+static void destroy_multi(mdgpu_plan* p);
 static void destroy_plan(mdgpu_plan* p) {
     if (!p) return;
+    if (p->multi) destroy_multi(p);
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
     for (auto& s : p->slots) {
@@ -206,11 +293,14 @@ static void destroy_plan(mdgpu_plan* p) {
             cudaFree(ps.d_geom); cudaFree(ps.d_aabb); free_cell_list(ps.trg); free_cell_list(ps.ref);
             cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_gpos[0]); cudaFree(ps.d_gpos[1]); cudaFree(ps.d_flags); cudaFree(ps.d_wgeom); cudaFree(ps.d_waabb); free_cell_list(ps.wtrg); free_cell_list(ps.wref); cudaFree(ps.d_dyn_idx); cudaFree(ps.d_dyn_n); cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
         }
-        cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames);
+        cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames); cudaFree(s.d_xtc_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.h_err) cudaFreeHost(s.h_err);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    if (p->pub_stream) cudaStreamDestroy(p->pub_stream);
     for (auto& st : p->xtc) {
         cudaFree(st.d_blob); cudaFree(st.d_off); if (st.h_off) cudaFreeHost(st.h_off); cudaFree(st.d_info); cudaFree(st.d_rec); cudaFree(st.d_state);
         if (st.ready) cudaEventDestroy(st.ready);
@@ -218,7 +308,7 @@ static void destroy_plan(mdgpu_plan* p) {
         if (st.stream) cudaStreamDestroy(st.stream);
     }
     for (auto& pr : p->props) {
-        for (int k = 0; k < 4; ++k) cudaFree(pr.d_idx[k]);
+        for (int k = 0; k < 4; ++k) { cudaFree(pr.d_idx[k]); cudaFree(pr.d_idx_c[k]); }
         if (pr.values_registered) cudaHostUnregister(pr.values.data());
         cudaFree(pr.d_vol_mean);
         cudaFree(pr.d_acc); cudaFree(pr.d_vol); cudaFree(pr.d_frame_total); cudaFree(pr.d_frame_min); cudaFree(pr.d_frame_max);
@@ -227,7 +317,8 @@ static void destroy_plan(mdgpu_plan* p) {
     for (auto& t : p->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (p->t_begin) cudaEventDestroy(p->t_begin);
     for (auto e : p->t_end) cudaEventDestroy(e);
-    cudaFree(p->d_mass); cudaFree(p->d_init);
+    cudaFree(p->d_mass); cudaFree(p->d_init); cudaFree(p->d_mass_c); cudaFree(p->d_init_c);
+    delete p->pool;
     delete p;
 }
 
@@ -245,6 +336,24 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
     mdgpu_plan_options_t o{}; if (opts) o = *opts;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { fail(MDGPU_ERR_CUDA, "no CUDA device available (libmdgpu has no CPU fallback)"); return nullptr; }
+    if (o.num_devices > 1) {   // one process, several GPUs: the root plan on devices[0] + one peer plan per further device
+        if (o.num_devices > 16) { fail(MDGPU_ERR_INVALID_ARG, "at most 16 devices per plan"); return nullptr; }
+        for (uint32_t g = 0; g < o.num_devices; ++g) {
+            if (o.devices[g] < 0 || o.devices[g] >= ndev) { fail(MDGPU_ERR_INVALID_ARG, "device %d out of range (%d devices)", o.devices[g], ndev); return nullptr; }
+            for (uint32_t h = 0; h < g; ++h) if (o.devices[h] == o.devices[g]) { fail(MDGPU_ERR_INVALID_ARG, "device %d listed twice", o.devices[g]); return nullptr; }
+        }
+        mdgpu_plan_options_t one = o; one.num_devices = 0; one.device = o.devices[0];
+        mdgpu_plan* root = mdgpu_plan_create(sys, props, num_props, num_frames, &one);
+        if (!root) return nullptr;
+        root->multi = new MultiDevice(); root->multi->devices.assign(o.devices, o.devices + o.num_devices);
+        for (uint32_t g = 1; g < o.num_devices; ++g) {
+            one.device = o.devices[g];
+            mdgpu_plan* q = mdgpu_plan_create(sys, props, num_props, num_frames, &one);
+            if (!q) { destroy_plan(root); return nullptr; }
+            root->multi->peers.push_back(q);
+        }
+        return root;
+    }
     if (o.device < 0 || o.device >= ndev) { fail(MDGPU_ERR_INVALID_ARG, "device %d out of range (%d devices)", o.device, ndev); return nullptr; }
     if (cudaSetDevice(o.device) != cudaSuccess) { fail(MDGPU_ERR_CUDA, "cudaSetDevice(%d) failed", o.device); return nullptr; }
     mdgpu_plan* p = new mdgpu_plan();
@@ -256,6 +365,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
     if (p->B > 4096) p->B = 4096;
     p->S = o.num_streams ? o.num_streams : 3; if (p->S > 8) p->S = 8;   // 3: copy of batch k+2 overlaps compute of k and k+1 (2 streams left the copy engine idle 25 % of the time)
     p->keep = o.keep_frame_results != 0; p->cell_cap = o.cell_capacity; p->rdf_variant = o.rdf_variant;
+    p->ingest_mode = o.ingest_mode; p->ingest_threads = o.ingest_threads;
     p->h_mass.assign(sys->num_atoms, 1.0f);
     if (sys->atom_mass) memcpy(p->h_mass.data(), sys->atom_mass, sizeof(float) * sys->num_atoms);
     if (sys->bond_conn_offset && sys->bond_conn_offset_count) {
@@ -439,12 +549,37 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             return bail(MDGPU_ERR_UNSUPPORTED, "property '" + pr.name + "': unsupported operation " + std::to_string(pr.op));
         }
         if (e != cudaSuccess) return bail(MDGPU_ERR_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(e));
-        pr.data.num_values = pr.values.size(); pr.data.values = pr.values.data();
-        pr.data.weights = pr.is_dist() ? pr.values.data() + MDGPU_DIST_BINS : nullptr;
+        pr.vptr = pr.values.data(); pr.amean = pr.agg_mean.data(); pr.avar = pr.agg_var.data(); pr.aext = pr.agg_ext.data();
+        pr.data.num_values = pr.values.size(); pr.data.values = pr.vptr;
+        pr.data.weights = pr.is_dist() ? pr.vptr + MDGPU_DIST_BINS : nullptr;
     }
     for (size_t i = 0; i < num_props; ++i) for (size_t j = 0; j < i; ++j) {
         Prop& a = p->props[i]; Prop& b = p->props[j];
         if (a.needs_cells() && b.needs_cells() && b.share_trg < 0 && a.cutoff_max == b.cutoff_max && a.h_idx[1] == b.h_idx[1]) { a.share_trg = (int)j; break; }
+    }
+    {   // compact atom space: what host ingest has to copy
+        const size_t N = sys->num_atoms; bool all_atoms = false;
+        std::vector<uint8_t> mark(N, 0);
+        for (auto& pr : p->props) {
+            if (pr.op == MDGPU_OP_WITHIN_COUNT || pr.ref_within > 0.0f) all_atoms = true;   // within() searches the whole system
+            for (int k = 0; k < 4; ++k) for (int32_t a : pr.h_idx[k]) mark[(size_t)a] = 1;
+        }
+        for (size_t a = 0; a < N; ++a) if (mark[a]) p->needed.push_back((int32_t)a);
+        const char* env = getenv("MDGPU_INGEST_MODE");
+        const uint32_t mode = env ? (uint32_t)atoi(env) : p->ingest_mode;
+        p->compact = !all_atoms && mode == 0 && p->needed.size() * 4 <= N * 3;
+        if (p->compact) {
+            std::vector<int32_t> map(N, -1); for (size_t j = 0; j < p->needed.size(); ++j) map[(size_t)p->needed[j]] = (int32_t)j;
+            p->num_atoms_c = p->needed.size(); p->axis_stride_c = (p->num_atoms_c + 3) & ~(size_t)3;
+            std::vector<float> mc(p->num_atoms_c); for (size_t j = 0; j < mc.size(); ++j) mc[j] = p->h_mass[(size_t)p->needed[j]];
+            if (upload(&p->d_mass_c, mc.data(), mc.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (masses)");
+            for (auto& pr : p->props) for (int k = 0; k < 4; ++k) if (!pr.h_idx[k].empty()) {
+                std::vector<int32_t> ci(pr.h_idx[k].size()); for (size_t j = 0; j < ci.size(); ++j) ci[j] = map[(size_t)pr.h_idx[k][j]];
+                pr.first_c[k] = ci[0];
+                if (upload(&pr.d_idx_c[k], ci.data(), ci.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (indices)");
+            }
+            if (cudaMalloc((void**)&p->d_init_c, sizeof(float) * 3 * p->axis_stride_c) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (initial frame)");
+        }
     }
     p->frame_mask.assign((num_frames + 63) / 64, 0);
     if (cudaMalloc((void**)&p->d_init, sizeof(float) * 3 * p->axis_stride) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (initial frame)");
@@ -456,9 +591,10 @@ void mdgpu_plan_destroy(mdgpu_plan* plan) { destroy_plan(plan); }
 
 int mdgpu_plan_clear(mdgpu_plan* p) {
     if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
+    if (p->multi) for (auto* q : p->multi->peers) { int rc = mdgpu_plan_clear(q); if (rc) return rc; }
     CUDA_TRY(cudaSetDevice(p->device));
     CUDA_TRY(cudaDeviceSynchronize());
-    for (auto& s : p->slots) s.busy = false;
+    for (auto& s : p->slots) { s.busy = false; if (s.h_err) *s.h_err = 0; if (s.d_err) CUDA_TRY(cudaMemset(s.d_err, 0, sizeof(int))); }
     for (auto& pr : p->props) {
         if (pr.d_acc) CUDA_TRY(cudaMemset(pr.d_acc, 0, sizeof(unsigned long long) * MDGPU_DIST_BINS));
         if (pr.d_vol) CUDA_TRY(cudaMemset(pr.d_vol, 0, sizeof(uint32_t) * MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM));
@@ -468,17 +604,17 @@ int mdgpu_plan_clear(mdgpu_plan* p) {
         if (pr.d_frame_min64) CUDA_TRY(cudaMemset(pr.d_frame_min64, 0, sizeof(unsigned long long) * p->num_frames));
         if (pr.d_frame_max64) CUDA_TRY(cudaMemset(pr.d_frame_max64, 0, sizeof(unsigned long long) * p->num_frames));
         if (pr.d_temporal) CUDA_TRY(cudaMemset(pr.d_temporal, 0, sizeof(float) * p->num_frames * pr.len));
-        std::fill(pr.agg_mean.begin(), pr.agg_mean.end(), 0.0f); std::fill(pr.agg_var.begin(), pr.agg_var.end(), 0.0f); std::fill(pr.agg_ext.begin(), pr.agg_ext.end(), 0.0f);
+        if (!pr.agg_mean.empty()) { std::fill(pr.amean, pr.amean + p->num_frames, 0.0f); std::fill(pr.avar, pr.avar + p->num_frames, 0.0f); std::fill(pr.aext, pr.aext + 2 * p->num_frames, 0.0f); }
         if (pr.d_keep) CUDA_TRY(cudaMemset(pr.d_keep, 0, sizeof(uint32_t) * p->num_frames * MDGPU_DIST_BINS));
         if (pr.d_keep64) CUDA_TRY(cudaMemset(pr.d_keep64, 0, sizeof(unsigned long long) * p->num_frames * MDGPU_DIST_BINS));
-        std::fill(pr.values.begin(), pr.values.end(), 0.0f);
-        if (pr.is_dist()) std::fill(pr.values.begin() + MDGPU_DIST_BINS, pr.values.end(), 1.0f);   // allocate_property_data :5613-5618
+        std::fill(pr.vptr, pr.vptr + pr.values.size(), 0.0f);
+        if (pr.is_dist()) std::fill(pr.vptr + MDGPU_DIST_BINS, pr.vptr + pr.values.size(), 1.0f);   // allocate_property_data :5613-5618
         pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;                                 // clear_property_data :5726-5727
         pr.data.min_range[0] = pr.data.min_range[1] = pr.data.max_range[0] = pr.data.max_range[1] = 0.0f;
         pr.frames_accumulated = 0; pr.frames_overridden = false; pr.data.frames_accumulated = 0;
     }
     { std::lock_guard<std::mutex> lk(p->mask_mutex); std::fill(p->frame_mask.begin(), p->frame_mask.end(), 0ull); }
-    p->interrupt = false;
+    p->interrupt = false; p->frames_retired = 0;
     for (int k = 0; k < 3; ++k) { p->timed_ms[k] = 0; p->timed_n[k] = 0; }
     p->dirty = true;
     return 0;
@@ -486,10 +622,16 @@ int mdgpu_plan_clear(mdgpu_plan* p) {
 
 int mdgpu_plan_set_initial_frame(mdgpu_plan* p, const float* x, const float* y, const float* z, const mdgpu_unitcell_t* cell) {
     if (!p || !x || !y || !z || !cell) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_set_initial_frame: null argument");
+    if (p->multi) for (auto* q : p->multi->peers) { int rc = mdgpu_plan_set_initial_frame(q, x, y, z, cell); if (rc) return rc; }
     CUDA_TRY(cudaSetDevice(p->device));
     CUDA_TRY(cudaMemcpy(p->d_init, x, sizeof(float) * p->num_atoms, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(p->d_init + p->axis_stride, y, sizeof(float) * p->num_atoms, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(p->d_init + 2 * p->axis_stride, z, sizeof(float) * p->num_atoms, cudaMemcpyHostToDevice));
+    if (p->compact) {
+        std::vector<float> c(3 * p->axis_stride_c, 0.0f); const float* src[3] = { x, y, z };
+        for (int ax = 0; ax < 3; ++ax) gather_axis(c.data() + (size_t)ax * p->axis_stride_c, src[ax], p->needed.data(), p->num_atoms_c);
+        CUDA_TRY(cudaMemcpy(p->d_init_c, c.data(), sizeof(float) * c.size(), cudaMemcpyHostToDevice));
+    }
     p->init_cell = *cell; p->have_init = true;
     for (auto& pr : p->props) {
         if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
@@ -515,6 +657,7 @@ int mdgpu_plan_set_initial_frame(mdgpu_plan* p, const float* x, const float* y, 
 // slot set-up (lazy: needs the initial frame for the default cell capacity)
 // ---------------------------------------------------------------------------------------------------------------
 static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool need_host_staging) {
+    std::lock_guard<std::mutex> guard(p->slot_mutex);   // concurrent callers: the first one builds the slots
     if (p->slots.empty()) {
         // default cell capacity: twice the grid the reference would build for the first frame, per property cutoff
         uint32_t cap = p->cell_cap;
@@ -535,6 +678,8 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
         for (auto& s : p->slots) {
             CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+            CUDA_TRY(cudaMallocHost((void**)&s.h_err, sizeof(int))); *s.h_err = 0;
             CUDA_TRY(dalloc(&s.d_cells, p->B));
             CUDA_TRY(cudaMallocHost((void**)&s.h_cells, sizeof(mdgpu_unitcell_t) * p->B));
             CUDA_TRY(dalloc(&s.d_err, 1)); CUDA_TRY(cudaMemset(s.d_err, 0, sizeof(int)));
@@ -588,15 +733,19 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
             }
         }
     }
-    if (need_host_staging) for (auto& s : p->slots) if (!s.d_frames) {
-        CUDA_TRY(dalloc(&s.d_frames, (size_t)p->B * 3 * p->axis_stride));
-        CUDA_TRY(cudaMallocHost((void**)&s.h_frames, sizeof(float) * (size_t)p->B * 3 * p->axis_stride));
+    if (need_host_staging) for (auto& s : p->slots) if (!s.d_frames) {   // host ingest staging, in the ingest (compact or full) atom space
+        const size_t AS = p->compact ? p->axis_stride_c : p->axis_stride;
+        CUDA_TRY(dalloc(&s.d_frames, (size_t)p->B * 3 * AS));
+        CUDA_TRY(cudaMallocHost((void**)&s.h_frames, sizeof(float) * (size_t)p->B * 3 * AS));
     }
     return 0;
 }
 
 // enqueue the property kernels of one batch whose frames are already in device memory
-static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t frame0) {
+// `c`: the frames are in the plan's COMPACT atom space (host ingest copied only the atoms the properties read): index lists, masses and the
+// initial frame of that space are used; otherwise the caller's full frames with global atom indices.
+static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t frame0, bool c) {
+    std::lock_guard<std::mutex> guard(p->submit_mutex);
     const int B = (int)fr.count;
     // all frames of a batch must agree on ortho vs triclinic (kernel template parameter)
     bool tri = (s.h_cells[0].flags & MDGPU_CELL_TRICLINIC) != 0;
@@ -606,12 +755,14 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
     bool all_pbc = true; for (int i = 0; i < B; ++i) all_pbc = all_pbc && ((s.h_cells[i].flags & MDGPU_CELL_PBC_ALL) == MDGPU_CELL_PBC_ALL);
     for (size_t i = 0; i < p->props.size(); ++i) {
         Prop& pr = p->props[i]; PropScratch& ps = s.ps[i];
+        int32_t* const* didx = c ? pr.d_idx_c : pr.d_idx;
+        const float* dmass = c ? p->d_mass_c : p->d_mass; const float* dinit = c ? p->d_init_c : p->d_init; const size_t init_as = c ? p->axis_stride_c : p->axis_stride;
         const PropScratch& cs = (pr.share_trg >= 0) ? s.ps[pr.share_trg] : ps;   // owner of the target cell list + geometry
         if (pr.needs_cells() && pr.share_trg < 0) {
             const float* aabb = nullptr;
-            if (!all_pbc) { launch_aabb(fr, pr.d_idx[1], (uint32_t)pr.h_idx[1].size(), ps.d_aabb, s.stream); aabb = ps.d_aabb; }
+            if (!all_pbc) { launch_aabb(fr, didx[1], (uint32_t)pr.h_idx[1].size(), ps.d_aabb, s.stream); aabb = ps.d_aabb; }
             launch_geom(s.d_cells, aabb, ps.d_geom, (double)pr.cutoff_max, (double)pr.cutoff_max, p->cell_cap, B, s.d_err, s.stream);
-            launch_cell_list(0, fr, pr.d_idx[1], nullptr, (uint32_t)pr.h_idx[1].size(), ps.d_geom, ps.trg, 0, s.stream);
+            launch_cell_list(0, fr, didx[1], nullptr, (uint32_t)pr.h_idx[1].size(), ps.d_geom, ps.trg, 0, s.stream);
         }
         switch (pr.op) {
         case MDGPU_OP_RDF: {
@@ -620,17 +771,17 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
                 if (!all_pbc) { launch_aabb(fr, nullptr, (uint32_t)p->num_atoms, ps.d_waabb, s.stream); waabb = ps.d_waabb; }
                 launch_geom(s.d_cells, waabb, ps.d_wgeom, within_cell_ext(pr.ref_within), (double)pr.ref_within, p->cell_cap, B, s.d_err, s.stream);
                 launch_cell_list(0, fr, nullptr, nullptr, (uint32_t)p->num_atoms, ps.d_wgeom, ps.wtrg, 0, s.stream);
-                launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_wgeom, ps.wref, 0, s.stream);
+                launch_cell_list(1, fr, didx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_wgeom, ps.wref, 0, s.stream);
                 WithinArgs w{};
-                w.geom = ps.d_wgeom; w.trg = ps.wtrg; w.ref = ps.wref; w.sel = pr.d_idx[0]; w.n_sel = (uint32_t)pr.h_idx[0].size();
+                w.geom = ps.d_wgeom; w.trg = ps.wtrg; w.ref = ps.wref; w.sel = didx[0]; w.n_sel = (uint32_t)pr.h_idx[0].size();
                 w.num_atoms = (uint32_t)p->num_atoms; w.flags = ps.d_flags; w.out = nullptr; w.frame0 = frame0; w.min_r2 = pr.ref_within_min * pr.ref_within_min; w.and_mask = pr.d_and_mask;
                 launch_within_list(w, B, tri, p->sm_count, ps.d_dyn_idx, ps.d_dyn_n, s.stream);
                 launch_cell_list_dyn(fr, ps.d_dyn_idx, ps.d_dyn_n, (uint32_t)p->num_atoms, cs.d_geom, ps.ref, s.stream);
             } else if (pr.n_struct) {
-                launch_group_com(fr, pr.d_idx[0], pr.d_soff, (uint32_t)pr.n_struct, p->d_mass, ps.d_com, s.stream);
+                launch_group_com(fr, didx[0], pr.d_soff, (uint32_t)pr.n_struct, dmass, ps.d_com, s.stream);
                 launch_cell_list(1, fr, nullptr, ps.d_com, (uint32_t)pr.n_struct, cs.d_geom, ps.ref, 0, s.stream);   // AoS stream: i = position index (:1721)
             } else {
-                launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), cs.d_geom, ps.ref, 0, s.stream);
+                launch_cell_list(1, fr, didx[0], nullptr, (uint32_t)pr.h_idx[0].size(), cs.d_geom, ps.ref, 0, s.stream);
             }
             if (!pr.n_struct) {   // candidate lists: the neighbour reach follows the frame's cell (an NPT or sheared cell can cross from 27 to 125 offsets)
                 size_t nn_max = 0;
@@ -657,7 +808,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.min_r2 = a.min_cutoff * a.min_cutoff;                                       // rdf_cb :5233
             a.frame_bins = ps.d_frame_bins; a.frame0 = frame0;
             a.pair_list = ps.d_pair_list; a.list_hdr = ps.d_list_hdr; a.list_cursor = ps.d_list_cursor; a.list_stride = ps.list_stride; a.hdr_stride = p->cell_cap; a.err = s.d_err;
-            a.excl_off = pr.n_struct ? pr.d_soff : nullptr; a.excl_idx = pr.n_struct ? pr.d_idx[0] : nullptr;   // md_bitfield_test_bit(&masks[i], j) :5252
+            a.excl_off = pr.n_struct ? pr.d_soff : nullptr; a.excl_idx = pr.n_struct ? didx[0] : nullptr;   // md_bitfield_test_bit(&masks[i], j) :5252
             a.symmetric = (!pr.n_struct && pr.ref_within == 0.0f && pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
             a.acc = pr.d_acc; a.frame_total = pr.d_frame_total; a.frame_min = pr.d_frame_min; a.frame_max = pr.d_frame_max; a.keep = pr.d_keep;
             TimedLaunch tl{};
@@ -669,8 +820,8 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "sdf '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
             SdfArgs a{};
             a.geom = cs.d_geom; a.trg = cs.trg; a.frames = fr; a.cells = s.d_cells;
-            a.init_xyz = p->d_init; a.init_axis_stride = p->axis_stride; a.mass = p->d_mass;
-            a.struct_idx = pr.d_idx[0]; a.n_struct = (uint32_t)pr.n_struct; a.struct_size = (uint32_t)pr.struct_size;
+            a.init_xyz = dinit; a.init_axis_stride = init_as; a.mass = dmass;
+            a.struct_idx = didx[0]; a.n_struct = (uint32_t)pr.n_struct; a.struct_size = (uint32_t)pr.struct_size;
             a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap; a.cutoff = pr.cutoff_max;
             a.scratch_xyzw = ps.d_sdf_xyzw; a.ref0 = ps.d_sdf_ref0; a.matrices = ps.d_sdf_mats;
             a.vol = pr.d_vol; a.frame_total = pr.d_frame_total; a.frame0 = frame0;
@@ -682,7 +833,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
         case MDGPU_OP_DENSITY_X: case MDGPU_OP_DENSITY_Y: case MDGPU_OP_DENSITY_Z: {
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "density '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
             DensityArgs a{};
-            a.frames = fr; a.idx = pr.d_idx[0]; a.n = (uint32_t)pr.h_idx[0].size(); a.mass = p->d_mass; a.axis = (int)pr.op - MDGPU_OP_DENSITY_X;
+            a.frames = fr; a.idx = didx[0]; a.n = (uint32_t)pr.h_idx[0].size(); a.mass = dmass; a.axis = (int)pr.op - MDGPU_OP_DENSITY_X;
             a.rc = pr.rc; a.re = pr.re; a.inv_ext = pr.inv_ext; a.min_point = pr.min_point;
             a.acc = pr.d_acc; a.frame_bins = ps.d_frame_bins64; a.frame_min = pr.d_frame_min64; a.frame_max = pr.d_frame_max64; a.keep = pr.d_keep64; a.frame0 = frame0;
             TimedLaunch tl{};
@@ -695,32 +846,32 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             if (!all_pbc) { launch_aabb(fr, nullptr, (uint32_t)p->num_atoms, ps.d_aabb, s.stream); aabb = ps.d_aabb; }   // every atom of the system
             launch_geom(s.d_cells, aabb, ps.d_geom, within_cell_ext(pr.cutoff_max), (double)pr.cutoff_max, p->cell_cap, B, s.d_err, s.stream);
             launch_cell_list(0, fr, nullptr, nullptr, (uint32_t)p->num_atoms, ps.d_geom, ps.trg, 0, s.stream);
-            launch_cell_list(1, fr, pr.d_idx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_geom, ps.ref, 0, s.stream);
+            launch_cell_list(1, fr, didx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_geom, ps.ref, 0, s.stream);
             WithinArgs a{};
-            a.geom = ps.d_geom; a.trg = ps.trg; a.ref = ps.ref; a.sel = pr.d_idx[0]; a.n_sel = (uint32_t)pr.h_idx[0].size();
+            a.geom = ps.d_geom; a.trg = ps.trg; a.ref = ps.ref; a.sel = didx[0]; a.n_sel = (uint32_t)pr.h_idx[0].size();
             a.num_atoms = (uint32_t)p->num_atoms; a.flags = ps.d_flags; a.out = pr.d_temporal; a.frame0 = frame0; a.min_r2 = pr.cutoff_min * pr.cutoff_min; a.and_mask = pr.d_and_mask;   // :2641
             launch_within_count(a, B, tri, p->sm_count, s.stream);
             break; }
         case MDGPU_OP_COM: {
             TemporalArgs a{};
             a.frames = fr; a.cells = s.d_cells; a.op = (int)pr.op; a.out = pr.d_temporal; a.frame0 = frame0;
-            a.atom[0] = pr.h_idx[0][0]; a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
-            if (pr.com_mask & 1u) launch_arg_com(fr, s.d_cells, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), p->d_mass, ps.d_argpos, 0, s.stream);
+            a.atom[0] = c ? pr.first_c[0] : pr.h_idx[0][0]; a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
+            if (pr.com_mask & 1u) launch_arg_com(fr, s.d_cells, didx[0], (uint32_t)pr.h_idx[0].size(), dmass, ps.d_argpos, 0, s.stream);
             launch_com_rows(a, B, s.stream);
             break; }
         case MDGPU_OP_COORD_X: case MDGPU_OP_COORD_Y: case MDGPU_OP_COORD_Z:
-            launch_coord_rows(fr, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), (int)pr.op - MDGPU_OP_COORD_X, pr.d_temporal, frame0, s.stream);
+            launch_coord_rows(fr, didx[0], (uint32_t)pr.h_idx[0].size(), (int)pr.op - MDGPU_OP_COORD_X, pr.d_temporal, frame0, s.stream);
             break;
         case MDGPU_OP_SHAPE_WEIGHTS: {
             ShapeArgs a{};
-            a.frames = fr; a.cells = s.d_cells; a.mass = p->d_mass; a.use_mass = (int)(pr.com_mask & 1u);
-            a.idx = pr.d_idx[0]; a.soff = pr.d_soff; a.n_struct = (uint32_t)pr.n_struct; a.n_atoms_total = (uint32_t)pr.h_idx[0].size();
+            a.frames = fr; a.cells = s.d_cells; a.mass = dmass; a.use_mass = (int)(pr.com_mask & 1u);
+            a.idx = didx[0]; a.soff = pr.d_soff; a.n_struct = (uint32_t)pr.n_struct; a.n_atoms_total = (uint32_t)pr.h_idx[0].size();
             a.scratch_xyzw = ps.d_sdf_xyzw; a.out = pr.d_temporal; a.frame0 = frame0;
             launch_shape_weights(a, B, s.stream);
             break; }
         case MDGPU_OP_PLANE: {
             RmsdArgs a{};
-            a.frames = fr; a.cells = s.d_cells; a.mass = p->d_mass; a.idx = pr.d_idx[0]; a.n = (uint32_t)pr.h_idx[0].size();
+            a.frames = fr; a.cells = s.d_cells; a.mass = dmass; a.idx = didx[0]; a.n = (uint32_t)pr.h_idx[0].size();
             a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap; a.scratch_xyzw = ps.d_sdf_xyzw; a.out = pr.d_temporal; a.frame0 = frame0;
             launch_plane(a, B, s.stream);
             break; }
@@ -728,34 +879,34 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             uint32_t cnt[2];
             for (int k = 0; k < 2; ++k) {
                 cnt[k] = (uint32_t)(pr.h_goff[k].empty() ? pr.h_idx[k].size() : pr.h_goff[k].size() - 1);
-                if (!pr.h_goff[k].empty()) launch_group_com(fr, pr.d_idx[k], pr.d_goff[k], cnt[k], p->d_mass, ps.d_gpos[k], s.stream);   // extract_com :857, as for rdf's group references
+                if (!pr.h_goff[k].empty()) launch_group_com(fr, didx[k], pr.d_goff[k], cnt[k], dmass, ps.d_gpos[k], s.stream);   // extract_com :857, as for rdf's group references
             }
-            launch_distance_pair(fr, s.d_cells, pr.d_idx[0], cnt[0], pr.d_idx[1], cnt[1], ps.d_gpos[0], ps.d_gpos[1], pr.d_temporal, frame0, s.stream);
+            launch_distance_pair(fr, s.d_cells, didx[0], cnt[0], didx[1], cnt[1], ps.d_gpos[0], ps.d_gpos[1], pr.d_temporal, frame0, s.stream);
             break; }
         case MDGPU_OP_RMSD: {
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "rmsd '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
             RmsdArgs a{};
-            a.frames = fr; a.cells = s.d_cells; a.init_xyz = p->d_init; a.init_axis_stride = p->axis_stride; a.mass = p->d_mass;
-            a.idx = pr.d_idx[0]; a.n = (uint32_t)pr.h_idx[0].size(); a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap;
+            a.frames = fr; a.cells = s.d_cells; a.init_xyz = dinit; a.init_axis_stride = init_as; a.mass = dmass;
+            a.idx = didx[0]; a.n = (uint32_t)pr.h_idx[0].size(); a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap;
             a.scratch_xyzw = ps.d_sdf_xyzw; a.out = pr.d_temporal; a.frame0 = frame0;
             launch_rmsd(a, B, s.stream);
             break; }
         case MDGPU_OP_DISTANCE_MIN: case MDGPU_OP_DISTANCE_MAX:   // both evaluate md_util_min_distance (md_script_functions.inl:3904, 3944)
-            launch_min_distance(fr, s.d_cells, pr.d_idx[0], (uint32_t)pr.h_idx[0].size(), pr.d_idx[1], (uint32_t)pr.h_idx[1].size(), pr.d_temporal, frame0, s.stream);
+            launch_min_distance(fr, s.d_cells, didx[0], (uint32_t)pr.h_idx[0].size(), didx[1], (uint32_t)pr.h_idx[1].size(), pr.d_temporal, frame0, s.stream);
             break;
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
             TemporalArgs a{};
             a.frames = fr; a.cells = s.d_cells; a.op = (int)pr.op; a.out = pr.d_temporal; a.frame0 = frame0;
             if (pr.n_struct) {
-                for (int k = 0; k < 4; ++k) a.ctx_idx[k] = pr.d_idx[k];
+                for (int k = 0; k < 4; ++k) a.ctx_idx[k] = didx[k];
                 a.n_ctx = (uint32_t)pr.n_struct;
                 launch_temporal_ctx(a, B, s.stream);
                 break;
             }
-            for (int k = 0; k < 4; ++k) a.atom[k] = pr.h_idx[k].empty() ? 0 : pr.h_idx[k][0];
+            for (int k = 0; k < 4; ++k) a.atom[k] = pr.h_idx[k].empty() ? 0 : (c ? pr.first_c[k] : pr.h_idx[k][0]);
             a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
             for (int k = 0; k < 4; ++k) if (pr.com_mask & (1u << k))
-                launch_arg_com(fr, s.d_cells, pr.d_idx[k], (uint32_t)pr.h_idx[k].size(), p->d_mass, ps.d_argpos, k, s.stream);
+                launch_arg_com(fr, s.d_cells, didx[k], (uint32_t)pr.h_idx[k].size(), dmass, ps.d_argpos, k, s.stream);
             launch_temporal(a, B, s.stream);
             break; }
         default: break;
@@ -763,6 +914,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
         pr.frames_accumulated += (uint64_t)B;
     }
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(s.h_err, s.d_err, sizeof(int), cudaMemcpyDeviceToHost, s.stream));   // read when the slot is retired
     CUDA_TRY(cudaEventRecord(s.done, s.stream));
     s.busy = true; s.pending_beg = frame0; s.pending_cnt = (uint32_t)B;
     p->dirty = true;
@@ -774,18 +926,192 @@ static void mark_frames(mdgpu_plan* p, uint32_t beg, uint32_t cnt) {
     for (uint32_t f = beg; f < beg + cnt && f < p->num_frames; ++f) p->frame_mask[f >> 6] |= (1ull << (f & 63));
 }
 
-// wait until a slot's previous batch has finished (its staging buffers become reusable); sets the frame-mask bits
+static int publish_batch(mdgpu_plan* p, uint32_t beg, uint32_t cnt);
+
+static int device_error(mdgpu_plan* p, int err) {
+    if (err == MDGPU_ERR_CAPACITY) return fail(err, "a frame needs more cells than the plan reserved from its first frame (cell capacity %u); raise mdgpu_plan_options_t.cell_capacity", p->cell_cap);
+    if (err == MDGPU_ERR_FRAME_SOURCE) return fail(err, "XTC: Failed to decode frame data (%d)", err);
+    return fail(err, "device-side error %d", err);
+}
+
+// wait until a slot's previous batch has finished (its staging buffers become reusable). Only the thread that owns the slot calls this.
+// The batch's device-side error word is inspected BEFORE its frames are declared done: a failed batch never shows up in the frame mask.
 static int retire_slot(mdgpu_plan* p, Slot& s) {
     if (!s.busy) return 0;
     CUDA_TRY(cudaEventSynchronize(s.done));
     s.busy = false;
+    if (s.h_err && *s.h_err) {
+        const int err = *s.h_err; *s.h_err = 0;
+        cudaMemsetAsync(s.d_err, 0, sizeof(int), s.stream); cudaStreamSynchronize(s.stream);
+        return device_error(p, err);
+    }
     mark_frames(p, s.pending_beg, s.pending_cnt);
+    p->frames_retired.fetch_add(s.pending_cnt);
+    if (p->progress_fn) return publish_batch(p, s.pending_beg, s.pending_cnt);
     return 0;
+}
+
+// Slot ownership: the calling thread gets exclusive use of one slot (stream + staging buffers), with that slot's previous batch retired.
+static int acquire_slot(mdgpu_plan* p, Slot** out, int want = -1) {
+    Slot* s = nullptr;
+    {
+        std::unique_lock<std::mutex> lk(p->slot_mutex);
+        for (;;) {
+            const size_t S = p->slots.size();
+            if (want >= 0) { if (!p->slots[(size_t)want].owned) s = &p->slots[(size_t)want]; }
+            else for (size_t i = 0; i < S && !s; ++i) { Slot& c = p->slots[(p->next_slot + i) % S]; if (!c.owned) { s = &c; p->next_slot = (p->next_slot + i + 1) % S; } }
+            if (s) break;
+            p->slot_cv.wait(lk);
+        }
+        s->owned = true;
+    }
+    *out = s;
+    const int rc = retire_slot(p, *s);
+    if (rc) { std::lock_guard<std::mutex> lk(p->slot_mutex); s->owned = false; p->slot_cv.notify_all(); *out = nullptr; }
+    return rc;
+}
+static void release_slot(mdgpu_plan* p, Slot* s) {
+    if (!s) return;
+    { std::lock_guard<std::mutex> lk(p->slot_mutex); s->owned = false; }
+    p->slot_cv.notify_all();
+}
+// retire every slot (waits for all batches in flight, whoever enqueued them)
+static int drain_slots(mdgpu_plan* p) {
+    int rc = 0;
+    for (size_t i = 0; i < p->slots.size(); ++i) { Slot* s = nullptr; const int r = acquire_slot(p, &s, (int)i); if (r && !rc) rc = r; release_slot(p, s); }
+    return rc;
 }
 
 static const mdgpu_unitcell_t* cell_at(const mdgpu_unitcell_t* cells, size_t stride_bytes, size_t i) {
     return (const mdgpu_unitcell_t*)((const char*)cells + i * (stride_bytes ? stride_bytes : 0));
 }
+
+static int eval_host_frames_1(mdgpu_plan* p, const float* h_xyz, size_t frame_stride, size_t axis_stride, const mdgpu_unitcell_t* cells, size_t cell_stride_bytes, uint32_t frame_beg, uint32_t count);
+static int eval_trajectory_1(mdgpu_plan* p, const mdgpu_trajectory_i* traj, uint32_t frame_beg, uint32_t frame_end, uint32_t loader_threads);
+static int multi_eval_host_frames(mdgpu_plan* p, const float* h_xyz, size_t frame_stride, size_t axis_stride, const mdgpu_unitcell_t* cells, size_t cell_stride_bytes, uint32_t frame_beg, uint32_t count);
+static int multi_eval_trajectory(mdgpu_plan* p, const mdgpu_trajectory_i* traj, uint32_t frame_beg, uint32_t frame_end, uint32_t loader_threads);
+static int multi_sync(mdgpu_plan* p);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Several GPUs from ONE process (VIAMD is one process, src/main.cpp:982-1011): the root plan owns one peer plan per further device. A frame
+// range is cut into contiguous blocks, one per device, each block evaluated by its own host thread into that device's
+// integer accumulators — no data-path collective. The single exchange step happens at mdgpu_plan_sync: NCCL reduce(sum) of the RDF bins,
+// SDF voxels, density sums, per-frame rows and the (disjoint, zero elsewhere) temporal rows onto the root device over NVLink, where the
+// usual fold then runs; the peers' accumulators are zeroed so every contribution is counted once.
+// NCCL is bound at run time (dlopen "libnccl.so.2", or $MDGPU_NCCL_LIB): single-device users never load it, and a process that already
+// carries a NCCL (torch) shares that one.
+// ---------------------------------------------------------------------------------------------------------------
+static int nccl_load(NcclApi& n) {
+    if (n.lib) return 0;
+    const char* path = getenv("MDGPU_NCCL_LIB");
+    n.lib = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!n.lib) return fail(MDGPU_ERR_CUDA, "multi-device plan: cannot load NCCL (%s)", dlerror());
+    n.CommInitAll = (decltype(n.CommInitAll))dlsym(n.lib, "ncclCommInitAll"); n.CommDestroy = (decltype(n.CommDestroy))dlsym(n.lib, "ncclCommDestroy");
+    n.GroupStart = (decltype(n.GroupStart))dlsym(n.lib, "ncclGroupStart"); n.GroupEnd = (decltype(n.GroupEnd))dlsym(n.lib, "ncclGroupEnd");
+    n.Reduce = (decltype(n.Reduce))dlsym(n.lib, "ncclReduce"); n.GetErrorString = (decltype(n.GetErrorString))dlsym(n.lib, "ncclGetErrorString");
+    if (!n.CommInitAll || !n.CommDestroy || !n.GroupStart || !n.GroupEnd || !n.Reduce) return fail(MDGPU_ERR_CUDA, "multi-device plan: NCCL library lacks a required entry point");
+    return 0;
+}
+#define NCCL_TRY(m, expr) do { const int r_ = (expr); if (r_ != 0) return fail(MDGPU_ERR_CUDA, "%s failed: %s", #expr, (m)->nccl.GetErrorString ? (m)->nccl.GetErrorString(r_) : "nccl error"); } while (0)
+
+static void destroy_multi(mdgpu_plan* p) {
+    MultiDevice* m = p->multi; if (!m) return;
+    for (size_t g = 0; g < m->comms.size(); ++g) if (m->comms[g]) { cudaSetDevice(m->devices[g]); m->nccl.CommDestroy(m->comms[g]); }
+    for (auto* q : m->peers) destroy_plan(q);
+    delete m; p->multi = nullptr;
+}
+
+// contiguous block of device g out of G (the partition VIAMD's range task uses per thread, src/task_system.cpp:73-87)
+static void frame_block(uint32_t count, size_t g, size_t G, uint32_t& off, uint32_t& cnt) {
+    const uint64_t a = (uint64_t)count * g / G, b = (uint64_t)count * (g + 1) / G; off = (uint32_t)a; cnt = (uint32_t)(b - a);
+}
+
+template <typename F> static int multi_run(mdgpu_plan* p, F&& body) {
+    MultiDevice* m = p->multi; const size_t G = m->peers.size() + 1;
+    std::vector<int> rcs(G, 0); std::vector<std::string> msgs(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g) th.emplace_back([&, g]() { mdgpu_plan* q = g ? m->peers[g - 1] : p; rcs[g] = body(q, g, G); if (rcs[g]) msgs[g] = g_last_error; });
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < G; ++g) if (rcs[g]) { g_last_error = msgs[g]; return rcs[g]; }
+    return 0;
+}
+
+static int multi_eval_host_frames(mdgpu_plan* p, const float* h_xyz, size_t frame_stride, size_t axis_stride, const mdgpu_unitcell_t* cells, size_t cell_stride_bytes, uint32_t frame_beg, uint32_t count) {
+    return multi_run(p, [&](mdgpu_plan* q, size_t g, size_t G) -> int {
+        uint32_t off, cnt; frame_block(count, g, G, off, cnt); if (!cnt) return 0;
+        return eval_host_frames_1(q, h_xyz + (size_t)off * frame_stride, frame_stride, axis_stride, cell_at(cells, cell_stride_bytes, off), cell_stride_bytes, frame_beg + off, cnt);
+    });
+}
+static int multi_eval_trajectory(mdgpu_plan* p, const mdgpu_trajectory_i* traj, uint32_t frame_beg, uint32_t frame_end, uint32_t loader_threads) {
+    return multi_run(p, [&](mdgpu_plan* q, size_t g, size_t G) -> int {
+        uint32_t off, cnt; frame_block(frame_end - frame_beg, g, G, off, cnt); if (!cnt) return 0;
+        return eval_trajectory_1(q, traj, frame_beg + off, frame_beg + off + cnt, std::max<uint32_t>(1u, (loader_threads ? loader_threads : 4u) / (uint32_t)G));
+    });
+}
+
+// the exchange step: everything the peers accumulated moves onto the root device
+static int multi_sync(mdgpu_plan* p) {
+    MultiDevice* m = p->multi; const size_t G = m->peers.size() + 1;
+    uint64_t fresh = 0;
+    for (auto* q : m->peers) { CUDA_TRY(cudaSetDevice(q->device)); int rc = drain_slots(q); if (rc) return rc; CUDA_TRY(cudaDeviceSynchronize()); fresh += q->frames_retired.load(); }
+    CUDA_TRY(cudaSetDevice(p->device)); { int rc = drain_slots(p); if (rc) return rc; } CUDA_TRY(cudaDeviceSynchronize());
+    if (!fresh) return 0;
+    { int rc = nccl_load(m->nccl); if (rc) return rc; }
+    if (m->comms.empty()) { m->comms.assign(G, nullptr); NCCL_TRY(m, m->nccl.CommInitAll(m->comms.data(), (int)G, m->devices.data())); }
+    cudaEvent_t t0 = nullptr, t1 = nullptr; cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, 0);
+    const size_t F = p->num_frames; const size_t NV = (size_t)MDGPU_VOL_DIM * MDGPU_VOL_DIM * MDGPU_VOL_DIM;
+    NCCL_TRY(m, m->nccl.GroupStart());
+    for (size_t i = 0; i < p->props.size(); ++i) {
+        struct Buf { void* ptr[64]; size_t count; int type; };
+        auto reduce = [&](auto member, size_t count, int type) -> int {
+            if (!(p->props[i].*member)) return 0;
+            for (size_t g = 0; g < G; ++g) {
+                mdgpu_plan* q = g ? m->peers[g - 1] : p; void* buf = (void*)(q->props[i].*member);
+                cudaSetDevice(q->device);
+                const int r = m->nccl.Reduce(buf, buf, count, type, NCCL_SUM, 0, m->comms[g], 0);
+                if (r != 0) return r;
+            }
+            return 0;
+        };
+        const Prop& pr = p->props[i];
+        NCCL_TRY(m, reduce(&Prop::d_acc, MDGPU_DIST_BINS, NCCL_UINT64));
+        NCCL_TRY(m, reduce(&Prop::d_vol, NV, NCCL_UINT32));
+        NCCL_TRY(m, reduce(&Prop::d_frame_total, F, NCCL_UINT64));
+        NCCL_TRY(m, reduce(&Prop::d_frame_min, F, NCCL_UINT32));   // rows of frames a device did not evaluate are zero: the sum merges them
+        NCCL_TRY(m, reduce(&Prop::d_frame_max, F, NCCL_UINT32));
+        NCCL_TRY(m, reduce(&Prop::d_frame_min64, F, NCCL_UINT64));
+        NCCL_TRY(m, reduce(&Prop::d_frame_max64, F, NCCL_UINT64));
+        NCCL_TRY(m, reduce(&Prop::d_keep, F * MDGPU_DIST_BINS, NCCL_UINT32));
+        NCCL_TRY(m, reduce(&Prop::d_keep64, F * MDGPU_DIST_BINS, NCCL_UINT64));
+        NCCL_TRY(m, reduce(&Prop::d_temporal, F * pr.len, NCCL_FLOAT32));   // disjoint rows, zero elsewhere: x + 0 is exact
+    }
+    NCCL_TRY(m, m->nccl.GroupEnd());
+    for (auto* q : m->peers) { CUDA_TRY(cudaSetDevice(q->device)); CUDA_TRY(cudaDeviceSynchronize()); }
+    CUDA_TRY(cudaSetDevice(p->device)); cudaEventRecord(t1, 0); CUDA_TRY(cudaDeviceSynchronize());
+    { float ms = 0; if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) { m->last_reduce_ms = ms; m->reduces++; } cudaEventDestroy(t0); cudaEventDestroy(t1); }
+    for (auto* q : m->peers) {   // moved, not copied: zero the peers so the next exchange does not count them again
+        CUDA_TRY(cudaSetDevice(q->device));
+        for (auto& pr : q->props) {
+            if (pr.d_acc) CUDA_TRY(cudaMemset(pr.d_acc, 0, sizeof(unsigned long long) * MDGPU_DIST_BINS));
+            if (pr.d_vol) CUDA_TRY(cudaMemset(pr.d_vol, 0, sizeof(uint32_t) * NV));
+            if (pr.d_frame_total) CUDA_TRY(cudaMemset(pr.d_frame_total, 0, sizeof(unsigned long long) * F));
+            if (pr.d_frame_min) CUDA_TRY(cudaMemset(pr.d_frame_min, 0, sizeof(uint32_t) * F));
+            if (pr.d_frame_max) CUDA_TRY(cudaMemset(pr.d_frame_max, 0, sizeof(uint32_t) * F));
+            if (pr.d_frame_min64) CUDA_TRY(cudaMemset(pr.d_frame_min64, 0, sizeof(unsigned long long) * F));
+            if (pr.d_frame_max64) CUDA_TRY(cudaMemset(pr.d_frame_max64, 0, sizeof(unsigned long long) * F));
+            if (pr.d_keep) CUDA_TRY(cudaMemset(pr.d_keep, 0, sizeof(uint32_t) * F * MDGPU_DIST_BINS));
+            if (pr.d_keep64) CUDA_TRY(cudaMemset(pr.d_keep64, 0, sizeof(unsigned long long) * F * MDGPU_DIST_BINS));
+            if (pr.d_temporal) CUDA_TRY(cudaMemset(pr.d_temporal, 0, sizeof(float) * F * pr.len));
+        }
+        p->frames_retired.fetch_add(q->frames_retired.exchange(0));
+        std::lock_guard<std::mutex> la(p->mask_mutex); std::lock_guard<std::mutex> lb(q->mask_mutex);
+        for (size_t w = 0; w < p->frame_mask.size(); ++w) { p->frame_mask[w] |= q->frame_mask[w]; q->frame_mask[w] = 0; }
+    }
+    CUDA_TRY(cudaSetDevice(p->device));
+    p->dirty = true;
+    return 0;
+}
+
 
 extern "C" {
 
@@ -793,61 +1119,87 @@ int mdgpu_eval_device_frames(mdgpu_plan* p, const float* d_xyz, size_t frame_str
                              const mdgpu_unitcell_t* cells, size_t cell_stride_bytes, uint32_t frame_beg, uint32_t count) {
     if (!p || !d_xyz || !cells) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_eval_device_frames: null argument");
     if ((size_t)frame_beg + count > p->num_frames) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Invalid frame range");   // md_script.c:6594-6597
+    if (p->multi) return fail(MDGPU_ERR_UNSUPPORTED, "mdgpu_eval_device_frames: frames resident on one device cannot feed a multi-device plan; use the host or trajectory entry points");
     CUDA_TRY(cudaSetDevice(p->device));
     if (!count) return 0;
     int rc = ensure_slots(p, cell_at(cells, cell_stride_bytes, 0), false); if (rc) return rc;
     for (uint32_t b0 = 0; b0 < count; b0 += p->B) {
         if (p->interrupt.load()) return fail(MDGPU_ERR_INTERRUPTED, "evaluation interrupted");
         const uint32_t nb = std::min(p->B, count - b0);
-        Slot& s = p->slots[p->next_slot++ % p->slots.size()];
-        rc = retire_slot(p, s); if (rc) return rc;
-        for (uint32_t i = 0; i < nb; ++i) s.h_cells[i] = *cell_at(cells, cell_stride_bytes, b0 + i);
+        Slot* s = nullptr; rc = acquire_slot(p, &s); if (rc) return rc;
+        for (uint32_t i = 0; i < nb; ++i) s->h_cells[i] = *cell_at(cells, cell_stride_bytes, b0 + i);
         BatchFrames fr{ d_xyz + (size_t)b0 * frame_stride, frame_stride, axis_stride, nb };
-        rc = enqueue_batch(p, s, fr, frame_beg + b0); if (rc) return rc;
+        rc = enqueue_batch(p, *s, fr, frame_beg + b0, false);
+        release_slot(p, s);
+        if (rc) return rc;
     }
     return 0;
 }
 
+// Host frames -> the slot's staging. Compact plans gather the atoms the properties read (ingest threads, pinned staging, one DMA of
+// |needed| / num_atoms of the bytes); otherwise whole frames: straight from the caller's buffer when it is pinned, through staging when not.
 int mdgpu_eval_host_frames(mdgpu_plan* p, const float* h_xyz, size_t frame_stride, size_t axis_stride,
                            const mdgpu_unitcell_t* cells, size_t cell_stride_bytes, uint32_t frame_beg, uint32_t count) {
     if (!p || !h_xyz || !cells) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_eval_host_frames: null argument");
     if ((size_t)frame_beg + count > p->num_frames) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Invalid frame range");
+    if (p->multi) return multi_eval_host_frames(p, h_xyz, frame_stride, axis_stride, cells, cell_stride_bytes, frame_beg, count);
+    return eval_host_frames_1(p, h_xyz, frame_stride, axis_stride, cells, cell_stride_bytes, frame_beg, count);
+}
+}  // extern "C"
+
+static int eval_host_frames_1(mdgpu_plan* p, const float* h_xyz, size_t frame_stride, size_t axis_stride,
+                              const mdgpu_unitcell_t* cells, size_t cell_stride_bytes, uint32_t frame_beg, uint32_t count) {
     CUDA_TRY(cudaSetDevice(p->device));
     if (!count) return 0;
     int rc = ensure_slots(p, cell_at(cells, cell_stride_bytes, 0), true); if (rc) return rc;
     cudaPointerAttributes attr{}; bool pinned = false;
     if (cudaPointerGetAttributes(&attr, h_xyz) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost); else cudaGetLastError();
-    const size_t N = p->num_atoms, AS = p->axis_stride;
+    const bool c = p->compact;
+    const size_t N = p->num_atoms, AS = c ? p->axis_stride_c : p->axis_stride, M = p->num_atoms_c;
+    std::vector<cudaEvent_t> direct;   // copies that read the caller's buffer: it may be refilled once they are done
     for (uint32_t b0 = 0; b0 < count; b0 += p->B) {
         if (p->interrupt.load()) return fail(MDGPU_ERR_INTERRUPTED, "evaluation interrupted");
         const uint32_t nb = std::min(p->B, count - b0);
-        Slot& s = p->slots[p->next_slot++ % p->slots.size()];
-        rc = retire_slot(p, s); if (rc) return rc;
-        for (uint32_t i = 0; i < nb; ++i) s.h_cells[i] = *cell_at(cells, cell_stride_bytes, b0 + i);
+        Slot* s = nullptr; rc = acquire_slot(p, &s); if (rc) return rc;
+        for (uint32_t i = 0; i < nb; ++i) s->h_cells[i] = *cell_at(cells, cell_stride_bytes, b0 + i);
         const float* src = h_xyz + (size_t)b0 * frame_stride;
-        if (pinned) {
-            // pinned source: DMA straight from the caller's buffer
+        cudaError_t e = cudaSuccess;
+        if (c) {
+            float* dst = s->h_frames; const int32_t* idx = p->needed.data();
+            ingest_pool(p)->parallel_for(nb * 3, [&](uint32_t w) {
+                const uint32_t i = w / 3, ax = w % 3;
+                gather_axis(dst + ((size_t)i * 3 + ax) * AS, src + (size_t)i * frame_stride + (size_t)ax * axis_stride, idx, M);
+            });
+            e = cudaMemcpyAsync(s->d_frames, s->h_frames, sizeof(float) * (size_t)nb * 3 * AS, cudaMemcpyHostToDevice, s->stream);
+        } else if (pinned) {
             if (frame_stride == 3 * axis_stride && axis_stride == AS && AS == N) {   // fully contiguous: one linear DMA
-                CUDA_TRY(cudaMemcpyAsync(s.d_frames, src, sizeof(float) * (size_t)nb * 3 * AS, cudaMemcpyHostToDevice, s.stream));
+                e = cudaMemcpyAsync(s->d_frames, src, sizeof(float) * (size_t)nb * 3 * AS, cudaMemcpyHostToDevice, s->stream);
             } else if (frame_stride == 3 * axis_stride) {
-                CUDA_TRY(cudaMemcpy2DAsync(s.d_frames, sizeof(float) * AS, src, sizeof(float) * axis_stride, sizeof(float) * N,
-                                           (size_t)nb * 3, cudaMemcpyHostToDevice, s.stream));
+                e = cudaMemcpy2DAsync(s->d_frames, sizeof(float) * AS, src, sizeof(float) * axis_stride, sizeof(float) * N, (size_t)nb * 3, cudaMemcpyHostToDevice, s->stream);
             } else {
-                for (uint32_t i = 0; i < nb; ++i)
-                    CUDA_TRY(cudaMemcpy2DAsync(s.d_frames + (size_t)i * 3 * AS, sizeof(float) * AS, src + (size_t)i * frame_stride, sizeof(float) * axis_stride,
-                                               sizeof(float) * N, 3, cudaMemcpyHostToDevice, s.stream));
+                for (uint32_t i = 0; i < nb && e == cudaSuccess; ++i)
+                    e = cudaMemcpy2DAsync(s->d_frames + (size_t)i * 3 * AS, sizeof(float) * AS, src + (size_t)i * frame_stride, sizeof(float) * axis_stride,
+                                          sizeof(float) * N, 3, cudaMemcpyHostToDevice, s->stream);
             }
+            if (e == cudaSuccess) e = cudaEventRecord(s->copied, s->stream);
+            if (std::find(direct.begin(), direct.end(), s->copied) == direct.end()) direct.push_back(s->copied);
         } else {
             for (uint32_t i = 0; i < nb; ++i) for (int ax = 0; ax < 3; ++ax)
-                memcpy(s.h_frames + ((size_t)i * 3 + ax) * AS, src + (size_t)i * frame_stride + (size_t)ax * axis_stride, sizeof(float) * N);
-            CUDA_TRY(cudaMemcpyAsync(s.d_frames, s.h_frames, sizeof(float) * (size_t)nb * 3 * AS, cudaMemcpyHostToDevice, s.stream));
+                memcpy(s->h_frames + ((size_t)i * 3 + ax) * AS, src + (size_t)i * frame_stride + (size_t)ax * axis_stride, sizeof(float) * N);
+            e = cudaMemcpyAsync(s->d_frames, s->h_frames, sizeof(float) * (size_t)nb * 3 * AS, cudaMemcpyHostToDevice, s->stream);
         }
-        BatchFrames fr{ s.d_frames, 3 * AS, AS, nb };
-        rc = enqueue_batch(p, s, fr, frame_beg + b0); if (rc) return rc;
+        if (e != cudaSuccess) { release_slot(p, s); return fail(MDGPU_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
+        BatchFrames fr{ s->d_frames, 3 * AS, AS, nb };
+        rc = enqueue_batch(p, *s, fr, frame_beg + b0, c);
+        release_slot(p, s);
+        if (rc) return rc;
     }
+    // "copied host->device batch by batch inside the call": when the call returns, the caller's buffer has been read
+    for (cudaEvent_t ev : direct) CUDA_TRY(cudaEventSynchronize(ev));
     return 0;
 }
 
+extern "C" {
 // ---- XTC input ---------------------------------------------------------------------------------------------------------------
 static uint32_t xtc_be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 static float xtc_bef32(const uint8_t* p) { const uint32_t u = xtc_be32(p); float f; memcpy(&f, &u, 4); return f; }
@@ -896,7 +1248,9 @@ int mdgpu_eval_xtc_frames(mdgpu_plan* p, const uint8_t* h_blob, const uint64_t* 
     for (uint32_t i = 0; i < count; ++i) if (frame_offsets[i + 1] <= frame_offsets[i] || (frame_offsets[i] & 3u)) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Invalid frame offset range");
     mdgpu_unitcell_t first{};
     if (!xtc_header_cell(h_blob + frame_offsets[0], frame_offsets[1] - frame_offsets[0], &first, nullptr, nullptr)) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Magic number did not match");
-    int rc = ensure_slots(p, &first, true); if (rc) return rc;
+    if (p->multi) return fail(MDGPU_ERR_UNSUPPORTED, "XTC input is evaluated on one device; create a single-device plan");
+    std::lock_guard<std::mutex> xtc_guard(p->xtc_mutex);   // the scan stages are one pipeline: one XTC evaluation at a time per plan
+    int rc = ensure_slots(p, &first, false); if (rc) return rc;
     const size_t AS = p->axis_stride, NA = p->num_atoms;
     const uint32_t SB = p->B * XTC_SUPER;
     const uint32_t nsuper = (count + SB - 1) / SB;
@@ -925,21 +1279,30 @@ int mdgpu_eval_xtc_frames(mdgpu_plan* p, const uint8_t* h_blob, const uint64_t* 
         for (uint32_t b0 = 0; b0 < ns; b0 += p->B) {
             if (p->interrupt.load()) return fail(MDGPU_ERR_INTERRUPTED, "evaluation interrupted");
             const uint32_t nb = std::min(p->B, ns - b0);
-            Slot& s = p->slots[p->next_slot++ % p->slots.size()];
-            rc = retire_slot(p, s); if (rc) return rc;
-            for (uint32_t i = 0; i < nb; ++i) {
+            Slot* sp = nullptr; rc = acquire_slot(p, &sp); if (rc) return rc;
+            Slot& s = *sp;
+            bool ok = true;
+            for (uint32_t i = 0; i < nb && ok; ++i) {
                 const uint64_t o = frame_offsets[s0 + b0 + i];
-                if (!xtc_header_cell(h_blob + o, (size_t)(frame_offsets[s0 + b0 + i + 1] - o), &s.h_cells[i], nullptr, nullptr)) return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Magic number did not match");
+                ok = xtc_header_cell(h_blob + o, (size_t)(frame_offsets[s0 + b0 + i + 1] - o), &s.h_cells[i], nullptr, nullptr);
             }
-            CUDA_TRY(cudaStreamWaitEvent(s.stream, st.ready, 0));
+            if (!ok) { release_slot(p, sp); return fail(MDGPU_ERR_FRAME_SOURCE, "XTC: Magic number did not match"); }
+            cudaError_t e = cudaSuccess;
+            if (!s.d_xtc_frames) e = dalloc(&s.d_xtc_frames, (size_t)p->B * 3 * AS);   // whole decoded frames (global atom indices)
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s.stream, st.ready, 0);
+            if (e != cudaSuccess) { release_slot(p, sp); return fail(MDGPU_ERR_CUDA, "XTC stage set-up failed: %s", cudaGetErrorString(e)); }
             launch_xtc_expand(st.d_blob, st.d_off + b0, (uint32_t)NA, (int)nb, st.d_info + b0, st.d_rec + (size_t)b0 * NA, st.d_state + (size_t)b0 * NA, NA,
-                              s.d_frames, 3 * AS, AS, s.d_err, s.stream);
-            CUDA_TRY(cudaEventRecord(st.consumed[st.n_consumed++], s.stream));
-            BatchFrames fr{ s.d_frames, 3 * AS, AS, nb };
-            rc = enqueue_batch(p, s, fr, frame_beg + s0 + b0); if (rc) return rc;
+                              s.d_xtc_frames, 3 * AS, AS, s.d_err, s.stream);
+            cudaEventRecord(st.consumed[st.n_consumed++], s.stream);
+            BatchFrames fr{ s.d_xtc_frames, 3 * AS, AS, nb };
+            rc = enqueue_batch(p, s, fr, frame_beg + s0 + b0, false);
+            release_slot(p, sp);
+            if (rc) return rc;
         }
     }
     p->next_xtc += nsuper;
+    // the compressed bytes are read from the caller's buffer by the stage copies: wait for them, as mdgpu_eval_host_frames does for its source
+    for (auto& st : p->xtc) if (st.ready) CUDA_TRY(cudaEventSynchronize(st.ready));
     return 0;
 }
 
@@ -1031,6 +1394,9 @@ int mdgpu_xtc_decode_frames(int device, const uint8_t* h_blob, const uint64_t* f
     return rc;
 }
 
+// md_script_eval_frame_range's frame loop (md_script.c:6573-6612 -> eval_properties :5730): re-entrant on one plan from many threads with
+// disjoint ranges (VIAMD's enkiTS range task, task_system.cpp:73-87). Every call creates its own readers (:5754) — `loader_threads` of them —
+// which decode frames into a slot's pinned staging (compact plans: into a per-reader scratch frame, then the needed atoms are gathered).
 int mdgpu_eval_trajectory(mdgpu_plan* p, const mdgpu_trajectory_i* traj, uint32_t frame_beg, uint32_t frame_end, uint32_t loader_threads) {
     if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
     if (!traj || !traj->inst || !traj->get_header || !traj->init_reader) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Trajectory was null");
@@ -1038,17 +1404,29 @@ int mdgpu_eval_trajectory(mdgpu_plan* p, const mdgpu_trajectory_i* traj, uint32_
     if (!traj->get_header(traj->inst, &hdr) || hdr.num_frames == 0) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Trajectory was empty");
     if (frame_beg > frame_end || frame_end > hdr.num_frames || frame_end > p->num_frames) return fail(MDGPU_ERR_INVALID_ARG, "Script eval: Invalid frame range");
     if (hdr.num_atoms != p->num_atoms) return fail(MDGPU_ERR_INVALID_ARG, "trajectory has %zu atoms, plan has %zu", hdr.num_atoms, p->num_atoms);
+    if (p->multi) return multi_eval_trajectory(p, traj, frame_beg, frame_end, loader_threads);
+    return eval_trajectory_1(p, traj, frame_beg, frame_end, loader_threads);
+}
+}  // extern "C"
+
+static int eval_trajectory_1(mdgpu_plan* p, const mdgpu_trajectory_i* traj, uint32_t frame_beg, uint32_t frame_end, uint32_t loader_threads) {
     CUDA_TRY(cudaSetDevice(p->device));
     const uint32_t T = std::max(1u, std::min(loader_threads ? loader_threads : 4u, 64u));
     std::vector<mdgpu_trajectory_reader_i> readers(T);
     for (uint32_t t = 0; t < T; ++t) { memset(&readers[t], 0, sizeof(readers[t])); if (!traj->init_reader(&readers[t], traj->inst)) return fail(MDGPU_ERR_FRAME_SOURCE, "Failed to initialize trajectory reader for evaluation"); }
     auto free_readers = [&]() { for (auto& r : readers) if (r.free) r.free(&r); };
-    const size_t AS = p->axis_stride;
-    if (!p->have_init) {   // initial configuration = frame 0 (md_script.c:5808)
-        std::vector<float> tmp(3 * AS); mdgpu_frame_header_t fh{};
-        if (!readers[0].load_frame(readers[0].inst, 0, &fh, tmp.data(), tmp.data() + AS, tmp.data() + 2 * AS)) { free_readers(); return fail(MDGPU_ERR_FRAME_SOURCE, "Failed to load frame during evaluation"); }
-        int rc = mdgpu_plan_set_initial_frame(p, tmp.data(), tmp.data() + AS, tmp.data() + 2 * AS, &fh.unitcell); if (rc) { free_readers(); return rc; }
+    const bool c = p->compact;
+    const size_t ASF = p->axis_stride, AS = c ? p->axis_stride_c : p->axis_stride, M = p->num_atoms_c;
+    {   // initial configuration = frame 0 (md_script.c:5808); the first caller loads it
+        std::lock_guard<std::mutex> guard(p->init_mutex);
+        if (!p->have_init) {
+            std::vector<float> tmp(3 * ASF); mdgpu_frame_header_t fh{};
+            if (!readers[0].load_frame(readers[0].inst, 0, &fh, tmp.data(), tmp.data() + ASF, tmp.data() + 2 * ASF)) { free_readers(); return fail(MDGPU_ERR_FRAME_SOURCE, "Failed to load frame during evaluation"); }
+            int rc = mdgpu_plan_set_initial_frame(p, tmp.data(), tmp.data() + ASF, tmp.data() + 2 * ASF, &fh.unitcell); if (rc) { free_readers(); return rc; }
+        }
     }
+    std::vector<std::vector<float>> scratch(c ? T : 0);
+    for (auto& v : scratch) v.resize(3 * ASF);
     int rc = 0; bool slots_ready = false;
     for (uint32_t b0 = frame_beg; b0 < frame_end && !rc; b0 += p->B) {
         if (p->interrupt.load()) { rc = fail(MDGPU_ERR_INTERRUPTED, "evaluation interrupted"); break; }
@@ -1057,65 +1435,75 @@ int mdgpu_eval_trajectory(mdgpu_plan* p, const mdgpu_trajectory_i* traj, uint32_
             mdgpu_frame_header_t fh{}; if (!readers[0].load_frame(readers[0].inst, b0, &fh, nullptr, nullptr, nullptr)) fh.unitcell = p->init_cell;
             rc = ensure_slots(p, &fh.unitcell, true); if (rc) break; slots_ready = true;
         }
-        Slot& s = p->slots[p->next_slot++ % p->slots.size()];
-        rc = retire_slot(p, s); if (rc) break;
+        Slot* sp = nullptr; rc = acquire_slot(p, &sp); if (rc) break;
+        Slot& s = *sp;
         std::atomic<int> failed{0};
         auto work = [&](uint32_t t) {
             for (uint32_t i = t; i < nb; i += T) {
                 mdgpu_frame_header_t fh{};
                 float* dst = s.h_frames + (size_t)i * 3 * AS;
-                if (!readers[t].load_frame(readers[t].inst, (int64_t)(b0 + i), &fh, dst, dst + AS, dst + 2 * AS)) { failed = 1; return; }
+                if (c) {
+                    float* tmp = scratch[t].data();
+                    if (!readers[t].load_frame(readers[t].inst, (int64_t)(b0 + i), &fh, tmp, tmp + ASF, tmp + 2 * ASF)) { failed = 1; return; }
+                    for (int ax = 0; ax < 3; ++ax) gather_axis(dst + (size_t)ax * AS, tmp + (size_t)ax * ASF, p->needed.data(), M);
+                } else if (!readers[t].load_frame(readers[t].inst, (int64_t)(b0 + i), &fh, dst, dst + AS, dst + 2 * AS)) { failed = 1; return; }
                 s.h_cells[i] = fh.unitcell;
             }
         };
         if (T == 1) work(0);
         else { std::vector<std::thread> th; for (uint32_t t = 0; t < T; ++t) th.emplace_back(work, t); for (auto& x : th) x.join(); }
-        if (failed) { rc = fail(MDGPU_ERR_FRAME_SOURCE, "Failed to load frame during evaluation"); break; }
+        if (failed) { release_slot(p, sp); rc = fail(MDGPU_ERR_FRAME_SOURCE, "Failed to load frame during evaluation"); break; }
         cudaError_t e = cudaMemcpyAsync(s.d_frames, s.h_frames, sizeof(float) * (size_t)nb * 3 * AS, cudaMemcpyHostToDevice, s.stream);
-        if (e != cudaSuccess) { rc = fail(MDGPU_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+        if (e != cudaSuccess) { release_slot(p, sp); rc = fail(MDGPU_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
         BatchFrames fr{ s.d_frames, 3 * AS, AS, nb };
-        rc = enqueue_batch(p, s, fr, b0);
+        rc = enqueue_batch(p, s, fr, b0, c);
+        release_slot(p, sp);
     }
     free_readers();
     return rc;
 }
 
-void mdgpu_plan_interrupt(mdgpu_plan* p) { if (p) p->interrupt = true; }
+extern "C" {
+void mdgpu_plan_interrupt(mdgpu_plan* p) { if (!p) return; p->interrupt = true; if (p->multi) for (auto* q : p->multi->peers) q->interrupt = true; }
+}
 
 static double sphere_volume(double r) { return (4.0 / 3.0) * 3.1415926535897932 * (r * r * r); }
 
-int mdgpu_plan_sync(mdgpu_plan* p) {
-    if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
-    CUDA_TRY(cudaSetDevice(p->device));
-    for (auto& s : p->slots) { int rc = retire_slot(p, s); if (rc) return rc; }
-    if (!p->dirty) return 0;
-    CUDA_TRY(cudaDeviceSynchronize());
-    for (auto& s : p->slots) {
-        int err = 0; CUDA_TRY(cudaMemcpy(&err, s.d_err, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) { cudaMemset(s.d_err, 0, sizeof(int)); return fail(err, err == MDGPU_ERR_CAPACITY ? "a frame needs more cells than the plan reserved from its first frame (cell capacity %u); raise mdgpu_plan_options_t.cell_capacity" : (err == MDGPU_ERR_FRAME_SOURCE ? "XTC: Failed to decode frame data (%d)" : "device-side error %d"), err == MDGPU_ERR_CAPACITY ? p->cell_cap : (uint32_t)err); }
-    }
-    for (auto& t : p->timed) { float ms = 0; if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { p->timed_ms[t.kind] += ms; p->timed_n[t.kind] += 1; } cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
-    p->timed.clear();
+// temporal rows [beg, beg+cnt) that are already in the host values: per-frame aggregates + running min / max + ranges
+// (compute_min_max_mean_variance md_script.c:5646-5677: two passes over the frame's values, in float)
+static void fold_temporal_rows(Prop& pr, uint32_t f, bool reset) {
+    if (reset) { pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX; }
+    float mn, mx, s1, s2; fold_frame_values(pr.vptr + (size_t)f * pr.len, pr.len, mn, mx, s1, s2);
+    pr.data.min_value = std::min(pr.data.min_value, mn); pr.data.max_value = std::max(pr.data.max_value, mx);
+    if (pr.len > 1) { pr.amean[f] = s1; pr.avar[f] = s2; pr.aext[2 * f] = mn; pr.aext[2 * f + 1] = mx; }
+}
+static void temporal_ranges(Prop& pr) {
+    if (pr.op == MDGPU_OP_DISTANCE || pr.op == MDGPU_OP_DISTANCE_MIN || pr.op == MDGPU_OP_DISTANCE_MAX || pr.op == MDGPU_OP_DISTANCE_PAIR) { pr.data.min_range[0] = 0.0f; pr.data.max_range[0] = pr.data.max_value; }   // value_range {0, FLT_MAX} (:3884)
+    else { pr.data.min_range[0] = pr.data.min_value; pr.data.max_range[0] = pr.data.max_value; }
+}
 
-    // evaluated frames
-    std::vector<uint32_t> done;
-    { std::lock_guard<std::mutex> lk(p->mask_mutex);
-      for (size_t f = 0; f < p->num_frames; ++f) if (p->frame_mask[f >> 6] >> (f & 63) & 1ull) done.push_back((uint32_t)f); }
+// Fold the device accumulators of the distribution / volume properties into the host-visible property data, over the frames in `done`.
+// `st`: stream the copies run on (the fold of a running evaluation uses the plan's publication stream and never drains the device).
+static int fold_accumulators(mdgpu_plan* p, const std::vector<uint32_t>& done, uint64_t evaluated, cudaStream_t st) {
     const size_t F = p->num_frames;
     for (auto& pr : p->props) {
-        const uint64_t n = pr.frames_overridden ? pr.frames_accumulated : (uint64_t)done.size();
+        // mean divisor = number of frame evaluations that went into the accumulators (the reference's count++ moving average, md_script.c:5912:
+        // a frame evaluated twice counts twice); after a cross-GPU exchange the caller states the global count
+        const uint64_t n = pr.frames_overridden ? pr.frames_accumulated : evaluated;
         pr.data.frames_accumulated = n;
         if (pr.op == MDGPU_OP_RDF) {
             std::vector<unsigned long long> acc(MDGPU_DIST_BINS), tot(F); std::vector<uint32_t> mn(F), mx(F);
-            CUDA_TRY(cudaMemcpy(acc.data(), pr.d_acc, sizeof(unsigned long long) * MDGPU_DIST_BINS, cudaMemcpyDeviceToHost));
-            CUDA_TRY(cudaMemcpy(tot.data(), pr.d_frame_total, sizeof(unsigned long long) * F, cudaMemcpyDeviceToHost));
-            CUDA_TRY(cudaMemcpy(mn.data(), pr.d_frame_min, sizeof(uint32_t) * F, cudaMemcpyDeviceToHost));
-            CUDA_TRY(cudaMemcpy(mx.data(), pr.d_frame_max, sizeof(uint32_t) * F, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpyAsync(acc.data(), pr.d_acc, sizeof(unsigned long long) * MDGPU_DIST_BINS, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(tot.data(), pr.d_frame_total, sizeof(unsigned long long) * F, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(mn.data(), pr.d_frame_min, sizeof(uint32_t) * F, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(mx.data(), pr.d_frame_max, sizeof(uint32_t) * F, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
             // mean of the per-frame integer bins: exact sum, one division (the reference keeps a float cumulative moving
-            // average, md_script.c:5912-5921, which drifts by ~sqrt(n)*6e-8 from this value)
-            for (int b = 0; b < MDGPU_DIST_BINS; ++b) pr.values[b] = n ? (float)((double)acc[b] / (double)n) : 0.0f;
-            pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;
-            for (uint32_t f : done) { pr.data.min_value = std::min(pr.data.min_value, (float)mn[f]); pr.data.max_value = std::max(pr.data.max_value, (float)mx[f]); }
+            // average, md_script.c:5912-5921, which drifts by ~1e-5 from this value after 4096 frames: tests/test_oracle_golden.py)
+            for (int b = 0; b < MDGPU_DIST_BINS; ++b) pr.vptr[b] = n ? (float)((double)acc[b] / (double)n) : 0.0f;
+            float vmin = +FLT_MAX, vmax = -FLT_MAX;
+            for (uint32_t f : done) { vmin = std::min(vmin, (float)mn[f]); vmax = std::max(vmax, (float)mx[f]); }
+            pr.data.min_value = vmin; pr.data.max_value = vmax;
             // weights of the last evaluated frame (the reference copies "whichever frame finished last", :5924); compute_rdf :5323-5337
             if (!done.empty()) {
                 const float min_cutoff = pr.cutoff_min > 1e-3f ? pr.cutoff_min : 1e-3f, max_cutoff = pr.cutoff_max;
@@ -1123,41 +1511,95 @@ int mdgpu_plan_sync(mdgpu_plan* p) {
                 const double ref_rho = (double)tot[done.back()] / total_vol;
                 const float drf = (max_cutoff - min_cutoff) / (float)MDGPU_DIST_BINS; const double dr = drf;
                 double prev = 0;
-                for (int64_t i = 0; i < MDGPU_DIST_BINS; ++i) { const double sv = sphere_volume(min_cutoff + (i + 0.5) * dr); const double bv = sv - prev; prev = sv; pr.values[MDGPU_DIST_BINS + i] = (float)(ref_rho * bv); }
+                for (int64_t i = 0; i < MDGPU_DIST_BINS; ++i) { const double sv = sphere_volume(min_cutoff + (i + 0.5) * dr); const double bv = sv - prev; prev = sv; pr.vptr[MDGPU_DIST_BINS + i] = (float)(ref_rho * bv); }
             }
             pr.data.min_range[0] = pr.cutoff_min; pr.data.max_range[0] = pr.cutoff_max;   // value_range set by internal_rdf :5415
         } else if (pr.op == MDGPU_OP_SDF) {
-            launch_mean_u32(pr.d_vol, pr.d_vol_mean, pr.values.size(), n, 0);   // exact mean, one division per voxel, on the device
-            CUDA_TRY(cudaMemcpy(pr.values.data(), pr.d_vol_mean, sizeof(float) * pr.values.size(), cudaMemcpyDeviceToHost));
+            launch_mean_u32(pr.d_vol, pr.d_vol_mean, pr.values.size(), n, st);   // exact mean, one division per voxel, on the device
+            CUDA_TRY(cudaMemcpyAsync(pr.vptr, pr.d_vol_mean, sizeof(float) * pr.values.size(), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
             // min_value / max_value are never updated for volumes in the reference (md_script.c:5936-5956)
         } else if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
             std::vector<unsigned long long> acc(MDGPU_DIST_BINS), mn(F), mx(F);
-            CUDA_TRY(cudaMemcpy(acc.data(), pr.d_acc, sizeof(unsigned long long) * MDGPU_DIST_BINS, cudaMemcpyDeviceToHost));
-            CUDA_TRY(cudaMemcpy(mn.data(), pr.d_frame_min64, sizeof(unsigned long long) * F, cudaMemcpyDeviceToHost));
-            CUDA_TRY(cudaMemcpy(mx.data(), pr.d_frame_max64, sizeof(unsigned long long) * F, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpyAsync(acc.data(), pr.d_acc, sizeof(unsigned long long) * MDGPU_DIST_BINS, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(mn.data(), pr.d_frame_min64, sizeof(unsigned long long) * F, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(mx.data(), pr.d_frame_max64, sizeof(unsigned long long) * F, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
             const double unit = 1.0 / 16777216.0;
-            for (int b = 0; b < MDGPU_DIST_BINS; ++b) pr.values[b] = n ? (float)(((double)acc[b] * unit / (double)n) * pr.dens_factor) : 0.0f;
-            for (int b = 0; b < MDGPU_DIST_BINS; ++b) pr.values[MDGPU_DIST_BINS + b] = 1.0f;
-            pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;
+            for (int b = 0; b < MDGPU_DIST_BINS; ++b) pr.vptr[b] = n ? (float)(((double)acc[b] * unit / (double)n) * pr.dens_factor) : 0.0f;
+            for (int b = 0; b < MDGPU_DIST_BINS; ++b) pr.vptr[MDGPU_DIST_BINS + b] = 1.0f;
+            float vmin = +FLT_MAX, vmax = -FLT_MAX;
             for (uint32_t f : done) {
-                pr.data.min_value = std::min(pr.data.min_value, (float)((double)(float)((double)mn[f] * unit) * pr.dens_factor));
-                pr.data.max_value = std::max(pr.data.max_value, (float)((double)(float)((double)mx[f] * unit) * pr.dens_factor));
+                vmin = std::min(vmin, (float)((double)(float)((double)mn[f] * unit) * pr.dens_factor));
+                vmax = std::max(vmax, (float)((double)(float)((double)mx[f] * unit) * pr.dens_factor));
             }
+            pr.data.min_value = vmin; pr.data.max_value = vmax;
             const float rad = pr.re * 0.5f;   // value_range {-rad, rad} (:4983-4995)
             pr.data.min_range[0] = -rad; pr.data.max_range[0] = rad;
-        } else {
-            CUDA_TRY(cudaMemcpy(pr.values.data(), pr.d_temporal, sizeof(float) * F * pr.len, cudaMemcpyDeviceToHost));
-            pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;
-            for (uint32_t f : done) {   // compute_min_max_mean_variance (md_script.c:5646-5677): two passes over the frame's values, in float
-                float mn, mx, s1, s2; fold_frame_values(pr.values.data() + (size_t)f * pr.len, pr.len, mn, mx, s1, s2);
-                pr.data.min_value = std::min(pr.data.min_value, mn); pr.data.max_value = std::max(pr.data.max_value, mx);
-                if (pr.len > 1) { pr.agg_mean[f] = s1; pr.agg_var[f] = s2; pr.agg_ext[2 * f] = mn; pr.agg_ext[2 * f + 1] = mx; }
-            }
-            if (pr.op == MDGPU_OP_DISTANCE || pr.op == MDGPU_OP_DISTANCE_MIN || pr.op == MDGPU_OP_DISTANCE_MAX || pr.op == MDGPU_OP_DISTANCE_PAIR) { pr.data.min_range[0] = 0.0f; pr.data.max_range[0] = pr.data.max_value; }   // value_range {0, FLT_MAX} (:3884)
-            else { pr.data.min_range[0] = pr.data.min_value; pr.data.max_range[0] = pr.data.max_value; }
         }
     }
-    p->dirty = false;
+    return 0;
+}
+
+static void done_frames(mdgpu_plan* p, std::vector<uint32_t>& done) {
+    std::lock_guard<std::mutex> lk(p->mask_mutex);
+    for (size_t f = 0; f < p->num_frames; ++f) if (p->frame_mask[f >> 6] >> (f & 63) & 1ull) done.push_back((uint32_t)f);
+}
+
+// Called by the thread that retires a batch when a progress callback is installed (the md_script shim): the rows of the batch's temporal
+// properties go to the host values at once, the running means of distributions / volumes at most every 100 ms; then the callback — the
+// shim sets the frame-mask bits there, so VIAMD's UI (src/main.cpp:1513-1524) sees partial results while the evaluation runs.
+static int publish_batch(mdgpu_plan* p, uint32_t beg, uint32_t cnt) {
+    {
+        std::lock_guard<std::mutex> guard(p->sync_mutex);
+        if (!p->pub_stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->pub_stream, cudaStreamNonBlocking));
+        const uint32_t end = (uint32_t)std::min<size_t>((size_t)beg + cnt, p->num_frames);
+        for (auto& pr : p->props) if (pr.d_temporal && end > beg) {
+            CUDA_TRY(cudaMemcpyAsync(pr.vptr + (size_t)beg * pr.len, pr.d_temporal + (size_t)beg * pr.len, sizeof(float) * (size_t)(end - beg) * pr.len, cudaMemcpyDeviceToHost, p->pub_stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(p->pub_stream));
+        for (auto& pr : p->props) if (pr.d_temporal) { for (uint32_t f = beg; f < end; ++f) fold_temporal_rows(pr, f, false); temporal_ranges(pr); pr.data.frames_accumulated = p->frames_retired.load(); }
+        const auto now = std::chrono::steady_clock::now();
+        if (now - p->last_pub >= std::chrono::milliseconds(100)) {
+            p->last_pub = now;
+            std::vector<uint32_t> done; done_frames(p, done);
+            int rc = fold_accumulators(p, done, p->frames_retired.load(), p->pub_stream); if (rc) return rc;
+        }
+    }
+    p->progress_fn(p->progress_user, beg, cnt);
+    return 0;
+}
+
+extern "C" {
+
+int mdgpu_plan_sync(mdgpu_plan* p) {
+    if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
+    if (p->multi) { int rc = multi_sync(p); if (rc) return rc; }
+    CUDA_TRY(cudaSetDevice(p->device));
+    { int rc = drain_slots(p); if (rc) return rc; }
+    std::lock_guard<std::mutex> guard(p->sync_mutex);
+    if (!p->dirty.load()) return 0;
+    CUDA_TRY(cudaDeviceSynchronize());
+    p->dirty = false;   // batches enqueued from here on set it again
+    for (auto& s : p->slots) {
+        int err = 0; CUDA_TRY(cudaMemcpy(&err, s.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) { cudaMemset(s.d_err, 0, sizeof(int)); if (s.h_err) *s.h_err = 0; p->dirty = true; return device_error(p, err); }
+    }
+    {
+        std::lock_guard<std::mutex> tl(p->submit_mutex);
+        for (auto& t : p->timed) { float ms = 0; if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { p->timed_ms[t.kind] += ms; p->timed_n[t.kind] += 1; } cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+        p->timed.clear();
+    }
+    std::vector<uint32_t> done; done_frames(p, done);
+    { int rc = fold_accumulators(p, done, p->frames_retired.load(), 0); if (rc) { p->dirty = true; return rc; } }
+    const size_t F = p->num_frames;
+    for (auto& pr : p->props) if (pr.d_temporal) {
+        CUDA_TRY(cudaMemcpy(pr.vptr, pr.d_temporal, sizeof(float) * F * pr.len, cudaMemcpyDeviceToHost));
+        pr.data.min_value = +FLT_MAX; pr.data.max_value = -FLT_MAX;
+        for (uint32_t f : done) fold_temporal_rows(pr, f, false);
+        temporal_ranges(pr);
+        pr.data.frames_accumulated = pr.frames_overridden ? pr.frames_accumulated : p->frames_retired.load();
+    }
     return 0;
 }
 
@@ -1172,6 +1614,13 @@ int mdgpu_plan_property_index(const mdgpu_plan* p, const char* name) {
 int mdgpu_plan_property_data(mdgpu_plan* p, size_t prop, mdgpu_property_data_t* out) {
     if (!p || !out || prop >= p->props.size()) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_property_data: invalid argument");
     int rc = mdgpu_plan_sync(p); if (rc) return rc;
+    *out = p->props[prop].data;
+    return 0;
+}
+
+// the property data as last folded, without waiting for anything (progress callbacks read the scalars this way)
+int mdgpu_plan_property_peek(mdgpu_plan* p, size_t prop, mdgpu_property_data_t* out) {
+    if (!p || !out || prop >= p->props.size()) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_property_peek: invalid argument");
     *out = p->props[prop].data;
     return 0;
 }
@@ -1210,9 +1659,64 @@ int mdgpu_plan_property_aggregate(mdgpu_plan* p, size_t prop, float* out_mean, f
     int rc = mdgpu_plan_sync(p); if (rc) return rc;
     const Prop& pr = p->props[prop];
     if (pr.agg_mean.empty()) return fail(MDGPU_ERR_INVALID_ARG, "property '%s' has one value per frame: no aggregate (md_script.c:5618)", pr.name.c_str());
-    if (out_mean) memcpy(out_mean, pr.agg_mean.data(), sizeof(float) * num_frames);
-    if (out_var) memcpy(out_var, pr.agg_var.data(), sizeof(float) * num_frames);
-    if (out_ext) memcpy(out_ext, pr.agg_ext.data(), sizeof(float) * 2 * num_frames);
+    if (out_mean && out_mean != pr.amean) memcpy(out_mean, pr.amean, sizeof(float) * num_frames);
+    if (out_var && out_var != pr.avar) memcpy(out_var, pr.avar, sizeof(float) * num_frames);
+    if (out_ext && out_ext != pr.aext) memcpy(out_ext, pr.aext, sizeof(float) * 2 * num_frames);
+    return 0;
+}
+
+// The md_script shim hands over md_script_property_data_t::values (and the aggregate arrays): results are written where VIAMD reads them.
+int mdgpu_plan_bind_property_storage(mdgpu_plan* p, size_t prop, float* values, size_t num_values, float* agg_mean, float* agg_var, float* agg_ext) {
+    if (!p || prop >= p->props.size() || !values) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_bind_property_storage: invalid argument");
+    Prop& pr = p->props[prop];
+    if (num_values != pr.values.size()) return fail(MDGPU_ERR_INVALID_ARG, "property '%s' has %zu values, the bound array %zu", pr.name.c_str(), pr.values.size(), num_values);
+    { int rc = mdgpu_plan_sync(p); if (rc) return rc; }
+    std::lock_guard<std::mutex> guard(p->sync_mutex);
+    memcpy(values, pr.vptr, sizeof(float) * num_values);
+    pr.vptr = values; pr.bound = true; pr.data.values = values; pr.data.weights = pr.is_dist() ? values + MDGPU_DIST_BINS : nullptr;
+    if (!pr.agg_mean.empty() && agg_mean && agg_var && agg_ext) {
+        memcpy(agg_mean, pr.amean, sizeof(float) * p->num_frames); memcpy(agg_var, pr.avar, sizeof(float) * p->num_frames); memcpy(agg_ext, pr.aext, sizeof(float) * 2 * p->num_frames);
+        pr.amean = agg_mean; pr.avar = agg_var; pr.aext = agg_ext;
+    }
+    return 0;
+}
+
+int mdgpu_plan_set_progress_callback(mdgpu_plan* p, mdgpu_progress_fn fn, void* user) {
+    if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
+    std::lock_guard<std::mutex> guard(p->sync_mutex);
+    p->progress_fn = fn; p->progress_user = user;
+    if (p->multi) for (auto* q : p->multi->peers) { q->progress_fn = nullptr; }   // peers publish through the root at sync
+    return 0;
+}
+
+// Run the calling thread (and the threads it creates later: ingest pool, loaders) on the CPUs next to the GPU: reads the device's
+// local_cpulist from sysfs. Pinned buffers the thread allocates and first touches afterwards land on that NUMA node.
+int mdgpu_bind_host_to_device(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return fail(MDGPU_ERR_CUDA, "cudaDeviceGetPCIBusId(%d) failed", device); }
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[128]; snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r"); if (!f) return fail(MDGPU_ERR_UNSUPPORTED, "no %s", path);
+    char line[4096] = {0}; if (!fgets(line, sizeof(line), f)) { fclose(f); return fail(MDGPU_ERR_UNSUPPORTED, "empty %s", path); } fclose(f);
+    cpu_set_t set; CPU_ZERO(&set); int n = 0;
+    for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0; const int k = sscanf(tok, "%d-%d", &a, &b); if (k < 1) continue; if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &set); ++n; }
+    }
+    if (!n) return fail(MDGPU_ERR_UNSUPPORTED, "no CPUs listed in %s", path);
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return fail(MDGPU_ERR_UNSUPPORTED, "sched_setaffinity failed");
+    return n;
+}
+
+int mdgpu_plan_exchange_stats(mdgpu_plan* p, double* last_ms, uint64_t* count) {
+    if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
+    if (last_ms) *last_ms = p->multi ? p->multi->last_reduce_ms : 0.0; if (count) *count = p->multi ? p->multi->reduces : 0;
+    return 0;
+}
+int mdgpu_plan_ingest_info(mdgpu_plan* p, size_t* atoms_per_frame, uint32_t* threads) {
+    if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
+    if (atoms_per_frame) *atoms_per_frame = p->compact ? p->num_atoms_c : p->num_atoms;
+    if (threads) *threads = p->compact ? (uint32_t)(ingest_pool(p)->th.size() + 1) : 0u;
     return 0;
 }
 

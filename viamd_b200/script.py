@@ -274,20 +274,22 @@ class _Parser:
             raise ScriptError(f"procedure '{proc}' is outside the GPU hot-path scope")
         self.expect("ch", ")")
         if self.peek() == ("id", "in"):   # `expr in contexts` (evaluate_context md_script.c:3418): one value per context
-            self.next(); begs = self.contexts()
+            self.next(); begs, ends = self.contexts()
             if proc not in ("distance", "angle", "dihedral") or p.com_args or any(len(i) != 1 for i in p.idx):
                 raise ScriptError("`in` is lowered for distance / angle / dihedral with integer arguments only")
+            for i in p.idx:   # remap_index_to_context rejects indices outside the context (md_script_functions.inl:1023-1040)
+                if np.any(begs + int(i[0]) >= ends): raise ScriptError(f"supplied index ({int(i[0]) + 1}) is not within the range of a context")
             p = api.in_contexts(ident, p.op, [int(i[0]) for i in p.idx], begs)
         self.expect("ch", ";")
         return p
 
-    def contexts(self) -> np.ndarray:
-        """right-hand side of `in`: residue(a:b) | residue(:) | resname('X') -> first atom of each context (md_bitfield beg_bit)"""
+    def contexts(self):
+        """right-hand side of `in`: residue(a:b) | residue(:) | resname('X') -> (first atom, one past the last atom) of each context (md_bitfield beg_bit / end_bit)"""
         off = np.asarray(self.sys.res_atom_offset)
         f = self.expect("id")[1]; self.expect("ch", "(")
         if f == "residue":
             lo, hi = self._range(len(off) - 1); self.expect("ch", ")")
-            return off[lo:hi].astype(np.int64)
+            return off[lo:hi].astype(np.int64), off[lo + 1:hi + 1].astype(np.int64)
         if f == "resname":
             if self.sys.resname is None: raise ScriptError("system has no residue data")
             pats = [self.expect("str")[1]]
@@ -295,7 +297,7 @@ class _Parser:
             self.expect("ch", ")")
             rn = np.asarray(self.sys.resname); hit = np.zeros(len(rn), bool)
             for pt in pats: hit |= np.array([fnmatch.fnmatchcase(r, pt) for r in rn])
-            return off[:-1][hit].astype(np.int64)
+            return off[:-1][hit].astype(np.int64), off[1:][hit].astype(np.int64)
         raise ScriptError(f"unsupported context expression '{f}'")
 
 
