@@ -1,23 +1,31 @@
 #!/usr/bin/env python
-"""bench.py — frames/s of the md_script per-frame hot path (RDF + SDF evaluation) on N B200s, next to the reference CPU path.
+"""bench.py — frames/s of the md_script per-frame hot path on N B200s, next to the reference CPU path.
 
-Metric / config (BASELINE.json): "frames/sec RDF+SDF eval, 100k-atom synthetic traj". Workload = synthetic water box
+Metric / config (BASELINE.json): "frames/sec RDF+SDF eval, 100k-atom synthetic traj". Default workload = synthetic water box
 n=32 (98 304 atoms, 32 768 O, L = 99.328 A, viamd_b200/csrc/synth.h), script
     r = rdf(element('O'), element('O'), 10.0);  v = sdf(residue(1:1000), element('O'), 10.0);
 i.e. BASELINE configs[1] and configs[2] evaluated together on every frame, as VIAMD evaluates all properties of a script per frame.
+`--config 2 | 3 | 4` select BASELINE configs[1] (rdf alone), configs[2] (sdf alone), configs[3] (1M-atom membrane: lipid-tail rdf +
+density_z over all atoms) instead; the line then carries that config's own metric name.
 
 A "step" = one pass of the hot path over one batch of `--frames-per-step` frames. Every step reads different frames (no frame is
-reused inside the timed region), and one step's input (frames_per_step x 1.18 MB) is far larger than the 126 MB L2.
+reused inside the timed region), and one step's input is far larger than the 126 MB L2.
 
   value : whole-job frames/s with the frames already resident in HBM when the timed region starts (device stopwatch: CUDA events
           on the library's streams, max over ranks).
-  e2e   : same metric through the public host API with HOST (pinned) buffers: every step copies its frames host->device and reads the
-          step's results (RDF bins/weights 8 KB + SDF volume 8 MB) back to the host inside the timed region.
+  e2e   : same metric through the public host API with HOST (pinned) buffers: every step brings its frames host->device — the library
+          gathers the atoms the script reads into pinned staging (ingest threads) and copies those — and reads the step's results (RDF
+          bins/weights 8 KB + SDF volume 8 MB) back to the host inside the timed region.
+  roofline : the dominant kernel, timed ALONE (a second plan with one stream, CUDA events around each launch): `achieved` = algorithmic
+          DRAM bytes / that time against the measured HBM peak, as the contract asks — and `fp32`, the bound that
+          actually holds for the pair kernel: pair tests the kernel executed (device counter, padding lanes included; tests avoided by
+          the cull and the symmetric mode are NOT counted) x 9 FP32 lane-operations / time, against SMs x 128 lanes x clock.
   N > 1 : frames are sharded contiguously per rank (weak scaling: every rank processes frames_per_step frames per step); one NCCL
-          all-reduce of the RDF bins and SDF voxel grid at the end, inside the timed region.
+          all-reduce of the RDF bins and SDF voxel grid at the end, inside the timed region; per-rank and all-reduce times in the line.
 
 `--impl reference` times the reference's own CPU md_script_eval_frame_range (oracle/_ref/ref_harness_fast: the unmodified mdlib
-sources compiled with their shipped flags) on all host cores for the same script/workload, on a bounded sample of frames per step.
+sources compiled with their shipped -O3 -ffast-math flags) on all host cores for the same script/workload: ONE process, frames already in
+memory, untimed warm-up passes inside it, every step a bounded sample of 8 frames per thread.
 """
 from __future__ import annotations
 
@@ -32,12 +40,26 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "frames/sec RDF+SDF eval, 100k-atom synthetic traj"
 UNIT = "frames/s"
-SCRIPT = "r = rdf(element('O'), element('O'), 10.0); v = sdf(residue(1:1000), element('O'), 10.0);"
 WATER_N, WATER_SEED = 32, 1234
-WORKLOAD = (f"BASELINE configs[1]+[2] on one trajectory: synthetic water n={WATER_N} ({3 * WATER_N ** 3} atoms, {WATER_N ** 3} O, "
-            f"L={WATER_N * 3.104:.3f} A), script: {SCRIPT}")
+MEMB = (38, 100, 48, 4321)   # nl, nw_xy, nwz, seed -> 994 656 atoms
+CONFIGS = {
+    "bench": dict(metric="frames/sec RDF+SDF eval, 100k-atom synthetic traj", system="water",
+                  script="r = rdf(element('O'), element('O'), 10.0); v = sdf(residue(1:1000), element('O'), 10.0);",
+                  what="BASELINE configs[1]+[2] on one trajectory", fps=4736, results=("r", "v")),
+    "2": dict(metric="frames/sec rdf(O,O,10) eval, 100k-atom synthetic traj", system="water",
+              script="r = rdf(element('O'), element('O'), 10.0);", what="BASELINE configs[1]", fps=4736, results=("r",)),
+    "3": dict(metric="frames/sec sdf(1000 structures, O, 10) eval, 100k-atom synthetic traj", system="water",
+              script="v = sdf(residue(1:1000), element('O'), 10.0);", what="BASELINE configs[2]", fps=4736, results=("v",)),
+    "4": dict(metric="frames/sec lipid-tail rdf + density_z eval, 1M-atom synthetic membrane", system="membrane",
+              script="rt = rdf(name('C2*'), name('C2*'), 12.0); dz = density_z(all);", what="BASELINE configs[3]", fps=288, results=("rt", "dz")),
+}
+
+
+def workload_string(cfg):
+    if cfg["system"] == "water":
+        return (f"{cfg['what']}: synthetic water n={WATER_N} ({3 * WATER_N ** 3} atoms, {WATER_N ** 3} O, L={WATER_N * 3.104:.3f} A), script: {cfg['script']}")
+    return f"{cfg['what']}: synthetic coarse-grained membrane (994656 atoms, 12-bead lipids + solvent beads, cell 304 x 304 x 111.6 A), script: {cfg['script']}"
 
 
 def dist_env():
@@ -114,46 +136,59 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
 
 
-def measured_traffic(frames_per_launch: float):
-    """dram__bytes_read+write of the dominant kernel per launch, from the committed ncu --set full capture (scaled to this run's
-    frames per launch); None when no capture is recorded."""
-    p = os.path.join(ROOT, "profiles", "rdf_traffic.json")
+def measured_traffic(kernel: str, frames_per_launch: float):
+    """dram__bytes_read+write of `kernel` per launch, from the committed ncu --set full capture of this round (profiles/r2_traffic.json,
+    scaled to this run's frames per launch); None when no capture is recorded."""
     try:
-        t = json.load(open(p))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[kernel]
         return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (frames_per_launch / t["frames_per_launch"])
     except Exception:
         return None
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 def harness_path(kind="fast"):
     return os.path.join(ROOT, "oracle", "_ref", f"ref_harness_{kind}")
 
 
-def ensure_water_gro(tmpdir):
+def ensure_gro(cfg, tmpdir):
     tool = os.path.join(ROOT, "oracle", "build", "synth_tool")
     if not os.path.exists(tool):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
-    gro = os.path.join(tmpdir, f"water{WATER_N}_{WATER_SEED}.gro")
-    if not os.path.exists(gro):
-        subprocess.check_call([tool, "water-gro", str(WATER_N), str(WATER_SEED), gro])
-    return gro
+    if cfg["system"] == "water":
+        gro = os.path.join(tmpdir, f"water{WATER_N}_{WATER_SEED}.gro")
+        if not os.path.exists(gro): subprocess.check_call([tool, "water-gro", str(WATER_N), str(WATER_SEED), gro])
+        return gro, f"synthwater:{WATER_N}:{WATER_SEED}:%d"
+    gro = os.path.join(tmpdir, "membrane_%d_%d_%d_%d.gro" % MEMB)
+    if not os.path.exists(gro): subprocess.check_call([tool, "membrane-gro", *map(str, MEMB), gro])
+    return gro, "synthmembrane:%d:%d:%d:%d:" % MEMB + "%d"
 
 
-def run_reference_sample(frames: int, threads: int, repeat: int = 1, total_frames: int = 1 << 20):
-    """Reference CPU md_script_eval_frame_range on `frames` frames with `threads` threads. Returns dict or None."""
+def run_reference(cfg, frames: int, threads: int, repeat: int, warmup: int):
+    """The reference's CPU md_script_eval_frame_range on `frames` in-memory frames with `threads` threads: ONE process, `warmup` untimed
+    and `repeat` timed full passes inside it (oracle/ref_harness.c mode `time`). Returns the harness's JSON dict or None."""
     h = harness_path("fast")
     if not os.path.exists(h):
         return None
-    tmp = os.environ.get("TMPDIR", "/tmp")
-    gro = ensure_water_gro(tmp)
-    out = subprocess.run([h, "time", "--sys", gro, "--traj", f"synthwater:{WATER_N}:{WATER_SEED}:{total_frames}", "--script", SCRIPT,
-                          "--frames", f"0:{frames}", "--threads", str(threads), "--repeat", str(repeat)], capture_output=True, text=True)
+    gro, spec = ensure_gro(cfg, os.environ.get("TMPDIR", "/tmp"))
+    out = subprocess.run([h, "time", "--sys", gro, "--traj", spec % frames, "--script", cfg["script"], "--frames", f"0:{frames}", "--threads", str(threads),
+                          "--repeat", str(repeat), "--warmup", str(warmup)], capture_output=True, text=True)
     for line in out.stdout.splitlines():
         if line.startswith("{"):
             return json.loads(line)
@@ -162,7 +197,7 @@ def run_reference_sample(frames: int, threads: int, repeat: int = 1, total_frame
 
 
 def oracle_port_sample(frames: int):
-    """Fallback CPU baseline: the plain-C oracle port on one core (kind 'port')."""
+    """CPU baseline when the reference harness is not built: the plain-C oracle port on one core (kind 'port'), water workload."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import oracle_lib as O
@@ -180,34 +215,34 @@ def oracle_port_sample(frames: int):
     return {"frames": frames, "threads": 1, "best_s": dt, "frames_per_s": frames / dt}
 
 
-def impl_reference(args):
+CPU_NOTE = ("unmodified mdlib sources, flags as shipped (-O3 -mavx2 -mfma -ffast-math; parity is pinned against the strict-IEEE build of the same sources), "
+            "one process, frames generated into memory before the clock starts, untimed warm-up passes inside the process")
+
+
+def cpu_sample_frames(cfg, threads):
+    return max(8 * threads, 16) if cfg["system"] == "water" else max(threads, 8)   # a membrane frame is 12 MB and ~10x the work
+
+
+def impl_reference(args, cfg):
     rank, local_rank, world = dist_env()
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    threads = cores
-    # bounded sample per step: ~2 frames per thread, so K+W steps finish within minutes even on few cores
-    sample = max(2 * threads, 16)
-    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    threads = os.cpu_count() or 1
+    sample = cpu_sample_frames(cfg, threads)
+    line = {"impl": "reference", "metric": cfg["metric"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": sample, "threads": threads}}
-    if os.path.exists(harness_path("fast")):
-        for _ in range(args.warmup):
-            run_reference_sample(sample, threads)
-        t_total, frames_total = 0.0, 0
-        for _ in range(args.steps):
-            r = run_reference_sample(sample, threads)
-            t_total += r["best_s"]; frames_total += r["frames"]
-        kind = "reference"
+            "config": {"workload": workload_string(cfg), "frames_per_step": sample, "threads": threads, "host_cpu": cpu_model()}}
+    r = run_reference(cfg, sample, threads, max(1, args.steps), max(1, args.warmup))
+    if r:
+        t_total = sum(r["times_s"]); frames_total = r["frames"] * len(r["times_s"])
+        kind, note = "reference", CPU_NOTE
     else:
-        t_total, frames_total = 0.0, 0
-        for _ in range(max(1, min(args.steps, 3))):
-            r = oracle_port_sample(4); t_total += r["best_s"]; frames_total += r["frames"]
-        kind, threads, sample = "port", 1, 4
+        r = oracle_port_sample(4); t_total, frames_total = r["best_s"], r["frames"]
+        kind, threads, sample, note = "port", 1, 4, "oracle/md_oracle.c scalar port (reference harness not built)"
     v = frames_total / t_total
     line.update({"value": v, "ms_per_step": 1e3 * t_total / max(1, args.steps),
-                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
-                                  "sample": f"{sample} frames per step x {args.steps} steps of the same workload, in-memory trajectory"},
+                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "host_cpu": cpu_model(),
+                                  "sample": f"{sample} frames ({sample // max(threads, 1)} per thread) per step x {args.steps} steps of the same workload; {note}"},
                  "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     emit(line)
     return 0
@@ -224,6 +259,42 @@ def emit(line):
     else: os.write(_REAL_STDOUT, data)
 
 
+class Workload:
+    """system + device-resident synthetic frames of one config"""
+
+    def __init__(self, vb, cfg, dev, rank, frames_local):
+        import numpy as np
+        self.vb, self.cfg, self.dev = vb, cfg, dev
+        if cfg["system"] == "water":
+            self.base, L = vb.synth_water_base(WATER_N, WATER_SEED); self.na = self.base.shape[1]
+            self.sysm = vb.water_system(WATER_N); self.cell = vb.UnitCell.from_basis(L, L, L); self.mol = None
+            self.f0 = vb.synth_water_frames_host(WATER_N, WATER_SEED, self.base, 0, 1)
+        else:
+            self.base, whole, self.mol, L3 = vb.synth_membrane_base(*MEMB); self.na = self.base.shape[1]
+            self.sysm = vb.membrane_system(*MEMB[:3]); self.cell = vb.UnitCell.from_basis(*L3)
+            self.f0 = vb.synth_membrane_frames_host(*MEMB, self.base, self.mol, 0, 1)
+        self.props = vb.compile_script(cfg["script"], self.sysm)
+        self.fstride = 3 * self.na
+        self.d_base = vb.device_alloc(dev, self.base.nbytes); vb.memcpy_h2d(dev, self.d_base, self.base.ctypes.data, self.base.nbytes)
+        self.d_mol = None
+        if self.mol is not None:
+            self.d_mol = vb.device_alloc(dev, self.mol.nbytes); vb.memcpy_h2d(dev, self.d_mol, self.mol.ctypes.data, self.mol.nbytes)
+        self.d_frames = vb.device_alloc(dev, frames_local * self.fstride * 4)
+        if cfg["system"] == "water":
+            vb.synth_water_frames_device(dev, WATER_N, WATER_SEED, self.d_base, rank * frames_local, frames_local, self.d_frames, self.fstride, self.na)
+        else:
+            vb.synth_membrane_frames_device(dev, *MEMB, self.d_base, self.d_mol, rank * frames_local, frames_local, self.d_frames, self.fstride, self.na)
+
+    def plan(self, num_frames, **kw):
+        p = self.vb.Plan(self.sysm, self.props, num_frames, device=self.dev, **kw)
+        p.set_initial_frame(*self.f0[0], self.cell)   # frame 0 of the trajectory is the initial configuration on every rank
+        return p
+
+    def free(self):
+        for p in (self.d_base, self.d_mol, self.d_frames):
+            if p: self.vb.device_free(self.dev, p)
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush(); _REAL_STDOUT = os.dup(1); os.dup2(2, 1)
@@ -232,15 +303,20 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=4736)   # 32 x 148 frames
+    ap.add_argument("--config", default="bench", choices=list(CONFIGS))
+    ap.add_argument("--frames-per-step", type=int, default=0)   # 0 = the config's default (32 x 148 frames for the water box)
     ap.add_argument("--batch-frames", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--rdf-variant", type=int, default=0)
+    ap.add_argument("--ingest-mode", type=int, default=0)       # 1 = whole frames cross PCIe (the round-1 behaviour)
+    ap.add_argument("--ingest-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-iso", action="store_true")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        return impl_reference(args)
+        return impl_reference(args, cfg)
 
     import numpy as np
     import torch
@@ -255,27 +331,21 @@ def main():
     dev = local_rank
     if vb.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    # this rank's host side (pinned staging, ingest threads, this thread) next to its GPU: GPU0-3 / GPU4-7 hang off different NUMA nodes
+    numa_cpus = vb.bind_host_to_device(dev)
 
-    K, W, FPS = args.steps, max(args.warmup, 3), args.frames_per_step
-    n, seed = WATER_N, WATER_SEED
-    base, L = vb.synth_water_base(n, seed); na = base.shape[1]
-    sysm = vb.water_system(n)
-    props = vb.compile_script(SCRIPT, sysm)
+    K, W = args.steps, max(args.warmup, 3)
+    FPS = args.frames_per_step or cfg["fps"]
+    B = args.batch_frames or (148 if cfg["system"] == "water" else 24)
     total_steps = W + K
+    na_est = 3 * WATER_N ** 3 if cfg["system"] == "water" else 994656
     # all (warm-up + timed) steps read distinct device-resident frames; keep that shard under ~60 GB of the 180 GB HBM
-    max_fps = int(60e9 // (total_steps * 3 * na * 4)) // 148 * 148
-    FPS = max(148, min(FPS, max_fps))
+    max_fps = int(60e9 // (total_steps * 3 * na_est * 4)) // B * B
+    FPS = max(B, min(FPS, max_fps))
     frames_local = total_steps * FPS
-    plan = vb.Plan(sysm, props, frames_local, device=dev, batch_frames=args.batch_frames, num_streams=args.streams, rdf_variant=args.rdf_variant)
-    cell = vb.UnitCell.from_basis(L, L, L)
-    f0 = vb.synth_water_frames_host(n, seed, base, 0, 1)
-    plan.set_initial_frame(*f0[0], cell)   # frame 0 of the trajectory is the initial configuration on every rank
-
-    # ---- device-resident frames of this rank's shard: global frame index = rank * frames_local + i
-    fstride = 3 * na
-    d_base = vb.device_alloc(dev, base.nbytes); vb.memcpy_h2d(dev, d_base, base.ctypes.data, base.nbytes)
-    d_frames = vb.device_alloc(dev, frames_local * fstride * 4)
-    vb.synth_water_frames_device(dev, n, seed, d_base, rank * frames_local, frames_local, d_frames, fstride, na)
+    wl = Workload(vb, cfg, dev, rank, frames_local)
+    na, fstride, cell = wl.na, wl.fstride, wl.cell
+    plan = wl.plan(frames_local, batch_frames=B, num_streams=args.streams, rdf_variant=args.rdf_variant, ingest_mode=args.ingest_mode, ingest_threads=args.ingest_threads)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -284,13 +354,12 @@ def main():
         torch.cuda.synchronize(dev)
 
     def step_device(i):
-        plan.eval_device_frames(d_frames + i * FPS * fstride * 4, fstride, na, cell, i * FPS, FPS)
+        plan.eval_device_frames(wl.d_frames + i * FPS * fstride * 4, fstride, na, cell, i * FPS, FPS)
 
     # ---- warm-up (untimed)
     for i in range(W):
         step_device(i)
     plan.sync()
-    plan.enable_kernel_timing(True)
     vb.launch_count(reset=True)
     sampler = ClockSampler(dev); sampler.start()
     barrier()
@@ -298,39 +367,47 @@ def main():
     t_wall0 = time.perf_counter()
     for i in range(W, W + K):
         step_device(i)
+    ms_allreduce = 0.0
     if world > 1:
         plan.sync()
+        ta = time.perf_counter()
         vdist.allreduce_plan(plan, total_frames=world * (W + K) * FPS)   # the one exchange step: bins + voxels over NCCL
+        ms_allreduce = (time.perf_counter() - ta) * 1e3
     ms_dev = plan.timer_end()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     launches = vb.launch_count()
-    plan.enable_kernel_timing(False)
-    k_ms, k_n = plan.kernel_time_ms("k_rdf_pairs")
+    ms_rank = ms_dev; per_rank_ms = [ms_dev]; per_rank_ar = [ms_allreduce]
     if world > 1:
-        t = torch.tensor([ms_dev], dtype=torch.float64, device=f"cuda:{dev}")
-        tdist.all_reduce(t, op=tdist.ReduceOp.MAX); ms_dev = float(t.item())
+        t = torch.tensor([ms_dev, ms_allreduce], dtype=torch.float64, device=f"cuda:{dev}")
+        g = [torch.zeros_like(t) for _ in range(world)]; tdist.all_gather(g, t)
+        per_rank_ms = [float(x[0]) for x in g]; per_rank_ar = [float(x[1]) for x in g]; ms_dev = max(per_rank_ms)
         t = torch.tensor([float(launches)], dtype=torch.float64, device=f"cuda:{dev}")
         tdist.all_reduce(t, op=tdist.ReduceOp.SUM); launches = int(t.item())
     value = world * K * FPS / (ms_dev * 1e-3)
-    d_r = plan.property_data("r"); d_v = plan.property_data("v")
-    checks = {"rdf_pairs_per_frame": float(np.float64(d_r.values[:1024]).sum()), "sdf_counts_per_frame": float(np.float64(d_v.values).sum())}
+    checks = {}
+    for name in cfg["results"]:
+        d = plan.property_data(name)
+        checks[name + "_sum_per_frame"] = float(np.float64(d.values[:1024] if d.weights is not None else d.values).sum())
 
-    # ---- end-to-end through the host API: pinned host frames -> H2D -> kernels -> D2H of the step's results
+    # ---- end-to-end through the host API: pinned host frames -> (gather of the atoms the script reads) -> H2D -> kernels -> D2H of the step's results
     e2e = None
     if not args.no_e2e:
-        plan.clear(); plan.set_initial_frame(*f0[0], cell)
+        plan.clear(); plan.set_initial_frame(*wl.f0[0], cell)
         nbuf = 2
         h_ptrs = [vb.host_alloc_pinned(FPS * fstride * 4) for _ in range(nbuf)]
-        for b, hp in enumerate(h_ptrs):   # fill the pinned staging buffers from the device-generated frames (exact same data)
-            vb.memcpy_d2h(dev, hp, d_frames + b * FPS * fstride * 4, FPS * fstride * 4)
+        for b, hp in enumerate(h_ptrs):   # fill the pinned buffers from the device-generated frames (exactly the frames of the device run)
+            vb.memcpy_d2h(dev, hp, wl.d_frames + b * FPS * fstride * 4, FPS * fstride * 4)
         Ke = max(2, min(K, 4))
+        atoms_copied, ingest_threads = plan.ingest_info()
 
         def step_host(i):
             plan.eval_host_ptr(h_ptrs[i % nbuf], fstride, na, cell, i * FPS, FPS)
-            dr = plan.property_data("r"); dv = plan.property_data("v")   # sync + D2H of bins and volume
-            return dr.values[0] + dv.values[0]
+            s = 0.0
+            for name in cfg["results"]:   # sync + D2H of the step's results
+                s += float(plan.property_data(name).values[0])
+            return s
 
         for i in range(2):
             step_host(i)
@@ -340,56 +417,105 @@ def main():
             step_host(i)
         barrier()
         dt = time.perf_counter() - t0
+        per_rank_e2e = [dt]
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{dev}")
-            tdist.all_reduce(t, op=tdist.ReduceOp.MAX); dt = float(t.item())
-        e2e = {"value": world * Ke * FPS / dt, "unit": UNIT, "h2d_bytes_per_step": FPS * fstride * 4,
-               "d2h_bytes_per_step": 2 * 1024 * 8 + 128 ** 3 * 4 + 2 * frames_local * 16, "steps": Ke}
+            g = [torch.zeros_like(t) for _ in range(world)]; tdist.all_gather(g, t); per_rank_e2e = [float(x[0]) for x in g]; dt = max(per_rank_e2e)
+        d2h = sum((2 * 1024 * 4) if plan.property_data(n).weights is not None else plan.property_data(n).values.size * 4 for n in cfg["results"])
+        e2e = {"value": world * Ke * FPS / dt, "unit": UNIT, "h2d_bytes_per_step": FPS * 3 * atoms_copied * 4, "d2h_bytes_per_step": d2h, "steps": Ke,
+               "host_frame_bytes_per_step": FPS * fstride * 4,
+               "ingest": {"atoms_copied_per_frame": atoms_copied, "atoms_per_frame": na, "gather_threads": ingest_threads,
+                          "note": "the library gathers the atoms the script reads out of the caller's whole frames into pinned staging and copies only those"
+                                  if atoms_copied < na else "whole frames are copied"},
+               "numa_bound_cpus": numa_cpus, "per_rank_s": per_rank_e2e}
         for hp in h_ptrs:
             vb.host_free_pinned(hp)
 
+    # ---- the kernels alone: a second plan with ONE stream, CUDA events around every launch, device counter of executed pair tests
+    iso = {}
+    if rank == 0 and not args.no_iso:
+        nb_iso = 6
+        p1 = wl.plan(frames_local, batch_frames=B, num_streams=1, rdf_variant=args.rdf_variant)
+        p1.eval_device_frames(wl.d_frames, fstride, na, cell, 0, 2 * B); p1.sync(); p1.clear(); p1.set_initial_frame(*wl.f0[0], cell)
+        p1.enable_kernel_timing(True)
+        p1.eval_device_frames(wl.d_frames + 2 * B * fstride * 4, fstride, na, cell, 2 * B, nb_iso * B); p1.sync()
+        for k in ("k_rdf_pairs", "k_rdf_cull", "k_sdf", "k_density"):
+            t, n = p1.kernel_time_ms(k)
+            if n: iso[k] = {"ms_per_launch": t / n, "launches": n, "frames_per_launch": B}
+        if "k_rdf_pairs" in iso:
+            iso["k_rdf_pairs"]["pair_tests_executed_per_launch"] = p1.kernel_counter(0) / iso["k_rdf_pairs"]["launches"]
+            iso["k_rdf_pairs"]["pair_tests_useful_per_launch"] = p1.kernel_counter(1) / iso["k_rdf_pairs"]["launches"]
+        p1.close()
+
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        B = args.batch_frames or 148
-        algo_bytes_per_frame = 12 * 32768    # xyz of the selected (O) atoms read once; bins stay on chip
-        avg_launch_s = (k_ms / max(k_n, 1)) * 1e-3
-        frames_per_launch = (K * FPS) / max(k_n, 1)
-        achieved = algo_bytes_per_frame * frames_per_launch / max(avg_launch_s, 1e-12) / 1e9
-        pair_tests_per_frame = 32768 * 27 * (32768 / 729.0)
+        peak, peak_src, sm_mhz_max = measured_peaks()
+        sm_count = 148
+        roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src}
+        rdf_props = [p for p in wl.props if p.op == vb.OP_RDF]; sdf_props = [p for p in wl.props if p.op == vb.OP_SDF]
+        dens_props = [p for p in wl.props if vb.OP_DENSITY_X <= p.op <= vb.OP_DENSITY_Z]
+        cand = {}
+        if "k_rdf_pairs" in iso: cand["k_rdf_pairs"] = iso["k_rdf_pairs"]["ms_per_launch"] + iso.get("k_rdf_cull", {}).get("ms_per_launch", 0.0)
+        if "k_sdf" in iso: cand["k_sdf"] = iso["k_sdf"]["ms_per_launch"]
+        if "k_density" in iso: cand["k_density"] = iso["k_density"]["ms_per_launch"]
+        if cand:
+            dom = max(cand, key=cand.get); ms = cand[dom]
+            if dom == "k_rdf_pairs":
+                sel = set(rdf_props[0].idx[0].tolist()) | set(rdf_props[0].idx[1].tolist())
+                algo = 12 * len(sel); kname = "k_rdf_cull + k_rdf_pairs_v2"
+                what = "12 B x |reference U target atoms|: their coordinates read once, bins stay on chip (SURVEY.md 8(d))"
+            elif dom == "k_sdf":
+                algo = 12 * (len(sdf_props[0].idx[0]) + len(sdf_props[0].idx[1])); kname = "k_sdf_ref0 + k_sdf_fit + k_sdf_scatter"
+                what = "12 B x (atoms of the reference structures + target atoms) (SURVEY.md 8(d)); the 8 MB voxel grid stays in L2"
+            else:
+                algo = 4 * len(dens_props[0].idx[0]); kname = "k_density"
+                what = "4 B x atoms: density_z reads one coordinate per atom (SURVEY.md 8(d) quotes 12 B/atom for xyz; masses and indices are static and L2-resident)"
+            achieved = algo * B / (ms * 1e-3) / 1e9
+            roof.update({"kernel": kname, "achieved": achieved, "frac": achieved / peak, "algorithmic_bytes_per_launch": algo * B, "algorithmic_bytes_per_frame": algo,
+                         "algorithmic_bytes_definition": what, "ms_per_launch_alone": ms, "frames_per_launch": B,
+                         "traffic": measured_traffic(dom, B),
+                         "timing": "CUDA events on the launching stream around each launch of a one-stream plan (no other kernel in flight), %d launches" % iso[dom]["launches"],
+                         "kernel_share_of_step": ms / (sum(cand.values()) or 1.0)})
+            if "k_rdf_pairs" in iso and iso["k_rdf_pairs"].get("pair_tests_executed_per_launch"):
+                tests = iso["k_rdf_pairs"]["pair_tests_executed_per_launch"]; t_pair = iso["k_rdf_pairs"]["ms_per_launch"] * 1e-3
+                lane_peak = sm_count * 128 * sm_mhz_max * 1e6
+                roof["fp32"] = {"kernel": "k_rdf_pairs_v2", "pair_tests_executed_per_launch": tests, "pair_tests_useful_per_launch": iso["k_rdf_pairs"]["pair_tests_useful_per_launch"],
+                                "lane_ops_per_test": 9, "ms_per_launch_alone": iso["k_rdf_pairs"]["ms_per_launch"],
+                                "achieved_lane_ops_per_s": tests * 9 / t_pair, "peak_lane_ops_per_s": lane_peak, "frac": tests * 9 / t_pair / lane_peak,
+                                "pair_tests_per_s": tests / t_pair,
+                                "definition": "tests the kernel executed (device counter; the cull's and the symmetric mode's avoided tests are not counted, padding lanes are) x 9 FP32 "
+                                              "operations (3 sub, 4 mul, 2 fma, each one lane-cycle; packed FFMA2-class instructions occupy the pipe two cycles) / the kernel's own time; "
+                                              "peak = %d SMs x 128 FP32 lanes x %.0f MHz" % (sm_count, sm_mhz_max),
+                                "cull_ms_per_launch_alone": iso.get("k_rdf_cull", {}).get("ms_per_launch")}
+            roof["kernels_alone_ms_per_launch"] = {k: v["ms_per_launch"] for k, v in iso.items()}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
+            "config": {"workload": workload_string(cfg),
                        "frames_per_step": FPS, "batch_frames": B, "parallelism": f"frame-sharded x{world}",
                        "l2_policy": "every step reads fresh frames; one step's input (%.2f GB) exceeds the 126 MB L2" % (FPS * fstride * 4 / 1e9)},
             "gpu_launches": launches,
             "clocks": clocks,
             "wall_s": t_wall,
             "checks": checks,
-            "roofline": {"bound": "hbm", "kernel": "k_rdf_pairs", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(frames_per_launch), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": algo_bytes_per_frame * frames_per_launch,
-                         "note": "k_rdf_pairs is FP32-ALU/shared-atomic bound, not DRAM bound (SURVEY.md §7): see alu",
-                         "kernel_share_of_step": (k_ms / max(ms_dev, 1e-9)),
-                         "alu": {"pair_tests_definition": "the reference's enumeration (refs x 27 neighbour cells x mean cell population); tests avoided by the symmetric mode and the exact cull count as done",
-                                 "pair_tests_per_s": pair_tests_per_frame * frames_per_launch / max(avg_launch_s, 1e-12),
-                                 "avg_launch_ms": avg_launch_s * 1e3, "launches_timed": k_n}},
+            "roofline": roof,
         }
+        if world > 1:
+            line["per_rank"] = {"device_ms": per_rank_ms, "allreduce_ms": per_rank_ar, "note": "device_ms: CUDA-event time of the timed region on each rank (the value uses the max); allreduce_ms: host time of the one exchange step"}
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = max(2 * cores, 32)
-            r = run_reference_sample(sample, cores)
+            sample = cpu_sample_frames(cfg, cores)
+            r = run_reference(cfg, sample, cores, 1, 1)
             if r:
-                line["cpu_baseline"] = {"value": r["frames_per_s"], "unit": UNIT, "cores": cores, "kind": "reference",
-                                        "sample": f"{sample} frames of the same workload through md_script_eval_frame_range (oracle/_ref/ref_harness_fast, shipped flags), {cores} threads, in-memory trajectory"}
+                line["cpu_baseline"] = {"value": r["frames"] / r["times_s"][0], "unit": UNIT, "cores": cores, "kind": "reference", "host_cpu": cpu_model(),
+                                        "sample": f"{sample} frames ({sample // cores} per thread) of the same workload through md_script_eval_frame_range on {cores} threads; {CPU_NOTE}"}
             else:
                 r = oracle_port_sample(4)
-                line["cpu_baseline"] = {"value": r["frames_per_s"], "unit": UNIT, "cores": 1, "kind": "port", "sample": "4 frames, oracle/md_oracle.c scalar port"}
+                line["cpu_baseline"] = {"value": r["frames_per_s"], "unit": UNIT, "cores": 1, "kind": "port", "host_cpu": cpu_model(), "sample": "4 frames, oracle/md_oracle.c scalar port"}
         emit(line)
-    vb.device_free(dev, d_base); vb.device_free(dev, d_frames)
+    wl.free()
     plan.close()
     if world > 1:
         tdist.destroy_process_group()

@@ -178,7 +178,8 @@ typedef struct mdgpu_plan_options_t {
     uint32_t num_streams;         /* CUDA streams the frame loop is dispatched onto; 0 = default (3) */
     uint32_t keep_frame_results;  /* 1: retain raw per-frame integer bins of distributions (parity tests) */
     uint32_t cell_capacity;       /* cells per frame the cell lists are sized for; 0 = 2x the initial frame's grid */
-    uint32_t rdf_variant;         /* kernel variant selector for experiments; 0 = default */
+    uint32_t rdf_variant;         /* rdf pair-kernel variant, all bit-identical in their results: 0 = default (packed FP32x2, 3 CTAs/SM), 1 = scalar kernel
+                                   * without candidate lists, 2 = 4 CTAs/SM, 4 = reference chunks staged by the TMA unit (cp.async.bulk + mbarrier) */
     uint32_t ingest_mode;         /* host ingest (mdgpu_eval_host_frames / _trajectory): 0 = copy only the atoms the properties read when they are
                                    * less than 3/4 of the system (gathered into pinned staging by the ingest threads), 1 = always whole frames */
     uint32_t ingest_threads;      /* host threads that gather frames into pinned staging; 0 = default (min(16, cores / 2)) */
@@ -292,7 +293,9 @@ int mdgpu_plan_set_frames_accumulated(mdgpu_plan* plan, size_t prop, uint64_t fr
 
 /* Kernel bookkeeping for bench.py: launches issued by this library since the counter was last reset, and
  * CUDA-event time (ms, summed over launches) measured on the launching stream when timing is enabled; `kernel` selects
- * "k_rdf_pairs" (the pair kernel alone), "k_sdf" (fit + scatter kernels of an sdf) or "k_density" (binning + finalize). */
+ * "k_rdf_pairs" (the pair kernel alone), "k_rdf_cull" (its candidate-list pre-pass), "k_sdf" (fit + scatter kernels of an sdf) or "k_density"
+ * (binning + finalize). The spans are exact only when one stream is in flight (a plan with num_streams = 1): with several slots the events
+ * also see the kernels of the other streams. */
 uint64_t mdgpu_launch_count(bool reset);
 int mdgpu_plan_enable_kernel_timing(mdgpu_plan* plan, int enable);
 /* Device-side stopwatch over everything the plan enqueues: _begin drains the device and records a CUDA event; _end records
@@ -300,6 +303,9 @@ int mdgpu_plan_enable_kernel_timing(mdgpu_plan* plan, int enable);
 int mdgpu_plan_timer_begin(mdgpu_plan* plan);
 int mdgpu_plan_timer_end(mdgpu_plan* plan, double* elapsed_ms);
 int mdgpu_plan_kernel_time_ms(mdgpu_plan* plan, const char* kernel, double* total_ms, uint64_t* launches);
+/* Device-side counters of the pair kernel, accumulated while kernel timing is enabled: which = 0 pair tests executed (padding lanes of the
+ * last chunk / reference group included: they occupy FP32 lanes), 1 = tests between a real reference point and a real listed target. */
+int mdgpu_plan_kernel_counter(mdgpu_plan* plan, uint32_t which, uint64_t* value);
 
 /* Host evaluation of the per-frame cell-grid geometry (the same code the device runs, one thread per frame); used by the
  * CPU-side tests and for sizing. out_i[13] = cdim[3], ncell[3], hlo[3], hdim[3], valid; out_f[7] = G00,G11,G22,H01,H02,H12,r2. */

@@ -22,6 +22,9 @@ typedef struct mem_traj_t {
     mdsynth_water_t water; float *bx, *by, *bz;
     /* synthmembrane */
     mdsynth_membrane_t memb; float* mbase; uint32_t* mmol;
+    /* frames [cache_beg, cache_end) of a synthetic trajectory generated ahead of time (timing runs: load_frame is then a memcpy, as for a
+     * trajectory held in memory) */
+    float* cache; size_t cache_beg, cache_end;
 } mem_traj_t;
 
 typedef struct raw_frame_hdr_t { double cell[6]; uint32_t flags; uint32_t pad; } raw_frame_hdr_t;
@@ -37,6 +40,12 @@ static bool mt_load_frame(struct md_trajectory_reader_o* inst, int64_t idx, md_t
     mem_traj_t* t = (mem_traj_t*)inst;
     if (idx < 0 || (size_t)idx >= t->num_frames) return false;
     md_unitcell_t cell = {0};
+    if (t->cache && x && (size_t)idx >= t->cache_beg && (size_t)idx < t->cache_end && t->kind != TRAJ_RAW) {
+        const float* p = t->cache + ((size_t)idx - t->cache_beg) * 3 * t->num_atoms;
+        memcpy(x, p, t->num_atoms * 4); memcpy(y, p + t->num_atoms, t->num_atoms * 4); memcpy(z, p + 2 * t->num_atoms, t->num_atoms * 4);
+        if (t->kind == TRAJ_SYNTHMEMBRANE) cell = md_unitcell_from_extent((double)t->memb.Lx, (double)t->memb.Ly, (double)t->memb.Lz);
+        else cell = md_unitcell_from_extent((double)t->water.L, (double)t->water.L, (double)t->water.L);
+    } else
     if (t->kind == TRAJ_RAW) {
         const unsigned char* p = t->raw + (size_t)idx * t->raw_frame_bytes;
         raw_frame_hdr_t fh; memcpy(&fh, p, sizeof(fh)); p += sizeof(fh);
@@ -106,6 +115,18 @@ static bool make_traj(md_trajectory_i* out, mem_traj_t* mt, const char* spec, md
     for (size_t i = 0; i < mt->num_frames; ++i) mt->frame_times[i] = (double)i;
     out->inst = (struct md_trajectory_o*)mt; out->free = mt_free; out->get_header = mt_get_header; out->init_reader = mt_init_reader;
     return true;
+}
+
+/* generate frames [beg, end) of a synthetic trajectory once; load_frame then copies them (no-op for other kinds) */
+static void mt_materialize(mem_traj_t* t, size_t beg, size_t end) {
+    if (t->kind == TRAJ_RAW || end <= beg) return;
+    const size_t n = t->num_atoms; float* c = malloc((end - beg) * 3 * n * sizeof(float)); if (!c) return;
+    for (size_t f = beg; f < end; ++f) {
+        float* p = c + (f - beg) * 3 * n;
+        if (t->kind == TRAJ_SYNTHMEMBRANE) mdsynth_membrane_frame(&t->memb, (uint32_t)f, t->mbase, t->mmol, p, p + n, p + 2 * n);
+        else mdsynth_water_frame(&t->water, (uint32_t)f, t->bx, t->by, t->bz, p, p + n, p + 2 * n);
+    }
+    t->cache = c; t->cache_beg = beg; t->cache_end = end;
 }
 
 /* ---------------------------------------------------------------- helpers */

@@ -33,8 +33,15 @@ RDF_PATCHES = [
     (r'float4 rf; asm volatile\("ld\.shared\.v4\.f32.*$', 'const float4 rf = *(const float4*)(emul_dyn_smem + sref_saddr + 16u * (uint32_t)(gi * V2_UNROLL + u));', 1),
     (r'^    extern __shared__ __align__\(16\) unsigned char smem_raw\[\];$', '    unsigned char* smem_raw = emul_dyn_smem;', 1),
     (r'^    asm volatile\("mov\.u32 %0, %0;".*$', '', 3),
-    (r'cudaFuncSetAttribute\(k_rdf_pairs_v2<\w+>, [^;]*;', ';', 2),                       # launcher-only runtime calls on kernel symbols
-    (r'cudaOccupancyMaxActiveBlocksPerMultiprocessor\(&bpsm\[\d\], k_rdf_pairs_v2<\w+>, [^;]*;', ';', 2),
+    (r'cudaFuncSetAttribute\(k_rdf_pairs_v2<[\w, ]+>, [^;]*;', ';', 6),                       # launcher-only runtime calls on kernel symbols
+    (r'cudaOccupancyMaxActiveBlocksPerMultiprocessor\(&n, k_rdf_pairs_v2<[\w, ]+>, [^;]*;', 'n = 3;', 6),
+    # TMA / mbarrier helpers of the VAR 2 kernel: the copy happens at once, the barrier is a phase counter
+    (r'^MDG_D void mbar_init\(uint32_t mbar_saddr, uint32_t count\) \{.*$', 'MDG_D void mbar_init(uint32_t mbar_saddr, uint32_t count) { *(unsigned long long*)(emul_dyn_smem + mbar_saddr) = 0ull; }', 1),
+    (r'^MDG_D void mbar_expect_tx\(uint32_t mbar_saddr, uint32_t bytes\) \{.*$', 'MDG_D void mbar_expect_tx(uint32_t mbar_saddr, uint32_t bytes) { }', 1),
+    (r'^MDG_D bool mbar_try_wait\(uint32_t mbar_saddr, uint32_t parity\) \{.*$', 'MDG_D bool mbar_try_wait(uint32_t mbar_saddr, uint32_t parity) { return (__atomic_load_n((unsigned long long*)(emul_dyn_smem + mbar_saddr), __ATOMIC_ACQUIRE) & 1ull) != (unsigned long long)parity; }', 1),
+    (r'^MDG_D void tma_load_1d\(uint32_t dst_saddr, const void\* src, uint32_t bytes, uint32_t mbar_saddr\) \{.*$', 'MDG_D void tma_load_1d(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t mbar_saddr) { memcpy(emul_dyn_smem + dst_saddr, src, bytes); __atomic_fetch_add((unsigned long long*)(emul_dyn_smem + mbar_saddr), 1ull, __ATOMIC_RELEASE); }', 1),
+    (r'^MDG_D void fence_mbar_init\(\) \{.*$', 'MDG_D void fence_mbar_init() { }', 1),
+    (r'^MDG_D void fence_proxy_async\(\) \{.*$', 'MDG_D void fence_proxy_async() { }', 1),
 ]
 PATCHES = {"rdf": RDF_PATCHES}
 

@@ -225,3 +225,20 @@ def test_several_devices_in_one_process_merge_at_sync(emulated_library, monkeypa
         plan.eval_host_frames(g["frames"][:2], cells[:2], 0); plan.sync(); plan.eval_host_frames(g["frames"][2:], cells[2:], 2)
         _same(want, _mix_results(plan))
         plan.close()
+
+
+def test_rdf_kernel_variants_under_emulation(emulated_library):
+    """rdf_variant 2 (4 CTAs / SM, shorter hit queue) and 4 (TMA-staged reference chunks; the bulk copy + mbarrier helpers are emulated by a
+    memcpy and a phase counter) give the reference's per-frame bins, orthorhombic goldens."""
+    import numpy as np
+    import test_gpu_parity as G
+    from helpers import load_golden, golden_system
+    g = load_golden("water6.npz"); s = golden_system(g)
+    for variant in (2, 4):
+        plan, cells = G._water_plan(g, s, "r = rdf(element('O'), element('O'), 6.0); rh = rdf(element('O'), element('H'), 1.5:6.0);", rdf_variant=variant)
+        plan.eval_host_frames(g["frames"], cells, 0)
+        for key in ("r", "rh"):
+            for f in range(g["frames"].shape[0]):
+                bins, tot = plan.frame_counts(key, f)
+                assert np.array_equal(bins.astype(np.float32), g[f"{key}__pf"][f, :1024]) and tot == int(bins.sum()), (variant, key, f)
+        plan.close()

@@ -560,3 +560,58 @@ def test_xtc_file_input(tmp_path):
     assert np.array_equal(a.property_data("d").values, b.property_data("d").values) and a.frame_mask().all()
     with pytest.raises(vb.MdgpuError): a.eval_xtc_file(str(tmp_path / "missing.xtc"), 0, 1)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 4])
+def test_rdf_kernel_variants_are_bit_identical(variant):
+    """mdgpu_plan_options_t.rdf_variant: 1 = scalar kernel without candidate lists, 2 = 4 CTAs / SM, 4 = reference chunks staged by the TMA unit
+    (cp.async.bulk + mbarrier). Every variant must produce the default kernel's per-frame bins: reference goldens (ortho + triclinic) and a
+    24 576-atom box against the default variant."""
+    vb = _vb()
+    for gname, keys, src in (("water6.npz", ("r", "rh"), "r = rdf(element('O'), element('O'), 6.0); rh = rdf(element('O'), element('H'), 1.5:6.0);"),
+                             ("tric6.npz", ("rt", "rth"), "rt = rdf(element('O'), element('O'), 6.0); rth = rdf(element('O'), element('H'), 2.0:7.0);")):
+        g = load_golden(gname); s = golden_system(g)
+        plan, cells = _water_plan(g, s, src, rdf_variant=variant)
+        plan.eval_host_frames(g["frames"], cells, 0)
+        for key in keys:
+            for f in range(g["frames"].shape[0]):
+                bins, tot = plan.frame_counts(key, f)
+                assert np.array_equal(bins.astype(np.float32), g[f"{key}__pf"][f, :1024]) and tot == int(bins.sum()), (gname, key, f)
+        plan.close()
+    n, seed, F = 20, 99, 6
+    base, L = vb.synth_water_base(n, seed); frames = vb.synth_water_frames_host(n, seed, base, 0, F)
+    sysm = vb.water_system(n); o = np.arange(0, 3 * n ** 3, 3, dtype=np.int32); cell = vb.UnitCell.from_basis(L, L, L)
+    out = []
+    for v in (0, variant):
+        plan = vb.Plan(sysm, [vb.rdf("r", o, o, 10.0)], F, keep_frame_results=True, rdf_variant=v)
+        plan.eval_host_frames(frames, cell, 0)
+        out.append([plan.frame_counts("r", f) for f in range(F)]); plan.close()
+    for (b0, t0), (b1, t1) in zip(*out): assert t0 == t1 > 0 and np.array_equal(b0, b1)
+
+
+def test_rdf_triclinic_unwrapped_coordinates_overflow_pass():
+    """a triclinic trajectory whose atoms are not wrapped into the unit cell (20 % shifted by a lattice vector) populates home
+    cells outside the cell grid — the reference serves them through its single wrap — so the candidate lists outgrow `neighbours x |targets|`.
+    The home cells that do not fit are evaluated by the overflow pass (k_rdf_pairs<.., OVF>) instead of failing with MDGPU_ERR_CAPACITY:
+    per-frame bins equal the oracle's and the list-free scalar kernel's, for different and for identical selections."""
+    vb = _vb(); rng = np.random.default_rng(5)
+    n, seed, F = 8, 321, 3
+    base, L = vb.synth_water_base(n, seed); fr = vb.synth_water_frames_host(n, seed, base, 0, F).astype(np.float64); na = 3 * n ** 3
+    xy, xz, yz = 0.21 * L, -0.13 * L, 0.17 * L
+    X, Y, Z = fr[:, 0].copy(), fr[:, 1].copy(), fr[:, 2].copy()
+    fr[:, 0] = X + (xy / L) * Y + (xz / L) * Z; fr[:, 1] = Y + (yz / L) * Z
+    mol = rng.random(n ** 3) < 0.2; sh = np.repeat(mol, 3)                      # whole molecules moved by +a / -b: still the same periodic system
+    fr[:, 0, sh] += L; half = sh & (np.arange(na) % 2 == 0); fr[:, 0, half] -= xy; fr[:, 1, half] -= L
+    fr = fr.astype(np.float32)
+    cell = vb.UnitCell.from_basis(L, L, L, xy, xz, yz); ocell = O.UnitCell.from_params(L, xy, xz, L, yz, L, O.TRICLINIC | O.PBC_ALL)
+    sysm = vb.water_system(n); o = np.arange(0, na, 3, dtype=np.int32); h = np.setdiff1d(np.arange(na, dtype=np.int32), o)
+    for ref, trg, cut in ((o, h, 7.0), (o, o, 7.5)):
+        res = []
+        for variant in (0, 1):
+            plan = vb.Plan(sysm, [vb.rdf("r", ref, trg, cut)], F, keep_frame_results=True, rdf_variant=variant)
+            plan.eval_host_frames(fr, cell, 0)
+            res.append([plan.frame_counts("r", f) for f in range(F)]); plan.close()
+        for f in range(F):
+            ob, ow, ot = O.rdf_frame(*fr[f], ref, trg, ocell, 0.0, cut)
+            for bins, tot in (res[0][f], res[1][f]):
+                assert tot == ot > 0 and np.array_equal(bins.astype(np.float32), ob), (len(trg), f)

@@ -614,6 +614,10 @@ class Plan:
     def timer_end(self) -> float:
         ms = C.c_double(); _check(lib().mdgpu_plan_timer_end(self._h, C.byref(ms))); return float(ms.value)
 
+    def kernel_counter(self, which: int) -> int:
+        v = C.c_uint64(); lib().mdgpu_plan_kernel_counter.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
+        _check(lib().mdgpu_plan_kernel_counter(self._h, which, C.byref(v))); return int(v.value)
+
     def kernel_time_ms(self, kernel="k_rdf_pairs"):
         ms = C.c_double(); n = C.c_uint64()
         _check(lib().mdgpu_plan_kernel_time_ms(self._h, kernel.encode(), C.byref(ms), C.byref(n)))

@@ -25,6 +25,9 @@ struct RdfArgs {
     // candidate lists (k_rdf_cull -> k_rdf_pairs_v2): per frame `list_stride` entries (target position | image code << 26), per home cell a
     // header {first entry, entries of class 0, 1, 2}; one cursor per frame (zeroed by the launcher); err receives MDGPU_ERR_CAPACITY on overflow
     uint32_t* pair_list; uint4* list_hdr; uint32_t* list_cursor; size_t list_stride; size_t hdr_stride; int* err;
+    // measurement only (null unless kernel timing is enabled): [0] pair tests the pair kernel executed, padding lanes included,
+    // [1] of those, tests between a real reference point and a real listed target
+    unsigned long long* counters;
     // finalize
     unsigned long long* acc;     // [1024] accumulated bins
     unsigned long long* frame_total;  // [num_frames]
@@ -33,7 +36,7 @@ struct RdfArgs {
     uint32_t* keep;              // [num_frames][1024] or null
 };
 void launch_group_com(const BatchFrames& fr, const int32_t* d_idx, const uint32_t* d_off, uint32_t n_groups, const float* d_mass, float* d_out, cudaStream_t s);
-void launch_rdf(const RdfArgs& a, int B, bool tri, int variant, int sm_count, cudaStream_t s, cudaEvent_t* ev_beg, cudaEvent_t* ev_end);
+void launch_rdf(const RdfArgs& a, int B, bool tri, int variant, int sm_count, cudaStream_t s, cudaEvent_t* ev4 /* null, or events recorded {before cull, after cull, before pairs, after pairs} */);
 
 unsigned long long run_sqrt_sweep(uint32_t lo_bits, uint32_t hi_bits);
 

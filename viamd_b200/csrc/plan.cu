@@ -130,7 +130,8 @@ struct XtcStage {
     XtcFrameInfo* d_info = nullptr; uint2* d_rec = nullptr; uint16_t* d_state = nullptr;
 };
 
-struct TimedLaunch { cudaEvent_t a, b; int kind; };   // kind: 0 rdf pair kernel, 1 sdf (all three kernels), 2 density (+finalize)
+struct TimedLaunch { cudaEvent_t a, b; int kind; };   // kind: 0 rdf pair kernel, 1 sdf (all three kernels), 2 density (+finalize), 3 rdf cull kernel
+constexpr int TIMED_KINDS = 4;
 
 typedef struct ncclComm* nccl_comm_t;
 struct NcclApi {
@@ -178,7 +179,7 @@ struct mdgpu_plan {
     std::mutex slot_mutex; std::condition_variable slot_cv; std::mutex submit_mutex; std::mutex sync_mutex;
     mdgpu_progress_fn progress_fn = nullptr; void* progress_user = nullptr; cudaStream_t pub_stream = nullptr;
     std::chrono::steady_clock::time_point last_pub{};
-    bool timing = false; std::vector<TimedLaunch> timed; double timed_ms[3] = {0, 0, 0}; uint64_t timed_n[3] = {0, 0, 0};
+    bool timing = false; std::vector<TimedLaunch> timed; double timed_ms[TIMED_KINDS] = {0, 0, 0, 0}; uint64_t timed_n[TIMED_KINDS] = {0, 0, 0, 0}; unsigned long long* d_counters = nullptr;
     bool tri_seen = false, ortho_seen = false;
     cudaEvent_t t_begin = nullptr; std::vector<cudaEvent_t> t_end;
     XtcStage xtc[XTC_STAGES]; uint64_t next_xtc = 0; std::mutex xtc_mutex;
@@ -317,7 +318,7 @@ static void destroy_plan(mdgpu_plan* p) {
     for (auto& t : p->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (p->t_begin) cudaEventDestroy(p->t_begin);
     for (auto e : p->t_end) cudaEventDestroy(e);
-    cudaFree(p->d_mass); cudaFree(p->d_init); cudaFree(p->d_mass_c); cudaFree(p->d_init_c);
+    cudaFree(p->d_mass); cudaFree(p->d_init); cudaFree(p->d_mass_c); cudaFree(p->d_init_c); cudaFree(p->d_counters);
     delete p->pool;
     delete p;
 }
@@ -615,7 +616,8 @@ int mdgpu_plan_clear(mdgpu_plan* p) {
     }
     { std::lock_guard<std::mutex> lk(p->mask_mutex); std::fill(p->frame_mask.begin(), p->frame_mask.end(), 0ull); }
     p->interrupt = false; p->frames_retired = 0;
-    for (int k = 0; k < 3; ++k) { p->timed_ms[k] = 0; p->timed_n[k] = 0; }
+    for (int k = 0; k < TIMED_KINDS; ++k) { p->timed_ms[k] = 0; p->timed_n[k] = 0; }
+    if (p->d_counters) CUDA_TRY(cudaMemset(p->d_counters, 0, sizeof(unsigned long long) * 8));
     p->dirty = true;
     return 0;
 }
@@ -811,10 +813,11 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.excl_off = pr.n_struct ? pr.d_soff : nullptr; a.excl_idx = pr.n_struct ? didx[0] : nullptr;   // md_bitfield_test_bit(&masks[i], j) :5252
             a.symmetric = (!pr.n_struct && pr.ref_within == 0.0f && pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
             a.acc = pr.d_acc; a.frame_total = pr.d_frame_total; a.frame_min = pr.d_frame_min; a.frame_max = pr.d_frame_max; a.keep = pr.d_keep;
-            TimedLaunch tl{};
-            if (p->timing) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); }
-            launch_rdf(a, B, tri, (int)p->rdf_variant, p->sm_count, s.stream, p->timing ? &tl.a : nullptr, p->timing ? &tl.b : nullptr);
-            if (p->timing) { tl.kind = 0; p->timed.push_back(tl); }
+            a.counters = p->timing ? p->d_counters : nullptr;
+            cudaEvent_t ev4[4] = { nullptr, nullptr, nullptr, nullptr };   // before cull, after cull, before pairs, after pairs
+            if (p->timing) for (auto& e : ev4) cudaEventCreate(&e);
+            launch_rdf(a, B, tri, (int)p->rdf_variant, p->sm_count, s.stream, p->timing ? ev4 : nullptr);
+            if (p->timing) { p->timed.push_back(TimedLaunch{ ev4[0], ev4[1], 3 }); p->timed.push_back(TimedLaunch{ ev4[2], ev4[3], 0 }); }
             break; }
         case MDGPU_OP_SDF: {
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "sdf '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
@@ -1769,11 +1772,25 @@ int mdgpu_plan_set_frames_accumulated(mdgpu_plan* p, size_t prop, uint64_t frame
     return 0;
 }
 
-int mdgpu_plan_enable_kernel_timing(mdgpu_plan* p, int enable) { if (!p) return MDGPU_ERR_INVALID_ARG; p->timing = enable != 0; return 0; }
+int mdgpu_plan_enable_kernel_timing(mdgpu_plan* p, int enable) {
+    if (!p) return MDGPU_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> guard(p->submit_mutex);
+    if (enable && !p->d_counters) { CUDA_TRY(cudaSetDevice(p->device)); CUDA_TRY(dalloc(&p->d_counters, 8)); CUDA_TRY(cudaMemset(p->d_counters, 0, sizeof(unsigned long long) * 8)); }
+    p->timing = enable != 0; return 0;
+}
+
+// measurement counters of the pair kernel (filled while kernel timing is enabled): which = 0 executed pair tests (padding lanes included), 1 useful ones
+int mdgpu_plan_kernel_counter(mdgpu_plan* p, uint32_t which, uint64_t* value) {
+    if (!p || !value || which >= 8) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_kernel_counter: invalid argument");
+    int rc = mdgpu_plan_sync(p); if (rc) return rc;
+    *value = 0;
+    if (p->d_counters) { unsigned long long v = 0; CUDA_TRY(cudaMemcpy(&v, p->d_counters + which, sizeof(v), cudaMemcpyDeviceToHost)); *value = v; }
+    return 0;
+}
 
 int mdgpu_plan_kernel_time_ms(mdgpu_plan* p, const char* kernel, double* total_ms, uint64_t* launches) {
     if (!p) return fail(MDGPU_ERR_INVALID_ARG, "null plan");
-    const int kind = (kernel && strncmp(kernel, "k_sdf", 5) == 0) ? 1 : (kernel && strncmp(kernel, "k_density", 9) == 0) ? 2 : 0;
+    const int kind = (kernel && strncmp(kernel, "k_sdf", 5) == 0) ? 1 : (kernel && strncmp(kernel, "k_density", 9) == 0) ? 2 : (kernel && strncmp(kernel, "k_rdf_cull", 10) == 0) ? 3 : 0;
     int rc = mdgpu_plan_sync(p); if (rc) return rc;
     if (total_ms) *total_ms = p->timed_ms[kind]; if (launches) *launches = p->timed_n[kind];
     return 0;
