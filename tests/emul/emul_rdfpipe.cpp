@@ -65,9 +65,9 @@ extern "C" int emul_rdf(const float* frames, size_t frame_stride, size_t axis_st
     if (!n_groups) {   // launch_rdf, default variant
         if (tri) emul_launch(dim3(4, B), dim3(CULL_WARPS * 32), [&]() { k_rdf_cull<true>(a); }); else emul_launch(dim3(4, B), dim3(CULL_WARPS * 32), [&]() { k_rdf_cull<false>(a); });
         if (err) return err;
-        if (tri) emul_launch(dim3(2, B), dim3(V2_THREADS), [&]() { k_rdf_pairs_v2<true>(a); }); else emul_launch(dim3(2, B), dim3(V2_THREADS), [&]() { k_rdf_pairs_v2<false>(a); });
+        if (tri) emul_launch(dim3(2, B), dim3(V2_THREADS), [&]() { k_rdf_pairs_v2<true, 0>(a); }); else emul_launch(dim3(2, B), dim3(V2_THREADS), [&]() { k_rdf_pairs_v2<false, 0>(a); });
     } else {           // exclusion path: scalar kernel
-        if (tri) emul_launch(dim3(2, B), dim3(RDF_THREADS), [&]() { k_rdf_pairs<true, true>(a); }); else emul_launch(dim3(2, B), dim3(RDF_THREADS), [&]() { k_rdf_pairs<false, true>(a); });
+        if (tri) emul_launch(dim3(2, B), dim3(RDF_THREADS), [&]() { k_rdf_pairs<true, true, false>(a); }); else emul_launch(dim3(2, B), dim3(RDF_THREADS), [&]() { k_rdf_pairs<false, true, false>(a); });
     }
     emul_launch(dim3(B), dim3(MDGPU_DIST_BINS), [&]() { k_rdf_finalize(a); });
     return err;
