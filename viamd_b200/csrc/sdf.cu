@@ -347,14 +347,15 @@ MDG_D int wrap_coord(int v, int N) { v += (v < 0) ? N : 0; v -= (v >= N) ? N : 0
 MDG_D int isign(int v) { return (v > 0) - (v < 0); }
 
 // K4: one warp per (structure, frame): target points of the cells overlapping AABB(com, cutoff) -> voxel increments.
-//  * the cells of the range are flattened into one index range (prefix table in shared memory), 32 candidates per warp step; the
-//    segment of each lane's candidate comes from a 32-bit mask of the segment boundaries inside the step (no per-lane search);
-//  * candidates that pass the box test and the exclusion mask are compacted into a per-warp ring in shared memory; the transform +
-//    voxel atomics run on full groups of 32 (the hit rate is ~22 %, so running them in place would leave two thirds of the lanes idle).
+//  * lanes enumerate the cells of the range once (wrap, image code, offsets) into a small per-warp segment table;
+//  * each HALF-warp then walks one cell at a time, 16 points per step (a cell of the bench workload holds ~45 targets: three steps at 94 %
+//    lane use, where a full warp per cell would run two steps at 70 % and a flattened index space pays a boundary search per step);
+//  * the box test passes ~60 % of the candidates (the box is 20 A wide, the 2-3 cells per axis it overlaps 22-33 A), so the transform
+//    and the voxel increment run in place under the hit predicate — compacting hits first costs more than the idle lanes it would fill
+//    (profiles/r2_01_fullset_ncu.txt: the ring version spent a third of its instructions on the compaction and another third on set-up).
 constexpr int SDF_WARPS = 8;
 constexpr int SDF_MAXSEG = 128;
 constexpr int SDF_EXCL_CACHE = 64;
-constexpr int SDF_RING = 64;
 
 struct SdfXform { float M[4][3]; float A00, A11, A22, O0, O1, O2, A10, A20, A21; };
 
@@ -365,13 +366,13 @@ MDG_D void sdf_splat(float vx, float vy, float vz, const SdfXform& X, uint32_t* 
     // triclinic: REFERENCE QUIRK — for_each_point_in_aabb_triclinic buffers the fractional image-shifted coordinates (:2122-2130) and its
     // *_CART_TRI callback macros (:715-737) skip the conversion, so sdf_cb transforms fractional numbers. Reproduced for parity.
     const float px = TRI ? vx : __fmaf_rn(vx, X.A00, X.O0), py = TRI ? vy : __fmaf_rn(vy, X.A11, X.O1), pz = TRI ? vz : __fmaf_rn(vz, X.A22, X.O2);
-    float c[3];   // mat4_mul_vec4(M, (x,y,z,1)) = ((x*M0 + y*M1) + z*M2) + 1*M3
+    float c[3];   // mat4_mul_vec4(M, (x,y,z,1)) = ((x*M0 + y*M1) + z*M2) + 1*M3; 1*M3 is M3 exactly
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         float v = __fmul_rn(px, X.M[0][r]);
         v = __fadd_rn(v, __fmul_rn(py, X.M[1][r]));
         v = __fadd_rn(v, __fmul_rn(pz, X.M[2][r]));
-        v = __fadd_rn(v, __fmul_rn(1.0f, X.M[3][r]));
+        v = __fadd_rn(v, X.M[3][r]);
         c[r] = v;
     }
     const uint32_t ix = (uint32_t)max(0, min(__float2int_rz(c[0]), MDGPU_VOL_DIM - 1));
@@ -383,11 +384,9 @@ MDG_D void sdf_splat(float vx, float vy, float vz, const SdfXform& X, uint32_t* 
 template <bool TRI>
 __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B) {
     const int f = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, hl = lane & 15, half = lane >> 4;
     const uint32_t s = blockIdx.x * SDF_WARPS + warp;
-    __shared__ uint32_t s_pre[SDF_WARPS][SDF_MAXSEG + 1];
-    __shared__ uint2 s_seg[SDF_WARPS][SDF_MAXSEG];        // x: start - pre (first point of the segment minus its flattened offset), y: image code
-    __shared__ float s_ring[SDF_WARPS][3][SDF_RING];
+    __shared__ uint2 s_seg[SDF_WARPS][SDF_MAXSEG];        // x: first point of the cell, y: point count | image code << 26
     __shared__ int32_t s_excl[SDF_WARPS][SDF_EXCL_CACHE];
     if (s >= a.n_struct) return;
     const FrameGeom& g = a.geom[f];
@@ -416,19 +415,18 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
     const int ex = cmax[0] - cmin[0], ey = cmax[1] - cmin[1], ez = cmax[2] - cmin[2];
     const int ncells = ex * ey * ez;
     const uint32_t lt = (1u << lane) - 1u;
-    float* rx = s_ring[warp][0]; float* ry = s_ring[warp][1]; float* rz = s_ring[warp][2];
-    uint32_t cnt = 0;                      // candidates waiting in the ring (warp-uniform, < 32 between steps)
-    unsigned long long local = 0;
+    uint32_t local = 0;                    // voxel increments of this lane
     for (int c0 = 0; c0 < ncells; c0 += SDF_MAXSEG) {   // (:1925-1943) cells of the range, SDF_MAXSEG at a time
         const int nc = min(SDF_MAXSEG, ncells - c0);
-        uint32_t base = 0; int nseg = 0;
+        int nseg = 0;
         __syncwarp();
         for (int n0 = 0; n0 < nc; n0 += 32) {
             const int n = n0 + lane;
             uint32_t len = 0, start = 0, code = 0x15;
             if (n < nc) {
                 const int q = c0 + n;
-                const int icx = cmin[0] + q % ex, icy = cmin[1] + (q / ex) % ey, icz = cmin[2] + q / (ex * ey);
+                const int qx = q % ex, qyz = q / ex;
+                const int icx = cmin[0] + qx, icy = cmin[1] + qyz % ey, icz = cmin[2] + qyz / ey;
                 const int cx = pbc[0] ? wrap_coord(icx, cd[0]) : icx, cy = pbc[1] ? wrap_coord(icy, cd[1]) : icy, cz = pbc[2] ? wrap_coord(icz, cd[2]) : icz;
                 if (!(cx < 0 || cx >= cd[0] || cy < 0 || cy >= cd[1] || cz < 0 || cz >= cd[2])) {
                     const uint32_t ci = ((uint32_t)cz * (uint32_t)cd[1] + (uint32_t)cy) * (uint32_t)cd[0] + (uint32_t)cx;
@@ -437,69 +435,48 @@ __global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B
                 }
             }
             const uint32_t have = __ballot_sync(0xffffffffu, len != 0u);   // keep non-empty cells only
-            uint32_t incl = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (len) { const int slot = nseg + __popc(have & lt); const uint32_t pre = base + incl - len; s_pre[warp][slot] = pre; s_seg[warp][slot] = make_uint2(start - pre, code); }
-            base += __shfl_sync(0xffffffffu, incl, 31);
+            if (len) s_seg[warp][nseg + __popc(have & lt)] = make_uint2(start, len | (code << 26));
             nseg += __popc(have);
         }
-        const uint32_t total = base;
-        if (lane == 0) s_pre[warp][nseg] = total;
         __syncwarp();
-        int kbase = 0;                     // segment that contains candidate j0 (warp-uniform)
-        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
-            // segment boundaries inside (j0, j0+32]: bit (b - j0 - 1). Segments are non-empty, so they are among the next 32 table entries.
-            const int kb = kbase + 1 + lane;
-            const uint32_t bnd = (kb <= nseg) ? s_pre[warp][kb] : 0xffffffffu;
-            const uint32_t rel = bnd - j0 - 1u;
-            const uint32_t bm = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
-            const uint32_t j = j0 + lane;
-            bool hit = false; float vx = 0.f, vy = 0.f, vz = 0.f;
-            if (j < total) {
-                const uint2 sg = s_seg[warp][kbase + __popc(bm & lt)];
-                const float4 t = pts[sg.x + j];
-                vx = t.x; vy = t.y; vz = t.z;
-                if (sg.y != 0x15u) {   // periodic image of the cell: + (-1|0|+1), rounded (:1962-1964); +0 is the identity
-                    vx = __fadd_rn(vx, (float)((int)(sg.y & 3u) - 1)); vy = __fadd_rn(vy, (float)((int)((sg.y >> 2) & 3u) - 1)); vz = __fadd_rn(vz, (float)((int)((sg.y >> 4) & 3u) - 1));
-                }
-                if (TRI) {   // box test on the cartesian image (fract_to_cart_tri_256 md_spatial_acc.c:594-603), all axes periodic (:2009)
-                    const float cx_ = __fmaf_rn(vx, X.A00, __fmaf_rn(vy, X.A10, __fmaf_rn(vz, X.A20, X.O0))), cy_ = __fmaf_rn(vy, X.A11, __fmaf_rn(vz, X.A21, X.O1)), cz_ = __fmaf_rn(vz, X.A22, X.O2);
-                    hit = cx_ >= lo3[0] && cy_ >= lo3[1] && cz_ >= lo3[2] && cx_ <= hi3[0] && cy_ <= hi3[1] && cz_ <= hi3[2];
-                } else hit = vx >= lo3[0] && vy >= lo3[1] && vz >= lo3[2] && vx <= hi3[0] && vy <= hi3[1] && vz <= hi3[2];
-                if (hit) {
-                    const uint32_t idx = __float_as_uint(t.w);
-                    if (ex_contig) hit = (idx - ex_lo) >= ex_n;
-                    else {
-                        bool excluded = false;
-                        const uint32_t nc_ = min(ex_n, (uint32_t)SDF_EXCL_CACHE);
-                        for (uint32_t q = 0; q < nc_; ++q) excluded |= ((uint32_t)s_excl[warp][q] == idx);
-                        for (uint32_t q = nc_; q < ex_n; ++q) excluded |= ((uint32_t)sidx[q] == idx);
-                        hit = !excluded;
+        for (int k0 = 0; k0 < nseg; k0 += 2) {   // one cell per half-warp
+            const int k = k0 + half;
+            const uint2 sg = (k < nseg) ? s_seg[warp][k] : make_uint2(0u, 0u);
+            const uint32_t len = sg.y & 0x3ffffffu, code = sg.y >> 26;
+            const uint32_t steps = max(__shfl_sync(0xffffffffu, len, 0), __shfl_sync(0xffffffffu, len, 16));
+            const float shx = (float)((int)(code & 3u) - 1), shy = (float)((int)((code >> 2) & 3u) - 1), shz = (float)((int)((code >> 4) & 3u) - 1);
+            for (uint32_t j = (uint32_t)hl; j < steps; j += 16u) {
+                if (j < len) {
+                    const float4 t = pts[sg.x + j];
+                    float vx = t.x, vy = t.y, vz = t.z;
+                    if (code != 0x15u) {   // periodic image of the cell: + (-1|0|+1), rounded (:1962-1964); +0 is the identity
+                        vx = __fadd_rn(vx, shx); vy = __fadd_rn(vy, shy); vz = __fadd_rn(vz, shz);
+                    }
+                    bool hit;
+                    if (TRI) {   // box test on the cartesian image (fract_to_cart_tri_256 md_spatial_acc.c:594-603), all axes periodic (:2009)
+                        const float cx_ = __fmaf_rn(vx, X.A00, __fmaf_rn(vy, X.A10, __fmaf_rn(vz, X.A20, X.O0))), cy_ = __fmaf_rn(vy, X.A11, __fmaf_rn(vz, X.A21, X.O1)), cz_ = __fmaf_rn(vz, X.A22, X.O2);
+                        hit = cx_ >= lo3[0] && cy_ >= lo3[1] && cz_ >= lo3[2] && cx_ <= hi3[0] && cy_ <= hi3[1] && cz_ <= hi3[2];
+                    } else hit = vx >= lo3[0] && vy >= lo3[1] && vz >= lo3[2] && vx <= hi3[0] && vy <= hi3[1] && vz <= hi3[2];
+                    if (hit) {
+                        const uint32_t idx = __float_as_uint(t.w);
+                        if (ex_contig) hit = (idx - ex_lo) >= ex_n;
+                        else {
+                            bool excluded = false;
+                            const uint32_t nc_ = min(ex_n, (uint32_t)SDF_EXCL_CACHE);
+                            for (uint32_t q = 0; q < nc_; ++q) excluded |= ((uint32_t)s_excl[warp][q] == idx);
+                            for (uint32_t q = nc_; q < ex_n; ++q) excluded |= ((uint32_t)sidx[q] == idx);
+                            hit = !excluded;
+                        }
+                        if (hit) { sdf_splat<TRI>(vx, vy, vz, X, a.vol); ++local; }
                     }
                 }
-            }
-            kbase += __popc(bm);
-            const uint32_t hm = __ballot_sync(0xffffffffu, hit);
-            if (hit) { const uint32_t p = cnt + __popc(hm & lt); rx[p] = vx; ry[p] = vy; rz[p] = vz; }
-            cnt += __popc(hm);
-            if (cnt >= 32u) {
-                __syncwarp();
-                sdf_splat<TRI>(rx[lane], ry[lane], rz[lane], X, a.vol);
-                const uint32_t rem = cnt - 32u;
-                float mx = 0.f, my = 0.f, mz = 0.f;
-                if (lane < rem) { mx = rx[32 + lane]; my = ry[32 + lane]; mz = rz[32 + lane]; }
-                __syncwarp();
-                if (lane < rem) { rx[lane] = mx; ry[lane] = my; rz[lane] = mz; }
-                cnt = rem; local += 32;
-                __syncwarp();
             }
         }
     }
     __syncwarp();
-    if (lane < cnt) sdf_splat<TRI>(rx[lane], ry[lane], rz[lane], X, a.vol);
-    local += cnt;
-    if (lane == 0 && local) atomicAdd(&a.frame_total[a.frame0 + f], local);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(&a.frame_total[a.frame0 + f], (unsigned long long)local);
 }
 
 // ------------------------------------------------------------------------------------------------- rmsd(selection)
