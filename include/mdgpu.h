@@ -108,6 +108,8 @@ typedef enum mdgpu_op {
                                   * (src/components/shapespace/shapespace.cpp:404-431) and _shape_weights (md_script_functions.inl:6005-6050) */
     MDGPU_OP_COORD_X = 17, MDGPU_OP_COORD_Y = 18, MDGPU_OP_COORD_Z = 19,   /* coord_x/_y/_z(selection): the atoms' coordinates -> temporal [F, n]  :5077-5169 */
     MDGPU_OP_RMSD = 11,      /* rmsd(selection) against the initial frame -> temporal                     :4287-4345 */
+    MDGPU_OP_BACKBONE_ANGLES = 20, /* (phi, psi) of every backbone segment per frame -> temporal [F, 2 * n_segments]: VIAMD's "Backbone Operations" pass
+                                    * (src/viamd.cpp:488-520 -> md_util_backbone_angles_compute md_util.c:2572-2620) */
 } mdgpu_op;
 
 /* One property = one `ident = proc(args);` statement whose selections were evaluated statically at compile time
@@ -137,6 +139,10 @@ typedef enum mdgpu_op {
  *   SHAPE_WEIGHTS: idx[0] = the atoms of num_structures structures back to back (structure_offsets, or structure_size each), bit 0 of com_args
  *              = weights are the atom masses (shapespace's use_mass; _shape_weights always uses them), else 1.
  *   COORD_X/_Y/_Z: idx[0] = the atoms.
+ *   BACKBONE_ANGLES: idx[0] = for each of the num_structures backbone segments the five atoms C(i-1), N(i), CA(i), C(i), N(i+1)
+ *              (md_protein_backbone_data_t::segment.atoms of the segment and its neighbours), back to back; -1 in any of the five marks a segment without angles (the first / last residue of a chain, chains shorter than 4:
+ *              md_util.c:2588-2592) whose two values stay 0. Row f holds md_backbone_angles_t[num_structures] = (phi, psi) pairs in radians:
+ *              phi = dihedral(C', N, CA, C), psi = dihedral(N, CA, C, N') with md_util_min_image_vec3 on the bond vectors, as `dihedral` evaluates.
  *   RMSD     : idx[0] = the atoms of the (flattened) selection; needs the initial frame and, to make molecules whole, the bond connectivity.
  *   DISTANCE/ANGLE/DIHEDRAL: idx[k] = the atoms of argument k (0-based). A single integer index is that atom's position; an
  *              argument that was a selection (bit k of com_args set, or more than one index) is its centre of mass as
@@ -178,8 +184,9 @@ typedef struct mdgpu_plan_options_t {
     uint32_t num_streams;         /* CUDA streams the frame loop is dispatched onto; 0 = default (3) */
     uint32_t keep_frame_results;  /* 1: retain raw per-frame integer bins of distributions (parity tests) */
     uint32_t cell_capacity;       /* cells per frame the cell lists are sized for; 0 = 2x the initial frame's grid */
-    uint32_t rdf_variant;         /* rdf pair-kernel variant, all bit-identical in their results: 0 = default (packed FP32x2, 3 CTAs/SM), 1 = scalar kernel
-                                   * without candidate lists, 2 = 4 CTAs/SM, 4 = reference chunks staged by the TMA unit (cp.async.bulk + mbarrier) */
+    uint32_t rdf_variant;         /* rdf pair-kernel variant, all bit-identical in their results: 0 = default (packed FP32x2, 4 CTAs/SM), 1 = scalar kernel
+                                   * without candidate lists, 2 = 3 CTAs/SM with a longer hit queue, 4 = reference chunks staged by the TMA unit
+                                   * (cp.async.bulk + mbarrier; measured 5 % slower, kept as the recorded alternative) */
     uint32_t ingest_mode;         /* host ingest (mdgpu_eval_host_frames / _trajectory): 0 = copy only the atoms the properties read when they are
                                    * less than 3/4 of the system (gathered into pinned staging by the ingest threads), 1 = always whole frames */
     uint32_t ingest_threads;      /* host threads that gather frames into pinned staging; 0 = default (min(16, cores / 2)) */
@@ -267,6 +274,11 @@ int mdgpu_plan_property_peek(mdgpu_plan* plan, size_t prop, mdgpu_property_data_
 /* Per-frame aggregates of a temporal with several values per frame (md_script_aggregate_t md_script.h:63-70, filled at md_script.c:5886-5890):
  * out_mean[num_frames], out_var[num_frames] (population variance), out_ext[num_frames][2] (min, max); any may be NULL. Implies mdgpu_plan_sync. */
 int mdgpu_plan_property_aggregate(mdgpu_plan* plan, size_t prop, float* out_mean, float* out_var, float* out_ext, size_t num_frames);
+
+/* Histogram of a temporal property over the evaluated frames, on the device: VIAMD's compute_histogram_masked (src/main.cpp:172-226, called from
+ * :1513 for every temporal display property whenever its fingerprint changes). The [F, dim] values stay in HBM; out_bins[(aggregate ? 1 : dim)][num_bins]
+ * receives counts scaled by 1 / (bin width x samples of the row), out_min_max (optional) the smallest / largest scaled bin. Implies mdgpu_plan_sync. */
+int mdgpu_plan_property_histogram(mdgpu_plan* plan, size_t prop, uint32_t num_bins, float range_min, float range_max, int aggregate, float* out_bins, float* out_min_max);
 
 /* Exact integer results (what parity is asserted on).
  *  _counts: accumulated counts over all evaluated frames: RDF 1024 x u64 bins; SDF 128^3 x u64 voxels (widened from u32);

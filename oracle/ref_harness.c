@@ -248,6 +248,42 @@ static int mode_shapespace(int argc, char** argv) {
 
 /* xtcwrite: frames [B,E) of any trajectory spec -> an .xtc file through the reference's bundled xdrfile writer (ext/xtc/xdrfile_xtc.c:
  * write_xtc), coordinates Angstrom -> nm. Fixture generation for the XTC decode path. */
+/* backbone angles per frame through the reference's md_util_backbone_angles_compute (VIAMD's "Backbone Operations" pass, src/viamd.cpp:488-520):
+ * MDBACKBN | u64 F | u64 nseg | i32 atoms[nseg][5] = C(i-1), N, CA, C, N(i+1) (-1: the segment has no angles) | f32 angles[F][nseg][2] */
+static int mode_backbone(int argc, char** argv) {
+    md_allocator_i* alloc = md_vm_arena_create(GIGABYTES(8));
+    md_system_t sys; if (!load_system(&sys, arg_val(argc, argv, "--sys", ""), alloc)) return 2;
+    md_trajectory_i traj = {0}; mem_traj_t mt;
+    if (!make_traj(&traj, &mt, arg_val(argc, argv, "--traj", "sys"), &sys)) return 2;
+    long b = 0, e = (long)md_trajectory_num_frames(&traj); parse_range(arg_val(argc, argv, "--frames", NULL), &b, &e);
+    const md_protein_backbone_data_t* bb = &sys.protein_backbone;
+    const size_t nseg = bb->segment.count; if (!nseg) { fprintf(stderr, "system has no protein backbone\n"); return 2; }
+    FILE* f = fopen(arg_val(argc, argv, "--out", "backbone.bin"), "wb"); if (!f) return 2;
+    wr(f, "MDBACKBN", 8); wr_u64(f, (uint64_t)(e - b)); wr_u64(f, (uint64_t)nseg);
+    int32_t* five = calloc(nseg * 5, sizeof(int32_t));
+    for (size_t i = 0; i < nseg * 5; ++i) five[i] = -1;
+    for (size_t r = 0; r < bb->range.count; ++r) {   /* the loop bounds of md_util_backbone_angles_compute (md_util.c:2584-2592) */
+        const size_t rb = bb->range.offset[r], re = bb->range.offset[r + 1];
+        if (re - rb < 4) continue;
+        for (size_t i = rb + 1; i + 1 < re; ++i) {
+            five[5 * i + 0] = bb->segment.atoms[i - 1].c; five[5 * i + 1] = bb->segment.atoms[i].n; five[5 * i + 2] = bb->segment.atoms[i].ca;
+            five[5 * i + 3] = bb->segment.atoms[i].c; five[5 * i + 4] = bb->segment.atoms[i + 1].n;
+        }
+    }
+    wr(f, five, nseg * 5 * sizeof(int32_t));
+    const size_t n = sys.atom.count; float* x = malloc(n * 4); float* y = malloc(n * 4); float* z = malloc(n * 4);
+    md_backbone_angles_t* ang = calloc(nseg, sizeof(md_backbone_angles_t));
+    for (long fr = b; fr < e; ++fr) {
+        md_trajectory_frame_header_t hdr = {0};
+        if (!md_trajectory_load_frame(&traj, fr, &hdr, x, y, z)) return 2;
+        md_util_backbone_angles_compute(ang, nseg, x, y, z, &hdr.unitcell, bb);
+        wr(f, ang, nseg * sizeof(md_backbone_angles_t));
+    }
+    fclose(f);
+    printf("{\"frames\": %ld, \"segments\": %zu}\n", e - b, nseg);
+    return 0;
+}
+
 static int mode_xtcwrite(int argc, char** argv) {
     md_allocator_i* alloc = md_vm_arena_create(GIGABYTES(8));
     md_system_t sys; if (!load_system(&sys, arg_val(argc, argv, "--sys", ""), alloc)) return 2;
@@ -276,6 +312,7 @@ int main(int argc, char** argv) {
     if (argc < 2) { fprintf(stderr, "usage: ref_harness sysinfo|eval|time|dumptraj ...\n"); return 1; }
     if (strcmp(argv[1], "dumptraj") == 0) return mode_dumptraj(argc, argv);
     if (strcmp(argv[1], "shapespace") == 0) return mode_shapespace(argc, argv);
+    if (strcmp(argv[1], "backbone") == 0) return mode_backbone(argc, argv);
     if (strcmp(argv[1], "sysinfo") == 0) return mode_sysinfo(argc, argv);
     if (strcmp(argv[1], "eval") == 0) return mode_eval(argc, argv, false);
     if (strcmp(argv[1], "time") == 0) return mode_eval(argc, argv, true);

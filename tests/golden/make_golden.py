@@ -249,6 +249,18 @@ def water12_avg(tmp):
     np.savez_compressed(os.path.join(HERE, "water12_avg.npz"), **out)
 
 
+def backbone(tmp):
+    """phi / psi of every backbone segment per frame from the reference's md_util_backbone_angles_compute (harness mode `backbone`: the loop body of
+    VIAMD's "Backbone Operations" task, src/viamd.cpp:488-520) on the 50 ala50 frames: the segments' five atoms (-1 rows: no angles) + angles[F][nseg][2]."""
+    o = os.path.join(tmp, "bb.bin")
+    run(HARNESS, "backbone", "--sys", "/root/reference/datasets/1ALA-500.pdb", "--traj", "sys", "--frames", "0:50", "--out", o)
+    b = open(o, "rb").read(); assert b[:8] == b"MDBACKBN"
+    F, ns = np.frombuffer(b, np.uint64, 2, 8); F, ns = int(F), int(ns)
+    five = np.frombuffer(b, np.int32, ns * 5, 24).reshape(ns, 5).copy()
+    ang = np.frombuffer(b, np.float32, F * ns * 2, 24 + ns * 20).reshape(F, ns, 2).copy()
+    np.savez_compressed(os.path.join(HERE, "backbone.npz"), five=five, angles=ang)
+
+
 def _write_gro(path, n, L):
     with open(path, "w") as f:
         f.write("synthetic\n%d\n" % n)
@@ -299,7 +311,7 @@ if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     only = sys.argv[1:]   # e.g. `python make_golden.py water32_full water12_avg` regenerates just those
     gens = dict(water6=water6, ala50=ala50, membrane6=membrane6, tric6=tric6, tric6_rmsd=tric6_rmsd, pairs6=pairs6, shapes=shapes, xtc_cases=xtc_cases,
-                water32_full=water32_full, water12_avg=water12_avg)
+                water32_full=water32_full, water12_avg=water12_avg, backbone=backbone)
     with tempfile.TemporaryDirectory() as tmp:
         for name, fn in gens.items():
             if not only or name in only: fn(tmp)

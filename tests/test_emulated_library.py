@@ -228,7 +228,7 @@ def test_several_devices_in_one_process_merge_at_sync(emulated_library, monkeypa
 
 
 def test_rdf_kernel_variants_under_emulation(emulated_library):
-    """rdf_variant 2 (4 CTAs / SM, shorter hit queue) and 4 (TMA-staged reference chunks; the bulk copy + mbarrier helpers are emulated by a
+    """rdf_variant 2 (3 CTAs / SM, longer hit queue; the default has 4) and 4 (TMA-staged reference chunks; the bulk copy + mbarrier helpers are emulated by a
     memcpy and a phase counter) give the reference's per-frame bins, orthorhombic goldens."""
     import numpy as np
     import test_gpu_parity as G

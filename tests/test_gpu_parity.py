@@ -564,7 +564,7 @@ def test_xtc_file_input(tmp_path):
 
 @pytest.mark.parametrize("variant", [1, 2, 4])
 def test_rdf_kernel_variants_are_bit_identical(variant):
-    """mdgpu_plan_options_t.rdf_variant: 1 = scalar kernel without candidate lists, 2 = 4 CTAs / SM, 4 = reference chunks staged by the TMA unit
+    """mdgpu_plan_options_t.rdf_variant: 1 = scalar kernel without candidate lists, 2 = 3 CTAs / SM (default: 4), 4 = reference chunks staged by the TMA unit
     (cp.async.bulk + mbarrier). Every variant must produce the default kernel's per-frame bins: reference goldens (ortho + triclinic) and a
     24 576-atom box against the default variant."""
     vb = _vb()

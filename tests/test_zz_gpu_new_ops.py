@@ -24,6 +24,11 @@ def _same(a, b):
     return bool(np.allclose(a, b, rtol=1e-5, atol=1e-6))
 
 
+def _vb():
+    import viamd_b200 as vb
+    return vb
+
+
 def _plan(g, s, src, **kw):
     import viamd_b200 as vb
     sysm = vb_system(s); props = vb.compile_script(src, sysm); F = g["frames"].shape[0]
@@ -349,3 +354,53 @@ def test_new_ops_through_the_md_script_shim(tmp_path):
     assert p.returncode == 0 and res["parity"] is True, res
     assert all(q["out_of_tol"] == 0 and q["frame_mask_equal"] for q in res["properties"])
 
+
+
+def test_backbone_angles_of_every_segment_per_frame():
+    """VIAMD's "Backbone Operations" pass (src/viamd.cpp:488-520 -> md_util_backbone_angles_compute md_util.c:2572-2620) as ONE op: (phi, psi) of
+    all backbone segments of 1ALA for 50 frames against the reference's own values (tests/golden/backbone.npz); chain ends stay 0 as in the
+    reference. atan2f on the device vs glibc: 1e-5."""
+    vb = _vb(); g = load_golden("backbone.npz"); a = load_golden("ala50.npz"); s = golden_system(a)
+    F, ns = g["angles"].shape[:2]
+    plan = vb.Plan(vb_system(s), [vb.backbone_angles("bb", g["five"])], F)
+    cells = [vb_cell(a["cells"][f], a["cell_flags"][f]) for f in range(F)]
+    plan.eval_host_frames(a["frames"], cells, 0)
+    d = plan.property_data("bb"); assert d.dim[:2] == (F, 2 * ns)
+    got = d.values.reshape(F, ns, 2)
+    np.testing.assert_allclose(got, g["angles"], rtol=1e-5, atol=2e-6)
+    assert np.all(got[:, 0] == 0) and np.all(got[:, -1] == 0) and np.all(np.abs(got[:, 1:-1]) > 0)
+    agg = plan.aggregate("bb"); assert agg["mean"].shape == (F,)
+    plan.close()
+
+
+def test_temporal_histogram_on_the_device():
+    """compute_histogram_masked (src/main.cpp:172-226), VIAMD's per-property display histogram, with the [F, dim] values left on the device:
+    per-column and aggregated forms, out-of-range values skipped, only evaluated frames counted, scale 1 / (bin width x samples)."""
+    vb = _vb(); g = load_golden("water6.npz"); pz = load_golden("pairs6.npz"); s = golden_system(g); F = g["frames"].shape[0]
+    plan = vb.Plan(vb_system(s), vb.compile_script("dp = distance_pair(atom(1:5), atom(20:30)); d = distance(1,10);", vb_system(s)), F)
+    cells = [vb_cell(g["cells"][f], g["cell_flags"][f]) for f in range(F)]
+    plan.eval_host_frames(g["frames"][:3], cells[:3], 0)                         # frame 3 stays unevaluated: it must not be counted
+    vals = pz["w_dp__full"].reshape(F, 55)[:3]
+
+    def ref_hist(v, nb, lo, hi, aggregate):                                       # the reference's loop, float for float
+        dim = v.shape[1]; rows = 1 if aggregate else dim
+        bins = np.zeros((rows, nb), np.float32); cnt = np.zeros(rows, np.int64)
+        ext = np.float32(hi) - np.float32(lo); inv = np.float32(1.0) / ext if ext > 0 else np.float32(0)
+        for f in range(v.shape[0]):
+            for i in range(dim):
+                x = np.float32(v[f, i])
+                if x < np.float32(lo) or np.float32(hi) < x: continue
+                b = min(max(int(np.float32(np.float32(x - np.float32(lo)) * inv) * np.float32(nb)), 0), nb - 1)
+                bins[0 if aggregate else i, b] += 1; cnt[0 if aggregate else i] += 1
+        width = ext / np.float32(nb)
+        for i in range(rows): bins[i] *= np.float32(1.0) / (width * np.float32(cnt[i]))
+        return bins
+    for nb, lo, hi, agg in ((32, 0.0, float(vals.max()), True), (16, 2.0, 9.0, False), (1024, 0.0, 20.0, True)):
+        got, (mn, mx) = plan.histogram("dp", nb, lo, hi, aggregate=agg)
+        want = ref_hist(vals, nb, lo, hi, agg)
+        assert got.shape == want.shape and np.array_equal(got, want) and mn == want.min() and mx == want.max(), (nb, agg)
+    got, _ = plan.histogram("d", 8, 8.0, 10.0)
+    assert got.shape == (1, 8) and np.array_equal(got, ref_hist(g["d__full"][:3].reshape(3, 1), 8, 8.0, 10.0, False))
+    with pytest.raises(vb.MdgpuError, match="not a temporal"):
+        vb.Plan(vb_system(s), vb.compile_script("r = rdf(element('O'), element('O'), 5.0);", vb_system(s)), F).histogram("r", 8, 0.0, 1.0)
+    plan.close()

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libmdgpu.so")
 DIST_BINS = 1024
 VOL_DIM = 128
 
-OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE, OP_WITHIN_COUNT, OP_SHAPE_WEIGHTS, OP_COORD_X, OP_COORD_Y, OP_COORD_Z = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19
+OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE, OP_WITHIN_COUNT, OP_SHAPE_WEIGHTS, OP_COORD_X, OP_COORD_Y, OP_COORD_Z, OP_BACKBONE_ANGLES = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20
 CELL_ORTHO, CELL_TRICLINIC, CELL_PBC_X, CELL_PBC_Y, CELL_PBC_Z, CELL_PBC_ALL = 1, 2, 4, 8, 16, 28
 
 
@@ -324,6 +324,13 @@ def coord(name, axis, idx):
     return Property(name, OP_COORD_X + int(axis), [np.asarray(idx, np.int32)])
 
 
+def backbone_angles(name, five):
+    """(phi, psi) of every backbone segment per frame (MDGPU_OP_BACKBONE_ANGLES): `five` is [n_segments, 5] = atoms C(i-1), N, CA, C, N(i+1) of each segment,
+    -1 rows for segments without angles (chain ends). The property is [F, 2 * n_segments] = md_backbone_angles_t per segment."""
+    five = np.ascontiguousarray(five, np.int32).reshape(-1, 5)
+    return Property(name, OP_BACKBONE_ANGLES, [five.reshape(-1)], num_structures=len(five))
+
+
 def rmsd(name, idx):
     """rmsd(selection): mass-weighted RMSD of the selection's atoms against the initial frame after wrap, bond-walk unwrap and an optimal
     rotation (_rmsd md_script_functions.inl:4287). Needs System.conn_offset / conn_idx to make molecules whole, as the reference does."""
@@ -488,6 +495,15 @@ class Plan:
         self._keep += [values, agg_mean, agg_var, agg_ext]
         ptr = lambda a: None if a is None else a.ctypes.data
         _check(lib().mdgpu_plan_bind_property_storage(self._h, self._index(name), values.ctypes.data, values.size, ptr(agg_mean), ptr(agg_var), ptr(agg_ext)))
+
+    def histogram(self, name, num_bins: int, range_min: float, range_max: float, aggregate: bool = False):
+        """VIAMD's compute_histogram_masked (src/main.cpp:172-226) of a temporal over the evaluated frames, counted on the device: ([rows, num_bins], (min, max))"""
+        i = self._index(name); dim = self.properties[i].num_structures if False else None
+        d = self.property_data(name); rows = 1 if aggregate else int(d.dim[1])
+        out = np.zeros((rows, num_bins), np.float32); mm = np.zeros(2, np.float32)
+        lib().mdgpu_plan_property_histogram.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        _check(lib().mdgpu_plan_property_histogram(self._h, i, num_bins, range_min, range_max, 1 if aggregate else 0, out.ctypes.data, mm.ctypes.data))
+        return out, (float(mm[0]), float(mm[1]))
 
     def exchange_stats(self):
         ms = C.c_double(); n = C.c_uint64(); _check(lib().mdgpu_plan_exchange_stats(self._h, C.byref(ms), C.byref(n))); return ms.value, int(n.value)

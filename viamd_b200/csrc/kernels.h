@@ -131,6 +131,8 @@ void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells,
 void launch_distance_pair(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb,
                           const float* d_posa, const float* d_posb, float* d_out, uint32_t frame0, cudaStream_t s);   // d_pos*: [B][n][3] group centres or null (atoms)
 void launch_coord_rows(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, int axis, float* d_out, uint32_t frame0, cudaStream_t s);   // coord_x/_y/_z
+void launch_temporal_histogram(const float* d_values, const unsigned long long* d_mask, uint32_t num_frames, uint32_t dim, float range_min, float range_max, float inv_range,
+                               uint32_t num_bins, int aggregate, uint32_t* d_counts, uint32_t* d_totals, cudaStream_t s);
 void launch_mean_u32(const uint32_t* d_in, float* d_out, size_t count, unsigned long long n, cudaStream_t s);
 
 // xtc.cu — compressed trajectory frames expanded on the device

@@ -385,7 +385,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
         for (int k = 0; k < 4; ++k) {
             if (d.idx[k] && d.idx_count[k]) {
                 pr.h_idx[k].assign(d.idx[k], d.idx[k] + d.idx_count[k]);
-                for (int32_t a : pr.h_idx[k]) if (a < 0 || (size_t)a >= sys->num_atoms) return bail(MDGPU_ERR_INVALID_ARG, "property '" + pr.name + "': atom index out of range");
+                for (int32_t a : pr.h_idx[k]) if ((a < 0 && !(pr.op == MDGPU_OP_BACKBONE_ANGLES && a == -1)) || (a >= 0 && (size_t)a >= sys->num_atoms)) return bail(MDGPU_ERR_INVALID_ARG, "property '" + pr.name + "': atom index out of range");
                 if (upload(&pr.d_idx[k], pr.h_idx[k].data(), pr.h_idx[k].size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (indices)");
             }
         }
@@ -537,6 +537,27 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f);
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 4; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
             break; }
+        case MDGPU_OP_BACKBONE_ANGLES: {   // two `dihedral in context` values per segment: phi = (C', N, CA, C), psi = (N, CA, C, N')
+            const size_t ns = pr.n_struct;
+            if (!ns || pr.h_idx[0].size() != 5 * ns) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': idx[0] must hold (C', N, CA, C, N') for each of the num_structures backbone segments");
+            const std::vector<int32_t> five = pr.h_idx[0];
+            std::vector<int32_t> ctx[4];
+            for (int k = 0; k < 4; ++k) ctx[k].resize(2 * ns);
+            for (size_t i = 0; i < ns; ++i) {
+                const int32_t* q = &five[5 * i];
+                const bool ok = q[0] >= 0 && q[1] >= 0 && q[2] >= 0 && q[3] >= 0 && q[4] >= 0;   // both angles or none (md_util.c:2592)
+                for (int k = 0; k < 4; ++k) { ctx[k][2 * i] = ok ? q[k] : -1; ctx[k][2 * i + 1] = ok ? q[k + 1] : -1; }
+            }
+            for (int k = 0; k < 4; ++k) {
+                cudaFree(pr.d_idx[k]); pr.d_idx[k] = nullptr; pr.h_idx[k] = ctx[k];
+                if (upload(&pr.d_idx[k], pr.h_idx[k].data(), pr.h_idx[k].size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (indices)");
+            }
+            pr.op = MDGPU_OP_DIHEDRAL; pr.n_struct = 2 * ns; pr.len = 2 * ns;
+            e = dalloc(&pr.d_temporal, num_frames * pr.len);
+            pr.values.assign(num_frames * pr.len, 0.0f);
+            pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f);
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = (int32_t)pr.len; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break; }
         case MDGPU_OP_RMSD: {   // an empty selection is valid and evaluates to 0 (_rmsd :4311, :4336-4338)
             std::vector<int2> pairs;   // without bonds md_util_unwrap_vec4 fails and its result is ignored (:4327): nothing is unwrapped
             build_unwrap_pairs(pairs, pr.h_idx[0].size(), p->conn_off, p->conn_idx);
@@ -563,7 +584,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
         std::vector<uint8_t> mark(N, 0);
         for (auto& pr : p->props) {
             if (pr.op == MDGPU_OP_WITHIN_COUNT || pr.ref_within > 0.0f) all_atoms = true;   // within() searches the whole system
-            for (int k = 0; k < 4; ++k) for (int32_t a : pr.h_idx[k]) mark[(size_t)a] = 1;
+            for (int k = 0; k < 4; ++k) for (int32_t a : pr.h_idx[k]) if (a >= 0) mark[(size_t)a] = 1;
         }
         for (size_t a = 0; a < N; ++a) if (mark[a]) p->needed.push_back((int32_t)a);
         const char* env = getenv("MDGPU_INGEST_MODE");
@@ -575,7 +596,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             std::vector<float> mc(p->num_atoms_c); for (size_t j = 0; j < mc.size(); ++j) mc[j] = p->h_mass[(size_t)p->needed[j]];
             if (upload(&p->d_mass_c, mc.data(), mc.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (masses)");
             for (auto& pr : p->props) for (int k = 0; k < 4; ++k) if (!pr.h_idx[k].empty()) {
-                std::vector<int32_t> ci(pr.h_idx[k].size()); for (size_t j = 0; j < ci.size(); ++j) ci[j] = map[(size_t)pr.h_idx[k][j]];
+                std::vector<int32_t> ci(pr.h_idx[k].size()); for (size_t j = 0; j < ci.size(); ++j) ci[j] = pr.h_idx[k][j] < 0 ? -1 : map[(size_t)pr.h_idx[k][j]];
                 pr.first_c[k] = ci[0];
                 if (upload(&pr.d_idx_c[k], ci.data(), ci.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (indices)");
             }
@@ -1626,6 +1647,33 @@ int mdgpu_plan_property_peek(mdgpu_plan* p, size_t prop, mdgpu_property_data_t* 
     if (!p || !out || prop >= p->props.size()) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_property_peek: invalid argument");
     *out = p->props[prop].data;
     return 0;
+}
+
+int mdgpu_plan_property_histogram(mdgpu_plan* p, size_t prop, uint32_t num_bins, float range_min, float range_max, int aggregate, float* out_bins, float* out_min_max) {
+    if (!p || prop >= p->props.size() || !out_bins || !num_bins) return fail(MDGPU_ERR_INVALID_ARG, "mdgpu_plan_property_histogram: invalid argument");
+    int rc = mdgpu_plan_sync(p); if (rc) return rc;
+    Prop& pr = p->props[prop];
+    if (!pr.d_temporal) return fail(MDGPU_ERR_INVALID_ARG, "property '%s' is not a temporal", pr.name.c_str());
+    const uint32_t dim = (uint32_t)pr.len, rows = aggregate ? 1u : dim;
+    std::vector<uint64_t> mask; { std::lock_guard<std::mutex> lk(p->mask_mutex); mask = p->frame_mask; }
+    unsigned long long* d_mask = nullptr; uint32_t* d_counts = nullptr; uint32_t* d_tot = nullptr;
+    auto done = [&](int r) { cudaFree(d_mask); cudaFree(d_counts); cudaFree(d_tot); return r; };
+    if (dalloc(&d_mask, mask.size()) != cudaSuccess || dalloc(&d_counts, (size_t)rows * num_bins) != cudaSuccess || dalloc(&d_tot, rows) != cudaSuccess) return done(fail(MDGPU_ERR_CUDA, "device allocation failed (histogram)"));
+    cudaMemcpy(d_mask, mask.data(), sizeof(uint64_t) * mask.size(), cudaMemcpyHostToDevice);
+    cudaMemset(d_counts, 0, sizeof(uint32_t) * (size_t)rows * num_bins); cudaMemset(d_tot, 0, sizeof(uint32_t) * rows);
+    const float range_ext = range_max - range_min, inv_range = range_ext > 0.0f ? 1.0f / range_ext : 0.0f;   // src/main.cpp:188-189
+    launch_temporal_histogram(pr.d_temporal, d_mask, (uint32_t)p->num_frames, dim, range_min, range_max, inv_range, num_bins, aggregate, d_counts, d_tot, 0);
+    std::vector<uint32_t> counts((size_t)rows * num_bins), tot(rows);
+    if (cudaMemcpy(counts.data(), d_counts, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(tot.data(), d_tot, sizeof(uint32_t) * rows, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return done(fail(MDGPU_ERR_CUDA, "histogram copy failed: %s", cudaGetErrorString(cudaGetLastError())));
+    float min_bin = FLT_MAX, max_bin = -FLT_MAX;
+    const float width = range_ext / (float)num_bins;                                  // :213-222
+    for (uint32_t i = 0; i < rows; ++i) {
+        const float scl = 1.0f / (width * (float)(int)tot[i]);
+        for (uint32_t j = 0; j < num_bins; ++j) { float v = (float)counts[(size_t)i * num_bins + j]; v *= scl; out_bins[(size_t)i * num_bins + j] = v; min_bin = std::min(min_bin, v); max_bin = std::max(max_bin, v); }
+    }
+    if (out_min_max) { out_min_max[0] = min_bin; out_min_max[1] = max_bin; }
+    return done(0);
 }
 
 int mdgpu_plan_property_counts(mdgpu_plan* p, size_t prop, uint64_t* out, size_t out_len) {

@@ -322,9 +322,39 @@ __global__ void k_temporal_ctx(TemporalArgs a, int B) {
     if (c >= a.n_ctx) return;
     const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride; const float* y = x + a.frames.axis_stride; const float* z = y + a.frames.axis_stride;
     const int nargs = a.op == MDGPU_OP_DISTANCE ? 2 : (a.op == MDGPU_OP_ANGLE ? 3 : 4);
-    float P[4][3];
-    for (int k = 0; k < nargs; ++k) { const int at = a.ctx_idx[k][c]; P[k][0] = x[at]; P[k][1] = y[at]; P[k][2] = z[at]; }
-    a.out[(size_t)(a.frame0 + f) * a.n_ctx + c] = temporal_value(a.op, P, a.cells[f]);
+    float P[4][3]; bool defined = true;
+    for (int k = 0; k < nargs; ++k) {
+        const int at = a.ctx_idx[k][c];
+        if (at < 0) { defined = false; break; }   // backbone angles: the end segments of a chain have no phi / psi and stay 0 (md_util.c:2576, :2592)
+        P[k][0] = x[at]; P[k][1] = y[at]; P[k][2] = z[at];
+    }
+    a.out[(size_t)(a.frame0 + f) * a.n_ctx + c] = defined ? temporal_value(a.op, P, a.cells[f]) : 0.0f;
+}
+
+// Histogram of a temporal's values over the frames of `mask` — the counting half of VIAMD's compute_histogram_masked (src/main.cpp:172-226):
+// values outside [range_min, range_max] are skipped, bin = clamp((int)(((v - min) * inv_range) * num_bins)). counts: [dim or 1][num_bins],
+// totals: [dim or 1] samples that landed in a bin.
+__global__ void k_temporal_histogram(const float* __restrict__ values, const unsigned long long* __restrict__ mask, uint32_t num_frames, uint32_t dim, float range_min, float range_max,
+                                     float inv_range, uint32_t num_bins, int aggregate, uint32_t* __restrict__ counts, uint32_t* __restrict__ totals) {
+    const size_t n = (size_t)num_frames * dim;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t f = (uint32_t)(i / dim), c = (uint32_t)(i % dim);
+        if (!((mask[f >> 6] >> (f & 63)) & 1ull)) continue;
+        const float v = values[i];
+        if (v < range_min || range_max < v) continue;
+        int b = __float2int_rz(__fmul_rn(__fmul_rn(__fsub_rn(v, range_min), inv_range), (float)num_bins));
+        b = max(0, min(b, (int)num_bins - 1));
+        const uint32_t row = aggregate ? 0u : c;
+        atomicAdd(&counts[(size_t)row * num_bins + (uint32_t)b], 1u);
+        atomicAdd(&totals[row], 1u);
+    }
+}
+void launch_temporal_histogram(const float* d_values, const unsigned long long* d_mask, uint32_t num_frames, uint32_t dim, float range_min, float range_max, float inv_range,
+                               uint32_t num_bins, int aggregate, uint32_t* d_counts, uint32_t* d_totals, cudaStream_t s) {
+    const size_t n = (size_t)num_frames * dim; if (!n) return;
+    const size_t want = (n + 255) / 256; const unsigned blocks = (unsigned)(want < 1184 ? want : 1184);
+    k_temporal_histogram<<<blocks, 256, 0, s>>>(d_values, d_mask, num_frames, dim, range_min, range_max, inv_range, num_bins, aggregate, d_counts, d_totals);
+    note_launch("k_temporal_histogram", s);
 }
 
 // com(x) (_com md_script_functions.inl:4726): the position coordinate_extract_com yields for the argument — an atom's coordinates or the
