@@ -108,6 +108,7 @@ typedef enum mdgpu_op {
                                   * (src/components/shapespace/shapespace.cpp:404-431) and _shape_weights (md_script_functions.inl:6005-6050) */
     MDGPU_OP_COORD_X = 17, MDGPU_OP_COORD_Y = 18, MDGPU_OP_COORD_Z = 19,   /* coord_x/_y/_z(selection): the atoms' coordinates -> temporal [F, n]  :5077-5169 */
     MDGPU_OP_RMSD = 11,      /* rmsd(selection) against the initial frame -> temporal                     :4287-4345 */
+    MDGPU_OP_CONTACT_COUNT = 21, /* contact_count(A[], B, cutoff [, path]) -> temporal [F, |A|]                      :2756-2866 */
     MDGPU_OP_BACKBONE_ANGLES = 20, /* (phi, psi) of every backbone segment per frame -> temporal [F, 2 * n_segments]: VIAMD's "Backbone Operations" pass
                                     * (src/viamd.cpp:488-520 -> md_util_backbone_angles_compute md_util.c:2572-2620) */
 } mdgpu_op;
@@ -139,6 +140,11 @@ typedef enum mdgpu_op {
  *   SHAPE_WEIGHTS: idx[0] = the atoms of num_structures structures back to back (structure_offsets, or structure_size each), bit 0 of com_args
  *              = weights are the atom masses (shapespace's use_mass; _shape_weights always uses them), else 1.
  *   COORD_X/_Y/_Z: idx[0] = the atoms.
+ *   CONTACT_COUNT: idx[0] = the atoms of the sets A_i back to back (structure_offsets, or structure_size each; num_structures sets), idx[1] = the atoms
+ *              of B (flattened), cutoff_max = cutoff. Per frame and set: the number of (a in A_i, b in B) pairs within the cutoff whose b is not
+ *              excluded, where the exclusion of set i is A_i & B grown along the bonds by `structure_size_b`... see structure_offsets_b below: the host
+ *              passes the exclusion lists it derived (CSR in idx[2] / structure_offsets_b, num_structures_b = num_structures). Value i of a frame is the
+ *              RUNNING total over sets 0..i: the reference never resets its counter between the sets of a frame (:2838-2847), reproduced.
  *   BACKBONE_ANGLES: idx[0] = for each of the num_structures backbone segments the five atoms C(i-1), N(i), CA(i), C(i), N(i+1)
  *              (md_protein_backbone_data_t::segment.atoms of the segment and its neighbours), back to back; -1 in any of the five marks a segment without angles (the first / last residue of a chain, chains shorter than 4:
  *              md_util.c:2588-2592) whose two values stay 0. Row f holds md_backbone_angles_t[num_structures] = (phi, psi) pairs in radians:
@@ -148,6 +154,16 @@ typedef enum mdgpu_op {
  *              argument that was a selection (bit k of com_args set, or more than one index) is its centre of mass as
  *              coordinate_extract_com evaluates it (:1717 -> md_util_com_compute md_util.c:8163: periodic cells use the
  *              trigonometric centre of mass _com_pbc_iw :7850, 8-lane float accumulation as in the AVX2 build). */
+/* A dynamic selection as an argument: within([radius_min:]radius_max, selection) [and static_selection] (_within_expl_flt / _frng
+ * md_script_functions.inl:2485-2720, `and` :1975), evaluated per frame on the device over the system-wide cell list (get_spatial_acc :734).
+ * For argument k of a property, idx[k] holds the atoms of the within() selection and dyn[k] the rest. */
+typedef struct mdgpu_dynamic_arg_t {
+    float radius_min, radius_max;   /* radius_max > 0 switches the argument to dynamic */
+    const int32_t* and_idx;         /* the static side of `selection and within(...)`, or NULL */
+    size_t and_count;
+    uint32_t has_and;               /* 1: and_idx is meaningful even when empty (`nothing and within(...)` selects nothing) */
+} mdgpu_dynamic_arg_t;
+
 typedef struct mdgpu_property_desc_t {
     const char* name;
     uint32_t op;
@@ -163,6 +179,9 @@ typedef struct mdgpu_property_desc_t {
     float ref_within_min;                /* ... within(min:radius, idx[0]) (_within_expl_frng :2609); 0 for the plain form */
     const uint32_t* structure_offsets_b; /* distance_pair: CSR groups of argument 1 when it was an array of selections (argument 0 uses structure_offsets) */
     size_t num_structures_b;
+    mdgpu_dynamic_arg_t dyn[4];          /* per argument: a dynamic selection (see above). Consumers: rdf reference and / or target, sdf target, density_x/_y/_z,
+                                          * distance / angle / dihedral / com (the centre of mass of the frame's selection), distance_min / _max, count().
+                                          * ref_within_radius (+ com_args bit 0 / idx[2]) is the round-1 spelling of dyn[0] for rdf and still honoured. */
 } mdgpu_property_desc_t;
 
 /* Result view: the fields of md_script_property_data_t (md_script.h:73-92) that the evaluation fills. */

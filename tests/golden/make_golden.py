@@ -249,6 +249,28 @@ def water12_avg(tmp):
     np.savez_compressed(os.path.join(HERE, "water12_avg.npz"), **out)
 
 
+DYN_SCRIPT = ("rwt = rdf(element('O'), within(4.0, residue(1)), 6.0); rww = rdf(within(4.0, residue(1)), within(5.0, residue(2)), 6.0); "
+              "vw = sdf(residue(1:20), within(6.0, residue(1:5)), 5.0); dzw = density_z(within(5.0, residue(1))); dw = distance(within(4.0, residue(1)), 200); "
+              "cmw = com(within(4.0, residue(1))); dmw = distance_min(within(3.5, residue(1)), residue(30)); "
+              "rwo = rdf(element('O') and within(5.0, residue(2)), element('H') and within(6.0, residue(3)), 5.0); aw = angle(within(2.5:5.0, residue(4)), 10, residue(7)); "
+              "cc = contact_count(residue(1:5), residue(10:40), 4.0); cc2 = contact_count(residue(3:20), element('O') and residue(50:216), 3.5);")
+
+
+def dyn6(tmp):
+    """Dynamic selections (within([min:]max, sel) [and static]) as arguments of every consumer the device path lowers, and contact_count with
+    disjoint sets (its exclusion mask is then empty and the reference deterministic, md_util.c:5537-5560), on the water6 and tric6 frames."""
+    out = {"script": np.array(DYN_SCRIPT)}
+    w = np.load(os.path.join(HERE, "water6.npz")); t = np.load(os.path.join(HERE, "tric6.npz"))
+    for tag, g, seed in (("w", w, "77"), ("t", t, "91")):
+        gro, raw, o = os.path.join(tmp, tag + "d.gro"), os.path.join(tmp, tag + "d.raw"), os.path.join(tmp, tag + "d.out")
+        F = g["frames"].shape[0]
+        run(SYNTH, "water-gro", "6", seed, gro); refio.write_raw_traj(raw, g["frames"], g["cells"], g["cell_flags"])
+        run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", DYN_SCRIPT, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
+        sub = {}; pack(sub, refio.read_refout(o), list(range(F)))
+        for k, v in sub.items(): out[f"{tag}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "dyn6.npz"), **out)
+
+
 def backbone(tmp):
     """phi / psi of every backbone segment per frame from the reference's md_util_backbone_angles_compute (harness mode `backbone`: the loop body of
     VIAMD's "Backbone Operations" task, src/viamd.cpp:488-520) on the 50 ala50 frames: the segments' five atoms (-1 rows: no angles) + angles[F][nseg][2]."""
@@ -311,7 +333,7 @@ if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     only = sys.argv[1:]   # e.g. `python make_golden.py water32_full water12_avg` regenerates just those
     gens = dict(water6=water6, ala50=ala50, membrane6=membrane6, tric6=tric6, tric6_rmsd=tric6_rmsd, pairs6=pairs6, shapes=shapes, xtc_cases=xtc_cases,
-                water32_full=water32_full, water12_avg=water12_avg, backbone=backbone)
+                water32_full=water32_full, water12_avg=water12_avg, backbone=backbone, dyn6=dyn6)
     with tempfile.TemporaryDirectory() as tmp:
         for name, fn in gens.items():
             if not only or name in only: fn(tmp)

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from helpers import load_golden, cell_from_row, golden_system, sel_element, vb_system, vb_cell
+from helpers import load_golden, cell_from_row, dense_from_sparse, golden_system, sel_element, vb_system, vb_cell
 
 pytestmark = pytest.mark.gpu
 
@@ -403,4 +403,68 @@ def test_temporal_histogram_on_the_device():
     assert got.shape == (1, 8) and np.array_equal(got, ref_hist(g["d__full"][:3].reshape(3, 1), 8, 8.0, 10.0, False))
     with pytest.raises(vb.MdgpuError, match="not a temporal"):
         vb.Plan(vb_system(s), vb.compile_script("r = rdf(element('O'), element('O'), 5.0);", vb_system(s)), F).histogram("r", 8, 0.0, 1.0)
+    plan.close()
+
+
+def _dyn_plan(tag):
+    vb = _vb(); g = load_golden("dyn6.npz"); src = load_golden("water6.npz" if tag == "w" else "tric6.npz"); s = golden_system(src)
+    sysm = vb_system(s); F = src["frames"].shape[0]
+    plan = vb.Plan(sysm, vb.compile_script(str(g["script"]), sysm), F, keep_frame_results=True, batch_frames=3)
+    cells = [vb_cell(src["cells"][f], src["cell_flags"][f]) for f in range(F)]
+    plan.set_initial_frame(*src["frames"][0], cells[0])
+    plan.eval_host_frames(src["frames"], cells, 0)
+    return plan, g, F
+
+
+@pytest.mark.parametrize("tag", ["w", "t"])
+def test_dynamic_selections_as_arguments_of_every_lowered_consumer(tag):
+    """within([min:]max, sel) [and static] as rdf reference AND target, sdf target, density_z argument, centre-of-mass argument
+    of distance / angle / com, distance_min argument — each against the reference's values on the orthorhombic (w) and the changing
+    triclinic (t) frames (tests/golden/dyn6.npz): integer bins / voxels bit-exact, floats as the static forms of the same procedures."""
+    plan, g, F = _dyn_plan(tag)
+    for key in ("rwt", "rww", "rwo"):
+        for f in range(F):
+            bins, tot = plan.frame_counts(key, f); ref = g[f"{tag}_{key}__pf"][f, :1024]
+            assert np.array_equal(bins.astype(np.float32), ref) and tot == int(ref.sum()), (key, f)
+        assert np.array_equal(plan.property_data(key).weights, g[f"{tag}_{key}__pf"][F - 1, 1024:]), key
+    vol = np.zeros(128 ** 3, np.float32)
+    for f in range(F): vol += dense_from_sparse(g[f"{tag}_vw__pf{f}_idx"], g[f"{tag}_vw__pf{f}_val"])
+    assert np.array_equal(plan.counts("vw").astype(np.float32), vol) and vol.sum() > 0
+    np.testing.assert_allclose(plan.property_data("dzw").values[:1024], g[f"{tag}_dzw__full"][:1024], rtol=1e-5, atol=1e-3)
+    for key in ("dw", "dmw"): assert _same(plan.property_data(key).values, g[f"{tag}_{key}__full"]), key
+    assert _same(plan.property_data("cmw").values, g[f"{tag}_cmw__full"])
+    np.testing.assert_allclose(plan.property_data("aw").values, g[f"{tag}_aw__full"], rtol=1e-5, atol=1e-6)
+    plan.close()
+
+
+@pytest.mark.parametrize("tag", ["w", "t"])
+def test_contact_count_running_totals(tag):
+    """contact_count(A[], B, cutoff) (md_script_functions.inl:2756-2866) with disjoint sets — the reference's exclusion mask is then empty and its
+    result deterministic: per frame the RUNNING total over the sets (the reference never resets its counter), equal to the reference's floats."""
+    plan, g, F = _dyn_plan(tag)
+    for key in ("cc", "cc2"):
+        d = plan.property_data(key); ref = g[f"{tag}_{key}__full"]
+        assert d.values.shape == ref.shape and np.array_equal(d.values, ref), key
+        row = d.values.reshape(F, -1); assert np.all(np.diff(row, axis=1) >= 0) and row[:, -1].min() > 0
+    plan.close()
+
+
+def test_contact_count_exclusion_lists_and_errors():
+    """overlapping sets: b atoms within `path_length` bonds of A_i & B are excluded (md_util_mask_grow_by_bonds, intended breadth-first semantics —
+    the reference walks an unzeroed depth array there, md_util.c:5560, so this case is pinned against a brute-force count, not the reference)."""
+    vb = _vb(); g = load_golden("water6.npz"); s = golden_system(g); sysm = vb_system(s); F = g["frames"].shape[0]
+    A = [np.arange(0, 9, dtype=np.int32), np.arange(30, 36, dtype=np.int32)]; Bsel = np.arange(0, 120, dtype=np.int32)
+    plan = vb.Plan(sysm, [vb.contact_count("c", A, Bsel, 3.5, sysm, 1)], F)
+    cells = [vb_cell(g["cells"][f], g["cell_flags"][f]) for f in range(F)]
+    plan.eval_host_frames(g["frames"], cells, 0)
+    got = plan.property_data("c").values.reshape(F, 2)
+    for f in range(F):
+        x, y, z = g["frames"][f]; cell = cell_from_row(g["cells"][f], g["cell_flags"][f]); run = 0; want = []
+        for a_set in A:
+            excl = set(vb.api.grow_by_bonds(np.intersect1d(a_set, Bsel), sysm.conn_offset, sysm.conn_idx, 1).tolist())
+            trg = np.array([b for b in Bsel if b not in excl], np.int32)
+            run += O.count_pairs(x, y, z, a_set, trg, cell, 3.5, 3.5); want.append(run)
+        assert list(got[f]) == [float(w) for w in want], f
+    with pytest.raises(vb.MdgpuError, match="cutoff distance must be positive"):
+        vb.Plan(sysm, [vb.contact_count("c", A, Bsel, 0.0, sysm)], F)
     plan.close()

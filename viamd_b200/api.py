@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(HERE, "libmdgpu.so")
 DIST_BINS = 1024
 VOL_DIM = 128
 
-OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE, OP_WITHIN_COUNT, OP_SHAPE_WEIGHTS, OP_COORD_X, OP_COORD_Y, OP_COORD_Z, OP_BACKBONE_ANGLES = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20
+OP_RDF, OP_SDF, OP_DENSITY_X, OP_DENSITY_Y, OP_DENSITY_Z, OP_DISTANCE, OP_ANGLE, OP_DIHEDRAL, OP_DISTANCE_MIN, OP_DISTANCE_MAX, OP_RMSD, OP_DISTANCE_PAIR, OP_COM, OP_PLANE, OP_WITHIN_COUNT, OP_SHAPE_WEIGHTS, OP_COORD_X, OP_COORD_Y, OP_COORD_Z, OP_BACKBONE_ANGLES, OP_CONTACT_COUNT = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21
 CELL_ORTHO, CELL_TRICLINIC, CELL_PBC_X, CELL_PBC_Y, CELL_PBC_Z, CELL_PBC_ALL = 1, 2, 4, 8, 16, 28
 
 
@@ -66,11 +66,15 @@ class _SystemDesc(C.Structure):
                 ("bond_conn_atom_idx", C.POINTER(C.c_int32)), ("bond_conn_offset_count", C.c_size_t)]
 
 
+class _DynArg(C.Structure):   # mdgpu_dynamic_arg_t
+    _fields_ = [("radius_min", C.c_float), ("radius_max", C.c_float), ("and_idx", C.POINTER(C.c_int32)), ("and_count", C.c_size_t), ("has_and", C.c_uint32)]
+
+
 class _PropertyDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("op", C.c_uint32), ("idx", C.POINTER(C.c_int32) * 4), ("idx_count", C.c_size_t * 4),
                 ("num_structures", C.c_size_t), ("structure_size", C.c_size_t), ("cutoff_min", C.c_float), ("cutoff_max", C.c_float),
                 ("structure_offsets", C.POINTER(C.c_uint32)), ("com_args", C.c_uint32), ("ref_within_radius", C.c_float), ("ref_within_min", C.c_float),
-                ("structure_offsets_b", C.POINTER(C.c_uint32)), ("num_structures_b", C.c_size_t)]
+                ("structure_offsets_b", C.POINTER(C.c_uint32)), ("num_structures_b", C.c_size_t), ("dyn", _DynArg * 4)]
 
 
 class _PropertyData(C.Structure):
@@ -218,10 +222,31 @@ class Property:
     ref_within: float = 0.0                          # rdf: > 0 -> references = within([ref_within_min:]ref_within, idx[0]) evaluated per frame
     ref_within_min: float = 0.0
     structure_offsets_b: Optional[np.ndarray] = None  # distance_pair: CSR groups of argument 1 (argument 0 uses structure_offsets)
+    dyn: dict = field(default_factory=dict)           # {k: (radius_min, radius_max, and_idx | None)}: argument k is within([min:]max, idx[k]) [and and_idx], per frame
+
+
+class Within:
+    """within([radius_min:]radius, selection) [and a static selection] as a property argument: the atoms of the system within reach of the
+    selection in each frame, the selection itself excluded (md_script_functions.inl:2485-2720) — evaluated per frame on the device."""
+
+    def __init__(self, radius, sel_idx, radius_min=0.0, and_idx=None):
+        self.radius, self.radius_min = float(radius), float(radius_min)
+        self.sel = np.asarray(sel_idx, np.int32); self.and_idx = None if and_idx is None else np.asarray(and_idx, np.int32)
+
+
+def _split_dyn(args):
+    """[index array | Within, ...] -> (idx lists, dyn dict)"""
+    idx, dyn = [], {}
+    for k, a in enumerate(args):
+        if isinstance(a, Within): idx.append(a.sel); dyn[k] = (a.radius_min, a.radius, a.and_idx)
+        else: idx.append(np.asarray(a, np.int32))
+    return idx, dyn
 
 
 def rdf(name, ref_idx, trg_idx, cutoff, cutoff_min=0.0):
-    return Property(name, OP_RDF, [np.asarray(ref_idx, np.int32), np.asarray(trg_idx, np.int32)], cutoff_min=float(cutoff_min), cutoff_max=float(cutoff))
+    """ref_idx / trg_idx: atom index arrays, or Within(...) for a selection evaluated per frame"""
+    idx, dyn = _split_dyn([ref_idx, trg_idx])
+    return Property(name, OP_RDF, idx, cutoff_min=float(cutoff_min), cutoff_max=float(cutoff), dyn=dyn)
 
 
 def rdf_within(name, radius, sel_idx, trg_idx, cutoff, cutoff_min=0.0, radius_min=0.0, and_idx=None):
@@ -244,11 +269,13 @@ def rdf_com(name, groups, trg_idx, cutoff, cutoff_min=0.0):
 def sdf(name, structures, trg_idx, cutoff):
     s = np.ascontiguousarray(structures, np.int32)
     assert s.ndim == 2, "structures: [num_structures, structure_size] atom indices"
-    return Property(name, OP_SDF, [s.reshape(-1), np.asarray(trg_idx, np.int32)], num_structures=s.shape[0], structure_size=s.shape[1], cutoff_max=float(cutoff))
+    idx, dyn = _split_dyn([s.reshape(-1), trg_idx])
+    return Property(name, OP_SDF, idx, num_structures=s.shape[0], structure_size=s.shape[1], cutoff_max=float(cutoff), dyn=dyn)
 
 
 def density(name, axis, idx):
-    return Property(name, OP_DENSITY_X + int(axis), [np.asarray(idx, np.int32)])
+    lst, dyn = _split_dyn([idx])
+    return Property(name, OP_DENSITY_X + int(axis), lst, dyn=dyn)
 
 
 def in_contexts(name, op, local_idx, context_first_atoms):
@@ -261,11 +288,12 @@ def in_contexts(name, op, local_idx, context_first_atoms):
 def _temporal(name, op, args):
     """each argument: an int (0-based atom index -> that atom's position) or an index array (a selection -> centre of mass,
     coordinate_extract_com md_script_functions.inl:1717)"""
-    idx, mask = [], 0
+    idx, mask, dyn = [], 0, {}
     for k, a in enumerate(args):
-        if np.ndim(a) == 0: idx.append(np.asarray([int(a)], np.int32))
+        if isinstance(a, Within): idx.append(a.sel); mask |= 1 << k; dyn[k] = (a.radius_min, a.radius, a.and_idx)   # the frame's dynamic selection: its centre of mass
+        elif np.ndim(a) == 0: idx.append(np.asarray([int(a)], np.int32))
         else: idx.append(np.asarray(a, np.int32)); mask |= 1 << k
-    return Property(name, op, idx, com_args=mask)
+    return Property(name, op, idx, com_args=mask, dyn=dyn)
 
 
 def distance(name, a, b):
@@ -274,12 +302,14 @@ def distance(name, a, b):
 
 def distance_min(name, a_idx, b_idx):
     """distance_min(a, b): smallest pair distance between the atoms of two selections (md_script_functions.inl:3892)"""
-    return Property(name, OP_DISTANCE_MIN, [np.asarray(a_idx, np.int32), np.asarray(b_idx, np.int32)])
+    idx, dyn = _split_dyn([a_idx, b_idx])
+    return Property(name, OP_DISTANCE_MIN, idx, dyn=dyn)
 
 
 def distance_max(name, a_idx, b_idx):
     """distance_max(a, b): the reference evaluates md_util_min_distance here as well (md_script_functions.inl:3944) — reproduced"""
-    return Property(name, OP_DISTANCE_MAX, [np.asarray(a_idx, np.int32), np.asarray(b_idx, np.int32)])
+    idx, dyn = _split_dyn([a_idx, b_idx])
+    return Property(name, OP_DISTANCE_MAX, idx, dyn=dyn)
 
 
 def distance_pair(name, a, b):
@@ -322,6 +352,37 @@ def shape_weights(name, groups, use_mass=True):
 def coord(name, axis, idx):
     """coord_x / coord_y / coord_z(selection): the atoms' coordinates along `axis` -> [F, n] (md_script_functions.inl:5077)"""
     return Property(name, OP_COORD_X + int(axis), [np.asarray(idx, np.int32)])
+
+
+def grow_by_bonds(atoms, conn_offset, conn_idx, extent: int):
+    """md_util_mask_grow_by_bonds (md_util.c:5537-5595) as intended: every atom within `extent` bonds of the given atoms (the reference walks
+    a depth array it never zeroes; with zeroed memory it is this breadth-first search)."""
+    atoms = [int(a) for a in atoms]
+    if not atoms or conn_offset is None: return np.asarray(sorted(atoms), np.int32)
+    depth = {a: 0 for a in atoms}; queue = list(atoms)
+    while queue:
+        a = queue.pop(0)
+        if depth[a] >= extent: continue
+        for k in range(int(conn_offset[a]), int(conn_offset[a + 1])):
+            b = int(conn_idx[k])
+            if b not in depth or depth[a] + 1 < depth[b]:
+                depth[b] = depth[a] + 1; queue.append(b)
+    return np.asarray(sorted(depth), np.int32)
+
+
+def contact_count(name, groups, b_idx, cutoff, system: "System" = None, path_length: int = 4):
+    """contact_count(A[], B, cutoff [, path_length]): per frame and set A_i the pairs (a in A_i, b in B) within the cutoff, b outside the set's
+    exclusion list = (A_i & B) grown by `path_length` bonds (md_script_functions.inl:2756-2866); the values of a frame are RUNNING totals over
+    the sets, as the reference's never-reset counter produces them. -> temporal [F, |A|]"""
+    groups = [np.asarray(g, np.int32) for g in groups]; b = np.unique(np.asarray(b_idx, np.int32))
+    off = np.zeros(len(groups) + 1, np.uint32); off[1:] = np.cumsum([len(g) for g in groups])
+    excl = []
+    for g in groups:
+        ov = np.intersect1d(g, b)
+        excl.append(grow_by_bonds(ov, None if system is None else system.conn_offset, None if system is None else system.conn_idx, path_length) if len(ov) else np.zeros(0, np.int32))
+    eoff = np.zeros(len(groups) + 1, np.uint32); eoff[1:] = np.cumsum([len(e) for e in excl])
+    return Property(name, OP_CONTACT_COUNT, [np.concatenate(groups).astype(np.int32), b, np.concatenate(excl).astype(np.int32) if eoff[-1] else np.zeros(0, np.int32)],
+                    num_structures=len(groups), cutoff_max=float(cutoff), structure_offsets=off, structure_offsets_b=eoff)
 
 
 def backbone_angles(name, five):
@@ -455,6 +516,11 @@ class Plan:
             for k, arr in enumerate(p.idx):
                 a = np.ascontiguousarray(arr, np.int32); self._keep.append(a)
                 d.idx[k] = a.ctypes.data_as(C.POINTER(C.c_int32)); d.idx_count[k] = a.size
+            for k, (rmin, rmax, and_idx) in p.dyn.items():
+                d.dyn[k].radius_min = rmin; d.dyn[k].radius_max = rmax
+                if and_idx is not None:
+                    m = np.ascontiguousarray(and_idx, np.int32); self._keep.append(m)
+                    d.dyn[k].and_idx = m.ctypes.data_as(C.POINTER(C.c_int32)); d.dyn[k].and_count = m.size; d.dyn[k].has_and = 1
         o = _PlanOptions(); o.device = device; o.batch_frames = batch_frames; o.num_streams = num_streams
         o.keep_frame_results = 1 if keep_frame_results else 0; o.cell_capacity = cell_capacity; o.rdf_variant = rdf_variant
         o.ingest_mode = ingest_mode; o.ingest_threads = ingest_threads

@@ -132,8 +132,9 @@ MDG_D void atomic_max_f(float* addr, float v) {
     while (__int_as_float(old) < v) { const int assumed = old; old = atomicCAS(ia, assumed, __float_as_int(v)); if (old == assumed) break; }
 }
 
-__global__ void k_aabb(BatchFrames fr, const int32_t* __restrict__ idx, uint32_t n, float* __restrict__ aabb /* [B][6], zero-initialised */) {
+__global__ void k_aabb(BatchFrames fr, const int32_t* __restrict__ idx_, uint32_t n_, float* __restrict__ aabb /* [B][6], zero-initialised */, DynSel dyn) {
     const int f = blockIdx.y;
+    const int32_t* __restrict__ idx = sel_list(idx_, dyn, f); const uint32_t n = sel_count(n_, dyn, f);
     const float* x = fr.xyz + (size_t)f * fr.frame_stride; const float* y = x + fr.axis_stride; const float* z = y + fr.axis_stride;
     float mn[3] = { 0.f, 0.f, 0.f }, mx[3] = { 0.f, 0.f, 0.f };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -150,9 +151,10 @@ __global__ void k_aabb(BatchFrames fr, const int32_t* __restrict__ idx, uint32_t
 // MODE 0: internal (target) points -> clamped cell index (:341-371)
 // MODE 1: external (reference) points -> unclamped home cell (:1713-1719 ortho wraps periodic axes, :1561-1566 triclinic does not)
 template <int MODE>
-__global__ void k_bin_points(BatchFrames fr, const int32_t* __restrict__ idx, const float* __restrict__ aos /* [B][n][3] or null */, uint32_t n,
-                             const FrameGeom* __restrict__ geom, CellList cl, int store_linear_idx) {
+__global__ void k_bin_points(BatchFrames fr, const int32_t* __restrict__ idx_, const float* __restrict__ aos /* [B][n][3] or null */, uint32_t n_,
+                             const FrameGeom* __restrict__ geom, CellList cl, int store_linear_idx, DynSel dyn) {
     const int f = blockIdx.y;
+    const int32_t* __restrict__ idx = sel_list(idx_, dyn, f); const uint32_t n = sel_count(n_, dyn, f);   // per-frame list of a dynamic selection, or the static one
     __shared__ FrameGeom g;
     for (int k = threadIdx.x; k < (int)(sizeof(FrameGeom) / 4); k += blockDim.x) ((uint32_t*)&g)[k] = ((const uint32_t*)&geom[f])[k];
     __syncthreads();
@@ -239,10 +241,10 @@ __global__ void k_scan_cells(const FrameGeom* __restrict__ geom, CellList cl) {
     }
 }
 
-__global__ void k_scatter_points(uint32_t n, CellList cl) {
+__global__ void k_scatter_points(uint32_t n, CellList cl, const uint32_t* __restrict__ dyn_n) {
     const int f = blockIdx.y;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= (dyn_n ? dyn_n[f] : n)) return;
     const size_t o = (size_t)f * cl.max_points + i;
     const uint32_t dst = cl.cell_cnt[(size_t)f * (cl.cap + 1) + cl.cell_of[o]] + cl.rank[o];
     cl.sorted[(size_t)f * cl.max_points + dst] = cl.scratch[o];
@@ -257,11 +259,12 @@ void launch_geom(const mdgpu_unitcell_t* d_cells, const float* d_aabb, FrameGeom
     note_launch("k_frame_geom", s);
 }
 
-void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float* d_aabb, cudaStream_t s) {
+void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float* d_aabb, cudaStream_t s, DynSel dyn) {
     cudaMemsetAsync(d_aabb, 0, sizeof(float) * 6 * fr.count, s);
+    if (dyn.n) n = dyn.stride;   // upper bound of a per-frame list
     if (!n) return;
     dim3 grid(min((n + 255u) / 256u, 64u), fr.count);
-    k_aabb<<<grid, 256, 0, s>>>(fr, d_idx, n, d_aabb);
+    k_aabb<<<grid, 256, 0, s>>>(fr, d_idx, n, d_aabb, dyn);
     note_launch("k_aabb", s);
 }
 
@@ -271,13 +274,14 @@ void launch_scan_home_cells(const FrameGeom* d_geom, const CellList& cl, int B, 
 }
 
 void launch_cell_list(int mode, const BatchFrames& fr, const int32_t* d_idx, const float* d_aos, uint32_t n, const FrameGeom* d_geom,
-                      const CellList& cl, int store_linear_idx, cudaStream_t s) {
+                      const CellList& cl, int store_linear_idx, cudaStream_t s, DynSel dyn) {
     cudaMemsetAsync(cl.cell_cnt, 0, sizeof(uint32_t) * (size_t)fr.count * (cl.cap + 1), s);
     cudaMemsetAsync(cl.oob, 0, sizeof(uint32_t) * fr.count, s);
+    if (dyn.n) n = dyn.stride;   // grid for the longest possible per-frame list; each frame stops at its own count
     if (n) {
         dim3 grid((n + 255u) / 256u, fr.count);
-        if (mode == 0) k_bin_points<0><<<grid, 256, 0, s>>>(fr, d_idx, d_aos, n, d_geom, cl, store_linear_idx);
-        else           k_bin_points<1><<<grid, 256, 0, s>>>(fr, d_idx, d_aos, n, d_geom, cl, store_linear_idx);
+        if (mode == 0) k_bin_points<0><<<grid, 256, 0, s>>>(fr, d_idx, d_aos, n, d_geom, cl, store_linear_idx, dyn);
+        else           k_bin_points<1><<<grid, 256, 0, s>>>(fr, d_idx, d_aos, n, d_geom, cl, store_linear_idx, dyn);
         note_launch("k_bin_points", s);
     }
     if (mode == 0) k_scan_cells<0><<<fr.count, 1024, 0, s>>>(d_geom, cl);
@@ -285,7 +289,7 @@ void launch_cell_list(int mode, const BatchFrames& fr, const int32_t* d_idx, con
     note_launch("k_scan_cells", s);
     if (n) {
         dim3 grid((n + 255u) / 256u, fr.count);
-        k_scatter_points<<<grid, 256, 0, s>>>(n, cl);
+        k_scatter_points<<<grid, 256, 0, s>>>(n, cl, dyn.n);
         note_launch("k_scatter_points", s);
     }
 }

@@ -57,6 +57,12 @@ struct BatchFrames {
     uint32_t count;
 };
 
+// A selection that changes per frame (within(...) evaluated on the device): frame f of the batch uses idx + f * stride, n[f] entries.
+// n == nullptr: not dynamic, the caller's static list applies.
+struct DynSel { const int32_t* idx; const uint32_t* n; uint32_t stride; };
+MDG_HD const int32_t* sel_list(const int32_t* stat, const DynSel& d, int f) { return d.n ? d.idx + (size_t)f * d.stride : stat; }
+MDG_HD uint32_t sel_count(uint32_t stat, const DynSel& d, int f) { return d.n ? d.n[f] : stat; }
+
 // launch counter (mdgpu_launch_count)
 void note_launch(const char* name, cudaStream_t s);
 

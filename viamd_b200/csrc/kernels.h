@@ -8,9 +8,9 @@ namespace mdg {
 void host_frame_geom(FrameGeom* g, const mdgpu_unitcell_t* uc, double cell_ext, double cutoff, const float* aabb, uint32_t cap);
 void launch_geom(const mdgpu_unitcell_t* d_cells, const float* d_aabb, FrameGeom* d_geom, double cell_ext, double cutoff, uint32_t cap,
                  int B, int* d_err, cudaStream_t s);
-void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float* d_aabb, cudaStream_t s);
+void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float* d_aabb, cudaStream_t s, DynSel dyn = DynSel{ nullptr, nullptr, 0 });
 void launch_cell_list(int mode, const BatchFrames& fr, const int32_t* d_idx, const float* d_aos, uint32_t n, const FrameGeom* d_geom,
-                      const CellList& cl, int store_linear_idx, cudaStream_t s);
+                      const CellList& cl, int store_linear_idx, cudaStream_t s, DynSel dyn = DynSel{ nullptr, nullptr, 0 });
 
 // rdf.cu
 struct RdfArgs {
@@ -22,6 +22,9 @@ struct RdfArgs {
     const int32_t* excl_idx;
     uint32_t frame0;             // global index of the batch's first frame
     int symmetric;               // reference selection == target selection
+    // contact_count (scalar kernel only): reference points carry their position in the concatenated set list; ref_set maps it to the set, whose
+    // exclusion list is excl_off / excl_idx[set] and whose pair count goes to "bin" set of the frame's row
+    const uint32_t* ref_set; int count_mode;
     // candidate lists (k_rdf_cull -> k_rdf_pairs_v2): per frame `list_stride` entries (target position | image code << 26), per home cell a
     // header {first entry, entries of class 0, 1, 2}; one cursor per frame (zeroed by the launcher); err receives MDGPU_ERR_CAPACITY on overflow
     uint32_t* pair_list; uint4* list_hdr; uint32_t* list_cursor; size_t list_stride; size_t hdr_stride; int* err;
@@ -38,6 +41,7 @@ struct RdfArgs {
 void launch_group_com(const BatchFrames& fr, const int32_t* d_idx, const uint32_t* d_off, uint32_t n_groups, const float* d_mass, float* d_out, cudaStream_t s);
 void launch_rdf(const RdfArgs& a, int B, bool tri, int variant, int sm_count, cudaStream_t s, cudaEvent_t* ev4 /* null, or events recorded {before cull, after cull, before pairs, after pairs} */);
 
+void launch_contact_rows(const uint32_t* d_frame_bins, uint32_t n_sets, float* d_out, uint32_t frame0, int B, cudaStream_t s);   // running totals over the sets -> temporal row
 unsigned long long run_sqrt_sweep(uint32_t lo_bits, uint32_t hi_bits);
 
 // sdf.cu
@@ -101,14 +105,14 @@ struct WithinArgs {
     uint32_t frame0;
 };
 void launch_within_count(const WithinArgs& a, int B, bool tri, int sm_count, cudaStream_t s);
-// the same marks as a per-frame ascending index list (dyn_idx [B][num_atoms], dyn_n [B]) and the home-grid cell list built from it
+// the same marks as a per-frame ascending index list (dyn_idx [B][num_atoms], dyn_n [B]); consumers take it as a DynSel
 void launch_within_list(const WithinArgs& a, int B, bool tri, int sm_count, int32_t* d_dyn_idx, uint32_t* d_dyn_n, cudaStream_t s);
-void launch_cell_list_dyn(const BatchFrames& fr, const int32_t* d_dyn_idx, const uint32_t* d_dyn_n, uint32_t max_n, const FrameGeom* d_geom, const CellList& cl, cudaStream_t s);
 void launch_scan_home_cells(const FrameGeom* d_geom, const CellList& cl, int B, cudaStream_t s);   // cells.cu: k_scan_cells<1> alone
 
 // props.cu
 struct DensityArgs {
     BatchFrames frames; const int32_t* idx; uint32_t n; const float* mass; int axis;
+    DynSel dyn;                            // density of a dynamic selection: per-frame list instead of idx / n
     float rc, re, inv_ext, min_point;      // reference point / extent / 1/extent / lower bound along the axis (initial cell)
     unsigned long long* acc;               // [1024] fixed-point mass sums (2^-24 Da)
     unsigned long long* frame_bins;        // [B][1024] scratch, zeroed by launcher
@@ -124,10 +128,11 @@ struct TemporalArgs {
     const int32_t* ctx_idx[4]; uint32_t n_ctx;   // `expr in contexts`: per-context atom of each argument (k_temporal_ctx), out is [num_frames][n_ctx]
 };
 void launch_temporal_ctx(const TemporalArgs& a, int B, cudaStream_t s);
-void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s);
+void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s, DynSel dyn = DynSel{ nullptr, nullptr, 0 });
 void launch_temporal(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_com_rows(const TemporalArgs& a, int B, cudaStream_t s);   // com(x): row (frame0 + f) of a [num_frames][3] temporal = position of argument 0
-void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s);
+void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s,
+                         DynSel da = DynSel{ nullptr, nullptr, 0 }, DynSel db = DynSel{ nullptr, nullptr, 0 });
 void launch_distance_pair(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb,
                           const float* d_posa, const float* d_posb, float* d_out, uint32_t frame0, cudaStream_t s);   // d_pos*: [B][n][3] group centres or null (atoms)
 void launch_coord_rows(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, int axis, float* d_out, uint32_t frame0, cudaStream_t s);   // coord_x/_y/_z

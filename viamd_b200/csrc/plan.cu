@@ -57,7 +57,11 @@ struct Prop {
     float cutoff_min = 0.f, cutoff_max = 0.f;
     std::vector<uint32_t> h_goff[2]; uint32_t* d_goff[2] = { nullptr, nullptr };   // distance_pair: CSR groups of argument 0 / 1 (arrays of selections)
     uint8_t* d_and_mask = nullptr;   // `selection and within(...)`: one byte per atom of the static side (count(within()) / rdf(within()))
-    float ref_within = 0.f, ref_within_min = 0.f;   // rdf: ref_within > 0 -> the reference atoms are within([min:]ref_within, idx[0]), evaluated per frame
+    float ref_within = 0.f, ref_within_min = 0.f;   // (kept for messages) rdf reference given through the round-1 fields; folded into dyn[0]
+    // Dynamic arguments: argument k is within([rmin:]rmax, h_idx[k]) [and a static selection], evaluated per frame on the device into an ascending
+    // index list (md_script_functions.inl:2485-2720); the consumers read that list instead of the static one.
+    struct DynArg { bool on = false; float rmin = 0.f, rmax = 0.f; uint8_t* d_and_mask = nullptr; } dyn[4];
+    bool any_dyn() const { return dyn[0].on || dyn[1].on || dyn[2].on || dyn[3].on; }
     // device accumulators
     unsigned long long* d_acc = nullptr;          // rdf: 1024 bins; density: 1024 fixed-point sums
     uint32_t* d_vol = nullptr;                    // sdf: 128^3
@@ -80,7 +84,8 @@ struct Prop {
     uint64_t frames_accumulated = 0;    // may be overridden after a cross-GPU reduction
     bool frames_overridden = false;
     bool is_dist() const { return op == MDGPU_OP_RDF || (op >= MDGPU_OP_DENSITY_X && op <= MDGPU_OP_DENSITY_Z); }
-    bool needs_cells() const { return op == MDGPU_OP_RDF || op == MDGPU_OP_SDF; }
+    bool needs_cells() const { return op == MDGPU_OP_RDF || op == MDGPU_OP_SDF || op == MDGPU_OP_CONTACT_COUNT; }
+    uint32_t* d_set_of = nullptr;   // contact_count: set of every atom of the concatenated A list
     int share_trg = -1;   // index of an earlier property with the same target selection and cutoff: its target cell list is reused
 };
 
@@ -93,8 +98,8 @@ struct PropScratch {   // per (stream slot, property)
     float* d_argpos = nullptr;   // distance/angle/dihedral with selection arguments: [B][4][3]
     float* d_gpos[2] = { nullptr, nullptr };   // distance_pair with arrays of selections: [B][n_groups][3] per argument
     uint8_t* d_flags = nullptr;  // count(within()) / rdf(within(), ...): [B][num_atoms]
-    // rdf whose reference set is within(radius, selection): the system-wide grid + lists of the within() query, and the per-frame reference list
-    FrameGeom* d_wgeom = nullptr; float* d_waabb = nullptr; CellList wtrg{}, wref{}; int32_t* d_dyn_idx = nullptr; uint32_t* d_dyn_n = nullptr;
+    // per dynamic argument: the system-wide grid + lists of its within() query (get_spatial_acc :734), the marks and the per-frame index list
+    struct DynScratch { FrameGeom* d_geom = nullptr; float* d_aabb = nullptr; CellList trg{}, ref{}; uint8_t* d_flags = nullptr; int32_t* d_idx = nullptr; uint32_t* d_n = nullptr; } dynw[4];
     // rdf candidate lists (k_rdf_cull): [B][list_stride] entries, [B][cap] headers, [B] cursors
     uint32_t* d_pair_list = nullptr; uint4* d_list_hdr = nullptr; uint32_t* d_list_cursor = nullptr; size_t list_stride = 0;
     mdgpu_unitcell_t nn_cell{}; size_t nn_of_cell = 0; bool nn_valid = false;   // neighbour-offset count of the last cell seen (list sizing)
@@ -292,7 +297,7 @@ static void destroy_plan(mdgpu_plan* p) {
     for (auto& s : p->slots) {
         for (auto& ps : s.ps) {
             cudaFree(ps.d_geom); cudaFree(ps.d_aabb); free_cell_list(ps.trg); free_cell_list(ps.ref);
-            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_gpos[0]); cudaFree(ps.d_gpos[1]); cudaFree(ps.d_flags); cudaFree(ps.d_wgeom); cudaFree(ps.d_waabb); free_cell_list(ps.wtrg); free_cell_list(ps.wref); cudaFree(ps.d_dyn_idx); cudaFree(ps.d_dyn_n); cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
+            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_gpos[0]); cudaFree(ps.d_gpos[1]); cudaFree(ps.d_flags); for (auto& w : ps.dynw) { cudaFree(w.d_geom); cudaFree(w.d_aabb); free_cell_list(w.trg); free_cell_list(w.ref); cudaFree(w.d_flags); cudaFree(w.d_idx); cudaFree(w.d_n); } cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
         }
         cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames); cudaFree(s.d_xtc_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
@@ -313,7 +318,7 @@ static void destroy_plan(mdgpu_plan* p) {
         if (pr.values_registered) cudaHostUnregister(pr.values.data());
         cudaFree(pr.d_vol_mean);
         cudaFree(pr.d_acc); cudaFree(pr.d_vol); cudaFree(pr.d_frame_total); cudaFree(pr.d_frame_min); cudaFree(pr.d_frame_max);
-        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap); cudaFree(pr.d_soff); cudaFree(pr.d_and_mask); cudaFree(pr.d_goff[0]); cudaFree(pr.d_goff[1]);
+        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap); cudaFree(pr.d_soff); cudaFree(pr.d_and_mask); cudaFree(pr.d_goff[0]); cudaFree(pr.d_goff[1]); cudaFree(pr.d_set_of); for (auto& dy : pr.dyn) cudaFree(dy.d_and_mask);
     }
     for (auto& t : p->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (p->t_begin) cudaEventDestroy(p->t_begin);
@@ -389,18 +394,38 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
                 if (upload(&pr.d_idx[k], pr.h_idx[k].data(), pr.h_idx[k].size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (indices)");
             }
         }
-        if ((pr.op == MDGPU_OP_WITHIN_COUNT || (pr.op == MDGPU_OP_RDF && d.ref_within_radius > 0.0f)) && (d.com_args & 1u)) {   // idx[2] = static side of `sel and within(...)`
+        {   // dynamic arguments (dyn[k]); rdf's round-1 spelling ref_within_radius + com_args bit 0 + idx[2] becomes dyn[0]
+            mdgpu_dynamic_arg_t da[4]; for (int k = 0; k < 4; ++k) da[k] = d.dyn[k];
+            if (pr.op == MDGPU_OP_RDF && d.ref_within_radius > 0.0f && !(da[0].radius_max > 0.0f)) {
+                da[0].radius_min = d.ref_within_min; da[0].radius_max = d.ref_within_radius; da[0].has_and = d.com_args & 1u;
+                da[0].and_idx = d.idx[2]; da[0].and_count = d.idx_count[2];
+            }
+            for (int k = 0; k < 4; ++k) if (da[k].radius_max > 0.0f && pr.op != MDGPU_OP_WITHIN_COUNT) {
+                const bool ok_op = (pr.op == MDGPU_OP_RDF && k < 2) || (pr.op == MDGPU_OP_SDF && k == 1) || (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z && k == 0) ||
+                                   ((pr.op == MDGPU_OP_DISTANCE || pr.op == MDGPU_OP_ANGLE || pr.op == MDGPU_OP_DIHEDRAL) && !d.num_structures) || (pr.op == MDGPU_OP_COM && k == 0) ||
+                                   ((pr.op == MDGPU_OP_DISTANCE_MIN || pr.op == MDGPU_OP_DISTANCE_MAX) && k < 2);
+                if (!ok_op) return bail(MDGPU_ERR_UNSUPPORTED, "property '" + pr.name + "': a dynamic selection is not lowered as argument " + std::to_string(k) + " of this procedure");
+                if (da[k].radius_min < 0.0f || da[k].radius_max < da[k].radius_min) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': The supplied radius range is invalid");   // :2654
+                pr.dyn[k].on = true; pr.dyn[k].rmin = da[k].radius_min; pr.dyn[k].rmax = da[k].radius_max;
+                if (da[k].has_and) {
+                    std::vector<uint8_t> m(sys->num_atoms, 0);
+                    for (size_t j = 0; j < da[k].and_count; ++j) { const int32_t a = da[k].and_idx[j]; if (a < 0 || (size_t)a >= sys->num_atoms) return bail(MDGPU_ERR_INVALID_ARG, "property '" + pr.name + "': atom index out of range"); m[(size_t)a] = 1; }
+                    if (upload(&pr.dyn[k].d_and_mask, m.data(), m.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (selection mask)");
+                }
+            }
+        }
+        if (pr.op == MDGPU_OP_WITHIN_COUNT && (d.com_args & 1u)) {   // idx[2] = static side of `sel and within(...)`
             std::vector<uint8_t> m(sys->num_atoms, 0); for (int32_t a : pr.h_idx[2]) m[(size_t)a] = 1;
             if (upload(&pr.d_and_mask, m.data(), m.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (selection mask)");
         }
         cudaError_t e = cudaSuccess;
         switch (pr.op) {
         case MDGPU_OP_RDF:
-            if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty reference positions");   // internal_rdf :5396-5403
-            if (pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty target positions");
+            if (pr.h_idx[0].empty() && !pr.dyn[0].on) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty reference positions");   // internal_rdf :5396-5403
+            if (pr.h_idx[1].empty() && !pr.dyn[1].on) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': empty target positions");
             if (pr.cutoff_min < 0.0f || pr.cutoff_max <= pr.cutoff_min) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': Invalid cutoff");
-            pr.ref_within = d.ref_within_radius; pr.ref_within_min = d.ref_within_min;
-            if (pr.ref_within < 0.0f || (pr.ref_within > 0.0f && pr.n_struct) || pr.ref_within_min < 0.0f || (pr.ref_within > 0.0f && pr.ref_within < pr.ref_within_min)) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': invalid within() reference");
+            pr.ref_within = pr.dyn[0].on ? pr.dyn[0].rmax : 0.0f; pr.ref_within_min = pr.dyn[0].rmin;
+            if (d.ref_within_radius < 0.0f || (pr.dyn[0].on && pr.n_struct) || d.ref_within_min < 0.0f) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': invalid within() reference");
             if (pr.n_struct) {   // references = centres of mass of atom groups, a group's own atoms excluded (compute_rdf :5274-5275)
                 if (d.structure_offsets) pr.h_soff.assign(d.structure_offsets, d.structure_offsets + pr.n_struct + 1);
                 else { if (!pr.struct_size) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': structure_size or structure_offsets required");
@@ -420,7 +445,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
         case MDGPU_OP_SDF: {
             if (!pr.n_struct || !pr.struct_size || pr.h_idx[0].size() != pr.n_struct * pr.struct_size)
                 return bail(MDGPU_ERR_INVALID_ARG, "sdf '" + pr.name + "': reference structures must be num_structures x structure_size atoms");
-            if (pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "sdf '" + pr.name + "': The supplied target bitfield is empty");
+            if (pr.h_idx[1].empty() && !pr.dyn[1].on) return bail(MDGPU_ERR_INVALID_ARG, "sdf '" + pr.name + "': The supplied target bitfield is empty");
             if (p->conn_off.empty()) return bail(MDGPU_ERR_INVALID_ARG, "sdf '" + pr.name + "': Missing bond connectivity");   // md_util.c:8746
             std::vector<int2> pairs; build_unwrap_pairs(pairs, pr.struct_size, p->conn_off, p->conn_idx);
             pr.n_unwrap = (uint32_t)pairs.size();
@@ -433,7 +458,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.data.dim[0] = 1; pr.data.dim[1] = MDGPU_VOL_DIM; pr.data.dim[2] = MDGPU_VOL_DIM; pr.data.dim[3] = MDGPU_VOL_DIM;
             break; }
         case MDGPU_OP_DENSITY_X: case MDGPU_OP_DENSITY_Y: case MDGPU_OP_DENSITY_Z:
-            if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "density '" + pr.name + "': empty selection");
+            if (pr.h_idx[0].empty() && !pr.dyn[0].on) return bail(MDGPU_ERR_INVALID_ARG, "density '" + pr.name + "': empty selection");
             e = dalloc(&pr.d_acc, MDGPU_DIST_BINS);
             if (e == cudaSuccess) e = dalloc(&pr.d_frame_min64, num_frames);
             if (e == cudaSuccess) e = dalloc(&pr.d_frame_max64, num_frames);
@@ -442,7 +467,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.data.dim[0] = 1; pr.data.dim[1] = 2; pr.data.dim[2] = MDGPU_DIST_BINS; pr.data.dim[3] = 0;
             break;
         case MDGPU_OP_DISTANCE_MIN: case MDGPU_OP_DISTANCE_MAX:
-            if (pr.h_idx[0].empty() || pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
+            if ((pr.h_idx[0].empty() && !pr.dyn[0].on) || (pr.h_idx[1].empty() && !pr.dyn[1].on)) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
             e = dalloc(&pr.d_temporal, num_frames);
             pr.values.assign(num_frames, 0.0f);
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
@@ -461,6 +486,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             }
             pr.com_mask = d.com_args & ((1u << need) - 1u);
             for (int k = 0; k < need; ++k) {
+                if (pr.dyn[k].on) { pr.com_mask |= 1u << k; continue; }   // a dynamic selection is a bitfield: its centre of mass
                 if (pr.h_idx[k].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
                 if (pr.h_idx[k].size() != 1) pr.com_mask |= 1u << k;   // several indices: centre of mass (coordinate_extract_com :1759)
             }
@@ -518,8 +544,8 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = (int32_t)pr.len; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
             break;
         case MDGPU_OP_COM: {   // com(x): a [F, 3] temporal (TI_FLOAT3)
-            if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
-            pr.com_mask = (d.com_args & 1u) | (pr.h_idx[0].size() != 1 ? 1u : 0u);
+            if (pr.h_idx[0].empty() && !pr.dyn[0].on) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
+            pr.com_mask = (d.com_args & 1u) | (pr.h_idx[0].size() != 1 ? 1u : 0u) | (pr.dyn[0].on ? 1u : 0u);
             pr.len = 3;
             e = dalloc(&pr.d_temporal, num_frames * pr.len);
             pr.values.assign(num_frames * pr.len, 0.0f);
@@ -536,6 +562,30 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.values.assign(num_frames * pr.len, 0.0f);
             pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f);
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 4; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
+            break; }
+        case MDGPU_OP_CONTACT_COUNT: {   // contact_count(A[], B, cutoff): per set the pairs (a in A_i, b in B) within the cutoff, b outside the set's exclusion list
+            if (!pr.n_struct || pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': no sets");
+            if (pr.n_struct > MDGPU_DIST_BINS) return bail(MDGPU_ERR_UNSUPPORTED, "'" + pr.name + "': more than 1024 sets");
+            if (!(pr.cutoff_max > 0.0f)) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': The cutoff distance must be positive.");   // :2862
+            if (pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty second set");
+            if (d.structure_offsets) pr.h_soff.assign(d.structure_offsets, d.structure_offsets + pr.n_struct + 1);
+            else { if (!pr.struct_size) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': structure_size or structure_offsets required");
+                   pr.h_soff.resize(pr.n_struct + 1); for (size_t k = 0; k <= pr.n_struct; ++k) pr.h_soff[k] = (uint32_t)(k * pr.struct_size); }
+            if (pr.h_soff.front() != 0 || pr.h_soff.back() != pr.h_idx[0].size()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': structure offsets do not cover idx[0]");
+            std::vector<uint32_t> set_of(pr.h_idx[0].size());
+            for (size_t k = 0; k < pr.n_struct; ++k) { if (pr.h_soff[k] > pr.h_soff[k + 1]) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': structure offsets must be non-decreasing"); for (uint32_t j = pr.h_soff[k]; j < pr.h_soff[k + 1]; ++j) set_of[j] = (uint32_t)k; }
+            // exclusion lists (A_i & B grown along the bonds, md_util_mask_grow_by_bonds): CSR in idx[2] / structure_offsets_b, empty when absent
+            pr.h_goff[1].assign(pr.n_struct + 1, 0u);
+            if (d.structure_offsets_b) { if (d.num_structures_b != pr.n_struct || d.structure_offsets_b[0] != 0 || d.structure_offsets_b[pr.n_struct] != pr.h_idx[2].size()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': exclusion offsets do not cover idx[2]");
+                                         pr.h_goff[1].assign(d.structure_offsets_b, d.structure_offsets_b + pr.n_struct + 1); }
+            else if (!pr.h_idx[2].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': exclusion atoms without offsets");
+            e = upload(&pr.d_set_of, set_of.data(), set_of.size());
+            if (e == cudaSuccess) e = upload(&pr.d_goff[1], pr.h_goff[1].data(), pr.h_goff[1].size());
+            pr.len = pr.n_struct;
+            if (e == cudaSuccess) e = dalloc(&pr.d_temporal, num_frames * pr.len);
+            pr.values.assign(num_frames * pr.len, 0.0f);
+            if (pr.len > 1) { pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f); }
+            pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = (int32_t)pr.len; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
             break; }
         case MDGPU_OP_BACKBONE_ANGLES: {   // two `dihedral in context` values per segment: phi = (C', N, CA, C), psi = (N, CA, C, N')
             const size_t ns = pr.n_struct;
@@ -577,13 +627,13 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
     }
     for (size_t i = 0; i < num_props; ++i) for (size_t j = 0; j < i; ++j) {
         Prop& a = p->props[i]; Prop& b = p->props[j];
-        if (a.needs_cells() && b.needs_cells() && b.share_trg < 0 && a.cutoff_max == b.cutoff_max && a.h_idx[1] == b.h_idx[1]) { a.share_trg = (int)j; break; }
+        if (a.needs_cells() && b.needs_cells() && b.share_trg < 0 && a.cutoff_max == b.cutoff_max && a.h_idx[1] == b.h_idx[1] && !a.dyn[1].on && !b.dyn[1].on) { a.share_trg = (int)j; break; }
     }
     {   // compact atom space: what host ingest has to copy
         const size_t N = sys->num_atoms; bool all_atoms = false;
         std::vector<uint8_t> mark(N, 0);
         for (auto& pr : p->props) {
-            if (pr.op == MDGPU_OP_WITHIN_COUNT || pr.ref_within > 0.0f) all_atoms = true;   // within() searches the whole system
+            if (pr.op == MDGPU_OP_WITHIN_COUNT || pr.any_dyn()) all_atoms = true;   // within() searches the whole system
             for (int k = 0; k < 4; ++k) for (int32_t a : pr.h_idx[k]) if (a >= 0) mark[(size_t)a] = 1;
         }
         for (size_t a = 0; a < N; ++a) if (mark[a]) p->needed.push_back((int32_t)a);
@@ -689,10 +739,10 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
             for (auto& pr : p->props) if (pr.needs_cells() || pr.op == MDGPU_OP_WITHIN_COUNT) {
                 FrameGeom g; host_frame_geom(&g, first_cell, pr.op == MDGPU_OP_WITHIN_COUNT ? within_cell_ext(pr.cutoff_max) : (double)pr.cutoff_max, pr.cutoff_max, nullptr, 0xffffffffu);
                 need = std::max<uint64_t>(need, 2ull * std::max<uint64_t>(g.num_cells, g.num_home) + 2);
-                if (pr.ref_within > 0.0f) {
-                    host_frame_geom(&g, first_cell, within_cell_ext(pr.ref_within), pr.ref_within, nullptr, 0xffffffffu);
-                    need = std::max<uint64_t>(need, 2ull * std::max<uint64_t>(g.num_cells, g.num_home) + 2);
-                }
+            }
+            for (auto& pr : p->props) for (auto& dy : pr.dyn) if (dy.on) {
+                FrameGeom g; host_frame_geom(&g, first_cell, within_cell_ext(dy.rmax), dy.rmax, nullptr, 0xffffffffu);
+                need = std::max<uint64_t>(need, 2ull * std::max<uint64_t>(g.num_cells, g.num_home) + 2);
             }
             cap = (uint32_t)std::min<uint64_t>(need, 1u << 26);
             p->cell_cap = cap;
@@ -709,30 +759,35 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
             s.ps.resize(p->props.size());
             for (size_t i = 0; i < p->props.size(); ++i) {
                 Prop& pr = p->props[i]; PropScratch& ps = s.ps[i];
+                for (int k = 0; k < 4; ++k) if (pr.dyn[k].on) {   // the within() query of a dynamic argument: system-wide lists + marks + per-frame index list
+                    auto& w = ps.dynw[k];
+                    CUDA_TRY(dalloc(&w.d_geom, p->B)); CUDA_TRY(dalloc(&w.d_aabb, (size_t)6 * p->B));
+                    int rc = alloc_cell_list(w.trg, p->B, (uint32_t)p->num_atoms, cap); if (rc) return rc;
+                    rc = alloc_cell_list(w.ref, p->B, (uint32_t)std::max<size_t>(pr.h_idx[k].size(), 1), cap); if (rc) return rc;
+                    CUDA_TRY(dalloc(&w.d_flags, (size_t)p->B * p->num_atoms));
+                    CUDA_TRY(dalloc(&w.d_idx, (size_t)p->B * p->num_atoms)); CUDA_TRY(dalloc(&w.d_n, p->B));
+                }
                 if (pr.needs_cells() && pr.share_trg < 0) {
                     CUDA_TRY(dalloc(&ps.d_geom, p->B)); CUDA_TRY(dalloc(&ps.d_aabb, (size_t)6 * p->B));
-                    int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)pr.h_idx[1].size(), cap); if (rc) return rc;
+                    int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)(pr.dyn[1].on ? p->num_atoms : pr.h_idx[1].size()), cap); if (rc) return rc;
                 }
                 if (pr.op == MDGPU_OP_RDF) {
-                    int rc = alloc_cell_list(ps.ref, p->B, (uint32_t)(pr.ref_within > 0.0f ? p->num_atoms : (pr.n_struct ? pr.n_struct : pr.h_idx[0].size())), cap); if (rc) return rc;
-                    if (pr.ref_within > 0.0f) {
-                        CUDA_TRY(dalloc(&ps.d_wgeom, p->B)); CUDA_TRY(dalloc(&ps.d_waabb, (size_t)6 * p->B));
-                        rc = alloc_cell_list(ps.wtrg, p->B, (uint32_t)p->num_atoms, cap); if (rc) return rc;
-                        rc = alloc_cell_list(ps.wref, p->B, (uint32_t)pr.h_idx[0].size(), cap); if (rc) return rc;
-                        CUDA_TRY(dalloc(&ps.d_flags, (size_t)p->B * p->num_atoms));
-                        CUDA_TRY(dalloc(&ps.d_dyn_idx, (size_t)p->B * p->num_atoms)); CUDA_TRY(dalloc(&ps.d_dyn_n, p->B));
-                    }
+                    int rc = alloc_cell_list(ps.ref, p->B, (uint32_t)(pr.dyn[0].on ? p->num_atoms : (pr.n_struct ? pr.n_struct : pr.h_idx[0].size())), cap); if (rc) return rc;
                     if (pr.n_struct) CUDA_TRY(dalloc(&ps.d_com, (size_t)p->B * pr.n_struct * 3));
                     else {   // candidate lists of the packed pair kernel: every target appears in at most (2n+1)^3 home cells' lists
                         FrameGeom g; host_frame_geom(&g, first_cell, pr.cutoff_max, pr.cutoff_max, nullptr, 0xffffffffu);
                         size_t nn = (size_t)(2 * std::max(g.ncell[0], 1) + 1) * (2 * std::max(g.ncell[1], 1) + 1) * (2 * std::max(g.ncell[2], 1) + 1);
                         if (g.valid <= 0 || (first_cell->flags & MDGPU_CELL_PBC_ALL) != MDGPU_CELL_PBC_ALL) nn = 125;   // grid from the data (AABB fit): size for the widest reach the reference allows
-                        ps.list_stride = std::min<size_t>(nn, 125) * pr.h_idx[1].size() + 1024;
+                        // a dynamic target set is sized for a quarter of the system; frames that select more are finished by the overflow pass
+                        ps.list_stride = std::min<size_t>(nn, 125) * (pr.dyn[1].on ? std::max<size_t>(p->num_atoms / 4, 1024) : pr.h_idx[1].size()) + 1024;
                         CUDA_TRY(dalloc(&ps.d_pair_list, (size_t)p->B * ps.list_stride));
                         CUDA_TRY(dalloc(&ps.d_list_hdr, (size_t)p->B * cap));
                         CUDA_TRY(dalloc(&ps.d_list_cursor, p->B));
                     }
                     CUDA_TRY(dalloc(&ps.d_frame_bins, (size_t)p->B * (MDGPU_DIST_BINS + 1)));   // + one work counter per frame (k_rdf_pairs_v2)
+                } else if (pr.op == MDGPU_OP_CONTACT_COUNT) {
+                    int rc = alloc_cell_list(ps.ref, p->B, (uint32_t)pr.h_idx[0].size(), cap); if (rc) return rc;
+                    CUDA_TRY(dalloc(&ps.d_frame_bins, (size_t)p->B * (MDGPU_DIST_BINS + 1)));
                 } else if (pr.op == MDGPU_OP_SDF) {
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * (pr.n_struct + 1) * pr.struct_size));
                     CUDA_TRY(dalloc(&ps.d_sdf_ref0, (size_t)p->B * 20));
@@ -781,25 +836,32 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
         int32_t* const* didx = c ? pr.d_idx_c : pr.d_idx;
         const float* dmass = c ? p->d_mass_c : p->d_mass; const float* dinit = c ? p->d_init_c : p->d_init; const size_t init_as = c ? p->axis_stride_c : p->axis_stride;
         const PropScratch& cs = (pr.share_trg >= 0) ? s.ps[pr.share_trg] : ps;   // owner of the target cell list + geometry
+        DynSel dsel[4];
+        for (int k = 0; k < 4; ++k) {   // dynamic arguments first: within([min:]max, idx[k]) [and mask] of every frame of the batch -> ascending per-frame lists
+            dsel[k] = DynSel{ nullptr, nullptr, 0 };
+            if (!pr.dyn[k].on) continue;
+            auto& w = ps.dynw[k];
+            const float* waabb = nullptr;
+            if (!all_pbc) { launch_aabb(fr, nullptr, (uint32_t)p->num_atoms, w.d_aabb, s.stream); waabb = w.d_aabb; }   // every atom of the system (get_spatial_acc :734)
+            launch_geom(s.d_cells, waabb, w.d_geom, within_cell_ext(pr.dyn[k].rmax), (double)pr.dyn[k].rmax, p->cell_cap, B, s.d_err, s.stream);
+            launch_cell_list(0, fr, nullptr, nullptr, (uint32_t)p->num_atoms, w.d_geom, w.trg, 0, s.stream);
+            launch_cell_list(1, fr, didx[k], nullptr, (uint32_t)pr.h_idx[k].size(), w.d_geom, w.ref, 0, s.stream);
+            WithinArgs wa{};
+            wa.geom = w.d_geom; wa.trg = w.trg; wa.ref = w.ref; wa.sel = didx[k]; wa.n_sel = (uint32_t)pr.h_idx[k].size();
+            wa.num_atoms = (uint32_t)p->num_atoms; wa.flags = w.d_flags; wa.out = nullptr; wa.frame0 = frame0; wa.min_r2 = pr.dyn[k].rmin * pr.dyn[k].rmin; wa.and_mask = pr.dyn[k].d_and_mask;
+            launch_within_list(wa, B, tri, p->sm_count, w.d_idx, w.d_n, s.stream);
+            dsel[k] = DynSel{ w.d_idx, w.d_n, (uint32_t)p->num_atoms };
+        }
         if (pr.needs_cells() && pr.share_trg < 0) {
             const float* aabb = nullptr;
-            if (!all_pbc) { launch_aabb(fr, didx[1], (uint32_t)pr.h_idx[1].size(), ps.d_aabb, s.stream); aabb = ps.d_aabb; }
+            if (!all_pbc) { launch_aabb(fr, didx[1], (uint32_t)pr.h_idx[1].size(), ps.d_aabb, s.stream, dsel[1]); aabb = ps.d_aabb; }
             launch_geom(s.d_cells, aabb, ps.d_geom, (double)pr.cutoff_max, (double)pr.cutoff_max, p->cell_cap, B, s.d_err, s.stream);
-            launch_cell_list(0, fr, didx[1], nullptr, (uint32_t)pr.h_idx[1].size(), ps.d_geom, ps.trg, 0, s.stream);
+            launch_cell_list(0, fr, didx[1], nullptr, (uint32_t)pr.h_idx[1].size(), ps.d_geom, ps.trg, 0, s.stream, dsel[1]);
         }
         switch (pr.op) {
         case MDGPU_OP_RDF: {
-            if (pr.ref_within > 0.0f) {   // references = within(radius, idx[0]) of this frame (_within_expl_flt :2485), then compute_rdf as usual
-                const float* waabb = nullptr;
-                if (!all_pbc) { launch_aabb(fr, nullptr, (uint32_t)p->num_atoms, ps.d_waabb, s.stream); waabb = ps.d_waabb; }
-                launch_geom(s.d_cells, waabb, ps.d_wgeom, within_cell_ext(pr.ref_within), (double)pr.ref_within, p->cell_cap, B, s.d_err, s.stream);
-                launch_cell_list(0, fr, nullptr, nullptr, (uint32_t)p->num_atoms, ps.d_wgeom, ps.wtrg, 0, s.stream);
-                launch_cell_list(1, fr, didx[0], nullptr, (uint32_t)pr.h_idx[0].size(), ps.d_wgeom, ps.wref, 0, s.stream);
-                WithinArgs w{};
-                w.geom = ps.d_wgeom; w.trg = ps.wtrg; w.ref = ps.wref; w.sel = didx[0]; w.n_sel = (uint32_t)pr.h_idx[0].size();
-                w.num_atoms = (uint32_t)p->num_atoms; w.flags = ps.d_flags; w.out = nullptr; w.frame0 = frame0; w.min_r2 = pr.ref_within_min * pr.ref_within_min; w.and_mask = pr.d_and_mask;
-                launch_within_list(w, B, tri, p->sm_count, ps.d_dyn_idx, ps.d_dyn_n, s.stream);
-                launch_cell_list_dyn(fr, ps.d_dyn_idx, ps.d_dyn_n, (uint32_t)p->num_atoms, cs.d_geom, ps.ref, s.stream);
+            if (pr.dyn[0].on) {   // references = the frame's dynamic selection (coordinate_extract on a single bitfield: ascending atoms; compute_rdf :5281-5290)
+                launch_cell_list(1, fr, nullptr, nullptr, 0, cs.d_geom, ps.ref, 0, s.stream, dsel[0]);
             } else if (pr.n_struct) {
                 launch_group_com(fr, didx[0], pr.d_soff, (uint32_t)pr.n_struct, dmass, ps.d_com, s.stream);
                 launch_cell_list(1, fr, nullptr, ps.d_com, (uint32_t)pr.n_struct, cs.d_geom, ps.ref, 0, s.stream);   // AoS stream: i = position index (:1721)
@@ -817,7 +879,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
                     }
                     nn_max = std::max(nn_max, ps.nn_of_cell);
                 }
-                const size_t need = nn_max * pr.h_idx[1].size() + 1024;
+                const size_t need = nn_max * (pr.dyn[1].on ? std::max<size_t>(p->num_atoms / 4, 1024) : pr.h_idx[1].size()) + 1024;
                 if (need > ps.list_stride) {   // the slot was retired before this batch: its buffers are idle
                     CUDA_TRY(cudaStreamSynchronize(s.stream));
                     cudaFree(ps.d_pair_list); ps.d_pair_list = nullptr; ps.list_stride = need;
@@ -832,13 +894,23 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.frame_bins = ps.d_frame_bins; a.frame0 = frame0;
             a.pair_list = ps.d_pair_list; a.list_hdr = ps.d_list_hdr; a.list_cursor = ps.d_list_cursor; a.list_stride = ps.list_stride; a.hdr_stride = p->cell_cap; a.err = s.d_err;
             a.excl_off = pr.n_struct ? pr.d_soff : nullptr; a.excl_idx = pr.n_struct ? didx[0] : nullptr;   // md_bitfield_test_bit(&masks[i], j) :5252
-            a.symmetric = (!pr.n_struct && pr.ref_within == 0.0f && pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
+            a.symmetric = (!pr.n_struct && !pr.dyn[0].on && !pr.dyn[1].on && pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
             a.acc = pr.d_acc; a.frame_total = pr.d_frame_total; a.frame_min = pr.d_frame_min; a.frame_max = pr.d_frame_max; a.keep = pr.d_keep;
             a.counters = p->timing ? p->d_counters : nullptr;
             cudaEvent_t ev4[4] = { nullptr, nullptr, nullptr, nullptr };   // before cull, after cull, before pairs, after pairs
             if (p->timing) for (auto& e : ev4) cudaEventCreate(&e);
             launch_rdf(a, B, tri, (int)p->rdf_variant, p->sm_count, s.stream, p->timing ? ev4 : nullptr);
             if (p->timing) { p->timed.push_back(TimedLaunch{ ev4[0], ev4[1], 3 }); p->timed.push_back(TimedLaunch{ ev4[2], ev4[3], 0 }); }
+            break; }
+        case MDGPU_OP_CONTACT_COUNT: {   // external points = the atoms of all sets (tag: position in the list), internal = B (md_script_functions.inl:2808-2846)
+            launch_cell_list(1, fr, didx[0], nullptr, (uint32_t)pr.h_idx[0].size(), cs.d_geom, ps.ref, 1, s.stream);
+            RdfArgs a{};
+            a.geom = cs.d_geom; a.trg = cs.trg; a.ref = ps.ref;
+            a.inv_cutoff_range = 1.0f; a.min_cutoff = 0.0f; a.min_r2 = 0.0f;
+            a.frame_bins = ps.d_frame_bins; a.frame0 = frame0; a.err = s.d_err;
+            a.excl_off = pr.d_goff[1]; a.excl_idx = didx[2]; a.ref_set = pr.d_set_of; a.count_mode = 1;
+            launch_rdf(a, B, tri, 1, p->sm_count, s.stream, nullptr);
+            launch_contact_rows(ps.d_frame_bins, (uint32_t)pr.n_struct, pr.d_temporal, frame0, B, s.stream);
             break; }
         case MDGPU_OP_SDF: {
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "sdf '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
@@ -857,7 +929,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
         case MDGPU_OP_DENSITY_X: case MDGPU_OP_DENSITY_Y: case MDGPU_OP_DENSITY_Z: {
             if (!p->have_init) return fail(MDGPU_ERR_INVALID_ARG, "density '%s' needs the initial frame (mdgpu_plan_set_initial_frame)", pr.name.c_str());
             DensityArgs a{};
-            a.frames = fr; a.idx = didx[0]; a.n = (uint32_t)pr.h_idx[0].size(); a.mass = dmass; a.axis = (int)pr.op - MDGPU_OP_DENSITY_X;
+            a.frames = fr; a.idx = didx[0]; a.n = (uint32_t)pr.h_idx[0].size(); a.mass = dmass; a.axis = (int)pr.op - MDGPU_OP_DENSITY_X; a.dyn = dsel[0];
             a.rc = pr.rc; a.re = pr.re; a.inv_ext = pr.inv_ext; a.min_point = pr.min_point;
             a.acc = pr.d_acc; a.frame_bins = ps.d_frame_bins64; a.frame_min = pr.d_frame_min64; a.frame_max = pr.d_frame_max64; a.keep = pr.d_keep64; a.frame0 = frame0;
             TimedLaunch tl{};
@@ -880,7 +952,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             TemporalArgs a{};
             a.frames = fr; a.cells = s.d_cells; a.op = (int)pr.op; a.out = pr.d_temporal; a.frame0 = frame0;
             a.atom[0] = c ? pr.first_c[0] : pr.h_idx[0][0]; a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
-            if (pr.com_mask & 1u) launch_arg_com(fr, s.d_cells, didx[0], (uint32_t)pr.h_idx[0].size(), dmass, ps.d_argpos, 0, s.stream);
+            if (pr.com_mask & 1u) launch_arg_com(fr, s.d_cells, didx[0], (uint32_t)pr.h_idx[0].size(), dmass, ps.d_argpos, 0, s.stream, dsel[0]);
             launch_com_rows(a, B, s.stream);
             break; }
         case MDGPU_OP_COORD_X: case MDGPU_OP_COORD_Y: case MDGPU_OP_COORD_Z:
@@ -916,7 +988,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             launch_rmsd(a, B, s.stream);
             break; }
         case MDGPU_OP_DISTANCE_MIN: case MDGPU_OP_DISTANCE_MAX:   // both evaluate md_util_min_distance (md_script_functions.inl:3904, 3944)
-            launch_min_distance(fr, s.d_cells, didx[0], (uint32_t)pr.h_idx[0].size(), didx[1], (uint32_t)pr.h_idx[1].size(), pr.d_temporal, frame0, s.stream);
+            launch_min_distance(fr, s.d_cells, didx[0], (uint32_t)pr.h_idx[0].size(), didx[1], (uint32_t)pr.h_idx[1].size(), pr.d_temporal, frame0, s.stream, dsel[0], dsel[1]);
             break;
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
             TemporalArgs a{};
@@ -930,7 +1002,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             for (int k = 0; k < 4; ++k) a.atom[k] = pr.h_idx[k].empty() ? 0 : (c ? pr.first_c[k] : pr.h_idx[k][0]);
             a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
             for (int k = 0; k < 4; ++k) if (pr.com_mask & (1u << k))
-                launch_arg_com(fr, s.d_cells, didx[k], (uint32_t)pr.h_idx[k].size(), dmass, ps.d_argpos, k, s.stream);
+                launch_arg_com(fr, s.d_cells, didx[k], (uint32_t)pr.h_idx[k].size(), dmass, ps.d_argpos, k, s.stream, dsel[k]);
             launch_temporal(a, B, s.stream);
             break; }
         default: break;

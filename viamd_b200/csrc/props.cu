@@ -27,8 +27,9 @@ __global__ void __launch_bounds__(256) k_density(DensityArgs a) {
     for (int b = threadIdx.x; b < MDGPU_DIST_BINS; b += blockDim.x) { hist_lo[b] = 0u; hist_hi[b] = 0u; }
     __syncthreads();
     const float* src = a.frames.xyz + (size_t)f * a.frames.frame_stride + (size_t)a.axis * a.frames.axis_stride;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
-        const int at = a.idx[i];
+    const int32_t* __restrict__ idx = sel_list(a.idx, a.dyn, f); const uint32_t n = sel_count(a.n, a.dyn, f);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int at = idx[i];
         const float v = deperiodize1p(src[at], a.rc, a.re);
         const float fc = __fmul_rn(__fsub_rn(v, a.min_point), a.inv_ext);
         const int b = max(0, min(__float2int_rz(__fmul_rn(fc, (float)MDGPU_DIST_BINS)), MDGPU_DIST_BINS - 1));
@@ -74,8 +75,9 @@ __global__ void k_density_finalize(DensityArgs a) {
 
 void launch_density(const DensityArgs& a, int B, cudaStream_t s) {
     cudaMemsetAsync(a.frame_bins, 0, sizeof(unsigned long long) * (size_t)B * MDGPU_DIST_BINS, s);
-    if (a.n) {
-        const uint32_t blocks = min((a.n + 256u * 8u - 1u) / (256u * 8u), 64u);   // ~8 atoms per thread, <=64 CTAs per frame
+    const uint32_t nmax = a.dyn.n ? a.dyn.stride : a.n;
+    if (nmax) {
+        const uint32_t blocks = min((nmax + 256u * 8u - 1u) / (256u * 8u), 64u);   // ~8 atoms per thread, <=64 CTAs per frame
         dim3 grid(blocks ? blocks : 1u, B);
         k_density<<<grid, 256, 0, s>>>(a);
         note_launch("k_density", s);
@@ -244,17 +246,19 @@ MDG_D void periodic_com_warp(const float* const src[3], const mdgpu_unitcell_t& 
     }
 }
 
-__global__ void k_arg_com(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ idx, uint32_t count,
-                          const float* __restrict__ mass, float* __restrict__ out /* [B][4][3] */, int arg) {
+__global__ void k_arg_com(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ idx_, uint32_t count_,
+                          const float* __restrict__ mass, float* __restrict__ out /* [B][4][3] */, int arg, DynSel dyn) {
     const int f = blockIdx.x, lane = threadIdx.x;
+    const int32_t* __restrict__ idx = sel_list(idx_, dyn, f); const uint32_t count = sel_count(count_, dyn, f);
+    if (count == 0) { if (lane < 3) out[((size_t)f * 4 + arg) * 3 + lane] = 0.0f; return; }   // md_util_com_compute: count == 0 -> (0, 0, 0) (md_util.c:8168)
     const float* x = fr.xyz + (size_t)f * fr.frame_stride;
     const float* src[3] = { x, x + fr.axis_stride, x + 2 * fr.axis_stride };
     periodic_com_warp(src, cells[f], idx, count, mass, out + ((size_t)f * 4 + arg) * 3, lane);
 }
 
-void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s) {
+void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s, DynSel dyn) {
     if (!fr.count || !count) return;
-    k_arg_com<<<fr.count, 32, 0, s>>>(fr, d_cells, d_idx, count, d_mass, d_out, arg);
+    k_arg_com<<<fr.count, 32, 0, s>>>(fr, d_cells, d_idx, count, d_mass, d_out, arg, dyn);
     note_launch("k_arg_com", s);
 }
 
@@ -394,9 +398,11 @@ MDG_D float pair_distance(float ax, float ay, float az, float bx, float by, floa
 
 // distance_min / distance_max (both md_util_min_distance, md_util.c:8242-8297): all pairs of two selections, one CTA per frame.
 // The minimum of floats is order independent, so the pairs are spread over the threads and reduced.
-__global__ void __launch_bounds__(256) k_min_distance(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ ia, uint32_t na,
-                                                      const int32_t* __restrict__ ib, uint32_t nb, float* __restrict__ out, uint32_t frame0) {
+__global__ void __launch_bounds__(256) k_min_distance(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ ia_, uint32_t na_,
+                                                      const int32_t* __restrict__ ib_, uint32_t nb_, float* __restrict__ out, uint32_t frame0, DynSel da, DynSel db) {
     const int f = blockIdx.x;
+    const int32_t* __restrict__ ia = sel_list(ia_, da, f); const uint32_t na = sel_count(na_, da, f);
+    const int32_t* __restrict__ ib = sel_list(ib_, db, f); const uint32_t nb = sel_count(nb_, db, f);
     const float* x = fr.xyz + (size_t)f * fr.frame_stride; const float* y = x + fr.axis_stride; const float* z = y + fr.axis_stride;
     const mdgpu_unitcell_t uc = cells[f];
     const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
@@ -441,9 +447,9 @@ __global__ void __launch_bounds__(256) k_distance_pair(BatchFrames fr, const mdg
     out[(size_t)(frame0 + f) * npairs + p] = pair_distance(pa[0], pa[1], pa[2], pb[0], pb[1], pb[2], uc.flags, ext, box);
 }
 
-void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s) {
+void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s, DynSel da, DynSel db) {
     if (!fr.count) return;
-    k_min_distance<<<fr.count, 256, 0, s>>>(fr, d_cells, d_ia, na, d_ib, nb, d_out, frame0);
+    k_min_distance<<<fr.count, 256, 0, s>>>(fr, d_cells, d_ia, na, d_ib, nb, d_out, frame0, da, db);
     note_launch("k_min_distance", s);
 }
 

@@ -128,48 +128,6 @@ __global__ void __launch_bounds__(256) k_within_compact(WithinArgs a, int32_t* _
     if (threadIdx.x == 0) dyn_n[f] = s_base;
 }
 
-// k_bin_points<1> (cells.cu) for a per-frame list: home cell of every listed atom (:1713-1719 ortho wraps periodic axes, :1561-1566
-// triclinic does not), unclamped inside the home grid, sentinel planes beyond the neighbour reach; same statements, same order.
-__global__ void k_bin_dyn(BatchFrames fr, const int32_t* __restrict__ dyn_idx, const uint32_t* __restrict__ dyn_n, uint32_t stride,
-                          const FrameGeom* __restrict__ geom, CellList cl) {
-    const int f = blockIdx.y;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= dyn_n[f]) return;
-    const FrameGeom& g = geom[f];
-    const int a = dyn_idx[(size_t)f * stride + i];
-    const float* x = fr.xyz + (size_t)f * fr.frame_stride;
-    const float r[3] = { x[a], x[fr.axis_stride + a], x[2 * fr.axis_stride + a] };
-    float s[3]; cart_to_fract(s, r, g);
-    const bool tri = (g.flags & MDGPU_CELL_TRICLINIC) != 0;
-    int hc[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (!tri && (g.flags & (MDGPU_CELL_PBC_X << k))) s[k] = __fsub_rn(s[k], floorf(s[k]));
-        const float cf = floorf(__fmul_rn(s[k], (float)g.cdim[k]));
-        const float lo = (float)g.hlo[k], hi = (float)(g.hlo[k] + g.hdim[k] - 1);
-        const float cl_ = fminf(fmaxf(cf, lo), hi);
-        hc[k] = (int)cl_ - g.hlo[k];
-        if (!(cf == cf)) hc[k] = 0;
-        if (!(cf >= 0.0f && cf < (float)g.cdim[k])) cl.oob[f] = 1u;
-    }
-    uint32_t cell = ((uint32_t)hc[2] * (uint32_t)g.hdim[1] + (uint32_t)hc[1]) * (uint32_t)g.hdim[0] + (uint32_t)hc[0];
-    if (g.valid <= 0) cell = 0;
-    const size_t o = (size_t)f * cl.max_points + i;
-    cl.scratch[o] = make_float4(s[0], s[1], s[2], __uint_as_float((uint32_t)a));
-    cl.cell_of[o] = cell;
-    cl.rank[o] = atomicAdd(&cl.cell_cnt[(size_t)f * (cl.cap + 1) + cell], 1u);
-}
-
-// k_scatter_points (cells.cu) limited to the frame's own count
-__global__ void k_scatter_dyn(const uint32_t* __restrict__ dyn_n, CellList cl) {
-    const int f = blockIdx.y;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= dyn_n[f]) return;
-    const size_t o = (size_t)f * cl.max_points + i;
-    const uint32_t dst = cl.cell_cnt[(size_t)f * (cl.cap + 1) + cl.cell_of[o]] + cl.rank[o];
-    cl.sorted[(size_t)f * cl.max_points + dst] = cl.scratch[o];
-}
-
 // zero the flags, mark: a few CTAs per frame, enough to fill the SMs across the batch
 static void launch_mark(const WithinArgs& a, int B, bool tri, int sm_count, cudaStream_t s) {
     cudaMemsetAsync(a.flags, 0, (size_t)B * a.num_atoms, s);
@@ -185,17 +143,6 @@ void launch_within_list(const WithinArgs& a, int B, bool tri, int sm_count, int3
     launch_mark(a, B, tri, sm_count, s);
     k_within_compact<<<B, 256, 0, s>>>(a, d_dyn_idx, d_dyn_n);
     note_launch("k_within_compact", s);
-}
-
-// launch_cell_list(1, ...) for the per-frame lists: cl.max_points is the list stride (num_atoms)
-void launch_cell_list_dyn(const BatchFrames& fr, const int32_t* d_dyn_idx, const uint32_t* d_dyn_n, uint32_t max_n, const FrameGeom* d_geom, const CellList& cl, cudaStream_t s) {
-    cudaMemsetAsync(cl.cell_cnt, 0, sizeof(uint32_t) * (size_t)fr.count * (cl.cap + 1), s);
-    cudaMemsetAsync(cl.oob, 0, sizeof(uint32_t) * fr.count, s);
-    if (!fr.count) return;
-    const dim3 grid((max_n + 255u) / 256u, fr.count);
-    if (max_n) { k_bin_dyn<<<grid, 256, 0, s>>>(fr, d_dyn_idx, d_dyn_n, cl.max_points, d_geom, cl); note_launch("k_bin_dyn", s); }
-    launch_scan_home_cells(d_geom, cl, (int)fr.count, s);
-    if (max_n) { k_scatter_dyn<<<grid, 256, 0, s>>>(d_dyn_n, cl); note_launch("k_scatter_dyn", s); }
 }
 
 void launch_within_count(const WithinArgs& a, int B, bool tri, int sm_count, cudaStream_t s) {

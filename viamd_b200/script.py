@@ -205,6 +205,13 @@ class _Parser:
         self.i = save
         return self.selection()
 
+    def sel_or_within(self, single=False):
+        """a selection argument that may be a dynamic one: index array, or api.Within for `within([min:]max, sel)` [and static]"""
+        if self._has_within_before_comma():
+            lo, hi, sel, cand = self.dyn_selection()
+            return api.Within(hi, sel, lo, cand)
+        return self.single_selection() if single else self.selection()
+
     def number(self) -> float:
         return float(self.expect("num")[1])
 
@@ -222,7 +229,7 @@ class _Parser:
         if self.peek() == ("id", "com"):   # com(x) as an argument contributes the position x itself would (_com :4726 = coordinate_extract_com)
             self.next(); self.expect("ch", "("); a = self.index(); self.expect("ch", ")")
             return a
-        return self.single_selection()
+        return self.sel_or_within(single=True)
 
     def statement(self) -> api.Property:
         ident = self.expect("id")[1]; self.expect("ch", "=")
@@ -233,23 +240,27 @@ class _Parser:
                 wlo, wr, wsel, wand = self.dyn_selection()
             grp = self.groups() if wr is None else None
             ref = None if (grp is not None or wr is not None) else self.selection()
-            self.expect("ch", ","); trg = self.selection(); self.expect("ch", ",")
+            self.expect("ch", ","); trg = self.sel_or_within(); self.expect("ch", ",")
             a = self.number(); lo, hi = 0.0, a
             if self.peek() == ("ch", ":"):
                 self.next(); lo, hi = a, self.number()
-            if wr is not None: p = api.rdf_within(ident, wr, wsel, trg, hi, lo, wlo, wand)
+            if wr is not None: p = api.rdf(ident, api.Within(wr, wsel, wlo, wand), trg, hi, lo) if isinstance(trg, api.Within) else api.rdf_within(ident, wr, wsel, trg, hi, lo, wlo, wand)
             else: p = api.rdf_com(ident, grp, trg, hi, lo) if grp is not None else api.rdf(ident, ref, trg, hi, lo)
         elif proc == "sdf":
-            st = self.structures(); self.expect("ch", ","); trg = self.selection(); self.expect("ch", ","); c = self.number()
+            st = self.structures(); self.expect("ch", ","); trg = self.sel_or_within(); self.expect("ch", ","); c = self.number()
             p = api.sdf(ident, st, trg, c)
         elif proc in ("density_x", "density_y", "density_z"):
-            p = api.density(ident, "xyz".index(proc[-1]), self.selection())
+            p = api.density(ident, "xyz".index(proc[-1]), self.sel_or_within())
         elif proc == "distance_pair":   # an array of selections (residue(a:b) over several residues) is one centre of mass per selection
             a = self.groups_or_selection(); self.expect("ch", ","); b = self.groups_or_selection()
             p = api.distance_pair(ident, a, b)
         elif proc in ("distance_min", "distance_max"):
-            a = self.single_selection(); self.expect("ch", ","); b = self.single_selection()
+            a = self.sel_or_within(single=True); self.expect("ch", ","); b = self.sel_or_within(single=True)
             p = {"distance_min": api.distance_min, "distance_max": api.distance_max, "distance_pair": api.distance_pair}[proc](ident, a, b)
+        elif proc == "contact_count":   # contact_count(A[], B, cutoff [, path_length])
+            a = self.groups_or_selection(); self.expect("ch", ","); b = self.selection(); self.expect("ch", ","); c = self.number(); pl = 4
+            if self.peek() == ("ch", ","): self.next(); pl = int(self.number())
+            p = api.contact_count(ident, a if isinstance(a, list) else [a], b, c, self.sys, pl)
         elif proc == "count":   # count(within(radius, selection)): the one dynamic selection the device path evaluates
             if not self._has_within_before_comma(): raise ScriptError("count() is lowered for within(radius, selection) expressions only")
             rlo, r, sel, cand = self.dyn_selection()
