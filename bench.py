@@ -518,6 +518,7 @@ def main():
     wl.free()
     plan.close()
     if world > 1:
+        tdist.barrier()   # rank 0 times the kernels alone after the timed region; the others wait for it here
         tdist.destroy_process_group()
     return 0
 

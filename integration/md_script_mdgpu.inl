@@ -116,7 +116,35 @@ static bool mdgpu__lower_within(mdgpu_property_desc_t* out, const ast_node_t* w,
     return true;
 }
 
-static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const ast_node_t* node, md_allocator_i* alloc) {
+/* argument k of a property: a static selection, or a dynamic one (within([min:]max, sel) [and static]) -> idx[k] (+ dyn[k]). Returns the number of
+ * bitfields of a static array argument through out_sets (1 for dynamic ones), or -1 when the argument is neither. */
+static int64_t mdgpu__lower_sel_arg(mdgpu_property_desc_t* out, int k, const ast_node_t* arg, size_t* out_sets, md_allocator_i* alloc) {
+    const ast_node_t* wmask = NULL; const ast_node_t* wnode = mdgpu__within_expr(arg, &wmask);
+    if (wnode) {
+        ast_node_t** c = wnode->children; size_t ns = 0; int64_t n;
+        mdgpu_dynamic_arg_t* dy = &out->dyn[k];
+        if (!(c[0]->flags & FLAG_CONSTANT) || c[1]->data.type.base_type != TYPE_BITFIELD) return -1;
+        if (c[0]->data.type.base_type == TYPE_FRANGE) { const frange_t r = *(const frange_t*)c[0]->data.ptr; dy->radius_min = r.beg; dy->radius_max = r.end; }   /* _within_expl_frng :2609 */
+        else if (c[0]->data.type.base_type == TYPE_FLOAT) { dy->radius_min = 0.0f; dy->radius_max = *(const float*)c[0]->data.ptr; }
+        else return -1;
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], &ns, NULL, c[1], alloc)) < 0) return -1;
+        out->idx_count[k] = mdgpu__flatten((int32_t*)out->idx[k], (size_t)n);   /* within is FLAG_FLATTEN (:673) */
+        if (wmask) {
+            int32_t* m = NULL;
+            if ((n = mdgpu__arg_indices(&m, NULL, NULL, wmask, alloc)) < 0) return -1;
+            dy->and_idx = m; dy->and_count = mdgpu__flatten(m, (size_t)n); dy->has_and = 1u;
+        }
+        if (out_sets) *out_sets = 1;
+        return (int64_t)out->idx_count[k];
+    }
+    {
+        int64_t n = mdgpu__arg_indices((int32_t**)&out->idx[k], out_sets, NULL, arg, alloc);
+        if (n >= 0) out->idx_count[k] = (size_t)n;
+        return n;
+    }
+}
+
+static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const ast_node_t* node, const md_system_t* mol, md_allocator_i* alloc) {
     const ast_node_t* rhs = mdgpu__rhs(node);
     const md_bitfield_t* ctx_bf = NULL; size_t n_ctx = 0;
     if (rhs->type == AST_CONTEXT && rhs->children && md_array_size(rhs->children) == 2) {   /* `expr in contexts` (evaluate_context md_script.c:3418) */
@@ -149,8 +177,8 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         }
         {
             size_t tsets = 0;
-            if ((n = mdgpu__arg_indices((int32_t**)&out->idx[1], &tsets, NULL, args[1], alloc)) < 0) goto dynamic; out->idx_count[1] = (size_t)n;
-            if (args[1]->data.type.base_type == TYPE_BITFIELD && tsets > 1) {   /* compute_rdf would use one centre of mass per bitfield (coordinate_extract) */
+            if ((n = mdgpu__lower_sel_arg(out, 1, args[1], &tsets, alloc)) < 0) goto dynamic;
+            if (!(out->dyn[1].radius_max > 0.0f) && args[1]->data.type.base_type == TYPE_BITFIELD && tsets > 1) {   /* compute_rdf would use one centre of mass per bitfield (coordinate_extract) */
                 MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections as rdf target (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false;
             }
         }
@@ -163,14 +191,14 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         out->op = MDGPU_OP_SDF;
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &nsets, &set_size, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
         out->num_structures = nsets; out->structure_size = set_size;
-        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[1], NULL, NULL, args[1], alloc)) < 0) goto dynamic; out->idx_count[1] = (size_t)n;
+        if ((n = mdgpu__lower_sel_arg(out, 1, args[1], NULL, alloc)) < 0) goto dynamic;
         if (!(args[2]->flags & FLAG_CONSTANT)) goto dynamic;
         out->cutoff_max = *(const float*)args[2]->data.ptr;
         return true;
     }
     if ((str_eq(pname, STR_LIT("density_x")) || str_eq(pname, STR_LIT("density_y")) || str_eq(pname, STR_LIT("density_z"))) && nargs == 1) {
         out->op = MDGPU_OP_DENSITY_X + (uint32_t)(pname.ptr[8] - 'x');
-        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], NULL, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
+        if ((n = mdgpu__lower_sel_arg(out, 0, args[0], NULL, alloc)) < 0) goto dynamic;
         out->idx_count[0] = mdgpu__flatten((int32_t*)out->idx[0], out->idx_count[0]);
         return true;
     }
@@ -185,7 +213,8 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         size_t ns = 0;
         const bool is_com = str_eq(pname, STR_LIT("com"));
         out->op = is_com ? MDGPU_OP_COM : MDGPU_OP_PLANE;
-        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
+        if (is_com) { if ((n = mdgpu__lower_sel_arg(out, 0, args[0], &ns, alloc)) < 0) goto dynamic; if (out->dyn[0].radius_max > 0.0f) { out->com_args = 1u; return true; } }
+        else { if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n; }
         if (args[0]->data.type.base_type == TYPE_BITFIELD) {
             if (ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false; }
             if (is_com) out->com_args = 1u;
@@ -197,6 +226,40 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         if (!wnode) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': count() is lowered for within(...) expressions only", STR_ARG(ident)); return false; }
         out->op = MDGPU_OP_WITHIN_COUNT;
         if (!mdgpu__lower_within(out, wnode, wmask, &out->cutoff_min, &out->cutoff_max, alloc)) goto dynamic;
+        return true;
+    }
+    if (str_eq(pname, STR_LIT("contact_count")) && (nargs == 3 || nargs == 4)) {   /* _contact_count :2756-2866 */
+        size_t na_sets = 0; int64_t nb;
+        out->op = MDGPU_OP_CONTACT_COUNT;
+        if (!mol) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': contact_count needs the system (bonds) to build its exclusion masks", STR_ARG(ident)); return false; }
+        if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &na_sets, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
+        if ((nb = mdgpu__arg_indices((int32_t**)&out->idx[1], NULL, NULL, args[1], alloc)) < 0) goto dynamic;
+        out->idx_count[1] = mdgpu__flatten((int32_t*)out->idx[1], (size_t)nb);                                    /* _internal_flatten_bf :2796 */
+        if (!(args[2]->flags & FLAG_CONSTANT) || args[2]->data.type.base_type != TYPE_FLOAT) goto dynamic;
+        out->cutoff_max = *(const float*)args[2]->data.ptr;
+        int path_length = 4;
+        if (nargs == 4) { if (!(args[3]->flags & FLAG_CONSTANT) || args[3]->data.type.base_type != TYPE_INT) goto dynamic; path_length = *(const int32_t*)args[3]->data.ptr; }
+        {
+            const md_bitfield_t* bf_a = (const md_bitfield_t*)args[0]->data.ptr;
+            uint32_t* off = (uint32_t*)md_alloc(alloc, sizeof(uint32_t) * (na_sets + 1));
+            uint32_t* eoff = (uint32_t*)md_alloc(alloc, sizeof(uint32_t) * (na_sets + 1));
+            off[0] = 0; for (size_t i = 0; i < na_sets; ++i) off[i + 1] = off[i] + (uint32_t)md_bitfield_popcount(&bf_a[i]);
+            /* the exclusion masks are static (topology only): built here with the reference's own function, once (md_script_functions.inl:2838-2840) */
+            md_bitfield_t bf_b = md_bitfield_create(alloc); md_bitfield_t excl = md_bitfield_create(alloc);
+            for (size_t j = 0; j < out->idx_count[1]; ++j) md_bitfield_set_bit(&bf_b, (uint64_t)out->idx[1][j]);
+            size_t total = 0; int32_t* eidx = NULL; size_t ecap = 0;
+            eoff[0] = 0;
+            for (size_t i = 0; i < na_sets; ++i) {
+                md_bitfield_clear(&excl); md_bitfield_and(&excl, &bf_a[i], &bf_b);
+                md_util_mask_grow_by_bonds(&excl, mol, (size_t)path_length, NULL);
+                const size_t c = md_bitfield_popcount(&excl);
+                if (total + c > ecap) { const size_t ncap = (total + c) * 2 + 16; int32_t* ne = (int32_t*)md_alloc(alloc, sizeof(int32_t) * ncap); if (total) MEMCPY(ne, eidx, sizeof(int32_t) * total); eidx = ne; ecap = ncap; }
+                if (c) md_bitfield_iter_extract_indices(eidx + total, c, md_bitfield_iter_create(&excl));
+                total += c; eoff[i + 1] = (uint32_t)total;
+            }
+            out->num_structures = na_sets; out->structure_offsets = off;
+            out->idx[2] = eidx; out->idx_count[2] = total; out->structure_offsets_b = eoff; out->num_structures_b = na_sets;
+        }
         return true;
     }
     if (str_eq(pname, STR_LIT("rmsd")) && nargs == 1) {   /* _rmsd :4287: the (flattened) selection against the initial configuration */
@@ -223,8 +286,8 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         out->op = str_eq(pname, STR_LIT("distance_min")) ? MDGPU_OP_DISTANCE_MIN : MDGPU_OP_DISTANCE_MAX;
         for (size_t k = 0; k < 2; ++k) {
             size_t ns = 0;
-            if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], &ns, NULL, args[k], alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n;
-            if (args[k]->data.type.base_type == TYPE_BITFIELD && ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (per-selection centres of mass) is not lowered for distance_min/max/pair", STR_ARG(ident)); return false; }
+            if ((n = mdgpu__lower_sel_arg(out, (int)k, args[k], &ns, alloc)) < 0) goto dynamic;
+            if (!(out->dyn[k].radius_max > 0.0f) && args[k]->data.type.base_type == TYPE_BITFIELD && ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (per-selection centres of mass) is not lowered for distance_min/max/pair", STR_ARG(ident)); return false; }
         }
         return true;
     }
@@ -258,7 +321,8 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
                 /* com(x) as an argument is the position coordinate_extract_com yields for x (_com :4726), which is what the argument x itself
                  * contributes (:1717): distance(com(sel), 5) == distance(sel, 5) */
                 if (a->type == AST_PROC_CALL && a->proc && str_eq(a->proc->name, STR_LIT("com")) && md_array_size(a->children) == 1) a = a->children[0];
-                if ((n = mdgpu__arg_indices((int32_t**)&out->idx[k], &ns, NULL, a, alloc)) < 0) goto dynamic; out->idx_count[k] = (size_t)n;
+                if ((n = mdgpu__lower_sel_arg(out, (int)k, a, &ns, alloc)) < 0) goto dynamic;
+                if (out->dyn[k].radius_max > 0.0f) { out->com_args |= 1u << k; continue; }   /* the frame's dynamic selection: its centre of mass */
                 if (a->data.type.base_type == TYPE_BITFIELD) {
                     if (ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections as argument (centre of sub-centres) is not lowered", STR_ARG(ident)); return false; }
                     out->com_args |= 1u << k;   /* a selection goes through md_util_com_compute even with one atom (coordinate_extract_com :1812) */
@@ -275,13 +339,13 @@ dynamic:
 }
 
 /* Lower every property of a compiled script. */
-static bool md_script_gpu_lower(md_script_gpu_lowered_t* out, const md_script_ir_t* ir, md_allocator_i* alloc) {
+static bool md_script_gpu_lower_sys(md_script_gpu_lowered_t* out, const md_script_ir_t* ir, const md_system_t* mol, md_allocator_i* alloc) {
     const size_t np = md_array_size(ir->property_names);
     out->num_props = np;
     out->props = (mdgpu_property_desc_t*)md_alloc(alloc, sizeof(mdgpu_property_desc_t) * (np ? np : 1));
     out->names = (char(*)[64])md_alloc(alloc, 64 * (np ? np : 1));
     for (size_t i = 0; i < np; ++i) {
-        if (!mdgpu__lower_property(&out->props[i], ir->property_names[i], ir->property_nodes[i], alloc)) return false;
+        if (!mdgpu__lower_property(&out->props[i], ir->property_names[i], ir->property_nodes[i], mol, alloc)) return false;
         const str_t nm = ir->property_names[i];
         memset(out->names[i], 0, 64); memcpy(out->names[i], nm.ptr, nm.len < 63 ? nm.len : 63);
         out->props[i].name = out->names[i];
@@ -289,10 +353,12 @@ static bool md_script_gpu_lower(md_script_gpu_lowered_t* out, const md_script_ir
     return true;
 }
 
+static bool md_script_gpu_lower(md_script_gpu_lowered_t* out, const md_script_ir_t* ir, md_allocator_i* alloc) { return md_script_gpu_lower_sys(out, ir, NULL, alloc); }
+
 /* md_script_eval_create counterpart for the device side: the plan holds what md_script_eval_t holds on the host. */
 static mdgpu_plan* md_script_gpu_plan_create(const md_script_ir_t* ir, const md_system_t* mol, size_t num_frames, int device, md_allocator_i* alloc) {
     md_script_gpu_lowered_t low = {0};
-    if (!md_script_gpu_lower(&low, ir, alloc)) return NULL;
+    if (!md_script_gpu_lower_sys(&low, ir, mol, alloc)) return NULL;
     float* mass = (float*)md_alloc(alloc, sizeof(float) * mol->atom.count);
     md_atom_extract_masses(mass, 0, mol->atom.count, &mol->atom);                       /* as eval_properties does, md_script.c:5764 */
     mdgpu_system_desc_t sys = {0};
@@ -428,7 +494,7 @@ static mdgpu_plan* mdgpu__plan_for(md_script_eval_t* eval, const md_script_ir_t*
             md_allocator_i* tmp = md_arena_allocator_create(md_get_heap_allocator(), MEGABYTES(1));
             md_script_gpu_lowered_t low = {0};
             mdgpu_plan* plan = NULL;
-            if (md_script_gpu_lower(&low, ir, tmp)) {
+            if (md_script_gpu_lower_sys(&low, ir, mol, tmp)) {
                 float* mass = (float*)md_alloc(tmp, sizeof(float) * (mol->atom.count ? mol->atom.count : 1));
                 md_atom_extract_masses(mass, 0, mol->atom.count, &mol->atom);                       /* as eval_properties does, md_script.c:5764 */
                 mdgpu_system_desc_t sd = {0};

@@ -28,14 +28,21 @@ static int mode_lower(int argc, char** argv) {
     md_script_ir_t* ir = md_script_ir_create(alloc);
     if (!md_script_ir_compile_from_source(ir, (str_t){ src, strlen(src) }, &sys, NULL, NULL) || !md_script_ir_valid(ir)) { fprintf(stderr, "script failed to compile\n"); return 2; }
     md_script_gpu_lowered_t low = {0};
-    if (!md_script_gpu_lower(&low, ir, alloc)) return 3;
+    if (!md_script_gpu_lower_sys(&low, ir, &sys, alloc)) return 3;
     FILE* f = fopen(arg_val(argc, argv, "--out", "lowered.bin"), "wb"); if (!f) return 2;
-    uint64_t np = low.num_props; fwrite("MDLOWER1", 1, 8, f); fwrite(&np, 8, 1, f);
+    uint64_t np = low.num_props; fwrite("MDLOWER2", 1, 8, f); fwrite(&np, 8, 1, f);
     for (size_t i = 0; i < low.num_props; ++i) {
         const mdgpu_property_desc_t* p = &low.props[i];
         uint64_t v[3] = { p->op, p->num_structures, p->structure_size };
         fwrite(low.names[i], 1, 64, f); fwrite(v, 8, 3, f); fwrite(&p->cutoff_min, 4, 1, f); fwrite(&p->cutoff_max, 4, 1, f);
         for (int k = 0; k < 4; ++k) { uint64_t c = p->idx_count[k]; fwrite(&c, 8, 1, f); if (c) fwrite(p->idx[k], 4, c, f); }
+        for (int k = 0; k < 4; ++k) {   /* dynamic arguments; rdf's round-1 spelling of a dynamic reference is reported as dyn[0] too */
+            mdgpu_dynamic_arg_t dy = p->dyn[k];
+            if (k == 0 && p->op == MDGPU_OP_RDF && p->ref_within_radius > 0.0f) { dy.radius_min = p->ref_within_min; dy.radius_max = p->ref_within_radius; dy.has_and = p->com_args & 1u; dy.and_idx = p->idx[2]; dy.and_count = p->idx_count[2]; }
+            uint64_t c = dy.has_and ? dy.and_count : 0, h = dy.has_and;
+            fwrite(&dy.radius_min, 4, 1, f); fwrite(&dy.radius_max, 4, 1, f); fwrite(&h, 8, 1, f); fwrite(&c, 8, 1, f); if (c) fwrite(dy.and_idx, 4, c, f);
+        }
+        { uint64_t nb = p->num_structures_b; fwrite(&nb, 8, 1, f); if (nb && p->structure_offsets_b) fwrite(p->structure_offsets_b, 4, nb + 1, f); }
     }
     fclose(f);
     printf("{\"properties\": %zu}\n", low.num_props);

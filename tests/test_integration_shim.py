@@ -21,7 +21,11 @@ SCRIPT = ("r = rdf(element('O'), element('O'), 6.0); v = sdf(residue(1:20), elem
 SCRIPT_NEW = ("rm = rmsd(residue(1:10)); dp = distance_pair(atom(1:5), atom(20:30)); c = com(residue(1)); ci = com(5); pl = plane(atom(1:30)); "
               "cw = count(within(4.0, residue(1))); dmn = distance_min(residue(1), atom(100:648)); dc = distance(residue(1), residue(5)); "
               "rw = rdf(within(4.0, residue(1)), element('O'), 6.0); cwr = count(within(2.5:5.0, residue(1))); rwr = rdf(within(3.0:6.0, residue(2)), element('O'), 1.0:6.5); "
-              "anc = angle(2,1,3) in residue(1:10); ddc = distance(1,3) in residue(:); cz = coord_z(atom(5:40)); dpg = distance_pair(residue(1:4), residue(10:15)); cwg = count(within(6.0, residue(1:5))); cwo = count(element('O') and within(4.0, residue(1))); rwo = rdf(element('H') and within(5.0, residue(2)), element('O'), 6.0); dcm = distance(com(atom(1:30)), 200); acm = angle(com(residue(1)), com(residue(2)), residue(3));")
+              "anc = angle(2,1,3) in residue(1:10); ddc = distance(1,3) in residue(:); cz = coord_z(atom(5:40)); dpg = distance_pair(residue(1:4), residue(10:15)); cwg = count(within(6.0, residue(1:5))); cwo = count(element('O') and within(4.0, residue(1))); rwo = rdf(element('H') and within(5.0, residue(2)), element('O'), 6.0); dcm = distance(com(atom(1:30)), 200); acm = angle(com(residue(1)), com(residue(2)), residue(3)); "
+              "rwt = rdf(element('O'), within(4.0, residue(1)), 6.0); rww = rdf(within(4.0, residue(1)), within(5.0, residue(2)), 6.0); vw = sdf(residue(1:20), within(6.0, residue(1:5)), 5.0); "
+              "dzw = density_z(within(5.0, residue(1))); dw = distance(within(4.0, residue(1)), 200); cmw = com(within(4.0, residue(1))); dmw = distance_min(within(3.5, residue(1)), residue(30)); "
+              "rwo2 = rdf(element('O') and within(5.0, residue(2)), element('H') and within(6.0, residue(3)), 5.0); aw = angle(within(2.5:5.0, residue(4)), 10, residue(7)); "
+              "cc = contact_count(residue(1:5), residue(10:40), 4.0); cc2 = contact_count(residue(3:20), element('O') and residue(50:216), 3.5);")
 
 
 def _need():
@@ -31,7 +35,7 @@ def _need():
 
 
 def _read_lowered(path):
-    b = open(path, "rb").read(); assert b[:8] == b"MDLOWER1"
+    b = open(path, "rb").read(); assert b[:8] == b"MDLOWER2"
     n, = struct.unpack_from("<Q", b, 8); off = 16; out = []
     for _ in range(n):
         name = b[off:off + 64].split(b"\0")[0].decode(); off += 64
@@ -41,7 +45,16 @@ def _read_lowered(path):
         for _k in range(4):
             c, = struct.unpack_from("<Q", b, off); off += 8
             lists.append(np.frombuffer(b, np.int32, c, off).copy()); off += 4 * c
-        out.append(dict(name=name, op=op, ns=ns, ss=ss, cmin=cmin, cmax=cmax, idx=lists))
+        dyn = {}
+        for k in range(4):
+            rmin, rmax = struct.unpack_from("<2f", b, off); off += 8
+            has_and, c = struct.unpack_from("<2Q", b, off); off += 16
+            a = np.frombuffer(b, np.int32, c, off).copy(); off += 4 * c
+            if rmax > 0: dyn[k] = (rmin, rmax, a if has_and else None)
+        nb, = struct.unpack_from("<Q", b, off); off += 8
+        eoff = None
+        if nb: eoff = np.frombuffer(b, np.uint32, nb + 1, off).copy(); off += 4 * (nb + 1)
+        out.append(dict(name=name, op=op, ns=ns, ss=ss, cmin=cmin, cmax=cmax, idx=lists, dyn=dyn, eoff=eoff))
     return out
 
 
@@ -62,7 +75,15 @@ def test_shim_lowering_matches_python_lowering(tmp_path):
         if b.op == vb.OP_RDF:   # array-of-selections reference -> centre-of-mass groups
             assert a["ns"] == b.num_structures
         for k, arr in enumerate(b.idx):
+            if b.op == vb.OP_RDF and b.ref_within > 0 and k == 2: continue   # the round-1 spelling keeps the AND mask in idx[2]; compared through dyn below
             assert np.array_equal(a["idx"][k], arr), (a["name"], k)
+        want = dict(b.dyn)
+        if b.op == vb.OP_RDF and b.ref_within > 0: want[0] = (b.ref_within_min, b.ref_within, b.idx[2] if b.com_args & 1 else None)
+        assert a["dyn"].keys() == want.keys(), a["name"]
+        for k, (rmin, rmax, cand) in want.items():
+            assert a["dyn"][k][0] == np.float32(rmin) and a["dyn"][k][1] == np.float32(rmax) and ((cand is None) == (a["dyn"][k][2] is None)), (a["name"], k)
+            if cand is not None: assert np.array_equal(a["dyn"][k][2], cand), (a["name"], k)
+        if b.op == vb.OP_CONTACT_COUNT: assert np.array_equal(a["eoff"], b.structure_offsets_b) and a["ns"] == b.num_structures
 
 
 @pytest.mark.gpu
