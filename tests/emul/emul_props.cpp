@@ -51,7 +51,7 @@ extern "C" int emul_com_rows(const float* frames, size_t frame_stride, size_t ax
 extern "C" int emul_min_distance(const float* frames, size_t frame_stride, size_t axis_stride, uint32_t num_frames, const mdgpu_unitcell_t* cells,
                                  const int32_t* ia, uint32_t na, const int32_t* ib, uint32_t nb, float* out) {
     mdg::BatchFrames fr{}; fr.xyz = frames; fr.frame_stride = frame_stride; fr.axis_stride = axis_stride; fr.count = num_frames;
-    emul_launch(dim3(num_frames, 1, 1), dim3(256, 1, 1), [&]() { mdg::k_min_distance(fr, cells, ia, na, ib, nb, out, 0); });   // launch_min_distance
+    emul_launch(dim3(num_frames, 1, 1), dim3(256, 1, 1), [&]() { mdg::k_min_distance(fr, cells, ia, na, ib, nb, out, 0, mdg::DynSel{}, mdg::DynSel{}); });   // launch_min_distance
     return 0;
 }
 
@@ -68,7 +68,7 @@ extern "C" int emul_temporal_args(const float* frames, size_t frame_stride, size
         a.atom[k] = idx[k][0];
         if (direct[k]) continue;
         a.com_mask |= 1u << k;
-        emul_launch(dim3(num_frames), dim3(32), [&]() { mdg::k_arg_com(fr, cells, idx[k], count[k], mass, pos.data(), k); });   // launch_arg_com
+        emul_launch(dim3(num_frames), dim3(32), [&]() { mdg::k_arg_com(fr, cells, idx[k], count[k], mass, pos.data(), k, mdg::DynSel{}); });   // launch_arg_com
     }
     emul_launch(dim3((num_frames + 63) / 64), dim3(64), [&]() { mdg::k_temporal(a, (int)num_frames); });
     return 0;

@@ -21,11 +21,11 @@ struct HostCellList {
 };
 void cell_list(int mode, const mdg::BatchFrames& fr, const int32_t* idx, const float* aos, uint32_t n, const mdg::FrameGeom* geom, const mdg::CellList& cl) {
     const dim3 grid((n + 255u) / 256u, fr.count);
-    if (n) { if (mode == 0) emul_launch(grid, dim3(256), [&]() { mdg::k_bin_points<0>(fr, idx, aos, n, geom, cl, 0); });
-             else           emul_launch(grid, dim3(256), [&]() { mdg::k_bin_points<1>(fr, idx, aos, n, geom, cl, 0); }); }
+    if (n) { if (mode == 0) emul_launch(grid, dim3(256), [&]() { mdg::k_bin_points<0>(fr, idx, aos, n, geom, cl, 0, mdg::DynSel{}); });
+             else           emul_launch(grid, dim3(256), [&]() { mdg::k_bin_points<1>(fr, idx, aos, n, geom, cl, 0, mdg::DynSel{}); }); }
     if (mode == 0) emul_launch(dim3(fr.count), dim3(128), [&]() { mdg::k_scan_cells<0>(geom, cl); });
     else           emul_launch(dim3(fr.count), dim3(128), [&]() { mdg::k_scan_cells<1>(geom, cl); });
-    if (n) emul_launch(grid, dim3(256), [&]() { mdg::k_scatter_points(n, cl); });
+    if (n) emul_launch(grid, dim3(256), [&]() { mdg::k_scatter_points(n, cl, nullptr); });
 }
 }  // namespace
 
@@ -40,7 +40,7 @@ extern "C" int emul_rdf(const float* frames, size_t frame_stride, size_t axis_st
     const bool tri = (cells[0].flags & MDGPU_CELL_TRICLINIC) != 0;
     bool all_pbc = true; for (int f = 0; f < B; ++f) all_pbc = all_pbc && ((cells[f].flags & MDGPU_CELL_PBC_ALL) == MDGPU_CELL_PBC_ALL);
     std::vector<float> aabb((size_t)6 * B, 0.0f);
-    if (!all_pbc) emul_launch(dim3(std::min((n_trg + 255u) / 256u, 64u), B), dim3(256), [&]() { k_aabb(fr, trg_idx, n_trg, aabb.data()); });
+    if (!all_pbc) emul_launch(dim3(std::min((n_trg + 255u) / 256u, 64u), B), dim3(256), [&]() { k_aabb(fr, trg_idx, n_trg, aabb.data(), mdg::DynSel{}); });
     std::vector<FrameGeom> geom(B); int err = 0;
     emul_launch(dim3((B + 63) / 64), dim3(64), [&]() { k_frame_geom(cells, all_pbc ? nullptr : aabb.data(), geom.data(), (double)cutoff_max, (double)cutoff_max, cap, B, &err); });
     if (err) return err;

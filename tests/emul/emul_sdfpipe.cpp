@@ -23,9 +23,9 @@ extern "C" int emul_sdf(const float* frames, size_t frame_stride, size_t axis_st
     CellList cl{}; cl.sorted = sorted.data(); cl.scratch = scratch.data(); cl.cell_of = cell_of.data(); cl.rank = rank.data(); cl.cell_cnt = cnt.data();
     cl.oob = cnt.data() + (size_t)num_frames * (cap + 1); cl.max_points = n_trg; cl.cap = cap;
     const dim3 grid((n_trg + 255u) / 256u, num_frames);   // launch_cell_list(0, ...), scan block narrowed to 128 threads
-    emul_launch(grid, dim3(256), [&]() { k_bin_points<0>(fr, trg_idx, nullptr, n_trg, geom.data(), cl, 0); });
+    emul_launch(grid, dim3(256), [&]() { k_bin_points<0>(fr, trg_idx, nullptr, n_trg, geom.data(), cl, 0, mdg::DynSel{}); });
     emul_launch(dim3(num_frames), dim3(128), [&]() { k_scan_cells<0>(geom.data(), cl); });
-    emul_launch(grid, dim3(256), [&]() { k_scatter_points(n_trg, cl); });
+    emul_launch(grid, dim3(256), [&]() { k_scatter_points(n_trg, cl, nullptr); });
 
     std::vector<float4> xyzw((size_t)num_frames * (n_struct + 1) * struct_size);
     std::vector<float> ref0((size_t)num_frames * 20), mats((size_t)num_frames * n_struct * 32);
@@ -36,7 +36,7 @@ extern "C" int emul_sdf(const float* frames, size_t frame_stride, size_t axis_st
     const int B = (int)num_frames;   // launch_sdf
     emul_launch(dim3((B + 31) / 32), dim3(32), [&]() { k_sdf_ref0(a, B); });
     emul_launch(dim3((n_struct + 63) / 64, B), dim3(64), [&]() { k_sdf_fit(a, B); });
-    if (tri) emul_launch(dim3((n_struct + SDF_WARPS - 1) / SDF_WARPS, B), dim3(SDF_WARPS * 32), [&]() { k_sdf_scatter<true>(a, B); });
-    else     emul_launch(dim3((n_struct + SDF_WARPS - 1) / SDF_WARPS, B), dim3(SDF_WARPS * 32), [&]() { k_sdf_scatter<false>(a, B); });
+    if (tri) emul_launch(dim3((n_struct + SDF_WARPS - 1) / SDF_WARPS, B), dim3(SDF_WARPS * 32), [&]() { k_sdf_scatter<true, 4>(a, B); });
+    else     emul_launch(dim3((n_struct + SDF_WARPS - 1) / SDF_WARPS, B), dim3(SDF_WARPS * 32), [&]() { k_sdf_scatter<false, 4>(a, B); });
     return 0;
 }

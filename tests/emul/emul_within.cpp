@@ -21,11 +21,11 @@ struct HostCellList {
 // launch_cell_list, with the scan block narrowed from 1024 to 128 threads (k_scan_cells is written for any multiple of 32)
 void cell_list(int mode, const mdg::BatchFrames& fr, const int32_t* idx, uint32_t n, const mdg::FrameGeom* geom, const mdg::CellList& cl) {
     const dim3 grid((n + 255u) / 256u, fr.count);
-    if (n) { if (mode == 0) emul_launch(grid, dim3(256), [&]() { mdg::k_bin_points<0>(fr, idx, nullptr, n, geom, cl, 0); });
-             else           emul_launch(grid, dim3(256), [&]() { mdg::k_bin_points<1>(fr, idx, nullptr, n, geom, cl, 0); }); }
+    if (n) { if (mode == 0) emul_launch(grid, dim3(256), [&]() { mdg::k_bin_points<0>(fr, idx, nullptr, n, geom, cl, 0, mdg::DynSel{}); });
+             else           emul_launch(grid, dim3(256), [&]() { mdg::k_bin_points<1>(fr, idx, nullptr, n, geom, cl, 0, mdg::DynSel{}); }); }
     if (mode == 0) emul_launch(dim3(fr.count), dim3(128), [&]() { mdg::k_scan_cells<0>(geom, cl); });
     else           emul_launch(dim3(fr.count), dim3(128), [&]() { mdg::k_scan_cells<1>(geom, cl); });
-    if (n) emul_launch(grid, dim3(256), [&]() { mdg::k_scatter_points(n, cl); });
+    if (n) emul_launch(grid, dim3(256), [&]() { mdg::k_scatter_points(n, cl, nullptr); });
 }
 }  // namespace
 
@@ -36,7 +36,7 @@ extern "C" int emul_within_count(const float* frames, size_t frame_stride, size_
     bool all_pbc = true, tri = (cells[0].flags & MDGPU_CELL_TRICLINIC) != 0;
     for (uint32_t f = 0; f < num_frames; ++f) all_pbc = all_pbc && ((cells[f].flags & MDGPU_CELL_PBC_ALL) == MDGPU_CELL_PBC_ALL);
     std::vector<float> aabb((size_t)6 * num_frames, 0.0f);
-    if (!all_pbc) emul_launch(dim3(std::min((num_atoms + 255u) / 256u, 64u), num_frames), dim3(256), [&]() { mdg::k_aabb(fr, nullptr, num_atoms, aabb.data()); });   // launch_aabb
+    if (!all_pbc) emul_launch(dim3(std::min((num_atoms + 255u) / 256u, 64u), num_frames), dim3(256), [&]() { mdg::k_aabb(fr, nullptr, num_atoms, aabb.data(), mdg::DynSel{}); });   // launch_aabb
     std::vector<mdg::FrameGeom> geom(num_frames); int err = 0;
     emul_launch(dim3((num_frames + 63) / 64), dim3(64), [&]() { mdg::k_frame_geom(cells, all_pbc ? nullptr : aabb.data(), geom.data(), cell_ext, (double)radius, cap, (int)num_frames, &err); });
     if (err) return err;

@@ -383,8 +383,8 @@ MDG_D void sdf_splat(float vx, float vy, float vz, const SdfXform& X, uint32_t* 
     atomicAdd(&vol[(iz * MDGPU_VOL_DIM + iy) * MDGPU_VOL_DIM + ix], 1u);
 }
 
-template <bool TRI>
-__global__ void __launch_bounds__(SDF_WARPS * 32) k_sdf_scatter(SdfArgs a, int B) {
+template <bool TRI, int MINB>
+__global__ void __launch_bounds__(SDF_WARPS * 32, MINB) k_sdf_scatter(SdfArgs a, int B) {
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, hl = lane & 15, half = lane >> 4;
     const uint32_t s = blockIdx.x * SDF_WARPS + warp;
@@ -918,7 +918,12 @@ void launch_sdf(const SdfArgs& a, int B, bool tri, cudaStream_t s) {
     dim3 g2((a.n_struct + SDF_WARPS - 1) / SDF_WARPS, B);
     static const bool ring = []() { const char* e = getenv("MDGPU_SDF"); return e && strcmp(e, "ring") == 0; }();
     if (ring) { if (tri) k_sdf_scatter_ring<true><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); else k_sdf_scatter_ring<false><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); }
-    else      { if (tri) k_sdf_scatter<true><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); else k_sdf_scatter<false><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); }
+    else {
+        static const int occ = []() { const char* e = getenv("MDGPU_SDF_OCC"); return e ? atoi(e) : 4; }();   // resident CTAs / SM the register allocation aims for
+        if (occ >= 5)      { if (tri) k_sdf_scatter<true, 5><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); else k_sdf_scatter<false, 5><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); }
+        else if (occ == 4) { if (tri) k_sdf_scatter<true, 4><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); else k_sdf_scatter<false, 4><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); }
+        else               { if (tri) k_sdf_scatter<true, 3><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); else k_sdf_scatter<false, 3><<<g2, SDF_WARPS * 32, 0, s>>>(a, B); }
+    }
     note_launch("k_sdf_scatter", s);
 }
 
