@@ -38,7 +38,7 @@ RDF_PATCHES = [
     # TMA / mbarrier helpers of the VAR 2 kernel: the copy happens at once, the barrier is a phase counter
     (r'^MDG_D void mbar_init\(uint32_t mbar_saddr, uint32_t count\) \{.*$', 'MDG_D void mbar_init(uint32_t mbar_saddr, uint32_t count) { *(unsigned long long*)(emul_dyn_smem + mbar_saddr) = 0ull; }', 1),
     (r'^MDG_D void mbar_expect_tx\(uint32_t mbar_saddr, uint32_t bytes\) \{.*$', 'MDG_D void mbar_expect_tx(uint32_t mbar_saddr, uint32_t bytes) { }', 1),
-    (r'^MDG_D bool mbar_try_wait\(uint32_t mbar_saddr, uint32_t parity\) \{.*$', 'MDG_D bool mbar_try_wait(uint32_t mbar_saddr, uint32_t parity) { return (__atomic_load_n((unsigned long long*)(emul_dyn_smem + mbar_saddr), __ATOMIC_ACQUIRE) & 1ull) != (unsigned long long)parity; }', 1),
+    (r'^MDG_D bool mbar_try_wait\(uint32_t mbar_saddr, uint32_t parity\) \{.*$', 'MDG_D bool mbar_try_wait(uint32_t mbar_saddr, uint32_t parity) { const bool done = (__atomic_load_n((unsigned long long*)(emul_dyn_smem + mbar_saddr), __ATOMIC_ACQUIRE) & 1ull) != (unsigned long long)parity; if (!done && emul_block) emul_yield(); return done; }', 1),
     (r'^MDG_D void tma_load_1d\(uint32_t dst_saddr, const void\* src, uint32_t bytes, uint32_t mbar_saddr\) \{.*$', 'MDG_D void tma_load_1d(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t mbar_saddr) { memcpy(emul_dyn_smem + dst_saddr, src, bytes); __atomic_fetch_add((unsigned long long*)(emul_dyn_smem + mbar_saddr), 1ull, __ATOMIC_RELEASE); }', 1),
     (r'^MDG_D void fence_mbar_init\(\) \{.*$', 'MDG_D void fence_mbar_init() { }', 1),
     (r'^MDG_D void fence_proxy_async\(\) \{.*$', 'MDG_D void fence_proxy_async() { }', 1),

@@ -6,7 +6,7 @@
 // -O2 -ffp-contract=off -fno-fast-math without -mfma, so a*b+c is never fused, as with nvcc --fmad=false), atomics, and two ways to run a kernel:
 //   * thread by thread (the caller loops over blockIdx / threadIdx and calls the kernel function): enough for kernels whose threads do
 //     not cooperate; the warp/block collectives abort if reached;
-//   * emul_launch(grid, block, fn): every thread of a block is a host thread, blocks run one after the other; __syncthreads / __syncwarp
+//   * emul_launch(grid, block, fn): every thread of a block is a fiber on the calling host thread, blocks run one after the other; __syncthreads / __syncwarp
 //     are barriers, the warp collectives (__shfl_*_sync, __ballot_sync, __any/__all_sync, __reduce_*_sync) exchange through a per-warp
 //     buffer, `__shared__` variables are function-local statics (one block at a time, so one copy is what a block sees). Threads that
 //     return drop out of the barriers, as exited threads do on the device. Lanes named in a collective's mask must all reach it.
@@ -18,11 +18,12 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
-#include <barrier>
+#include <stdio.h>
+#include <sys/mman.h>
+#include <ucontext.h>
 #include <functional>
 #include <memory>
 #include <mutex>
-#include <thread>
 #include <vector>
 
 #undef __shared__
@@ -60,22 +61,47 @@ alignas(16) static unsigned char emul_dyn_smem[228 * 1024];
 template <typename T> static inline size_t __cvta_generic_to_shared(const T* p) { return (size_t)((const unsigned char*)p - emul_dyn_smem); }
 
 // ---------------------------------------------------------------------------------------------- block / warp cooperation (emul_launch)
-struct EmulWarp { std::unique_ptr<std::barrier<>> bar; unsigned long long slot[32]; };
-struct EmulBlock { std::unique_ptr<std::barrier<>> bar; std::vector<EmulWarp> warps; };
+// Every thread of a block is a FIBER (ucontext) on the host thread that called emul_launch; blocks run one after the other. A barrier is
+// "count, and while the generation has not advanced, switch to the next unfinished fiber of the block" — no OS threads, no futexes (the
+// first version used one host thread per device thread and std::barrier; on the 8-core CI container the CPU suite spent 25 of its 32
+// CPU-minutes in the kernel). Scheduling is round-robin in thread order and deterministic. Threads that return drop out of the barriers.
+struct EmulBar { int expected = 0, count = 0; unsigned gen = 0; };
+struct EmulWarp { EmulBar bar; unsigned long long slot[32]; };
+struct EmulFiber { ucontext_t ctx; uint3 tid; int lane, warp; bool done; };
+struct EmulBlock {
+    EmulBar bar; std::vector<EmulWarp> warps; std::vector<EmulFiber> fibers; int cur = 0, live = 0; ucontext_t main_ctx;
+    const std::function<void()>* fn = nullptr;
+};
 static thread_local EmulBlock* emul_block = nullptr;
 static thread_local int emul_lane = 0, emul_warp = 0;
 
+static inline void emul_enter(const EmulFiber& f) { threadIdx = f.tid; emul_lane = f.lane; emul_warp = f.warp; }   // this translation unit's view of "which thread am I"
+static inline void emul_yield() {
+    EmulBlock* b = emul_block; const int n = (int)b->fibers.size(), me = b->cur; int nx = me;
+    do { nx = nx + 1 == n ? 0 : nx + 1; } while (b->fibers[nx].done && nx != me);
+    if (nx == me) return;
+    b->cur = nx; swapcontext(&b->fibers[me].ctx, &b->fibers[nx].ctx);
+    emul_enter(b->fibers[me]);
+}
+static inline void emul_bar_wait(EmulBar& x) {
+    const unsigned g = x.gen;
+    if (++x.count >= x.expected) { x.count = 0; ++x.gen; return; }
+    unsigned long long spins = 0;
+    while (x.gen == g) { emul_yield(); if (++spins > (1ull << 26)) { fprintf(stderr, "cuda_emul: barrier never completed (divergent collective?)\n"); abort(); } }
+}
+static inline void emul_bar_drop(EmulBar& x) { if (--x.expected > 0 && x.count >= x.expected) { x.count = 0; ++x.gen; } }
+
 static inline EmulWarp& emul_w() { if (!emul_block) abort(); /* collective reached in thread-by-thread mode */ return emul_block->warps[emul_warp]; }
-static inline void __syncthreads() { if (!emul_block) abort(); emul_block->bar->arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { if (emul_block) emul_w().bar->arrive_and_wait(); }   // thread-by-thread mode: lanes run one after the other
+static inline void __syncthreads() { if (!emul_block) abort(); emul_bar_wait(emul_block->bar); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { if (emul_block) emul_bar_wait(emul_w().bar); }   // thread-by-thread mode: lanes run one after the other
 
 // every lane publishes a value, then reads the slot of `src` (two warp barriers: publish | read)
 template <typename T> static inline T emul_exchange(T v, int src) {
     static_assert(sizeof(T) <= 8, "shuffle of more than 8 bytes");
     EmulWarp& w = emul_w(); unsigned long long bits = 0; memcpy(&bits, &v, sizeof(T)); w.slot[emul_lane] = bits;
-    w.bar->arrive_and_wait();
+    emul_bar_wait(w.bar);
     T r; const unsigned long long got = w.slot[src & 31]; memcpy(&r, &got, sizeof(T));
-    w.bar->arrive_and_wait();
+    emul_bar_wait(w.bar);
     return r;
 }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32) { return emul_exchange(v, (emul_lane & ~(width - 1)) | (src & (width - 1))); }
@@ -85,9 +111,9 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m, int 
 // gather of one value per lane over the lanes of `mask`, folded by f
 template <typename F> static inline unsigned emul_fold(unsigned mask, unsigned v, unsigned init, F f) {
     EmulWarp& w = emul_w(); w.slot[emul_lane] = v;
-    w.bar->arrive_and_wait();
+    emul_bar_wait(w.bar);
     unsigned r = init; for (int l = 0; l < 32; ++l) if (mask >> l & 1u) r = f(r, (unsigned)w.slot[l], l);
-    w.bar->arrive_and_wait();
+    emul_bar_wait(w.bar);
     return r;
 }
 static inline unsigned __ballot_sync(unsigned mask, int pred) { return emul_fold(mask, pred ? 1u : 0u, 0u, [](unsigned r, unsigned v, int l) { return r | (v << l); }); }
@@ -98,28 +124,52 @@ static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return emu
 static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return emul_fold(mask, v, 0u, [](unsigned r, unsigned x, int) { return r > x ? r : x; }); }
 static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) { return emul_fold(mask, v, 0xffffffffu, [](unsigned r, unsigned x, int) { return r < x ? r : x; }); }
 
-// run fn() as every thread of every block of the grid; blocks one after the other, the threads of a block concurrently
+// fiber stacks of the calling host thread (kept for its lifetime; pages are touched only as deep as a kernel's frames go)
+static constexpr size_t EMUL_STACK_BYTES = 512 * 1024;
+struct EmulStacks { std::vector<void*> s; ~EmulStacks() { for (void* p : s) munmap(p, EMUL_STACK_BYTES); } };
+static inline void* emul_stack(int t) {
+    static thread_local EmulStacks st;
+    while ((int)st.s.size() <= t) { void* p = mmap(nullptr, EMUL_STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0); if (p == MAP_FAILED) abort(); st.s.push_back(p); }
+    return st.s[t];
+}
+static void emul_fiber_main() {
+    EmulBlock* b = emul_block; EmulFiber& f = b->fibers[b->cur];
+    emul_enter(f);
+    (*b->fn)();
+    b = emul_block; EmulFiber& me = b->fibers[b->cur];                 // (the fiber may have been resumed any number of times since)
+    b->warps[me.warp].slot[me.lane] = 0;                               // an exited lane contributes 0 to later ballots
+    me.done = true; --b->live; emul_bar_drop(b->warps[me.warp].bar); emul_bar_drop(b->bar);
+    if (b->live == 0) { setcontext(&b->main_ctx); abort(); }
+    const int n = (int)b->fibers.size(); int nx = b->cur; do { nx = nx + 1 == n ? 0 : nx + 1; } while (b->fibers[nx].done);
+    b->cur = nx; setcontext(&b->fibers[nx].ctx); abort();
+}
+
+// run fn() as every thread of every block of the grid; blocks one after the other.
 // One launch at a time, process-wide: `__shared__` variables are single static copies, so kernels enqueued by different host threads
 // (concurrent callers of one plan, the per-device threads of a multi-device plan) must not overlap here as they may on a device.
 inline std::mutex& emul_launch_mutex() { static std::mutex m; return m; }
 static inline void emul_launch(dim3 grid, dim3 block, const std::function<void()>& fn) {
     std::lock_guard<std::mutex> emul_guard(emul_launch_mutex());
     const int nthreads = (int)(block.x * block.y * block.z), nwarps = (nthreads + 31) / 32;
+    if (!nthreads) return;
+    EmulBlock blk; blk.warps.resize(nwarps); blk.fibers.resize(nthreads); blk.fn = &fn;
+    gridDim = grid; blockDim = block;
+    const uint3 saved_tid = threadIdx, saved_bid = blockIdx;
     for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
-        EmulBlock blk; blk.bar = std::make_unique<std::barrier<>>(nthreads); blk.warps.resize(nwarps);
-        for (int w = 0; w < nwarps; ++w) { blk.warps[w].bar = std::make_unique<std::barrier<>>(std::min(32, nthreads - 32 * w)); memset(blk.warps[w].slot, 0, sizeof(blk.warps[w].slot)); }
-        std::vector<std::thread> th; th.reserve(nthreads);
-        for (int t = 0; t < nthreads; ++t) th.emplace_back([&, t]() {
-            gridDim = grid; blockDim = block; blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
-            threadIdx.x = t % block.x; threadIdx.y = (t / block.x) % block.y; threadIdx.z = t / (block.x * block.y);
-            emul_block = &blk; emul_lane = t & 31; emul_warp = t >> 5;
-            fn();
-            blk.warps[emul_warp].slot[emul_lane] = 0;        // an exited lane contributes 0 to later ballots
-            blk.warps[emul_warp].bar->arrive_and_drop(); blk.bar->arrive_and_drop();
-            emul_block = nullptr;
-        });
-        for (auto& t : th) t.join();
+        blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+        blk.bar = EmulBar{nthreads, 0, 0};
+        for (int w = 0; w < nwarps; ++w) { blk.warps[w].bar = EmulBar{std::min(32, nthreads - 32 * w), 0, 0}; memset(blk.warps[w].slot, 0, sizeof(blk.warps[w].slot)); }
+        for (int t = 0; t < nthreads; ++t) {
+            EmulFiber& f = blk.fibers[t];
+            f.tid.x = t % block.x; f.tid.y = (t / block.x) % block.y; f.tid.z = t / (block.x * block.y); f.lane = t & 31; f.warp = t >> 5; f.done = false;
+            getcontext(&f.ctx); f.ctx.uc_stack.ss_sp = emul_stack(t); f.ctx.uc_stack.ss_size = EMUL_STACK_BYTES; f.ctx.uc_link = nullptr;
+            makecontext(&f.ctx, emul_fiber_main, 0);
+        }
+        blk.cur = 0; blk.live = nthreads; emul_block = &blk;
+        swapcontext(&blk.main_ctx, &blk.fibers[0].ctx);      // returns when the last fiber of the block has finished
+        emul_block = nullptr;
     }
+    threadIdx = saved_tid; blockIdx = saved_bid; emul_lane = 0; emul_warp = 0;
 }
 
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {   // prmt.b32, default mode
