@@ -29,8 +29,7 @@ RDF_PATCHES = [
     (r'^MDG_D float q_load\(uint32_t addr\) \{.*$', 'MDG_D float q_load(uint32_t addr) { return *(const float*)(emul_dyn_smem + addr); }', 1),
     (r'MDG_D float sqrt_rn_normal\(float x\) \{.*?\n\}', 'MDG_D float sqrt_rn_normal(float x) { return sqrtf(x); }   /* the device sequence is swept against IEEE sqrt on the GPU */', 1),
     (r'^    asm volatile\("red\.shared\.add\.u32 \[%0\], %1;".*$', '    __atomic_fetch_add((uint32_t*)(emul_dyn_smem + hist_saddr + 4u * (uint32_t)bin), w, __ATOMIC_RELAXED);', 1),
-    (r'^    asm volatile\("\{ \.reg \.pred q;.*$', '    if (p) __atomic_fetch_add((uint32_t*)(emul_dyn_smem + hist_saddr + 4u * (uint32_t)bin), w, __ATOMIC_RELAXED);', 1),
-    (r'float4 rf; asm volatile\("ld\.shared\.v4\.f32.*$', 'const float4 rf = *(const float4*)(emul_dyn_smem + sref_saddr + 16u * (uint32_t)(gi * V2_UNROLL + u));', 1),
+    (r'^    float4 rf; asm volatile\("ld\.shared\.v4\.f32.*$', '    return *(const float4*)(emul_dyn_smem + saddr + (uint32_t)OFF);', 1),
     (r'^    extern __shared__ __align__\(16\) unsigned char smem_raw\[\];$', '    unsigned char* smem_raw = emul_dyn_smem;', 1),
     (r'^    asm volatile\("mov\.u32 %0, %0;".*$', '', 3),
     (r'cudaFuncSetAttribute\(k_rdf_pairs_v2<[\w, ]+>, [^;]*;', ';', 6),                       # launcher-only runtime calls on kernel symbols
