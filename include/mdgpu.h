@@ -182,6 +182,10 @@ typedef struct mdgpu_property_desc_t {
     mdgpu_dynamic_arg_t dyn[4];          /* per argument: a dynamic selection (see above). Consumers: rdf reference and / or target, sdf target, density_x/_y/_z,
                                           * distance / angle / dihedral / com (the centre of mass of the frame's selection), distance_min / _max, count().
                                           * ref_within_radius (+ com_args bit 0 / idx[2]) is the round-1 spelling of dyn[0] for rdf and still honoured. */
+    const uint32_t* arg_offsets[4];      /* distance / angle / dihedral / com: argument k was an ARRAY of arg_parts[k] >= 2 selections. idx[k] holds them back to */
+    uint32_t arg_parts[4];               /* back, arg_offsets[k] their arg_parts[k] + 1 CSR offsets. Its position is the centre of the selections' centres:
+                                          * md_util_com_compute per selection, then md_util_com_compute_vec4 over those with weight 1
+                                          * (coordinate_extract_com md_script_functions.inl:1826-1842). 0 or 1: idx[k] is one selection. */
 } mdgpu_property_desc_t;
 
 /* Result view: the fields of md_script_property_data_t (md_script.h:73-92) that the evaluation fills. */

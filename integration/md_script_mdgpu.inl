@@ -76,6 +76,16 @@ static int64_t mdgpu__arg_indices(int32_t** out, size_t* out_num_sets, size_t* o
     return -1;
 }
 
+/* CSR offsets of the bitfields of a static array argument inside the concatenated list mdgpu__arg_indices returns (n + 1 entries) */
+static uint32_t* mdgpu__arg_part_offsets(const ast_node_t* arg, md_allocator_i* alloc) {
+    const md_bitfield_t* bf = (const md_bitfield_t*)arg->data.ptr;
+    const size_t n = element_count(arg->data);
+    uint32_t* off = (uint32_t*)md_alloc(alloc, sizeof(uint32_t) * (n + 1));
+    off[0] = 0;
+    for (size_t i = 0; i < n; ++i) off[i + 1] = off[i] + (uint32_t)md_bitfield_popcount(&bf[i]);
+    return off;
+}
+
 /* _internal_flatten_bf: union of an array of bitfields. The concatenated index lists of disjoint sets are already that union; sort + unique
  * covers overlapping ones. Returns the new count. */
 static size_t mdgpu__flatten(int32_t* v, size_t n) {
@@ -216,7 +226,10 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         if (is_com) { if ((n = mdgpu__lower_sel_arg(out, 0, args[0], &ns, alloc)) < 0) goto dynamic; if (out->dyn[0].radius_max > 0.0f) { out->com_args = 1u; return true; } }
         else { if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n; }
         if (args[0]->data.type.base_type == TYPE_BITFIELD) {
-            if (ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false; }
+            if (ns > 1) {
+                if (!is_com) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false; }
+                out->arg_offsets[0] = mdgpu__arg_part_offsets(args[0], alloc); out->arg_parts[0] = (uint32_t)ns;   /* the centre of the selections' centres (coordinate_extract_com :1826-1842) */
+            }
             if (is_com) out->com_args = 1u;
         }
         return true;
@@ -324,7 +337,9 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
                 if ((n = mdgpu__lower_sel_arg(out, (int)k, a, &ns, alloc)) < 0) goto dynamic;
                 if (out->dyn[k].radius_max > 0.0f) { out->com_args |= 1u << k; continue; }   /* the frame's dynamic selection: its centre of mass */
                 if (a->data.type.base_type == TYPE_BITFIELD) {
-                    if (ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections as argument (centre of sub-centres) is not lowered", STR_ARG(ident)); return false; }
+                    /* an array of selections: the centre of the selections' centres (coordinate_extract_com :1826-1842). distance() is FLAG_FLATTEN
+                     * (md_script_functions.inl:680), so the front-end has already merged its array arguments into one bitfield: ns == 1 there. */
+                    if (ns > 1) { out->arg_offsets[k] = mdgpu__arg_part_offsets(a, alloc); out->arg_parts[k] = (uint32_t)ns; }
                     out->com_args |= 1u << k;   /* a selection goes through md_util_com_compute even with one atom (coordinate_extract_com :1812) */
                 }
             }

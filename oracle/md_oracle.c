@@ -1109,12 +1109,9 @@ static float m3_eigen_values(m3 M, float ev_sorted[3]) {
     ev_sorted[0] = ev[l[0]]; ev_sorted[1] = ev[l[1]]; ev_sorted[2] = ev[l[2]];
     return mx;
 }
-void mdo_shape_weights(const float* x, const float* y, const float* z, const float* mass, const int32_t* idx, size_t n, const mdo_unitcell_t* cell, float out[3]) {
-    out[0] = out[1] = out[2] = 0.0f;
-    if (n == 0) return;
-    v4* p = malloc(sizeof(v4) * n);
-    for (size_t k = 0; k < n; ++k) { const int32_t a = idx[k]; p[k][0] = x[a]; p[k][1] = y[a]; p[k][2] = z[a]; p[k][3] = mass ? mass[a] : 1.0f; }
-    float com[3];
+/* md_util_com_compute_vec4 (md_util.c:8188-8201) of n points xyzw: com_pbc_vec4 (:8063-8162: serial float accumulation of w*sin, w*cos per
+ * axis, 4-lane sincos, double atan2; the triclinic centre goes through the 1/2pi-scaled inverse twice, as written) in a cell, com_vec4 (:8048) without */
+static void com_compute_v4(float com[3], const v4* p, size_t n, const mdo_unitcell_t* cell) {
     const double TWO_PI_D = 2.0 * 3.1415926535897932, PI_D = 3.1415926535897932;
     if (cell->flags & MDO_CELL_ORTHO) {
         const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
@@ -1134,12 +1131,10 @@ void mdo_shape_weights(const float* x, const float* y, const float* z, const flo
             double theta = PI_D; if (r2 > 1.0e-15) theta += atan2(-yy, -xx);
             com[a] = (float)((theta / TWO_PI_D) * ext[a]);
         }
-        for (size_t k = 0; k < n; ++k) for (int a = 0; a < 3; ++a) p[k][a] = deperiodize1(p[k][a], com[a], ext[a]);
     } else if (cell->flags & MDO_CELL_TRICLINIC) {
-        double Ad[3][3], Id[3][3]; cell_A(Ad, cell); cell_I(Id, cell);
-        float A[3][3], I[3][3];   /* I = mat3_mul(mat3_scale(1/2pi), Ai): C[col][row] = S[row][row] * Ai[col][row] (core/md_vec_math.h:1631) */
+        double Id[3][3]; cell_I(Id, cell);
+        float I[3][3];   /* I = mat3_mul(mat3_scale(1/2pi), Ai): C[col][row] = S[row][row] * Ai[col][row] (core/md_vec_math.h:1631) */
         const float inv_tp = 1.0f / (float)TWO_PI_D;
-        for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) A[c][r] = (float)Ad[c][r];
         for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) {   /* exact form of MULT(col,row): A.e[0][row]*B.e[col][0] + A.e[1][row]*B.e[col][1] + A.e[2][row]*B.e[col][2] with A = scale */
             const float S[3][3] = { { inv_tp, 0, 0 }, { 0, inv_tp, 0 }, { 0, 0, inv_tp } };
             const float Ai[3] = { (float)Id[c][0], (float)Id[c][1], (float)Id[c][2] };
@@ -1161,14 +1156,46 @@ void mdo_shape_weights(const float* x, const float* y, const float* z, const flo
             double theta = PI_D; if (r2 > 1.0e-8) theta += atan2(-yy, -xx);
             com[a] = (float)(theta * I[a][0] + theta * I[a][1] + theta * I[a][2]);   /* :8158, I.elem[i][0..2] */
         }
+    } else {
+        com_v4(com, p, n);   /* no cell: com_vec4 */
+    }
+}
+
+/* position of an argument that is an ARRAY of selections (coordinate_extract_com md_script_functions.inl:1826-1842): md_util_com_compute of each
+ * selection (mdo_com), then md_util_com_compute_vec4 over those centres with weight 1. idx holds the selections back to back, off their CSR offsets. */
+void mdo_arg_position_parts(const float* x, const float* y, const float* z, const float* mass, const int32_t* idx, const uint32_t* off, size_t n_parts,
+                            const mdo_unitcell_t* cell, float out[3]) {
+    v4* p = malloc(sizeof(v4) * (n_parts ? n_parts : 1));
+    for (size_t k = 0; k < n_parts; ++k) {
+        float c[3] = { 0.0f, 0.0f, 0.0f };
+        if (off[k + 1] > off[k]) mdo_com(x, y, z, mass, idx + off[k], off[k + 1] - off[k], cell, c);   /* count == 0 -> (0, 0, 0) (md_util.c:8168) */
+        p[k][0] = c[0]; p[k][1] = c[1]; p[k][2] = c[2]; p[k][3] = 1.0f;
+    }
+    out[0] = out[1] = out[2] = 0.0f;
+    if (n_parts) com_compute_v4(out, p, n_parts, cell);
+    free(p);
+}
+
+void mdo_shape_weights(const float* x, const float* y, const float* z, const float* mass, const int32_t* idx, size_t n, const mdo_unitcell_t* cell, float out[3]) {
+    out[0] = out[1] = out[2] = 0.0f;
+    if (n == 0) return;
+    v4* p = malloc(sizeof(v4) * n);
+    for (size_t k = 0; k < n; ++k) { const int32_t a = idx[k]; p[k][0] = x[a]; p[k][1] = y[a]; p[k][2] = z[a]; p[k][3] = mass ? mass[a] : 1.0f; }
+    float com[3];
+    com_compute_v4(com, p, n, cell);
+    if (cell->flags & MDO_CELL_ORTHO) {
+        const float ext[3] = { (float)cell->x, (float)cell->y, (float)cell->z };
+        for (size_t k = 0; k < n; ++k) for (int a = 0; a < 3; ++a) p[k][a] = deperiodize1(p[k][a], com[a], ext[a]);
+    } else if (cell->flags & MDO_CELL_TRICLINIC) {
+        double Ad[3][3]; cell_A(Ad, cell);
+        float A[3][3];
+        for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) A[c][r] = (float)Ad[c][r];
         const float box[3][3] = { { A[0][0], 0, 0 }, { A[1][0], A[1][1], 0 }, { A[2][0], A[2][1], A[2][2] } };
         for (size_t k = 1; k < n; ++k) {   /* deperiodize_triclinic from atom 1 on (:8993) */
             float d[3] = { p[k][0] - com[0], p[k][1] - com[1], p[k][2] - com[2] };
             min_image_triclinic(d, box);
             p[k][0] = com[0] + d[0]; p[k][1] = com[1] + d[1]; p[k][2] = com[2] + d[2];
         }
-    } else {
-        com_v4(com, p, n);   /* no cell: com_vec4; md_util_deperiodize_vec4 does nothing */
     }
     float ev[3]; m3_eigen_values(covariance_v4(p, n, com), ev);
     const float scl = 1.0f / (ev[0] + ev[1] + ev[2]);

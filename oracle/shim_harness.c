@@ -30,7 +30,7 @@ static int mode_lower(int argc, char** argv) {
     md_script_gpu_lowered_t low = {0};
     if (!md_script_gpu_lower_sys(&low, ir, &sys, alloc)) return 3;
     FILE* f = fopen(arg_val(argc, argv, "--out", "lowered.bin"), "wb"); if (!f) return 2;
-    uint64_t np = low.num_props; fwrite("MDLOWER2", 1, 8, f); fwrite(&np, 8, 1, f);
+    uint64_t np = low.num_props; fwrite("MDLOWER3", 1, 8, f); fwrite(&np, 8, 1, f);
     for (size_t i = 0; i < low.num_props; ++i) {
         const mdgpu_property_desc_t* p = &low.props[i];
         uint64_t v[3] = { p->op, p->num_structures, p->structure_size };
@@ -43,6 +43,7 @@ static int mode_lower(int argc, char** argv) {
             fwrite(&dy.radius_min, 4, 1, f); fwrite(&dy.radius_max, 4, 1, f); fwrite(&h, 8, 1, f); fwrite(&c, 8, 1, f); if (c) fwrite(dy.and_idx, 4, c, f);
         }
         { uint64_t nb = p->num_structures_b; fwrite(&nb, 8, 1, f); if (nb && p->structure_offsets_b) fwrite(p->structure_offsets_b, 4, nb + 1, f); }
+        for (int k = 0; k < 4; ++k) { uint64_t np_k = p->arg_offsets[k] ? p->arg_parts[k] : 0; fwrite(&np_k, 8, 1, f); if (np_k) fwrite(p->arg_offsets[k], 4, np_k + 1, f); }   /* arrays of selections as one argument */
     }
     fclose(f);
     printf("{\"properties\": %zu}\n", low.num_props);

@@ -192,6 +192,27 @@ def pairs6(tmp):
     np.savez_compressed(os.path.join(HERE, "pairs6.npz"), **out)
 
 
+ARR_SCRIPT = ("da = distance(residue(1:4), residue(10)); db = distance(residue(2:9), residue(20:31)); dc = distance(residue(1:3), 40); "
+              "aa = angle(residue(1:2), residue(5:7), 30); ha = dihedral(residue(1:2), residue(3:4), residue(5:6), residue(7:9)); "
+              "ca = com(residue(1:6)); cb = com(residue(100:140)); dd = distance(com(residue(1:4)), residue(50:52));")
+
+
+def arrargs(tmp):
+    """An ARRAY of selections as ONE position argument of distance / angle / dihedral / com: the centre of the selections' centres
+    (coordinate_extract_com md_script_functions.inl:1826-1842 -> md_util_com_compute per selection, then md_util_com_compute_vec4, whose triclinic
+    branch is the one 'as written'), on the water6 frames (orthorhombic) and the tric6 frames (triclinic cell changing every frame)."""
+    out = {"script": np.array(ARR_SCRIPT)}
+    w = np.load(os.path.join(HERE, "water6.npz")); t = np.load(os.path.join(HERE, "tric6.npz"))
+    for tag, g, seed in (("w", w, "77"), ("t", t, "91")):
+        gro, raw, o = os.path.join(tmp, tag + "a.gro"), os.path.join(tmp, tag + "a.raw"), os.path.join(tmp, tag + "a.out")
+        F = g["frames"].shape[0]
+        run(SYNTH, "water-gro", "6", seed, gro); refio.write_raw_traj(raw, g["frames"], g["cells"], g["cell_flags"])
+        run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", ARR_SCRIPT, "--out", o, "--full", f"0:{F}")
+        for name, pr in refio.read_refout(o).items():
+            out[f"{tag}_{name}__dim"] = np.array(pr.dim, np.int32); out[f"{tag}_{name}__full"] = pr.full
+    np.savez_compressed(os.path.join(HERE, "arrargs.npz"), **out)
+
+
 def shapes(tmp):
     """Shape weights per structure and frame from the reference's own functions (harness mode `shapespace`: the loop body of VIAMD's shape-space
     component): 1ALA residues (15 structures of 9-12 atoms, orthorhombic, mass-weighted), water6 residues with unit weights, tric6 residues."""
@@ -333,7 +354,7 @@ if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     only = sys.argv[1:]   # e.g. `python make_golden.py water32_full water12_avg` regenerates just those
     gens = dict(water6=water6, ala50=ala50, membrane6=membrane6, tric6=tric6, tric6_rmsd=tric6_rmsd, pairs6=pairs6, shapes=shapes, xtc_cases=xtc_cases,
-                water32_full=water32_full, water12_avg=water12_avg, backbone=backbone, dyn6=dyn6)
+                water32_full=water32_full, water12_avg=water12_avg, backbone=backbone, dyn6=dyn6, arrargs=arrargs)
     with tempfile.TemporaryDirectory() as tmp:
         for name, fn in gens.items():
             if not only or name in only: fn(tmp)

@@ -139,8 +139,16 @@ def count_pairs(x, y, z, ref_idx, trg_idx, cell, cell_ext, cutoff):
 
 
 def arg_position(x, y, z, mass, arg, cell):
-    """argument of distance/angle/dihedral: int -> the atom's position, index array -> centre of mass (coordinate_extract_com)"""
+    """argument of distance/angle/dihedral: int -> the atom's position, index array -> centre of mass, list of index arrays (an ARRAY of
+    selections) -> centre of the selections' centres (coordinate_extract_com)"""
     x, y, z, mass = _f32(x), _f32(y), _f32(z), _f32(mass)
+    if isinstance(arg, list) and len(arg) > 1:
+        sels = [_i32(g) for g in arg]; off = np.zeros(len(sels) + 1, np.uint32); off[1:] = np.cumsum([len(g) for g in sels])
+        idx = np.ascontiguousarray(np.concatenate(sels), np.int32); out = np.zeros(3, np.float32)
+        lib().mdo_arg_position_parts(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(mass, C.c_float), _p(idx, C.c_int32), _p(off, C.c_uint32),
+                                     C.c_size_t(len(sels)), C.byref(cell), _p(out, C.c_float))
+        return out
+    if isinstance(arg, list): arg = arg[0]
     direct = np.ndim(arg) == 0
     idx = np.ascontiguousarray([int(arg)] if direct else arg, np.int32); out = np.zeros(3, np.float32)
     lib().mdo_arg_position(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), _p(mass, C.c_float), _p(idx, C.c_int32), C.c_size_t(len(idx)),

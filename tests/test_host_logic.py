@@ -75,9 +75,16 @@ def test_script_lowering(vb):
     c, ci, pl = vb.compile_script("c = com(residue(2)); ci = com(7); pl = plane(atom(1:9));", s)
     assert c.op == vb.OP_COM and c.com_args == 1 and list(c.idx[0]) == [3, 4, 5] and ci.com_args == 0 and list(ci.idx[0]) == [6]
     assert pl.op == vb.OP_PLANE and list(pl.idx[0]) == list(range(9))
-    for src in ("x = com(residue(1:3));", "x = plane(residue(1:3));", "x = distance(residue(1:2), 5);", "x = distance_min(residue(1:2), element('O'));"):
+    for src in ("x = plane(residue(1:3));", "x = coord_x(residue(1:3));", "x = distance_min(residue(1:2), element('O'));"):
         with pytest.raises(vb.ScriptError):   # one position per selection in the reference: not lowered, never flattened silently
             vb.compile_script(src, s)
+    # an ARRAY of selections as one position argument: the centre of the selections' centres for com / angle / dihedral (arg_offsets),
+    # the union for distance (FLAG_FLATTEN, md_script_functions.inl:680) — a com(...) inside distance included
+    ca, an, df, dcm = vb.compile_script("ca = com(residue(1:3)); an = angle(residue(1:2), 7, com(residue(3:5))); df = distance(residue(1:2), 5); dcm = distance(com(residue(1:3)), residue(4));", s)
+    assert ca.op == vb.OP_COM and list(ca.idx[0]) == list(range(9)) and list(ca.arg_offsets[0]) == [0, 3, 6, 9] and ca.com_args == 1
+    assert sorted(an.arg_offsets) == [0, 2] and list(an.arg_offsets[2]) == [0, 3, 6, 9] and list(an.idx[2]) == list(range(6, 15)) and list(an.idx[1]) == [6] and an.com_args == 5
+    assert not df.arg_offsets and list(df.idx[0]) == list(range(6)) and df.com_args == 1
+    assert not dcm.arg_offsets and list(dcm.idx[0]) == list(range(9)) and list(dcm.idx[1]) == [9, 10, 11] and dcm.com_args == 3
     rwp = vb.compile_script("rw = rdf(within(4.0, residue(2)), element('O'), 2.0:6.0);", s)[0]
     assert rwp.op == vb.OP_RDF and rwp.ref_within == 4.0 and list(rwp.idx[0]) == [3, 4, 5] and rwp.cutoff_min == 2.0 and rwp.num_structures == 0
     inc = vb.compile_script("x = dihedral(1,2,3,1) in residue(2:4);", s)[0]

@@ -25,7 +25,10 @@ SCRIPT_NEW = ("rm = rmsd(residue(1:10)); dp = distance_pair(atom(1:5), atom(20:3
               "rwt = rdf(element('O'), within(4.0, residue(1)), 6.0); rww = rdf(within(4.0, residue(1)), within(5.0, residue(2)), 6.0); vw = sdf(residue(1:20), within(6.0, residue(1:5)), 5.0); "
               "dzw = density_z(within(5.0, residue(1))); dw = distance(within(4.0, residue(1)), 200); cmw = com(within(4.0, residue(1))); dmw = distance_min(within(3.5, residue(1)), residue(30)); "
               "rwo2 = rdf(element('O') and within(5.0, residue(2)), element('H') and within(6.0, residue(3)), 5.0); aw = angle(within(2.5:5.0, residue(4)), 10, residue(7)); "
-              "cc = contact_count(residue(1:5), residue(10:40), 4.0); cc2 = contact_count(residue(3:20), element('O') and residue(50:216), 3.5);")
+              "cc = contact_count(residue(1:5), residue(10:40), 4.0); cc2 = contact_count(residue(3:20), element('O') and residue(50:216), 3.5); "
+              # an ARRAY of selections as one position argument: centre of the selections' centres for angle / dihedral / com, the union for distance (FLAG_FLATTEN)
+              "aar = angle(residue(1:2), residue(5:7), 30); har = dihedral(residue(1:2), residue(3:4), residue(5:6), residue(7:9)); car = com(residue(1:6)); "
+              "dar = distance(residue(1:4), residue(10)); ddr = distance(com(residue(1:4)), residue(50:52)); acr = angle(com(residue(1:3)), 100, residue(20));")
 
 
 def _need():
@@ -35,7 +38,7 @@ def _need():
 
 
 def _read_lowered(path):
-    b = open(path, "rb").read(); assert b[:8] == b"MDLOWER2"
+    b = open(path, "rb").read(); assert b[:8] == b"MDLOWER3"
     n, = struct.unpack_from("<Q", b, 8); off = 16; out = []
     for _ in range(n):
         name = b[off:off + 64].split(b"\0")[0].decode(); off += 64
@@ -54,7 +57,11 @@ def _read_lowered(path):
         nb, = struct.unpack_from("<Q", b, off); off += 8
         eoff = None
         if nb: eoff = np.frombuffer(b, np.uint32, nb + 1, off).copy(); off += 4 * (nb + 1)
-        out.append(dict(name=name, op=op, ns=ns, ss=ss, cmin=cmin, cmax=cmax, idx=lists, dyn=dyn, eoff=eoff))
+        parts = {}
+        for k in range(4):
+            c, = struct.unpack_from("<Q", b, off); off += 8
+            if c: parts[k] = np.frombuffer(b, np.uint32, c + 1, off).copy(); off += 4 * (c + 1)
+        out.append(dict(name=name, op=op, ns=ns, ss=ss, cmin=cmin, cmax=cmax, idx=lists, dyn=dyn, eoff=eoff, parts=parts))
     return out
 
 
@@ -84,6 +91,8 @@ def test_shim_lowering_matches_python_lowering(tmp_path):
             assert a["dyn"][k][0] == np.float32(rmin) and a["dyn"][k][1] == np.float32(rmax) and ((cand is None) == (a["dyn"][k][2] is None)), (a["name"], k)
             if cand is not None: assert np.array_equal(a["dyn"][k][2], cand), (a["name"], k)
         if b.op == vb.OP_CONTACT_COUNT: assert np.array_equal(a["eoff"], b.structure_offsets_b) and a["ns"] == b.num_structures
+        assert a["parts"].keys() == b.arg_offsets.keys(), a["name"]
+        for k, o in b.arg_offsets.items(): assert np.array_equal(a["parts"][k], o), (a["name"], k)
 
 
 @pytest.mark.gpu

@@ -437,6 +437,26 @@ def test_dynamic_selections_as_arguments_of_every_lowered_consumer(tag):
     plan.close()
 
 
+def test_array_of_selections_as_one_position_argument():
+    """angle / dihedral / com with an ARRAY of selections as one argument (residue(a:b) over several residues): the centre of the selections'
+    centres — md_util_com_compute per selection, then md_util_com_compute_vec4 (coordinate_extract_com md_script_functions.inl:1826-1842) —
+    while distance() is FLAG_FLATTEN and takes the union, com(...) inside it included. Against the reference (tests/golden/arrargs.npz),
+    orthorhombic and changing triclinic cell (whose vec4 centre goes through the scaled inverse twice, as written)."""
+    vb = _vb(); g = load_golden("arrargs.npz")
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        src = load_golden(name); sysm = vb_system(golden_system(src)); F = src["frames"].shape[0]
+        props = vb.compile_script(str(g["script"]), sysm)
+        assert {p.name: sorted(p.arg_offsets) for p in props} == {"da": [], "db": [], "dc": [], "aa": [0, 1], "ha": [0, 1, 2, 3], "ca": [0], "cb": [0], "dd": []}
+        plan = vb.Plan(sysm, props, F, batch_frames=3)
+        plan.eval_host_frames(src["frames"], [vb_cell(src["cells"][f], src["cell_flags"][f]) for f in range(F)], 0)
+        for key in ("da", "db", "dc", "dd", "ca", "cb"): assert _same(plan.property_data(key).values, g[f"{tag}_{key}__full"]), (tag, key)
+        for key in ("aa", "ha"): np.testing.assert_allclose(plan.property_data(key).values, g[f"{tag}_{key}__full"], rtol=1e-5, atol=1e-6, err_msg=f"{tag} {key}")
+        plan.close()
+    with pytest.raises(vb.MdgpuError):   # offsets that do not cover the list
+        p = vb.angle("x", [np.arange(0, 3), np.arange(3, 6)], 10, 20); p.arg_offsets[0] = np.array([0, 3, 5], np.uint32)
+        vb.Plan(sysm, [p], 2)
+
+
 @pytest.mark.parametrize("tag", ["w", "t"])
 def test_contact_count_running_totals(tag):
     """contact_count(A[], B, cutoff) (md_script_functions.inl:2756-2866) with disjoint sets — the reference's exclusion mask is then empty and its

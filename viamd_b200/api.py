@@ -74,7 +74,8 @@ class _PropertyDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("op", C.c_uint32), ("idx", C.POINTER(C.c_int32) * 4), ("idx_count", C.c_size_t * 4),
                 ("num_structures", C.c_size_t), ("structure_size", C.c_size_t), ("cutoff_min", C.c_float), ("cutoff_max", C.c_float),
                 ("structure_offsets", C.POINTER(C.c_uint32)), ("com_args", C.c_uint32), ("ref_within_radius", C.c_float), ("ref_within_min", C.c_float),
-                ("structure_offsets_b", C.POINTER(C.c_uint32)), ("num_structures_b", C.c_size_t), ("dyn", _DynArg * 4)]
+                ("structure_offsets_b", C.POINTER(C.c_uint32)), ("num_structures_b", C.c_size_t), ("dyn", _DynArg * 4),
+                ("arg_offsets", C.POINTER(C.c_uint32) * 4), ("arg_parts", C.c_uint32 * 4)]
 
 
 class _PropertyData(C.Structure):
@@ -223,6 +224,7 @@ class Property:
     ref_within_min: float = 0.0
     structure_offsets_b: Optional[np.ndarray] = None  # distance_pair: CSR groups of argument 1 (argument 0 uses structure_offsets)
     dyn: dict = field(default_factory=dict)           # {k: (radius_min, radius_max, and_idx | None)}: argument k is within([min:]max, idx[k]) [and and_idx], per frame
+    arg_offsets: dict = field(default_factory=dict)   # {k: CSR offsets}: argument k of distance / angle / dihedral / com is an ARRAY of selections (centre of their centres)
 
 
 class Within:
@@ -288,12 +290,18 @@ def in_contexts(name, op, local_idx, context_first_atoms):
 def _temporal(name, op, args):
     """each argument: an int (0-based atom index -> that atom's position) or an index array (a selection -> centre of mass,
     coordinate_extract_com md_script_functions.inl:1717)"""
-    idx, mask, dyn = [], 0, {}
+    idx, mask, dyn, parts = [], 0, {}, {}
     for k, a in enumerate(args):
         if isinstance(a, Within): idx.append(a.sel); mask |= 1 << k; dyn[k] = (a.radius_min, a.radius, a.and_idx)   # the frame's dynamic selection: its centre of mass
+        elif isinstance(a, list):   # an ARRAY of selections: the centre of the selections' centres (coordinate_extract_com :1826-1842)
+            sels = [np.asarray(g, np.int32) for g in a]; mask |= 1 << k
+            if len(sels) == 1: idx.append(sels[0])
+            else:
+                off = np.zeros(len(sels) + 1, np.uint32); off[1:] = np.cumsum([len(g) for g in sels])
+                idx.append(np.concatenate(sels).astype(np.int32)); parts[k] = off
         elif np.ndim(a) == 0: idx.append(np.asarray([int(a)], np.int32))
         else: idx.append(np.asarray(a, np.int32)); mask |= 1 << k
-    return Property(name, op, idx, com_args=mask, dyn=dyn)
+    return Property(name, op, idx, com_args=mask, dyn=dyn, arg_offsets=parts)
 
 
 def distance(name, a, b):
@@ -516,6 +524,9 @@ class Plan:
             for k, arr in enumerate(p.idx):
                 a = np.ascontiguousarray(arr, np.int32); self._keep.append(a)
                 d.idx[k] = a.ctypes.data_as(C.POINTER(C.c_int32)); d.idx_count[k] = a.size
+            for k, off in p.arg_offsets.items():
+                ao = np.ascontiguousarray(off, np.uint32); self._keep.append(ao)
+                d.arg_offsets[k] = ao.ctypes.data_as(C.POINTER(C.c_uint32)); d.arg_parts[k] = len(ao) - 1
             for k, (rmin, rmax, and_idx) in p.dyn.items():
                 d.dyn[k].radius_min = rmin; d.dyn[k].radius_max = rmax
                 if and_idx is not None:

@@ -77,6 +77,10 @@ struct ShapeArgs {                   // shape weights of n_struct structures per
     uint32_t frame0;
 };
 void launch_shape_weights(const ShapeArgs& a, int B, cudaStream_t s);
+// an ARRAY of selections as one position argument (coordinate_extract_com :1826-1842): centre of every selection -> d_parts [B][n_parts] (xyz, w = 1),
+// then md_util_com_compute_vec4 over them -> d_out[f][arg]
+void launch_arg_com_parts(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, const uint32_t* d_off, uint32_t n_parts, const float* d_mass, float4* d_parts, cudaStream_t s);
+void launch_arg_combine(const float4* d_parts, uint32_t n_parts, const mdgpu_unitcell_t* d_cells, float* d_out, int arg, int B, cudaStream_t s);
 
 struct RmsdArgs {                    // rmsd(selection) against the initial frame, one value per frame
     BatchFrames frames;

@@ -56,6 +56,7 @@ struct Prop {
     std::vector<uint32_t> h_soff; uint32_t* d_soff = nullptr;   // rdf with centre-of-mass references: CSR offsets of the groups in idx[0]
     float cutoff_min = 0.f, cutoff_max = 0.f;
     std::vector<uint32_t> h_goff[2]; uint32_t* d_goff[2] = { nullptr, nullptr };   // distance_pair: CSR groups of argument 0 / 1 (arrays of selections)
+    std::vector<uint32_t> h_aoff[4]; uint32_t* d_aoff[4] = { nullptr, nullptr, nullptr, nullptr };   // distance / angle / dihedral / com: argument k is an ARRAY of selections (centre of their centres)
     uint8_t* d_and_mask = nullptr;   // `selection and within(...)`: one byte per atom of the static side (count(within()) / rdf(within()))
     float ref_within = 0.f, ref_within_min = 0.f;   // (kept for messages) rdf reference given through the round-1 fields; folded into dyn[0]
     // Dynamic arguments: argument k is within([rmin:]rmax, h_idx[k]) [and a static selection], evaluated per frame on the device into an ascending
@@ -97,6 +98,7 @@ struct PropScratch {   // per (stream slot, property)
     float* d_com = nullptr;   // rdf with centre-of-mass references: [B][n_struct][3]
     float* d_argpos = nullptr;   // distance/angle/dihedral with selection arguments: [B][4][3]
     float* d_gpos[2] = { nullptr, nullptr };   // distance_pair with arrays of selections: [B][n_groups][3] per argument
+    float4* d_parts[4] = { nullptr, nullptr, nullptr, nullptr };   // array-of-selections arguments: [B][n_parts] centres (xyz, 1)
     uint8_t* d_flags = nullptr;  // count(within()) / rdf(within(), ...): [B][num_atoms]
     // per dynamic argument: the system-wide grid + lists of its within() query (get_spatial_acc :734), the marks and the per-frame index list
     struct DynScratch { FrameGeom* d_geom = nullptr; float* d_aabb = nullptr; CellList trg{}, ref{}; uint8_t* d_flags = nullptr; int32_t* d_idx = nullptr; uint32_t* d_n = nullptr; } dynw[4];
@@ -297,7 +299,7 @@ static void destroy_plan(mdgpu_plan* p) {
     for (auto& s : p->slots) {
         for (auto& ps : s.ps) {
             cudaFree(ps.d_geom); cudaFree(ps.d_aabb); free_cell_list(ps.trg); free_cell_list(ps.ref);
-            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_gpos[0]); cudaFree(ps.d_gpos[1]); cudaFree(ps.d_flags); for (auto& w : ps.dynw) { cudaFree(w.d_geom); cudaFree(w.d_aabb); free_cell_list(w.trg); free_cell_list(w.ref); cudaFree(w.d_flags); cudaFree(w.d_idx); cudaFree(w.d_n); } cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
+            cudaFree(ps.d_frame_bins); cudaFree(ps.d_frame_bins64); cudaFree(ps.d_sdf_xyzw); cudaFree(ps.d_sdf_ref0); cudaFree(ps.d_sdf_mats); cudaFree(ps.d_com); cudaFree(ps.d_argpos); cudaFree(ps.d_gpos[0]); cudaFree(ps.d_gpos[1]); for (auto* q : ps.d_parts) cudaFree(q); cudaFree(ps.d_flags); for (auto& w : ps.dynw) { cudaFree(w.d_geom); cudaFree(w.d_aabb); free_cell_list(w.trg); free_cell_list(w.ref); cudaFree(w.d_flags); cudaFree(w.d_idx); cudaFree(w.d_n); } cudaFree(ps.d_pair_list); cudaFree(ps.d_list_hdr); cudaFree(ps.d_list_cursor);
         }
         cudaFree(s.d_frames); if (s.h_frames) cudaFreeHost(s.h_frames); cudaFree(s.d_xtc_frames);
         cudaFree(s.d_cells); if (s.h_cells) cudaFreeHost(s.h_cells); cudaFree(s.d_err);
@@ -318,7 +320,7 @@ static void destroy_plan(mdgpu_plan* p) {
         if (pr.values_registered) cudaHostUnregister(pr.values.data());
         cudaFree(pr.d_vol_mean);
         cudaFree(pr.d_acc); cudaFree(pr.d_vol); cudaFree(pr.d_frame_total); cudaFree(pr.d_frame_min); cudaFree(pr.d_frame_max);
-        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap); cudaFree(pr.d_soff); cudaFree(pr.d_and_mask); cudaFree(pr.d_goff[0]); cudaFree(pr.d_goff[1]); cudaFree(pr.d_set_of); for (auto& dy : pr.dyn) cudaFree(dy.d_and_mask);
+        cudaFree(pr.d_frame_min64); cudaFree(pr.d_frame_max64); cudaFree(pr.d_keep); cudaFree(pr.d_keep64); cudaFree(pr.d_temporal); cudaFree(pr.d_unwrap); cudaFree(pr.d_soff); cudaFree(pr.d_and_mask); cudaFree(pr.d_goff[0]); cudaFree(pr.d_goff[1]); for (auto* q : pr.d_aoff) cudaFree(q); cudaFree(pr.d_set_of); for (auto& dy : pr.dyn) cudaFree(dy.d_and_mask);
     }
     for (auto& t : p->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     if (p->t_begin) cudaEventDestroy(p->t_begin);
@@ -380,6 +382,17 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
         if (sys->bond_conn_atom_idx) p->conn_idx.assign(sys->bond_conn_atom_idx, sys->bond_conn_atom_idx + nconn);
     }
     auto bail = [&](int code, const std::string& msg) -> mdgpu_plan* { fail(code, "%s", msg.c_str()); destroy_plan(p); return nullptr; };
+    // argument k of distance / angle / dihedral / com given as an ARRAY of selections (arg_parts[k] >= 2): idx[k] holds them back to back
+    auto take_arg_parts = [&](Prop& pr, const mdgpu_property_desc_t& d, int k) -> std::string {
+        const uint32_t n = d.arg_parts[k]; const uint32_t* off = d.arg_offsets[k];
+        if (pr.dyn[k].on) return "'" + pr.name + "': an array of selections cannot be a dynamic argument";
+        if (!off || off[0] != 0u || off[n] != pr.h_idx[k].size()) return "'" + pr.name + "': argument offsets do not cover the index list";
+        for (uint32_t g = 0; g < n; ++g) if (off[g] > off[g + 1]) return "'" + pr.name + "': argument offsets must be non-decreasing";
+        pr.h_aoff[k].assign(off, off + n + 1);
+        if (upload(&pr.d_aoff[k], pr.h_aoff[k].data(), pr.h_aoff[k].size()) != cudaSuccess) return "device allocation failed (argument offsets)";
+        pr.com_mask |= 1u << k;
+        return std::string();
+    };
     if (upload(&p->d_mass, p->h_mass.data(), p->h_mass.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (masses)");
 
     p->props.resize(num_props);
@@ -475,7 +488,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
             const int need = pr.op == MDGPU_OP_DISTANCE ? 2 : (pr.op == MDGPU_OP_ANGLE ? 3 : 4);
             if (pr.n_struct) {   // `expr in contexts` (evaluate_context md_script.c:3418): idx[k][c] = argument k's atom in context c, one value per context
-                if (d.com_args) return bail(MDGPU_ERR_UNSUPPORTED, "'" + pr.name + "': selection arguments inside a context expression are not lowered");
+                if (d.com_args || d.arg_parts[0] > 1u || d.arg_parts[1] > 1u || d.arg_parts[2] > 1u || d.arg_parts[3] > 1u) return bail(MDGPU_ERR_UNSUPPORTED, "'" + pr.name + "': selection arguments inside a context expression are not lowered");
                 for (int k = 0; k < need; ++k) if (pr.h_idx[k].size() != pr.n_struct) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': one atom per context and argument expected");
                 pr.len = pr.n_struct;
                 e = dalloc(&pr.d_temporal, num_frames * pr.len);
@@ -485,6 +498,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
                 break;
             }
             pr.com_mask = d.com_args & ((1u << need) - 1u);
+            for (int k = 0; k < need; ++k) if (d.arg_parts[k] > 1u) { const std::string er = take_arg_parts(pr, d, k); if (!er.empty()) return bail(MDGPU_ERR_INVALID_ARG, er); }
             for (int k = 0; k < need; ++k) {
                 if (pr.dyn[k].on) { pr.com_mask |= 1u << k; continue; }   // a dynamic selection is a bitfield: its centre of mass
                 if (pr.h_idx[k].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
@@ -546,6 +560,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
         case MDGPU_OP_COM: {   // com(x): a [F, 3] temporal (TI_FLOAT3)
             if (pr.h_idx[0].empty() && !pr.dyn[0].on) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
             pr.com_mask = (d.com_args & 1u) | (pr.h_idx[0].size() != 1 ? 1u : 0u) | (pr.dyn[0].on ? 1u : 0u);
+            if (d.arg_parts[0] > 1u) { const std::string er = take_arg_parts(pr, d, 0); if (!er.empty()) return bail(MDGPU_ERR_INVALID_ARG, er); }
             pr.len = 3;
             e = dalloc(&pr.d_temporal, num_frames * pr.len);
             pr.values.assign(num_frames * pr.len, 0.0f);
@@ -807,6 +822,7 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     CUDA_TRY(dalloc(&ps.d_frame_bins64, (size_t)p->B * MDGPU_DIST_BINS));
                 } else if (pr.com_mask) {
                     CUDA_TRY(dalloc(&ps.d_argpos, (size_t)p->B * 12));
+                    for (int k = 0; k < 4; ++k) if (!pr.h_aoff[k].empty()) CUDA_TRY(dalloc(&ps.d_parts[k], (size_t)p->B * (pr.h_aoff[k].size() - 1)));
                 }
             }
         }
@@ -822,6 +838,16 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
 // enqueue the property kernels of one batch whose frames are already in device memory
 // `c`: the frames are in the plan's COMPACT atom space (host ingest copied only the atoms the properties read): index lists, masses and the
 // initial frame of that space are used; otherwise the caller's full frames with global atom indices.
+// position of argument k of distance / angle / dihedral / com when it is a selection: its centre of mass (coordinate_extract_com
+// md_script_functions.inl:1717), or for an array of selections the centre of the selections' centres (:1826-1842) -> ps.d_argpos[f][k]
+static void arg_position(Prop& pr, PropScratch& ps, int k, const BatchFrames& fr, Slot& s, int32_t* const* didx, const float* dmass, DynSel dsel) {
+    if (!pr.h_aoff[k].empty()) {
+        const uint32_t n = (uint32_t)pr.h_aoff[k].size() - 1u;
+        launch_arg_com_parts(fr, s.d_cells, didx[k], pr.d_aoff[k], n, dmass, ps.d_parts[k], s.stream);
+        launch_arg_combine(ps.d_parts[k], n, s.d_cells, ps.d_argpos, k, (int)fr.count, s.stream);
+    } else launch_arg_com(fr, s.d_cells, didx[k], (uint32_t)pr.h_idx[k].size(), dmass, ps.d_argpos, k, s.stream, dsel);
+}
+
 static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t frame0, bool c) {
     std::lock_guard<std::mutex> guard(p->submit_mutex);
     const int B = (int)fr.count;
@@ -952,7 +978,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             TemporalArgs a{};
             a.frames = fr; a.cells = s.d_cells; a.op = (int)pr.op; a.out = pr.d_temporal; a.frame0 = frame0;
             a.atom[0] = c ? pr.first_c[0] : pr.h_idx[0][0]; a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
-            if (pr.com_mask & 1u) launch_arg_com(fr, s.d_cells, didx[0], (uint32_t)pr.h_idx[0].size(), dmass, ps.d_argpos, 0, s.stream, dsel[0]);
+            if (pr.com_mask & 1u) arg_position(pr, ps, 0, fr, s, didx, dmass, dsel[0]);
             launch_com_rows(a, B, s.stream);
             break; }
         case MDGPU_OP_COORD_X: case MDGPU_OP_COORD_Y: case MDGPU_OP_COORD_Z:
@@ -1001,8 +1027,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             }
             for (int k = 0; k < 4; ++k) a.atom[k] = pr.h_idx[k].empty() ? 0 : (c ? pr.first_c[k] : pr.h_idx[k][0]);
             a.pos = ps.d_argpos; a.com_mask = pr.com_mask;
-            for (int k = 0; k < 4; ++k) if (pr.com_mask & (1u << k))
-                launch_arg_com(fr, s.d_cells, didx[k], (uint32_t)pr.h_idx[k].size(), dmass, ps.d_argpos, k, s.stream, dsel[k]);
+            for (int k = 0; k < 4; ++k) if (pr.com_mask & (1u << k)) arg_position(pr, ps, k, fr, s, didx, dmass, dsel[k]);
             launch_temporal(a, B, s.stream);
             break; }
         default: break;

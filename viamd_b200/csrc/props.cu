@@ -262,6 +262,25 @@ void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, cons
     note_launch("k_arg_com", s);
 }
 
+// One warp per (frame, selection of an array argument): md_util_com_compute of that selection, stored as xyzw with w = 1 for k_arg_combine.
+__global__ void k_arg_com_parts(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ idx, const uint32_t* __restrict__ off, uint32_t n_parts,
+                                const float* __restrict__ mass, float4* __restrict__ parts /* [B][n_parts] */) {
+    const int f = blockIdx.x, lane = threadIdx.x; const uint32_t part = blockIdx.y;
+    float* o = (float*)(parts + (size_t)f * n_parts + part);
+    const uint32_t beg = off[part], count = off[part + 1] - beg;
+    if (lane == 0) o[3] = 1.0f;                                                         // vec4_from_vec3(com, 1.0f) :1840
+    if (count == 0) { if (lane < 3) o[lane] = 0.0f; return; }                           // md_util_com_compute: count == 0 -> (0, 0, 0) (md_util.c:8168)
+    const float* x = fr.xyz + (size_t)f * fr.frame_stride;
+    const float* src[3] = { x, x + fr.axis_stride, x + 2 * fr.axis_stride };
+    periodic_com_warp(src, cells[f], idx + beg, count, mass, o, lane);
+}
+
+void launch_arg_com_parts(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, const uint32_t* d_off, uint32_t n_parts, const float* d_mass, float4* d_parts, cudaStream_t s) {
+    if (!fr.count || !n_parts) return;
+    k_arg_com_parts<<<dim3(fr.count, n_parts), 32, 0, s>>>(fr, d_cells, d_idx, d_off, n_parts, d_mass, d_parts);
+    note_launch("k_arg_com_parts", s);
+}
+
 // distance / angle / dihedral on the argument positions: an atom's coordinates (single index, coordinate_extract_com :1755) or the
 // centre of mass k_arg_com left in a.pos
 // distance (:3851-3890) / angle (:4099-4114) / dihedral (:4171-4196) of up to four positions in one cell

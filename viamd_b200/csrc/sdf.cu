@@ -793,23 +793,11 @@ MDG_D void sincos_cephes4(float x, float& out_s, float& out_c) {
     out_c = __uint_as_float(__float_as_uint(__fadd_rn(y, y2)) ^ sign_bit_cos);
 }
 
-// One warp per (structure, frame): the lanes extract, lane 0 does the ordered work (float sums over the atoms in index order, double
-// covariance). Row (frame0 + f) of the property holds n_struct x (linear, planar, isotropic).
-__global__ void __launch_bounds__(32) k_shape_weights(ShapeArgs a, int B) {
-    const int f = blockIdx.y, lane = threadIdx.x;
-    const uint32_t sidx = blockIdx.x;
-    if (f >= B || sidx >= a.n_struct) return;
-    const uint32_t beg = a.soff[sidx], n = a.soff[sidx + 1] - beg;
-    float* o = a.out + ((size_t)(a.frame0 + f) * a.n_struct + sidx) * 3;
-    if (n == 0) { if (lane == 0) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; } return; }   // count == 0: the entry keeps its zero (:6029)
-    const mdgpu_unitcell_t uc = a.cells[f];
-    const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride;
-    float4* p = a.scratch_xyzw + (size_t)f * a.n_atoms_total + beg;
-    for (uint32_t k = lane; k < n; k += 32) { const int at = a.idx[beg + k]; p[k] = make_float4(x[at], x[a.frames.axis_stride + at], x[2 * a.frames.axis_stride + at], a.use_mass ? a.mass[at] : 1.0f); }
-    __syncwarp();
-    if (lane != 0) return;
+// md_util_com_compute_vec4 (md_util.c:8188-8201) of n points xyzw: com_pbc_vec4 (:8063-8162) in a cell — serial float sums of w*sin, w*cos
+// per axis in index order, 4-lane sincos, double atan2; the triclinic branch as written (in_idx == NULL: theta through the 1/2pi-scaled
+// inverse, and the result through it again) — com_vec4 (:8048) without one. One thread.
+MDG_D void com_compute_vec4(const float4* p, uint32_t n, const mdgpu_unitcell_t& uc, float com[3]) {
     const double TWO_PI_D = 2.0 * 3.1415926535897932, PI_D = 3.1415926535897932;
-    float com[3];
     if (uc.flags & MDGPU_CELL_ORTHO) {
         const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
         const float tp = (float)TWO_PI_D;
@@ -828,7 +816,6 @@ __global__ void __launch_bounds__(32) k_shape_weights(ShapeArgs a, int B) {
             double theta = PI_D; if (r2 > 1.0e-15) theta += atan2(-yy, -xx);
             com[c] = (float)((theta / TWO_PI_D) * (double)ext[c]);
         }
-        for (uint32_t k = 0; k < n; ++k) { float4 v = p[k]; v.x = deperiodize1(v.x, com[0], ext[0]); v.y = deperiodize1(v.y, com[1], ext[1]); v.z = deperiodize1(v.z, com[2], ext[2]); p[k] = v; }
     } else if (uc.flags & MDGPU_CELL_TRICLINIC) {
         const double i11 = uc.x > 0.0 ? 1.0 / uc.x : 0.0, i22 = uc.y > 0.0 ? 1.0 / uc.y : 0.0, i33 = uc.z > 0.0 ? 1.0 / uc.z : 0.0;   // md_unitcell.inl:158-176
         const double i12 = (uc.x * uc.y) > 0.0 ? -uc.xy / (uc.x * uc.y) : 0.0;
@@ -857,6 +844,34 @@ __global__ void __launch_bounds__(32) k_shape_weights(ShapeArgs a, int B) {
             double theta = PI_D; if (r2 > 1.0e-8) theta += atan2(-yy, -xx);
             com[c] = (float)(theta * (double)I[c][0] + theta * (double)I[c][1] + theta * (double)I[c][2]);   // :8158, as written
         }
+    } else {   // no cell: com_vec4, nothing to deperiodize
+        float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+        for (uint32_t k = 0; k < n; ++k) { const float4 v = p[k]; ax = ax + v.x * v.w; ay = ay + v.y * v.w; az = az + v.z * v.w; aw = aw + v.w * 1.0f; }
+        com[0] = ax / aw; com[1] = ay / aw; com[2] = az / aw;
+    }
+}
+
+// One warp per (structure, frame): the lanes extract, lane 0 does the ordered work (float sums over the atoms in index order, double
+// covariance). Row (frame0 + f) of the property holds n_struct x (linear, planar, isotropic).
+__global__ void __launch_bounds__(32) k_shape_weights(ShapeArgs a, int B) {
+    const int f = blockIdx.y, lane = threadIdx.x;
+    const uint32_t sidx = blockIdx.x;
+    if (f >= B || sidx >= a.n_struct) return;
+    const uint32_t beg = a.soff[sidx], n = a.soff[sidx + 1] - beg;
+    float* o = a.out + ((size_t)(a.frame0 + f) * a.n_struct + sidx) * 3;
+    if (n == 0) { if (lane == 0) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; } return; }   // count == 0: the entry keeps its zero (:6029)
+    const mdgpu_unitcell_t uc = a.cells[f];
+    const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride;
+    float4* p = a.scratch_xyzw + (size_t)f * a.n_atoms_total + beg;
+    for (uint32_t k = lane; k < n; k += 32) { const int at = a.idx[beg + k]; p[k] = make_float4(x[at], x[a.frames.axis_stride + at], x[2 * a.frames.axis_stride + at], a.use_mass ? a.mass[at] : 1.0f); }
+    __syncwarp();
+    if (lane != 0) return;
+    float com[3];
+    com_compute_vec4(p, n, uc, com);
+    if (uc.flags & MDGPU_CELL_ORTHO) {
+        const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
+        for (uint32_t k = 0; k < n; ++k) { float4 v = p[k]; v.x = deperiodize1(v.x, com[0], ext[0]); v.y = deperiodize1(v.y, com[1], ext[1]); v.z = deperiodize1(v.z, com[2], ext[2]); p[k] = v; }
+    } else if (uc.flags & MDGPU_CELL_TRICLINIC) {
         const float box[3][3] = { { (float)uc.x, 0.f, 0.f }, { (float)uc.xy, (float)uc.y, 0.f }, { (float)uc.xz, (float)uc.yz, (float)uc.z } };
         for (uint32_t k = 1; k < n; ++k) {   // deperiodize_triclinic from atom 1 on (:8993)
             float4 v = p[k];
@@ -864,10 +879,6 @@ __global__ void __launch_bounds__(32) k_shape_weights(ShapeArgs a, int B) {
             min_image_triclinic(d, box);
             v.x = __fadd_rn(com[0], d[0]); v.y = __fadd_rn(com[1], d[1]); v.z = __fadd_rn(com[2], d[2]); p[k] = v;
         }
-    } else {   // no cell: com_vec4, nothing to deperiodize
-        float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
-        for (uint32_t k = 0; k < n; ++k) { const float4 v = p[k]; ax = ax + v.x * v.w; ay = ay + v.y * v.w; az = az + v.z * v.w; aw = aw + v.w * 1.0f; }
-        com[0] = ax / aw; com[1] = ay / aw; com[2] = az / aw;
     }
     double C[3][3] = { { 0 } }; double ws = 0.0;   // mat3_covariance_matrix_vec4 (core/md_vec_math.c:101-156)
     for (uint32_t k = 0; k < n; ++k) {
@@ -889,6 +900,23 @@ __global__ void __launch_bounds__(32) k_shape_weights(ShapeArgs a, int B) {
     const float e0 = ev[l0], e1 = ev[l1], e2 = ev[l2];
     const float sc = 1.0f / ((e0 + e1) + e2);   // md_util_shape_weights md_util.c:9070-9076
     o[0] = (e0 - e1) * sc; o[1] = 2.0f * (e1 - e2) * sc; o[2] = 3.0f * e2 * sc;
+}
+
+// An ARRAY of selections as one position argument of distance / angle / dihedral / com: the centres k_arg_com_parts left in `parts`
+// (weight 1 each) -> md_util_com_compute_vec4 with the frame's cell (coordinate_extract_com md_script_functions.inl:1841). One thread per frame.
+__global__ void k_arg_combine(const float4* __restrict__ parts, uint32_t n_parts, const mdgpu_unitcell_t* __restrict__ cells, float* __restrict__ out /* [B][4][3] */, int arg, int B) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= B) return;
+    float com[3];
+    com_compute_vec4(parts + (size_t)f * n_parts, n_parts, cells[f], com);
+    float* o = out + ((size_t)f * 4 + arg) * 3;
+    o[0] = com[0]; o[1] = com[1]; o[2] = com[2];
+}
+
+void launch_arg_combine(const float4* d_parts, uint32_t n_parts, const mdgpu_unitcell_t* d_cells, float* d_out, int arg, int B, cudaStream_t s) {
+    if (B <= 0 || !n_parts) return;
+    k_arg_combine<<<(B + 63) / 64, 64, 0, s>>>(d_parts, n_parts, d_cells, d_out, arg, B);
+    note_launch("k_arg_combine", s);
 }
 
 void launch_shape_weights(const ShapeArgs& a, int B, cudaStream_t s) {

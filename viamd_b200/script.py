@@ -222,14 +222,18 @@ class _Parser:
             self.next(); return a, self.number()
         return 0.0, a
 
-    def index(self):
-        """argument of distance/angle/dihedral: a 1-based atom index (-> int) or a selection (-> index array, centre of mass)"""
+    def index(self, flatten=False):
+        """argument of distance/angle/dihedral/com: a 1-based atom index (-> int), a selection (-> index array, centre of mass) or an ARRAY of
+        selections (residue(a:b) over several residues standing alone -> list of index arrays: the centre of the selections' centres,
+        coordinate_extract_com :1826-1842). distance() is FLAG_FLATTEN (md_script_functions.inl:680): its arguments, com(...) inside it included,
+        are evaluated flattened -> the union."""
         if self.peek()[0] == "num":
             return int(float(self.expect("num")[1])) - 1   # md_script atom indices are 1-based
         if self.peek() == ("id", "com"):   # com(x) as an argument contributes the position x itself would (_com :4726 = coordinate_extract_com)
-            self.next(); self.expect("ch", "("); a = self.index(); self.expect("ch", ")")
+            self.next(); self.expect("ch", "("); a = self.index(flatten); self.expect("ch", ")")
             return a
-        return self.sel_or_within(single=True)
+        if self._has_within_before_comma(): return self.sel_or_within()
+        return self.selection() if flatten else self.groups_or_selection()
 
     def statement(self) -> api.Property:
         ident = self.expect("id")[1]; self.expect("ch", "=")
@@ -266,7 +270,9 @@ class _Parser:
             rlo, r, sel, cand = self.dyn_selection()
             p = api.count_within(ident, r, sel, rlo, cand)
         elif proc in ("coord_x", "coord_y", "coord_z"):
-            a = self.index(); p = api.coord(ident, "xyz".index(proc[-1]), [a] if np.ndim(a) == 0 else a)
+            a = self.index()
+            if isinstance(a, list): raise ScriptError("an array of selections as coord argument (one centre of mass per selection, coordinate_extract :1503) is not lowered")
+            p = api.coord(ident, "xyz".index(proc[-1]), [a] if np.ndim(a) == 0 else a)
         elif proc == "com":
             p = api.com(ident, self.index())
         elif proc == "plane":
@@ -274,7 +280,7 @@ class _Parser:
         elif proc == "rmsd":
             p = api.rmsd(ident, self.selection())   # an array of selections is flattened into their union (_internal_flatten_bf :4305)
         elif proc == "distance":
-            a = self.index(); self.expect("ch", ","); b = self.index(); p = api.distance(ident, a, b)
+            a = self.index(True); self.expect("ch", ","); b = self.index(True); p = api.distance(ident, a, b)
         elif proc == "angle":
             a = self.index(); self.expect("ch", ","); b = self.index(); self.expect("ch", ","); c = self.index(); p = api.angle(ident, a, b, c)
         elif proc == "dihedral":
