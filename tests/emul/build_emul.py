@@ -140,5 +140,16 @@ def build_fake_nccl() -> str:
     return out
 
 
+def build_loopback_nccl() -> str:
+    """tests/emul/build/libloopbacknccl.so: fake_nccl.cpp on real device memory (cudaMemcpy staging) — lets a one-GPU box run the multi-device plan
+    with both devices on the same GPU; needs the CUDA runtime, so it is built where it is used (the GPU tests)"""
+    out = os.path.join(HERE, "build", "libloopbacknccl.so"); src = os.path.join(HERE, "fake_nccl.cpp")
+    if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DMDG_LOOPBACK_CUDA", "-I/usr/local/cuda/include", "-o", out, src,
+                               "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart"])
+    return out
+
+
 if __name__ == "__main__":
     print(build("sdf")); print(build("props")); print(build("within", ["cells", "within"])); print(build("sdfpipe", ["cells", "sdf"])); print(build("xtc")); print(build("rdfpipe", ["cells", "props", "rdf"])); print(build_library())

@@ -1,6 +1,8 @@
 """Parity tests proper: the CUDA path (through the libmdgpu C ABI) against the golden vectors of the unmodified reference
 and against the plain-C oracle on seeded inputs. Integer work is asserted bit-exact; float temporals within 1e-5 relative
 (BASELINE.json north_star tolerance; acosf/atan2f differ in the last ulp between glibc and CUDA)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -615,3 +617,37 @@ def test_rdf_triclinic_unwrapped_coordinates_overflow_pass():
             ob, ow, ot = O.rdf_frame(*fr[f], ref, trg, ocell, 0.0, cut)
             for bins, tot in (res[0][f], res[1][f]):
                 assert tot == ot > 0 and np.array_equal(bins.astype(np.float32), ob), (len(trg), f)
+
+
+def test_two_device_plans_of_one_process_on_one_gpu_through_a_loopback_exchange(monkeypatch):
+    """SURVEY 8(e) inside the library (mdgpu_plan_options_t.num_devices = 2) on the hardware a one-GPU box offers: both "devices" are GPU 0
+    (MDGPU_ALLOW_DUPLICATE_DEVICES) and the exchange step's NCCL entry points are the loopback of tests/emul/fake_nccl.cpp (device buffers
+    staged through the host) — real NCCL refuses two ranks on one device. What runs on the device is everything else: the peer plan and its
+    stream slots, one host thread per device block, the reduce onto devices[0] with peers zeroed, frame masks merged, the fold. Results equal
+    the single-device plan's; a second sync changes nothing; evaluating the halves separately merges once."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul"))
+    import build_emul
+    from test_emulated_library import SCRIPT_MIX, _mix_results
+    import viamd_b200.api as api
+    emulated = "emul" in os.path.basename(api.LIB_PATH)   # (this file's tests also run on the CPU emulation of the library: host-memory exchange there)
+    monkeypatch.setenv("MDGPU_ALLOW_DUPLICATE_DEVICES", "1"); monkeypatch.setenv("MDGPU_NCCL_LIB", build_emul.build_fake_nccl() if emulated else build_emul.build_loopback_nccl())
+    vb = _vb(); g = load_golden("water6.npz"); sysm = vb_system(golden_system(g)); F = g["frames"].shape[0]
+    cells = [vb_cell(g["cells"][f], g["cell_flags"][f]) for f in range(F)]
+    def same(a, b):
+        assert a.keys() == b.keys()
+        for k in a: assert np.array_equal(a[k], b[k]), k
+    one = vb.Plan(sysm, vb.compile_script(SCRIPT_MIX, sysm), F, keep_frame_results=True); one.set_initial_frame(*g["frames"][0], cells[0])
+    one.eval_host_frames(g["frames"], cells, 0); want = _mix_results(one); one.close()
+    for src in ("host", "traj"):
+        plan = vb.Plan(sysm, vb.compile_script(SCRIPT_MIX, sysm), F, keep_frame_results=True, devices=[0, 0])
+        plan.set_initial_frame(*g["frames"][0], cells[0])
+        if src == "host": plan.eval_host_frames(g["frames"], cells, 0)
+        else: assert plan.eval_frame_range(vb.ArrayTrajectory(g["frames"], cells), 0, F, loader_threads=2)
+        same(want, _mix_results(plan)); plan.sync(); same(want, _mix_results(plan))
+        assert plan.exchange_stats()[1] == 1
+        bins, tot = plan.frame_counts("r", F - 1); assert tot == int(bins.sum()) > 0       # a frame the second plan evaluated
+        plan.clear()
+        plan.eval_host_frames(g["frames"][:2], cells[:2], 0); plan.sync(); plan.eval_host_frames(g["frames"][2:], cells[2:], 2)
+        same(want, _mix_results(plan))
+        plan.close()
