@@ -313,6 +313,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-iso", action="store_true")
+    # rehearsal switches for the N>1 flow on a ONE-GPU machine (never set by the driver): every rank on cuda:0 and gloo instead of NCCL, which refuses
+    # two ranks on one device. Everything else — torchrun environment, sharding, barriers, the exchange step, max over ranks, rank-0 line — is the real flow.
+    ap.add_argument("--dist-backend", default="nccl", choices=["nccl", "gloo"])
+    ap.add_argument("--one-device", action="store_true")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -324,11 +328,13 @@ def main():
     from viamd_b200 import dist as vdist
 
     rank, local_rank, world = dist_env()
+    dev = 0 if args.one_device else local_rank
     if world > 1:
         import torch.distributed as tdist
-        torch.cuda.set_device(local_rank)
-        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = local_rank
+        torch.cuda.set_device(dev)
+        if args.dist_backend == "nccl": tdist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+        else: tdist.init_process_group("gloo")
+    small = f"cuda:{dev}" if args.dist_backend == "nccl" else "cpu"   # where the few scalars exchanged between ranks live (gloo gathers CPU tensors only)
     if vb.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
     # this rank's host side (pinned staging, ingest threads, this thread) next to its GPU: GPU0-3 / GPU4-7 hang off different NUMA nodes
@@ -380,10 +386,10 @@ def main():
     launches = vb.launch_count()
     ms_rank = ms_dev; per_rank_ms = [ms_dev]; per_rank_ar = [ms_allreduce]
     if world > 1:
-        t = torch.tensor([ms_dev, ms_allreduce], dtype=torch.float64, device=f"cuda:{dev}")
+        t = torch.tensor([ms_dev, ms_allreduce], dtype=torch.float64, device=small)
         g = [torch.zeros_like(t) for _ in range(world)]; tdist.all_gather(g, t)
         per_rank_ms = [float(x[0]) for x in g]; per_rank_ar = [float(x[1]) for x in g]; ms_dev = max(per_rank_ms)
-        t = torch.tensor([float(launches)], dtype=torch.float64, device=f"cuda:{dev}")
+        t = torch.tensor([float(launches)], dtype=torch.float64, device=small)
         tdist.all_reduce(t, op=tdist.ReduceOp.SUM); launches = int(t.item())
     value = world * K * FPS / (ms_dev * 1e-3)
     checks = {}
@@ -419,7 +425,7 @@ def main():
         dt = time.perf_counter() - t0
         per_rank_e2e = [dt]
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{dev}")
+            t = torch.tensor([dt], dtype=torch.float64, device=small)
             g = [torch.zeros_like(t) for _ in range(world)]; tdist.all_gather(g, t); per_rank_e2e = [float(x[0]) for x in g]; dt = max(per_rank_e2e)
         d2h = sum((2 * 1024 * 4) if plan.property_data(n).weights is not None else plan.property_data(n).values.size * 4 for n in cfg["results"])
         e2e = {"value": world * Ke * FPS / dt, "unit": UNIT, "h2d_bytes_per_step": FPS * 3 * atoms_copied * 4, "d2h_bytes_per_step": d2h, "steps": Ke,
@@ -500,6 +506,8 @@ def main():
             "checks": checks,
             "roofline": roof,
         }
+        if args.one_device or args.dist_backend != "nccl":
+            line["config"]["rehearsal"] = "NOT a multi-GPU measurement: every rank on cuda:0, ranks exchange through %s" % args.dist_backend
         if world > 1:
             line["per_rank"] = {"device_ms": per_rank_ms, "allreduce_ms": per_rank_ar, "note": "device_ms: CUDA-event time of the timed region on each rank (the value uses the max); allreduce_ms: host time of the one exchange step"}
         if e2e:
