@@ -204,7 +204,7 @@ typedef struct mdgpu_plan mdgpu_plan;
 typedef struct mdgpu_plan_options_t {
     int      device;              /* CUDA device ordinal */
     uint32_t batch_frames;        /* frames per launch batch; 0 = default (one per SM) */
-    uint32_t num_streams;         /* CUDA streams the frame loop is dispatched onto; 0 = default (4) */
+    uint32_t num_streams;         /* CUDA streams (slots) the frame loop is dispatched onto; 0 = default (6), at most 8 */
     uint32_t keep_frame_results;  /* 1: retain raw per-frame integer bins of distributions (parity tests) */
     uint32_t cell_capacity;       /* cells per frame the cell lists are sized for; 0 = 2x the initial frame's grid */
     uint32_t rdf_variant;         /* rdf pair-kernel variant, all bit-identical in their results: 0 = default (packed FP32x2, 4 CTAs/SM), 1 = scalar kernel

@@ -372,7 +372,9 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
     p->axis_stride = (sys->num_atoms + 3) & ~(size_t)3;
     p->B = o.batch_frames ? o.batch_frames : (uint32_t)p->sm_count;
     if (p->B > 4096) p->B = 4096;
-    p->S = o.num_streams ? o.num_streams : 4; if (p->S > 8) p->S = 8;   // 4 slots: copies of batches k+2, k+3 overlap the kernels of k, k+1 (2 left the copy engine idle a quarter of the time; 4 vs 3: +0.7 %, profiles/r2_04_kernel_ab.json)
+    // 6 slots: host ingest end to end 50.0 k frames/s against 49.2 k with 4 and 50.0 k with 8 (device-resident frames: 52.0 / 52.5 / 51.7 k), profiles/r2_17_streams_ab.json;
+    // 2 left the copy engine idle a third of the time (round 1, profiles/r01g_e2e_streams.txt)
+    p->S = o.num_streams ? o.num_streams : 6; if (p->S > 8) p->S = 8;
     p->keep = o.keep_frame_results != 0; p->cell_cap = o.cell_capacity; p->rdf_variant = o.rdf_variant;
     p->ingest_mode = o.ingest_mode; p->ingest_threads = o.ingest_threads;
     p->h_mass.assign(sys->num_atoms, 1.0f);
