@@ -213,6 +213,24 @@ def arrargs(tmp):
     np.savez_compressed(os.path.join(HERE, "arrargs.npz"), **out)
 
 
+BIGCUT_SCRIPT = "r1 = rdf(element('O'), element('O'), 12.0); r2 = rdf(element('O'), element('H'), 17.0); v = sdf(residue(1:10), element('O'), 12.0); r4 = rdf(residue(1:20), element('H'), 11.0);"
+
+
+def bigcut6(tmp):
+    """Cutoffs beyond half the box (12, 17 and 11 A in the 18.6 A water6 / tric6 boxes): the neighbour reach grows to 2 - 3 cells per axis, a pair is
+    met through several periodic images and the reference's single wrap decides which of them count (md_spatial_acc.c:1724-1755). (Beyond the box
+    length the reference itself crashes: rdf(..., 25.0) segfaults there, so that regime has no parity to pin.)"""
+    out = {"script": np.array(BIGCUT_SCRIPT)}
+    w = np.load(os.path.join(HERE, "water6.npz")); t = np.load(os.path.join(HERE, "tric6.npz")); F = 2
+    for tag, g, seed in (("w", w, "77"), ("t", t, "91")):
+        gro, raw, o = os.path.join(tmp, tag + "b.gro"), os.path.join(tmp, tag + "b.raw"), os.path.join(tmp, tag + "b.out")
+        run(SYNTH, "water-gro", "6", seed, gro); refio.write_raw_traj(raw, g["frames"][:F], g["cells"][:F], g["cell_flags"][:F])
+        run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", BIGCUT_SCRIPT, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
+        sub = {}; pack(sub, refio.read_refout(o), list(range(F)))
+        for k, v in sub.items(): out[f"{tag}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "bigcut6.npz"), **out)
+
+
 def shapes(tmp):
     """Shape weights per structure and frame from the reference's own functions (harness mode `shapespace`: the loop body of VIAMD's shape-space
     component): 1ALA residues (15 structures of 9-12 atoms, orthorhombic, mass-weighted), water6 residues with unit weights, tric6 residues."""
@@ -354,7 +372,7 @@ if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     only = sys.argv[1:]   # e.g. `python make_golden.py water32_full water12_avg` regenerates just those
     gens = dict(water6=water6, ala50=ala50, membrane6=membrane6, tric6=tric6, tric6_rmsd=tric6_rmsd, pairs6=pairs6, shapes=shapes, xtc_cases=xtc_cases,
-                water32_full=water32_full, water12_avg=water12_avg, backbone=backbone, dyn6=dyn6, arrargs=arrargs)
+                water32_full=water32_full, water12_avg=water12_avg, backbone=backbone, dyn6=dyn6, arrargs=arrargs, bigcut6=bigcut6)
     with tempfile.TemporaryDirectory() as tmp:
         for name, fn in gens.items():
             if not only or name in only: fn(tmp)

@@ -437,6 +437,25 @@ def test_dynamic_selections_as_arguments_of_every_lowered_consumer(tag):
     plan.close()
 
 
+def test_cutoffs_beyond_half_the_box():
+    """tests/golden/bigcut6.npz: rdf (12, 17, 11 A; plain and centre-of-mass references) and sdf (12 A) in the 18.6 A boxes — neighbour reach of 2 - 3
+    cells, pairs met through several periodic images — bins and voxels equal to the reference's, orthorhombic and changing triclinic cell."""
+    vb = _vb(); g = load_golden("bigcut6.npz")
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        src = load_golden(name); sysm = vb_system(golden_system(src)); F = 2
+        plan = vb.Plan(sysm, vb.compile_script(str(g["script"]), sysm), F, keep_frame_results=True)
+        cells = [vb_cell(src["cells"][f], src["cell_flags"][f]) for f in range(F)]
+        plan.set_initial_frame(*src["frames"][0], cells[0]); plan.eval_host_frames(src["frames"][:F], cells, 0)
+        for key in ("r1", "r2", "r4"):
+            for f in range(F):
+                bins, tot = plan.frame_counts(key, f); ref = g[f"{tag}_{key}__pf"][f, :1024]
+                assert np.array_equal(bins.astype(np.float32), ref) and tot == int(ref.sum()) > 0, (tag, key, f)
+        vol = np.zeros(128 ** 3, np.float32)
+        for f in range(F): vol += dense_from_sparse(g[f"{tag}_v__pf{f}_idx"], g[f"{tag}_v__pf{f}_val"])
+        assert np.array_equal(plan.counts("v").astype(np.float32), vol) and vol.sum() > 0, tag
+        plan.close()
+
+
 def test_array_of_selections_as_one_position_argument():
     """angle / dihedral / com with an ARRAY of selections as one argument (residue(a:b) over several residues): the centre of the selections'
     centres — md_util_com_compute per selection, then md_util_com_compute_vec4 (coordinate_extract_com md_script_functions.inl:1826-1842) —
