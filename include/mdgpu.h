@@ -177,7 +177,9 @@ typedef struct mdgpu_property_desc_t {
     uint32_t com_args;                   /* distance/angle/dihedral: bit k = argument k is a selection (centre of mass even for one atom) */
     float ref_within_radius;             /* rdf: > 0 -> the reference argument was within(radius, idx[0]): the dynamic selection is evaluated per frame */
     float ref_within_min;                /* ... within(min:radius, idx[0]) (_within_expl_frng :2609); 0 for the plain form */
-    const uint32_t* structure_offsets_b; /* distance_pair: CSR groups of argument 1 when it was an array of selections (argument 0 uses structure_offsets) */
+    const uint32_t* structure_offsets_b; /* distance_pair: CSR groups of argument 1 when it was an array of selections (argument 0 uses structure_offsets);
+                                          * rdf: the TARGET was an array of num_structures_b selections (idx[1] back to back): their centres of mass are the
+                                          * target points (compute_rdf md_script_functions.inl:5293-5302); contact_count: the exclusion CSR */
     size_t num_structures_b;
     mdgpu_dynamic_arg_t dyn[4];          /* per argument: a dynamic selection (see above). Consumers: rdf reference and / or target, sdf target, density_x/_y/_z,
                                           * distance / angle / dihedral / com (the centre of mass of the frame's selection), distance_min / _max, count().

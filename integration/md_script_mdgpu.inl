@@ -188,8 +188,9 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         {
             size_t tsets = 0;
             if ((n = mdgpu__lower_sel_arg(out, 1, args[1], &tsets, alloc)) < 0) goto dynamic;
-            if (!(out->dyn[1].radius_max > 0.0f) && args[1]->data.type.base_type == TYPE_BITFIELD && tsets > 1) {   /* compute_rdf would use one centre of mass per bitfield (coordinate_extract) */
-                MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections as rdf target (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false;
+            if (!(out->dyn[1].radius_max > 0.0f) && args[1]->data.type.base_type == TYPE_BITFIELD && tsets > 1) {   /* one centre of mass per bitfield is the target point (coordinate_extract :1503, compute_rdf :5299) */
+                if (wnode) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': a dynamic reference set with an array of selections as target is not lowered", STR_ARG(ident)); return false; }
+                out->structure_offsets_b = mdgpu__arg_part_offsets(args[1], alloc); out->num_structures_b = tsets;
             }
         }
         if (!(args[2]->flags & FLAG_CONSTANT)) goto dynamic;

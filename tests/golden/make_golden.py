@@ -231,6 +231,26 @@ def bigcut6(tmp):
     np.savez_compressed(os.path.join(HERE, "bigcut6.npz"), **out)
 
 
+RDFTRG_SCRIPT = ("ra = rdf(residue(1:20), residue(10:30), 5.0); rb = rdf(element('O'), residue(10:60), 6.0); rc = rdf(residue(1:40), residue(1:40), 2.0:8.0); "
+                 "rd = rdf(atom(1:60), residue(1:20), 4.0);")
+
+
+def rdftrg6(tmp):
+    """An ARRAY of selections as rdf TARGET: one centre of mass per selection is the target point (coordinate_extract md_script_functions.inl:1503 ->
+    extract_com :857, compute_rdf :5293-5302). With an array as reference too, the exclusion test reads bit j of reference group i's mask with j the
+    target's ORDINAL (rdf_cb_excl_mask :5252) — reproduced as written. water6 (orthorhombic) and tric6 (triclinic, cell changing every frame)."""
+    out = {"script": np.array(RDFTRG_SCRIPT)}
+    w = np.load(os.path.join(HERE, "water6.npz")); t = np.load(os.path.join(HERE, "tric6.npz"))
+    for tag, g, seed in (("w", w, "77"), ("t", t, "91")):
+        gro, raw, o = os.path.join(tmp, tag + "g.gro"), os.path.join(tmp, tag + "g.raw"), os.path.join(tmp, tag + "g.out")
+        F = g["frames"].shape[0]
+        run(SYNTH, "water-gro", "6", seed, gro); refio.write_raw_traj(raw, g["frames"], g["cells"], g["cell_flags"])
+        run(HARNESS, "eval", "--sys", gro, "--traj", f"raw:{raw}", "--script", RDFTRG_SCRIPT, "--out", o, "--perframe", f"0:{F}", "--full", f"0:{F}")
+        sub = {}; pack(sub, refio.read_refout(o), list(range(F)))
+        for k, v in sub.items(): out[f"{tag}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "rdftrg6.npz"), **out)
+
+
 def shapes(tmp):
     """Shape weights per structure and frame from the reference's own functions (harness mode `shapespace`: the loop body of VIAMD's shape-space
     component): 1ALA residues (15 structures of 9-12 atoms, orthorhombic, mass-weighted), water6 residues with unit weights, tric6 residues."""
@@ -372,7 +392,7 @@ if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     only = sys.argv[1:]   # e.g. `python make_golden.py water32_full water12_avg` regenerates just those
     gens = dict(water6=water6, ala50=ala50, membrane6=membrane6, tric6=tric6, tric6_rmsd=tric6_rmsd, pairs6=pairs6, shapes=shapes, xtc_cases=xtc_cases,
-                water32_full=water32_full, water12_avg=water12_avg, backbone=backbone, dyn6=dyn6, arrargs=arrargs, bigcut6=bigcut6)
+                water32_full=water32_full, water12_avg=water12_avg, backbone=backbone, dyn6=dyn6, arrargs=arrargs, bigcut6=bigcut6, rdftrg6=rdftrg6)
     with tempfile.TemporaryDirectory() as tmp:
         for name, fn in gens.items():
             if not only or name in only: fn(tmp)

@@ -81,6 +81,21 @@ def rdf_frame(x, y, z, ref_idx, trg_idx, cell: UnitCell, min_cutoff, max_cutoff,
     return bins, w, int(total)
 
 
+def rdf_frame_args(x, y, z, mass, ref, trg, cell, min_cutoff, max_cutoff):
+    """rdf of one frame with either argument an atom index array or a LIST of index arrays (an array of selections: one centre of mass per selection,
+    extract_com; as reference also the exclusion masks, tested against the target's index — its ORDINAL when the targets are centres of mass,
+    rdf_cb_excl_mask md_script_functions.inl:5252). The target points are handed to the oracle as coordinate arrays of their own."""
+    x, y, z = _f32(x), _f32(y), _f32(z)
+    eo = ei = None
+    if isinstance(ref, list): rp, eo, ei = group_com(x, y, z, mass, ref)
+    else: r = _i32(ref); rp = np.ascontiguousarray(np.stack([x[r], y[r], z[r]], axis=1), np.float32)
+    if isinstance(trg, list):
+        tp, _, _ = group_com(x, y, z, mass, trg)
+        tx, ty, tz = (np.ascontiguousarray(tp[:, k]) for k in range(3)); ti = np.arange(len(trg), dtype=np.int32)
+    else: tx, ty, tz, ti = x, y, z, _i32(trg)
+    return rdf_frame(tx, ty, tz, None, ti, cell, min_cutoff, max_cutoff, ref_pos=rp, excl_off=eo, excl_idx=ei)
+
+
 def group_com(x, y, z, mass, groups):
     """groups: list of int32 index arrays -> (AoS positions [n,3], offsets, concatenated indices)"""
     x, y, z, mass = _f32(x), _f32(y), _f32(z), _f32(mass)

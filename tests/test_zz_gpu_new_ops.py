@@ -437,6 +437,25 @@ def test_dynamic_selections_as_arguments_of_every_lowered_consumer(tag):
     plan.close()
 
 
+def test_rdf_with_an_array_of_selections_as_target():
+    """tests/golden/rdftrg6.npz: rdf whose target (and in two cases also the reference) is an array of selections — the targets are the selections'
+    centres of mass, binned from an AoS stream; exclusion by the target's ordinal as the reference has it. Per-frame bins, pair totals and the
+    last frame's weights equal the reference's, orthorhombic and changing triclinic cell."""
+    vb = _vb(); g = load_golden("rdftrg6.npz")
+    for tag, name in (("w", "water6.npz"), ("t", "tric6.npz")):
+        src = load_golden(name); sysm = vb_system(golden_system(src)); F = src["frames"].shape[0]
+        props = vb.compile_script(str(g["script"]), sysm)
+        assert [p.structure_offsets_b is not None for p in props] == [True] * 4 and [p.num_structures for p in props] == [20, 0, 40, 0]
+        plan = vb.Plan(sysm, props, F, keep_frame_results=True, batch_frames=3)
+        plan.eval_host_frames(src["frames"], [vb_cell(src["cells"][f], src["cell_flags"][f]) for f in range(F)], 0)
+        for key in ("ra", "rb", "rc", "rd"):
+            for f in range(F):
+                bins, tot = plan.frame_counts(key, f); ref = g[f"{tag}_{key}__pf"][f, :1024]
+                assert np.array_equal(bins.astype(np.float32), ref) and tot == int(ref.sum()) > 0, (tag, key, f)
+            assert np.array_equal(plan.property_data(key).weights, g[f"{tag}_{key}__pf"][F - 1, 1024:]), (tag, key)
+        plan.close()
+
+
 def test_cutoffs_beyond_half_the_box():
     """tests/golden/bigcut6.npz: rdf (12, 17, 11 A; plain and centre-of-mass references) and sdf (12 A) in the 18.6 A boxes — neighbour reach of 2 - 3
     cells, pairs met through several periodic images — bins and voxels equal to the reference's, orthorhombic and changing triclinic cell."""

@@ -245,10 +245,22 @@ def _split_dyn(args):
     return idx, dyn
 
 
+def _trg_groups(trg):
+    """a target that is a LIST of index arrays is an ARRAY of selections: one centre of mass per selection is the target point (coordinate_extract
+    md_script_functions.inl:1503 -> extract_com :857; compute_rdf :5293-5302). Returns (concatenated indices | the argument itself, CSR offsets | None)."""
+    if not isinstance(trg, list): return trg, None
+    groups = [np.asarray(g, np.int32) for g in trg]
+    if len(groups) == 1: return groups[0], None
+    off = np.zeros(len(groups) + 1, np.uint32); off[1:] = np.cumsum([len(g) for g in groups])
+    return np.concatenate(groups).astype(np.int32), off
+
+
 def rdf(name, ref_idx, trg_idx, cutoff, cutoff_min=0.0):
-    """ref_idx / trg_idx: atom index arrays, or Within(...) for a selection evaluated per frame"""
+    """ref_idx / trg_idx: atom index arrays, or Within(...) for a selection evaluated per frame; trg_idx may be a list of index arrays (an array of
+    selections: their centres of mass are the targets)"""
+    trg_idx, toff = _trg_groups(trg_idx)
     idx, dyn = _split_dyn([ref_idx, trg_idx])
-    return Property(name, OP_RDF, idx, cutoff_min=float(cutoff_min), cutoff_max=float(cutoff), dyn=dyn)
+    return Property(name, OP_RDF, idx, cutoff_min=float(cutoff_min), cutoff_max=float(cutoff), dyn=dyn, structure_offsets_b=toff)
 
 
 def rdf_within(name, radius, sel_idx, trg_idx, cutoff, cutoff_min=0.0, radius_min=0.0, and_idx=None):
@@ -264,8 +276,9 @@ def rdf_com(name, groups, trg_idx, cutoff, cutoff_min=0.0):
     and a group's own atoms are excluded from its pairs (compute_rdf md_script_functions.inl:5274-5275, rdf_cb_excl_mask :5243)."""
     groups = [np.asarray(g, np.int32) for g in groups]
     off = np.zeros(len(groups) + 1, np.uint32); off[1:] = np.cumsum([len(g) for g in groups])
+    trg_idx, toff = _trg_groups(trg_idx)   # targets may be an array of selections too: with the reference's exclusion test on the target ORDINAL (rdf_cb_excl_mask :5252)
     return Property(name, OP_RDF, [np.concatenate(groups).astype(np.int32), np.asarray(trg_idx, np.int32)], num_structures=len(groups),
-                    cutoff_min=float(cutoff_min), cutoff_max=float(cutoff), structure_offsets=off)
+                    cutoff_min=float(cutoff_min), cutoff_max=float(cutoff), structure_offsets=off, structure_offsets_b=toff)
 
 
 def sdf(name, structures, trg_idx, cutoff):

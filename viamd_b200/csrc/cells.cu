@@ -132,14 +132,16 @@ MDG_D void atomic_max_f(float* addr, float v) {
     while (__int_as_float(old) < v) { const int assumed = old; old = atomicCAS(ia, assumed, __float_as_int(v)); if (old == assumed) break; }
 }
 
-__global__ void k_aabb(BatchFrames fr, const int32_t* __restrict__ idx_, uint32_t n_, float* __restrict__ aabb /* [B][6], zero-initialised */, DynSel dyn) {
+__global__ void k_aabb(BatchFrames fr, const int32_t* __restrict__ idx_, uint32_t n_, float* __restrict__ aabb /* [B][6], zero-initialised */, DynSel dyn,
+                       const float* __restrict__ aos = nullptr /* [B][n][3]: positions given directly (centres of mass of groups) instead of atoms */) {
     const int f = blockIdx.y;
     const int32_t* __restrict__ idx = sel_list(idx_, dyn, f); const uint32_t n = sel_count(n_, dyn, f);
     const float* x = fr.xyz + (size_t)f * fr.frame_stride; const float* y = x + fr.axis_stride; const float* z = y + fr.axis_stride;
     float mn[3] = { 0.f, 0.f, 0.f }, mx[3] = { 0.f, 0.f, 0.f };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int a = idx ? idx[i] : (int)i;
-        const float r[3] = { x[a], y[a], z[a] };
+        float r[3];
+        if (aos) { const float* q = aos + ((size_t)f * n + i) * 3; r[0] = q[0]; r[1] = q[1]; r[2] = q[2]; }
+        else { const int a = idx ? idx[i] : (int)i; r[0] = x[a]; r[1] = y[a]; r[2] = z[a]; }
         for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], r[k]); mx[k] = fmaxf(mx[k], r[k]); }
     }
     for (int k = 0; k < 3; ++k) {
@@ -259,12 +261,12 @@ void launch_geom(const mdgpu_unitcell_t* d_cells, const float* d_aabb, FrameGeom
     note_launch("k_frame_geom", s);
 }
 
-void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float* d_aabb, cudaStream_t s, DynSel dyn) {
+void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float* d_aabb, cudaStream_t s, DynSel dyn, const float* d_aos) {
     cudaMemsetAsync(d_aabb, 0, sizeof(float) * 6 * fr.count, s);
     if (dyn.n) n = dyn.stride;   // upper bound of a per-frame list
     if (!n) return;
     dim3 grid(min((n + 255u) / 256u, 64u), fr.count);
-    k_aabb<<<grid, 256, 0, s>>>(fr, d_idx, n, d_aabb, dyn);
+    k_aabb<<<grid, 256, 0, s>>>(fr, d_idx, n, d_aabb, dyn, d_aos);
     note_launch("k_aabb", s);
 }
 

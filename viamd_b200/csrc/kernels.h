@@ -8,7 +8,7 @@ namespace mdg {
 void host_frame_geom(FrameGeom* g, const mdgpu_unitcell_t* uc, double cell_ext, double cutoff, const float* aabb, uint32_t cap);
 void launch_geom(const mdgpu_unitcell_t* d_cells, const float* d_aabb, FrameGeom* d_geom, double cell_ext, double cutoff, uint32_t cap,
                  int B, int* d_err, cudaStream_t s);
-void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float* d_aabb, cudaStream_t s, DynSel dyn = DynSel{ nullptr, nullptr, 0 });
+void launch_aabb(const BatchFrames& fr, const int32_t* d_idx, uint32_t n, float* d_aabb, cudaStream_t s, DynSel dyn = DynSel{ nullptr, nullptr, 0 }, const float* d_aos = nullptr);
 void launch_cell_list(int mode, const BatchFrames& fr, const int32_t* d_idx, const float* d_aos, uint32_t n, const FrameGeom* d_geom,
                       const CellList& cl, int store_linear_idx, cudaStream_t s, DynSel dyn = DynSel{ nullptr, nullptr, 0 });
 

@@ -88,6 +88,7 @@ struct Prop {
     bool needs_cells() const { return op == MDGPU_OP_RDF || op == MDGPU_OP_SDF || op == MDGPU_OP_CONTACT_COUNT; }
     uint32_t* d_set_of = nullptr;   // contact_count: set of every atom of the concatenated A list
     int share_trg = -1;   // index of an earlier property with the same target selection and cutoff: its target cell list is reused
+    size_t trg_groups = 0;   // rdf: the target argument was an ARRAY of selections: one centre of mass per selection is the target point (h_goff[1] = their CSR offsets in idx[1])
 };
 
 struct PropScratch {   // per (stream slot, property)
@@ -450,6 +451,14 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
                 for (size_t k = 0; k < pr.n_struct; ++k) if (pr.h_soff[k] > pr.h_soff[k + 1]) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': structure offsets must be non-decreasing");
                 if (upload(&pr.d_soff, pr.h_soff.data(), pr.h_soff.size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (structure offsets)");
             }
+            if (d.num_structures_b) {   // targets = centres of mass of atom groups (coordinate_extract :1503 -> extract_com :857 on an array of selections, compute_rdf :5293-5302)
+                const size_t n = d.num_structures_b; const uint32_t* off = d.structure_offsets_b;
+                if (pr.dyn[1].on) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': an array of selections cannot be a dynamic target");
+                if (!off || off[0] != 0u || off[n] != pr.h_idx[1].size()) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': target group offsets do not cover idx[1]");
+                for (size_t k = 0; k < n; ++k) if (off[k] > off[k + 1]) return bail(MDGPU_ERR_INVALID_ARG, "rdf '" + pr.name + "': target group offsets must be non-decreasing");
+                pr.h_goff[1].assign(off, off + n + 1); pr.trg_groups = n;
+                if (upload(&pr.d_goff[1], pr.h_goff[1].data(), pr.h_goff[1].size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (target group offsets)");
+            }
             e = dalloc(&pr.d_acc, MDGPU_DIST_BINS);
             if (e == cudaSuccess) e = dalloc(&pr.d_frame_total, num_frames);
             if (e == cudaSuccess) e = dalloc(&pr.d_frame_min, num_frames);
@@ -645,7 +654,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
     }
     for (size_t i = 0; i < num_props; ++i) for (size_t j = 0; j < i; ++j) {
         Prop& a = p->props[i]; Prop& b = p->props[j];
-        if (a.needs_cells() && b.needs_cells() && b.share_trg < 0 && a.cutoff_max == b.cutoff_max && a.h_idx[1] == b.h_idx[1] && !a.dyn[1].on && !b.dyn[1].on) { a.share_trg = (int)j; break; }
+        if (a.needs_cells() && b.needs_cells() && b.share_trg < 0 && a.cutoff_max == b.cutoff_max && a.h_idx[1] == b.h_idx[1] && !a.dyn[1].on && !b.dyn[1].on && !a.trg_groups && !b.trg_groups) { a.share_trg = (int)j; break; }
     }
     {   // compact atom space: what host ingest has to copy
         const size_t N = sys->num_atoms; bool all_atoms = false;
@@ -787,7 +796,8 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                 }
                 if (pr.needs_cells() && pr.share_trg < 0) {
                     CUDA_TRY(dalloc(&ps.d_geom, p->B)); CUDA_TRY(dalloc(&ps.d_aabb, (size_t)6 * p->B));
-                    int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)(pr.dyn[1].on ? p->num_atoms : pr.h_idx[1].size()), cap); if (rc) return rc;
+                    int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)(pr.dyn[1].on ? p->num_atoms : (pr.trg_groups ? pr.trg_groups : pr.h_idx[1].size())), cap); if (rc) return rc;
+                    if (pr.trg_groups) CUDA_TRY(dalloc(&ps.d_gpos[1], (size_t)p->B * pr.trg_groups * 3));
                 }
                 if (pr.op == MDGPU_OP_RDF) {
                     int rc = alloc_cell_list(ps.ref, p->B, (uint32_t)(pr.dyn[0].on ? p->num_atoms : (pr.n_struct ? pr.n_struct : pr.h_idx[0].size())), cap); if (rc) return rc;
@@ -883,9 +893,16 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
         }
         if (pr.needs_cells() && pr.share_trg < 0) {
             const float* aabb = nullptr;
+            if (pr.trg_groups) {   // the target points are the groups' centres of mass: an AoS stream, j = position index (compute_rdf :5299-5301)
+                launch_group_com(fr, didx[1], pr.d_goff[1], (uint32_t)pr.trg_groups, dmass, ps.d_gpos[1], s.stream);
+                if (!all_pbc) { launch_aabb(fr, nullptr, (uint32_t)pr.trg_groups, ps.d_aabb, s.stream, DynSel{ nullptr, nullptr, 0 }, ps.d_gpos[1]); aabb = ps.d_aabb; }
+                launch_geom(s.d_cells, aabb, ps.d_geom, (double)pr.cutoff_max, (double)pr.cutoff_max, p->cell_cap, B, s.d_err, s.stream);
+                launch_cell_list(0, fr, nullptr, ps.d_gpos[1], (uint32_t)pr.trg_groups, ps.d_geom, ps.trg, 0, s.stream);
+            } else {
             if (!all_pbc) { launch_aabb(fr, didx[1], (uint32_t)pr.h_idx[1].size(), ps.d_aabb, s.stream, dsel[1]); aabb = ps.d_aabb; }
             launch_geom(s.d_cells, aabb, ps.d_geom, (double)pr.cutoff_max, (double)pr.cutoff_max, p->cell_cap, B, s.d_err, s.stream);
             launch_cell_list(0, fr, didx[1], nullptr, (uint32_t)pr.h_idx[1].size(), ps.d_geom, ps.trg, 0, s.stream, dsel[1]);
+            }
         }
         switch (pr.op) {
         case MDGPU_OP_RDF: {
@@ -923,7 +940,7 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             a.frame_bins = ps.d_frame_bins; a.frame0 = frame0;
             a.pair_list = ps.d_pair_list; a.list_hdr = ps.d_list_hdr; a.list_cursor = ps.d_list_cursor; a.list_stride = ps.list_stride; a.hdr_stride = p->cell_cap; a.err = s.d_err;
             a.excl_off = pr.n_struct ? pr.d_soff : nullptr; a.excl_idx = pr.n_struct ? didx[0] : nullptr;   // md_bitfield_test_bit(&masks[i], j) :5252
-            a.symmetric = (!pr.n_struct && !pr.dyn[0].on && !pr.dyn[1].on && pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
+            a.symmetric = (!pr.n_struct && !pr.trg_groups && !pr.dyn[0].on && !pr.dyn[1].on && pr.h_idx[0] == pr.h_idx[1]) ? 1 : 0;   // same selection on both sides: unshifted pairs are evaluated once, counted twice
             a.acc = pr.d_acc; a.frame_total = pr.d_frame_total; a.frame_min = pr.d_frame_min; a.frame_max = pr.d_frame_max; a.keep = pr.d_keep;
             a.counters = p->timing ? p->d_counters : nullptr;
             cudaEvent_t ev4[4] = { nullptr, nullptr, nullptr, nullptr };   // before cull, after cull, before pairs, after pairs

@@ -244,10 +244,13 @@ class _Parser:
                 wlo, wr, wsel, wand = self.dyn_selection()
             grp = self.groups() if wr is None else None
             ref = None if (grp is not None or wr is not None) else self.selection()
-            self.expect("ch", ","); trg = self.sel_or_within(); self.expect("ch", ",")
+            self.expect("ch", ",")
+            trg = self.sel_or_within() if self._has_within_before_comma() else self.groups_or_selection()   # an array of selections as target: one centre of mass each
+            self.expect("ch", ",")
             a = self.number(); lo, hi = 0.0, a
             if self.peek() == ("ch", ":"):
                 self.next(); lo, hi = a, self.number()
+            if wr is not None and isinstance(trg, list): raise ScriptError("a dynamic reference set with an array of selections as target is not lowered")
             if wr is not None: p = api.rdf(ident, api.Within(wr, wsel, wlo, wand), trg, hi, lo) if isinstance(trg, api.Within) else api.rdf_within(ident, wr, wsel, trg, hi, lo, wlo, wand)
             else: p = api.rdf_com(ident, grp, trg, hi, lo) if grp is not None else api.rdf(ident, ref, trg, hi, lo)
         elif proc == "sdf":
