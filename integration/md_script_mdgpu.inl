@@ -217,7 +217,9 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         size_t ns = 0;
         out->op = MDGPU_OP_COORD_X + (uint32_t)(pname.ptr[6] - 'x');
         if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n;
-        if (args[0]->data.type.base_type == TYPE_BITFIELD && ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false; }
+        if (args[0]->data.type.base_type == TYPE_BITFIELD && ns > 1) {   /* one value per selection: the coordinate of its centre of mass (coordinate_extract :1503) */
+            out->structure_offsets = mdgpu__arg_part_offsets(args[0], alloc); out->num_structures = ns;
+        }
         return true;
     }
     if ((str_eq(pname, STR_LIT("com")) || str_eq(pname, STR_LIT("plane"))) && nargs == 1) {   /* _com :4726, _plane :4755: [F,3] / [F,4] temporals */
@@ -301,7 +303,10 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         for (size_t k = 0; k < 2; ++k) {
             size_t ns = 0;
             if ((n = mdgpu__lower_sel_arg(out, (int)k, args[k], &ns, alloc)) < 0) goto dynamic;
-            if (!(out->dyn[k].radius_max > 0.0f) && args[k]->data.type.base_type == TYPE_BITFIELD && ns > 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (per-selection centres of mass) is not lowered for distance_min/max/pair", STR_ARG(ident)); return false; }
+            if (!(out->dyn[k].radius_max > 0.0f) && args[k]->data.type.base_type == TYPE_BITFIELD && ns > 1) {   /* one centre of mass per selection (coordinate_extract :1503), as for distance_pair */
+                uint32_t* off = mdgpu__arg_part_offsets(args[k], alloc);
+                if (k == 0) { out->structure_offsets = off; out->num_structures = ns; } else { out->structure_offsets_b = off; out->num_structures_b = ns; }
+            }
         }
         return true;
     }

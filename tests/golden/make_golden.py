@@ -194,7 +194,10 @@ def pairs6(tmp):
 
 ARR_SCRIPT = ("da = distance(residue(1:4), residue(10)); db = distance(residue(2:9), residue(20:31)); dc = distance(residue(1:3), 40); "
               "aa = angle(residue(1:2), residue(5:7), 30); ha = dihedral(residue(1:2), residue(3:4), residue(5:6), residue(7:9)); "
-              "ca = com(residue(1:6)); cb = com(residue(100:140)); dd = distance(com(residue(1:4)), residue(50:52));")
+              "ca = com(residue(1:6)); cb = com(residue(100:140)); dd = distance(com(residue(1:4)), residue(50:52)); "
+              # one position (centre of mass, extract_com) per selection of an array: distance_min / _max, coord_*
+              "dmg = distance_min(residue(1:4), residue(10:30)); dmh = distance_min(residue(1), residue(2:9)); dxg = distance_max(residue(3:5), element('O')); "
+              "cxg = coord_x(residue(1:5)); czg = coord_z(residue(10:40));")
 
 
 def arrargs(tmp):

@@ -75,9 +75,11 @@ def test_script_lowering(vb):
     c, ci, pl = vb.compile_script("c = com(residue(2)); ci = com(7); pl = plane(atom(1:9));", s)
     assert c.op == vb.OP_COM and c.com_args == 1 and list(c.idx[0]) == [3, 4, 5] and ci.com_args == 0 and list(ci.idx[0]) == [6]
     assert pl.op == vb.OP_PLANE and list(pl.idx[0]) == list(range(9))
-    for src in ("x = plane(residue(1:3));", "x = coord_x(residue(1:3));", "x = distance_min(residue(1:2), element('O'));"):
-        with pytest.raises(vb.ScriptError):   # one position per selection in the reference: not lowered, never flattened silently
-            vb.compile_script(src, s)
+    with pytest.raises(vb.ScriptError):   # one position per selection in the reference: not lowered for plane(), never flattened silently
+        vb.compile_script("x = plane(residue(1:3));", s)
+    cxg, dmg = vb.compile_script("cxg = coord_x(residue(1:3)); dmg = distance_min(residue(1:2), element('O'));", s)   # one centre of mass per selection of the array
+    assert cxg.num_structures == 3 and list(cxg.structure_offsets) == [0, 3, 6, 9] and list(cxg.idx[0]) == list(range(9))
+    assert dmg.op == vb.OP_DISTANCE_MIN and dmg.num_structures == 2 and list(dmg.structure_offsets) == [0, 3, 6] and dmg.structure_offsets_b is None and len(dmg.idx[1]) == 64
     # an ARRAY of selections as one position argument: the centre of the selections' centres for com / angle / dihedral (arg_offsets),
     # the union for distance (FLAG_FLATTEN, md_script_functions.inl:680) — a com(...) inside distance included
     ca, an, df, dcm = vb.compile_script("ca = com(residue(1:3)); an = angle(residue(1:2), 7, com(residue(3:5))); df = distance(residue(1:2), 5); dcm = distance(com(residue(1:3)), residue(4));", s)

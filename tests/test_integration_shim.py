@@ -30,7 +30,8 @@ SCRIPT_NEW = ("rm = rmsd(residue(1:10)); dp = distance_pair(atom(1:5), atom(20:3
               "aar = angle(residue(1:2), residue(5:7), 30); har = dihedral(residue(1:2), residue(3:4), residue(5:6), residue(7:9)); car = com(residue(1:6)); "
               "dar = distance(residue(1:4), residue(10)); ddr = distance(com(residue(1:4)), residue(50:52)); acr = angle(com(residue(1:3)), 100, residue(20)); "
               # an ARRAY of selections as rdf target: one centre of mass per selection is the target point
-              "rta = rdf(residue(1:20), residue(10:30), 5.0); rtb = rdf(element('O'), residue(10:60), 6.0);")
+              "rta = rdf(residue(1:20), residue(10:30), 5.0); rtb = rdf(element('O'), residue(10:60), 6.0); "
+              "dmg = distance_min(residue(1:4), residue(10:30)); dxg = distance_max(residue(3:5), element('O')); cxg = coord_x(residue(1:5));")
 
 
 def _need():
@@ -93,7 +94,9 @@ def test_shim_lowering_matches_python_lowering(tmp_path):
             assert a["dyn"][k][0] == np.float32(rmin) and a["dyn"][k][1] == np.float32(rmax) and ((cand is None) == (a["dyn"][k][2] is None)), (a["name"], k)
             if cand is not None: assert np.array_equal(a["dyn"][k][2], cand), (a["name"], k)
         if b.op == vb.OP_CONTACT_COUNT: assert np.array_equal(a["eoff"], b.structure_offsets_b) and a["ns"] == b.num_structures
-        if b.op == vb.OP_RDF: assert (a["eoff"] is None) == (b.structure_offsets_b is None) and (a["eoff"] is None or np.array_equal(a["eoff"], b.structure_offsets_b)), a["name"]
+        if b.op in (vb.OP_RDF, vb.OP_DISTANCE_MIN, vb.OP_DISTANCE_MAX, vb.OP_DISTANCE_PAIR):
+            assert (a["eoff"] is None) == (b.structure_offsets_b is None) and (a["eoff"] is None or np.array_equal(a["eoff"], b.structure_offsets_b)), a["name"]
+        if b.op in (vb.OP_DISTANCE_MIN, vb.OP_DISTANCE_MAX, vb.OP_DISTANCE_PAIR, vb.OP_COORD_X): assert a["ns"] == b.num_structures, a["name"]
         assert a["parts"].keys() == b.arg_offsets.keys(), a["name"]
         for k, o in b.arg_offsets.items(): assert np.array_equal(a["parts"][k], o), (a["name"], k)
 

@@ -321,16 +321,32 @@ def distance(name, a, b):
     return _temporal(name, OP_DISTANCE, (a, b))
 
 
-def distance_min(name, a_idx, b_idx):
-    """distance_min(a, b): smallest pair distance between the atoms of two selections (md_script_functions.inl:3892)"""
+def _groups_or_idx(args):
+    """index array -> (array, None); LIST of index arrays (an array of selections: one centre of mass each, extract_com :857) -> (concatenated, CSR offsets)"""
+    idx, offs = [], []
+    for arg in args:
+        if isinstance(arg, (list, tuple)) and len(arg) > 1:
+            g = [np.asarray(x, np.int32) for x in arg]; off = np.zeros(len(g) + 1, np.uint32); off[1:] = np.cumsum([len(x) for x in g])
+            idx.append(np.concatenate(g).astype(np.int32)); offs.append(off)
+        else: idx.append(arg[0] if isinstance(arg, (list, tuple)) else arg); offs.append(None)
+    return idx, offs
+
+
+def _min_distance(name, op, a_idx, b_idx):
+    (a_idx, b_idx), offs = _groups_or_idx([a_idx, b_idx])
     idx, dyn = _split_dyn([a_idx, b_idx])
-    return Property(name, OP_DISTANCE_MIN, idx, dyn=dyn)
+    return Property(name, op, idx, dyn=dyn, num_structures=0 if offs[0] is None else len(offs[0]) - 1, structure_offsets=offs[0], structure_offsets_b=offs[1])
+
+
+def distance_min(name, a_idx, b_idx):
+    """distance_min(a, b): smallest pair distance between the atoms of two selections (md_script_functions.inl:3892); an argument given as a LIST of
+    index arrays is an array of selections: its positions are the selections' centres of mass (coordinate_extract :1503)"""
+    return _min_distance(name, OP_DISTANCE_MIN, a_idx, b_idx)
 
 
 def distance_max(name, a_idx, b_idx):
     """distance_max(a, b): the reference evaluates md_util_min_distance here as well (md_script_functions.inl:3944) — reproduced"""
-    idx, dyn = _split_dyn([a_idx, b_idx])
-    return Property(name, OP_DISTANCE_MAX, idx, dyn=dyn)
+    return _min_distance(name, OP_DISTANCE_MAX, a_idx, b_idx)
 
 
 def distance_pair(name, a, b):
@@ -371,8 +387,10 @@ def shape_weights(name, groups, use_mass=True):
 
 
 def coord(name, axis, idx):
-    """coord_x / coord_y / coord_z(selection): the atoms' coordinates along `axis` -> [F, n] (md_script_functions.inl:5077)"""
-    return Property(name, OP_COORD_X + int(axis), [np.asarray(idx, np.int32)])
+    """coord_x / coord_y / coord_z(selection): the atoms' coordinates along `axis` -> [F, n] (md_script_functions.inl:5077); a LIST of index arrays
+    (an array of selections) yields one value per selection, the coordinate of its centre of mass (coordinate_extract :1503)"""
+    (idx,), offs = _groups_or_idx([idx])
+    return Property(name, OP_COORD_X + int(axis), [np.asarray(idx, np.int32)], num_structures=0 if offs[0] is None else len(offs[0]) - 1, structure_offsets=offs[0])
 
 
 def grow_by_bonds(atoms, conn_offset, conn_idx, extent: int):

@@ -386,6 +386,22 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
         if (sys->bond_conn_atom_idx) p->conn_idx.assign(sys->bond_conn_atom_idx, sys->bond_conn_atom_idx + nconn);
     }
     auto bail = [&](int code, const std::string& msg) -> mdgpu_plan* { fail(code, "%s", msg.c_str()); destroy_plan(p); return nullptr; };
+    // arguments 0 / 1 of distance_pair / distance_min / _max and argument 0 of coord_* given as ARRAYS of selections: one position (centre of mass) per
+    // selection; CSR offsets in structure_offsets (argument 0, num_structures groups) / structure_offsets_b (argument 1)
+    auto take_groups = [&](Prop& pr, const mdgpu_property_desc_t& d, size_t cnt[2]) -> std::string {
+        const uint32_t* goff[2] = { d.structure_offsets, d.structure_offsets_b }; const size_t gn[2] = { d.num_structures, d.num_structures_b };
+        for (int k = 0; k < 2; ++k) {
+            cnt[k] = pr.h_idx[k].size();
+            if (!gn[k]) continue;
+            if (pr.dyn[k].on) return "'" + pr.name + "': an array of selections cannot be a dynamic argument";
+            if (!goff[k] || goff[k][0] != 0 || goff[k][gn[k]] != pr.h_idx[k].size()) return "'" + pr.name + "': group offsets do not cover the index list";
+            for (size_t g = 0; g < gn[k]; ++g) if (goff[k][g] > goff[k][g + 1]) return "'" + pr.name + "': group offsets must be non-decreasing";
+            pr.h_goff[k].assign(goff[k], goff[k] + gn[k] + 1); cnt[k] = gn[k];
+            if (upload(&pr.d_goff[k], pr.h_goff[k].data(), pr.h_goff[k].size()) != cudaSuccess) return "device allocation failed (group offsets)";
+        }
+        pr.n_struct = 0;   // num_structures described argument 0's groups here, not structures
+        return std::string();
+    };
     // argument k of distance / angle / dihedral / com given as an ARRAY of selections (arg_parts[k] >= 2): idx[k] holds them back to back
     auto take_arg_parts = [&](Prop& pr, const mdgpu_property_desc_t& d, int k) -> std::string {
         const uint32_t n = d.arg_parts[k]; const uint32_t* off = d.arg_offsets[k];
@@ -493,6 +509,7 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             break;
         case MDGPU_OP_DISTANCE_MIN: case MDGPU_OP_DISTANCE_MAX:
             if ((pr.h_idx[0].empty() && !pr.dyn[0].on) || (pr.h_idx[1].empty() && !pr.dyn[1].on)) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
+            { size_t cnt[2]; const std::string er = take_groups(pr, d, cnt); if (!er.empty()) return bail(MDGPU_ERR_INVALID_ARG, er); }   // arrays of selections: one centre of mass per selection
             e = dalloc(&pr.d_temporal, num_frames);
             pr.values.assign(num_frames, 0.0f);
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 1; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
@@ -523,15 +540,8 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
         case MDGPU_OP_DISTANCE_PAIR: {
             if (pr.h_idx[0].empty() || pr.h_idx[1].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
             // an argument that was an ARRAY of selections contributes one position per selection: extract_com (:857, no periodic treatment; coordinate_extract :1503)
-            size_t cnt[2] = { pr.h_idx[0].size(), pr.h_idx[1].size() };
-            const uint32_t* goff[2] = { d.structure_offsets, d.structure_offsets_b }; const size_t gn[2] = { d.num_structures, d.num_structures_b };
-            for (int k = 0; k < 2; ++k) if (gn[k]) {
-                if (!goff[k] || goff[k][0] != 0 || goff[k][gn[k]] != pr.h_idx[k].size()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': group offsets do not cover the index list");
-                for (size_t g = 0; g < gn[k]; ++g) if (goff[k][g] > goff[k][g + 1]) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': group offsets must be non-decreasing");
-                pr.h_goff[k].assign(goff[k], goff[k] + gn[k] + 1); cnt[k] = gn[k];
-                if (upload(&pr.d_goff[k], pr.h_goff[k].data(), pr.h_goff[k].size()) != cudaSuccess) return bail(MDGPU_ERR_CUDA, "device allocation failed (group offsets)");
-            }
-            pr.n_struct = 0;   // num_structures described argument 0's groups here, not structures
+            size_t cnt[2];
+            { const std::string er = take_groups(pr, d, cnt); if (!er.empty()) return bail(MDGPU_ERR_INVALID_ARG, er); }
             pr.len = cnt[0] * cnt[1];
             if (pr.len > 1000000) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': The size produced by the operation is " + std::to_string(pr.len) + ", which exceeds the upper limit of 1'000'000");   // :4056
             e = dalloc(&pr.d_temporal, num_frames * pr.len);
@@ -563,7 +573,8 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             break; }
         case MDGPU_OP_COORD_X: case MDGPU_OP_COORD_Y: case MDGPU_OP_COORD_Z:   // coord_x/_y/_z(selection): [F, n]
             if (pr.h_idx[0].empty()) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': empty argument");
-            pr.len = pr.h_idx[0].size();
+            { size_t cnt[2]; const std::string er = take_groups(pr, d, cnt); if (!er.empty()) return bail(MDGPU_ERR_INVALID_ARG, er);   // an array of selections: one value per selection
+              pr.len = cnt[0]; }
             e = dalloc(&pr.d_temporal, num_frames * pr.len);
             pr.values.assign(num_frames * pr.len, 0.0f);
             if (pr.len > 1) { pr.agg_mean.assign(num_frames, 0.0f); pr.agg_var.assign(num_frames, 0.0f); pr.agg_ext.assign(2 * num_frames, 0.0f); }
@@ -820,7 +831,7 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * (pr.n_struct + 1) * pr.struct_size));
                     CUDA_TRY(dalloc(&ps.d_sdf_ref0, (size_t)p->B * 20));
                     CUDA_TRY(dalloc(&ps.d_sdf_mats, (size_t)p->B * pr.n_struct * 32));
-                } else if (pr.op == MDGPU_OP_DISTANCE_PAIR) {
+                } else if (pr.op == MDGPU_OP_DISTANCE_PAIR || ((pr.op == MDGPU_OP_DISTANCE_MIN || pr.op == MDGPU_OP_DISTANCE_MAX || (pr.op >= MDGPU_OP_COORD_X && pr.op <= MDGPU_OP_COORD_Z)) && (!pr.h_goff[0].empty() || !pr.h_goff[1].empty()))) {
                     for (int k = 0; k < 2; ++k) if (!pr.h_goff[k].empty()) CUDA_TRY(dalloc(&ps.d_gpos[k], (size_t)p->B * (pr.h_goff[k].size() - 1) * 3));
                 } else if (pr.op == MDGPU_OP_WITHIN_COUNT) {
                     CUDA_TRY(dalloc(&ps.d_geom, p->B)); CUDA_TRY(dalloc(&ps.d_aabb, (size_t)6 * p->B));
@@ -1002,6 +1013,12 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             launch_com_rows(a, B, s.stream);
             break; }
         case MDGPU_OP_COORD_X: case MDGPU_OP_COORD_Y: case MDGPU_OP_COORD_Z:
+            if (!pr.h_goff[0].empty()) {
+                const uint32_t n = (uint32_t)pr.h_goff[0].size() - 1;
+                launch_group_com(fr, didx[0], pr.d_goff[0], n, dmass, ps.d_gpos[0], s.stream);
+                launch_coord_rows_pos(ps.d_gpos[0], n, (int)pr.op - MDGPU_OP_COORD_X, pr.d_temporal, frame0, B, s.stream);
+                break;
+            }
             launch_coord_rows(fr, didx[0], (uint32_t)pr.h_idx[0].size(), (int)pr.op - MDGPU_OP_COORD_X, pr.d_temporal, frame0, s.stream);
             break;
         case MDGPU_OP_SHAPE_WEIGHTS: {
@@ -1034,6 +1051,15 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             launch_rmsd(a, B, s.stream);
             break; }
         case MDGPU_OP_DISTANCE_MIN: case MDGPU_OP_DISTANCE_MAX:   // both evaluate md_util_min_distance (md_script_functions.inl:3904, 3944)
+            if (!pr.h_goff[0].empty() || !pr.h_goff[1].empty()) {
+                uint32_t cnt[2];
+                for (int k = 0; k < 2; ++k) {
+                    cnt[k] = (uint32_t)(pr.h_goff[k].empty() ? pr.h_idx[k].size() : pr.h_goff[k].size() - 1);
+                    if (!pr.h_goff[k].empty()) launch_group_com(fr, didx[k], pr.d_goff[k], cnt[k], dmass, ps.d_gpos[k], s.stream);
+                }
+                launch_min_distance_pos(fr, s.d_cells, didx[0], cnt[0], didx[1], cnt[1], ps.d_gpos[0], ps.d_gpos[1], pr.d_temporal, frame0, s.stream);
+                break;
+            }
             launch_min_distance(fr, s.d_cells, didx[0], (uint32_t)pr.h_idx[0].size(), didx[1], (uint32_t)pr.h_idx[1].size(), pr.d_temporal, frame0, s.stream, dsel[0], dsel[1]);
             break;
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {

@@ -466,6 +466,54 @@ __global__ void __launch_bounds__(256) k_distance_pair(BatchFrames fr, const mdg
     out[(size_t)(frame0 + f) * npairs + p] = pair_distance(pa[0], pa[1], pa[2], pb[0], pb[1], pb[2], uc.flags, ext, box);
 }
 
+// distance_min / distance_max when an argument was an ARRAY of selections: that argument's positions are the selections' centres of mass
+// (coordinate_extract md_script_functions.inl:1503 -> extract_com :857; posa / posb as for k_distance_pair), then md_util_min_distance (md_util.c:8242)
+__global__ void __launch_bounds__(256) k_min_distance_pos(BatchFrames fr, const mdgpu_unitcell_t* __restrict__ cells, const int32_t* __restrict__ ia, uint32_t na,
+                                                          const int32_t* __restrict__ ib, uint32_t nb, const float* __restrict__ posa, const float* __restrict__ posb,
+                                                          float* __restrict__ out, uint32_t frame0) {
+    const int f = blockIdx.x;
+    const float* x = fr.xyz + (size_t)f * fr.frame_stride; const float* y = x + fr.axis_stride; const float* z = y + fr.axis_stride;
+    const mdgpu_unitcell_t uc = cells[f];
+    const float ext[3] = { (float)uc.x, (float)uc.y, (float)uc.z };
+    const float box[3][3] = { { (float)uc.x, 0.f, 0.f }, { (float)uc.xy, (float)uc.y, 0.f }, { (float)uc.xz, (float)uc.yz, (float)uc.z } };
+    float best = 3.402823466e+38f;
+    const unsigned long long npairs = (unsigned long long)na * nb;
+    for (unsigned long long p = threadIdx.x; p < npairs; p += blockDim.x) {
+        const uint32_t i = (uint32_t)(p / nb), j = (uint32_t)(p % nb);
+        float pa[3], pb[3];
+        if (posa) { const float* q = posa + ((size_t)f * na + i) * 3; pa[0] = q[0]; pa[1] = q[1]; pa[2] = q[2]; } else { const int a = ia[i]; pa[0] = x[a]; pa[1] = y[a]; pa[2] = z[a]; }
+        if (posb) { const float* q = posb + ((size_t)f * nb + j) * 3; pb[0] = q[0]; pb[1] = q[1]; pb[2] = q[2]; } else { const int b = ib[j]; pb[0] = x[b]; pb[1] = y[b]; pb[2] = z[b]; }
+        best = fminf(best, pair_distance(pa[0], pa[1], pa[2], pb[0], pb[1], pb[2], uc.flags, ext, box));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    __shared__ float s_best[8];
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int w = 1; w < 8; ++w) best = fminf(best, s_best[w]); out[frame0 + f] = best; }
+}
+
+void launch_min_distance_pos(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb,
+                             const float* d_posa, const float* d_posb, float* d_out, uint32_t frame0, cudaStream_t s) {
+    if (!fr.count) return;
+    k_min_distance_pos<<<fr.count, 256, 0, s>>>(fr, d_cells, d_ia, na, d_ib, nb, d_posa, d_posb, d_out, frame0);
+    note_launch("k_min_distance_pos", s);
+}
+
+// coord_x / _y / _z of an ARRAY of selections: one coordinate per selection, of its centre of mass (coordinate_extract :1503); pos [B][n][3]
+__global__ void k_coord_rows_pos(const float* __restrict__ pos, uint32_t n, int axis, float* __restrict__ out, uint32_t frame0) {
+    const int f = blockIdx.y;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    out[(size_t)(frame0 + f) * n + k] = pos[((size_t)f * n + k) * 3 + axis];
+}
+
+void launch_coord_rows_pos(const float* d_pos, uint32_t n, int axis, float* d_out, uint32_t frame0, int B, cudaStream_t s) {
+    if (!n || B <= 0) return;
+    k_coord_rows_pos<<<dim3((n + 255u) / 256u, (unsigned)B), 256, 0, s>>>(d_pos, n, axis, d_out, frame0);
+    note_launch("k_coord_rows_pos", s);
+}
+
 void launch_min_distance(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_ia, uint32_t na, const int32_t* d_ib, uint32_t nb, float* d_out, uint32_t frame0, cudaStream_t s, DynSel da, DynSel db) {
     if (!fr.count) return;
     k_min_distance<<<fr.count, 256, 0, s>>>(fr, d_cells, d_ia, na, d_ib, nb, d_out, frame0, da, db);

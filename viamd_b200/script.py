@@ -262,8 +262,9 @@ class _Parser:
             a = self.groups_or_selection(); self.expect("ch", ","); b = self.groups_or_selection()
             p = api.distance_pair(ident, a, b)
         elif proc in ("distance_min", "distance_max"):
-            a = self.sel_or_within(single=True); self.expect("ch", ","); b = self.sel_or_within(single=True)
-            p = {"distance_min": api.distance_min, "distance_max": api.distance_max, "distance_pair": api.distance_pair}[proc](ident, a, b)
+            a = self.sel_or_within() if self._has_within_before_comma() else self.groups_or_selection(); self.expect("ch", ",")   # an array of selections: one centre of mass per selection
+            b = self.sel_or_within() if self._has_within_before_comma() else self.groups_or_selection()
+            p = {"distance_min": api.distance_min, "distance_max": api.distance_max}[proc](ident, a, b)
         elif proc == "contact_count":   # contact_count(A[], B, cutoff [, path_length])
             a = self.groups_or_selection(); self.expect("ch", ","); b = self.selection(); self.expect("ch", ","); c = self.number(); pl = 4
             if self.peek() == ("ch", ","): self.next(); pl = int(self.number())
@@ -273,9 +274,8 @@ class _Parser:
             rlo, r, sel, cand = self.dyn_selection()
             p = api.count_within(ident, r, sel, rlo, cand)
         elif proc in ("coord_x", "coord_y", "coord_z"):
-            a = self.index()
-            if isinstance(a, list): raise ScriptError("an array of selections as coord argument (one centre of mass per selection, coordinate_extract :1503) is not lowered")
-            p = api.coord(ident, "xyz".index(proc[-1]), [a] if np.ndim(a) == 0 else a)
+            a = self.index()   # an array of selections: one value per selection (its centre of mass, coordinate_extract :1503)
+            p = api.coord(ident, "xyz".index(proc[-1]), a if isinstance(a, list) else ([a] if np.ndim(a) == 0 else a))
         elif proc == "com":
             p = api.com(ident, self.index())
         elif proc == "plane":
