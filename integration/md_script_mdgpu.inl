@@ -230,8 +230,8 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
         else { if ((n = mdgpu__arg_indices((int32_t**)&out->idx[0], &ns, NULL, args[0], alloc)) < 0) goto dynamic; out->idx_count[0] = (size_t)n; }
         if (args[0]->data.type.base_type == TYPE_BITFIELD) {
             if (ns > 1) {
-                if (!is_com) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections (one centre of mass per selection) is not lowered", STR_ARG(ident)); return false; }
-                out->arg_offsets[0] = mdgpu__arg_part_offsets(args[0], alloc); out->arg_parts[0] = (uint32_t)ns;   /* the centre of the selections' centres (coordinate_extract_com :1826-1842) */
+                if (!is_com) { out->structure_offsets = mdgpu__arg_part_offsets(args[0], alloc); out->num_structures = ns; }   /* plane through the selections' centres of mass (coordinate_extract :1503) */
+                else { out->arg_offsets[0] = mdgpu__arg_part_offsets(args[0], alloc); out->arg_parts[0] = (uint32_t)ns; }   /* the centre of the selections' centres (coordinate_extract_com :1826-1842) */
             }
             if (is_com) out->com_args = 1u;
         }

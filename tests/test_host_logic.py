@@ -75,8 +75,8 @@ def test_script_lowering(vb):
     c, ci, pl = vb.compile_script("c = com(residue(2)); ci = com(7); pl = plane(atom(1:9));", s)
     assert c.op == vb.OP_COM and c.com_args == 1 and list(c.idx[0]) == [3, 4, 5] and ci.com_args == 0 and list(ci.idx[0]) == [6]
     assert pl.op == vb.OP_PLANE and list(pl.idx[0]) == list(range(9))
-    with pytest.raises(vb.ScriptError):   # one position per selection in the reference: not lowered for plane(), never flattened silently
-        vb.compile_script("x = plane(residue(1:3));", s)
+    plg = vb.compile_script("x = plane(residue(1:3));", s)[0]   # the plane through the three residues' centres of mass
+    assert plg.op == vb.OP_PLANE and plg.num_structures == 3 and list(plg.structure_offsets) == [0, 3, 6, 9]
     cxg, dmg = vb.compile_script("cxg = coord_x(residue(1:3)); dmg = distance_min(residue(1:2), element('O'));", s)   # one centre of mass per selection of the array
     assert cxg.num_structures == 3 and list(cxg.structure_offsets) == [0, 3, 6, 9] and list(cxg.idx[0]) == list(range(9))
     assert dmg.op == vb.OP_DISTANCE_MIN and dmg.num_structures == 2 and list(dmg.structure_offsets) == [0, 3, 6] and dmg.structure_offsets_b is None and len(dmg.idx[1]) == 64

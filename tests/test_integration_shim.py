@@ -31,7 +31,7 @@ SCRIPT_NEW = ("rm = rmsd(residue(1:10)); dp = distance_pair(atom(1:5), atom(20:3
               "dar = distance(residue(1:4), residue(10)); ddr = distance(com(residue(1:4)), residue(50:52)); acr = angle(com(residue(1:3)), 100, residue(20)); "
               # an ARRAY of selections as rdf target: one centre of mass per selection is the target point
               "rta = rdf(residue(1:20), residue(10:30), 5.0); rtb = rdf(element('O'), residue(10:60), 6.0); "
-              "dmg = distance_min(residue(1:4), residue(10:30)); dxg = distance_max(residue(3:5), element('O')); cxg = coord_x(residue(1:5));")
+              "dmg = distance_min(residue(1:4), residue(10:30)); dxg = distance_max(residue(3:5), element('O')); cxg = coord_x(residue(1:5)); plg = plane(residue(1:10));")
 
 
 def _need():
@@ -96,7 +96,7 @@ def test_shim_lowering_matches_python_lowering(tmp_path):
         if b.op == vb.OP_CONTACT_COUNT: assert np.array_equal(a["eoff"], b.structure_offsets_b) and a["ns"] == b.num_structures
         if b.op in (vb.OP_RDF, vb.OP_DISTANCE_MIN, vb.OP_DISTANCE_MAX, vb.OP_DISTANCE_PAIR):
             assert (a["eoff"] is None) == (b.structure_offsets_b is None) and (a["eoff"] is None or np.array_equal(a["eoff"], b.structure_offsets_b)), a["name"]
-        if b.op in (vb.OP_DISTANCE_MIN, vb.OP_DISTANCE_MAX, vb.OP_DISTANCE_PAIR, vb.OP_COORD_X): assert a["ns"] == b.num_structures, a["name"]
+        if b.op in (vb.OP_DISTANCE_MIN, vb.OP_DISTANCE_MAX, vb.OP_DISTANCE_PAIR, vb.OP_COORD_X, vb.OP_PLANE): assert a["ns"] == b.num_structures, a["name"]
         assert a["parts"].keys() == b.arg_offsets.keys(), a["name"]
         for k, o in b.arg_offsets.items(): assert np.array_equal(a["parts"][k], o), (a["name"], k)
 

@@ -367,8 +367,10 @@ def com(name, a):
 
 
 def plane(name, idx):
-    """plane(selection): [F, 4] — unit normal of the best-fit plane through the atoms (third principal axis) and normal . centre (_plane :4755)"""
-    return Property(name, OP_PLANE, [np.asarray(idx, np.int32)])
+    """plane(selection): [F, 4] — unit normal of the best-fit plane through the atoms (third principal axis) and normal . centre (_plane :4755);
+    a LIST of index arrays (an array of selections) fits the plane through the selections' centres of mass"""
+    (idx,), offs = _groups_or_idx([idx])
+    return Property(name, OP_PLANE, [np.asarray(idx, np.int32)], num_structures=0 if offs[0] is None else len(offs[0]) - 1, structure_offsets=offs[0])
 
 
 def count_within(name, radius, sel_idx, radius_min=0.0, and_idx=None):

@@ -88,6 +88,7 @@ struct RmsdArgs {                    // rmsd(selection) against the initial fram
     const float* init_xyz; size_t init_axis_stride;
     const float* mass;
     const int32_t* idx; uint32_t n;  // the selection's atoms, ascending
+    const float* pos;                // plane() of an ARRAY of selections: [B][n][3] centres of mass, the n positions (idx unused); else null
     const int2* unwrap_pairs; uint32_t n_unwrap;
     float4* scratch_xyzw;            // [B][2][n]
     float* out;                      // [num_frames]

@@ -591,8 +591,11 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
             pr.data.dim[0] = (int32_t)num_frames; pr.data.dim[1] = 3; pr.data.dim[2] = 0; pr.data.dim[3] = 0;
             break; }
         case MDGPU_OP_PLANE: {   // plane(selection): a [F, 4] temporal (TI_FLOAT4)
-            if (pr.h_idx[0].size() < 3) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': Invalid number of positions, need at least 3 to compute a plane");   // :4815
-            std::vector<int2> pairs; build_unwrap_pairs(pairs, pr.h_idx[0].size(), p->conn_off, p->conn_idx);
+            size_t cnt[2];   // an array of selections: its positions are the selections' centres of mass (coordinate_extract :1503)
+            { const std::string er = take_groups(pr, d, cnt); if (!er.empty()) return bail(MDGPU_ERR_INVALID_ARG, er); }
+            if (cnt[0] < 3) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': Invalid number of positions, need at least 3 to compute a plane");   // :4815
+            // md_util_unwrap_vec4 is called without indices (:4771): position i is unwrapped along the bonds of ATOM i, whatever was selected — as written
+            std::vector<int2> pairs; build_unwrap_pairs(pairs, cnt[0], p->conn_off, p->conn_idx);
             pr.n_unwrap = (uint32_t)pairs.size();
             e = upload(&pr.d_unwrap, pairs.data(), pairs.size());
             pr.len = 4;
@@ -831,8 +834,9 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                     CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * (pr.n_struct + 1) * pr.struct_size));
                     CUDA_TRY(dalloc(&ps.d_sdf_ref0, (size_t)p->B * 20));
                     CUDA_TRY(dalloc(&ps.d_sdf_mats, (size_t)p->B * pr.n_struct * 32));
-                } else if (pr.op == MDGPU_OP_DISTANCE_PAIR || ((pr.op == MDGPU_OP_DISTANCE_MIN || pr.op == MDGPU_OP_DISTANCE_MAX || (pr.op >= MDGPU_OP_COORD_X && pr.op <= MDGPU_OP_COORD_Z)) && (!pr.h_goff[0].empty() || !pr.h_goff[1].empty()))) {
+                } else if (pr.op == MDGPU_OP_DISTANCE_PAIR || ((pr.op == MDGPU_OP_DISTANCE_MIN || pr.op == MDGPU_OP_DISTANCE_MAX || (pr.op >= MDGPU_OP_COORD_X && pr.op <= MDGPU_OP_COORD_Z) || pr.op == MDGPU_OP_PLANE) && (!pr.h_goff[0].empty() || !pr.h_goff[1].empty()))) {
                     for (int k = 0; k < 2; ++k) if (!pr.h_goff[k].empty()) CUDA_TRY(dalloc(&ps.d_gpos[k], (size_t)p->B * (pr.h_goff[k].size() - 1) * 3));
+                    if (pr.op == MDGPU_OP_PLANE) CUDA_TRY(dalloc(&ps.d_sdf_xyzw, (size_t)p->B * pr.h_idx[0].size()));   // the plane fit's xyzw scratch
                 } else if (pr.op == MDGPU_OP_WITHIN_COUNT) {
                     CUDA_TRY(dalloc(&ps.d_geom, p->B)); CUDA_TRY(dalloc(&ps.d_aabb, (size_t)6 * p->B));
                     int rc = alloc_cell_list(ps.trg, p->B, (uint32_t)p->num_atoms, cap); if (rc) return rc;
@@ -1031,6 +1035,10 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
         case MDGPU_OP_PLANE: {
             RmsdArgs a{};
             a.frames = fr; a.cells = s.d_cells; a.mass = dmass; a.idx = didx[0]; a.n = (uint32_t)pr.h_idx[0].size();
+            if (!pr.h_goff[0].empty()) {
+                a.n = (uint32_t)pr.h_goff[0].size() - 1;
+                launch_group_com(fr, didx[0], pr.d_goff[0], a.n, dmass, ps.d_gpos[0], s.stream); a.pos = ps.d_gpos[0];
+            }
             a.unwrap_pairs = pr.d_unwrap; a.n_unwrap = pr.n_unwrap; a.scratch_xyzw = ps.d_sdf_xyzw; a.out = pr.d_temporal; a.frame0 = frame0;
             launch_plane(a, B, s.stream);
             break; }

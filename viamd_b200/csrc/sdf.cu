@@ -732,7 +732,8 @@ __global__ void __launch_bounds__(32) k_plane(RmsdArgs a, int B) {
     const mdgpu_unitcell_t uc = a.cells[f];
     const float* x = a.frames.xyz + (size_t)f * a.frames.frame_stride;
     float4* p = a.scratch_xyzw + (size_t)f * n;
-    for (uint32_t k = lane; k < n; k += 32) { const int at = a.idx[k]; p[k] = make_float4(x[at], x[a.frames.axis_stride + at], x[2 * a.frames.axis_stride + at], 1.0f); }
+    if (a.pos) for (uint32_t k = lane; k < n; k += 32) { const float* q = a.pos + ((size_t)f * n + k) * 3; p[k] = make_float4(q[0], q[1], q[2], 1.0f); }   // one centre of mass per selection (coordinate_extract :1503)
+    else for (uint32_t k = lane; k < n; k += 32) { const int at = a.idx[k]; p[k] = make_float4(x[at], x[a.frames.axis_stride + at], x[2 * a.frames.axis_stride + at], 1.0f); }
     __syncwarp();
     if (lane != 0) return;
     float com[3];

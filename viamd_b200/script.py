@@ -279,7 +279,7 @@ class _Parser:
         elif proc == "com":
             p = api.com(ident, self.index())
         elif proc == "plane":
-            p = api.plane(ident, self.single_selection())
+            p = api.plane(ident, self.groups_or_selection())   # an array of selections: the plane through their centres of mass
         elif proc == "rmsd":
             p = api.rmsd(ident, self.selection())   # an array of selections is flattened into their union (_internal_flatten_bf :4305)
         elif proc == "distance":
