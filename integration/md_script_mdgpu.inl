@@ -154,6 +154,10 @@ static int64_t mdgpu__lower_sel_arg(mdgpu_property_desc_t* out, int k, const ast
     }
 }
 
+/* the script and system being lowered (md_script_gpu_lower_sys sets them): context-relative arguments are evaluated with the reference's own evaluator */
+static _Thread_local const md_script_ir_t* mdgpu__lower_ir = NULL;
+static _Thread_local const md_system_t* mdgpu__lower_mol = NULL;
+
 static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const ast_node_t* node, const md_system_t* mol, md_allocator_i* alloc) {
     const ast_node_t* rhs = mdgpu__rhs(node);
     const md_bitfield_t* ctx_bf = NULL; size_t n_ctx = 0;
@@ -317,8 +321,39 @@ static bool mdgpu__lower_property(mdgpu_property_desc_t* out, str_t ident, const
             out->op = dist ? MDGPU_OP_DISTANCE : (ang ? MDGPU_OP_ANGLE : MDGPU_OP_DIHEDRAL);
             out->num_structures = n_ctx;
             for (size_t k = 0; k < need; ++k) {
+                const ast_node_t* an = args[k];
+                if (an->type == AST_PROC_CALL && an->proc && str_eq(an->proc->name, STR_LIT("com")) && md_array_size(an->children) == 1) an = an->children[0];   /* com(x) contributes x's position (:4726) */
+                if (an->data.type.base_type == TYPE_BITFIELD && !(an->flags & FLAG_DYNAMIC)) {
+                    /* a selection inside the contexts: in context c its position is the centre of mass of (selection AND context) (coordinate_extract_com
+                     * with ctx->mol_ctx, md_script_functions.inl:1812-1823). A constant node carries the whole-system selection; a context-relative one
+                     * (atom(2:3) in residue(:)) is evaluated per context by the reference's own evaluator, as evaluate_context does (md_script.c:3463-3494). */
+                    uint32_t* off = (uint32_t*)md_alloc(alloc, sizeof(uint32_t) * (n_ctx + 1)); off[0] = 0;
+                    md_array(int32_t) all = 0;
+                    md_bitfield_t tmp = {0}; md_bitfield_init(&tmp, alloc);
+                    for (size_t c = 0; c < n_ctx; ++c) {
+                        const md_bitfield_t* src = NULL; size_t nsrc = 0;
+                        data_t dd = {0};
+                        if ((an->flags & FLAG_CONSTANT) && an->data.ptr) { src = (const md_bitfield_t*)an->data.ptr; nsrc = element_count(an->data); }
+                        else {
+                            eval_context_t ectx = { .ir = (md_script_ir_t*)mdgpu__lower_ir, .mol = mdgpu__lower_mol, .temp_alloc = alloc, .alloc = alloc };
+                            ectx.mol_ctx = &ctx_bf[c];
+                            dd.type = an->data.type; allocate_data(&dd, dd.type, alloc);
+                            if (!evaluate_node(&dd, an, &ectx)) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': argument %zu could not be evaluated in context %zu", STR_ARG(ident), k, c); return false; }
+                            src = (const md_bitfield_t*)dd.ptr; nsrc = element_count(dd);
+                        }
+                        if (nsrc != 1) { MD_LOG_ERROR("mdgpu: property '" STR_FMT "': an array of selections inside a context expression is not lowered", STR_ARG(ident)); return false; }
+                        md_bitfield_and(&tmp, src, &ctx_bf[c]);
+                        const size_t cnt = md_bitfield_popcount(&tmp);
+                        const size_t at = md_array_size(all);
+                        md_array_resize(all, at + cnt, alloc);
+                        if (cnt) md_bitfield_iter_extract_indices(all + at, cnt, md_bitfield_iter_create(&tmp));
+                        off[c + 1] = off[c] + (uint32_t)cnt;
+                    }
+                    out->idx[k] = all; out->idx_count[k] = md_array_size(all); out->arg_offsets[k] = off; out->arg_parts[k] = (uint32_t)n_ctx; out->com_args |= 1u << k;
+                    continue;
+                }
                 if (!(args[k]->flags & FLAG_CONSTANT) || args[k]->data.type.base_type != TYPE_INT || element_count(args[k]->data) != 1) {
-                    MD_LOG_ERROR("mdgpu: property '" STR_FMT "': `in` is lowered for integer arguments only", STR_ARG(ident)); return false;
+                    MD_LOG_ERROR("mdgpu: property '" STR_FMT "': `in` is lowered for integer and selection arguments", STR_ARG(ident)); return false;
                 }
                 const int32_t v = *(const int32_t*)args[k]->data.ptr;
                 int32_t* idx = (int32_t*)md_alloc(alloc, sizeof(int32_t) * n_ctx);
@@ -361,6 +396,7 @@ dynamic:
 
 /* Lower every property of a compiled script. */
 static bool md_script_gpu_lower_sys(md_script_gpu_lowered_t* out, const md_script_ir_t* ir, const md_system_t* mol, md_allocator_i* alloc) {
+    mdgpu__lower_ir = ir; mdgpu__lower_mol = mol;
     const size_t np = md_array_size(ir->property_names);
     out->num_props = np;
     out->props = (mdgpu_property_desc_t*)md_alloc(alloc, sizeof(mdgpu_property_desc_t) * (np ? np : 1));

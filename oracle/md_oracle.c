@@ -1224,6 +1224,17 @@ float mdo_dihedral_pos(const float p[4][3], const mdo_unitcell_t* cell) {
             const float half = ext[i] * 0.5f;
             if (ext[i] > 0.0f) { while (dx[k][i] > half) dx[k][i] -= ext[i]; while (dx[k][i] <= -half) dx[k][i] += ext[i]; }
         }
+    } else if (cell->flags & MDO_CELL_TRICLINIC) {   /* min_image_triclinic with the half diagonal md_util.c:8360-8423: zone reduction along c, b, a, then the 27 images */
+        double Ad[3][3]; cell_A(Ad, cell);
+        float box[3][3]; for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) box[c][r] = (float)Ad[c][r];
+        const float half[3] = { box[0][0] * 0.5f, box[1][1] * 0.5f, box[2][2] * 0.5f };
+        for (int k = 0; k < 3; ++k) {
+            for (int i = 2; i >= 0; i--) if (half[i] > 0.0f) {
+                while (dx[k][i] > half[i]) for (int j = i; j >= 0; j--) dx[k][j] -= box[i][j];
+                while (dx[k][i] <= -half[i]) for (int j = i; j >= 0; j--) dx[k][j] += box[i][j];
+            }
+            min_image_triclinic(dx[k], (const float (*)[3])box);
+        }
     }
     /* vec3_dihedral_angle core/md_vec_math.h:558-567 */
     const float* d1 = dx[0]; const float* d2 = dx[1]; const float* d3 = dx[2];

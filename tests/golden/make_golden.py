@@ -197,7 +197,10 @@ ARR_SCRIPT = ("da = distance(residue(1:4), residue(10)); db = distance(residue(2
               "ca = com(residue(1:6)); cb = com(residue(100:140)); dd = distance(com(residue(1:4)), residue(50:52)); "
               # one position (centre of mass, extract_com) per selection of an array: distance_min / _max, coord_*
               "dmg = distance_min(residue(1:4), residue(10:30)); dmh = distance_min(residue(1), residue(2:9)); dxg = distance_max(residue(3:5), element('O')); "
-              "cxg = coord_x(residue(1:5)); czg = coord_z(residue(10:40)); plg = plane(residue(1:10)); plh = plane(residue(20:200));")
+              "cxg = coord_x(residue(1:5)); czg = coord_z(residue(10:40)); plg = plane(residue(1:10)); plh = plane(residue(20:200)); "
+              # selections inside `in` contexts: per context the centre of mass of (selection AND context); atom(a:b) relative to the context
+              "dctx = distance(element('O'), element('H')) in residue(1:10); actx = angle(atom(2), element('O'), 3) in residue(1:5); "
+              "ectx = distance(element('O'), atom(2:3)) in residue(2:5); hctx = dihedral(1, element('O'), atom(2:3), 3) in residue(:);")
 
 
 def arrargs(tmp):

@@ -31,7 +31,16 @@ SCRIPT_NEW = ("rm = rmsd(residue(1:10)); dp = distance_pair(atom(1:5), atom(20:3
               "dar = distance(residue(1:4), residue(10)); ddr = distance(com(residue(1:4)), residue(50:52)); acr = angle(com(residue(1:3)), 100, residue(20)); "
               # an ARRAY of selections as rdf target: one centre of mass per selection is the target point
               "rta = rdf(residue(1:20), residue(10:30), 5.0); rtb = rdf(element('O'), residue(10:60), 6.0); "
-              "dmg = distance_min(residue(1:4), residue(10:30)); dxg = distance_max(residue(3:5), element('O')); cxg = coord_x(residue(1:5)); plg = plane(residue(1:10));")
+              "dmg = distance_min(residue(1:4), residue(10:30)); dxg = distance_max(residue(3:5), element('O')); cxg = coord_x(residue(1:5)); plg = plane(residue(1:10)); "
+              # selections inside `in` contexts (the shim evaluates context-relative arguments with the reference's own evaluator)
+              "dctx = distance(element('O'), element('H')) in residue(1:10); ectx = distance(element('O'), atom(2:3)) in residue(2:5); hctx = dihedral(1, element('O'), atom(2:3), 3) in residue(:);")
+
+
+# forms only the shim lowers (the Python mirror rejects them): arguments that are relative to the context — residue(1) inside `in residue(2:4)` is the
+# context's own first residue, `element('O') and atom(1:2)` counts atoms from the context's first atom. The shim evaluates them per context with
+# mdlib's own evaluate_node, as evaluate_context does.
+SCRIPT_SHIM_ONLY = ("xr = distance(residue(1), 2) in residue(2:4); ya = distance(element('O') and atom(1:2), 3) in residue(2:4); "
+                    "dcx = distance(com(element('H')), 1) in residue(10:20);")
 
 
 def _need():
@@ -130,7 +139,7 @@ def test_md_script_api_through_the_shim_against_the_emulated_library(tmp_path):
     gro = str(tmp_path / "w6.gro")
     subprocess.check_call([TOOL, "water-gro", "6", "1008", gro])
     script = ("r = rdf(element('O'), element('O'), 6.0); d = distance(1,10); rc = rdf(residue(1:20), element('O'), 5.0); v = sdf(residue(1:20), element('O'), 5.0); "
-              "dz = density_z(element('O')); " + SCRIPT_NEW)
+              "dz = density_z(element('O')); " + SCRIPT_NEW + " " + SCRIPT_SHIM_ONLY)
     env = dict(os.environ, LD_LIBRARY_PATH=str(libdir))
     p = subprocess.run([SHIM, "eval", "--sys", gro, "--traj", "synthwater:6:1008:5", "--script", script], capture_output=True, text=True, env=env)
     line = [l for l in p.stdout.splitlines() if l.startswith("{")]
@@ -139,7 +148,7 @@ def test_md_script_api_through_the_shim_against_the_emulated_library(tmp_path):
     assert p.returncode == 0 and res["parity"] is True, res
     assert all(q["out_of_tol"] == 0 and q["frame_mask_equal"] for q in res["properties"])
     exact = {q["name"]: q["max_abs"] for q in res["properties"]}
-    assert all(exact[k] == 0 for k in ("d", "rm", "dp", "c", "ci", "pl", "cw", "dmn", "dc", "v")), exact
+    assert all(exact[k] == 0 for k in ("d", "rm", "dp", "c", "ci", "pl", "cw", "dmn", "dc", "v", "xr", "ya", "dcx", "dctx", "ectx", "car", "dar", "ddr", "dmg", "cxg", "plg")), exact
 
 
 

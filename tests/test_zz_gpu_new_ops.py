@@ -485,14 +485,18 @@ def test_array_of_selections_as_one_position_argument():
         src = load_golden(name); sysm = vb_system(golden_system(src)); F = src["frames"].shape[0]
         props = vb.compile_script(str(g["script"]), sysm)
         assert {p.name: sorted(p.arg_offsets) for p in props} == {"da": [], "db": [], "dc": [], "aa": [0, 1], "ha": [0, 1, 2, 3], "ca": [0], "cb": [0], "dd": [],
-                                                                    "dmg": [], "dmh": [], "dxg": [], "cxg": [], "czg": [], "plg": [], "plh": []}
-        assert [(p.num_structures, p.structure_offsets_b is not None) for p in props[-7:]] == [(4, True), (0, True), (3, False), (5, False), (31, False), (10, False), (181, False)]
+                                                                    "dmg": [], "dmh": [], "dxg": [], "cxg": [], "czg": [], "plg": [], "plh": [],
+                                                                    "dctx": [0, 1], "actx": [0, 1], "ectx": [0, 1], "hctx": [1, 2]}
+        assert [(p.num_structures, p.structure_offsets_b is not None) for p in props[-11:-4]] == [(4, True), (0, True), (3, False), (5, False), (31, False), (10, False), (181, False)]
+        assert [p.num_structures for p in props[-4:]] == [10, 5, 4, 216]   # contexts
         plan = vb.Plan(sysm, props, F, batch_frames=3)
         plan.eval_host_frames(src["frames"], [vb_cell(src["cells"][f], src["cell_flags"][f]) for f in range(F)], 0)
         for key in ("da", "db", "dc", "dd", "ca", "cb"): assert _same(plan.property_data(key).values, g[f"{tag}_{key}__full"]), (tag, key)
         for key in ("dmg", "dmh", "dxg", "cxg", "czg"):   # one centre of mass per selection: distance_min / _max over them, coord_* of them
             assert np.array_equal(plan.property_data(key).values, g[f"{tag}_{key}__full"]), (tag, key)
         for key in ("plg", "plh"): assert _same(plan.property_data(key).values, g[f"{tag}_{key}__full"]), (tag, key)   # the plane through the selections' centres of mass
+        for key in ("dctx", "ectx"): assert _same(plan.property_data(key).values, g[f"{tag}_{key}__full"]), (tag, key)   # selections inside `in` contexts
+        for key in ("actx", "hctx"): np.testing.assert_allclose(plan.property_data(key).values, g[f"{tag}_{key}__full"], rtol=1e-5, atol=1e-6, err_msg=f"{tag} {key}")
         for key in ("aa", "ha"): np.testing.assert_allclose(plan.property_data(key).values, g[f"{tag}_{key}__full"], rtol=1e-5, atol=1e-6, err_msg=f"{tag} {key}")
         plan.close()
     with pytest.raises(vb.MdgpuError):   # offsets that do not cover the list

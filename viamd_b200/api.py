@@ -295,9 +295,17 @@ def density(name, axis, idx):
 
 def in_contexts(name, op, local_idx, context_first_atoms):
     """`name = distance|angle|dihedral(i, j, ...) in <contexts>`: the integer arguments (0-based here) are relative to each context's first atom
-    (remap_index_to_context); one value per context and frame -> [F, n_contexts] (evaluate_context md_script.c:3418)."""
+    (remap_index_to_context); an argument given as a LIST of index arrays (one per context) is a selection: the atoms of (selection AND context),
+    whose centre of mass is the position. One value per context and frame -> [F, n_contexts] (evaluate_context md_script.c:3418)."""
     beg = np.asarray(context_first_atoms, np.int64)
-    return Property(name, op, [(beg + int(a)).astype(np.int32) for a in local_idx], num_structures=len(beg))
+    idx, parts, mask = [], {}, 0
+    for k, a in enumerate(local_idx):
+        if isinstance(a, list):   # a selection argument: per context the atoms of (selection AND context); its position there is their centre of mass
+            assert len(a) == len(beg)
+            off = np.zeros(len(a) + 1, np.uint32); off[1:] = np.cumsum([len(g) for g in a])
+            idx.append(np.concatenate(a).astype(np.int32) if off[-1] else np.zeros(0, np.int32)); parts[k] = off; mask |= 1 << k
+        else: idx.append((beg + int(a)).astype(np.int32))
+    return Property(name, op, idx, num_structures=len(beg), com_args=mask, arg_offsets=parts)
 
 
 def _temporal(name, op, args):

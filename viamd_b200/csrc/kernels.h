@@ -131,6 +131,7 @@ struct TemporalArgs {
     BatchFrames frames; const mdgpu_unitcell_t* cells; int op; int atom[4]; float* out; uint32_t frame0;
     const float* pos; uint32_t com_mask;   // [B][4][3] centres of mass (k_arg_com) for the arguments whose bit is set
     const int32_t* ctx_idx[4]; uint32_t n_ctx;   // `expr in contexts`: per-context atom of each argument (k_temporal_ctx), out is [num_frames][n_ctx]
+    const float4* ctx_pos[4];                    // ... or, for an argument that is a selection, [B][n_ctx] centres of mass of (selection AND context) (k_arg_com_parts); null: the atom
 };
 void launch_temporal_ctx(const TemporalArgs& a, int B, cudaStream_t s);
 void launch_arg_com(const BatchFrames& fr, const mdgpu_unitcell_t* d_cells, const int32_t* d_idx, uint32_t count, const float* d_mass, float* d_out, int arg, cudaStream_t s, DynSel dyn = DynSel{ nullptr, nullptr, 0 });

@@ -517,8 +517,15 @@ mdgpu_plan* mdgpu_plan_create(const mdgpu_system_desc_t* sys, const mdgpu_proper
         case MDGPU_OP_DISTANCE: case MDGPU_OP_ANGLE: case MDGPU_OP_DIHEDRAL: {
             const int need = pr.op == MDGPU_OP_DISTANCE ? 2 : (pr.op == MDGPU_OP_ANGLE ? 3 : 4);
             if (pr.n_struct) {   // `expr in contexts` (evaluate_context md_script.c:3418): idx[k][c] = argument k's atom in context c, one value per context
-                if (d.com_args || d.arg_parts[0] > 1u || d.arg_parts[1] > 1u || d.arg_parts[2] > 1u || d.arg_parts[3] > 1u) return bail(MDGPU_ERR_UNSUPPORTED, "'" + pr.name + "': selection arguments inside a context expression are not lowered");
-                for (int k = 0; k < need; ++k) if (pr.h_idx[k].size() != pr.n_struct) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': one atom per context and argument expected");
+                // an argument that is a selection: idx[k] = the atoms of (selection AND context c) for every context back to back, arg_offsets[k] their
+                // n_contexts + 1 offsets (arg_parts[k] == num_structures); its position in context c is that group's centre of mass
+                // (coordinate_extract_com with ctx->mol_ctx, md_script_functions.inl:1812-1823). Integer arguments: one atom per context.
+                for (int k = 0; k < need; ++k) {
+                    if (d.arg_parts[k]) {
+                        if (d.arg_parts[k] != pr.n_struct) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': one group of atoms per context expected for a selection argument");
+                        const std::string er = take_arg_parts(pr, d, k); if (!er.empty()) return bail(MDGPU_ERR_INVALID_ARG, er);
+                    } else if (pr.h_idx[k].size() != pr.n_struct) return bail(MDGPU_ERR_INVALID_ARG, "'" + pr.name + "': one atom per context and argument expected");
+                }
                 pr.len = pr.n_struct;
                 e = dalloc(&pr.d_temporal, num_frames * pr.len);
                 pr.values.assign(num_frames * pr.len, 0.0f);
@@ -849,7 +856,7 @@ static int ensure_slots(mdgpu_plan* p, const mdgpu_unitcell_t* first_cell, bool 
                 } else if (pr.op >= MDGPU_OP_DENSITY_X && pr.op <= MDGPU_OP_DENSITY_Z) {
                     CUDA_TRY(dalloc(&ps.d_frame_bins64, (size_t)p->B * MDGPU_DIST_BINS));
                 } else if (pr.com_mask) {
-                    CUDA_TRY(dalloc(&ps.d_argpos, (size_t)p->B * 12));
+                    if (!pr.n_struct) CUDA_TRY(dalloc(&ps.d_argpos, (size_t)p->B * 12));
                     for (int k = 0; k < 4; ++k) if (!pr.h_aoff[k].empty()) CUDA_TRY(dalloc(&ps.d_parts[k], (size_t)p->B * (pr.h_aoff[k].size() - 1)));
                 }
             }
@@ -1074,7 +1081,13 @@ static int enqueue_batch(mdgpu_plan* p, Slot& s, const BatchFrames& fr, uint32_t
             TemporalArgs a{};
             a.frames = fr; a.cells = s.d_cells; a.op = (int)pr.op; a.out = pr.d_temporal; a.frame0 = frame0;
             if (pr.n_struct) {
-                for (int k = 0; k < 4; ++k) a.ctx_idx[k] = didx[k];
+                for (int k = 0; k < 4; ++k) {
+                    a.ctx_idx[k] = didx[k]; a.ctx_pos[k] = nullptr;
+                    if (!pr.h_aoff[k].empty()) {   // a selection inside the contexts: one centre of mass per context
+                        launch_arg_com_parts(fr, s.d_cells, didx[k], pr.d_aoff[k], (uint32_t)pr.n_struct, dmass, ps.d_parts[k], s.stream);
+                        a.ctx_pos[k] = ps.d_parts[k];
+                    }
+                }
                 a.n_ctx = (uint32_t)pr.n_struct;
                 launch_temporal_ctx(a, B, s.stream);
                 break;

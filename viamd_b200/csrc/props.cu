@@ -309,6 +309,18 @@ MDG_D float temporal_value(int op, const float P[4][3], const mdgpu_unitcell_t& 
                 }
             }
         }
+        else if (uc.flags & MDGPU_CELL_TRICLINIC) {   // min_image_triclinic with the half diagonal (md_util.c:8360-8423): zone reduction along c, b, a, then the 27 images
+            const float box[3][3] = { { (float)uc.x, 0.f, 0.f }, { (float)uc.xy, (float)uc.y, 0.f }, { (float)uc.xz, (float)uc.yz, (float)uc.z } };
+            const float half3[3] = { box[0][0] * 0.5f, box[1][1] * 0.5f, box[2][2] * 0.5f };
+            for (int k = 0; k < 3; ++k) {
+                for (int i = 2; i >= 0; --i) if (half3[i] > 0.0f) {
+                    int guard = 0;
+                    while (dx[k][i] > half3[i] && guard++ < 64) for (int j = i; j >= 0; --j) dx[k][j] = __fsub_rn(dx[k][j], box[i][j]);
+                    while (dx[k][i] <= -half3[i] && guard++ < 128) for (int j = i; j >= 0; --j) dx[k][j] = __fadd_rn(dx[k][j], box[i][j]);
+                }
+                min_image_triclinic_p(dx[k], box);
+            }
+        }
         const float* d1 = dx[0]; const float* d2 = dx[1]; const float* d3 = dx[2];   // vec3_dihedral_angle core/md_vec_math.h:558-567
         const float v1[3] = { d1[1] * d2[2] - d1[2] * d2[1], d1[2] * d2[0] - d1[0] * d2[2], d1[0] * d2[1] - d1[1] * d2[0] };
         const float v2[3] = { d2[1] * d3[2] - d2[2] * d3[1], d2[2] * d3[0] - d2[0] * d3[2], d2[0] * d3[1] - d2[1] * d3[0] };
@@ -347,6 +359,7 @@ __global__ void k_temporal_ctx(TemporalArgs a, int B) {
     const int nargs = a.op == MDGPU_OP_DISTANCE ? 2 : (a.op == MDGPU_OP_ANGLE ? 3 : 4);
     float P[4][3]; bool defined = true;
     for (int k = 0; k < nargs; ++k) {
+        if (a.ctx_pos[k]) { const float4 q = a.ctx_pos[k][(size_t)f * a.n_ctx + c]; P[k][0] = q.x; P[k][1] = q.y; P[k][2] = q.z; continue; }   // selection AND context: its centre of mass (coordinate_extract_com with ctx->mol_ctx, :1812-1823)
         const int at = a.ctx_idx[k][c];
         if (at < 0) { defined = false; break; }   // backbone angles: the end segments of a chain have no phi / psi and stay 0 (md_util.c:2576, :2592)
         P[k][0] = x[at]; P[k][1] = y[at]; P[k][2] = z[at];

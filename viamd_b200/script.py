@@ -228,16 +228,39 @@ class _Parser:
         coordinate_extract_com :1826-1842). distance() is FLAG_FLATTEN (md_script_functions.inl:680): its arguments, com(...) inside it included,
         are evaluated flattened -> the union."""
         if self.peek()[0] == "num":
-            return int(float(self.expect("num")[1])) - 1   # md_script atom indices are 1-based
+            v = int(float(self.expect("num")[1])) - 1   # md_script atom indices are 1-based
+            self.arg_meta.append(("int", v)); return v
         if self.peek() == ("id", "com"):   # com(x) as an argument contributes the position x itself would (_com :4726 = coordinate_extract_com)
             self.next(); self.expect("ch", "("); a = self.index(flatten); self.expect("ch", ")")
             return a
-        if self._has_within_before_comma(): return self.sel_or_within()
-        return self.selection() if flatten else self.groups_or_selection()
+        if self._has_within_before_comma(): self.arg_meta.append(("other",)); return self.sel_or_within()
+        if self.peek() == ("id", "atom"):   # atom(a:b) standing alone: relative to the context when the expression is evaluated `in` contexts
+            save = self.i; self.next(); self.expect("ch", "("); lo, hi = self._range(self.sys.num_atoms); self.expect("ch", ")")
+            if self.peek() in (("ch", ","), ("ch", ")")): self.arg_meta.append(("atomrange", lo, hi))
+            else: self.arg_meta.append(("other",))
+            self.i = save
+            return self.selection()
+        ctx_relative = self._arg_mentions(("atom", "residue"))   # inside `in` contexts these count from the context's first atom / residue: only the shim
+        a = self.selection() if flatten else self.groups_or_selection()   # (which asks mdlib's own evaluator per context) lowers such arguments
+        self.arg_meta.append(("other",) if (isinstance(a, list) or ctx_relative) else ("sel", a))
+        return a
+
+    def _arg_mentions(self, names) -> bool:
+        """does the argument that starts here (up to its top-level `,` or `)`) call one of `names`"""
+        depth = 0
+        for t in self.t[self.i:]:
+            if t == ("ch", "("): depth += 1
+            elif t == ("ch", ")"):
+                if depth == 0: return False
+                depth -= 1
+            elif t == ("ch", ",") and depth == 0: return False
+            elif t[0] == "id" and t[1] in names: return True
+        return False
 
     def statement(self) -> api.Property:
         ident = self.expect("id")[1]; self.expect("ch", "=")
         proc = self.expect("id")[1]; self.expect("ch", "(")
+        self.arg_meta = []   # how each argument of distance / angle / dihedral was written (index()): decides its meaning inside `in` contexts
         if proc == "rdf":
             wr = None
             if self._has_within_before_comma():   # dynamic reference set: within([min:]max, selection), optionally `and` a static selection
@@ -295,11 +318,20 @@ class _Parser:
         self.expect("ch", ")")
         if self.peek() == ("id", "in"):   # `expr in contexts` (evaluate_context md_script.c:3418): one value per context
             self.next(); begs, ends = self.contexts()
-            if proc not in ("distance", "angle", "dihedral") or p.com_args or any(len(i) != 1 for i in p.idx):
-                raise ScriptError("`in` is lowered for distance / angle / dihedral with integer arguments only")
-            for i in p.idx:   # remap_index_to_context rejects indices outside the context (md_script_functions.inl:1023-1040)
-                if np.any(begs + int(i[0]) >= ends): raise ScriptError(f"supplied index ({int(i[0]) + 1}) is not within the range of a context")
-            p = api.in_contexts(ident, p.op, [int(i[0]) for i in p.idx], begs)
+            if proc not in ("distance", "angle", "dihedral") or any(m[0] == "other" for m in self.arg_meta) or len(self.arg_meta) != len(p.idx):
+                raise ScriptError("`in` is lowered for distance / angle / dihedral with integer or selection arguments")
+            args = []
+            for m in self.arg_meta:
+                if m[0] == "int":   # remap_index_to_context rejects indices outside the context (md_script_functions.inl:1023-1040)
+                    if np.any(begs + m[1] >= ends): raise ScriptError(f"supplied index ({m[1] + 1}) is not within the range of a context")
+                    args.append(m[1])
+                elif m[0] == "atomrange":   # atom(a:b) inside a context is relative to the context's first atom
+                    if np.any(begs + m[2] > ends): raise ScriptError(f"supplied range ({m[1] + 1}:{m[2]}) is not within range of its context")
+                    args.append([np.arange(b + m[1], b + m[2], dtype=np.int32) for b in begs])
+                else:               # a selection: in context c the centre of mass of (selection AND context) (coordinate_extract_com with ctx->mol_ctx, :1812-1823)
+                    sel = np.asarray(m[1], np.int64)
+                    args.append([sel[(sel >= b) & (sel < e)].astype(np.int32) for b, e in zip(begs, ends)])
+            p = api.in_contexts(ident, p.op, args, begs)
         self.expect("ch", ";")
         return p
 
