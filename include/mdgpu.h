@@ -108,7 +108,7 @@ typedef enum mdgpu_op {
                                   * (src/components/shapespace/shapespace.cpp:404-431) and _shape_weights (md_script_functions.inl:6005-6050) */
     MDGPU_OP_COORD_X = 17, MDGPU_OP_COORD_Y = 18, MDGPU_OP_COORD_Z = 19,   /* coord_x/_y/_z(selection): the atoms' coordinates -> temporal [F, n]  :5077-5169 */
     MDGPU_OP_RMSD = 11,      /* rmsd(selection) against the initial frame -> temporal                     :4287-4345 */
-    MDGPU_OP_CONTACT_COUNT = 21, /* contact_count(A[], B, cutoff [, path]) -> temporal [F, |A|]                      :2756-2866 */
+    MDGPU_OP_CONTACT_COUNT = 21, /* contact_count(A[], B, cutoff) -> temporal [F, |A|]; exclusion lists from the caller :2756-2866 */
     MDGPU_OP_BACKBONE_ANGLES = 20, /* (phi, psi) of every backbone segment per frame -> temporal [F, 2 * n_segments]: VIAMD's "Backbone Operations" pass
                                     * (src/viamd.cpp:488-520 -> md_util_backbone_angles_compute md_util.c:2572-2620) */
 } mdgpu_op;

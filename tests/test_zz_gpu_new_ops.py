@@ -535,3 +535,11 @@ def test_contact_count_exclusion_lists_and_errors():
     with pytest.raises(vb.MdgpuError, match="cutoff distance must be positive"):
         vb.Plan(sysm, [vb.contact_count("c", A, Bsel, 0.0, sysm)], F)
     plan.close()
+
+
+@pytest.mark.parametrize("golden,seed", [("water6.npz", "77"), ("tric6.npz", "91")])
+def test_statement_forms_against_the_reference_itself(tmp_path, golden, seed):
+    """The 45-form sweep of tests/test_emulated_library.py with libmdgpu itself on the device: the prebuilt reference harness (oracle/_ref, no access to
+    /root/reference at run time) evaluates the script on the box's CPU, the library evaluates the lowered statements on the GPU."""
+    from test_emulated_library import run_statement_forms
+    run_statement_forms(tmp_path, golden, seed)

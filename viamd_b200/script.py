@@ -288,10 +288,10 @@ class _Parser:
             a = self.sel_or_within() if self._has_within_before_comma() else self.groups_or_selection(); self.expect("ch", ",")   # an array of selections: one centre of mass per selection
             b = self.sel_or_within() if self._has_within_before_comma() else self.groups_or_selection()
             p = {"distance_min": api.distance_min, "distance_max": api.distance_max}[proc](ident, a, b)
-        elif proc == "contact_count":   # contact_count(A[], B, cutoff [, path_length])
-            a = self.groups_or_selection(); self.expect("ch", ","); b = self.selection(); self.expect("ch", ","); c = self.number(); pl = 4
-            if self.peek() == ("ch", ","): self.next(); pl = int(self.number())
-            p = api.contact_count(ident, a if isinstance(a, list) else [a], b, c, self.sys, pl)
+        elif proc == "contact_count":   # contact_count(A[], B, cutoff): the only registered signature (md_script_functions.inl:705); _contact_count's path length stays at its default 4 (:2762)
+            a = self.groups_or_selection(); self.expect("ch", ","); b = self.selection(); self.expect("ch", ","); c = self.number()
+            if self.peek() == ("ch", ","): raise ScriptError("Could not find matching procedure 'contact_count' which takes four arguments")
+            p = api.contact_count(ident, a if isinstance(a, list) else [a], b, c, self.sys, 4)
         elif proc == "count":   # count(within(radius, selection)): the one dynamic selection the device path evaluates
             if not self._has_within_before_comma(): raise ScriptError("count() is lowered for within(radius, selection) expressions only")
             rlo, r, sel, cand = self.dyn_selection()
