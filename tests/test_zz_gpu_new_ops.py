@@ -537,6 +537,28 @@ def test_contact_count_exclusion_lists_and_errors():
     plan.close()
 
 
+def test_array_and_context_forms_with_empty_or_single_atom_groups():
+    """Degenerate groups in the array / context forms: an empty selection inside an array (its centre is (0, 0, 0), md_util_com_compute's count == 0
+    answer, md_util.c:8168), an empty (selection AND context), single-atom selections, 216 parts in one argument — no fault, finite values, and the
+    non-degenerate entries equal the same quantity computed without the degenerate neighbours."""
+    vb = _vb(); g = load_golden("water6.npz"); sysm = vb_system(golden_system(g)); F = 2
+    cells = [vb_cell(g["cells"][f], g["cell_flags"][f]) for f in range(F)]; E = np.zeros(0, np.int32)
+    props = [vb.in_contexts("c_empty", vb.OP_DISTANCE, [[np.array([0], np.int32), E, np.array([6], np.int32)], 1], [0, 3, 6]),
+             vb.in_contexts("c_full", vb.OP_DISTANCE, [[np.array([0], np.int32), np.array([6], np.int32)], 1], [0, 6]),
+             vb.angle("a_emptypart", [np.arange(0, 3), E, np.arange(6, 9)], 10, 20),
+             vb.com("c_single", [np.array([5], np.int32), np.array([7], np.int32)]),
+             vb.distance_min("dm_g", [np.arange(0, 3), E], [np.arange(30, 33), np.arange(60, 63)]),
+             vb.coord("cx_g", 0, [np.arange(0, 3), E, np.arange(3, 4)]), vb.coord("cx_a", 0, [np.arange(0, 3), np.arange(3, 4)]),
+             vb.rdf("rt_g", np.arange(0, 60, 3), [np.arange(3 * k, 3 * k + 3) for k in range(40, 44)] + [E], 6.0),
+             vb.com("c_many", [np.arange(3 * k, 3 * k + 3) for k in range(216)])]
+    plan = vb.Plan(sysm, props, F, keep_frame_results=True); plan.set_initial_frame(*g["frames"][0], cells[0]); plan.eval_host_frames(g["frames"][:F], cells, 0)
+    val = {p.name: np.asarray(plan.property_data(p.name).values).copy() for p in props}
+    assert all(np.all(np.isfinite(v)) for v in val.values())
+    assert np.array_equal(val["c_empty"].reshape(F, 3)[:, [0, 2]], val["c_full"].reshape(F, 2))
+    assert np.array_equal(val["cx_g"].reshape(F, 3)[:, [0, 2]], val["cx_a"].reshape(F, 2)) and np.all(val["cx_g"].reshape(F, 3)[:, 1] == 0)
+    plan.close()
+
+
 @pytest.mark.parametrize("golden,seed", [("water6.npz", "77"), ("tric6.npz", "91")])
 def test_statement_forms_against_the_reference_itself(tmp_path, golden, seed):
     """The 45-form sweep of tests/test_emulated_library.py with libmdgpu itself on the device: the prebuilt reference harness (oracle/_ref, no access to
